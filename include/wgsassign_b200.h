@@ -1,0 +1,157 @@
+/*
+ * wgsassign_b200 - C ABI of the B200-native WGSassign genotype-likelihood hot path.
+ *
+ * This header is the drop-in boundary.  The reference has no FFI of
+ * its own: its native layer is a set of Cython `cpdef`s that its Python drivers call once
+ * per EM iteration / per (individual, population).  That granularity cannot be kept on a
+ * GPU, so each entry point below replaces one reference *driver* (Python function + the
+ * Cython kernels under it) and is what a ctypes binding in the reference's modules would
+ * call.  Citations are file:line in the reference checkout (WGSassign/...).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; every call returns 0 on success, non-zero on
+ *     error, and wgs_last_error() then describes it (no exceptions cross the ABI);
+ *   - all array arguments are HOST pointers, C-contiguous, in the reference's layouts:
+ *       L   float32 [M, 2N]  L[s,2i]=P(G=0), L[s,2i+1]=P(G=1)      (reader_cy.pyx:16-77)
+ *       A   float32 [M, K]   columns in np.unique(pop names) order  (WGSassign.py:213-243)
+ *       AD  int32   [M, 2N]  (ref/major, alt/minor) read counts      (WGSassign.py:320)
+ *     the pointer is borrowed for the duration of the call only; pinned host memory
+ *     (wgs_host_alloc) is copied at full PCIe rate, pageable memory works too;
+ *   - outputs are caller-allocated; calls are synchronous (return when outputs are valid);
+ *   - there is NO CPU fallback: without a CUDA device wgs_create fails.
+ *
+ * Site sharding (one process per GPU): each rank creates a context on its device, uploads
+ * its contiguous site range, and calls wgs_set_shard() with the global site count and an
+ * all-reduce callback; per-site outputs are then local slices and the small
+ * per-individual/per-population sums are returned as float64 partials ("_partial") that
+ * the caller combines in fixed rank order.
+ */
+#ifndef WGSASSIGN_B200_H
+#define WGSASSIGN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wgs_ctx wgs_ctx;
+
+#define WGS_ABI_VERSION 1
+
+/* dtype codes for the all-reduce callback */
+#define WGS_F64 0
+#define WGS_I64 1
+
+/* Sum `n` elements of `buf` (dtype WGS_F64 / WGS_I64) across all ranks, in place, host memory. */
+typedef void (*wgs_allreduce_fn)(void *buf, int64_t n, int32_t dtype, void *user);
+
+int32_t     wgs_abi_version(void);
+int32_t     wgs_device_count(void);
+const char *wgs_last_error(const wgs_ctx *ctx); /* ctx may be NULL: last create() error */
+
+int32_t wgs_create(int32_t device, wgs_ctx **out);
+void    wgs_destroy(wgs_ctx *ctx);
+
+/* Pinned host buffers for full-rate H2D (optional). */
+void *wgs_host_alloc(int64_t bytes);
+void  wgs_host_free(void *p);
+
+/* ---- data residency --------------------------------------------------------------------- */
+
+/* Population structure of the N individuals (Beagle column order): pop_of_ind[i] in [0,K) is
+ * the index of individual i's population in np.unique order (WGSassign.py:211-213,
+ * glassy.py:63-67).  Must be called before wgs_upload_gl for the reference-panel ops
+ * (ref_af / loo / fisher / reference z-score); not needed for pop_like.  K may be 0 to clear. */
+int32_t wgs_set_pops(wgs_ctx *ctx, const int32_t *pop_of_ind, int32_t N, int32_t K);
+
+/* Repack L [M,2N] into the device layout (population-sorted (g0,g1) pairs, 32-byte aligned
+ * population slabs; g2 is never stored, it is recomputed as 1-g0-g1 like the reference
+ * does).  which=0: the GL matrix; which=1: the optional down-sampled matrix that
+ * glassy.loo scores against (glassy.py:96). */
+int32_t wgs_upload_gl(wgs_ctx *ctx, const float *L, int64_t M, int32_t N, int32_t which);
+
+/* Allele depths [M,2N] int32, packed on device to 2 x uint8 per individual
+ * (counts above 254 are rejected with an error rather than clamped). */
+int32_t wgs_upload_ad(wgs_ctx *ctx, const int32_t *AD, int64_t M, int32_t N);
+
+/* Multi-GPU site sharding: global number of sites, global index of this shard's first site,
+ * and the cross-rank sum used for the EM stop rule and the z-score class tallies. */
+int32_t wgs_set_shard(wgs_ctx *ctx, int64_t M_total, int64_t site_offset,
+                      wgs_allreduce_fn fn, void *user);
+
+/* Device-side seeded synthetic data of the SURVEY 8d model (benchmarks): fills the resident
+ * GL (and AD when with_ad) for M sites x N individuals; requires wgs_set_pops first. */
+int32_t wgs_synth(wgs_ctx *ctx, int64_t M, int32_t N, uint64_t seed, float depth, int32_t with_ad);
+/* Copy a slice of the resident data back in the reference layouts (any pointer may be NULL). */
+int32_t wgs_download(wgs_ctx *ctx, int64_t site0, int64_t nsites, float *L_out, int32_t *AD_out);
+
+/* ---- operators -------------------------------------------------------------------------- */
+
+/* emMAF.emMAF(L_pop, iter, tole, t) (emMAF.py:15-27 over emMAF_cy.pyx:10-33): EM allele
+ * frequency of ONE group given its own [M,2n] matrix; f_out [M]; *iters_out = iteration it
+ * converged at (1-based) or 0 if it did not within `iter`.  No clipping. Self-contained. */
+int32_t wgs_emMAF(wgs_ctx *ctx, const float *L_pop, int64_t M, int32_t n, int32_t iter, double tole,
+                  float *f_out, int32_t *iters_out);
+
+/* Per-population EM + clipping (WGSassign.py:225-242): af_out [M,K], iters_out [K]. */
+int32_t wgs_ref_af(wgs_ctx *ctx, int32_t iter, double tole, float *af_out, int32_t *iters_out);
+
+/* glassy.assignLL (glassy.py:18-44 over glassy_cy.pyx:12-21): float64 sums over this
+ * context's sites, out [N,K]; the caller rounds to float32 after combining shards. */
+int32_t wgs_pop_like_partial(wgs_ctx *ctx, const float *af, int32_t K, double *out);
+
+/* glassy.loo (glassy.py:47-112): leave-one-out EM for every individual, then the
+ * log-likelihood of each individual under every population with the reference's
+ * in-place column overwrite order (glassy.py:89).  af_inout [M,K] is read (full-data AF)
+ * and left as the reference leaves it.  ll [N,K] float64; ll_parts [N*parts,K] float64
+ * (may be NULL when parts==1); iters_out [N].  use_ds: score against the which=1 matrix. */
+int32_t wgs_loo_partial(wgs_ctx *ctx, float *af_inout, int32_t iter, double tole, int32_t use_ds,
+                        int32_t parts, double *ll, double *ll_parts, int32_t *iters_out);
+
+/* fisher.fisher_obs + fisher.fisher_obs_ind in one pass (fisher.py:11-59 over
+ * fisher_cy.pyx:12-65): f_obs, ne_obs [M,K] float32 (local sites); ne_ind_sum [N] float64 =
+ * sum over local sites of the per-individual n-tilde (caller divides by the global M). */
+int32_t wgs_fisher_partial(wgs_ctx *ctx, const float *af, float *f_obs, float *ne_obs,
+                           double *ne_ind_sum);
+
+/* z-score (WGSassign.py:311-446 over zscore.py:11-120 and zscore_cy.pyx:10-56). */
+typedef struct {
+    float   z;         /* (w_obs - z_mu) / sqrt(z_var), float32 like the reference */
+    float   w_obs;     /* sum of observed per-site log-likelihoods */
+    float   z_mu;      /* sum of expected per-site log-likelihoods */
+    float   z_var;     /* sum of per-site variances */
+    int64_t loci_kept; /* len(L_keep) - bit-exact */
+    int32_t n_classes; /* rows of AD_array - bit-exact */
+    int32_t em_iters;  /* reference mode: LOO EM iterations on the kept sites */
+} wgs_zrow;
+
+/* mode 0: --get_assignment_z_score (af [M,K] + pop_of_ind give each individual's column);
+ * mode 1: --get_reference_z_score (LOO EM on the kept sites, af ignored).
+ * Individuals ind_start <= i < ind_end; out[ind_end-ind_start]. */
+int32_t wgs_zscore(wgs_ctx *ctx, int32_t mode, const float *af, int32_t K, int32_t n_threshold,
+                   int32_t single_read, int32_t ind_start, int32_t ind_end, int32_t iter,
+                   double tole, wgs_zrow *out);
+
+/* Per-individual allele-depth class table of the last wgs_zscore call, for tally parity:
+ * rows of (ref, alt, depth, n_loci) in first-occurrence order restricted to kept classes. */
+int32_t wgs_zscore_classes(wgs_ctx *ctx, int32_t ind, int32_t max_rows, int32_t *rows_out,
+                           int32_t *n_rows);
+
+/* ---- instrumentation --------------------------------------------------------------------- */
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+int64_t wgs_launch_count(const wgs_ctx *ctx);
+/* Device time (ms, CUDA events on the context's stream) and launch count of the named kernel
+ * family accumulated since wgs_timing_reset: "pop_like", "em_pop", "loo_em", "loo_like",
+ * "fisher", "repack", "ztally", "zkeep", "zmoments". */
+int32_t wgs_timing_reset(wgs_ctx *ctx, int32_t enable);
+int32_t wgs_timing_get(wgs_ctx *ctx, const char *name, double *ms, int64_t *launches);
+/* Algorithmic work of the same kernel family since wgs_timing_reset: bytes that must cross
+ * HBM (inputs read once + outputs written once per launch) and work units (likelihood or
+ * posterior evaluations); DESIGN.md states the per-unit figures. */
+int32_t wgs_timing_work(wgs_ctx *ctx, const char *name, double *bytes, double *units);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WGSASSIGN_B200_H */

@@ -1,0 +1,232 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI via the
+drop-in entry points, against the golden fixtures of the unmodified reference and against
+the CPU oracle on seeded synthetic inputs.
+
+Tolerances are BASELINE.json's: assignment argmax / LOO assignments / EM iteration counts
+bit-exact; allele frequencies within 1e-5 absolute; log-likelihoods within 1e-6 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import parse_tsv
+
+pytestmark = pytest.mark.gpu
+
+AF_ATOL = 1e-5
+LL_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def wgs():
+    import wgsassign_b200._lib as _lib
+    if _lib.lib().wgs_device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box")
+    from wgsassign_b200 import emMAF, fisher, glassy, session
+    session.reset()
+
+    class NS:
+        pass
+    ns = NS()
+    ns.lib, ns.emMAF, ns.fisher, ns.glassy, ns.session = _lib, emMAF, fisher, glassy, session
+    yield ns
+    session.reset()
+
+
+def rel_err(a, b):
+    return np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)) / np.maximum(np.abs(b.astype(np.float64)), 1e-30))
+
+
+def test_repack_roundtrip(wgs):
+    from wgsassign_b200 import synth
+    d = synth.synth(301, 23, 4, seed=3, interleave=True)
+    L, AD = d["L"], d["AD"]
+    pop_of, pops = wgs.session.pops_from_ids(d["IDs"])
+    ctx = wgs.lib.Context(0)
+    ctx.set_pops(pop_of, len(pops))
+    ctx.upload_gl(L)
+    ctx.upload_ad(AD)
+    L2, AD2 = ctx.download(0, 301, want_ad=True)
+    assert np.array_equal(L, L2) and np.array_equal(AD, AD2)
+    L3 = ctx.download(100, 50)
+    assert np.array_equal(L[100:150], L3)
+    ctx.close()
+
+
+def test_config2_pop_like_bundled(wgs, bundled):
+    ll = wgs.glassy.assignLL(bundled["L_nonbreeding"], bundled["c1_pop_af"], 1)
+    gold = bundled["c2_pop_like"]
+    assert ll.dtype == np.float32 and ll.shape == (34, 5)
+    assert rel_err(ll, gold) < LL_RTOL
+    assert "".join(str(int(x)) for x in np.argmax(ll, 1)) == "1120222122011010110000333013331333"
+
+
+def test_config1_reference_af_bundled(wgs, bundled, capsys):
+    L, IDs = bundled["L_breeding"], bundled["IDs_breeding"]
+    pop_of, pops = wgs.session.pops_from_ids(IDs)
+    ctx = wgs.session.context(L, pop_of, len(pops))
+    af, its = ctx.ref_af(200, 1e-4)
+    assert list(its) == list(bundled["c1_em_iters_ref"])
+    assert np.max(np.abs(af - bundled["c1_pop_af"])) < AF_ATOL
+    assert af.min() == np.float32(1 / 48) and af.max() == bundled["c1_pop_af"].max()
+    # the emMAF drop-in on one population's column copy (emMAF.py:15)
+    cols = np.flatnonzero(np.repeat(IDs[:, 1] == pops[0], 2))
+    f = wgs.emMAF.emMAF(np.ascontiguousarray(L[:, cols]), 200, 1e-4, 1)
+    assert "EM (MAF) converged at iteration: 17" in capsys.readouterr().out
+    n0 = int(np.sum(IDs[:, 1] == pops[0]))
+    clipped = np.clip(f, np.float32(1 / (2 * (n0 + 1))), np.float32(1 - 1 / (2 * (n0 + 1))))
+    assert np.max(np.abs(clipped - bundled["c1_pop_af"][:, 0])) < AF_ATOL
+
+
+def test_config1_loo_bundled(wgs, bundled):
+    L, IDs = bundled["L_breeding"], bundled["IDs_breeding"]
+    af = bundled["c1_pop_af"].copy()
+    ll, parts = wgs.glassy.loo(L, af, IDs, 1, 200, 1e-4)
+    hdr, rows = parse_tsv(str(bundled["c1_loo_tsv"]))
+    gold = np.array([[float(x) for x in r[2:]] for r in rows])
+    assert rel_err(ll, gold) < 2e-6          # the golden TSV itself carries only 6 decimals
+    assert np.array_equal(np.argmax(ll, 1), np.argmax(gold, 1))
+    assert "".join(str(int(x)) for x in np.argmax(ll, 1)) == \
+        "2222222422333333333333333311111111113333333444401010010100000111111111144444444422222"
+    assert np.array_equal(parts, ll)
+
+
+def test_config1_loo_matches_oracle_exact_quantities(wgs, bundled, oracle_mod):
+    """LOO against the oracle directly: iteration counts, full-precision likelihoods and
+    the mutated AF matrix the reference leaves behind (glassy.py:89)."""
+    L, IDs = bundled["L_breeding"], bundled["IDs_breeding"]
+    af_o = bundled["c1_pop_af"].copy()
+    ll_o, _, its_o = oracle_mod.loo(L, af_o, IDs, 1, 200, 1e-4)
+    pop_of, pops = wgs.session.pops_from_ids(IDs)
+    ctx = wgs.session.context(L, pop_of, len(pops))
+    af_g = bundled["c1_pop_af"].copy()
+    ll_g, _, its_g = ctx.loo_partial(af_g, 200, 1e-4)
+    assert list(its_g) == list(its_o) == list(bundled["c1_em_iters_loo"])
+    assert rel_err(ll_g, ll_o) < LL_RTOL
+    assert np.max(np.abs(af_g - af_o)) < AF_ATOL
+
+
+def test_config1_downsampled_partitions(wgs, bundled):
+    L, IDs = bundled["L_breeding"], bundled["IDs_breeding"]
+    common = np.isin(bundled["sites_breeding"], bundled["sites_breeding_ds"])
+    Lf = np.ascontiguousarray(L[common])
+    af = bundled["c1ds_pop_af"].copy()
+    ll, parts = wgs.glassy.loo(Lf, af, IDs, 1, 200, 1e-4, downsampled_L=bundled["L_breeding_ds"], num_partitions=3)
+    _, rows = parse_tsv(str(bundled["c1ds_loo_tsv"]))
+    gold = np.array([[float(x) for x in r[2:]] for r in rows])
+    assert rel_err(ll, gold) < 2e-6
+    assert np.array_equal(np.argmax(ll, 1), np.argmax(gold, 1))
+    _, prow = parse_tsv(str(bundled["c1ds_loo_parts_tsv"]))
+    pgold = np.array([[float(x) for x in r[3:]] for r in prow])
+    assert parts.shape == pgold.shape == (85 * 3, 5)
+    assert rel_err(parts, pgold) < 5e-6
+    # size-independent property: the modulo partitions tile the sites exactly once
+    assert rel_err(parts.reshape(85, 3, 5).astype(np.float64).sum(1), ll) < 1e-6
+
+
+def test_config1_fisher_bundled(wgs, bundled):
+    L, IDs, af = bundled["L_breeding"], bundled["IDs_breeding"], bundled["c1_pop_af"]
+    f_obs, ne_obs = wgs.fisher.fisher_obs(L, af, IDs, 1)
+    ne_ind = wgs.fisher.fisher_obs_ind(L, af, IDs, 1)
+    gf, gn = bundled["c1_fisher_obs"], bundled["c1_ne_obs"]
+    scale_f, scale_n = np.abs(gf).max(0), np.abs(gn).max(0)
+    assert np.max(np.abs(f_obs - gf) / (np.abs(gf) + 1e-3 * scale_f)) < 1e-4
+    assert np.max(np.abs(ne_obs - gn) / (np.abs(gn) + 1e-3 * scale_n)) < 1e-4
+    assert rel_err(ne_obs.mean(0), gn.mean(0)) < 1e-5
+    gold_ind = np.array([float(x) for x in str(bundled["c1_ne_ind_txt"]).split()])
+    assert rel_err(ne_ind, gold_ind) < 1e-5
+
+
+@pytest.mark.parametrize("m,n,k,interleave,seed", [
+    (1000, 37, 3, True, 11),        # ragged: N not a multiple of 4/32, interleaved populations
+    (2500, 130, 20, False, 12),     # K = 20 tile, several column groups
+    (777, 9, 2, True, 13),          # tiny populations
+    (64, 70, 7, False, 14),         # fewer sites than one tile
+])
+def test_synthetic_vs_oracle(wgs, oracle_mod, m, n, k, interleave, seed):
+    from wgsassign_b200 import synth
+    d = synth.synth(m, n, k, seed=seed, interleave=interleave, with_ad=False)
+    L, IDs = d["L"], d["IDs"]
+    af_o, pops, its_o = oracle_mod.reference_af(L, IDs, 200, 1e-4, 2)
+    pop_of, pops2 = wgs.session.pops_from_ids(IDs)
+    ctx = wgs.session.context(L, pop_of, len(pops2))
+    af_g, its_g = ctx.ref_af(200, 1e-4)
+    assert list(its_g) == list(its_o)
+    assert np.max(np.abs(af_g - af_o)) < AF_ATOL
+    # pop_like on the oracle's AF
+    ll_o = oracle_mod.assignLL(L, af_o, 2)
+    ll_g = wgs.glassy.assignLL(L, af_o, 1)
+    assert rel_err(ll_g, ll_o) < LL_RTOL
+    assert np.array_equal(np.argmax(ll_g, 1), np.argmax(ll_o, 1))
+    # fisher
+    f_o, ne_o = oracle_mod.fisher_obs(L, af_o, IDs, 2)
+    f_g, ne_g = wgs.fisher.fisher_obs(L, af_o, IDs, 1)
+    assert np.max(np.abs(f_g - f_o) / (np.abs(f_o) + 1e-3 * np.abs(f_o).max(0))) < 1e-4
+    assert rel_err(wgs.fisher.fisher_obs_ind(L, af_o, IDs, 1), oracle_mod.fisher_obs_ind(L, af_o, IDs, 2)) < 1e-5
+    # LOO
+    if n <= 40:
+        a1, a2 = af_o.copy(), af_o.copy()
+        llo, _, itso = oracle_mod.loo(L, a1, IDs, 2, 200, 1e-4)
+        llg, _, itsg = ctx.loo_partial(a2, 200, 1e-4)
+        assert list(itsg) == list(itso)
+        assert rel_err(llg, llo) < LL_RTOL
+        assert np.array_equal(np.argmax(llg, 1), np.argmax(llo, 1))
+        assert np.max(np.abs(a1 - a2)) < AF_ATOL
+
+
+def test_edge_cases(wgs, oracle_mod):
+    """Boundary allele frequencies (log 0 = -inf like the reference), missing data rows,
+    a single-member population (0/0 = NaN in the reference's LOO) and an empty site set."""
+    from wgsassign_b200 import synth
+    d = synth.synth(200, 10, 2, seed=21, with_ad=False)
+    L, IDs = d["L"], d["IDs"]
+    A = np.full((200, 2), 0.3, np.float32)
+    A[5, 0] = 0.0
+    A[9, 1] = 1.0
+    L2 = L.copy()
+    L2[5, 0:2] = (0.0, 0.0)       # individual 0 is hom-alt at a site where pop 0 has a = 0
+    L2[:, 6:8] = 0.333333         # individual 3 entirely missing
+    ll_o = oracle_mod.assignLL(L2, A, 1)
+    ll_g = wgs.glassy.assignLL(L2, A, 1)
+    assert np.isneginf(ll_o[0, 0]) and np.isneginf(ll_g[0, 0])
+    fin = np.isfinite(ll_o)
+    assert np.array_equal(fin, np.isfinite(ll_g))
+    assert rel_err(ll_g[fin], ll_o[fin]) < LL_RTOL
+    # single-member population
+    IDs1 = IDs.copy()
+    IDs1[:, 1] = "a"
+    IDs1[9, 1] = "b"
+    af_o, _, _ = oracle_mod.reference_af(L, IDs1, 200, 1e-4, 1)
+    a1, a2 = af_o.copy(), af_o.copy()
+    llo, _, itso = oracle_mod.loo(L, a1, IDs1, 1, 20, 1e-4)
+    pop_of, pops = wgs.session.pops_from_ids(IDs1)
+    ctx = wgs.session.context(L, pop_of, len(pops))
+    llg, _, itsg = ctx.loo_partial(a2, 20, 1e-4)
+    assert list(itsg) == list(itso)
+    assert np.array_equal(np.isnan(llo), np.isnan(llg))
+    ok = ~np.isnan(llo)
+    assert rel_err(llg[ok], llo[ok]) < LL_RTOL
+
+
+def test_wrong_dtype_rejected(wgs):
+    with pytest.raises(ValueError):
+        wgs.glassy.assignLL(np.zeros((4, 4), np.float64), np.zeros((4, 1), np.float32), 1)
+    with pytest.raises(ValueError):
+        wgs.glassy.assignLL(np.zeros((8, 4), np.float32)[::2], np.zeros((4, 1), np.float32), 1)
+
+
+def test_determinism_and_partition_property_large(wgs):
+    """Size-independent properties on a device-generated matrix larger than L2:
+    bitwise run-to-run determinism, and modulo partitions summing to the whole."""
+    ctx = wgs.lib.Context(0)
+    n, k, m = 500, 10, 200_000
+    pop_of = ((np.arange(n) * k) // n).astype(np.int32)
+    ctx.set_pops(pop_of, k)
+    ctx.synth(m, n, seed=7)
+    af, its = ctx.ref_af(200, 1e-4)
+    assert af.min() >= np.float32(1 / 102) and af.max() <= np.float32(1 - 1 / 102)
+    ll1 = ctx.pop_like_partial(af)
+    ll2 = ctx.pop_like_partial(af)
+    assert np.array_equal(ll1, ll2)
+    # individuals are most likely under their own population on depth-consistent data
+    assert np.mean(np.argmax(ll1, 1) == pop_of) > 0.99
+    ctx.close()

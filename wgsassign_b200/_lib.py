@@ -1,0 +1,287 @@
+"""ctypes binding of ``libwgsassign_b200.so`` (C ABI in ``include/wgsassign_b200.h``).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There
+is no CPU fallback: if the library is missing or no CUDA device is present every operator
+raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libwgsassign_b200.so")
+SOURCES = [os.path.join(_PKG, "csrc", "wgs_api.cu")]
+HEADERS = [os.path.join(_PKG, "csrc", "wgs_kernels.cuh"), os.path.join(_PKG, "csrc", "wgs_zscore.cuh"),
+           os.path.join(_ROOT, "include", "wgsassign_b200.h")]
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p)
+WGS_F64, WGS_I64 = 0, 1
+
+
+class ZRow(ctypes.Structure):
+    _fields_ = [("z", ctypes.c_float), ("w_obs", ctypes.c_float), ("z_mu", ctypes.c_float),
+                ("z_var", ctypes.c_float), ("loci_kept", ctypes.c_int64), ("n_classes", ctypes.c_int32),
+                ("em_iters", ctypes.c_int32)]
+
+
+# every symbol include/wgsassign_b200.h declares: (restype, argtypes)
+_vp, _i32, _i64, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+SYMBOLS = {
+    "wgs_abi_version": (_i32, []),
+    "wgs_device_count": (_i32, []),
+    "wgs_last_error": (ctypes.c_char_p, [_vp]),
+    "wgs_create": (_i32, [_i32, ctypes.POINTER(_vp)]),
+    "wgs_destroy": (None, [_vp]),
+    "wgs_host_alloc": (_vp, [_i64]),
+    "wgs_host_free": (None, [_vp]),
+    "wgs_set_pops": (_i32, [_vp, _vp, _i32, _i32]),
+    "wgs_upload_gl": (_i32, [_vp, _vp, _i64, _i32, _i32]),
+    "wgs_upload_ad": (_i32, [_vp, _vp, _i64, _i32]),
+    "wgs_set_shard": (_i32, [_vp, _i64, _i64, ALLREDUCE_FN, _vp]),
+    "wgs_synth": (_i32, [_vp, _i64, _i32, ctypes.c_uint64, ctypes.c_float, _i32]),
+    "wgs_download": (_i32, [_vp, _i64, _i64, _vp, _vp]),
+    "wgs_emMAF": (_i32, [_vp, _vp, _i64, _i32, _i32, _f64, _vp, _vp]),
+    "wgs_ref_af": (_i32, [_vp, _i32, _f64, _vp, _vp]),
+    "wgs_pop_like_partial": (_i32, [_vp, _vp, _i32, _vp]),
+    "wgs_loo_partial": (_i32, [_vp, _vp, _i32, _f64, _i32, _i32, _vp, _vp, _vp]),
+    "wgs_fisher_partial": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "wgs_zscore": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _vp]),
+    "wgs_zscore_classes": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "wgs_launch_count": (_i64, [_vp]),
+    "wgs_timing_reset": (_i32, [_vp, _i32]),
+    "wgs_timing_get": (_i32, [_vp, ctypes.c_char_p, _vp, _vp]),
+    "wgs_timing_work": (_i32, [_vp, ctypes.c_char_p, _vp, _vp]),
+}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--shared", "-Xcompiler", "-fPIC"]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS if os.path.exists(p))
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library for sm_100a in-tree (works without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    subprocess.check_call(cmd, cwd=_ROOT)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library with typed signatures.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "wgsassign_b200: %s is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.wgs_abi_version() != 1:
+            raise RuntimeError("wgsassign_b200: ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+class WgsError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+
+
+def _as(a, dtype, ndim, what):
+    """The reference's typed memoryviews raise ValueError on a wrong dtype/layout."""
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or a.ndim != ndim or not a.flags.c_contiguous:
+        raise ValueError("%s: expected a C-contiguous %s array with %d dimension(s)" % (what, np.dtype(dtype).name, ndim))
+    return a
+
+
+class Context:
+    """One GPU's resident state: the repacked GL matrix (+ optional down-sampled matrix and
+    allele depths) and the operators over it."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p(0)
+        self._cb = None
+        L = lib()
+        if L.wgs_create(int(device), ctypes.byref(self._h)) != 0:
+            raise WgsError(L.wgs_last_error(None).decode())
+        self.device = device
+        self.M = 0
+        self.N = 0
+        self.K = 0
+
+    def close(self):
+        if self._h:
+            lib().wgs_destroy(self._h)
+            self._h = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise WgsError(lib().wgs_last_error(self._h).decode())
+
+    # ---- residency ----
+    def set_pops(self, pop_of_ind, K):
+        p = np.ascontiguousarray(pop_of_ind, dtype=np.int32)
+        self._ck(lib().wgs_set_pops(self._h, _ptr(p), p.shape[0], int(K)))
+        self.N, self.K = p.shape[0], int(K)
+
+    def upload_gl(self, L, which=0):
+        _as(L, np.float32, 2, "L")
+        if L.shape[1] % 2:
+            raise ValueError("L must have 2 columns per individual")
+        self._ck(lib().wgs_upload_gl(self._h, _ptr(L), L.shape[0], L.shape[1] // 2, int(which)))
+        if which == 0:
+            self.M, self.N = L.shape[0], L.shape[1] // 2
+
+    def upload_ad(self, AD):
+        _as(AD, np.int32, 2, "AD")
+        self._ck(lib().wgs_upload_ad(self._h, _ptr(AD), AD.shape[0], AD.shape[1] // 2))
+
+    def set_shard(self, M_total, site_offset, allreduce=None):
+        """allreduce(buf: np.ndarray) must sum `buf` across ranks in place."""
+        if allreduce is None:
+            self._cb = ctypes.cast(None, ALLREDUCE_FN)
+        else:
+            def _tramp(buf, n, dtype, user, _f=allreduce):
+                ct = ctypes.c_double if dtype == WGS_F64 else ctypes.c_int64
+                arr = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ct)), shape=(n,))
+                _f(arr)
+            self._cb = ALLREDUCE_FN(_tramp)
+        self._ck(lib().wgs_set_shard(self._h, int(M_total), int(site_offset), self._cb, None))
+
+    def synth(self, M, N, seed=0, depth=2.0, with_ad=False):
+        self._ck(lib().wgs_synth(self._h, int(M), int(N), int(seed), float(depth), int(with_ad)))
+        self.M, self.N = int(M), int(N)
+
+    def download(self, site0, nsites, want_ad=False):
+        L = np.empty((nsites, 2 * self.N), np.float32)
+        AD = np.empty((nsites, 2 * self.N), np.int32) if want_ad else None
+        self._ck(lib().wgs_download(self._h, int(site0), int(nsites), _ptr(L), _ptr(AD)))
+        return (L, AD) if want_ad else L
+
+    # ---- operators ----
+    def emMAF(self, L_pop, iters, tole):
+        _as(L_pop, np.float32, 2, "L")
+        f = np.empty(L_pop.shape[0], np.float32)
+        it = ctypes.c_int32(0)
+        self._ck(lib().wgs_emMAF(self._h, _ptr(L_pop), L_pop.shape[0], L_pop.shape[1] // 2, int(iters), float(tole),
+                                 _ptr(f), ctypes.byref(it)))
+        return f, it.value
+
+    def ref_af(self, iters, tole):
+        af = np.empty((self.M, self.K), np.float32)
+        its = np.zeros(self.K, np.int32)
+        self._ck(lib().wgs_ref_af(self._h, int(iters), float(tole), _ptr(af), _ptr(its)))
+        return af, its
+
+    def pop_like_partial(self, af):
+        _as(af, np.float32, 2, "af")
+        if af.shape[0] != self.M:
+            raise ValueError("af has %d rows, the GL matrix %d sites" % (af.shape[0], self.M))
+        out = np.empty((self.N, af.shape[1]), np.float64)
+        self._ck(lib().wgs_pop_like_partial(self._h, _ptr(af), af.shape[1], _ptr(out)))
+        return out
+
+    def loo_partial(self, af, iters, tole, use_ds=False, parts=1):
+        _as(af, np.float32, 2, "af")
+        if af.shape != (self.M, self.K):
+            raise ValueError("af must be [M,K] = %s" % ((self.M, self.K),))
+        ll = np.empty((self.N, self.K), np.float64)
+        llp = np.empty((self.N * parts, self.K), np.float64)
+        its = np.zeros(self.N, np.int32)
+        self._ck(lib().wgs_loo_partial(self._h, _ptr(af), int(iters), float(tole), int(bool(use_ds)), int(parts),
+                                       _ptr(ll), _ptr(llp), _ptr(its)))
+        return ll, llp, its
+
+    def fisher_partial(self, af):
+        _as(af, np.float32, 2, "af")
+        if af.shape != (self.M, self.K):
+            raise ValueError("af must be [M,K] = %s" % ((self.M, self.K),))
+        f_obs = np.empty((self.M, self.K), np.float32)
+        ne = np.empty((self.M, self.K), np.float32)
+        ind = np.empty(self.N, np.float64)
+        self._ck(lib().wgs_fisher_partial(self._h, _ptr(af), _ptr(f_obs), _ptr(ne), _ptr(ind)))
+        return f_obs, ne, ind
+
+    def zscore(self, mode, af, n_threshold, single_read, ind_start, ind_end, iters=200, tole=1e-4):
+        n = ind_end - ind_start
+        rows = (ZRow * max(n, 1))()
+        K = 0 if af is None else af.shape[1]
+        if af is not None:
+            _as(af, np.float32, 2, "af")
+        self._ck(lib().wgs_zscore(self._h, int(mode), _ptr(af), K, int(n_threshold), int(bool(single_read)),
+                                  int(ind_start), int(ind_end), int(iters), float(tole), ctypes.byref(rows)))
+        return [rows[i] for i in range(n)]
+
+    def zscore_classes(self, ind, max_rows=4096):
+        buf = np.zeros((max_rows, 4), np.int32)
+        n = ctypes.c_int32(0)
+        self._ck(lib().wgs_zscore_classes(self._h, int(ind), max_rows, _ptr(buf), ctypes.byref(n)))
+        return buf[:n.value].copy()
+
+    # ---- instrumentation ----
+    def launch_count(self):
+        return int(lib().wgs_launch_count(self._h))
+
+    def timing_reset(self, enable=True):
+        self._ck(lib().wgs_timing_reset(self._h, int(enable)))
+
+    def timing_get(self, name):
+        ms = ctypes.c_double(0)
+        n = ctypes.c_int64(0)
+        self._ck(lib().wgs_timing_get(self._h, name.encode(), ctypes.byref(ms), ctypes.byref(n)))
+        b = ctypes.c_double(0)
+        u = ctypes.c_double(0)
+        self._ck(lib().wgs_timing_work(self._h, name.encode(), ctypes.byref(b), ctypes.byref(u)))
+        return dict(ms=ms.value, launches=n.value, bytes=b.value, units=u.value)
+
+
+def pinned_empty(shape, dtype):
+    """A numpy array in pinned host memory (full-rate H2D).  Freed when garbage-collected."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = lib().wgs_host_alloc(max(nbytes, 1))
+    if not p:
+        raise WgsError("cudaHostAlloc failed")
+    buf = (ctypes.c_char * nbytes).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().wgs_host_free(self.ptr)
+            except Exception:
+                pass
+    _PINNED[id(buf)] = (_Owner(p), buf)
+    return arr
+
+
+_PINNED = {}

@@ -1,0 +1,919 @@
+// wgsassign_b200 - C ABI (include/wgsassign_b200.h) over the sm_100a kernels.
+// Host-side orchestration only: residency, launch configuration, the EM stop-rule loop and
+// fixed-order reductions.  There is no CPU implementation of any operator in this file.
+#include "../../include/wgsassign_b200.h"
+#include "wgs_kernels.cuh"
+#include "wgs_zscore.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace wgs;
+
+namespace {
+std::string g_create_error;
+constexpr int kNumSM_fallback = 148;
+
+struct TimedLaunch { int name_id; cudaEvent_t a, b; };
+struct FamilyStat { double ms = 0, bytes = 0, units = 0; long launches = 0; };
+
+}  // namespace
+
+struct wgs_ctx {
+    int device = 0;
+    int num_sm = kNumSM_fallback;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    std::string err;
+
+    // structure
+    int N = 0, K = 0, ldg = 0;
+    bool pops_set = false;
+    std::vector<int> pop_of_ind, col_of_ind, ind_of_col, pop_of_col;
+    std::vector<PopDesc> pops;
+    int *d_ind_of_col = nullptr, *d_col_of_ind = nullptr, *d_pop_of_col = nullptr;
+    PopDesc* d_pops = nullptr;
+
+    // resident data
+    float2* G[2] = {nullptr, nullptr};
+    long Mg[2] = {0, 0};
+    uchar2* AD = nullptr;
+    long M_ad = 0;
+
+    // sharding
+    long M_total = -1, site_offset = 0;
+    wgs_allreduce_fn fn = nullptr;
+    void* user = nullptr;
+
+    // z-score class tables of the last call
+    std::vector<std::vector<int>> zclasses;
+
+    // instrumentation
+    long launches = 0;
+    bool timing = false;
+    std::vector<std::string> tnames;
+    std::vector<TimedLaunch> timed;
+    std::map<std::string, FamilyStat> tdone;
+
+    long M() const { return Mg[0]; }
+    long Mtot() const { return M_total >= 0 ? M_total : Mg[0]; }
+};
+
+namespace {
+
+int fail(wgs_ctx* c, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return 1;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int name_id(wgs_ctx* ctx, const char* name)
+{
+    for (size_t i = 0; i < ctx->tnames.size(); ++i) if (ctx->tnames[i] == name) return (int)i;
+    ctx->tnames.push_back(name);
+    return (int)ctx->tnames.size() - 1;
+}
+
+struct LaunchScope {
+    wgs_ctx* ctx; cudaStream_t st; TimedLaunch tl; bool on;
+    LaunchScope(wgs_ctx* c, const char* name, cudaStream_t s) : ctx(c), st(s), on(c->timing) {
+        ++ctx->launches;
+        if (on) {
+            tl.name_id = name_id(ctx, name);
+            cudaEventCreate(&tl.a); cudaEventCreate(&tl.b);
+            cudaEventRecord(tl.a, st);
+        }
+    }
+    ~LaunchScope() { if (on) { cudaEventRecord(tl.b, st); ctx->timed.push_back(tl); } }
+};
+#define LAUNCH(name, kern, grid, block, smem, st, ...)                 \
+    do {                                                               \
+        LaunchScope ls_(ctx, name, st);                                \
+        kern<<<grid, block, smem, st>>>(__VA_ARGS__);                  \
+    } while (0)
+
+void add_work(wgs_ctx* ctx, const char* name, double bytes, double units)
+{
+    if (!ctx->timing) return;
+    auto& slot = ctx->tdone[name];
+    slot.bytes += bytes; slot.units += units;
+}
+
+void fold_timing(wgs_ctx* ctx)
+{
+    for (auto& t : ctx->timed) {
+        cudaEventSynchronize(t.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        auto& slot = ctx->tdone[ctx->tnames[t.name_id]];
+        slot.ms += ms; slot.launches += 1;
+        cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+    }
+    ctx->timed.clear();
+}
+
+template <class T> int dev_alloc(wgs_ctx* ctx, T** p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CU(cudaMalloc((void**)p, count * sizeof(T)));
+    return 0;
+}
+template <class T> void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+struct DevBuf {   // RAII for temporaries
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() { return (T*)p; }
+};
+int buf_alloc(wgs_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    CU(cudaMalloc(&b.p, bytes));
+    return 0;
+}
+
+int grid_for(long n, int block, int cap) { return (int)std::max<long>(1, std::min<long>((n + block - 1) / block, cap)); }
+
+// ---- structure ---------------------------------------------------------------------------
+int build_structure(wgs_ctx* ctx, const int32_t* pop_of_ind, int N, int K)
+{
+    ctx->N = N; ctx->K = K;
+    ctx->pop_of_ind.assign(N, 0);
+    int Ks = std::max(K, 1);
+    if (K > 0) for (int i = 0; i < N; ++i) {
+        if (pop_of_ind[i] < 0 || pop_of_ind[i] >= K) return fail(ctx, "pop_of_ind[%d]=%d outside [0,%d)", i, pop_of_ind[i], K);
+        ctx->pop_of_ind[i] = pop_of_ind[i];
+    }
+    std::vector<int> cnt(Ks, 0);
+    for (int i = 0; i < N; ++i) ++cnt[ctx->pop_of_ind[i]];
+    ctx->pops.assign(Ks, PopDesc{0, 0});
+    int col = 0;
+    for (int k = 0; k < Ks; ++k) {
+        ctx->pops[k].col0 = col; ctx->pops[k].n = cnt[k];
+        col += (cnt[k] + 3) / 4 * 4;                 // 32-byte aligned slabs
+    }
+    ctx->ldg = std::max(col, 4);
+    ctx->ind_of_col.assign(ctx->ldg, -1);
+    ctx->pop_of_col.assign(ctx->ldg, 0);
+    ctx->col_of_ind.assign(N, 0);
+    std::vector<int> fillp(Ks, 0);
+    for (int i = 0; i < N; ++i) {
+        int k = ctx->pop_of_ind[i];
+        int c = ctx->pops[k].col0 + fillp[k]++;
+        ctx->col_of_ind[i] = c; ctx->ind_of_col[c] = i;
+    }
+    for (int k = 0; k < Ks; ++k) {
+        int end = (k + 1 < Ks) ? ctx->pops[k + 1].col0 : ctx->ldg;
+        for (int c = ctx->pops[k].col0; c < end; ++c) ctx->pop_of_col[c] = k;
+    }
+    dev_free(ctx->d_ind_of_col); dev_free(ctx->d_col_of_ind); dev_free(ctx->d_pop_of_col); dev_free(ctx->d_pops);
+    if (dev_alloc(ctx, &ctx->d_ind_of_col, ctx->ldg) || dev_alloc(ctx, &ctx->d_col_of_ind, N) ||
+        dev_alloc(ctx, &ctx->d_pop_of_col, ctx->ldg) || dev_alloc(ctx, &ctx->d_pops, Ks)) return 1;
+    CU(cudaMemcpy(ctx->d_ind_of_col, ctx->ind_of_col.data(), ctx->ldg * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_col_of_ind, ctx->col_of_ind.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_pop_of_col, ctx->pop_of_col.data(), ctx->ldg * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_pops, ctx->pops.data(), Ks * sizeof(PopDesc), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void drop_data(wgs_ctx* ctx)
+{
+    dev_free(ctx->G[0]); dev_free(ctx->G[1]); dev_free(ctx->AD);
+    ctx->Mg[0] = ctx->Mg[1] = ctx->M_ad = 0;
+}
+
+int ensure_structure(wgs_ctx* ctx, int N)
+{
+    if (ctx->N == N && ctx->ldg > 0) return 0;
+    if (ctx->pops_set) return fail(ctx, "matrix has %d individuals but wgs_set_pops was given %d", N, ctx->N);
+    drop_data(ctx);
+    return build_structure(ctx, nullptr, N, 0);
+}
+
+// chunked host -> device with a column permutation kernel per chunk (two staging buffers)
+template <class Elem, class Fn>
+int upload_rows(wgs_ctx* ctx, const Elem* host, long M, int N, Fn&& repack)
+{
+    const size_t row_bytes = (size_t)N * sizeof(Elem);
+    long chunk = std::max<long>(1, (long)((size_t)(96u << 20) / row_bytes));
+    chunk = std::min(chunk, std::max<long>(M, 1));
+    Elem* stage[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {ctx->stream, ctx->stream2};
+    for (int b = 0; b < 2; ++b) CU(cudaMalloc((void**)&stage[b], (size_t)chunk * row_bytes));
+    int b = 0;
+    int rc = 0;
+    for (long r0 = 0; r0 < M && !rc; r0 += chunk, b ^= 1) {
+        long rows = std::min(chunk, M - r0);
+        cudaError_t e = cudaMemcpyAsync(stage[b], host + (size_t)r0 * N, (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st[b]);
+        if (e != cudaSuccess) { rc = fail(ctx, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+        repack(stage[b], r0, rows, st[b]);
+    }
+    cudaStreamSynchronize(st[0]); cudaStreamSynchronize(st[1]);
+    cudaFree(stage[0]); cudaFree(stage[1]);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---- likelihood launch configuration --------------------------------------------------------
+struct LikeCfg { int wx, gx, gy; long sites_per_block; };
+LikeCfg like_cfg(wgs_ctx* ctx, long M, int blocks_per_sm)
+{
+    LikeCfg c;
+    int groups = (ctx->ldg + 31) / 32;
+    c.wx = 1;
+    while (c.wx < 8 && c.wx * 2 <= groups) c.wx *= 2;
+    c.gx = (groups + c.wx - 1) / c.wx;
+    long target = (long)ctx->num_sm * blocks_per_sm * 2;
+    long gy = std::max<long>(1, target / c.gx);
+    long max_gy = std::max<long>(1, (M + kPopLikeTS - 1) / kPopLikeTS);
+    gy = std::min(gy, max_gy);
+    long spb = (M + gy - 1) / gy;
+    spb = (spb + kPopLikeTS - 1) / kPopLikeTS * kPopLikeTS;
+    if (spb < kPopLikeTS) spb = kPopLikeTS;
+    c.sites_per_block = spb;
+    c.gy = (int)std::max<long>(1, (M + spb - 1) / spb);
+    return c;
+}
+
+int pick_R(float margin)
+{
+    // like >= ~margin^2; R factors on a mantissa in [1,2) must stay above 2^-100
+    if (!(margin > 0.f)) return 1;
+    double bits = -2.0 * std::log2((double)margin);
+    if (bits < 1.0) bits = 1.0;
+    int r = (int)(100.0 / bits);
+    if (r >= 8) return 8;
+    if (r >= 4) return 4;
+    if (r >= 2) return 2;
+    return 1;
+}
+
+const int kKT[] = {2, 4, 5, 8, 10, 16, 20};
+int pick_KT(int Krem)
+{
+    for (int kt : kKT) if (kt >= Krem) return kt;
+    return 20;
+}
+
+template <int KT, int R>
+int launch_pop_like_t(wgs_ctx* ctx, const float2* G, long M, const float* dA, int K, int k0, const LikeCfg& c,
+                      long pm, long pr, double* partials)
+{
+    size_t smem = (size_t)kPopLikeTS * KT * sizeof(float4) + 8 * 32 * 4 * sizeof(double);
+    auto kern = pop_like_kernel<KT, R>;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH("pop_like", kern, dim3(c.gx, c.gy), kPopLikeThreads, smem, ctx->stream,
+           G, ctx->ldg, M, dA, K, k0, c.wx, c.sites_per_block, pm, pr, ctx->site_offset, partials);
+    {   // algorithmic: every (g0,g1) pair once per pass + this pass's AF columns; one evaluation per (site, ind, pop)
+        int kt = std::min(KT, K - k0);
+        add_work(ctx, "pop_like", (double)M * ctx->N * 8.0 + (double)M * kt * 4.0, (double)M * ctx->N * kt);
+    }
+    return 0;
+}
+template <int KT, int R>
+int launch_loo_like_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, int ldf, const int* rc, int K, int k0,
+                      const LikeCfg& c, long pm, long pr, double* partials)
+{
+    size_t smem = 8 * 32 * 4 * sizeof(double);
+    LAUNCH("loo_like", (loo_like_kernel<KT, R>), dim3(c.gx, c.gy), kPopLikeThreads, smem, ctx->stream,
+           G, ctx->ldg, M, Fx, ldf, rc, K, k0, c.wx, c.sites_per_block, pm, pr, ctx->site_offset, partials);
+    {   // GL pairs once + the LOO state row (one float per individual) + full-data AF columns
+        int kt = std::min(KT, K - k0);
+        add_work(ctx, "loo_like", (double)M * ctx->N * 12.0 + (double)M * kt * 4.0, (double)M * ctx->N * kt);
+    }
+    return 0;
+}
+
+#define DISPATCH_R(FN, KTV, R, ...)                                      \
+    switch (R) {                                                         \
+        case 8: rc_ = FN<KTV, 8>(__VA_ARGS__); break;                    \
+        case 4: rc_ = FN<KTV, 4>(__VA_ARGS__); break;                    \
+        case 2: rc_ = FN<KTV, 2>(__VA_ARGS__); break;                    \
+        default: rc_ = FN<KTV, 1>(__VA_ARGS__); break;                   \
+    }
+#define DISPATCH_KT(FN, KT, R, ...)                                      \
+    do {                                                                 \
+        switch (KT) {                                                    \
+            case 2: DISPATCH_R(FN, 2, R, __VA_ARGS__) break;             \
+            case 4: DISPATCH_R(FN, 4, R, __VA_ARGS__) break;             \
+            case 5: DISPATCH_R(FN, 5, R, __VA_ARGS__) break;             \
+            case 8: DISPATCH_R(FN, 8, R, __VA_ARGS__) break;             \
+            case 10: DISPATCH_R(FN, 10, R, __VA_ARGS__) break;           \
+            case 16: DISPATCH_R(FN, 16, R, __VA_ARGS__) break;           \
+            default: DISPATCH_R(FN, 20, R, __VA_ARGS__) break;           \
+        }                                                                \
+    } while (0)
+
+// margin of a device AF matrix -> renormalisation interval
+int af_R(wgs_ctx* ctx, const float* dA, long n, int* R_out)
+{
+    DevBuf b;
+    if (buf_alloc(ctx, b, sizeof(int))) return 1;
+    int init = 0x3f000000;   // 0.5f
+    CU(cudaMemcpyAsync(b.p, &init, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH("af_margin", af_margin_kernel, grid_for(n, 256, ctx->num_sm * 8), 256, 0, ctx->stream, dA, n, b.as<int>());
+    int bits = 0;
+    CU(cudaMemcpyAsync(&bits, b.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float m;
+    memcpy(&m, &bits, 4);
+    *R_out = pick_R(m);
+    return 0;
+}
+
+// partial sums [ldg][K] on device -> host [N][K] in Beagle order
+int cols_to_host(wgs_ctx* ctx, const double* d_colsums, int K, double* out)
+{
+    std::vector<double> h((size_t)ctx->ldg * K);
+    CU(cudaMemcpyAsync(h.data(), d_colsums, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->N; ++i)
+        memcpy(out + (size_t)i * K, h.data() + (size_t)ctx->col_of_ind[i] * K, K * sizeof(double));
+    return 0;
+}
+
+// ---- EM loop ------------------------------------------------------------------------------
+struct EmState {
+    int np = 0;                  // problems (columns of the partials)
+    int ld = 0;                  // leading dimension of partials
+    int nblocks = 0;
+    DevBuf partials, ssq, count, active, iters, nactive;
+    std::vector<int> h_active, h_iters;
+};
+
+int em_state_init(wgs_ctx* ctx, EmState& st, int np, int ld, int nblocks, const std::vector<int>& active0)
+{
+    st.np = np; st.ld = ld; st.nblocks = nblocks;
+    if (buf_alloc(ctx, st.partials, (size_t)nblocks * ld * sizeof(double)) || buf_alloc(ctx, st.ssq, (size_t)np * sizeof(double)) ||
+        buf_alloc(ctx, st.active, (size_t)np * sizeof(int)) || buf_alloc(ctx, st.iters, (size_t)np * sizeof(int)) ||
+        buf_alloc(ctx, st.nactive, sizeof(int))) return 1;
+    CU(cudaMemsetAsync(st.partials.p, 0, (size_t)nblocks * ld * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(st.iters.p, 0, (size_t)np * sizeof(int), ctx->stream));
+    st.h_active = active0;
+    st.h_iters.assign(np, 0);
+    CU(cudaMemcpyAsync(st.active.p, st.h_active.data(), (size_t)np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// After a step kernel has written st.partials: reduce, (all-reduce across ranks), decide.
+// d_count: optional per-problem site counts (already global); else count_all.
+int em_after_step(wgs_ctx* ctx, EmState& st, double tole, int iteration, const double* d_count, double count_all, int* n_active)
+{
+    LAUNCH("em_ssq_reduce", em_ssq_reduce_kernel, grid_for(st.np, 128, 64), 128, 0, ctx->stream,
+           st.partials.as<double>(), st.nblocks, st.np, st.ld, st.ssq.as<double>());
+    if (ctx->fn) {
+        std::vector<double> h(st.np);
+        CU(cudaMemcpyAsync(h.data(), st.ssq.p, st.np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->fn(h.data(), st.np, WGS_F64, ctx->user);
+        CU(cudaMemcpyAsync(st.ssq.p, h.data(), st.np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LAUNCH("em_decide", em_decide_kernel, 1, 1024, 0, ctx->stream, st.ssq.as<double>(), d_count, count_all, st.np, tole,
+           iteration, st.active.as<int>(), st.iters.as<int>(), st.nactive.as<int>());
+    CU(cudaMemcpyAsync(n_active, st.nactive.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(st.h_active.data(), st.active.p, st.np * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Per-population EM on the resident G: Fpop [M][K] (device) <- converged, UNclipped f.
+int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* Fpop, std::vector<int>& iters_out)
+{
+    const long M = ctx->M();
+    const int K = std::max(ctx->K, 1);
+    if (K > kMaxKq * 32) return fail(ctx, "more than %d populations not supported", kMaxKq * 32);
+    int nblocks = (int)std::max<long>(1, std::min<long>((M + 7) / 8, (long)ctx->num_sm * 8));
+    EmState st;
+    if (em_state_init(ctx, st, K, K, nblocks, std::vector<int>(K, 1))) return 1;
+    LAUNCH("fill", fill_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, Fpop, M * K, 0.25f);
+    int n_active = K;
+    for (int it = 1; it <= iter && n_active > 0; ++it) {
+        LAUNCH("em_pop", em_pop_step_kernel, nblocks, 256, 0, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, Fpop,
+               st.active.as<int>(), st.partials.as<double>());
+        {   // 8 B per (site, individual of an active population) + f read/write
+            double inds = 0, act = 0;
+            for (int k = 0; k < K; ++k) if (st.h_active[k]) { inds += ctx->pops[k].n; act += 1; }
+            add_work(ctx, "em_pop", (double)M * inds * 8.0 + (double)M * act * 8.0, (double)M * inds);
+        }
+        if (em_after_step(ctx, st, tole, it, nullptr, (double)ctx->Mtot(), &n_active)) return 1;
+    }
+    iters_out.resize(K);
+    CU(cudaMemcpy(iters_out.data(), st.iters.p, K * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+struct LooLaunch { int block, rows_per_pass, passes; size_t smem; };
+LooLaunch loo_cfg(int n, int ni)
+{
+    LooLaunch best{0, 0, 1, 0};
+    double best_u = -1;
+    for (int bd = 128; bd <= 512; bd += 32) {
+        int rpp = bd / ni;
+        if (rpp < 1) continue;
+        double u = (double)(rpp * ni) / bd;
+        if (u > best_u + 1e-9 || (std::fabs(u - best_u) < 1e-9 && bd <= 256)) { best_u = u; best.block = bd; best.rows_per_pass = rpp; }
+    }
+    int stride = n | 1;
+    size_t row_bytes = (size_t)stride * sizeof(float4);
+    int max_rows = (int)std::max<size_t>(1, (size_t)(64 * 1024) / row_bytes);
+    int passes = std::max(1, std::min(16, max_rows / std::max(1, best.rows_per_pass)));
+    best.passes = passes;
+    best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float);
+    return best;
+}
+
+// Leave-one-out EM for every individual on the resident G.  F [M][ldf] (device): columns
+// [0,ldg) <- converged UNclipped LOO estimates.  mask/d_count optional (reference z-score).
+int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const unsigned char* mask, const double* d_count,
+               std::vector<int>& iters_cols)
+{
+    const long M = ctx->M();
+    const int ldg = ctx->ldg, K = ctx->K;
+    std::vector<int> active0(ldg, 0);
+    for (int c = 0; c < ldg; ++c)
+        if (ctx->ind_of_col[c] >= 0 && ctx->pops[ctx->pop_of_col[c]].n > 1) active0[c] = 1;
+    int nblocks = ctx->num_sm * 2;
+    EmState st;
+    if (em_state_init(ctx, st, ldg, ldg, nblocks, active0)) return 1;
+    {   // f = 0.25 everywhere; NaN for the (degenerate) single-member populations, like 0/0 in the reference
+        std::vector<float> row(ldg, 0.25f);
+        for (int c = 0; c < ldg; ++c)
+            if (ctx->ind_of_col[c] >= 0 && ctx->pops[ctx->pop_of_col[c]].n <= 1) row[c] = std::numeric_limits<float>::quiet_NaN();
+        DevBuf drow;
+        if (buf_alloc(ctx, drow, ldg * sizeof(float))) return 1;
+        CU(cudaMemcpyAsync(drow.p, row.data(), ldg * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH("fill", bcast_row_kernel, grid_for(M * ldg, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F, ldf, ldg, M, drow.as<float>());
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    int n_active = 0;
+    for (int a : active0) n_active += a;
+    for (int it = 1; it <= iter && n_active > 0; ++it) {
+        for (int k = 0; k < K; ++k) {
+            PopDesc pd = ctx->pops[k];
+            if (pd.n <= 1) continue;
+            bool any = false;
+            for (int j = 0; j < pd.n; ++j) any = any || st.h_active[pd.col0 + j];
+            if (!any) continue;
+            LooLaunch lc = loo_cfg(pd.n, pd.n);
+            if (lc.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (512)", pd.n);
+            if (lc.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", pd.n);
+            if (lc.smem > 48 * 1024) CU(cudaFuncSetAttribute(loo_em_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
+            int TS = lc.rows_per_pass * lc.passes;
+            long ntiles = (M + TS - 1) / TS;
+            LAUNCH("loo_em", loo_em_step_kernel, nblocks, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
+                   lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
+            {   // the population's GL tile once + read/write of every active problem's f; n evaluations per active (site, problem)
+                double act = 0;
+                for (int j = 0; j < pd.n; ++j) act += st.h_active[pd.col0 + j] ? 1 : 0;
+                add_work(ctx, "loo_em", (double)M * pd.n * 8.0 + (double)M * act * 8.0, (double)M * act * pd.n);
+            }
+        }
+        if (em_after_step(ctx, st, tole, it, d_count, (double)ctx->Mtot(), &n_active)) return 1;
+    }
+    iters_cols.resize(ldg);
+    CU(cudaMemcpy(iters_cols.data(), st.iters.p, ldg * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// clip bounds per sorted column for n_eff = n_pop - minus individuals (float like numpy's compare/assign)
+void clip_bounds(wgs_ctx* ctx, int minus, std::vector<float>& lo, std::vector<float>& hi)
+{
+    lo.assign(ctx->ldg, 0.f); hi.assign(ctx->ldg, 1.f);
+    for (int c = 0; c < ctx->ldg; ++c) {
+        int n = ctx->pops[ctx->pop_of_col[c]].n - minus;
+        double l = 1.0 / (2.0 * (n + 1));
+        lo[c] = (float)l; hi[c] = (float)(1.0 - l);
+    }
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int32_t wgs_abi_version(void) { return WGS_ABI_VERSION; }
+
+int32_t wgs_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* wgs_last_error(const wgs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t wgs_create(int32_t device, wgs_ctx** out)
+{
+    wgs_ctx* ctx = nullptr;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(nullptr, "no CUDA device available (%s) - wgsassign_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, "device %d out of range (%d devices)", device, n);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10) return fail(nullptr, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    ctx = new wgs_ctx();
+    ctx->device = device;
+    ctx->num_sm = prop.multiProcessorCount;
+    cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    *out = ctx;
+    return 0;
+}
+
+void wgs_destroy(wgs_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    fold_timing(ctx);
+    drop_data(ctx);
+    dev_free(ctx->d_ind_of_col); dev_free(ctx->d_col_of_ind); dev_free(ctx->d_pop_of_col); dev_free(ctx->d_pops);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
+    delete ctx;
+}
+
+void* wgs_host_alloc(int64_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void wgs_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int32_t wgs_set_pops(wgs_ctx* ctx, const int32_t* pop_of_ind, int32_t N, int32_t K)
+{
+    cudaSetDevice(ctx->device);
+    if (N <= 0) return fail(ctx, "N must be positive");
+    drop_data(ctx);
+    ctx->pops_set = K > 0;
+    return build_structure(ctx, pop_of_ind, N, K);
+}
+
+int32_t wgs_set_shard(wgs_ctx* ctx, int64_t M_total, int64_t site_offset, wgs_allreduce_fn fn, void* user)
+{
+    ctx->M_total = M_total; ctx->site_offset = site_offset; ctx->fn = fn; ctx->user = user;
+    return 0;
+}
+
+int32_t wgs_upload_gl(wgs_ctx* ctx, const float* L, int64_t M, int32_t N, int32_t which)
+{
+    cudaSetDevice(ctx->device);
+    if (which < 0 || which > 1) return fail(ctx, "which must be 0 or 1");
+    if (M < 0 || N <= 0) return fail(ctx, "bad shape");
+    if (which == 0) { if (ensure_structure(ctx, N)) return 1; }
+    else if (N != ctx->N || M != ctx->Mg[0]) return fail(ctx, "down-sampled matrix must match the GL matrix shape");
+    dev_free(ctx->G[which]);
+    if (dev_alloc(ctx, &ctx->G[which], (size_t)std::max<long>(M, 1) * ctx->ldg)) return 1;
+    ctx->Mg[which] = M;
+    float2* G = ctx->G[which];
+    return upload_rows<float2>(ctx, (const float2*)L, M, N, [&](float2* stage, long r0, long rows, cudaStream_t st) {
+        LAUNCH("repack", repack_kernel, grid_for(rows * ctx->ldg, 256, ctx->num_sm * 16), 256, 0, st, stage, N,
+               G + (size_t)r0 * ctx->ldg, ctx->ldg, ctx->d_ind_of_col, rows);
+    });
+}
+
+int32_t wgs_upload_ad(wgs_ctx* ctx, const int32_t* AD, int64_t M, int32_t N)
+{
+    cudaSetDevice(ctx->device);
+    if (N != ctx->N || M != ctx->Mg[0]) return fail(ctx, "allele-depth matrix must match the GL matrix shape (upload GL first)");
+    dev_free(ctx->AD);
+    if (dev_alloc(ctx, &ctx->AD, (size_t)std::max<long>(M, 1) * ctx->ldg)) return 1;
+    ctx->M_ad = M;
+    DevBuf flag;
+    if (buf_alloc(ctx, flag, sizeof(int))) return 1;
+    CU(cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    uchar2* dst = ctx->AD;
+    int rc = upload_rows<int2>(ctx, (const int2*)AD, M, N, [&](int2* stage, long r0, long rows, cudaStream_t st) {
+        LAUNCH("repack", repack_ad_kernel, grid_for(rows * ctx->ldg, 256, ctx->num_sm * 16), 256, 0, st, stage, N,
+               dst + (size_t)r0 * ctx->ldg, ctx->ldg, ctx->d_ind_of_col, rows, flag.as<int>());
+    });
+    if (rc) return rc;
+    int bad = 0;
+    CU(cudaMemcpy(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) return fail(ctx, "allele depth outside [0,254]: the packed uint8 layout cannot hold it");
+    return 0;
+}
+
+int32_t wgs_synth(wgs_ctx* ctx, int64_t M, int32_t N, uint64_t seed, float depth, int32_t with_ad)
+{
+    cudaSetDevice(ctx->device);
+    if (ensure_structure(ctx, N)) return 1;
+    drop_data(ctx);
+    if (dev_alloc(ctx, &ctx->G[0], (size_t)M * ctx->ldg)) return 1;
+    ctx->Mg[0] = M;
+    if (with_ad) { if (dev_alloc(ctx, &ctx->AD, (size_t)M * ctx->ldg)) return 1; ctx->M_ad = M; }
+    LAUNCH("synth", synth_kernel, grid_for(M * ctx->ldg, 256, ctx->num_sm * 16), 256, 0, ctx->stream, ctx->G[0], ctx->AD,
+           ctx->ldg, (long)M, ctx->d_ind_of_col, ctx->d_pop_of_col, seed, depth, ctx->site_offset);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int32_t wgs_download(wgs_ctx* ctx, int64_t site0, int64_t nsites, float* L_out, int32_t* AD_out)
+{
+    cudaSetDevice(ctx->device);
+    if (site0 < 0 || site0 + nsites > ctx->Mg[0]) return fail(ctx, "site range outside the resident matrix");
+    const int N = ctx->N;
+    if (L_out) {
+        DevBuf tmp;
+        if (buf_alloc(ctx, tmp, (size_t)nsites * N * sizeof(float2))) return 1;
+        LAUNCH("unpack", unpack_kernel, grid_for(nsites * N, 256, ctx->num_sm * 16), 256, 0, ctx->stream,
+               ctx->G[0] + (size_t)site0 * ctx->ldg, ctx->ldg, ctx->d_col_of_ind, N, tmp.as<float2>(), (long)nsites);
+        CU(cudaMemcpyAsync(L_out, tmp.p, (size_t)nsites * N * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (AD_out) {
+        if (!ctx->AD) return fail(ctx, "no allele depths resident");
+        DevBuf tmp;
+        if (buf_alloc(ctx, tmp, (size_t)nsites * N * sizeof(int2))) return 1;
+        LAUNCH("unpack", unpack_ad_kernel, grid_for(nsites * N, 256, ctx->num_sm * 16), 256, 0, ctx->stream,
+               ctx->AD + (size_t)site0 * ctx->ldg, ctx->ldg, ctx->d_col_of_ind, N, tmp.as<int2>(), (long)nsites);
+        CU(cudaMemcpyAsync(AD_out, tmp.p, (size_t)nsites * N * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int32_t wgs_ref_af(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32_t* iters_out)
+{
+    cudaSetDevice(ctx->device);
+    if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
+    if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for reference-panel operators");
+    const long M = ctx->M();
+    const int K = ctx->K;
+    DevBuf F;
+    if (buf_alloc(ctx, F, (size_t)M * K * sizeof(float))) return 1;
+    std::vector<int> its;
+    if (run_em_pop(ctx, iter, tole, F.as<float>(), its)) return 1;
+    std::vector<float> lo(K), hi(K);
+    for (int k = 0; k < K; ++k) { double l = 1.0 / (2.0 * (ctx->pops[k].n + 1)); lo[k] = (float)l; hi[k] = (float)(1.0 - l); }
+    DevBuf dlo, dhi;
+    if (buf_alloc(ctx, dlo, K * sizeof(float)) || buf_alloc(ctx, dhi, K * sizeof(float))) return 1;
+    CU(cudaMemcpyAsync(dlo.p, lo.data(), K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dhi.p, hi.data(), K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH("clip", clip_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F.as<float>(), K, K, M,
+           dlo.as<float>(), dhi.as<float>());
+    CU(cudaMemcpyAsync(af_out, F.p, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    for (int k = 0; k < K; ++k) iters_out[k] = its[k];
+    return 0;
+}
+
+int32_t wgs_emMAF(wgs_ctx* ctx, const float* L_pop, int64_t M, int32_t n, int32_t iter, double tole, float* f_out, int32_t* iters_out)
+{
+    cudaSetDevice(ctx->device);
+    wgs_ctx* sub = nullptr;
+    if (wgs_create(ctx->device, &sub)) return fail(ctx, "%s", wgs_last_error(nullptr));
+    sub->timing = false;
+    std::vector<int32_t> zeros(n, 0);
+    int rc = wgs_set_pops(sub, zeros.data(), n, 1);
+    if (!rc) rc = wgs_upload_gl(sub, L_pop, M, n, 0);
+    if (!rc) {
+        sub->M_total = ctx->M_total; sub->fn = ctx->fn; sub->user = ctx->user;
+        DevBuf F;
+        std::vector<int> its;
+        auto body = [&](wgs_ctx* ctx) -> int {
+            if (buf_alloc(ctx, F, (size_t)std::max<long>(M, 1) * sizeof(float))) return 1;
+            if (run_em_pop(ctx, iter, tole, F.as<float>(), its)) return 1;
+            CU(cudaMemcpy(f_out, F.p, (size_t)M * sizeof(float), cudaMemcpyDeviceToHost));
+            return 0;
+        };
+        rc = body(sub);
+        if (!rc) *iters_out = its[0];
+    }
+    ctx->launches += sub->launches;
+    if (rc) ctx->err = sub->err;
+    wgs_destroy(sub);
+    return rc;
+}
+
+int32_t wgs_pop_like_partial(wgs_ctx* ctx, const float* af, int32_t K, double* out)
+{
+    cudaSetDevice(ctx->device);
+    if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
+    if (K <= 0) return fail(ctx, "K must be positive");
+    const long M = ctx->M();
+    DevBuf dA, partials, sums;
+    if (buf_alloc(ctx, dA, (size_t)M * K * sizeof(float))) return 1;
+    CU(cudaMemcpyAsync(dA.p, af, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    int R = 1;
+    if (af_R(ctx, dA.as<float>(), M * K, &R)) return 1;
+    LikeCfg c = like_cfg(ctx, M, 3);
+    size_t np = (size_t)ctx->ldg * K;
+    if (buf_alloc(ctx, partials, (size_t)c.gy * np * sizeof(double)) || buf_alloc(ctx, sums, np * sizeof(double))) return 1;
+    for (int k0 = 0; k0 < K;) {
+        int KT = pick_KT(K - k0);
+        int rc_ = 0;
+        DISPATCH_KT(launch_pop_like_t, KT, R, ctx, ctx->G[0], M, dA.as<float>(), K, k0, c, 1L, 0L, partials.as<double>());
+        if (rc_) return rc_;
+        k0 += KT;
+    }
+    LAUNCH("reduce", reduce_partials_kernel, grid_for(np, 256, ctx->num_sm * 4), 256, 0, ctx->stream, partials.as<double>(), c.gy,
+           (long)np, sums.as<double>());
+    if (cols_to_host(ctx, sums.as<double>(), K, out)) return 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, int32_t use_ds, int32_t parts,
+                        double* ll, double* ll_parts, int32_t* iters_out)
+{
+    cudaSetDevice(ctx->device);
+    if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
+    if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for reference-panel operators");
+    if (use_ds && !ctx->G[1]) return fail(ctx, "down-sampled GL matrix not resident (wgs_upload_gl which=1)");
+    if (parts < 1) return fail(ctx, "parts must be >= 1");
+    const long M = ctx->M();
+    const int K = ctx->K, ldg = ctx->ldg, N = ctx->N;
+    const int ldf = ldg + (K + 3) / 4 * 4;
+    DevBuf F, dA, dcols;
+    if (buf_alloc(ctx, F, (size_t)M * ldf * sizeof(float)) || buf_alloc(ctx, dA, (size_t)M * K * sizeof(float)) ||
+        buf_alloc(ctx, dcols, K * sizeof(int))) return 1;
+    CU(cudaMemcpyAsync(dA.p, af_inout, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int> ident(K);
+    for (int k = 0; k < K; ++k) ident[k] = k;
+    CU(cudaMemcpyAsync(dcols.p, ident.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(F.p, 0, (size_t)M * ldf * sizeof(float), ctx->stream));
+    LAUNCH("gather", gather_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, dA.as<float>(), K,
+           dcols.as<int>(), K, F.as<float>(), ldf, ldg, M);
+
+    std::vector<int> its_cols;
+    if (run_em_loo(ctx, iter, tole, F.as<float>(), ldf, nullptr, nullptr, its_cols)) return 1;
+    for (int i = 0; i < N; ++i) iters_out[i] = its_cols[ctx->col_of_ind[i]];
+
+    // clip to [1/(2n), 1-1/(2n)] with n = n_pop (glassy.py:80-85: n_pop-1 individuals were used)
+    std::vector<float> lo, hi;
+    clip_bounds(ctx, 1, lo, hi);
+    DevBuf dlo, dhi;
+    if (buf_alloc(ctx, dlo, ldg * sizeof(float)) || buf_alloc(ctx, dhi, ldg * sizeof(float))) return 1;
+    CU(cudaMemcpyAsync(dlo.p, lo.data(), ldg * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dhi.p, hi.data(), ldg * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH("clip", clip_cols_kernel, grid_for(M * ldg, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F.as<float>(), ldf, ldg, M,
+           dlo.as<float>(), dhi.as<float>());
+
+    // which column of F each (individual, population) pair reads (glassy.py:89 overwrite order)
+    std::vector<int> rc((size_t)ldg * K, ldf - 1), last(K, -1);
+    for (int i = 0; i < N; ++i) {
+        int c = ctx->col_of_ind[i], p = ctx->pop_of_ind[i];
+        for (int j = 0; j < K; ++j)
+            rc[(size_t)c * K + j] = (j == p) ? c : (last[j] >= 0 ? ctx->col_of_ind[last[j]] : ldg + j);
+        last[p] = i;
+    }
+    DevBuf drc;
+    if (buf_alloc(ctx, drc, rc.size() * sizeof(int))) return 1;
+    CU(cudaMemcpyAsync(drc.p, rc.data(), rc.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+
+    int R = 1;
+    {   // margin over everything the likelihood can read: clipped LOO columns and the full-data AF
+        int Ra = 1;
+        if (af_R(ctx, dA.as<float>(), M * K, &Ra)) return 1;
+        float mlo = 0.5f;
+        for (int c = 0; c < ldg; ++c) if (ctx->ind_of_col[c] >= 0) mlo = std::min(mlo, lo[c]);
+        R = std::min(Ra, pick_R(mlo));
+        for (int k = 0; k < K; ++k) if (ctx->pops[k].n <= 1) R = 1;
+    }
+    LikeCfg c = like_cfg(ctx, M, 3);
+    size_t np = (size_t)ldg * K;
+    DevBuf partials, sums;
+    if (buf_alloc(ctx, partials, (size_t)c.gy * np * sizeof(double)) || buf_alloc(ctx, sums, np * sizeof(double))) return 1;
+    const float2* Gsrc = use_ds ? ctx->G[1] : ctx->G[0];
+    std::vector<double> tmp((size_t)N * K);
+    for (int pass = 0; pass < (parts > 1 ? parts + 1 : 1); ++pass) {
+        long pm = pass == 0 ? 1 : parts, pr = pass == 0 ? 0 : pass - 1;
+        for (int k0 = 0; k0 < K;) {
+            int KT = pick_KT(K - k0);
+            int rc_ = 0;
+            DISPATCH_KT(launch_loo_like_t, KT, R, ctx, Gsrc, M, F.as<float>(), ldf, drc.as<int>(), K, k0, c, pm, pr, partials.as<double>());
+            if (rc_) return rc_;
+            k0 += KT;
+        }
+        LAUNCH("reduce", reduce_partials_kernel, grid_for(np, 256, ctx->num_sm * 4), 256, 0, ctx->stream, partials.as<double>(),
+               c.gy, (long)np, sums.as<double>());
+        if (pass == 0) { if (cols_to_host(ctx, sums.as<double>(), K, ll)) return 1; }
+        else {
+            if (!ll_parts) return fail(ctx, "ll_parts is NULL but parts > 1");
+            if (cols_to_host(ctx, sums.as<double>(), K, tmp.data())) return 1;
+            for (int i = 0; i < N; ++i)
+                memcpy(ll_parts + ((size_t)i * parts + pr) * K, tmp.data() + (size_t)i * K, K * sizeof(double));
+        }
+    }
+    if (parts == 1 && ll_parts) memcpy(ll_parts, ll, (size_t)N * K * sizeof(double));
+
+    // af as the reference leaves it: column j = LOO estimate of the LAST member of population j
+    std::vector<int> lastcol(K);
+    for (int j = 0; j < K; ++j) lastcol[j] = last[j] >= 0 ? ctx->col_of_ind[last[j]] : ldg + j;
+    CU(cudaMemcpyAsync(dcols.p, lastcol.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH("gather", gather_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F.as<float>(), ldf,
+           dcols.as<int>(), K, dA.as<float>(), K, 0, M);
+    CU(cudaMemcpyAsync(af_inout, dA.p, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int32_t wgs_fisher_partial(wgs_ctx* ctx, const float* af, float* f_obs, float* ne_obs, double* ne_ind_sum)
+{
+    cudaSetDevice(ctx->device);
+    if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
+    if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for reference-panel operators");
+    const long M = ctx->M();
+    const int K = ctx->K, ldg = ctx->ldg;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * ldg * sizeof(float) > 96 * 1024) warps /= 2;
+    size_t smem = (size_t)warps * ldg * sizeof(float);
+    if (smem > 200 * 1024) return fail(ctx, "too many individuals for the Fisher kernel's shared-memory accumulators");
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fisher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nblocks = (int)std::max<long>(1, std::min<long>((M + warps - 1) / warps, (long)ctx->num_sm * 4));
+    DevBuf dA, dF, dNe, partials, sums;
+    if (buf_alloc(ctx, dA, (size_t)M * K * sizeof(float)) || buf_alloc(ctx, dF, (size_t)M * K * sizeof(float)) ||
+        buf_alloc(ctx, dNe, (size_t)M * K * sizeof(float)) || buf_alloc(ctx, partials, (size_t)nblocks * ldg * sizeof(double)) ||
+        buf_alloc(ctx, sums, ldg * sizeof(double))) return 1;
+    CU(cudaMemcpyAsync(dA.p, af, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH("fisher", fisher_kernel, nblocks, warps * 32, smem, ctx->stream, ctx->G[0], ldg, M, ctx->d_pops, K, dA.as<float>(),
+           dF.as<float>(), dNe.as<float>(), warps, partials.as<double>());
+    add_work(ctx, "fisher", (double)M * ctx->N * 8.0 + (double)M * K * 12.0, (double)M * ctx->N);
+    LAUNCH("reduce", reduce_partials_kernel, grid_for(ldg, 256, 64), 256, 0, ctx->stream, partials.as<double>(), nblocks, (long)ldg,
+           sums.as<double>());
+    CU(cudaMemcpyAsync(f_obs, dF.p, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ne_obs, dNe.p, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<double> h(ldg);
+    CU(cudaMemcpyAsync(h.data(), sums.p, ldg * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    for (int i = 0; i < ctx->N; ++i) ne_ind_sum[i] = h[ctx->col_of_ind[i]];
+    return 0;
+}
+
+int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32_t n_threshold, int32_t single_read,
+                   int32_t ind_start, int32_t ind_end, int32_t iter, double tole, wgs_zrow* out)
+{
+    (void)mode; (void)af; (void)K; (void)n_threshold; (void)single_read; (void)ind_start; (void)ind_end; (void)iter; (void)tole; (void)out;
+    return fail(ctx, "wgs_zscore: not implemented in this build");
+}
+
+int32_t wgs_zscore_classes(wgs_ctx* ctx, int32_t ind, int32_t max_rows, int32_t* rows_out, int32_t* n_rows)
+{
+    if (ind < 0 || ind >= (int)ctx->zclasses.size()) return fail(ctx, "no class table for individual %d", ind);
+    const auto& v = ctx->zclasses[ind];
+    int n = (int)v.size() / 4;
+    *n_rows = n;
+    for (int r = 0; r < std::min(n, max_rows); ++r) memcpy(rows_out + 4 * r, v.data() + 4 * r, 4 * sizeof(int));
+    return 0;
+}
+
+int64_t wgs_launch_count(const wgs_ctx* ctx) { return ctx->launches; }
+
+int32_t wgs_timing_reset(wgs_ctx* ctx, int32_t enable)
+{
+    cudaSetDevice(ctx->device);
+    fold_timing(ctx);
+    ctx->tdone.clear();
+    ctx->timing = enable != 0;
+    return 0;
+}
+
+int32_t wgs_timing_get(wgs_ctx* ctx, const char* name, double* ms, int64_t* launches)
+{
+    cudaSetDevice(ctx->device);
+    fold_timing(ctx);
+    auto it = ctx->tdone.find(name);
+    *ms = it == ctx->tdone.end() ? 0.0 : it->second.ms;
+    *launches = it == ctx->tdone.end() ? 0 : it->second.launches;
+    return 0;
+}
+
+int32_t wgs_timing_work(wgs_ctx* ctx, const char* name, double* bytes, double* units)
+{
+    auto it = ctx->tdone.find(name);
+    *bytes = it == ctx->tdone.end() ? 0.0 : it->second.bytes;
+    *units = it == ctx->tdone.end() ? 0.0 : it->second.units;
+    return 0;
+}
+
+}  // extern "C"

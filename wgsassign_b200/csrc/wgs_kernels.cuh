@@ -1,0 +1,745 @@
+// wgsassign_b200 - sm_100a kernels of the WGSassign genotype-likelihood hot path.
+//
+// Device layout ("G"): float2 G[M][ldg], one (g0,g1) pair per (site, individual); the third
+// genotype likelihood is never stored - it is recomputed as 1-g0-g1 exactly like the
+// reference does (emMAF_cy.pyx:21, glassy_cy.pyx:20).  Columns are population-sorted (stable
+// in Beagle order inside a population) and every population slab starts on a 32-byte
+// boundary (4 individuals), so one population is a contiguous, sector-aligned run of a row.
+//
+// None of these kernels is a contraction: there are no tensor-core instructions here.  The
+// likelihood kernels are bound by FP32 issue (K >= ~10) or HBM (small K), the leave-one-out
+// EM by the MUFU reciprocal rate, the per-population EM and Fisher kernels by HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wgs {
+
+constexpr int kWarp = 32;
+constexpr int kPopLikeThreads = 256;
+constexpr int kPopLikeTS = 64;      // sites per shared-memory AF tile
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct PopDesc {
+    int col0;     // first sorted column of the slab
+    int n;        // individuals in the population
+};
+
+__device__ __forceinline__ float2 ld_stream2(const float2* p) {
+    // streaming 64-bit load: read once, keep it out of L1
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+
+// 1 - g0 - g1 with the rounding error of the first subtraction carried (the reference
+// evaluates this sub-expression in double before it is multiplied, emMAF_cy.pyx:21).
+__device__ __forceinline__ float third_gl(float g0, float g1) {
+    float t = 1.0f - g0;
+    float e = (1.0f - t) - g0;      // exact: Fast2Sum error term of t
+    return (t - g1) + e;
+}
+
+// one MUFU.RCP, no denormal fix-up code (operands here are sums of likelihood terms, never denormal
+// unless the likelihood itself is 0, where 0 * inf = NaN reproduces the reference's 0/0)
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// repack: staging rows in the reference layout [rows][2N] -> G[rows][ldg] (sorted columns)
+// ---------------------------------------------------------------------------------------
+__global__ void repack_kernel(const float2* __restrict__ stage, int N, float2* __restrict__ G, int ldg,
+                              const int* __restrict__ ind_of_col, long rows)
+{
+    long total = rows * (long)ldg;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long r = e / ldg;
+        int c = (int)(e - r * ldg);
+        int src = ind_of_col[c];
+        float2 v = make_float2(0.f, 0.f);
+        if (src >= 0) v = stage[r * (long)N + src];
+        G[e] = v;
+    }
+}
+
+// inverse of repack for wgs_download: G rows -> reference layout
+__global__ void unpack_kernel(const float2* __restrict__ G, int ldg, const int* __restrict__ col_of_ind, int N,
+                              float2* __restrict__ out, long rows)
+{
+    long total = rows * (long)N;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long r = e / N;
+        int i = (int)(e - r * N);
+        out[e] = G[r * (long)ldg + col_of_ind[i]];
+    }
+}
+
+// allele depths: int32 [rows][2N] -> uchar2 [rows][ldg]; *overflow |= 1 if a count > 254
+__global__ void repack_ad_kernel(const int2* __restrict__ stage, int N, uchar2* __restrict__ AD, int ldg,
+                                 const int* __restrict__ ind_of_col, long rows, int* __restrict__ overflow)
+{
+    long total = rows * (long)ldg;
+    int bad = 0;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long r = e / ldg;
+        int c = (int)(e - r * ldg);
+        int src = ind_of_col[c];
+        uchar2 v = make_uchar2(0, 0);
+        if (src >= 0) {
+            int2 a = stage[r * (long)N + src];
+            if (a.x < 0 || a.x > 254 || a.y < 0 || a.y > 254) bad = 1;
+            v = make_uchar2((unsigned char)a.x, (unsigned char)a.y);
+        }
+        AD[e] = v;
+    }
+    if (bad) atomicOr(overflow, 1);
+}
+
+__global__ void unpack_ad_kernel(const uchar2* __restrict__ AD, int ldg, const int* __restrict__ col_of_ind, int N,
+                                 int2* __restrict__ out, long rows)
+{
+    long total = rows * (long)N;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long r = e / N;
+        int i = (int)(e - r * N);
+        uchar2 v = AD[r * (long)ldg + col_of_ind[i]];
+        out[e] = make_int2(v.x, v.y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// min over the AF matrix of min(a, 1-a): picks the renormalisation interval of pop_like
+// ---------------------------------------------------------------------------------------
+__global__ void af_margin_kernel(const float* __restrict__ A, long n, int* __restrict__ out_bits)
+{
+    float m = 0.5f;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        float a = A[e];
+        float v = fminf(a, 1.0f - a);
+        if (!(v > 0.f)) v = 0.f;          // NaN, <= 0 -> 0
+        m = fminf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(out_bits, __float_as_int(m));   // m >= 0: int order == float order
+}
+
+// ---------------------------------------------------------------------------------------
+// Likelihood accumulation without a logarithm per evaluation.
+//
+// sum_s log(like_s) is accumulated as a running PRODUCT of the per-site likelihoods in
+// FP32 whose exponent is moved into an integer every R sites (integer ALU, no MUFU): the
+// sum of logs is (esum + log2(mantissa)) * ln2, evaluated once per thread in FP64.  The
+// rounding error of the product is one FP32 rounding per site, unbiased - smaller than the
+// error of an FP32 log per site - and the integer part is exact.  R is chosen on the host
+// from the smallest allele-frequency margin so that R factors can never underflow.
+// A factor that is zero / negative / NaN (the reference then yields -inf or NaN, glassy_cy.pyx:21)
+// is caught at the next renormalisation and recorded in a per-population bit mask.
+// ---------------------------------------------------------------------------------------
+template <int KT>
+struct LikeAcc {
+    float prod[KT];
+    int esum[KT];
+    unsigned zero_mask, nan_mask;
+    int nren;
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { prod[k] = 1.0f; esum[k] = 0; }
+        zero_mask = nan_mask = 0u; nren = 0;
+    }
+    __device__ __forceinline__ void renorm() {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            int b = __float_as_int(prod[k]);
+            if ((unsigned)(b - 0x00800000) < 0x7F000000u) {      // positive normal
+                esum[k] += (b >> 23);
+                prod[k] = __int_as_float((b & 0x007fffff) | 0x3f800000);
+            } else {
+                if (prod[k] == 0.0f || (b > 0 && b < 0x00800000)) zero_mask |= (1u << k);   // 0 or denormal
+                else nan_mask |= (1u << k);                                             // negative, inf, NaN
+                esum[k] += 127;
+                prod[k] = 1.0f;
+            }
+        }
+        ++nren;
+    }
+    // natural-log sum of everything accumulated so far for slot k
+    __device__ __forceinline__ double value(int k) const {
+        if (nan_mask & (1u << k)) return __longlong_as_double(0x7ff8000000000000LL);
+        if (zero_mask & (1u << k)) return __longlong_as_double(0xfff0000000000000LL);
+        double e = (double)(esum[k] - 127 * nren);
+        return (e + log2((double)prod[k])) * 0.693147180559945309417232121458;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// pop_like: sum over sites of log(GL . HWE(A[s,k])) for every (individual, population)
+// (glassy_cy.pyx:12-21 + glassy.py:31-42).  One thread = one individual (column); a warp
+// = 32 consecutive columns at one site, so a site's GL row is read with one fully
+// coalesced 256-byte request per warp; the HWE triples of the site tile are computed once
+// per block into shared memory and read back as 128-bit broadcasts.
+// grid.x = column groups (fast, so that co-scheduled blocks share the AF tile in L2),
+// grid.y = site splits.  partials[split][col][K] (float64) are reduced in a fixed order
+// by reduce_partials_kernel - deterministic, no atomics.
+// ---------------------------------------------------------------------------------------
+template <int KT, int R>
+__global__ void __launch_bounds__(kPopLikeThreads)
+pop_like_kernel(const float2* __restrict__ G, int ldg, long M,
+                const float* __restrict__ A, int K, int k0,
+                int wx,                                  // column groups per block (power of two <= 8)
+                long sites_per_block,
+                long part_mod, long part_rem, long site_offset,
+                double* __restrict__ partials)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* H = reinterpret_cast<float4*>(smem_raw);                 // [TS][KT]
+    double* red = reinterpret_cast<double*>(H + kPopLikeTS * KT);    // [8][32][4]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy_count = (kPopLikeThreads / 32) / wx;
+    const int cgx = warp % wx, wy = warp / wx;
+    const int col = (blockIdx.x * wx + cgx) * 32 + lane;
+    const bool col_ok = col < ldg;
+    const long s_begin = (long)blockIdx.y * sites_per_block;
+    const long s_end = min(M, s_begin + sites_per_block);
+
+    LikeAcc<KT> acc;
+    acc.init();
+
+    const int per_warp = kPopLikeTS / wy_count;       // sites of a tile handled by one warp (multiple of 8)
+    for (long s0 = s_begin; s0 < s_end; s0 += kPopLikeTS) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < kPopLikeTS * KT; e += kPopLikeThreads) {
+            int sl = e / KT, kk = e - sl * KT;
+            long s = s0 + sl;
+            float a = 0.5f;
+            if (s < s_end && k0 + kk < K) a = __ldg(&A[s * K + k0 + kk]);
+            float om = 1.0f - a;
+            H[e] = make_float4(om * om, 2.0f * a * om, a * a, 0.f);
+        }
+        __syncthreads();
+        for (int u0 = 0; u0 < per_warp; u0 += 8) {
+            float2 g[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                long s = s0 + wy + (long)wy_count * (u0 + u);
+                g[u] = make_float2(1.0f, 0.0f);
+                if (col_ok && s < s_end) g[u] = ld_stream2(&G[s * (long)ldg + col]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                int sl = wy + wy_count * (u0 + u);
+                long s = s0 + sl;
+                bool use = s < s_end;
+                if (part_mod > 1) use = use && ((site_offset + s) % part_mod == part_rem);
+                if (use) {                                        // warp-uniform
+                    float g0 = g[u].x, g1 = g[u].y, g2 = third_gl(g0, g1);
+#pragma unroll
+                    for (int kk = 0; kk < KT; ++kk) {
+                        float4 h = H[sl * KT + kk];
+                        float like = fmaf(g0, h.x, fmaf(g1, h.y, g2 * h.z));
+                        acc.prod[kk] *= like;
+                    }
+                }
+                if (((u + 1) % R) == 0) acc.renorm();
+            }
+        }
+    }
+    acc.renorm();   // brings every slot to a known state (also folds a trailing partial group)
+
+    // fixed-order reduction over the wy_count warps that share this column group
+    for (int kk0 = 0; kk0 < KT; kk0 += 4) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (kk0 + q < KT) red[(warp * 32 + lane) * 4 + q] = acc.value(kk0 + q);
+        __syncthreads();
+        if (wy == 0 && col_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int kk = kk0 + q;
+                if (kk < KT && k0 + kk < K) {
+                    double v = 0.0;
+                    for (int w = 0; w < wy_count; ++w) v += red[((w * wx + cgx) * 32 + lane) * 4 + q];
+                    partials[((long)blockIdx.y * ldg + col) * K + k0 + kk] = v;
+                }
+            }
+        }
+    }
+}
+
+// out[col][k] = sum over splits (fixed order) of partials[split][col][k]
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int nsplit, long n, double* __restrict__ out)
+{
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        double v = 0.0;
+        for (int sp = 0; sp < nsplit; ++sp) v += partials[(long)sp * n + e];
+        out[e] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// loo_like: like pop_like, but the allele frequency of (individual c, population j) is a
+// per-pair COLUMN of the leave-one-out state matrix Fx[M][ldf]: the reference overwrites
+// af[:, pop(i)] with individual i's LOO estimate and never restores it (glassy.py:89), so
+// population j's column seen by individual i is the LOO estimate of the latest earlier
+// member of j (or the full-data AF, stored in the last K columns of Fx).  rc[col][K] holds
+// that column index.  Same accumulation/reduction scheme as pop_like.
+// ---------------------------------------------------------------------------------------
+template <int KT, int R>
+__global__ void __launch_bounds__(kPopLikeThreads)
+loo_like_kernel(const float2* __restrict__ G, int ldg, long M,
+                const float* __restrict__ Fx, int ldf,
+                const int* __restrict__ rc, int K, int k0,
+                int wx, long sites_per_block,
+                long part_mod, long part_rem, long site_offset,
+                double* __restrict__ partials)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* red = reinterpret_cast<double*>(smem_raw);    // [8][32][4]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy_count = (kPopLikeThreads / 32) / wx;
+    const int cgx = warp % wx, wy = warp / wx;
+    const int col = (blockIdx.x * wx + cgx) * 32 + lane;
+    const bool col_ok = col < ldg;
+    const long s_begin = (long)blockIdx.y * sites_per_block;
+    const long s_end = min(M, s_begin + sites_per_block);
+
+    int rcol[KT];
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk)
+        rcol[kk] = (col_ok && k0 + kk < K) ? rc[(long)col * K + k0 + kk] : (ldf - 1);
+
+    LikeAcc<KT> acc;
+    acc.init();
+    int cnt = 0;
+    for (long s = s_begin + wy; s < s_end; s += wy_count) {
+        bool use = true;
+        if (part_mod > 1) use = ((site_offset + s) % part_mod == part_rem);
+        if (use) {
+            float2 g = make_float2(1.0f, 0.0f);
+            if (col_ok) g = ld_stream2(&G[s * (long)ldg + col]);
+            float g0 = g.x, g1 = g.y, g2 = third_gl(g0, g1);
+            const float* frow = Fx + s * (long)ldf;
+#pragma unroll
+            for (int kk = 0; kk < KT; ++kk) {
+                float a = __ldg(&frow[rcol[kk]]);
+                float om = 1.0f - a;
+                float like = fmaf(g0, om * om, fmaf(g1, 2.0f * a * om, g2 * (a * a)));
+                acc.prod[kk] *= like;
+            }
+            if (++cnt == R) { acc.renorm(); cnt = 0; }
+        }
+    }
+    acc.renorm();
+
+    for (int kk0 = 0; kk0 < KT; kk0 += 4) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (kk0 + q < KT) red[(warp * 32 + lane) * 4 + q] = acc.value(kk0 + q);
+        __syncthreads();
+        if (wy == 0 && col_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int kk = kk0 + q;
+                if (kk < KT && k0 + kk < K) {
+                    double v = 0.0;
+                    for (int w = 0; w < wy_count; ++w) v += red[((w * wx + cgx) * 32 + lane) * 4 + q];
+                    partials[((long)blockIdx.y * ldg + col) * K + k0 + kk] = v;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// EM posterior term of one individual at allele frequency f (emMAF_cy.pyx:19-22):
+//   (p1 + 2 p2) / (2 (p0 + p1 + p2)),  p = GL * HWE(f)
+// with H0 = 2(1-f)^2, H1 = 2f(1-f), H2 = 2f^2 precomputed per (site, problem):
+//   num = g1 H1 + g2 H2 ; den = g0 H0 + g1 H1 + num.
+// ---------------------------------------------------------------------------------------
+struct EmCoef { float H0, H1, H2; };
+__device__ __forceinline__ EmCoef em_coef(float f) {
+    float om = 1.0f - f;
+    EmCoef c;
+    c.H0 = 2.0f * om * om; c.H1 = 2.0f * f * om; c.H2 = 2.0f * f * f;
+    return c;
+}
+struct EmFrac { float num, rden; };
+__device__ __forceinline__ EmFrac em_frac(float g0, float g1, float g2, const EmCoef& c) {
+    EmFrac r;
+    r.num = fmaf(g1, c.H1, g2 * c.H2);
+    float den = fmaf(g0, c.H0, fmaf(g1, c.H1, r.num));
+    r.rden = fast_rcp(den);
+    return r;
+}
+__device__ __forceinline__ float em_term(float g0, float g1, float g2, const EmCoef& c) {
+    float num = fmaf(g1, c.H1, g2 * c.H2);
+    float den = fmaf(g0, c.H0, fmaf(g1, c.H1, num));
+    return num * fast_rcp(den);
+}
+
+// ---------------------------------------------------------------------------------------
+// em_pop_step: ONE EM iteration of every still-active population (emMAF_cy.pyx:10-23 for
+// all K groups at once).  A warp owns a site: lanes stride over the population's
+// contiguous slab (coalesced 256-byte requests), a shuffle tree forms the site sum.
+// HBM-bound: 8 bytes per (site, individual, iteration).  Lane (k & 31) of each warp
+// accumulates the squared change of population k; partials[block][K] feed the global
+// stop rule (emMAF_cy.pyx:26-33).  mask (optional, uchar [M][ld_mask]) restricts the
+// squared-change sum to kept sites.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxKq = 4;   // K <= 128
+__global__ void __launch_bounds__(256)
+em_pop_step_kernel(const float2* __restrict__ G, int ldg, long M,
+                   const PopDesc* __restrict__ pops, int K,
+                   float* __restrict__ Fpop,             // [M][K], in place
+                   const int* __restrict__ active,       // [K]
+                   double* __restrict__ partials)        // [gridDim.x][K]
+{
+    __shared__ float sh[8][kMaxKq * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float ssq[kMaxKq];
+#pragma unroll
+    for (int q = 0; q < kMaxKq; ++q) ssq[q] = 0.f;
+
+    for (long s = (long)blockIdx.x * 8 + warp; s < M; s += (long)gridDim.x * 8) {
+        const float2* row = G + s * (long)ldg;
+        for (int k = 0; k < K; ++k) {
+            if (!active[k]) continue;
+            PopDesc pd = pops[k];
+            float f = Fpop[s * K + k];
+            EmCoef c = em_coef(f);
+            float sum = 0.f;
+            for (int j = lane; j < pd.n; j += 32) {
+                float2 g = ld_stream2(&row[pd.col0 + j]);
+                sum += em_term(g.x, g.y, third_gl(g.x, g.y), c);
+            }
+            sum = warp_sum(sum);
+            float fnew = __fdiv_rn(sum, (float)pd.n);
+            float d = fnew - f;
+            if (lane == (k & 31)) {
+#pragma unroll
+                for (int q = 0; q < kMaxKq; ++q) if (q == (k >> 5)) ssq[q] += d * d;
+            }
+            if (lane == 0) Fpop[s * K + k] = fnew;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kMaxKq; ++q) sh[warp][q * 32 + lane] = ssq[q];
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += (double)sh[w][k];
+        partials[(long)blockIdx.x * K + k] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// loo_em_step: ONE EM iteration of every still-active leave-one-out problem of ONE
+// population (glassy.py:65-78: emMAF on the population minus individual i, for every i).
+// Problem i at site s follows its own trajectory f_i, so each (site, i) evaluates all n
+// posterior terms at f_i and removes its own: n^2 evaluations per site and iteration from
+// ONE read of the population's GL tile (staged in shared memory as (g0,g1,g2) float4,
+// read back as 128-bit broadcasts).  Bound by the MUFU reciprocal rate, not by HBM.
+// Thread t < Bp owns problem i = t % n for the whole launch, so its squared change is a
+// register; partials[block][col] are reduced in fixed order by em_ssq_reduce_kernel.
+// mask (optional): uchar keep[M][ldg] - sites whose squared change counts (reference
+// z-score runs the EM on kept sites only, WGSassign.py:358-359; a site outside the mask
+// cannot influence another site, so it is simply skipped).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+loo_em_step_kernel(const float2* __restrict__ G, int ldg, long M,
+                   int col0, int n, int rows_per_pass, int passes,
+                   float* __restrict__ F, int ldf,              // [M][ldf], in place
+                   const int* __restrict__ active,              // [ldg]
+                   const unsigned char* __restrict__ mask,      // [M][ldg] or null
+                   double* __restrict__ partials,               // [gridDim.x][ldg]
+                   long ntiles)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* tile = reinterpret_cast<float4*>(smem_raw);
+    const int stride = n | 1;                                   // odd float4 stride: rows never share a bank group
+    const int TS = rows_per_pass * passes;
+    float* red = reinterpret_cast<float*>(tile + (size_t)TS * stride);   // [blockDim.x]
+
+    const int t = threadIdx.x;
+    const int Bp = rows_per_pass * n;
+    const int i = t % n, r = t / n;
+    const bool worker = t < Bp;
+    const bool my_active = worker && active[col0 + i] != 0;
+    const float inv_div = (float)(n - 1);
+    float ssq = 0.f;
+
+    for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const long s0 = tl * TS;
+        __syncthreads();
+        for (int e = t; e < TS * n; e += blockDim.x) {
+            int sl = e / n, j = e - sl * n;
+            long s = s0 + sl;
+            float2 g = make_float2(1.0f / 3, 1.0f / 3);
+            if (s < M) g = ld_stream2(&G[s * (long)ldg + col0 + j]);
+            tile[sl * stride + j] = make_float4(g.x, g.y, third_gl(g.x, g.y), 0.f);
+        }
+        __syncthreads();
+        if (my_active) {
+            for (int p = 0; p < passes; ++p) {
+                int sl = p * rows_per_pass + r;
+                long s = s0 + sl;
+                if (s >= M) break;
+                if (mask && !mask[s * (long)ldg + col0 + i]) continue;
+                float* fp = F + s * (long)ldf + col0 + i;
+                float f = *fp;
+                EmCoef c = em_coef(f);
+                const float4* trow = tile + sl * stride;
+                // The left-out individual is skipped by predication, not subtracted afterwards:
+                // sum-minus-own cancels to 0 when the others contribute ~nothing, and an exact
+                // f = 0 turns the next iteration's 0/0 into NaN where the reference stays finite.
+                float a0 = 0.f, a1 = 0.f;
+                int j = 0;
+                for (; j + 8 <= n; j += 8) {
+                    const int d = i - j;                  // own index relative to this block of 8
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        float4 g = trow[j + u];
+                        EmFrac tf = em_frac(g.x, g.y, g.z, c);
+                        if (d != u) {
+                            if (u & 1) a1 = fmaf(tf.num, tf.rden, a1);
+                            else a0 = fmaf(tf.num, tf.rden, a0);
+                        }
+                    }
+                }
+                for (; j < n; ++j) {
+                    float4 g = trow[j];
+                    EmFrac tf = em_frac(g.x, g.y, g.z, c);
+                    if (j != i) a0 = fmaf(tf.num, tf.rden, a0);
+                }
+                float sum = a0 + a1;
+                float fnew = __fdiv_rn(sum, inv_div);
+                float d = fnew - f;
+                ssq += d * d;
+                *fp = fnew;
+            }
+        }
+    }
+    __syncthreads();
+    red[t] = ssq;
+    __syncthreads();
+    if (t < n) {
+        double v = 0.0;
+        for (int q = 0; q < rows_per_pass; ++q) v += (double)red[q * n + t];
+        partials[(long)blockIdx.x * ldg + col0 + t] = v;
+    }
+}
+
+// ssq[p] = sum over blocks (fixed order) of partials[block][p]
+__global__ void em_ssq_reduce_kernel(const double* __restrict__ partials, int nblocks, int np, int ld,
+                                     double* __restrict__ ssq)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        double v = 0.0;
+        for (int b = 0; b < nblocks; ++b) v += partials[(long)b * ld + p];
+        ssq[p] = v;
+    }
+}
+
+// Stop rule of emMAF.py:21-25 with rmse1d's float divide / double sqrt (emMAF_cy.pyx:32-33).
+// count[p] = number of sites in problem p's sum.  Single block.
+__global__ void em_decide_kernel(const double* __restrict__ ssq, const double* __restrict__ count, double count_all,
+                                 int np, double tole, int iteration,
+                                 int* __restrict__ active, int* __restrict__ iters, int* __restrict__ n_active)
+{
+    __shared__ int sh_cnt;
+    if (threadIdx.x == 0) sh_cnt = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int p = threadIdx.x; p < np; p += blockDim.x) {
+        if (!active[p]) continue;
+        double cnt = count ? count[p] : count_all;
+        float res = (float)ssq[p];
+        res = res / (float)cnt;
+        double diff = sqrt((double)res);
+        if (diff < tole) { active[p] = 0; iters[p] = iteration; }
+        else ++mine;
+    }
+    atomicAdd(&sh_cnt, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *n_active = sh_cnt;
+}
+
+__global__ void fill_kernel(float* __restrict__ p, long n, float v)
+{
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = v;
+}
+
+// F[s][c] <- row[c] for c < ncols: start state of the leave-one-out EM
+__global__ void bcast_row_kernel(float* __restrict__ F, int ld, int ncols, long M, const float* __restrict__ row)
+{
+    long total = M * (long)ncols;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long s = e / ncols;
+        int c = (int)(e - s * ncols);
+        F[s * (long)ld + c] = row[c];
+    }
+}
+
+// F[s][c] <- clamp(F[s][c], lo[c], hi[c]) for c < ncols (WGSassign.py:236-240, glassy.py:80-85)
+__global__ void clip_cols_kernel(float* __restrict__ F, int ld, int ncols, long M,
+                                 const float* __restrict__ lo, const float* __restrict__ hi)
+{
+    long total = M * (long)ncols;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long s = e / ncols;
+        int c = (int)(e - s * ncols);
+        float* p = F + s * (long)ld + c;
+        float v = *p;
+        if (v < lo[c]) v = lo[c];
+        if (v > hi[c]) v = hi[c];
+        *p = v;
+    }
+}
+
+// dst[s][j] = src[s][cols[j]] (j < nc): column gather between row-major float matrices
+__global__ void gather_cols_kernel(const float* __restrict__ src, int lds, const int* __restrict__ cols, int nc,
+                                   float* __restrict__ dst, int ldd, int dst_col0, long M)
+{
+    long total = M * (long)nc;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long s = e / nc;
+        int j = (int)(e - s * nc);
+        int c = cols[j];
+        if (c >= 0) dst[s * (long)ldd + dst_col0 + j] = src[s * (long)lds + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// fisher: observed Fisher information per (site, population), the effective sample size
+// n-tilde, and every individual's own n-tilde sum, in ONE pass over G (fisher_cy.pyx:12-65;
+// fisher.py:11-59 makes N+K passes).  Warp per site; lanes stride over each population's
+// slab.  HBM-bound: 8 B per (site, individual) in, 8 B per (site, population) out.
+// Per-individual sums live in a per-warp private shared-memory row (no atomics), reduced
+// over warps then over blocks in fixed order.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float fisher_term(float g0, float g1, float th, float om)
+{
+    float g2 = third_gl(g0, g1);
+    float u = fmaf(g0, om * om, fmaf(g1, 2.0f * th * om, g2 * th * th));
+    float n1 = 2.0f * ((g0 + g2) - 2.0f * g1);
+    float n2 = fmaf(th, n1, 2.0f * (g1 - g0));
+    float x = __fdiv_rn(n2, u), y = __fdiv_rn(n1, u);
+    return fmaf(x, x, -y);
+}
+
+__global__ void __launch_bounds__(256)
+fisher_kernel(const float2* __restrict__ G, int ldg, long M,
+              const PopDesc* __restrict__ pops, int K,
+              const float* __restrict__ A,                 // [M][K]
+              float* __restrict__ f_obs, float* __restrict__ ne_obs,   // [M][K]
+              int warps_per_block,
+              double* __restrict__ ind_partials)           // [gridDim.x][ldg]
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* accw = reinterpret_cast<float*>(smem_raw);      // [warps][ldg]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* mine = accw + (size_t)warp * ldg;
+    for (int c = lane; c < ldg; c += 32) mine[c] = 0.f;
+    __syncwarp();
+    for (long s = (long)blockIdx.x * warps_per_block + warp; s < M; s += (long)gridDim.x * warps_per_block) {
+        const float2* row = G + s * (long)ldg;
+        for (int k = 0; k < K; ++k) {
+            PopDesc pd = pops[k];
+            float th = __ldg(&A[s * K + k]);
+            float om = 1.0f - th;
+            float w = 0.5f * th * om;
+            float sum = 0.f;
+            for (int j = lane; j < pd.n; j += 32) {
+                float2 g = ld_stream2(&row[pd.col0 + j]);
+                float term = fisher_term(g.x, g.y, th, om);
+                sum += term;
+                mine[pd.col0 + j] += term * w;
+            }
+            sum = warp_sum(sum);
+            if (lane == 0) {
+                f_obs[s * K + k] = sum;
+                ne_obs[s * K + k] = 0.5f * sum * th * om;
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < ldg; c += blockDim.x) {
+        double v = 0.0;
+        for (int w = 0; w < warps_per_block; ++w) v += (double)accw[(size_t)w * ldg + c];
+        ind_partials[(long)blockIdx.x * ldg + c] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// synthetic data (benchmarks): SURVEY 8d model with a counter-based hash, generated in the
+// device layout.  AF of population k at site s is an arcsine-distributed value clipped to
+// [0.02, 0.98]; genotype = two Bernoulli draws; depth ~ Poisson(depth) by CDF inversion;
+// alt reads = Bernoulli(e | 0.5 | 1-e) per read; GL normalised and rounded to 6 decimals.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01(uint64_t h) { return (float)((h >> 40) + 0.5f) * (1.0f / 16777216.0f); }
+
+__device__ __forceinline__ float synth_af(uint64_t seed, long site, int k) {
+    float u = u01(mix64(seed ^ mix64((uint64_t)site * 1315423911ull + (uint64_t)k * 2654435761ull + 17)));
+    float sn = sinpif(0.5f * u);
+    float p = sn * sn;
+    return fminf(fmaxf(p, 0.02f), 0.98f);
+}
+
+__global__ void synth_kernel(float2* __restrict__ G, uchar2* __restrict__ AD, int ldg, long M,
+                             const int* __restrict__ ind_of_col, const int* __restrict__ pop_of_col,
+                             uint64_t seed, float depth, long site_offset)
+{
+    long total = M * (long)ldg;
+    const float e = 0.01f;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        long s = idx / ldg;
+        int c = (int)(idx - s * ldg);
+        int ind = ind_of_col[c];
+        float2 gl = make_float2(0.f, 0.f);
+        uchar2 ad = make_uchar2(0, 0);
+        if (ind >= 0) {
+            long gs = site_offset + s;
+            float p = synth_af(seed, gs, pop_of_col[c]);
+            uint64_t h = mix64(seed ^ mix64((uint64_t)gs * 0x100000001B3ull + (uint64_t)ind));
+            int geno = (u01(h) < p) + (u01(mix64(h + 1)) < p);
+            // Poisson by inversion
+            float u = u01(mix64(h + 2));
+            float pk = expf(-depth), cdf = pk;
+            int D = 0;
+            while (u > cdf && D < 60) { ++D; pk *= depth / D; cdf += pk; }
+            float pa = geno == 0 ? e : (geno == 1 ? 0.5f : 1.0f - e);
+            int alt = 0;
+            for (int rd = 0; rd < D; ++rd) alt += (u01(mix64(h + 3 + rd)) < pa);
+            int ref = D - alt;
+            double l0 = pow(1.0 - (double)e, ref) * pow((double)e, alt);
+            double l1 = pow(0.5, D);
+            double l2 = pow(1.0 - (double)e, alt) * pow((double)e, ref);
+            double tot = l0 + l1 + l2;
+            gl.x = (float)(rint(l0 / tot * 1e6) * 1e-6);
+            gl.y = (float)(rint(l1 / tot * 1e6) * 1e-6);
+            ad = make_uchar2((unsigned char)ref, (unsigned char)alt);
+        }
+        G[idx] = gl;
+        if (AD) AD[idx] = ad;
+    }
+}
+
+}  // namespace wgs

@@ -1,0 +1,97 @@
+"""Site sharding across the GPUs of one node.
+
+One process per GPU (`torchrun`); every rank holds a contiguous range of sites.  Every
+kernel is independent per site, so the only exchanges are tiny: the per-problem sum of
+squared AF changes once per EM iteration (so that all ranks stop at the reference's global
+iteration, emMAF.py:21-25), the allele-depth class tallies of the z-score, and the final
+per-individual x per-population float64 partial sums.  Partials are all-gathered and
+summed in rank order, so a result does not depend on reduction timing.
+
+`torch.distributed` is the plumbing (NCCL over NVLink on GPUs, gloo in CPU tests).
+"""
+import numpy as np
+
+_cfg = {"enabled": False, "rank": 0, "world": 1, "M_total": None, "offset": 0, "device": None}
+
+
+def shard_range(M, rank, world):
+    """Contiguous site range [lo, hi) of `rank` out of `world`."""
+    lo = (M * rank) // world
+    hi = (M * (rank + 1)) // world
+    return lo, hi
+
+
+def enable(M_total, offset, device=None):
+    """Declare that this process holds sites [offset, offset+M_local) of M_total."""
+    import torch.distributed as td
+    if not td.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    _cfg.update(enabled=True, rank=td.get_rank(), world=td.get_world_size(), M_total=int(M_total),
+                offset=int(offset), device=device)
+
+
+def disable():
+    _cfg.update(enabled=False, rank=0, world=1, M_total=None, offset=0, device=None)
+
+
+def enabled():
+    return _cfg["enabled"] and _cfg["world"] > 1
+
+
+def rank():
+    return _cfg["rank"]
+
+
+def world():
+    return _cfg["world"]
+
+
+def total_sites(M_local):
+    return _cfg["M_total"] if _cfg["enabled"] else M_local
+
+
+def allreduce_sum(arr):
+    """In-place sum of a float64/int64 NumPy array across ranks: all-gather, then a
+    rank-ordered sum (deterministic for a given world size)."""
+    if not enabled():
+        return arr
+    import torch
+    import torch.distributed as td
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    dev = _cfg["device"]
+    if dev is not None:
+        t = t.to(dev)
+    bufs = [torch.empty_like(t) for _ in range(_cfg["world"])]
+    td.all_gather(bufs, t)
+    acc = bufs[0].clone()
+    for b in bufs[1:]:
+        acc += b
+    arr[...] = acc.cpu().numpy().reshape(arr.shape)
+    return arr
+
+
+def gather_rows(arr):
+    """Concatenate per-rank row blocks (per-site outputs such as the AF matrix) on every rank."""
+    if not enabled():
+        return arr
+    import torch
+    import torch.distributed as td
+    dev = _cfg["device"]
+    counts = [shard_range(_cfg["M_total"], r, _cfg["world"]) for r in range(_cfg["world"])]
+    out = []
+    for r, (lo, hi) in enumerate(counts):
+        shape = (hi - lo,) + tuple(arr.shape[1:])
+        t = torch.from_numpy(np.ascontiguousarray(arr)) if r == _cfg["rank"] else torch.empty(shape, dtype=torch.from_numpy(arr[:0]).dtype)
+        if dev is not None:
+            t = t.to(dev)
+        td.broadcast(t, src=r)
+        out.append(t.cpu().numpy())
+    return np.concatenate(out, axis=0)
+
+
+def attach(ctx):
+    """Give a Context the shard geometry and the all-reduce callback."""
+    if enabled():
+        ctx.set_shard(_cfg["M_total"], _cfg["offset"], allreduce_sum)
+    else:
+        ctx.set_shard(-1, 0, None)

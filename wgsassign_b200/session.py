@@ -1,0 +1,82 @@
+"""Resident-matrix cache behind the drop-in entry points.
+
+The reference's drivers take the GL matrix as a NumPy array on every call.  Re-uploading
+it for each of `--get_reference_af`, `--ne_obs` and `--loo` would triple the PCIe traffic,
+so the entry points ask this module for a :class:`~wgsassign_b200._lib.Context` that
+already holds the matrix; it is re-uploaded only when the array (address, shape, sampled
+checksum) or the population assignment changes.
+"""
+import os
+
+import numpy as np
+
+from . import _lib
+from . import dist
+
+_state = {"ctx": None, "key": None, "ds_key": None, "ad_key": None}
+
+
+def device_index():
+    return int(os.environ.get("LOCAL_RANK", os.environ.get("WGS_DEVICE", "0")))
+
+
+def _sig(a):
+    """Cheap identity of an array's contents: address, shape and a strided sample."""
+    flat = a.reshape(-1)
+    step = max(1, flat.shape[0] // 4096)
+    sample = flat[::step]
+    return (a.ctypes.data, a.shape, a.dtype.str, float(np.sum(sample, dtype=np.float64)))
+
+
+def pops_from_ids(IDs):
+    """(pop_of_ind int32 [N], pops) with populations in np.unique order (WGSassign.py:213)."""
+    pops, inv = np.unique(IDs[:, 1], return_inverse=True)
+    return inv.astype(np.int32), pops
+
+
+def context(L, pop_of_ind=None, K=0):
+    """Context holding `L` repacked for the given population assignment (None = flat)."""
+    pkey = None if pop_of_ind is None else (int(K), np.asarray(pop_of_ind, np.int32).tobytes())
+    key = (_sig(L), pkey)
+    ctx = _state["ctx"]
+    if ctx is not None and _state["key"] == key:
+        return ctx
+    if ctx is None:
+        ctx = _lib.Context(device_index())
+        _state["ctx"] = ctx
+    n = L.shape[1] // 2
+    if pop_of_ind is None:
+        ctx.set_pops(np.zeros(n, np.int32), 0)
+    else:
+        if len(pop_of_ind) != n:
+            raise ValueError("Number of individuals in beagle and reference ID file do not match!")
+        ctx.set_pops(pop_of_ind, K)
+    ctx.upload_gl(L, 0)
+    dist.attach(ctx)
+    _state["key"] = key
+    _state["ds_key"] = None
+    _state["ad_key"] = None
+    return ctx
+
+
+def with_downsampled(ctx, L_ds):
+    key = _sig(L_ds)
+    if _state["ds_key"] != key:
+        ctx.upload_gl(L_ds, 1)
+        _state["ds_key"] = key
+    return ctx
+
+
+def with_ad(ctx, AD):
+    key = _sig(AD)
+    if _state["ad_key"] != key:
+        ctx.upload_ad(np.ascontiguousarray(AD, dtype=np.int32))
+        _state["ad_key"] = key
+    return ctx
+
+
+def reset():
+    ctx = _state["ctx"]
+    if ctx is not None:
+        ctx.close()
+    _state.update(ctx=None, key=None, ds_key=None, ad_key=None)
