@@ -1,0 +1,62 @@
+#include <cuda_runtime.h>
+#include <cstdio>
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c){
+  unsigned long long ra,rb,rc,rd;
+  ra = ((unsigned long long)__float_as_uint(a.y)<<32)|__float_as_uint(a.x);
+  rb = ((unsigned long long)__float_as_uint(b.y)<<32)|__float_as_uint(b.x);
+  rc = ((unsigned long long)__float_as_uint(c.y)<<32)|__float_as_uint(c.x);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra),"l"(rb),"l"(rc));
+  return make_float2(__uint_as_float((unsigned)rd), __uint_as_float((unsigned)(rd>>32)));
+}
+template<int MODE>
+__global__ void k(float* out, float x, int iters){
+  float2 a0=make_float2(x,x+1), a1=make_float2(x+2,x+3), a2=make_float2(x+4,x+5), a3=make_float2(x+6,x+7);
+  float2 a4=make_float2(x,x+1.5f), a5=make_float2(x+2,x+3.5f), a6=make_float2(x+4,x+5.5f), a7=make_float2(x+6,x+7.5f);
+  float2 b=make_float2(1.0001f,0.9999f), c=make_float2(0.001f,0.002f);
+  for(int i=0;i<iters;i++){
+    if(MODE==0){
+#pragma unroll
+      for(int u=0;u<4;u++){
+      a0=ffma2(a0,b,c);a1=ffma2(a1,b,c);a2=ffma2(a2,b,c);a3=ffma2(a3,b,c);
+      a4=ffma2(a4,b,c);a5=ffma2(a5,b,c);a6=ffma2(a6,b,c);a7=ffma2(a7,b,c);}
+    } else if (MODE==1) {
+#pragma unroll
+      for(int u=0;u<4;u++){
+      a0.x=fmaf(a0.x,b.x,c.x);a0.y=fmaf(a0.y,b.y,c.y);a1.x=fmaf(a1.x,b.x,c.x);a1.y=fmaf(a1.y,b.y,c.y);
+      a2.x=fmaf(a2.x,b.x,c.x);a2.y=fmaf(a2.y,b.y,c.y);a3.x=fmaf(a3.x,b.x,c.x);a3.y=fmaf(a3.y,b.y,c.y);
+      a4.x=fmaf(a4.x,b.x,c.x);a4.y=fmaf(a4.y,b.y,c.y);a5.x=fmaf(a5.x,b.x,c.x);a5.y=fmaf(a5.y,b.y,c.y);
+      a6.x=fmaf(a6.x,b.x,c.x);a6.y=fmaf(a6.y,b.y,c.y);a7.x=fmaf(a7.x,b.x,c.x);a7.y=fmaf(a7.y,b.y,c.y);}
+    } else if (MODE==2) { // MUFU rcp
+#pragma unroll
+      for(int u=0;u<4;u++){
+      asm volatile("rcp.approx.ftz.f32 %0,%0;":"+f"(a0.x));asm volatile("rcp.approx.ftz.f32 %0,%0;":"+f"(a0.y));
+      asm volatile("rcp.approx.ftz.f32 %0,%0;":"+f"(a1.x));asm volatile("rcp.approx.ftz.f32 %0,%0;":"+f"(a1.y));
+      asm volatile("rcp.approx.ftz.f32 %0,%0;":"+f"(a2.x));asm volatile("rcp.approx.ftz.f32 %0,%0;":"+f"(a2.y));
+      asm volatile("rcp.approx.ftz.f32 %0,%0;":"+f"(a3.x));asm volatile("rcp.approx.ftz.f32 %0,%0;":"+f"(a3.y));}
+    } else { // mixed: 1 MUFU + 4 FFMA2 per group
+#pragma unroll
+      for(int u=0;u<4;u++){
+      asm volatile("rcp.approx.ftz.f32 %0,%0;":"+f"(a0.x)); a1=ffma2(a1,b,c);a2=ffma2(a2,b,c);a3=ffma2(a3,b,c);a4=ffma2(a4,b,c);
+      asm volatile("rcp.approx.ftz.f32 %0,%0;":"+f"(a0.y)); a5=ffma2(a5,b,c);a6=ffma2(a6,b,c);a7=ffma2(a7,b,c);a1=ffma2(a1,b,c);}
+    }
+  }
+  out[blockIdx.x*blockDim.x+threadIdx.x]=a0.x+a0.y+a1.x+a1.y+a2.x+a2.y+a3.x+a3.y+a4.x+a4.y+a5.x+a5.y+a6.x+a6.y+a7.x+a7.y;
+}
+template<int MODE> double run(float* d, int iters, double opsPerIter){
+  cudaEvent_t e0,e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k<MODE><<<148*8,256>>>(d,1.0f,10);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0); k<MODE><<<148*8,256>>>(d,1.0f,iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms,e0,e1);
+  double ops = (double)148*8*256*iters*opsPerIter;
+  return ops/(ms*1e-3);
+}
+int main(){
+  float* d; cudaMalloc(&d, 148*8*256*4);
+  int it=20000;
+  printf("FFMA2 : %.3e packed-instr-lanes/s (x2 FMAs)\n", run<0>(d,it,32));
+  printf("FFMA  : %.3e instr-lanes/s\n", run<1>(d,it,64));
+  printf("MUFU  : %.3e rcp/s\n", run<2>(d,it,32));
+  printf("MIX   : %.3e groups/s (1 rcp + 4 ffma2)\n", run<3>(d,it,8));
+  return 0;
+}

@@ -422,24 +422,31 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* Fpop, std::vector<int
     return 0;
 }
 
-struct LooLaunch { int block, rows_per_pass, passes; size_t smem; };
-LooLaunch loo_cfg(int n, int ni)
+struct LooLaunch { int block, rows_per_pass, passes, grid; size_t smem; };
+int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
 {
-    LooLaunch best{0, 0, 1, 0};
+    LooLaunch best{0, 0, 1, 0, 0};
     double best_u = -1;
     for (int bd = 128; bd <= 512; bd += 32) {
-        int rpp = bd / ni;
+        int rpp = bd / n;
         if (rpp < 1) continue;
-        double u = (double)(rpp * ni) / bd;
-        if (u > best_u + 1e-9 || (std::fabs(u - best_u) < 1e-9 && bd <= 256)) { best_u = u; best.block = bd; best.rows_per_pass = rpp; }
+        double u = (double)(rpp * n) / bd;
+        if (u > best_u + 1e-9) { best_u = u; best.block = bd; best.rows_per_pass = rpp; }
     }
-    int stride = n | 1;
-    size_t row_bytes = (size_t)stride * sizeof(float4);
-    int max_rows = (int)std::max<size_t>(1, (size_t)(64 * 1024) / row_bytes);
-    int passes = std::max(1, std::min(16, max_rows / std::max(1, best.rows_per_pass)));
+    if (best.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (512)", n);
+    int np = (n + 1) / 2, stride = np | 1;
+    size_t row_bytes = (size_t)stride * 24;                     // 16 B (g0,g1 pairs) + 8 B (g2 pair) per pair
+    int passes = kLooMaxPasses;
+    while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 20 * 1024) --passes;
     best.passes = passes;
     best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float);
-    return best;
+    if (best.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", n);
+    if (best.smem > 48 * 1024) CU(cudaFuncSetAttribute(loo_em_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step_kernel, best.block, best.smem));
+    best.grid = ctx->num_sm * std::max(occ, 1);
+    *out = best;
+    return 0;
 }
 
 // Leave-one-out EM for every individual on the resident G.  F [M][ldf] (device): columns
@@ -452,7 +459,13 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     std::vector<int> active0(ldg, 0);
     for (int c = 0; c < ldg; ++c)
         if (ctx->ind_of_col[c] >= 0 && ctx->pops[ctx->pop_of_col[c]].n > 1) active0[c] = 1;
-    int nblocks = ctx->num_sm * 2;
+    std::vector<LooLaunch> cfgs(K);
+    int nblocks = 1;
+    for (int k = 0; k < K; ++k) {
+        if (ctx->pops[k].n <= 1) continue;
+        if (loo_cfg(ctx, ctx->pops[k].n, &cfgs[k])) return 1;
+        nblocks = std::max(nblocks, cfgs[k].grid);
+    }
     EmState st;
     if (em_state_init(ctx, st, ldg, ldg, nblocks, active0)) return 1;
     {   // f = 0.25 everywhere; NaN for the (degenerate) single-member populations, like 0/0 in the reference
@@ -474,13 +487,10 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
             bool any = false;
             for (int j = 0; j < pd.n; ++j) any = any || st.h_active[pd.col0 + j];
             if (!any) continue;
-            LooLaunch lc = loo_cfg(pd.n, pd.n);
-            if (lc.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (512)", pd.n);
-            if (lc.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", pd.n);
-            if (lc.smem > 48 * 1024) CU(cudaFuncSetAttribute(loo_em_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
+            const LooLaunch& lc = cfgs[k];
             int TS = lc.rows_per_pass * lc.passes;
             long ntiles = (M + TS - 1) / TS;
-            LAUNCH("loo_em", loo_em_step_kernel, nblocks, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
+            LAUNCH("loo_em", loo_em_step_kernel, lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
                    lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
             {   // the population's GL tile once + read/write of every active problem's f; n evaluations per active (site, problem)
                 double act = 0;

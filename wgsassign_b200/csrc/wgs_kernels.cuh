@@ -48,6 +48,38 @@ __device__ __forceinline__ float fast_rcp(float x) {
     return r;
 }
 
+// Packed FP32x2 arithmetic (Blackwell FFMA2/FMUL2): two independent FP32 lanes per 64-bit
+// register.  Measured on B200 (scripts/microbench/issue_rates.cu): FFMA2 issues at half the
+// FFMA rate, i.e. the same FLOP/s for half the issue slots - which is what an issue-bound
+// kernel needs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -448,15 +480,27 @@ em_pop_step_kernel(const float2* __restrict__ G, int ldg, long M,
 // loo_em_step: ONE EM iteration of every still-active leave-one-out problem of ONE
 // population (glassy.py:65-78: emMAF on the population minus individual i, for every i).
 // Problem i at site s follows its own trajectory f_i, so each (site, i) evaluates all n
-// posterior terms at f_i and removes its own: n^2 evaluations per site and iteration from
-// ONE read of the population's GL tile (staged in shared memory as (g0,g1,g2) float4,
-// read back as 128-bit broadcasts).  Bound by the MUFU reciprocal rate, not by HBM.
+// posterior terms at f_i: n^2 evaluations per site and iteration from ONE read of the
+// population's GL tile.  The tile is staged in shared memory by PAIRS of individuals,
+//   tA[site][pair] = {(g0_a,g0_b), (g1_a,g1_b)}   (128-bit)   tB[site][pair] = (g2_a,g2_b) (64-bit)
+// so that the four multiply-adds of two posterior terms issue as FMUL2 + 3 FFMA2; the two
+// reciprocals (MUFU.RCP) and the two accumulating FFMAs stay scalar.  All lanes of a warp
+// that share a site read the same address (broadcast).  Bound by the MUFU reciprocal rate
+// (16 per clock per SM), not by HBM.
+//
+// The left-out individual's own term is removed after the loop.  (sum - own) can cancel to
+// exactly 0 when nobody else carries the allele, and an exact 0 (or 1) would turn the next
+// iteration's 0 * inf into NaN where the reference stays finite, so f is kept inside
+// [1e-12, 1-2^-24]; both are far outside the clipping range applied afterwards
+// (glassy.py:80-85) and 7 orders below the 1e-5 parity tolerance.
+//
 // Thread t < Bp owns problem i = t % n for the whole launch, so its squared change is a
 // register; partials[block][col] are reduced in fixed order by em_ssq_reduce_kernel.
 // mask (optional): uchar keep[M][ldg] - sites whose squared change counts (reference
 // z-score runs the EM on kept sites only, WGSassign.py:358-359; a site outside the mask
 // cannot influence another site, so it is simply skipped).
 // ---------------------------------------------------------------------------------------
+constexpr int kLooMaxPasses = 4;
 __global__ void __launch_bounds__(512)
 loo_em_step_kernel(const float2* __restrict__ G, int ldg, long M,
                    int col0, int n, int rows_per_pass, int passes,
@@ -467,68 +511,87 @@ loo_em_step_kernel(const float2* __restrict__ G, int ldg, long M,
                    long ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* tile = reinterpret_cast<float4*>(smem_raw);
-    const int stride = n | 1;                                   // odd float4 stride: rows never share a bank group
+    const int np = (n + 1) >> 1;                                // pairs of individuals
+    const int stride = np | 1;                                  // odd: two rows never share a bank group
     const int TS = rows_per_pass * passes;
-    float* red = reinterpret_cast<float*>(tile + (size_t)TS * stride);   // [blockDim.x]
+    ulonglong2* tA = reinterpret_cast<ulonglong2*>(smem_raw);                   // [TS][stride]
+    f32x2* tB = reinterpret_cast<f32x2*>(tA + (size_t)TS * stride);             // [TS][stride]
+    float* red = reinterpret_cast<float*>(tB + (size_t)TS * stride);            // [blockDim.x]
 
     const int t = threadIdx.x;
     const int Bp = rows_per_pass * n;
     const int i = t % n, r = t / n;
     const bool worker = t < Bp;
     const bool my_active = worker && active[col0 + i] != 0;
-    const float inv_div = (float)(n - 1);
+    const float divisor = (float)(n - 1);
     float ssq = 0.f;
 
     for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         const long s0 = tl * TS;
-        __syncthreads();
-        for (int e = t; e < TS * n; e += blockDim.x) {
-            int sl = e / n, j = e - sl * n;
+        // this thread's f values for the tile: issued before the tile fill so that their
+        // latency overlaps it
+        float fv[kLooMaxPasses];
+        bool ok[kLooMaxPasses];
+#pragma unroll
+        for (int p = 0; p < kLooMaxPasses; ++p) {
+            long s = s0 + p * rows_per_pass + r;
+            ok[p] = my_active && p < passes && s < M;
+            if (ok[p] && mask) ok[p] = mask[s * (long)ldg + col0 + i] != 0;
+            fv[p] = 0.25f;
+            if (ok[p]) fv[p] = F[s * (long)ldf + col0 + i];
+        }
+        __syncthreads();                                        // previous tile fully consumed
+        for (int e = t; e < TS * np; e += blockDim.x) {
+            int sl = e / np, q = e - sl * np;
             long s = s0 + sl;
-            float2 g = make_float2(1.0f / 3, 1.0f / 3);
-            if (s < M) g = ld_stream2(&G[s * (long)ldg + col0 + j]);
-            tile[sl * stride + j] = make_float4(g.x, g.y, third_gl(g.x, g.y), 0.f);
+            float4 g = make_float4(1.f, 0.f, 1.f, 0.f);
+            if (s < M) g = ld_stream4(reinterpret_cast<const float4*>(&G[s * (long)ldg + col0 + 2 * q]));
+            if (2 * q + 1 >= n) { g.z = 1.f; g.w = 0.f; }       // odd n: the pad partner contributes exactly 0
+            ulonglong2 a;
+            a.x = pack2(g.x, g.z);
+            a.y = pack2(g.y, g.w);
+            tA[sl * stride + q] = a;
+            tB[sl * stride + q] = pack2(third_gl(g.x, g.y), third_gl(g.z, g.w));
         }
         __syncthreads();
-        if (my_active) {
-            for (int p = 0; p < passes; ++p) {
-                int sl = p * rows_per_pass + r;
-                long s = s0 + sl;
-                if (s >= M) break;
-                if (mask && !mask[s * (long)ldg + col0 + i]) continue;
-                float* fp = F + s * (long)ldf + col0 + i;
-                float f = *fp;
-                EmCoef c = em_coef(f);
-                const float4* trow = tile + sl * stride;
-                // The left-out individual is skipped by predication, not subtracted afterwards:
-                // sum-minus-own cancels to 0 when the others contribute ~nothing, and an exact
-                // f = 0 turns the next iteration's 0/0 into NaN where the reference stays finite.
-                float a0 = 0.f, a1 = 0.f;
-                int j = 0;
-                for (; j + 8 <= n; j += 8) {
-                    const int d = i - j;                  // own index relative to this block of 8
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        float4 g = trow[j + u];
-                        EmFrac tf = em_frac(g.x, g.y, g.z, c);
-                        if (d != u) {
-                            if (u & 1) a1 = fmaf(tf.num, tf.rden, a1);
-                            else a0 = fmaf(tf.num, tf.rden, a0);
-                        }
-                    }
-                }
-                for (; j < n; ++j) {
-                    float4 g = trow[j];
-                    EmFrac tf = em_frac(g.x, g.y, g.z, c);
-                    if (j != i) a0 = fmaf(tf.num, tf.rden, a0);
-                }
-                float sum = a0 + a1;
-                float fnew = __fdiv_rn(sum, inv_div);
-                float d = fnew - f;
-                ssq += d * d;
-                *fp = fnew;
+        for (int p = 0; p < kLooMaxPasses; ++p) {
+            if (!ok[p]) continue;
+            const int sl = p * rows_per_pass + r;
+            const float f = fv[p];
+            const float om = 1.0f - f;
+            const float H0 = 2.0f * om * om, H1 = 2.0f * f * om, H2 = 2.0f * f * f;
+            const f32x2 H0p = pack2(H0, H0), H1p = pack2(H1, H1), H2p = pack2(H2, H2);
+            const ulonglong2* rowA = tA + sl * stride;
+            const f32x2* rowB = tB + sl * stride;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+            for (int q = 0; q < np; ++q) {
+                ulonglong2 ab = rowA[q];
+                f32x2 num = ffma2(ab.y, H1p, fmul2(rowB[q], H2p));
+                f32x2 den = ffma2(ab.x, H0p, ffma2(ab.y, H1p, num));
+                float2 nn = unpack2(num), dd = unpack2(den);
+                a0 = fmaf(nn.x, fast_rcp(dd.x), a0);
+                a1 = fmaf(nn.y, fast_rcp(dd.y), a1);
             }
+            // own term, recomputed with the same operations so that it cancels what was added
+            float own;
+            {
+                ulonglong2 ab = rowA[i >> 1];
+                float2 g0 = unpack2(ab.x), g1 = unpack2(ab.y), g2 = unpack2(rowB[i >> 1]);
+                bool hi = i & 1;
+                float x0 = hi ? g0.y : g0.x, x1 = hi ? g1.y : g1.x, x2 = hi ? g2.y : g2.x;
+                float num = fmaf(x1, H1, x2 * H2);
+                float den = fmaf(x0, H0, fmaf(x1, H1, num));
+                own = num * fast_rcp(den);
+            }
+            float sum = (a0 + a1) - own;
+            float fnew = __fdiv_rn(sum, divisor);
+            if (fnew < 1e-12f) fnew = 1e-12f;                  // comparisons are false for NaN: NaN survives
+            if (fnew > 0.99999994f) fnew = 0.99999994f;
+            float d = fnew - f;
+            ssq += d * d;
+            F[(s0 + sl) * (long)ldf + col0 + i] = fnew;
         }
     }
     __syncthreads();
@@ -547,7 +610,15 @@ __global__ void em_ssq_reduce_kernel(const double* __restrict__ partials, int nb
 {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
         double v = 0.0;
-        for (int b = 0; b < nblocks; ++b) v += partials[(long)b * ld + p];
+        int b = 0;
+        for (; b + 8 <= nblocks; b += 8) {                      // 8 independent loads in flight, fixed add order
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = partials[(long)(b + u) * ld + p];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += x[u];
+        }
+        for (; b < nblocks; ++b) v += partials[(long)b * ld + p];
         ssq[p] = v;
     }
 }
