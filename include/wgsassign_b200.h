@@ -133,10 +133,16 @@ int32_t wgs_zscore(wgs_ctx *ctx, int32_t mode, const float *af, int32_t K, int32
                    int32_t single_read, int32_t ind_start, int32_t ind_end, int32_t iter,
                    double tole, wgs_zrow *out);
 
-/* Per-individual allele-depth class table of the last wgs_zscore call, for tally parity:
- * rows of (ref, alt, depth, n_loci) in first-occurrence order restricted to kept classes. */
+/* Per-individual allele-depth class table (the reference's AD_array, zscore.py:39) of the last
+ * wgs_zscore call, for tally parity: rows of (ref, alt, depth, n_loci) ordered by (depth, alt).
+ * The reference's row order is first occurrence in the file; no output depends on it. */
 int32_t wgs_zscore_classes(wgs_ctx *ctx, int32_t ind, int32_t max_rows, int32_t *rows_out,
                            int32_t *n_rows);
+
+/* Number of (site, individual) pairs of the last wgs_zscore call whose read depth exceeded
+ * the dense class table (40 reads); such sites are treated as "class not kept", which is what
+ * the reference does unless every one of the depth+1 splits of that depth was observed. */
+int64_t wgs_zscore_deep_sites(const wgs_ctx *ctx);
 
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */

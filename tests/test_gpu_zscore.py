@@ -1,0 +1,103 @@
+"""GPU parity of the z-score path against the golden fixture produced by the reference CLI
+(tests/golden/zscore.npz) and against the oracle on other seeds.
+
+Bit-exact: loci kept, allele-depth class tallies (AD_array rows), EM iteration counts.
+1e-6 relative: the three float32 components (W_obs, z_mu, z_var).  z itself is the
+difference of two sums of magnitude ~|W| divided by sqrt(var), so its tolerance is the
+propagated component tolerance (hard part 4).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def zs():
+    import wgsassign_b200._lib as _lib
+    if _lib.lib().wgs_device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box")
+    from wgsassign_b200 import session, zscore
+    session.reset()
+    yield zscore
+    session.reset()
+
+
+def sort_rows(a):
+    a = np.asarray(a).reshape(-1, 4)
+    return a[np.lexsort((a[:, 1], a[:, 2]))]
+
+
+def check_rows(got, ref_z, ref_comp, ref_loci, ref_classes=None):
+    for j, r in enumerate(got):
+        assert r["loci_kept"] == ref_loci[j]
+        w, mu, var = ref_comp[j]
+        for a, b in ((r["w_obs"], w), (r["z_mu"], mu), (r["z_var"], var)):
+            assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b)), (j, a, b)
+        tol = 2e-6 * (abs(w) + abs(mu)) / np.sqrt(var) + 1e-5 * abs(ref_z[j])
+        assert abs(float(r["z"]) - ref_z[j]) <= tol, (j, r["z"], ref_z[j], tol)
+        if ref_classes is not None:
+            assert np.array_equal(sort_rows(r["AD_array"]), sort_rows(ref_classes[j]))
+
+
+def test_assignment_zscore_golden(zs, zgold):
+    L, AD, IDs, af = zgold["L"], zgold["AD"].astype(np.int32), zgold["IDs"], zgold["af"]
+    pops = np.unique(IDs[:, 1])
+    got = zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops)
+    ref_z = [float(x) for x in str(zgold["z_assign_txt"]).split()]
+    comp = zgold["z_assign_components"]
+    check_rows(got, ref_z, comp[:, :3], list(zgold["z_assign_loci"]), [zgold["AD_array_%d" % i] for i in range(12)])
+    assert [r["loci_kept"] for r in got] == [int(x) for x in comp[:, 3]]
+
+
+def test_assignment_zscore_thresholds(zs, zgold, oracle_mod):
+    L, AD, IDs, af = zgold["L"], zgold["AD"].astype(np.int32), zgold["IDs"], zgold["af"]
+    pops = np.unique(IDs[:, 1])
+    got = zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops, n_threshold=25, ind_start=2, ind_end=9)
+    ref = oracle_mod.zscore_assignment(L, AD, af, IDs, pops, n_threshold=25, ind_start=2, ind_end=9)
+    assert ["%.7f" % r["z"] for r in ref] == str(zgold["z_assign_thr25_txt"]).split()
+    check_rows(got, [float(r["z"]) for r in ref], [(float(r["w_obs"]), float(r["z_mu"]), float(r["z_var"])) for r in ref],
+               list(zgold["z_assign_thr25_loci"]), [r["AD_array"] for r in ref])
+    got = zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops, single_read=True)
+    ref = oracle_mod.zscore_assignment(L, AD, af, IDs, pops, single_read=True)
+    check_rows(got, [float(r["z"]) for r in ref], [(float(r["w_obs"]), float(r["z_mu"]), float(r["z_var"])) for r in ref],
+               list(zgold["z_assign_single_loci"]), [r["AD_array"] for r in ref])
+
+
+def test_reference_zscore_golden(zs, zgold, oracle_mod):
+    L, AD, IDs = zgold["L"], zgold["AD"].astype(np.int32), zgold["IDs"]
+    got = zs.zscore_all(L, AD, IDs, zs.MODE_REFERENCE)
+    ref = oracle_mod.zscore_reference(L, AD, IDs, 200, 1e-4)
+    assert ["%.7f" % r["z"] for r in ref] == str(zgold["z_ref_txt"]).split()
+    assert [r["em_iters"] for r in got] == list(zgold["z_ref_em_iters"])
+    check_rows(got, [float(r["z"]) for r in ref], [(float(r["w_obs"]), float(r["z_mu"]), float(r["z_var"])) for r in ref],
+               list(zgold["z_ref_loci"]), [r["AD_array"] for r in ref])
+
+
+@pytest.mark.parametrize("m,n,k,depth,seed", [(5000, 40, 4, 2.0, 31), (3000, 21, 3, 5.0, 32)])
+def test_zscore_vs_oracle_synthetic(zs, oracle_mod, m, n, k, depth, seed):
+    from wgsassign_b200 import synth
+    d = synth.synth(m, n, k, seed=seed, depth=depth, interleave=True)
+    L, AD, IDs = d["L"], d["AD"], d["IDs"]
+    af, pops, _ = oracle_mod.reference_af(L, IDs, 200, 1e-4, 2)
+    sub = (3, min(n, 11))
+    got = zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops, ind_start=sub[0], ind_end=sub[1])
+    ref = oracle_mod.zscore_assignment(L, AD, af, IDs, pops, ind_start=sub[0], ind_end=sub[1], t=2)
+    check_rows(got, [float(r["z"]) for r in ref], [(float(r["w_obs"]), float(r["z_mu"]), float(r["z_var"])) for r in ref],
+               [r["loci_kept"] for r in ref], [r["AD_array"] for r in ref])
+    got = zs.zscore_all(L, AD, IDs, zs.MODE_REFERENCE, ind_start=sub[0], ind_end=sub[1])
+    ref = oracle_mod.zscore_reference(L, AD, IDs, 200, 1e-4, ind_start=sub[0], ind_end=sub[1], t=2)
+    assert [r["em_iters"] for r in got] == [r["em_iter"] for r in ref]
+    check_rows(got, [float(r["z"]) for r in ref], [(float(r["w_obs"]), float(r["z_mu"]), float(r["z_var"])) for r in ref],
+               [r["loci_kept"] for r in ref], [r["AD_array"] for r in ref])
+
+
+def test_zscore_errors(zs, zgold):
+    L, AD, IDs, af = zgold["L"], zgold["AD"].astype(np.int32), zgold["IDs"], zgold["af"]
+    pops = np.unique(IDs[:, 1])
+    with pytest.raises(AssertionError, match="loci were kept"):
+        zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops, n_threshold=10 ** 6)
+    big = AD.copy()
+    big[0, 0] = 300
+    with pytest.raises(Exception, match="254"):
+        zs.zscore_all(L, big, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops)

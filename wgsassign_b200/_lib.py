@@ -50,6 +50,7 @@ SYMBOLS = {
     "wgs_fisher_partial": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "wgs_zscore": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _vp]),
     "wgs_zscore_classes": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "wgs_zscore_deep_sites": (_i64, [_vp]),
     "wgs_launch_count": (_i64, [_vp]),
     "wgs_timing_reset": (_i32, [_vp, _i32]),
     "wgs_timing_get": (_i32, [_vp, ctypes.c_char_p, _vp, _vp]),
@@ -243,6 +244,9 @@ class Context:
         n = ctypes.c_int32(0)
         self._ck(lib().wgs_zscore_classes(self._h, int(ind), max_rows, _ptr(buf), ctypes.byref(n)))
         return buf[:n.value].copy()
+
+    def zscore_deep_sites(self):
+        return int(lib().wgs_zscore_deep_sites(self._h))
 
     # ---- instrumentation ----
     def launch_count(self):

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -53,6 +54,7 @@ struct wgs_ctx {
 
     // z-score class tables of the last call
     std::vector<std::vector<int>> zclasses;
+    long z_deep_sites = 0;
 
     // instrumentation
     long launches = 0;
@@ -452,13 +454,13 @@ int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
 // Leave-one-out EM for every individual on the resident G.  F [M][ldf] (device): columns
 // [0,ldg) <- converged UNclipped LOO estimates.  mask/d_count optional (reference z-score).
 int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const unsigned char* mask, const double* d_count,
-               std::vector<int>& iters_cols)
+               std::vector<int>& iters_cols, const std::vector<unsigned char>* sel = nullptr)
 {
     const long M = ctx->M();
     const int ldg = ctx->ldg, K = ctx->K;
     std::vector<int> active0(ldg, 0);
     for (int c = 0; c < ldg; ++c)
-        if (ctx->ind_of_col[c] >= 0 && ctx->pops[ctx->pop_of_col[c]].n > 1) active0[c] = 1;
+        if (ctx->ind_of_col[c] >= 0 && ctx->pops[ctx->pop_of_col[c]].n > 1 && (!sel || (*sel)[c])) active0[c] = 1;
     std::vector<LooLaunch> cfgs(K);
     int nblocks = 1;
     for (int k = 0; k < K; ++k) {
@@ -880,12 +882,208 @@ int32_t wgs_fisher_partial(wgs_ctx* ctx, const float* af, float* f_obs, float* n
     return 0;
 }
 
+// exact binomial coefficient (depth <= 40 fits easily in 64 bits)
+static double binom(int n, int k)
+{
+    if (k > n - k) k = n - k;
+    unsigned long long r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (unsigned long long)(n - k + i) / (unsigned long long)i;
+    return (double)r;
+}
+
 int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32_t n_threshold, int32_t single_read,
                    int32_t ind_start, int32_t ind_end, int32_t iter, double tole, wgs_zrow* out)
 {
-    (void)mode; (void)af; (void)K; (void)n_threshold; (void)single_read; (void)ind_start; (void)ind_end; (void)iter; (void)tole; (void)out;
-    return fail(ctx, "wgs_zscore: not implemented in this build");
+    cudaSetDevice(ctx->device);
+    if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
+    if (!ctx->AD || ctx->M_ad != ctx->M()) return fail(ctx, "no allele depths resident (wgs_upload_ad)");
+    if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for the z-score operators");
+    if (ind_start < 0 || ind_end > ctx->N || ind_start >= ind_end) return fail(ctx, "individual range [%d,%d) outside [0,%d)", ind_start, ind_end, ctx->N);
+    if (mode == 0 && (!af || K != ctx->K)) return fail(ctx, "assignment mode needs af [M,%d]", ctx->K);
+    const long M = ctx->M();
+    const int ldg = ctx->ldg, N = ctx->N;
+    const double e = 0.01;                                       // WGSassign.py:350, :430
+
+    std::vector<unsigned char> sel(ldg, 0);
+    for (int i = ind_start; i < ind_end; ++i) sel[ctx->col_of_ind[i]] = 1;
+    DevBuf dsel, dtable, ddeep;
+    const size_t tab_n = (size_t)ldg * kZClasses;
+    if (buf_alloc(ctx, dsel, ldg) || buf_alloc(ctx, dtable, tab_n * sizeof(ZTally)) || buf_alloc(ctx, ddeep, ldg * sizeof(unsigned long long))) return 1;
+    CU(cudaMemcpyAsync(dsel.p, sel.data(), ldg, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(dtable.p, 0, tab_n * sizeof(ZTally), ctx->stream));
+    CU(cudaMemsetAsync(ddeep.p, 0, ldg * sizeof(unsigned long long), ctx->stream));
+
+    // launch geometry shared by the three streaming passes
+    LikeCfg c = like_cfg(ctx, M, 4);
+    {
+        int wy_count = 8 / c.wx;
+        long cap = 2047L * wy_count;                              // 32-bit register sums in ztally
+        if (c.sites_per_block > cap) { c.sites_per_block = cap; c.gy = (int)((M + cap - 1) / cap); }
+    }
+    const double pairs = (double)M * (ind_end - ind_start);
+    // class counts and float32 class means, per (column, class)
+    std::vector<long long> ccnt(tab_n, 0);
+    std::vector<float> cmean(tab_n * 3, 0.f);
+    const char* env_exact = getenv("WGS_Z_EXACT_MEANS");
+    const bool exact_means = ctx->fn != nullptr || (env_exact && env_exact[0] == '1');
+    if (exact_means) {
+        // order-independent fixed-point tally (shardable)
+        LAUNCH("ztally", ztally_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
+               c.wx, c.sites_per_block, dtable.as<ZTally>(), ddeep.as<unsigned long long>());
+        add_work(ctx, "ztally", pairs * 10.0, pairs);
+        std::vector<ZTally> table(tab_n);
+        CU(cudaMemcpyAsync(table.data(), dtable.p, tab_n * sizeof(ZTally), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->fn) ctx->fn(table.data(), (int64_t)tab_n * 4, WGS_I64, ctx->user);
+        for (size_t g = 0; g < tab_n; ++g) {
+            ccnt[g] = table[g].cnt;
+            if (table[g].cnt > 0) {
+                double n = (double)table[g].cnt;
+                cmean[3 * g + 0] = (float)((double)table[g].s0 * kZUnit / n);
+                cmean[3 * g + 1] = (float)((double)table[g].s1 * kZUnit / n);
+                cmean[3 * g + 2] = (float)((double)table[g].s2 * kZUnit / n);
+            }
+        }
+    } else {
+        // reference-faithful: sequential float32 sums in site order, float32 divide (numpy's float32 mean)
+        LAUNCH("ztally", ztally_seq_kernel, (ldg + 31) / 32, 32, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
+               dtable.as<ZTallyF>(), ddeep.as<unsigned long long>());
+        add_work(ctx, "ztally", pairs * 10.0, pairs);
+        std::vector<ZTallyF> table(tab_n);
+        CU(cudaMemcpyAsync(table.data(), dtable.p, tab_n * sizeof(ZTallyF), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (size_t g = 0; g < tab_n; ++g) {
+            ccnt[g] = table[g].cnt;
+            if (table[g].cnt > 0) {
+                float n = (float)table[g].cnt;
+                cmean[3 * g + 0] = table[g].s0 / n; cmean[3 * g + 1] = table[g].s1 / n; cmean[3 * g + 2] = table[g].s2 / n;
+            }
+        }
+    }
+
+    // ---- class decisions on the host (zscore.py:23-39, :63-79): a few hundred rows per individual ----
+    std::vector<signed char> kmax(tab_n, -1);
+    std::vector<float> kmean(tab_n, 0.f);
+    std::vector<float4> zlike(tab_n, make_float4(0.f, 0.f, 0.f, 0.f)), zfac(tab_n, make_float4(0.f, 0.f, 0.f, 0.f));
+    ctx->zclasses.assign(N, std::vector<int>());
+    std::vector<int> n_classes(N, 0);
+    for (int i = ind_start; i < ind_end; ++i) {
+        const int col = ctx->col_of_ind[i];
+        const long long* t = ccnt.data() + (size_t)col * kZClasses;
+        std::vector<int> ids;                                     // classes passing the count filter
+        int per_depth[kZDepthCap + 1] = {0};
+        for (int d = 0; d <= kZDepthCap; ++d)
+            for (int alt = 0; alt <= d; ++alt) {
+                int id = zclass_id(d - alt, alt);
+                if (t[id] <= 0) continue;
+                bool pass = single_read ? (d == 1) : (t[id] > n_threshold && d != 0);
+                if (pass) { ids.push_back(id); ++per_depth[d]; }
+            }
+        if (ids.empty()) return fail(ctx, "No loci were kept! Too stringent filtering?");
+        if (ids.size() == 1) return fail(ctx, "Not enough loci were kept! Too stringent filtering?");
+        auto& rows = ctx->zclasses[i];
+        for (int d = 0; d <= kZDepthCap; ++d) {
+            if (!(d < per_depth[d])) continue;                   // zscore.py:38: depth kept iff all d+1 splits present
+            for (int alt = 0; alt <= d; ++alt) {
+                int ref = d - alt, id = zclass_id(ref, alt);
+                size_t g = (size_t)col * kZClasses + id;
+                float m0 = cmean[3 * g], m1 = cmean[3 * g + 1], m2 = cmean[3 * g + 2];
+                int mx = 0; float mv = m0;
+                if (m1 > mv) { mx = 1; mv = m1; }
+                if (m2 > mv) { mx = 2; mv = m2; }
+                kmax[g] = (signed char)mx; kmean[g] = mv;
+                zlike[g] = make_float4(m0, m1, m2, 0.f);
+                double comb = binom(d, alt);
+                zfac[g] = make_float4((float)(comb * std::pow(1.0 - e, ref) * std::pow(e, alt)), (float)(comb * std::pow(0.5, d)),
+                                      (float)(comb * std::pow(1.0 - e, alt) * std::pow(e, ref)), 0.f);
+                rows.push_back(ref); rows.push_back(alt); rows.push_back(d); rows.push_back((int)t[id]);
+                ++n_classes[i];
+            }
+        }
+        if (n_classes[i] == 0) return fail(ctx, "individual %d: no read depth has all of its allele-count splits (zscore.py:36-39 leaves AD_array empty)", i);
+    }
+
+    DevBuf dkmax, dkmean, dlike, dfac, dkeep, dkept;
+    if (buf_alloc(ctx, dkmax, tab_n) || buf_alloc(ctx, dkmean, tab_n * sizeof(float)) || buf_alloc(ctx, dlike, tab_n * sizeof(float4)) ||
+        buf_alloc(ctx, dfac, tab_n * sizeof(float4)) || buf_alloc(ctx, dkeep, (size_t)std::max<long>(M, 1) * ldg) ||
+        buf_alloc(ctx, dkept, ldg * sizeof(unsigned long long))) return 1;
+    CU(cudaMemcpyAsync(dkmax.p, kmax.data(), tab_n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dkmean.p, kmean.data(), tab_n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dlike.p, zlike.data(), tab_n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dfac.p, zfac.data(), tab_n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(dkept.p, 0, ldg * sizeof(unsigned long long), ctx->stream));
+    LAUNCH("zkeep", zkeep_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
+           dkmax.as<signed char>(), dkmean.as<float>(), c.wx, c.sites_per_block, dkeep.as<unsigned char>(), dkept.as<unsigned long long>());
+    add_work(ctx, "zkeep", pairs * 11.0, pairs);
+    std::vector<long long> kept(ldg);
+    CU(cudaMemcpyAsync(kept.data(), dkept.p, ldg * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->fn) ctx->fn(kept.data(), ldg, WGS_I64, ctx->user);
+
+    // ---- allele frequencies seen by each individual ----
+    DevBuf dAF, dafcol;
+    std::vector<int> afcol(ldg, 0), em_iters(ldg, 0);
+    int af_ld = 0;
+    if (buf_alloc(ctx, dafcol, ldg * sizeof(int))) return 1;
+    if (mode == 0) {
+        af_ld = ctx->K;
+        if (buf_alloc(ctx, dAF, (size_t)std::max<long>(M, 1) * af_ld * sizeof(float))) return 1;
+        CU(cudaMemcpyAsync(dAF.p, af, (size_t)M * af_ld * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        for (int col = 0; col < ldg; ++col) afcol[col] = ctx->pop_of_col[col];
+    } else {
+        af_ld = ldg;
+        if (buf_alloc(ctx, dAF, (size_t)std::max<long>(M, 1) * af_ld * sizeof(float))) return 1;
+        std::vector<double> cnt(ldg);
+        std::vector<unsigned char> sel_em(sel);
+        for (int col = 0; col < ldg; ++col) { cnt[col] = (double)kept[col]; if (kept[col] == 0) sel_em[col] = 0; }
+        DevBuf dcnt;
+        if (buf_alloc(ctx, dcnt, ldg * sizeof(double))) return 1;
+        CU(cudaMemcpyAsync(dcnt.p, cnt.data(), ldg * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (run_em_loo(ctx, iter, tole, dAF.as<float>(), af_ld, dkeep.as<unsigned char>(), dcnt.as<double>(), em_iters, &sel_em)) return 1;
+        std::vector<float> lo, hi;
+        clip_bounds(ctx, 1, lo, hi);                              // WGSassign.py:360-364
+        DevBuf dlo, dhi;
+        if (buf_alloc(ctx, dlo, ldg * sizeof(float)) || buf_alloc(ctx, dhi, ldg * sizeof(float))) return 1;
+        CU(cudaMemcpyAsync(dlo.p, lo.data(), ldg * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dhi.p, hi.data(), ldg * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH("clip", clip_cols_kernel, grid_for(M * ldg, 256, ctx->num_sm * 8), 256, 0, ctx->stream, dAF.as<float>(), af_ld, ldg, M,
+               dlo.as<float>(), dhi.as<float>());
+        for (int col = 0; col < ldg; ++col) afcol[col] = col;
+    }
+    CU(cudaMemcpyAsync(dafcol.p, afcol.data(), ldg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+
+    DevBuf partials, sums;
+    const size_t np3 = (size_t)ldg * 3;
+    if (buf_alloc(ctx, partials, (size_t)c.gy * np3 * sizeof(double)) || buf_alloc(ctx, sums, np3 * sizeof(double))) return 1;
+    LAUNCH("zmoments", zmoments_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dkeep.as<unsigned char>(),
+           dAF.as<float>(), af_ld, dafcol.as<int>(), dlike.as<float4>(), dfac.as<float4>(), c.wx, c.sites_per_block, partials.as<double>());
+    add_work(ctx, "zmoments", pairs * 15.0, pairs);
+    LAUNCH("reduce", reduce_partials_kernel, grid_for(np3, 256, 64), 256, 0, ctx->stream, partials.as<double>(), c.gy, (long)np3, sums.as<double>());
+    std::vector<double> h(np3);
+    CU(cudaMemcpyAsync(h.data(), sums.p, np3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> deep(ldg);
+    CU(cudaMemcpyAsync(deep.data(), ddeep.p, ldg * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    if (ctx->fn) ctx->fn(h.data(), (int64_t)np3, WGS_F64, ctx->user);
+    ctx->z_deep_sites = 0;
+    for (int col = 0; col < ldg; ++col) ctx->z_deep_sites += (long)deep[col];
+
+    for (int i = ind_start; i < ind_end; ++i) {
+        const int col = ctx->col_of_ind[i];
+        wgs_zrow& r = out[i - ind_start];
+        r.w_obs = (float)h[(size_t)col * 3 + 0];                  // zscore.py:100 / WGSassign.py:369-370: float32 sums
+        r.z_mu = (float)h[(size_t)col * 3 + 1];
+        r.z_var = (float)h[(size_t)col * 3 + 2];
+        r.z = (r.w_obs - r.z_mu) / sqrtf(r.z_var);                // WGSassign.py:371 in float32 (NaN when nothing was kept)
+        r.loci_kept = kept[col];
+        r.n_classes = n_classes[i];
+        r.em_iters = mode == 1 ? em_iters[col] : 0;
+    }
+    return 0;
 }
+
+int64_t wgs_zscore_deep_sites(const wgs_ctx* ctx) { return ctx->z_deep_sites; }
 
 int32_t wgs_zscore_classes(wgs_ctx* ctx, int32_t ind, int32_t max_rows, int32_t* rows_out, int32_t* n_rows)
 {

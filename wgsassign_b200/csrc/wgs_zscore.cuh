@@ -1,3 +1,306 @@
-// z-score kernels (allele-depth class tally, keep mask, expected/variance moments)
+// z-score kernels: allele-depth class tally, keep mask, expected / variance moments
+// (zscore.py:11-120 and zscore_cy.pyx:10-56; assembled in WGSassign.py:346-381, :425-443).
+//
+// For every individual the reference (1) groups its sites by the (ref, alt) read-count pair
+// and takes the mean GL triple of each group, (2) keeps a group when it is frequent enough
+// and every split of its depth is present, (3) keeps a site when its group is kept and its
+// GL at the group's most likely genotype is within 0.01 of the group mean, and (4) sums the
+// observed log-likelihood and its expectation / variance over all read splits of the site's
+// depth.  Steps 1-3 are two pure-Python O(M) loops per individual in the reference (~80 % of
+// its z-score wall time); here they are two streaming passes over (GL, AD) for ALL
+// individuals at once.
+//
+// Class tables are dense over (ref, alt) with ref + alt <= kZDepthCap.  Tallies are integers
+// (bit-exact).  GL sums are signed 64-bit fixed point at 2^-36 (two 18-bit limbs per value,
+// |error| <= 2^-37 per value - members of a class share nearly identical GLs, so a coarser
+// grid would bias the class mean), hence order-independent: the same bits whatever the grid
+// or the number of GPUs.
 #pragma once
 #include "wgs_kernels.cuh"
+
+namespace wgs {
+
+constexpr int kZDepthCap = 40;
+constexpr int kZClasses = (kZDepthCap + 1) * (kZDepthCap + 2) / 2;   // 861
+constexpr int kZHotDepth = 4;
+constexpr int kZHot = (kZHotDepth + 1) * (kZHotDepth + 2) / 2;       // 15 classes held in registers
+constexpr float kZLimb = 262144.0f;                                  // 2^18 per limb; sums are in units of 2^-36
+constexpr double kZUnit = 1.0 / 68719476736.0;                       // 2^-36
+
+__host__ __device__ inline int zclass_id(int ref, int alt)
+{
+    int d = ref + alt;
+    return d * (d + 1) / 2 + alt;
+}
+
+struct ZTally { long long cnt, s0, s1, s2; };
+
+// numpy's `1 - L0 - L1` on float32 scalars (zscore.py:17, :54): two float32 roundings
+__device__ __forceinline__ float third_gl_np(float g0, float g1) { return __fsub_rn(__fsub_rn(1.0f, g0), g1); }
+
+// value -> (hi, lo) 18-bit limbs: g = hi * 2^-18 + lo * 2^-36 (+- 2^-37); every step is exact in FP32
+__device__ __forceinline__ void fix_limbs(float g, int& hi, int& lo)
+{
+    float gs = g * kZLimb;
+    float fl = floorf(gs);
+    hi = (int)fl;
+    lo = __float2int_rn((gs - fl) * kZLimb);
+}
+
+__device__ __forceinline__ void tally_flush(ZTally* t, int cnt, int h0, int l0, int h1, int l1, int h2, int l2)
+{
+    if (cnt) {
+        atomicAdd((unsigned long long*)&t->cnt, (unsigned long long)(long long)cnt);
+        atomicAdd((unsigned long long*)&t->s0, (unsigned long long)(((long long)h0 << 18) + l0));
+        atomicAdd((unsigned long long*)&t->s1, (unsigned long long)(((long long)h1 << 18) + l1));
+        atomicAdd((unsigned long long*)&t->s2, (unsigned long long)(((long long)h2 << 18) + l2));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// ztally: per (individual, class) site count and fixed-point GL sums (zscore.py:13-22).
+// Thread = individual, warp = 32 consecutive columns of one site (coalesced 256 B GL +
+// 64 B AD requests).  The classes of depth <= 4 (95 % of sites at 2x) live in registers and
+// are updated by predicated integer adds - no atomics in the streaming loop; deeper
+// classes go straight to the table with 64-bit integer atomics.  A thread sees at most
+// 2047 sites per launch so the 32-bit register limb sums cannot overflow.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
+              const unsigned char* __restrict__ sel,       // [ldg] 1 = individual requested
+              int wx, long sites_per_block,
+              ZTally* __restrict__ table,                  // [ldg][kZClasses]
+              unsigned long long* __restrict__ deep)       // [ldg] sites with depth > kZDepthCap
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy_count = 8 / wx;
+    const int cgx = warp % wx, wy = warp / wx;
+    const int col = (blockIdx.x * wx + cgx) * 32 + lane;
+    const bool on = col < ldg && sel[col];
+    const long s_begin = (long)blockIdx.y * sites_per_block;
+    const long s_end = min(M, s_begin + sites_per_block);
+    if (!on) return;
+
+    int cnt[kZHot], h0[kZHot], l0[kZHot], h1[kZHot], l1[kZHot], h2[kZHot], l2[kZHot];
+#pragma unroll
+    for (int c = 0; c < kZHot; ++c) { cnt[c] = 0; h0[c] = l0[c] = h1[c] = l1[c] = h2[c] = l2[c] = 0; }
+    int ndeep = 0;
+    ZTally* mine = table + (size_t)col * kZClasses;
+
+    for (long s = s_begin + wy; s < s_end; s += wy_count) {
+        float2 g = ld_stream2(&G[s * (long)ldg + col]);
+        uchar2 ad = AD[s * (long)ldg + col];
+        int ref = ad.x, alt = ad.y, d = ref + alt;
+        int vh0, vl0, vh1, vl1, vh2, vl2;
+        fix_limbs(g.x, vh0, vl0);
+        fix_limbs(g.y, vh1, vl1);
+        fix_limbs(third_gl_np(g.x, g.y), vh2, vl2);
+        if (d <= kZHotDepth) {
+            int code = zclass_id(ref, alt);
+#pragma unroll
+            for (int c = 0; c < kZHot; ++c) {
+                if (code == c) {
+                    cnt[c] += 1;
+                    h0[c] += vh0; l0[c] += vl0; h1[c] += vh1; l1[c] += vl1; h2[c] += vh2; l2[c] += vl2;
+                }
+            }
+        } else if (d <= kZDepthCap) {
+            tally_flush(mine + zclass_id(ref, alt), 1, vh0, vl0, vh1, vl1, vh2, vl2);
+        } else {
+            ++ndeep;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kZHot; ++c) tally_flush(mine + c, cnt[c], h0[c], l0[c], h1[c], l1[c], h2[c], l2[c]);
+    if (ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
+}
+
+// ---------------------------------------------------------------------------------------
+// ztally_seq: the reference-faithful tally.  The reference's class mean is numpy's float32
+// mean over the class's rows (zscore.py:22), i.e. a SEQUENTIAL float32 sum in site order
+// whose rounding error grows with the class size (already 4e-6 relative at 400 sites) and
+// feeds both the 0.01 keep test and the expected log-likelihood.  Reproducing its bits
+// needs the same order: one thread per individual walks all sites in order (a warp = 32
+// individuals, so loads stay coalesced; 8 sites are prefetched ahead).  Hot classes are
+// float accumulators in registers updated by predicated adds; the rest are read-modify-
+// written in the individual's own table row (no other thread touches it).
+// Used on a single GPU; site-sharded runs use the order-independent ztally_kernel above
+// (at that scale the reference's own float32 mean has lost its precision anyway).
+// ---------------------------------------------------------------------------------------
+struct ZTallyF { float s0, s1, s2; int cnt; };
+
+__global__ void __launch_bounds__(32)
+ztally_seq_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
+                  const unsigned char* __restrict__ sel,
+                  ZTallyF* __restrict__ table,             // [ldg][kZClasses], zeroed
+                  unsigned long long* __restrict__ deep)
+{
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    if (col >= ldg || !sel[col]) return;
+    int cnt[kZHot];
+    float a0[kZHot], a1[kZHot], a2[kZHot];
+#pragma unroll
+    for (int c = 0; c < kZHot; ++c) { cnt[c] = 0; a0[c] = a1[c] = a2[c] = 0.f; }
+    int ndeep = 0;
+    ZTallyF* mine = table + (size_t)col * kZClasses;
+    for (long sb = 0; sb < M; sb += 8) {
+        float2 g[8];
+        uchar2 ad[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            g[u] = make_float2(0.f, 0.f); ad[u] = make_uchar2(255, 255);
+            if (sb + u < M) { g[u] = ld_stream2(&G[(sb + u) * (long)ldg + col]); ad[u] = AD[(sb + u) * (long)ldg + col]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (sb + u >= M) break;
+            int ref = ad[u].x, alt = ad[u].y, d = ref + alt;
+            float g0 = g[u].x, g1 = g[u].y, g2 = third_gl_np(g0, g1);
+            if (d <= kZHotDepth) {
+                int code = zclass_id(ref, alt);
+#pragma unroll
+                for (int c = 0; c < kZHot; ++c) {
+                    if (code == c) {
+                        cnt[c] += 1;
+                        a0[c] = __fadd_rn(a0[c], g0); a1[c] = __fadd_rn(a1[c], g1); a2[c] = __fadd_rn(a2[c], g2);
+                    }
+                }
+            } else if (d <= kZDepthCap) {
+                ZTallyF* t = mine + zclass_id(ref, alt);
+                ZTallyF v = *t;
+                v.s0 = __fadd_rn(v.s0, g0); v.s1 = __fadd_rn(v.s1, g1); v.s2 = __fadd_rn(v.s2, g2); v.cnt += 1;
+                *t = v;
+            } else {
+                ++ndeep;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kZHot; ++c) { ZTallyF v; v.s0 = a0[c]; v.s1 = a1[c]; v.s2 = a2[c]; v.cnt = cnt[c]; mine[c] = v; }
+    if (ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
+}
+
+// Per-(individual, class) decision tables built on the host from the tallies:
+//   kmax[col][id]  : -1 class not kept, else argmax of the class mean (zscore.py:53)
+//   kmean[col][id] : the class mean at that argmax (float32)
+//   zlike/zfac[col][id] : class mean GL triple (AD_like) and binomial read probabilities
+//                         (AD_factorial), zscore.py:63-79
+// ---------------------------------------------------------------------------------------
+// zkeep: keep[s][col] = class kept && !(|mean[max] - GL[max]| > 0.01)  (zscore.py:43-61)
+// and the per-individual kept-site count (loci_kept - bit-exact).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+zkeep_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
+             const unsigned char* __restrict__ sel,
+             const signed char* __restrict__ kmax, const float* __restrict__ kmean,
+             int wx, long sites_per_block,
+             unsigned char* __restrict__ keep,             // [M][ldg]
+             unsigned long long* __restrict__ kept)        // [ldg]
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy_count = 8 / wx;
+    const int cgx = warp % wx, wy = warp / wx;
+    const int col = (blockIdx.x * wx + cgx) * 32 + lane;
+    const bool on = col < ldg && sel[col];
+    const long s_begin = (long)blockIdx.y * sites_per_block;
+    const long s_end = min(M, s_begin + sites_per_block);
+    if (col >= ldg) return;
+    const signed char* km = kmax + (size_t)col * kZClasses;
+    const float* kv = kmean + (size_t)col * kZClasses;
+    int nk = 0;
+    for (long s = s_begin + wy; s < s_end; s += wy_count) {
+        unsigned char k = 0;
+        if (on) {
+            uchar2 ad = AD[s * (long)ldg + col];
+            int ref = ad.x, alt = ad.y;
+            if (ref + alt <= kZDepthCap) {
+                int id = zclass_id(ref, alt);
+                int mx = km[id];
+                if (mx >= 0) {
+                    float2 g = ld_stream2(&G[s * (long)ldg + col]);
+                    float gl = mx == 0 ? g.x : (mx == 1 ? g.y : third_gl_np(g.x, g.y));
+                    float diff = fabsf(__fsub_rn(kv[id], gl));
+                    k = !(diff > 0.01f);
+                }
+            }
+        }
+        keep[s * (long)ldg + col] = k;
+        nk += k;
+    }
+    if (nk) atomicAdd(&kept[col], (unsigned long long)nk);
+}
+
+// ---------------------------------------------------------------------------------------
+// zmoments: for every kept (site, individual): observed log-likelihood, its expectation
+// over all read splits of the site's depth and the variance (zscore_cy.pyx:10-56).
+// af = afbase[s * af_ld + afcol[col]]: a column of the caller's AF matrix (assignment
+// mode) or the individual's own leave-one-out state column (reference mode).
+// Per-thread float64 sums -> partials[split][col][3] -> fixed-order reduction.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+zmoments_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
+                const unsigned char* __restrict__ keep,
+                const float* __restrict__ afbase, int af_ld, const int* __restrict__ afcol,
+                const float4* __restrict__ zlike, const float4* __restrict__ zfac,
+                int wx, long sites_per_block,
+                double* __restrict__ partials)             // [gridDim.y][ldg][3]
+{
+    __shared__ double red[8][32][3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy_count = 8 / wx;
+    const int cgx = warp % wx, wy = warp / wx;
+    const int col = (blockIdx.x * wx + cgx) * 32 + lane;
+    const bool col_ok = col < ldg;
+    const long s_begin = (long)blockIdx.y * sites_per_block;
+    const long s_end = min(M, s_begin + sites_per_block);
+    double w_obs = 0.0, w_mu = 0.0, w_var = 0.0;
+    if (col_ok) {
+        const int ac = afcol[col];
+        const float4* lk = zlike + (size_t)col * kZClasses;
+        const float4* fc = zfac + (size_t)col * kZClasses;
+        for (long s = s_begin + wy; s < s_end; s += wy_count) {
+            if (!keep[s * (long)ldg + col]) continue;
+            float2 g = ld_stream2(&G[s * (long)ldg + col]);
+            uchar2 ad = AD[s * (long)ldg + col];
+            float a = __ldg(&afbase[s * (long)af_ld + ac]);
+            float om = 1.0f - a;
+            float P0 = om * om, P1 = 2.0f * om * a, P2 = a * a;                 // zscore_cy.pyx:19-21
+            float lobs = logf(fmaf(g.x, P0, fmaf(g.y, P1, third_gl(g.x, g.y) * P2)));   // :22-25
+            int Dl = ad.x + ad.y;
+            int base = Dl * (Dl + 1) / 2;
+            float wl = 0.f;
+            for (int x = 0; x <= Dl; ++x) {                 // class (ref = x, alt = Dl - x), the order of :28-30
+                int id = base + (Dl - x);
+                float4 l = lk[id], f = fc[id];
+                float e = logf(fmaf(l.x, P0, fmaf(l.y, P1, l.z * P2)));       // :31
+                wl = __fadd_rn(wl, e * P0 * f.x);                              // :32-34, float32 after every add
+                wl = __fadd_rn(wl, e * P1 * f.y);
+                wl = __fadd_rn(wl, e * P2 * f.z);
+            }
+            float vr = 0.f;
+            for (int x = 0; x <= Dl; ++x) {
+                int id = base + (Dl - x);
+                float4 l = lk[id], f = fc[id];
+                float e = logf(fmaf(l.x, P0, fmaf(l.y, P1, l.z * P2)));
+                float dd = wl - e;
+                dd = dd * dd;
+                vr = __fadd_rn(vr, dd * P0 * f.x);                             // :54-56
+                vr = __fadd_rn(vr, dd * P1 * f.y);
+                vr = __fadd_rn(vr, dd * P2 * f.z);
+            }
+            w_obs += (double)lobs; w_mu += (double)wl; w_var += (double)vr;
+        }
+    }
+    red[warp][lane][0] = w_obs; red[warp][lane][1] = w_mu; red[warp][lane][2] = w_var;
+    __syncthreads();
+    if (wy == 0 && col_ok) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            double v = 0.0;
+            for (int w = 0; w < wy_count; ++w) v += red[w * wx + cgx][lane][q];
+            partials[((long)blockIdx.y * ldg + col) * 3 + q] = v;
+        }
+    }
+}
+
+}  // namespace wgs
