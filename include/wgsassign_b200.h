@@ -144,6 +144,19 @@ int32_t wgs_zscore_classes(wgs_ctx *ctx, int32_t ind, int32_t max_rows, int32_t 
  * the reference does unless every one of the depth+1 splits of that depth was observed. */
 int64_t wgs_zscore_deep_sites(const wgs_ctx *ctx);
 
+/* ---- host-side Beagle reader (reader_cy.pyx:16-77) ---------------------------------------- */
+/* Parses a gzipped Beagle GL file with `threads` parser threads (<= 0: all cores).  The matrix
+ * equals the reference reader's bit for bit ((float)atof of the first two GLs of each triple). */
+typedef struct wgs_beagle wgs_beagle;
+int32_t     wgs_beagle_open(const char *path, int32_t threads, wgs_beagle **out);
+const char *wgs_beagle_last_error(void);
+int64_t     wgs_beagle_sites(const wgs_beagle *b);
+int32_t     wgs_beagle_inds(const wgs_beagle *b);
+const char *wgs_beagle_sample(const wgs_beagle *b, int32_t i);
+const char *wgs_beagle_site(const wgs_beagle *b, int64_t s);
+int32_t     wgs_beagle_copy(const wgs_beagle *b, float *L_out); /* [sites, 2*inds] */
+void        wgs_beagle_close(wgs_beagle *b);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t wgs_launch_count(const wgs_ctx *ctx);

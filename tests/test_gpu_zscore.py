@@ -101,3 +101,20 @@ def test_zscore_errors(zs, zgold):
     big[0, 0] = 300
     with pytest.raises(Exception, match="254"):
         zs.zscore_all(L, big, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops)
+
+
+def test_exact_mean_variant_keeps_tallies(zs, zgold, monkeypatch):
+    """The order-independent fixed-point tally used under site sharding: identical integer
+    tallies; class means differ from numpy's sequential float32 mean only by that mean's own
+    accumulation error (4e-6 relative at 400 sites), which can move a site sitting on the 0.01
+    keep threshold, so loci kept agree to a couple of sites and the sums to ~1e-3."""
+    L, AD, IDs, af = zgold["L"], zgold["AD"].astype(np.int32), zgold["IDs"], zgold["af"]
+    pops = np.unique(IDs[:, 1])
+    monkeypatch.setenv("WGS_Z_EXACT_MEANS", "1")
+    got = zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops)
+    comp = zgold["z_assign_components"]
+    for j, r in enumerate(got):
+        assert abs(r["loci_kept"] - int(comp[j, 3])) <= 3
+        assert np.array_equal(sort_rows(r["AD_array"]), sort_rows(zgold["AD_array_%d" % j]))
+        assert abs(float(r["w_obs"]) - comp[j, 0]) <= 2e-3 * abs(comp[j, 0])
+        assert abs(float(r["z_mu"]) - comp[j, 1]) <= 2e-3 * abs(comp[j, 1])

@@ -13,7 +13,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libwgsassign_b200.so")
-SOURCES = [os.path.join(_PKG, "csrc", "wgs_api.cu")]
+SOURCES = [os.path.join(_PKG, "csrc", "wgs_api.cu"), os.path.join(_PKG, "csrc", "wgs_reader.cpp")]
 HEADERS = [os.path.join(_PKG, "csrc", "wgs_kernels.cuh"), os.path.join(_PKG, "csrc", "wgs_zscore.cuh"),
            os.path.join(_ROOT, "include", "wgsassign_b200.h")]
 
@@ -51,6 +51,14 @@ SYMBOLS = {
     "wgs_zscore": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _vp]),
     "wgs_zscore_classes": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "wgs_zscore_deep_sites": (_i64, [_vp]),
+    "wgs_beagle_open": (_i32, [ctypes.c_char_p, _i32, ctypes.POINTER(_vp)]),
+    "wgs_beagle_last_error": (ctypes.c_char_p, []),
+    "wgs_beagle_sites": (_i64, [_vp]),
+    "wgs_beagle_inds": (_i32, [_vp]),
+    "wgs_beagle_sample": (ctypes.c_char_p, [_vp, _i32]),
+    "wgs_beagle_site": (ctypes.c_char_p, [_vp, _i64]),
+    "wgs_beagle_copy": (_i32, [_vp, _vp]),
+    "wgs_beagle_close": (None, [_vp]),
     "wgs_launch_count": (_i64, [_vp]),
     "wgs_timing_reset": (_i32, [_vp, _i32]),
     "wgs_timing_get": (_i32, [_vp, ctypes.c_char_p, _vp, _vp]),
@@ -58,7 +66,7 @@ SYMBOLS = {
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC"]
+              "--shared", "-Xcompiler", "-fPIC", "-lz"]
 
 
 def needs_build():
