@@ -225,6 +225,8 @@ def main():
     from wgsassign_b200 import _lib, dist
     if world > 1:
         import torch.distributed as td
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep rank 0's stdout to the one JSON line
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
     M_local = args.sites
     M_total = M_local * world
@@ -325,6 +327,10 @@ def main():
         extra = {k: family(ctx, k, hbm_peak) for k in ("pop_like", "fisher")}
         ctx.timing_reset(False)
 
+    if world > 1:
+        import torch.distributed as td
+        td.barrier()
+        td.destroy_process_group()
     if rank != 0:
         return 0
 
