@@ -247,8 +247,11 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        af, its = ctx.ref_af(MAF_ITER, MAF_TOLE)
+    def step(host_af=False):
+        """One pass of --get_reference_af + --loo.  Resident form: the AF matrix stays on the
+        device between the two operators; host form (e2e): it is returned to the host, as the
+        CLI needs it for <out>.pop_af.npy, and passed back in."""
+        af, its = ctx.ref_af(MAF_ITER, MAF_TOLE, download=host_af)
         ll, _, lits = ctx.loo_partial(af, MAF_ITER, MAF_TOLE)
         dist.allreduce_sum(ll)
         return af, ll, its, lits
@@ -297,7 +300,7 @@ def main():
             ctx2.set_pops(pop_of, N_POP)
             ctx2.upload_gl(Lh)
             dist.attach(ctx2)
-            return step()
+            return step(host_af=True)
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -319,6 +322,8 @@ def main():
 
     # ---- extras: the other kernels of the path on the same resident matrix (untimed for `value`) ----
     extra = {}
+    if af is None:
+        af, _ = ctx.ref_af(MAF_ITER, MAF_TOLE)
     if not args.no_extra:
         ctx.timing_reset(True)
         for _ in range(3):

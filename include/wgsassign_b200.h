@@ -94,7 +94,8 @@ int32_t wgs_download(wgs_ctx *ctx, int64_t site0, int64_t nsites, float *L_out, 
 int32_t wgs_emMAF(wgs_ctx *ctx, const float *L_pop, int64_t M, int32_t n, int32_t iter, double tole,
                   float *f_out, int32_t *iters_out);
 
-/* Per-population EM + clipping (WGSassign.py:225-242): af_out [M,K], iters_out [K]. */
+/* Per-population EM + clipping (WGSassign.py:225-242): af_out [M,K], iters_out [K].  The result
+ * also stays resident on the device; af_out may be NULL when only wgs_loo_partial will use it. */
 int32_t wgs_ref_af(wgs_ctx *ctx, int32_t iter, double tole, float *af_out, int32_t *iters_out);
 
 /* glassy.assignLL (glassy.py:18-44 over glassy_cy.pyx:12-21): float64 sums over this
@@ -105,7 +106,8 @@ int32_t wgs_pop_like_partial(wgs_ctx *ctx, const float *af, int32_t K, double *o
  * log-likelihood of each individual under every population with the reference's
  * in-place column overwrite order (glassy.py:89).  af_inout [M,K] is read (full-data AF)
  * and left as the reference leaves it.  ll [N,K] float64; ll_parts [N*parts,K] float64
- * (may be NULL when parts==1); iters_out [N].  use_ds: score against the which=1 matrix. */
+ * (may be NULL when parts==1); iters_out [N].  use_ds: score against the which=1 matrix.
+ * af_inout may be NULL: the matrix left on the device by wgs_ref_af is used and updated in place. */
 int32_t wgs_loo_partial(wgs_ctx *ctx, float *af_inout, int32_t iter, double tole, int32_t use_ds,
                         int32_t parts, double *ll, double *ll_parts, int32_t *iters_out);
 

@@ -202,8 +202,10 @@ class Context:
                                  _ptr(f), ctypes.byref(it)))
         return f, it.value
 
-    def ref_af(self, iters, tole):
-        af = np.empty((self.M, self.K), np.float32)
+    def ref_af(self, iters, tole, download=True):
+        """Per-population EM + clipping.  With download=False the matrix stays on the device
+        only (for a following loo_partial(None, ...)) and None is returned for it."""
+        af = np.empty((self.M, self.K), np.float32) if download else None
         its = np.zeros(self.K, np.int32)
         self._ck(lib().wgs_ref_af(self._h, int(iters), float(tole), _ptr(af), _ptr(its)))
         return af, its
@@ -217,9 +219,12 @@ class Context:
         return out
 
     def loo_partial(self, af, iters, tole, use_ds=False, parts=1):
-        _as(af, np.float32, 2, "af")
-        if af.shape != (self.M, self.K):
-            raise ValueError("af must be [M,K] = %s" % ((self.M, self.K),))
+        """af: float32 [M,K] (mutated in place like glassy.py:89) or None to use the matrix
+        the last ref_af left on the device."""
+        if af is not None:
+            _as(af, np.float32, 2, "af")
+            if af.shape != (self.M, self.K):
+                raise ValueError("af must be [M,K] = %s" % ((self.M, self.K),))
         ll = np.empty((self.N, self.K), np.float64)
         llp = np.empty((self.N * parts, self.K), np.float64)
         its = np.zeros(self.N, np.int32)

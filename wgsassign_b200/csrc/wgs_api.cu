@@ -6,6 +6,7 @@
 #include "wgs_zscore.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -51,6 +52,14 @@ struct wgs_ctx {
     long M_total = -1, site_offset = 0;
     wgs_allreduce_fn fn = nullptr;
     void* user = nullptr;
+
+    // caching allocator
+    std::multimap<size_t, void*> pool_free;
+    std::map<void*, size_t> pool_size;
+
+    // allele frequencies kept on the device between wgs_ref_af and wgs_loo_partial (NULL host pointers)
+    float* d_af = nullptr;
+    long af_rows = 0; int af_cols = 0;
 
     // z-score class tables of the last call
     std::vector<std::vector<int>> zclasses;
@@ -131,24 +140,83 @@ void fold_timing(wgs_ctx* ctx)
     ctx->timed.clear();
 }
 
+// WGS_TRACE=1: wall-clock of the host-side phases of every API call on stderr
+struct Trace {
+    const char* what; std::chrono::steady_clock::time_point t0; bool on;
+    explicit Trace(const char* w) : what(w), t0(std::chrono::steady_clock::now()) { static int en = getenv("WGS_TRACE") ? 1 : 0; on = en; }
+    void lap(const char* phase) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[wgs trace] %-14s %-18s %9.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+// Device memory comes from a per-context caching pool: cudaMalloc / cudaFree of multi-GB
+// temporaries on every call cost tens of milliseconds (cudaFree synchronises the device),
+// more than the kernels of a small problem.  All work is stream-ordered on ctx->stream, so
+// a block can be handed to the next user as soon as the host releases it.
+size_t pool_round(size_t bytes) { return bytes < (1u << 20) ? ((bytes + 511) / 512) * 512 : ((bytes + (1u << 20) - 1) >> 20) << 20; }
+
+void pool_trim(wgs_ctx* ctx)
+{
+    for (auto& kv : ctx->pool_free) cudaFree(kv.second);
+    ctx->pool_free.clear();
+}
+
+void* pool_take(wgs_ctx* ctx, size_t bytes)
+{
+    bytes = pool_round(std::max<size_t>(bytes, 16));
+    auto it = ctx->pool_free.lower_bound(bytes);
+    if (it != ctx->pool_free.end() && it->first <= bytes + bytes / 4 + (1u << 20)) {
+        void* p = it->second;
+        ctx->pool_size[p] = it->first;
+        ctx->pool_free.erase(it);
+        return p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim(ctx);                                       // give everything cached back and retry once
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    ctx->pool_size[p] = bytes;
+    return p;
+}
+
+void pool_give(wgs_ctx* ctx, void* p)
+{
+    if (!p) return;
+    auto it = ctx->pool_size.find(p);
+    if (it == ctx->pool_size.end()) { cudaFree(p); return; }
+    ctx->pool_free.insert({it->second, p});
+    ctx->pool_size.erase(it);
+}
+
 template <class T> int dev_alloc(wgs_ctx* ctx, T** p, size_t count)
 {
-    *p = nullptr;
-    if (count == 0) count = 1;
-    CU(cudaMalloc((void**)p, count * sizeof(T)));
+    *p = (T*)pool_take(ctx, std::max<size_t>(count, 1) * sizeof(T));
+    if (!*p) return fail(ctx, "out of device memory allocating %zu bytes", std::max<size_t>(count, 1) * sizeof(T));
     return 0;
 }
-template <class T> void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
+template <class T> void dev_free(wgs_ctx* ctx, T*& p) { pool_give(ctx, p); p = nullptr; }
 
-struct DevBuf {   // RAII for temporaries
+struct DevBuf {   // RAII for temporaries (returned to the pool)
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    wgs_ctx* owner = nullptr;
+    ~DevBuf() { if (p) pool_give(owner, p); }
+    template <class T> T* as() { return (T*)p; }
+};
+struct RawBuf {   // non-owning view with the DevBuf accessors
+    void* p;
     template <class T> T* as() { return (T*)p; }
 };
 int buf_alloc(wgs_ctx* ctx, DevBuf& b, size_t bytes)
 {
-    if (bytes == 0) bytes = 16;
-    CU(cudaMalloc(&b.p, bytes));
+    if (b.p) { pool_give(b.owner, b.p); b.p = nullptr; }
+    b.owner = ctx;
+    b.p = pool_take(ctx, bytes);
+    if (!b.p) return fail(ctx, "out of device memory allocating %zu bytes", bytes);
     return 0;
 }
 
@@ -186,7 +254,7 @@ int build_structure(wgs_ctx* ctx, const int32_t* pop_of_ind, int N, int K)
         int end = (k + 1 < Ks) ? ctx->pops[k + 1].col0 : ctx->ldg;
         for (int c = ctx->pops[k].col0; c < end; ++c) ctx->pop_of_col[c] = k;
     }
-    dev_free(ctx->d_ind_of_col); dev_free(ctx->d_col_of_ind); dev_free(ctx->d_pop_of_col); dev_free(ctx->d_pops);
+    dev_free(ctx, ctx->d_ind_of_col); dev_free(ctx, ctx->d_col_of_ind); dev_free(ctx, ctx->d_pop_of_col); dev_free(ctx, ctx->d_pops);
     if (dev_alloc(ctx, &ctx->d_ind_of_col, ctx->ldg) || dev_alloc(ctx, &ctx->d_col_of_ind, N) ||
         dev_alloc(ctx, &ctx->d_pop_of_col, ctx->ldg) || dev_alloc(ctx, &ctx->d_pops, Ks)) return 1;
     CU(cudaMemcpy(ctx->d_ind_of_col, ctx->ind_of_col.data(), ctx->ldg * sizeof(int), cudaMemcpyHostToDevice));
@@ -198,8 +266,8 @@ int build_structure(wgs_ctx* ctx, const int32_t* pop_of_ind, int N, int K)
 
 void drop_data(wgs_ctx* ctx)
 {
-    dev_free(ctx->G[0]); dev_free(ctx->G[1]); dev_free(ctx->AD);
-    ctx->Mg[0] = ctx->Mg[1] = ctx->M_ad = 0;
+    dev_free(ctx, ctx->G[0]); dev_free(ctx, ctx->G[1]); dev_free(ctx, ctx->AD); dev_free(ctx, ctx->d_af);
+    ctx->Mg[0] = ctx->Mg[1] = ctx->M_ad = 0; ctx->af_rows = 0; ctx->af_cols = 0;
 }
 
 int ensure_structure(wgs_ctx* ctx, int N)
@@ -219,7 +287,10 @@ int upload_rows(wgs_ctx* ctx, const Elem* host, long M, int N, Fn&& repack)
     chunk = std::min(chunk, std::max<long>(M, 1));
     Elem* stage[2] = {nullptr, nullptr};
     cudaStream_t st[2] = {ctx->stream, ctx->stream2};
-    for (int b = 0; b < 2; ++b) CU(cudaMalloc((void**)&stage[b], (size_t)chunk * row_bytes));
+    for (int b = 0; b < 2; ++b) {
+        stage[b] = (Elem*)pool_take(ctx, (size_t)chunk * row_bytes);
+        if (!stage[b]) return fail(ctx, "out of device memory for the upload staging buffers");
+    }
     int b = 0;
     int rc = 0;
     for (long r0 = 0; r0 < M && !rc; r0 += chunk, b ^= 1) {
@@ -229,7 +300,7 @@ int upload_rows(wgs_ctx* ctx, const Elem* host, long M, int N, Fn&& repack)
         repack(stage[b], r0, rows, st[b]);
     }
     cudaStreamSynchronize(st[0]); cudaStreamSynchronize(st[1]);
-    cudaFree(stage[0]); cudaFree(stage[1]);
+    pool_give(ctx, stage[0]); pool_give(ctx, stage[1]);
     if (rc) return rc;
     CU(cudaGetLastError());
     return 0;
@@ -237,12 +308,14 @@ int upload_rows(wgs_ctx* ctx, const Elem* host, long M, int N, Fn&& repack)
 
 // ---- likelihood launch configuration --------------------------------------------------------
 struct LikeCfg { int wx, gx, gy; long sites_per_block; };
-LikeCfg like_cfg(wgs_ctx* ctx, long M, int blocks_per_sm)
+LikeCfg like_cfg(wgs_ctx* ctx, long M, int blocks_per_sm, int inds_per_thread = 1)
 {
     LikeCfg c;
-    int groups = (ctx->ldg + 31) / 32;
+    int groups = (ctx->ldg + 32 * inds_per_thread - 1) / (32 * inds_per_thread);
+    // column groups per block: the largest power of two that wastes < 7 % of the warp slots on columns past ldg
     c.wx = 1;
-    while (c.wx < 8 && c.wx * 2 <= groups) c.wx *= 2;
+    for (int w = 2; w <= 8; w *= 2)
+        if ((groups + w - 1) / w * w <= groups + groups * 7 / 100) c.wx = w;
     c.gx = (groups + c.wx - 1) / c.wx;
     long target = (long)ctx->num_sm * blocks_per_sm * 2;
     long gy = std::max<long>(1, target / c.gx);
@@ -258,11 +331,11 @@ LikeCfg like_cfg(wgs_ctx* ctx, long M, int blocks_per_sm)
 
 int pick_R(float margin)
 {
-    // like >= ~margin^2; R factors on a mantissa in [1,2) must stay above 2^-100
+    // like >= ~margin^2; R factors on a mantissa in [1,2) must stay above 2^-120 (FP32 normal range ends at 2^-126)
     if (!(margin > 0.f)) return 1;
     double bits = -2.0 * std::log2((double)margin);
     if (bits < 1.0) bits = 1.0;
-    int r = (int)(100.0 / bits);
+    int r = (int)(120.0 / bits);
     if (r >= 8) return 8;
     if (r >= 4) return 4;
     if (r >= 2) return 2;
@@ -276,20 +349,34 @@ int pick_KT(int Krem)
     return 20;
 }
 
-template <int KT, int R>
-int launch_pop_like_t(wgs_ctx* ctx, const float2* G, long M, const float* dA, int K, int k0, const LikeCfg& c,
-                      long pm, long pr, double* partials)
+template <int KT, int R, int I>
+int launch_pop_like_i(wgs_ctx* ctx, const float2* G, long M, const float* dA, int K, int k0, const LikeCfg& c, double* partials)
 {
-    size_t smem = (size_t)kPopLikeTS * KT * sizeof(float4) + 8 * 32 * 4 * sizeof(double);
-    auto kern = pop_like_kernel<KT, R>;
+    constexpr int KP = (KT + 1) / 2;
+    size_t smem = (size_t)kPopLikeTS * KP * (sizeof(ulonglong2) + sizeof(f32x2)) + 8 * 32 * 4 * sizeof(double);
+    auto kern = pop_like_kernel<KT, R, I>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAUNCH("pop_like", kern, dim3(c.gx, c.gy), kPopLikeThreads, smem, ctx->stream,
-           G, ctx->ldg, M, dA, K, k0, c.wx, c.sites_per_block, pm, pr, ctx->site_offset, partials);
+           G, ctx->ldg, M, dA, K, k0, c.wx, c.sites_per_block, partials);
     {   // algorithmic: every (g0,g1) pair once per pass + this pass's AF columns; one evaluation per (site, ind, pop)
         int kt = std::min(KT, K - k0);
         add_work(ctx, "pop_like", (double)M * ctx->N * 8.0 + (double)M * kt * 4.0, (double)M * ctx->N * kt);
     }
     return 0;
+}
+// individuals per thread: as many as the register file allows for the tile width, 1 when the matrix is narrow
+constexpr int pop_like_imax(int KT) { return KT <= 10 ? 2 : 1; }
+int pop_like_inds(int KT, int ldg)
+{
+    const char* e = getenv("WGS_POPLIKE_I");      // experiment switch: 1 forces one individual per thread
+    if (e && e[0] == '1') return 1;
+    return ldg > 64 ? pop_like_imax(KT) : 1;
+}
+template <int KT, int R>
+int launch_pop_like_t(wgs_ctx* ctx, const float2* G, long M, const float* dA, int K, int k0, const LikeCfg& c, double* partials, int I)
+{
+    if (I == 1) return launch_pop_like_i<KT, R, 1>(ctx, G, M, dA, K, k0, c, partials);
+    return launch_pop_like_i<KT, R, pop_like_imax(KT)>(ctx, G, M, dA, K, k0, c, partials);
 }
 template <int KT, int R>
 int launch_loo_like_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, int ldf, const int* rc, int K, int k0,
@@ -403,7 +490,7 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* Fpop, std::vector<int
     const long M = ctx->M();
     const int K = std::max(ctx->K, 1);
     if (K > kMaxKq * 32) return fail(ctx, "more than %d populations not supported", kMaxKq * 32);
-    int nblocks = (int)std::max<long>(1, std::min<long>((M + 7) / 8, (long)ctx->num_sm * 8));
+    int nblocks = (int)std::max<long>(1, std::min<long>((M + 8 * kEmPopU - 1) / (8 * kEmPopU), (long)ctx->num_sm * 8));
     EmState st;
     if (em_state_init(ctx, st, K, K, nblocks, std::vector<int>(K, 1))) return 1;
     LAUNCH("fill", fill_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, Fpop, M * K, 0.25f);
@@ -562,7 +649,8 @@ void wgs_destroy(wgs_ctx* ctx)
     cudaSetDevice(ctx->device);
     fold_timing(ctx);
     drop_data(ctx);
-    dev_free(ctx->d_ind_of_col); dev_free(ctx->d_col_of_ind); dev_free(ctx->d_pop_of_col); dev_free(ctx->d_pops);
+    dev_free(ctx, ctx->d_ind_of_col); dev_free(ctx, ctx->d_col_of_ind); dev_free(ctx, ctx->d_pop_of_col); dev_free(ctx, ctx->d_pops);
+    pool_trim(ctx);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
@@ -597,7 +685,7 @@ int32_t wgs_upload_gl(wgs_ctx* ctx, const float* L, int64_t M, int32_t N, int32_
     if (M < 0 || N <= 0) return fail(ctx, "bad shape");
     if (which == 0) { if (ensure_structure(ctx, N)) return 1; }
     else if (N != ctx->N || M != ctx->Mg[0]) return fail(ctx, "down-sampled matrix must match the GL matrix shape");
-    dev_free(ctx->G[which]);
+    dev_free(ctx, ctx->G[which]);
     if (dev_alloc(ctx, &ctx->G[which], (size_t)std::max<long>(M, 1) * ctx->ldg)) return 1;
     ctx->Mg[which] = M;
     float2* G = ctx->G[which];
@@ -611,7 +699,7 @@ int32_t wgs_upload_ad(wgs_ctx* ctx, const int32_t* AD, int64_t M, int32_t N)
 {
     cudaSetDevice(ctx->device);
     if (N != ctx->N || M != ctx->Mg[0]) return fail(ctx, "allele-depth matrix must match the GL matrix shape (upload GL first)");
-    dev_free(ctx->AD);
+    dev_free(ctx, ctx->AD);
     if (dev_alloc(ctx, &ctx->AD, (size_t)std::max<long>(M, 1) * ctx->ldg)) return 1;
     ctx->M_ad = M;
     DevBuf flag;
@@ -678,21 +766,27 @@ int32_t wgs_ref_af(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32
     if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for reference-panel operators");
     const long M = ctx->M();
     const int K = ctx->K;
-    DevBuf F;
-    if (buf_alloc(ctx, F, (size_t)M * K * sizeof(float))) return 1;
+    Trace tr("ref_af");
+    dev_free(ctx, ctx->d_af);
+    if (dev_alloc(ctx, &ctx->d_af, (size_t)std::max<long>(M, 1) * K)) return 1;
+    ctx->af_rows = M; ctx->af_cols = K;
+    float* F = ctx->d_af;
     std::vector<int> its;
-    if (run_em_pop(ctx, iter, tole, F.as<float>(), its)) return 1;
+    tr.lap("alloc");
+    if (run_em_pop(ctx, iter, tole, F, its)) return 1;
+    tr.lap("em");
     std::vector<float> lo(K), hi(K);
     for (int k = 0; k < K; ++k) { double l = 1.0 / (2.0 * (ctx->pops[k].n + 1)); lo[k] = (float)l; hi[k] = (float)(1.0 - l); }
     DevBuf dlo, dhi;
     if (buf_alloc(ctx, dlo, K * sizeof(float)) || buf_alloc(ctx, dhi, K * sizeof(float))) return 1;
     CU(cudaMemcpyAsync(dlo.p, lo.data(), K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(dhi.p, hi.data(), K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH("clip", clip_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F.as<float>(), K, K, M,
+    LAUNCH("clip", clip_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F, K, K, M,
            dlo.as<float>(), dhi.as<float>());
-    CU(cudaMemcpyAsync(af_out, F.p, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (af_out) CU(cudaMemcpyAsync(af_out, F, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
+    tr.lap("clip+d2h");
     for (int k = 0; k < K; ++k) iters_out[k] = its[k];
     return 0;
 }
@@ -736,13 +830,16 @@ int32_t wgs_pop_like_partial(wgs_ctx* ctx, const float* af, int32_t K, double* o
     CU(cudaMemcpyAsync(dA.p, af, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     int R = 1;
     if (af_R(ctx, dA.as<float>(), M * K, &R)) return 1;
-    LikeCfg c = like_cfg(ctx, M, 3);
+    // one launch geometry for all passes: the widest tile decides the individuals per thread
+    int I = pop_like_inds(pick_KT(K), ctx->ldg);
+    LikeCfg c = like_cfg(ctx, M, 2, I);
     size_t np = (size_t)ctx->ldg * K;
     if (buf_alloc(ctx, partials, (size_t)c.gy * np * sizeof(double)) || buf_alloc(ctx, sums, np * sizeof(double))) return 1;
     for (int k0 = 0; k0 < K;) {
         int KT = pick_KT(K - k0);
+        if (I > 1 && pop_like_inds(KT, ctx->ldg) != I) KT = 20;     // keep I constant across passes (only when K > 20)
         int rc_ = 0;
-        DISPATCH_KT(launch_pop_like_t, KT, R, ctx, ctx->G[0], M, dA.as<float>(), K, k0, c, 1L, 0L, partials.as<double>());
+        DISPATCH_KT(launch_pop_like_t, KT, R, ctx, ctx->G[0], M, dA.as<float>(), K, k0, c, partials.as<double>(), I);
         if (rc_) return rc_;
         k0 += KT;
     }
@@ -764,19 +861,38 @@ int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole
     const long M = ctx->M();
     const int K = ctx->K, ldg = ctx->ldg, N = ctx->N;
     const int ldf = ldg + (K + 3) / 4 * 4;
-    DevBuf F, dA, dcols;
-    if (buf_alloc(ctx, F, (size_t)M * ldf * sizeof(float)) || buf_alloc(ctx, dA, (size_t)M * K * sizeof(float)) ||
-        buf_alloc(ctx, dcols, K * sizeof(int))) return 1;
-    CU(cudaMemcpyAsync(dA.p, af_inout, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    Trace tr("loo");
+    DevBuf F, dcols;
+    if (!af_inout && !(ctx->d_af && ctx->af_rows == M && ctx->af_cols == K))
+        return fail(ctx, "af_inout is NULL but no allele-frequency matrix is resident (call wgs_ref_af first)");
+    if (af_inout) {
+        dev_free(ctx, ctx->d_af);
+        if (dev_alloc(ctx, &ctx->d_af, (size_t)std::max<long>(M, 1) * K)) return 1;
+        ctx->af_rows = M; ctx->af_cols = K;
+        CU(cudaMemcpyAsync(ctx->d_af, af_inout, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    RawBuf dA{ctx->d_af};
+    if (buf_alloc(ctx, F, (size_t)M * ldf * sizeof(float)) || buf_alloc(ctx, dcols, K * sizeof(int))) return 1;
     std::vector<int> ident(K);
     for (int k = 0; k < K; ++k) ident[k] = k;
     CU(cudaMemcpyAsync(dcols.p, ident.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(F.p, 0, (size_t)M * ldf * sizeof(float), ctx->stream));
+    {   // columns [ldg, ldf): the caller's full-data AF, then pad columns that only idle lanes read (kept finite)
+        DevBuf dpad;
+        std::vector<float> half(ldf - ldg, 0.5f);
+        if (buf_alloc(ctx, dpad, half.size() * sizeof(float))) return 1;
+        CU(cudaMemcpyAsync(dpad.p, half.data(), half.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH("fill", bcast_row_kernel, grid_for(M * (ldf - ldg), 256, ctx->num_sm * 8), 256, 0, ctx->stream, F.as<float>() + ldg, ldf,
+               ldf - ldg, M, dpad.as<float>());
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     LAUNCH("gather", gather_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, dA.as<float>(), K,
            dcols.as<int>(), K, F.as<float>(), ldf, ldg, M);
 
     std::vector<int> its_cols;
+    CU(cudaStreamSynchronize(ctx->stream));
+    tr.lap("alloc+h2d+init");
     if (run_em_loo(ctx, iter, tole, F.as<float>(), ldf, nullptr, nullptr, its_cols)) return 1;
+    tr.lap("em");
     for (int i = 0; i < N; ++i) iters_out[i] = its_cols[ctx->col_of_ind[i]];
 
     // clip to [1/(2n), 1-1/(2n)] with n = n_pop (glassy.py:80-85: n_pop-1 individuals were used)
@@ -836,6 +952,7 @@ int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole
         }
     }
     if (parts == 1 && ll_parts) memcpy(ll_parts, ll, (size_t)N * K * sizeof(double));
+    tr.lap("like");
 
     // af as the reference leaves it: column j = LOO estimate of the LAST member of population j
     std::vector<int> lastcol(K);
@@ -843,9 +960,10 @@ int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole
     CU(cudaMemcpyAsync(dcols.p, lastcol.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH("gather", gather_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F.as<float>(), ldf,
            dcols.as<int>(), K, dA.as<float>(), K, 0, M);
-    CU(cudaMemcpyAsync(af_inout, dA.p, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (af_inout) CU(cudaMemcpyAsync(af_inout, dA.p, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
+    tr.lap("af d2h");
     return 0;
 }
 
@@ -861,7 +979,7 @@ int32_t wgs_fisher_partial(wgs_ctx* ctx, const float* af, float* f_obs, float* n
     size_t smem = (size_t)warps * ldg * sizeof(float);
     if (smem > 200 * 1024) return fail(ctx, "too many individuals for the Fisher kernel's shared-memory accumulators");
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fisher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nblocks = (int)std::max<long>(1, std::min<long>((M + warps - 1) / warps, (long)ctx->num_sm * 4));
+    int nblocks = (int)std::max<long>(1, std::min<long>((M + warps * kFisherU - 1) / (warps * kFisherU), (long)ctx->num_sm * 4));
     DevBuf dA, dF, dNe, partials, sums;
     if (buf_alloc(ctx, dA, (size_t)M * K * sizeof(float)) || buf_alloc(ctx, dF, (size_t)M * K * sizeof(float)) ||
         buf_alloc(ctx, dNe, (size_t)M * K * sizeof(float)) || buf_alloc(ctx, partials, (size_t)nblocks * ldg * sizeof(double)) ||

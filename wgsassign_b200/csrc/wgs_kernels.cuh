@@ -189,17 +189,29 @@ struct LikeAcc {
         zero_mask = nan_mask = 0u; nren = 0;
     }
     __device__ __forceinline__ void renorm() {
+        unsigned worst = 0u;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-            int b = __float_as_int(prod[k]);
-            if ((unsigned)(b - 0x00800000) < 0x7F000000u) {      // positive normal
+        for (int k = 0; k < KT; ++k) worst = max(worst, (unsigned)(__float_as_int(prod[k]) - 0x00800000));
+        if (worst < 0x7F000000u) {                             // all positive normal
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                int b = __float_as_int(prod[k]);
                 esum[k] += (b >> 23);
                 prod[k] = __int_as_float((b & 0x007fffff) | 0x3f800000);
-            } else {
-                if (prod[k] == 0.0f || (b > 0 && b < 0x00800000)) zero_mask |= (1u << k);   // 0 or denormal
-                else nan_mask |= (1u << k);                                             // negative, inf, NaN
-                esum[k] += 127;
-                prod[k] = 1.0f;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                int b = __float_as_int(prod[k]);
+                if ((unsigned)(b - 0x00800000) < 0x7F000000u) {
+                    esum[k] += (b >> 23);
+                    prod[k] = __int_as_float((b & 0x007fffff) | 0x3f800000);
+                } else {
+                    if (prod[k] == 0.0f || (b > 0 && b < 0x00800000)) zero_mask |= (1u << k);   // 0 or denormal
+                    else nan_mask |= (1u << k);                                             // negative, inf, NaN
+                    esum[k] += 127;
+                    prod[k] = 1.0f;
+                }
             }
         }
         ++nren;
@@ -217,92 +229,206 @@ struct LikeAcc {
 // pop_like: sum over sites of log(GL . HWE(A[s,k])) for every (individual, population)
 // (glassy_cy.pyx:12-21 + glassy.py:31-42).  One thread = one individual (column); a warp
 // = 32 consecutive columns at one site, so a site's GL row is read with one fully
-// coalesced 256-byte request per warp; the HWE triples of the site tile are computed once
-// per block into shared memory and read back as 128-bit broadcasts.
+// coalesced 256-byte request per warp, 8 sites in flight per thread.  The HWE triples of
+// the site tile are computed once per block into shared memory, packed by PAIRS of
+// populations {(h0a,h0b),(h1a,h1b)} + (h2a,h2b), so one evaluation pair costs
+// LDS.128 + LDS.64 + FMUL2 + 2 FFMA2 (likelihoods) + FMUL2 (running products): three issue
+// slots per evaluation; no logarithm (see LikeAcc).  HBM-bound up to K ~ 10, FP32-pipe
+// bound above.
 // grid.x = column groups (fast, so that co-scheduled blocks share the AF tile in L2),
 // grid.y = site splits.  partials[split][col][K] (float64) are reduced in a fixed order
 // by reduce_partials_kernel - deterministic, no atomics.
 // ---------------------------------------------------------------------------------------
-template <int KT, int R>
+template <int KT>
+struct LikeAcc2 {                       // LikeAcc over packed pairs of populations
+    static constexpr int KP = (KT + 1) / 2;
+    f32x2 prod[KP];
+    int esum[2 * KP];
+    unsigned zero_mask, nan_mask;
+    int nren;
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int q = 0; q < KP; ++q) { prod[q] = pack2(1.0f, 1.0f); esum[2 * q] = esum[2 * q + 1] = 0; }
+        zero_mask = nan_mask = 0u; nren = 0;
+    }
+    __device__ __forceinline__ float renorm1(float p, int k) {
+        int b = __float_as_int(p);
+        if ((unsigned)(b - 0x00800000) < 0x7F000000u) {
+            esum[k] += (b >> 23);
+            return __int_as_float((b & 0x007fffff) | 0x3f800000);
+        }
+        if (p == 0.0f || (b > 0 && b < 0x00800000)) zero_mask |= (1u << k);
+        else nan_mask |= (1u << k);
+        esum[k] += 127;
+        return 1.0f;
+    }
+    __device__ __forceinline__ void renorm() {
+        // fast path: every product is a positive normal number (one unsigned max per slot decides)
+        unsigned worst = 0u;
+#pragma unroll
+        for (int q = 0; q < KP; ++q) {
+            float2 v = unpack2(prod[q]);
+            worst = max(worst, (unsigned)(__float_as_int(v.x) - 0x00800000));
+            worst = max(worst, (unsigned)(__float_as_int(v.y) - 0x00800000));
+        }
+        if (worst < 0x7F000000u) {
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                float2 v = unpack2(prod[q]);
+                int b0 = __float_as_int(v.x), b1 = __float_as_int(v.y);
+                esum[2 * q] += (b0 >> 23);
+                esum[2 * q + 1] += (b1 >> 23);
+                prod[q] = pack2(__int_as_float((b0 & 0x007fffff) | 0x3f800000), __int_as_float((b1 & 0x007fffff) | 0x3f800000));
+            }
+        } else {                                               // rare: a zero / negative / NaN factor somewhere
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                float2 v = unpack2(prod[q]);
+                prod[q] = pack2(renorm1(v.x, 2 * q), renorm1(v.y, 2 * q + 1));
+            }
+        }
+        ++nren;
+    }
+    __device__ __forceinline__ double value(int k) const {
+        if (nan_mask & (1u << k)) return __longlong_as_double(0x7ff8000000000000LL);
+        if (zero_mask & (1u << k)) return __longlong_as_double(0xfff0000000000000LL);
+        float2 v = unpack2(prod[k >> 1]);
+        double e = (double)(esum[k] - 127 * nren);
+        return (e + log2((double)((k & 1) ? v.y : v.x))) * 0.693147180559945309417232121458;
+    }
+};
+
+// One thread carries I individuals (columns col, col+32, ...): the shared-memory HWE pair is
+// read once per I evaluation pairs.  A broadcast LDS still delivers 24 B to every lane, and at
+// one individual per thread that delivered-byte rate (128 B/clk/SM), not issue, is the limit
+// (measured: 2.1e12 evaluations/s at I = 1).
+template <int KT, int R, int I, bool FULL>
+__device__ __forceinline__ void pop_like_tile(const float2* const (&Gcol)[I], int ldg, long s0, long s_end,
+                                              int wy, int wy_count, int per_warp,
+                                              const ulonglong2* __restrict__ HA, const f32x2* __restrict__ HB,
+                                              LikeAcc2<KT> (&acc)[I])
+{
+    constexpr int KP = (KT + 1) / 2;
+    constexpr int PF = (I >= 4) ? 4 : 8;                  // sites prefetched per thread
+    for (int u0 = 0; u0 < per_warp; u0 += PF) {
+        float2 g[PF][I];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            long s = s0 + wy + (long)wy_count * (u0 + u);
+#pragma unroll
+            for (int i = 0; i < I; ++i) {
+                if (FULL || s < s_end) g[u][i] = ld_stream2(Gcol[i] + s * (long)ldg);
+                else g[u][i] = make_float2(1.0f, 0.0f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int sl = wy + wy_count * (u0 + u);
+            if (FULL || s0 + sl < s_end) {                    // warp-uniform
+                float g0[I], g1[I], g2[I];
+#pragma unroll
+                for (int i = 0; i < I; ++i) { g0[i] = g[u][i].x; g1[i] = g[u][i].y; g2[i] = third_gl(g0[i], g1[i]); }
+#pragma unroll
+                for (int q = 0; q < KP; ++q) {
+                    const ulonglong2 h = HA[sl * KP + q];
+                    const f32x2 h2 = HB[sl * KP + q];
+#pragma unroll
+                    for (int i = 0; i < I; ++i) {
+                        f32x2 like = ffma2(pack2(g0[i], g0[i]), h.x, ffma2(pack2(g1[i], g1[i]), h.y, fmul2(pack2(g2[i], g2[i]), h2)));
+                        acc[i].prod[q] = fmul2(acc[i].prod[q], like);
+                    }
+                }
+            }
+            if (((u0 + u + 1) % R) == 0) {
+#pragma unroll
+                for (int i = 0; i < I; ++i) acc[i].renorm();
+            }
+        }
+    }
+}
+
+template <int KT, int R, int I>
 __global__ void __launch_bounds__(kPopLikeThreads)
 pop_like_kernel(const float2* __restrict__ G, int ldg, long M,
                 const float* __restrict__ A, int K, int k0,
-                int wx,                                  // column groups per block (power of two <= 8)
+                int wx,                                  // column groups (of 32*I) per block (power of two <= 8)
                 long sites_per_block,
-                long part_mod, long part_rem, long site_offset,
                 double* __restrict__ partials)
 {
+    constexpr int KP = (KT + 1) / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* H = reinterpret_cast<float4*>(smem_raw);                 // [TS][KT]
-    double* red = reinterpret_cast<double*>(H + kPopLikeTS * KT);    // [8][32][4]
+    ulonglong2* HA = reinterpret_cast<ulonglong2*>(smem_raw);        // [TS][KP]
+    f32x2* HB = reinterpret_cast<f32x2*>(HA + kPopLikeTS * KP);      // [TS][KP]
+    double* red = reinterpret_cast<double*>(HB + kPopLikeTS * KP);   // [8][32][4]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wy_count = (kPopLikeThreads / 32) / wx;
     const int cgx = warp % wx, wy = warp / wx;
-    const int col = (blockIdx.x * wx + cgx) * 32 + lane;
-    const bool col_ok = col < ldg;
+    const int col_base = (blockIdx.x * wx + cgx) * 32 * I + lane;
+    const float2* Gcol[I];
+    bool col_ok[I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        int c = col_base + 32 * i;
+        col_ok[i] = c < ldg;
+        Gcol[i] = G + (col_ok[i] ? c : ldg - 1);         // out-of-range slots read a valid column and are never stored
+    }
     const long s_begin = (long)blockIdx.y * sites_per_block;
     const long s_end = min(M, s_begin + sites_per_block);
 
-    LikeAcc<KT> acc;
-    acc.init();
+    LikeAcc2<KT> acc[I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) acc[i].init();
 
     const int per_warp = kPopLikeTS / wy_count;       // sites of a tile handled by one warp (multiple of 8)
     for (long s0 = s_begin; s0 < s_end; s0 += kPopLikeTS) {
         __syncthreads();
-        for (int e = threadIdx.x; e < kPopLikeTS * KT; e += kPopLikeThreads) {
-            int sl = e / KT, kk = e - sl * KT;
+        for (int e = threadIdx.x; e < kPopLikeTS * KP; e += kPopLikeThreads) {
+            int sl = e / KP, q = e - sl * KP;
             long s = s0 + sl;
-            float a = 0.5f;
-            if (s < s_end && k0 + kk < K) a = __ldg(&A[s * K + k0 + kk]);
-            float om = 1.0f - a;
-            H[e] = make_float4(om * om, 2.0f * a * om, a * a, 0.f);
+            float hh[2][3];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int k = k0 + 2 * q + h;
+                hh[h][0] = hh[h][1] = hh[h][2] = 1.0f;      // dummy slot: likelihood 1
+                if (s < s_end && 2 * q + h < KT && k < K) {
+                    float a = __ldg(&A[s * K + k]);
+                    float om = 1.0f - a;
+                    hh[h][0] = om * om; hh[h][1] = 2.0f * a * om; hh[h][2] = a * a;
+                }
+            }
+            ulonglong2 v;
+            v.x = pack2(hh[0][0], hh[1][0]); v.y = pack2(hh[0][1], hh[1][1]);
+            HA[e] = v;
+            HB[e] = pack2(hh[0][2], hh[1][2]);
         }
         __syncthreads();
-        for (int u0 = 0; u0 < per_warp; u0 += 8) {
-            float2 g[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                long s = s0 + wy + (long)wy_count * (u0 + u);
-                g[u] = make_float2(1.0f, 0.0f);
-                if (col_ok && s < s_end) g[u] = ld_stream2(&G[s * (long)ldg + col]);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                int sl = wy + wy_count * (u0 + u);
-                long s = s0 + sl;
-                bool use = s < s_end;
-                if (part_mod > 1) use = use && ((site_offset + s) % part_mod == part_rem);
-                if (use) {                                        // warp-uniform
-                    float g0 = g[u].x, g1 = g[u].y, g2 = third_gl(g0, g1);
-#pragma unroll
-                    for (int kk = 0; kk < KT; ++kk) {
-                        float4 h = H[sl * KT + kk];
-                        float like = fmaf(g0, h.x, fmaf(g1, h.y, g2 * h.z));
-                        acc.prod[kk] *= like;
-                    }
-                }
-                if (((u + 1) % R) == 0) acc.renorm();
-            }
-        }
+        if (col_base - lane >= ldg) continue;             // the whole warp is past the last column (warp-uniform)
+        if (s0 + kPopLikeTS <= s_end) pop_like_tile<KT, R, I, true>(Gcol, ldg, s0, s_end, wy, wy_count, per_warp, HA, HB, acc);
+        else pop_like_tile<KT, R, I, false>(Gcol, ldg, s0, s_end, wy, wy_count, per_warp, HA, HB, acc);
     }
-    acc.renorm();   // brings every slot to a known state (also folds a trailing partial group)
+#pragma unroll
+    for (int i = 0; i < I; ++i) acc[i].renorm();   // brings every slot to a known state (also folds a trailing partial group)
 
     // fixed-order reduction over the wy_count warps that share this column group
-    for (int kk0 = 0; kk0 < KT; kk0 += 4) {
-        __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (kk0 + q < KT) red[(warp * 32 + lane) * 4 + q] = acc.value(kk0 + q);
-        __syncthreads();
-        if (wy == 0 && col_ok) {
+    for (int i = 0; i < I; ++i) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                int kk = kk0 + q;
-                if (kk < KT && k0 + kk < K) {
-                    double v = 0.0;
-                    for (int w = 0; w < wy_count; ++w) v += red[((w * wx + cgx) * 32 + lane) * 4 + q];
-                    partials[((long)blockIdx.y * ldg + col) * K + k0 + kk] = v;
+        for (int kk0 = 0; kk0 < KT; kk0 += 4) {
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (kk0 + q < KT) red[(warp * 32 + lane) * 4 + q] = acc[i].value(kk0 + q);
+            __syncthreads();
+            if (wy == 0 && col_ok[i]) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int kk = kk0 + q;
+                    if (kk < KT && k0 + kk < K) {
+                        double v = 0.0;
+                        for (int w = 0; w < wy_count; ++w) v += red[((w * wx + cgx) * 32 + lane) * 4 + q];
+                        partials[((long)blockIdx.y * ldg + col_base + 32 * i) * K + k0 + kk] = v;
+                    }
                 }
             }
         }
@@ -354,26 +480,44 @@ loo_like_kernel(const float2* __restrict__ G, int ldg, long M,
     LikeAcc<KT> acc;
     acc.init();
     int cnt = 0;
-    for (long s = s_begin + wy; s < s_end; s += wy_count) {
-        bool use = true;
-        if (part_mod > 1) use = ((site_offset + s) % part_mod == part_rem);
-        if (use) {
-            float2 g = make_float2(1.0f, 0.0f);
-            if (col_ok) g = ld_stream2(&G[s * (long)ldg + col]);
-            float g0 = g.x, g1 = g.y, g2 = third_gl(g0, g1);
-            const float* frow = Fx + s * (long)ldf;
+    constexpr int PF = (KT > 10) ? 2 : 4;                  // sites in flight per thread (GL + KT state gathers each)
+    const float2* Gc = G + (col_ok ? col : ldg - 1);
+    const long s_stop = (col - lane >= ldg) ? s_begin : s_end;      // a warp entirely past the last column does nothing
+    for (long sb = s_begin + wy; sb < s_stop; sb += (long)wy_count * PF) {
+        float2 g[PF];
+        float a[PF][KT];
+        bool use[PF];
 #pragma unroll
-            for (int kk = 0; kk < KT; ++kk) {
-                float a = __ldg(&frow[rcol[kk]]);
-                float om = 1.0f - a;
-                float like = fmaf(g0, om * om, fmaf(g1, 2.0f * a * om, g2 * (a * a)));
-                acc.prod[kk] *= like;
+        for (int u = 0; u < PF; ++u) {
+            long s = sb + (long)wy_count * u;
+            use[u] = s < s_end;
+            if (part_mod > 1) use[u] = use[u] && ((site_offset + s) % part_mod == part_rem);
+            g[u] = make_float2(1.0f, 0.0f);
+            if (use[u]) {
+                g[u] = ld_stream2(Gc + s * (long)ldg);
+                const float* frow = Fx + s * (long)ldf;
+#pragma unroll
+                for (int kk = 0; kk < KT; ++kk) a[u][kk] = __ldg(&frow[rcol[kk]]);
             }
-            if (++cnt == R) { acc.renorm(); cnt = 0; }
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            if (use[u]) {                                     // warp-uniform
+                float g0 = g[u].x, g1 = g[u].y, g2 = third_gl(g0, g1);
+#pragma unroll
+                for (int kk = 0; kk < KT; ++kk) {
+                    float av = a[u][kk];
+                    float om = 1.0f - av;
+                    float like = fmaf(g0, om * om, fmaf(g1, 2.0f * av * om, g2 * (av * av)));
+                    acc.prod[kk] *= like;
+                }
+                if (++cnt == R) { acc.renorm(); cnt = 0; }
+            }
         }
     }
     acc.renorm();
 
+#pragma unroll
     for (int kk0 = 0; kk0 < KT; kk0 += 4) {
         __syncthreads();
 #pragma unroll
@@ -431,6 +575,7 @@ __device__ __forceinline__ float em_term(float g0, float g1, float g2, const EmC
 // squared-change sum to kept sites.
 // ---------------------------------------------------------------------------------------
 constexpr int kMaxKq = 4;   // K <= 128
+constexpr int kEmPopU = 8;  // sites per warp pass: 8 independent 256-byte row requests in flight per lane
 __global__ void __launch_bounds__(256)
 em_pop_step_kernel(const float2* __restrict__ G, int ldg, long M,
                    const PopDesc* __restrict__ pops, int K,
@@ -439,31 +584,54 @@ em_pop_step_kernel(const float2* __restrict__ G, int ldg, long M,
                    double* __restrict__ partials)        // [gridDim.x][K]
 {
     __shared__ float sh[8][kMaxKq * 32];
+    constexpr int U = kEmPopU;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float ssq[kMaxKq];
 #pragma unroll
     for (int q = 0; q < kMaxKq; ++q) ssq[q] = 0.f;
 
-    for (long s = (long)blockIdx.x * 8 + warp; s < M; s += (long)gridDim.x * 8) {
-        const float2* row = G + s * (long)ldg;
+    for (long s0 = ((long)blockIdx.x * 8 + warp) * U; s0 < M; s0 += (long)gridDim.x * 8 * U) {
+        const float2* row0 = G + s0 * (long)ldg;
         for (int k = 0; k < K; ++k) {
             if (!active[k]) continue;
-            PopDesc pd = pops[k];
-            float f = Fpop[s * K + k];
-            EmCoef c = em_coef(f);
-            float sum = 0.f;
-            for (int j = lane; j < pd.n; j += 32) {
-                float2 g = ld_stream2(&row[pd.col0 + j]);
-                sum += em_term(g.x, g.y, third_gl(g.x, g.y), c);
+            const PopDesc pd = pops[k];
+            float f[U], sum[U];
+            EmCoef c[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                f[u] = (s0 + u < M) ? Fpop[(s0 + u) * K + k] : 0.25f;
+                c[u] = em_coef(f[u]);
+                sum[u] = 0.f;
             }
-            sum = warp_sum(sum);
-            float fnew = __fdiv_rn(sum, (float)pd.n);
-            float d = fnew - f;
+            for (int j = lane; j < pd.n; j += 32) {
+                float2 g[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    g[u] = make_float2(1.0f / 3, 1.0f / 3);
+                    if (s0 + u < M) g[u] = ld_stream2(row0 + (long)u * ldg + pd.col0 + j);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) sum[u] += em_term(g[u].x, g[u].y, third_gl(g[u].x, g[u].y), c[u]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+            }
+            float dsq = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (s0 + u < M) {
+                    float fnew = __fdiv_rn(sum[u], (float)pd.n);
+                    float d = fnew - f[u];
+                    dsq += d * d;
+                    if (lane == 0) Fpop[(s0 + u) * K + k] = fnew;
+                }
+            }
             if (lane == (k & 31)) {
 #pragma unroll
-                for (int q = 0; q < kMaxKq; ++q) if (q == (k >> 5)) ssq[q] += d * d;
+                for (int q = 0; q < kMaxKq; ++q) if (q == (k >> 5)) ssq[q] += dsq;
             }
-            if (lane == 0) Fpop[s * K + k] = fnew;
         }
     }
 #pragma unroll
@@ -710,6 +878,7 @@ __device__ __forceinline__ float fisher_term(float g0, float g1, float th, float
     return fmaf(x, x, -y);
 }
 
+constexpr int kFisherU = 4;  // sites per warp pass
 __global__ void __launch_bounds__(256)
 fisher_kernel(const float2* __restrict__ G, int ldg, long M,
               const PopDesc* __restrict__ pops, int K,
@@ -719,29 +888,52 @@ fisher_kernel(const float2* __restrict__ G, int ldg, long M,
               double* __restrict__ ind_partials)           // [gridDim.x][ldg]
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int U = kFisherU;
     float* accw = reinterpret_cast<float*>(smem_raw);      // [warps][ldg]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* mine = accw + (size_t)warp * ldg;
     for (int c = lane; c < ldg; c += 32) mine[c] = 0.f;
     __syncwarp();
-    for (long s = (long)blockIdx.x * warps_per_block + warp; s < M; s += (long)gridDim.x * warps_per_block) {
-        const float2* row = G + s * (long)ldg;
+    for (long s0 = ((long)blockIdx.x * warps_per_block + warp) * U; s0 < M; s0 += (long)gridDim.x * warps_per_block * U) {
+        const float2* row0 = G + s0 * (long)ldg;
         for (int k = 0; k < K; ++k) {
-            PopDesc pd = pops[k];
-            float th = __ldg(&A[s * K + k]);
-            float om = 1.0f - th;
-            float w = 0.5f * th * om;
-            float sum = 0.f;
-            for (int j = lane; j < pd.n; j += 32) {
-                float2 g = ld_stream2(&row[pd.col0 + j]);
-                float term = fisher_term(g.x, g.y, th, om);
-                sum += term;
-                mine[pd.col0 + j] += term * w;
+            const PopDesc pd = pops[k];
+            float th[U], om[U], w[U], sum[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                th[u] = (s0 + u < M) ? __ldg(&A[(s0 + u) * K + k]) : 0.5f;
+                om[u] = 1.0f - th[u];
+                w[u] = 0.5f * th[u] * om[u];
+                sum[u] = 0.f;
             }
-            sum = warp_sum(sum);
+            for (int j = lane; j < pd.n; j += 32) {
+                float2 g[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    g[u] = make_float2(1.0f / 3, 1.0f / 3);
+                    if (s0 + u < M) g[u] = ld_stream2(row0 + (long)u * ldg + pd.col0 + j);
+                }
+                float ind = 0.f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    float term = fisher_term(g[u].x, g[u].y, th[u], om[u]);
+                    if (s0 + u < M) { sum[u] += term; ind = fmaf(term, w[u], ind); }
+                }
+                mine[pd.col0 + j] += ind;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+            }
             if (lane == 0) {
-                f_obs[s * K + k] = sum;
-                ne_obs[s * K + k] = 0.5f * sum * th * om;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (s0 + u < M) {
+                        f_obs[(s0 + u) * K + k] = sum[u];
+                        ne_obs[(s0 + u) * K + k] = 0.5f * sum[u] * th[u] * om[u];
+                    }
+                }
             }
         }
     }

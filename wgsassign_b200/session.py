@@ -45,6 +45,7 @@ def context(L, pop_of_ind=None, K=0):
         ctx = _lib.Context(device_index())
         _state["ctx"] = ctx
     n = L.shape[1] // 2
+    _state.update(key=None, ds_key=None, ad_key=None)      # nothing is trusted until the upload has succeeded
     if pop_of_ind is None:
         ctx.set_pops(np.zeros(n, np.int32), 0)
     else:
@@ -62,6 +63,7 @@ def context(L, pop_of_ind=None, K=0):
 def with_downsampled(ctx, L_ds):
     key = _sig(L_ds)
     if _state["ds_key"] != key:
+        _state["ds_key"] = None
         ctx.upload_gl(L_ds, 1)
         _state["ds_key"] = key
     return ctx
@@ -70,6 +72,7 @@ def with_downsampled(ctx, L_ds):
 def with_ad(ctx, AD):
     key = _sig(AD)
     if _state["ad_key"] != key:
+        _state["ad_key"] = None                            # a failed upload must not leave a stale key behind
         ctx.upload_ad(np.ascontiguousarray(AD, dtype=np.int32))
         _state["ad_key"] = key
     return ctx
