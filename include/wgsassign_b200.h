@@ -159,6 +159,11 @@ const char *wgs_beagle_site(const wgs_beagle *b, int64_t s);
 int32_t     wgs_beagle_copy(const wgs_beagle *b, float *L_out); /* [sites, 2*inds] */
 void        wgs_beagle_close(wgs_beagle *b);
 
+/* Diagnostic read stream over the resident GL matrix (no arithmetic): mode 0 = flat 128-bit
+ * read of the whole matrix, mode 1 = one population slab at a time (the access pattern of the
+ * per-population kernels).  Returns the device time of one pass and the bytes it read. */
+int32_t wgs_debug_stream(wgs_ctx *ctx, int32_t mode, double *ms_out, double *bytes_out);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t wgs_launch_count(const wgs_ctx *ctx);

@@ -59,6 +59,7 @@ SYMBOLS = {
     "wgs_beagle_site": (ctypes.c_char_p, [_vp, _i64]),
     "wgs_beagle_copy": (_i32, [_vp, _vp]),
     "wgs_beagle_close": (None, [_vp]),
+    "wgs_debug_stream": (_i32, [_vp, _i32, _vp, _vp]),
     "wgs_launch_count": (_i64, [_vp]),
     "wgs_timing_reset": (_i32, [_vp, _i32]),
     "wgs_timing_get": (_i32, [_vp, ctypes.c_char_p, _vp, _vp]),
@@ -260,6 +261,12 @@ class Context:
 
     def zscore_deep_sites(self):
         return int(lib().wgs_zscore_deep_sites(self._h))
+
+    def debug_stream(self, mode):
+        ms = ctypes.c_double(0)
+        nb = ctypes.c_double(0)
+        self._ck(lib().wgs_debug_stream(self._h, int(mode), ctypes.byref(ms), ctypes.byref(nb)))
+        return ms.value, nb.value
 
     # ---- instrumentation ----
     def launch_count(self):

@@ -355,7 +355,7 @@ int launch_pop_like_i(wgs_ctx* ctx, const float2* G, long M, const float* dA, in
     constexpr int KP = (KT + 1) / 2;
     size_t smem = (size_t)kPopLikeTS * KP * (sizeof(ulonglong2) + sizeof(f32x2)) + 8 * 32 * 4 * sizeof(double);
     auto kern = pop_like_kernel<KT, R, I>;
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAUNCH("pop_like", kern, dim3(c.gx, c.gy), kPopLikeThreads, smem, ctx->stream,
            G, ctx->ldg, M, dA, K, k0, c.wx, c.sites_per_block, partials);
     {   // algorithmic: every (g0,g1) pair once per pass + this pass's AF columns; one evaluation per (site, ind, pop)
@@ -484,20 +484,34 @@ int em_after_step(wgs_ctx* ctx, EmState& st, double tole, int iteration, const d
     return 0;
 }
 
-// Per-population EM on the resident G: Fpop [M][K] (device) <- converged, UNclipped f.
-int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* Fpop, std::vector<int>& iters_out)
+// Per-population EM on the resident G: FT [K][M] (device, population-major) <- converged, UNclipped f.
+int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>& iters_out)
 {
     const long M = ctx->M();
     const int K = std::max(ctx->K, 1);
     if (K > kMaxKq * 32) return fail(ctx, "more than %d populations not supported", kMaxKq * 32);
-    int nblocks = (int)std::max<long>(1, std::min<long>((M + 8 * kEmPopU - 1) / (8 * kEmPopU), (long)ctx->num_sm * 8));
+    int nmax = 1;
+    for (int k = 0; k < K; ++k) nmax = std::max(nmax, ctx->pops[k].n);
+    int row16 = (nmax + 3) / 4 * 2;                             // widest slab in 16-byte units ...
+    while (row16 % 8 != kEmT % 8) ++row16;                      // ... padded so that kEmT threads x 2 rows hit 8 distinct bank groups
+    int R = 128;
+    while (R > 8 && 2 * (size_t)R * row16 * 16 > 110 * 1024) R /= 2;
+    size_t smem = 2 * (size_t)R * row16 * 16;
+    if (smem > 220 * 1024) return fail(ctx, "population of %d individuals exceeds the EM shared-memory tile", nmax);
+    // always opt in: static + dynamic shared memory together may cross the 48 KB default limit
+    CU(cudaFuncSetAttribute(em_pop_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, em_pop_step_kernel, R * kEmT, smem));
+    long ntiles = (M + R - 1) / R;
+    // one full wave of persistent blocks: gx * K <= resident slots
+    int gx = (int)std::max<long>(1, std::min<long>(ntiles, ((long)ctx->num_sm * std::max(occ, 1)) / K));
     EmState st;
-    if (em_state_init(ctx, st, K, K, nblocks, std::vector<int>(K, 1))) return 1;
-    LAUNCH("fill", fill_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, Fpop, M * K, 0.25f);
+    if (em_state_init(ctx, st, K, K, gx, std::vector<int>(K, 1))) return 1;
+    LAUNCH("fill", fill_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, FT, M * K, 0.25f);
     int n_active = K;
     for (int it = 1; it <= iter && n_active > 0; ++it) {
-        LAUNCH("em_pop", em_pop_step_kernel, nblocks, 256, 0, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, Fpop,
-               st.active.as<int>(), st.partials.as<double>());
+        LAUNCH("em_pop", em_pop_step_kernel, dim3(gx, K), R * kEmT, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT,
+               st.active.as<int>(), row16, st.partials.as<double>());
         {   // 8 B per (site, individual of an active population) + f read/write
             double inds = 0, act = 0;
             for (int k = 0; k < K; ++k) if (st.h_active[k]) { inds += ctx->pops[k].n; act += 1; }
@@ -530,7 +544,7 @@ int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
     best.passes = passes;
     best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float);
     if (best.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", n);
-    if (best.smem > 48 * 1024) CU(cudaFuncSetAttribute(loo_em_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem));
+    if (best.smem > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem));
     int occ = 1;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step_kernel, best.block, best.smem));
     best.grid = ctx->num_sm * std::max(occ, 1);
@@ -771,9 +785,11 @@ int32_t wgs_ref_af(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32
     if (dev_alloc(ctx, &ctx->d_af, (size_t)std::max<long>(M, 1) * K)) return 1;
     ctx->af_rows = M; ctx->af_cols = K;
     float* F = ctx->d_af;
+    DevBuf FT;
+    if (buf_alloc(ctx, FT, (size_t)std::max<long>(M, 1) * K * sizeof(float))) return 1;
     std::vector<int> its;
     tr.lap("alloc");
-    if (run_em_pop(ctx, iter, tole, F, its)) return 1;
+    if (run_em_pop(ctx, iter, tole, FT.as<float>(), its)) return 1;
     tr.lap("em");
     std::vector<float> lo(K), hi(K);
     for (int k = 0; k < K; ++k) { double l = 1.0 / (2.0 * (ctx->pops[k].n + 1)); lo[k] = (float)l; hi[k] = (float)(1.0 - l); }
@@ -781,8 +797,8 @@ int32_t wgs_ref_af(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32
     if (buf_alloc(ctx, dlo, K * sizeof(float)) || buf_alloc(ctx, dhi, K * sizeof(float))) return 1;
     CU(cudaMemcpyAsync(dlo.p, lo.data(), K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(dhi.p, hi.data(), K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH("clip", clip_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F, K, K, M,
-           dlo.as<float>(), dhi.as<float>());
+    LAUNCH("clip", clip_transpose_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, FT.as<float>(), M, K,
+           dlo.as<float>(), dhi.as<float>(), 1, F);
     if (af_out) CU(cudaMemcpyAsync(af_out, F, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
@@ -974,19 +990,29 @@ int32_t wgs_fisher_partial(wgs_ctx* ctx, const float* af, float* f_obs, float* n
     if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for reference-panel operators");
     const long M = ctx->M();
     const int K = ctx->K, ldg = ctx->ldg;
-    int warps = 8;
-    while (warps > 1 && (size_t)warps * ldg * sizeof(float) > 96 * 1024) warps /= 2;
-    size_t smem = (size_t)warps * ldg * sizeof(float);
-    if (smem > 200 * 1024) return fail(ctx, "too many individuals for the Fisher kernel's shared-memory accumulators");
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fisher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nblocks = (int)std::max<long>(1, std::min<long>((M + warps * kFisherU - 1) / (warps * kFisherU), (long)ctx->num_sm * 4));
+    int nmax = 1;
+    for (int k = 0; k < K; ++k) nmax = std::max(nmax, ctx->pops[k].n);
+    int row16 = (nmax + 3) / 4 * 2;
+    while (row16 % 8 != kEmT % 8) ++row16;
+    const int accw_ld = (nmax + 3) / 4 * 4 + 4;
+    int R = 128;
+    while (R > 8 && 2 * (size_t)R * row16 * 16 > 100 * 1024) R /= 2;
+    const int nw = R * kEmT / 32;
+    size_t smem = 2 * (size_t)R * row16 * 16 + (size_t)nw * accw_ld * sizeof(float);
+    if (smem > 220 * 1024) return fail(ctx, "population of %d individuals exceeds the Fisher shared-memory tile", nmax);
+    CU(cudaFuncSetAttribute(fisher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fisher_kernel, R * kEmT, smem));
+    long ntiles = (M + R - 1) / R;
+    int nblocks = (int)std::max<long>(1, std::min<long>(ntiles, ((long)ctx->num_sm * std::max(occ, 1)) / K));
     DevBuf dA, dF, dNe, partials, sums;
     if (buf_alloc(ctx, dA, (size_t)M * K * sizeof(float)) || buf_alloc(ctx, dF, (size_t)M * K * sizeof(float)) ||
         buf_alloc(ctx, dNe, (size_t)M * K * sizeof(float)) || buf_alloc(ctx, partials, (size_t)nblocks * ldg * sizeof(double)) ||
         buf_alloc(ctx, sums, ldg * sizeof(double))) return 1;
     CU(cudaMemcpyAsync(dA.p, af, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH("fisher", fisher_kernel, nblocks, warps * 32, smem, ctx->stream, ctx->G[0], ldg, M, ctx->d_pops, K, dA.as<float>(),
-           dF.as<float>(), dNe.as<float>(), warps, partials.as<double>());
+    CU(cudaMemsetAsync(partials.p, 0, (size_t)nblocks * ldg * sizeof(double), ctx->stream));   // pad columns are never written
+    LAUNCH("fisher", fisher_kernel, dim3(nblocks, K), R * kEmT, smem, ctx->stream, ctx->G[0], ldg, M, ctx->d_pops, K, dA.as<float>(),
+           dF.as<float>(), dNe.as<float>(), row16, accw_ld, partials.as<double>());
     add_work(ctx, "fisher", (double)M * ctx->N * 8.0 + (double)M * K * 12.0, (double)M * ctx->N);
     LAUNCH("reduce", reduce_partials_kernel, grid_for(ldg, 256, 64), 256, 0, ctx->stream, partials.as<double>(), nblocks, (long)ldg,
            sums.as<double>());
@@ -1210,6 +1236,35 @@ int32_t wgs_zscore_classes(wgs_ctx* ctx, int32_t ind, int32_t max_rows, int32_t*
     int n = (int)v.size() / 4;
     *n_rows = n;
     for (int r = 0; r < std::min(n, max_rows); ++r) memcpy(rows_out + 4 * r, v.data() + 4 * r, 4 * sizeof(int));
+    return 0;
+}
+
+int32_t wgs_debug_stream(wgs_ctx* ctx, int32_t mode, double* ms_out, double* bytes_out)
+{
+    cudaSetDevice(ctx->device);
+    if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
+    const long M = ctx->M();
+    const int K = std::max(ctx->K, 1);
+    DevBuf sink;
+    if (buf_alloc(ctx, sink, 16)) return 1;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    dim3 grid = mode == 0 ? dim3(ctx->num_sm * 8) : dim3(std::max(1, ctx->num_sm * 8 / K), K);
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(a, ctx->stream);
+        LAUNCH("probe", stream_probe_kernel, grid, 256, 0, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, mode, sink.as<float>());
+        cudaEventRecord(b, ctx->stream);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_out = ms;
+    double bytes = 0;
+    if (mode == 0) bytes = (double)M * ctx->ldg * 8.0;
+    else for (int k = 0; k < K; ++k) bytes += (double)M * ((ctx->pops[k].n + 1) / 2) * 16.0;
+    *bytes_out = bytes;
+    CU(cudaGetLastError());
     return 0;
 }
 
