@@ -525,29 +525,58 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
     return 0;
 }
 
-struct LooLaunch { int block, rows_per_pass, passes, grid; size_t smem; };
+struct LooLaunch { int block, rows_per_pass, passes, grid, U; bool big; size_t smem; };
+
+// blocks of <= 384 threads are compiled for 3 resident blocks per SM (<= 56 registers), larger ones for 2
+template <int U> int loo_prepare_t(wgs_ctx* ctx, LooLaunch& L)
+{
+    int occ = 1;
+    if (L.big) {
+        if (L.smem > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step_kernel<U, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step_kernel<U, 512, 2>, L.block, L.smem));
+    } else {
+        if (L.smem > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step_kernel<U, 384, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step_kernel<U, 384, 3>, L.block, L.smem));
+    }
+    L.grid = ctx->num_sm * std::max(occ, 1);
+    return 0;
+}
+
 int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
 {
-    LooLaunch best{0, 0, 1, 0, 0};
+    LooLaunch best{0, 0, 1, 0, 4, false, 0};
+    const int npairs = (n + 1) / 2;                               // threads per site row (two problems each)
     double best_u = -1;
     for (int bd = 128; bd <= 512; bd += 32) {
-        int rpp = bd / n;
+        int rpp = bd / npairs;
         if (rpp < 1) continue;
-        double u = (double)(rpp * n) / bd;
+        double u = (double)(rpp * npairs) / bd;
+        if (bd > 384 && best_u >= 0.88) break;                    // prefer the 3-blocks-per-SM variant unless it idles > 12 % of its threads
         if (u > best_u + 1e-9) { best_u = u; best.block = bd; best.rows_per_pass = rpp; }
     }
-    if (best.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (512)", n);
-    int np = (n + 1) / 2, stride = np | 1;
+    if (best.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (1024)", n);
+    best.big = best.block > 384;
+    int np = (n + 1) / 2;
+    int pad_best = 1 << 30;
+    for (int U = 4; U <= 7; ++U) {                                // unroll factor that pads the pair loop least (ties: larger)
+        int pad = (np + U - 1) / U * U - np;
+        if (pad <= pad_best) { pad_best = pad; best.U = U; }
+    }
+    int npu = (np + best.U - 1) / best.U * best.U, stride = npu | 1;
     size_t row_bytes = (size_t)stride * 24;                     // 16 B (g0,g1 pairs) + 8 B (g2 pair) per pair
     int passes = kLooMaxPasses;
-    while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 20 * 1024) --passes;
+    while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 24 * 1024) --passes;
     best.passes = passes;
-    best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float);
+    best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float2);
     if (best.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", n);
-    if (best.smem > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem));
-    int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step_kernel, best.block, best.smem));
-    best.grid = ctx->num_sm * std::max(occ, 1);
+    int rc = 0;
+    switch (best.U) {
+        case 4: rc = loo_prepare_t<4>(ctx, best); break;
+        case 5: rc = loo_prepare_t<5>(ctx, best); break;
+        case 6: rc = loo_prepare_t<6>(ctx, best); break;
+        default: rc = loo_prepare_t<7>(ctx, best); break;
+    }
+    if (rc) return rc;
     *out = best;
     return 0;
 }
@@ -593,8 +622,22 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
             const LooLaunch& lc = cfgs[k];
             int TS = lc.rows_per_pass * lc.passes;
             long ntiles = (M + TS - 1) / TS;
-            LAUNCH("loo_em", loo_em_step_kernel, lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
-                   lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
+#define LOO_LAUNCH(UU)                                                                                                          \
+    do {                                                                                                                        \
+        if (lc.big)                                                                                                             \
+            LAUNCH("loo_em", (loo_em_step_kernel<UU, 512, 2>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n, \
+                   lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);           \
+        else                                                                                                                    \
+            LAUNCH("loo_em", (loo_em_step_kernel<UU, 384, 3>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n, \
+                   lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);           \
+    } while (0)
+            switch (lc.U) {
+                case 4: LOO_LAUNCH(4); break;
+                case 5: LOO_LAUNCH(5); break;
+                case 6: LOO_LAUNCH(6); break;
+                default: LOO_LAUNCH(7); break;
+            }
+#undef LOO_LAUNCH
             {   // the population's GL tile once + read/write of every active problem's f; n evaluations per active (site, problem)
                 double act = 0;
                 for (int j = 0; j < pd.n; ++j) act += st.h_active[pd.col0 + j] ? 1 : 0;

@@ -722,9 +722,13 @@ em_pop_step_kernel(const float2* __restrict__ G, int ldg, long M,
 // population's GL tile.  The tile is staged in shared memory by PAIRS of individuals,
 //   tA[site][pair] = {(g0_a,g0_b), (g1_a,g1_b)}   (128-bit)   tB[site][pair] = (g2_a,g2_b) (64-bit)
 // so that the four multiply-adds of two posterior terms issue as FMUL2 + 3 FFMA2; the two
-// reciprocals (MUFU.RCP) and the two accumulating FFMAs stay scalar.  All lanes of a warp
-// that share a site read the same address (broadcast).  Bound by the MUFU reciprocal rate
-// (16 per clock per SM), not by HBM.
+// reciprocals (MUFU.RCP) and the two accumulating FFMAs stay scalar.
+//
+// One thread owns TWO problems (the two members of pair ti) at one site and feeds both from
+// the same shared-memory read: a broadcast LDS still delivers its 24 bytes to every lane, and
+// with one problem per thread that delivered-byte rate (128 B/clk/SM) - not MUFU, not issue -
+// was the limit (83 % of it at 2.5e12 evaluations/s).  Two problems per read halve it and
+// leave the MUFU reciprocal rate (16 per clock per SM) as the binding unit.
 //
 // The left-out individual's own term is removed after the loop.  (sum - own) can cancel to
 // exactly 0 when nobody else carries the allele, and an exact 0 (or 1) would turn the next
@@ -732,14 +736,25 @@ em_pop_step_kernel(const float2* __restrict__ G, int ldg, long M,
 // [1e-12, 1-2^-24]; both are far outside the clipping range applied afterwards
 // (glassy.py:80-85) and 7 orders below the 1e-5 parity tolerance.
 //
-// Thread t < Bp owns problem i = t % n for the whole launch, so its squared change is a
-// register; partials[block][col] are reduced in fixed order by em_ssq_reduce_kernel.
+// A thread keeps its two problems for the whole launch, so their squared changes are
+// registers; partials[block][col] are reduced in fixed order by em_ssq_reduce_kernel.
 // mask (optional): uchar keep[M][ldg] - sites whose squared change counts (reference
 // z-score runs the EM on kept sites only, WGSassign.py:358-359; a site outside the mask
 // cannot influence another site, so it is simply skipped).
 // ---------------------------------------------------------------------------------------
 constexpr int kLooMaxPasses = 4;
-__global__ void __launch_bounds__(512)
+struct LooCoef { f32x2 H0, H1, H2; float h0, h1, h2; };
+__device__ __forceinline__ LooCoef loo_coef(float f) {
+    LooCoef c;
+    const float om = 1.0f - f;
+    c.h0 = 2.0f * om * om; c.h1 = 2.0f * f * om; c.h2 = 2.0f * f * f;
+    c.H0 = pack2(c.h0, c.h0); c.H1 = pack2(c.h1, c.h1); c.H2 = pack2(c.h2, c.h2);
+    return c;
+}
+// U = pairs per unrolled inner-loop trip; the tile rows are padded with zero-contribution pairs to a
+// multiple of U (the host picks the U in {4,5,6,7} that pads least), so there is no remainder loop.
+template <int U, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 loo_em_step_kernel(const float2* __restrict__ G, int ldg, long M,
                    int col0, int n, int rows_per_pass, int passes,
                    float* __restrict__ F, int ldf,              // [M][ldf], in place
@@ -749,41 +764,49 @@ loo_em_step_kernel(const float2* __restrict__ G, int ldg, long M,
                    long ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int np = (n + 1) >> 1;                                // pairs of individuals
-    const int stride = np | 1;                                  // odd: two rows never share a bank group
+    const int np = (n + 1) >> 1;                                // pairs of individuals = threads per site row
+    const int npu = (np + U - 1) / U * U;                       // padded to the unroll factor
+    const int stride = npu | 1;                                 // odd: two rows never share a bank group
     const int TS = rows_per_pass * passes;
     ulonglong2* tA = reinterpret_cast<ulonglong2*>(smem_raw);                   // [TS][stride]
     f32x2* tB = reinterpret_cast<f32x2*>(tA + (size_t)TS * stride);             // [TS][stride]
-    float* red = reinterpret_cast<float*>(tB + (size_t)TS * stride);            // [blockDim.x]
+    float2* red = reinterpret_cast<float2*>(tB + (size_t)TS * stride);          // [blockDim.x]
 
     const int t = threadIdx.x;
-    const int Bp = rows_per_pass * n;
-    const int i = t % n, r = t / n;
+    const int Bp = rows_per_pass * np;
+    const int ti = t % np, r = t / np;                          // this thread's pair (problems 2ti, 2ti+1) and row
     const bool worker = t < Bp;
-    const bool my_active = worker && active[col0 + i] != 0;
-    const float divisor = (float)(n - 1);
-    float ssq = 0.f;
+    const int cA = col0 + 2 * ti, cB = cA + 1;
+    const bool hasB = 2 * ti + 1 < n;
+    const bool actA = worker && active[cA] != 0;
+    const bool actB = worker && hasB && active[cB] != 0;
+    const bool any_act = actA || actB;
+    const float inv_div = 1.0f / (float)(n - 1);
+    float ssqA = 0.f, ssqB = 0.f;
 
     for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         const long s0 = tl * TS;
-        // this thread's f values for the tile: issued before the tile fill so that their
-        // latency overlaps it
-        float fv[kLooMaxPasses];
-        bool ok[kLooMaxPasses];
+        // this thread's f pairs for the tile: issued before the tile fill so that the latency overlaps it
+        float2 fv[kLooMaxPasses];
+        bool okA[kLooMaxPasses], okB[kLooMaxPasses];
 #pragma unroll
         for (int p = 0; p < kLooMaxPasses; ++p) {
-            long s = s0 + p * rows_per_pass + r;
-            ok[p] = my_active && p < passes && s < M;
-            if (ok[p] && mask) ok[p] = mask[s * (long)ldg + col0 + i] != 0;
-            fv[p] = 0.25f;
-            if (ok[p]) fv[p] = F[s * (long)ldf + col0 + i];
+            const long s = s0 + p * rows_per_pass + r;
+            const bool in = any_act && p < passes && s < M;
+            okA[p] = in && actA; okB[p] = in && actB;
+            if (in && mask) {
+                okA[p] = okA[p] && mask[s * (long)ldg + cA] != 0;
+                okB[p] = okB[p] && mask[s * (long)ldg + cB] != 0;
+            }
+            fv[p] = make_float2(0.25f, 0.25f);
+            if (okA[p] || okB[p]) fv[p] = *reinterpret_cast<const float2*>(&F[s * (long)ldf + cA]);
         }
         __syncthreads();                                        // previous tile fully consumed
-        for (int e = t; e < TS * np; e += blockDim.x) {
-            int sl = e / np, q = e - sl * np;
+        for (int e = t; e < TS * npu; e += blockDim.x) {
+            int sl = e / npu, q = e - sl * npu;
             long s = s0 + sl;
-            float4 g = make_float4(1.f, 0.f, 1.f, 0.f);
-            if (s < M) g = ld_stream4(reinterpret_cast<const float4*>(&G[s * (long)ldg + col0 + 2 * q]));
+            float4 g = make_float4(1.f, 0.f, 1.f, 0.f);         // (1,0,0): contributes exactly 0
+            if (s < M && q < np) g = ld_stream4(reinterpret_cast<const float4*>(&G[s * (long)ldg + col0 + 2 * q]));
             if (2 * q + 1 >= n) { g.z = 1.f; g.w = 0.f; }       // odd n: the pad partner contributes exactly 0
             ulonglong2 a;
             a.x = pack2(g.x, g.z);
@@ -794,50 +817,60 @@ loo_em_step_kernel(const float2* __restrict__ G, int ldg, long M,
         __syncthreads();
 #pragma unroll
         for (int p = 0; p < kLooMaxPasses; ++p) {
-            if (!ok[p]) continue;
+            if (!(okA[p] || okB[p])) continue;
             const int sl = p * rows_per_pass + r;
-            const float f = fv[p];
-            const float om = 1.0f - f;
-            const float H0 = 2.0f * om * om, H1 = 2.0f * f * om, H2 = 2.0f * f * f;
-            const f32x2 H0p = pack2(H0, H0), H1p = pack2(H1, H1), H2p = pack2(H2, H2);
+            const LooCoef ca = loo_coef(fv[p].x), cb = loo_coef(fv[p].y);
             const ulonglong2* rowA = tA + sl * stride;
             const f32x2* rowB = tB + sl * stride;
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-            for (int q = 0; q < np; ++q) {
-                ulonglong2 ab = rowA[q];
-                f32x2 num = ffma2(ab.y, H1p, fmul2(rowB[q], H2p));
-                f32x2 den = ffma2(ab.x, H0p, ffma2(ab.y, H1p, num));
-                float2 nn = unpack2(num), dd = unpack2(den);
-                a0 = fmaf(nn.x, fast_rcp(dd.x), a0);
-                a1 = fmaf(nn.y, fast_rcp(dd.y), a1);
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+            for (int q0 = 0; q0 < npu; q0 += U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const ulonglong2 ab = rowA[q0 + u];
+                    const f32x2 g2 = rowB[q0 + u];
+                    f32x2 numa = ffma2(ab.y, ca.H1, fmul2(g2, ca.H2));
+                    f32x2 numb = ffma2(ab.y, cb.H1, fmul2(g2, cb.H2));
+                    f32x2 dena = ffma2(ab.x, ca.H0, ffma2(ab.y, ca.H1, numa));
+                    f32x2 denb = ffma2(ab.x, cb.H0, ffma2(ab.y, cb.H1, numb));
+                    float2 na = unpack2(numa), da = unpack2(dena), nb = unpack2(numb), db = unpack2(denb);
+                    a0 = fmaf(na.x, fast_rcp(da.x), a0);
+                    a1 = fmaf(na.y, fast_rcp(da.y), a1);
+                    b0 = fmaf(nb.x, fast_rcp(db.x), b0);
+                    b1 = fmaf(nb.y, fast_rcp(db.y), b1);
+                }
             }
-            // own term, recomputed with the same operations so that it cancels what was added
-            float own;
+            // own terms (the two halves of pair ti), recomputed with the same operations so that they cancel
+            float ownA, ownB;
             {
-                ulonglong2 ab = rowA[i >> 1];
-                float2 g0 = unpack2(ab.x), g1 = unpack2(ab.y), g2 = unpack2(rowB[i >> 1]);
-                bool hi = i & 1;
-                float x0 = hi ? g0.y : g0.x, x1 = hi ? g1.y : g1.x, x2 = hi ? g2.y : g2.x;
-                float num = fmaf(x1, H1, x2 * H2);
-                float den = fmaf(x0, H0, fmaf(x1, H1, num));
-                own = num * fast_rcp(den);
+                const ulonglong2 ab = rowA[ti];
+                const float2 g0 = unpack2(ab.x), g1 = unpack2(ab.y), g2 = unpack2(rowB[ti]);
+                float num = fmaf(g1.x, ca.h1, g2.x * ca.h2);
+                float den = fmaf(g0.x, ca.h0, fmaf(g1.x, ca.h1, num));
+                ownA = num * fast_rcp(den);
+                num = fmaf(g1.y, cb.h1, g2.y * cb.h2);
+                den = fmaf(g0.y, cb.h0, fmaf(g1.y, cb.h1, num));
+                ownB = num * fast_rcp(den);
             }
-            float sum = (a0 + a1) - own;
-            float fnew = __fdiv_rn(sum, divisor);
-            if (fnew < 1e-12f) fnew = 1e-12f;                  // comparisons are false for NaN: NaN survives
-            if (fnew > 0.99999994f) fnew = 0.99999994f;
-            float d = fnew - f;
-            ssq += d * d;
-            F[(s0 + sl) * (long)ldf + col0 + i] = fnew;
+            float fa = ((a0 + a1) - ownA) * inv_div;
+            float fb = ((b0 + b1) - ownB) * inv_div;
+            if (fa < 1e-12f) fa = 1e-12f;                      // comparisons are false for NaN: NaN survives
+            if (fa > 0.99999994f) fa = 0.99999994f;
+            if (fb < 1e-12f) fb = 1e-12f;
+            if (fb > 0.99999994f) fb = 0.99999994f;
+            float* dst = &F[(s0 + sl) * (long)ldf + cA];
+            if (okA[p]) { float d = fa - fv[p].x; ssqA += d * d; dst[0] = fa; }
+            if (okB[p]) { float d = fb - fv[p].y; ssqB += d * d; dst[1] = fb; }
         }
     }
     __syncthreads();
-    red[t] = ssq;
+    red[t] = make_float2(ssqA, ssqB);
     __syncthreads();
-    if (t < n) {
+    if (t < n) {                                                // problem t = half (t & 1) of pair t / 2
         double v = 0.0;
-        for (int q = 0; q < rows_per_pass; ++q) v += (double)red[q * n + t];
+        for (int q = 0; q < rows_per_pass; ++q) {
+            float2 x = red[q * np + (t >> 1)];
+            v += (double)((t & 1) ? x.y : x.x);
+        }
         partials[(long)blockIdx.x * ldg + col0 + t] = v;
     }
 }
