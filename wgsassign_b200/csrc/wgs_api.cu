@@ -1111,8 +1111,12 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     // class counts and float32 class means, per (column, class)
     std::vector<long long> ccnt(tab_n, 0);
     std::vector<float> cmean(tab_n * 3, 0.f);
+    // reference-faithful sequential float32 class means up to 2^18 sites on one GPU; the exact,
+    // order-independent tally above that and whenever sites are sharded (see wgs_zscore.cuh)
     const char* env_exact = getenv("WGS_Z_EXACT_MEANS");
-    const bool exact_means = ctx->fn != nullptr || (env_exact && env_exact[0] == '1');
+    bool exact_means = ctx->fn != nullptr || ctx->Mtot() > (1L << 18);
+    if (env_exact && env_exact[0] == '1') exact_means = true;
+    if (env_exact && env_exact[0] == '0' && !ctx->fn) exact_means = false;
     if (exact_means) {
         // order-independent fixed-point tally (shardable)
         LAUNCH("ztally", ztally_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),

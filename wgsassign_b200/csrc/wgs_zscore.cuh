@@ -23,7 +23,9 @@ namespace wgs {
 constexpr int kZDepthCap = 40;
 constexpr int kZClasses = (kZDepthCap + 1) * (kZDepthCap + 2) / 2;   // 861
 constexpr int kZHotDepth = 4;
-constexpr int kZHot = (kZHotDepth + 1) * (kZHotDepth + 2) / 2;       // 15 classes held in registers
+constexpr int kZHot = (kZHotDepth + 1) * (kZHotDepth + 2) / 2;       // 15 classes held in registers (sequential kernel)
+constexpr int kZHotDepthX = 3;                                       // exact kernel: 7 accumulators per class, 10 classes
+constexpr int kZHotX = (kZHotDepthX + 1) * (kZHotDepthX + 2) / 2;
 constexpr float kZLimb = 262144.0f;                                  // 2^18 per limb; sums are in units of 2^-36
 constexpr double kZUnit = 1.0 / 68719476736.0;                       // 2^-36
 
@@ -60,12 +62,12 @@ __device__ __forceinline__ void tally_flush(ZTally* t, int cnt, int h0, int l0, 
 // ---------------------------------------------------------------------------------------
 // ztally: per (individual, class) site count and fixed-point GL sums (zscore.py:13-22).
 // Thread = individual, warp = 32 consecutive columns of one site (coalesced 256 B GL +
-// 64 B AD requests).  The classes of depth <= 4 (95 % of sites at 2x) live in registers and
+// 64 B AD requests).  The classes of depth <= 3 (86 % of sites at 2x) live in registers and
 // are updated by predicated integer adds - no atomics in the streaming loop; deeper
 // classes go straight to the table with 64-bit integer atomics.  A thread sees at most
 // 2047 sites per launch so the 32-bit register limb sums cannot overflow.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
               const unsigned char* __restrict__ sel,       // [ldg] 1 = individual requested
               int wx, long sites_per_block,
@@ -81,37 +83,49 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
     const long s_end = min(M, s_begin + sites_per_block);
     if (!on) return;
 
-    int cnt[kZHot], h0[kZHot], l0[kZHot], h1[kZHot], l1[kZHot], h2[kZHot], l2[kZHot];
+    int cnt[kZHotX], h0[kZHotX], l0[kZHotX], h1[kZHotX], l1[kZHotX], h2[kZHotX], l2[kZHotX];
 #pragma unroll
-    for (int c = 0; c < kZHot; ++c) { cnt[c] = 0; h0[c] = l0[c] = h1[c] = l1[c] = h2[c] = l2[c] = 0; }
+    for (int c = 0; c < kZHotX; ++c) { cnt[c] = 0; h0[c] = l0[c] = h1[c] = l1[c] = h2[c] = l2[c] = 0; }
     int ndeep = 0;
     ZTally* mine = table + (size_t)col * kZClasses;
 
-    for (long s = s_begin + wy; s < s_end; s += wy_count) {
-        float2 g = ld_stream2(&G[s * (long)ldg + col]);
-        uchar2 ad = AD[s * (long)ldg + col];
-        int ref = ad.x, alt = ad.y, d = ref + alt;
-        int vh0, vl0, vh1, vl1, vh2, vl2;
-        fix_limbs(g.x, vh0, vl0);
-        fix_limbs(g.y, vh1, vl1);
-        fix_limbs(third_gl_np(g.x, g.y), vh2, vl2);
-        if (d <= kZHotDepth) {
-            int code = zclass_id(ref, alt);
+    constexpr int PF = 2;                                     // sites in flight per thread
+    for (long sb = s_begin + wy; sb < s_end; sb += (long)wy_count * PF) {
+        float2 gq[PF];
+        uchar2 aq[PF];
 #pragma unroll
-            for (int c = 0; c < kZHot; ++c) {
-                if (code == c) {
-                    cnt[c] += 1;
-                    h0[c] += vh0; l0[c] += vl0; h1[c] += vh1; l1[c] += vl1; h2[c] += vh2; l2[c] += vl2;
+        for (int u = 0; u < PF; ++u) {
+            long s = sb + (long)wy_count * u;
+            gq[u] = make_float2(0.f, 0.f); aq[u] = make_uchar2(255, 255);       // depth 510: counted nowhere
+            if (s < s_end) { gq[u] = ld_stream2(&G[s * (long)ldg + col]); aq[u] = AD[s * (long)ldg + col]; }
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            if (sb + (long)wy_count * u >= s_end) break;
+            const float2 g = gq[u];
+            int ref = aq[u].x, alt = aq[u].y, d = ref + alt;
+            int vh0, vl0, vh1, vl1, vh2, vl2;
+            fix_limbs(g.x, vh0, vl0);
+            fix_limbs(g.y, vh1, vl1);
+            fix_limbs(third_gl_np(g.x, g.y), vh2, vl2);
+            if (d <= kZHotDepthX) {
+                int code = zclass_id(ref, alt);
+#pragma unroll
+                for (int c = 0; c < kZHotX; ++c) {
+                    if (code == c) {
+                        cnt[c] += 1;
+                        h0[c] += vh0; l0[c] += vl0; h1[c] += vh1; l1[c] += vl1; h2[c] += vh2; l2[c] += vl2;
+                    }
                 }
+            } else if (d <= kZDepthCap) {
+                tally_flush(mine + zclass_id(ref, alt), 1, vh0, vl0, vh1, vl1, vh2, vl2);
+            } else {
+                ++ndeep;
             }
-        } else if (d <= kZDepthCap) {
-            tally_flush(mine + zclass_id(ref, alt), 1, vh0, vl0, vh1, vl1, vh2, vl2);
-        } else {
-            ++ndeep;
         }
     }
 #pragma unroll
-    for (int c = 0; c < kZHot; ++c) tally_flush(mine + c, cnt[c], h0[c], l0[c], h1[c], l1[c], h2[c], l2[c]);
+    for (int c = 0; c < kZHotX; ++c) tally_flush(mine + c, cnt[c], h0[c], l0[c], h1[c], l1[c], h2[c], l2[c]);
     if (ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
 }
 
@@ -124,8 +138,9 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
 // individuals, so loads stay coalesced; 8 sites are prefetched ahead).  Hot classes are
 // float accumulators in registers updated by predicated adds; the rest are read-modify-
 // written in the individual's own table row (no other thread touches it).
-// Used on a single GPU; site-sharded runs use the order-independent ztally_kernel above
-// (at that scale the reference's own float32 mean has lost its precision anyway).
+// Used on a single GPU up to 2^18 sites (it is serial in the site index: ~0.8 us per site);
+// larger and site-sharded runs use the order-independent ztally_kernel above (at that scale the
+// reference's own float32 mean has lost its precision anyway).  WGS_Z_EXACT_MEANS=0/1 overrides.
 // ---------------------------------------------------------------------------------------
 struct ZTallyF { float s0, s1, s2; int cnt; };
 
