@@ -217,7 +217,7 @@ def family(ctx, name, peak_gbs, sites=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sites", type=int, default=SITES_PER_GPU, help="sites per GPU (default: cfg3's 1M)")
@@ -240,9 +240,18 @@ def main():
     from wgsassign_b200 import _lib, dist
     if world > 1:
         import torch.distributed as td
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep rank 0's stdout to the one JSON line
-        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # keep rank 0's stdout to the one JSON line: NCCL prints its version banner to stdout at
+        # communicator creation for any NCCL_DEBUG level >= VERSION, so create it with fd 1 -> stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            td.init_process_group("nccl", device_id=torch.device("cuda", local))
+            td.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     M_local = args.sites
     M_total = M_local * world
     if world > 1:
