@@ -368,7 +368,9 @@ def main():
         return 0
 
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
-    mufu_peak = 148 * 16 * sm_mhz * 1e6      # MUFU lanes/clk/SM x clock actually sustained
+    # MUFU.RCP rate MEASURED on this pool's B200 (scripts/microbench/mufu_rate.cu, profiles/mufu_rate_r1.txt):
+    # 15.48 per clock per SM at 1,965 MHz = 4.50e12/s; scaled by the clock this run sustained
+    mufu_peak = 148 * 15.48 * sm_mhz * 1e6
     le = fam["loo_em"]
     roofline = {"kernel": "loo_em_step_kernel", "bound": "hbm", "achieved": le["achieved_gbs"], "peak": hbm_peak,
                 "unit": "GB/s", "frac": le["hbm_frac"], "traffic": le.get("ncu_dram_bytes_per_launch"),
@@ -378,7 +380,7 @@ def main():
                 "note": "by design NOT HBM-bound: each GL tile is read once per iteration and re-used for n^2 posterior "
                         "evaluations from shared memory; the binding limit is the MUFU reciprocal rate (see `issue`); "
                         "the HBM-bound kernels of the path are in `kernels` (em_pop, pop_like, fisher)",
-                "issue": {"bound": "mufu.rcp", "achieved": le["units_per_s"], "peak": mufu_peak, "unit": "posterior evals/s",
+                "issue": {"bound": "mufu.rcp", "achieved": le["units_per_s"], "peak": mufu_peak, "peak_source": "measured 15.48 rcp/clk/SM (profiles/mufu_rate_r1.txt)", "unit": "posterior evals/s",
                           "frac": le["units_per_s"] / mufu_peak, "sm_mhz": sm_mhz}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

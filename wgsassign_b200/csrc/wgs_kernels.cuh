@@ -875,6 +875,164 @@ loo_em_step_kernel(const float2* __restrict__ G, int ldg, long M,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Pre-packed tiles for the leave-one-out EM.  The pair packing above is the same for all
+// ~15 iterations of all problems, so it is done ONCE per call: loo_pack_kernel writes, per
+// population, PA[M][np2] = {(g0_a,g0_b),(g1_a,g1_b)} and PB[M][np2] = (g2_a,g2_b) (np2 = pair
+// count padded to the unroll factor and to an even number; pads contribute exactly 0).  The
+// step kernel then has no fill code at all: warp 0 streams tile rows with TMA bulk copies
+// (cp.async.bulk, two per row) into a double buffer guarded by mbarriers, and the next tile
+// is already in shared memory when the block finishes the current one.
+// ---------------------------------------------------------------------------------------
+__global__ void loo_pack_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n, int np2,
+                                ulonglong2* __restrict__ PA, f32x2* __restrict__ PB)
+{
+    const int np = (n + 1) >> 1;
+    long total = M * (long)np2;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long s = e / np2;
+        int q = (int)(e - s * np2);
+        float4 g = make_float4(1.f, 0.f, 1.f, 0.f);             // (1,0,0): contributes exactly 0
+        if (q < np) g = ld_stream4(reinterpret_cast<const float4*>(&G[s * (long)ldg + col0 + 2 * q]));
+        if (2 * q + 1 >= n) { g.z = 1.f; g.w = 0.f; }
+        ulonglong2 a;
+        a.x = pack2(g.x, g.z);
+        a.y = pack2(g.y, g.w);
+        PA[e] = a;
+        PB[e] = pack2(third_gl(g.x, g.y), third_gl(g.z, g.w));
+    }
+}
+
+template <int U, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+loo_em_step_tma_kernel(const ulonglong2* __restrict__ PA, const f32x2* __restrict__ PB, int np2, long M,
+                       int ldg, int col0, int n, int rows_per_pass, int passes, int strideA, int strideB,
+                       float* __restrict__ F, int ldf,              // [M][ldf], in place
+                       const int* __restrict__ active,              // [ldg]
+                       const unsigned char* __restrict__ mask,      // [M][ldg] or null
+                       double* __restrict__ partials,               // [gridDim.x][ldg]
+                       long ntiles)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    const int np = (n + 1) >> 1;
+    const int npu = (np + U - 1) / U * U;                       // loop bound (<= np2)
+    const int TS = rows_per_pass * passes;
+    const size_t szA = (size_t)TS * strideA, szB = (size_t)TS * strideB;
+    ulonglong2* tA0 = reinterpret_cast<ulonglong2*>(smem_raw);                  // [2][TS][strideA]
+    f32x2* tB0 = reinterpret_cast<f32x2*>(tA0 + 2 * szA);                       // [2][TS][strideB]
+    float2* red = reinterpret_cast<float2*>(tB0 + 2 * szB);                     // [blockDim.x]
+
+    const int t = threadIdx.x;
+    const int Bp = rows_per_pass * np;
+    const int ti = t % np, r = t / np;
+    const bool worker = t < Bp;
+    const int cA = col0 + 2 * ti, cB = cA + 1;
+    const bool hasB = 2 * ti + 1 < n;
+    const bool actA = worker && active[cA] != 0;
+    const bool actB = worker && hasB && active[cB] != 0;
+    const bool any_act = actA || actB;
+    const float inv_div = 1.0f / (float)(n - 1);
+    float ssqA = 0.f, ssqB = 0.f;
+
+    if (t == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    auto issue = [&](long tile, int buf) {
+        if (tile < ntiles && t < 32) {
+            const long s0 = tile * TS;
+            const int rows = (int)min((long)TS, M - s0);
+            if (t == 0) mbar_expect_tx(&mbar[buf], (unsigned)(rows * np2 * 24));
+            __syncwarp();
+            for (int rr = t; rr < rows; rr += 32) {
+                bulk_g2s(tA0 + buf * szA + (size_t)rr * strideA, PA + (s0 + rr) * (long)np2, (unsigned)(np2 * 16), &mbar[buf]);
+                bulk_g2s(tB0 + buf * szB + (size_t)rr * strideB, PB + (s0 + rr) * (long)np2, (unsigned)(np2 * 8), &mbar[buf]);
+            }
+        }
+    };
+    issue(blockIdx.x, 0);
+    issue(blockIdx.x + (long)gridDim.x, 1);
+
+    int it = 0;
+    for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const long s0 = tl * TS;
+        float2 fv[kLooMaxPasses];
+        bool okA[kLooMaxPasses], okB[kLooMaxPasses];
+#pragma unroll
+        for (int p = 0; p < kLooMaxPasses; ++p) {
+            const long s = s0 + p * rows_per_pass + r;
+            const bool in = any_act && p < passes && s < M;
+            okA[p] = in && actA; okB[p] = in && actB;
+            if (in && mask) {
+                okA[p] = okA[p] && mask[s * (long)ldg + cA] != 0;
+                okB[p] = okB[p] && mask[s * (long)ldg + cB] != 0;
+            }
+            fv[p] = make_float2(0.25f, 0.25f);
+            if (okA[p] || okB[p]) fv[p] = *reinterpret_cast<const float2*>(&F[s * (long)ldf + cA]);
+        }
+        mbar_wait(&mbar[buf], (unsigned)((it >> 1) & 1));       // the tile has landed
+        const ulonglong2* tA = tA0 + buf * szA;
+        const f32x2* tB = tB0 + buf * szB;
+#pragma unroll
+        for (int p = 0; p < kLooMaxPasses; ++p) {
+            if (!(okA[p] || okB[p])) continue;
+            const int sl = p * rows_per_pass + r;
+            const LooCoef ca = loo_coef(fv[p].x), cb = loo_coef(fv[p].y);
+            const ulonglong2* rowA = tA + sl * strideA;
+            const f32x2* rowB = tB + sl * strideB;
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+            for (int q0 = 0; q0 < npu; q0 += U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const ulonglong2 ab = rowA[q0 + u];
+                    const f32x2 g2 = rowB[q0 + u];
+                    f32x2 numa = ffma2(ab.y, ca.H1, fmul2(g2, ca.H2));
+                    f32x2 numb = ffma2(ab.y, cb.H1, fmul2(g2, cb.H2));
+                    f32x2 dena = ffma2(ab.x, ca.H0, ffma2(ab.y, ca.H1, numa));
+                    f32x2 denb = ffma2(ab.x, cb.H0, ffma2(ab.y, cb.H1, numb));
+                    float2 na = unpack2(numa), da = unpack2(dena), nb = unpack2(numb), db = unpack2(denb);
+                    a0 = fmaf(na.x, fast_rcp(da.x), a0);
+                    a1 = fmaf(na.y, fast_rcp(da.y), a1);
+                    b0 = fmaf(nb.x, fast_rcp(db.x), b0);
+                    b1 = fmaf(nb.y, fast_rcp(db.y), b1);
+                }
+            }
+            float ownA, ownB;
+            {
+                const ulonglong2 ab = rowA[ti];
+                const float2 g0 = unpack2(ab.x), g1 = unpack2(ab.y), g2 = unpack2(rowB[ti]);
+                float num = fmaf(g1.x, ca.h1, g2.x * ca.h2);
+                float den = fmaf(g0.x, ca.h0, fmaf(g1.x, ca.h1, num));
+                ownA = num * fast_rcp(den);
+                num = fmaf(g1.y, cb.h1, g2.y * cb.h2);
+                den = fmaf(g0.y, cb.h0, fmaf(g1.y, cb.h1, num));
+                ownB = num * fast_rcp(den);
+            }
+            float fa = ((a0 + a1) - ownA) * inv_div;
+            float fb = ((b0 + b1) - ownB) * inv_div;
+            if (fa < 1e-12f) fa = 1e-12f;
+            if (fa > 0.99999994f) fa = 0.99999994f;
+            if (fb < 1e-12f) fb = 1e-12f;
+            if (fb > 0.99999994f) fb = 0.99999994f;
+            float* dst = &F[(s0 + sl) * (long)ldf + cA];
+            if (okA[p]) { float d = fa - fv[p].x; ssqA += d * d; dst[0] = fa; }
+            if (okB[p]) { float d = fb - fv[p].y; ssqB += d * d; dst[1] = fb; }
+        }
+        __syncthreads();                                        // all warps are done with this buffer
+        issue(tl + 2 * (long)gridDim.x, buf);
+    }
+    red[t] = make_float2(ssqA, ssqB);
+    __syncthreads();
+    if (t < n) {
+        double v = 0.0;
+        for (int q = 0; q < rows_per_pass; ++q) {
+            float2 x = red[q * np + (t >> 1)];
+            v += (double)((t & 1) ? x.y : x.x);
+        }
+        partials[(long)blockIdx.x * ldg + col0 + t] = v;
+    }
+}
+
 // ssq[p] = sum over blocks (fixed order) of partials[block][p]
 __global__ void em_ssq_reduce_kernel(const double* __restrict__ partials, int nblocks, int np, int ld,
                                      double* __restrict__ ssq)
