@@ -129,7 +129,8 @@ typedef struct {
 } wgs_zrow;
 
 /* mode 0: --get_assignment_z_score (af [M,K] + pop_of_ind give each individual's column);
- * mode 1: --get_reference_z_score (LOO EM on the kept sites, af ignored).
+ * mode 1: --get_reference_z_score (LOO EM on the kept sites, af ignored);
+ * mode 2: preparation only (class tallies + kept-site counts; z fields are NaN).
  * Individuals ind_start <= i < ind_end; out[ind_end-ind_start]. */
 int32_t wgs_zscore(wgs_ctx *ctx, int32_t mode, const float *af, int32_t K, int32_t n_threshold,
                    int32_t single_read, int32_t ind_start, int32_t ind_end, int32_t iter,
@@ -140,6 +141,22 @@ int32_t wgs_zscore(wgs_ctx *ctx, int32_t mode, const float *af, int32_t K, int32
  * The reference's row order is first occurrence in the file; no output depends on it. */
 int32_t wgs_zscore_classes(wgs_ctx *ctx, int32_t ind, int32_t max_rows, int32_t *rows_out,
                            int32_t *n_rows);
+
+/* Finer-grained z-score entry points behind the reference's per-individual functions:
+ *  - wgs_zscore(mode 2, ...) runs the preparation only (tallies, class decisions, kept counts);
+ *  - wgs_zscore_table: every observed class of individual `ind` from the last wgs_zscore call,
+ *    rows of 7 floats (ref, alt, n_loci, mean GL0, GL1, GL2, kept flag): zscore.AD_summary's dict;
+ *  - wgs_zkeep_one: zscore.get_L_keep (zscore.py:43-61) for the caller's AD_array [C,4] and class
+ *    means [C,3]; writes the kept site indices (ascending) and their number;
+ *  - wgs_zmoments_list: zscore_cy.expected_W_l + variance_W_l (zscore_cy.pyx:10-56) over the
+ *    caller's kept-site list, AF vector and class tables; per-site float32 outputs [mk]. */
+int32_t wgs_zscore_table(wgs_ctx *ctx, int32_t ind, int32_t max_rows, float *rows_out, int32_t *n_rows);
+int32_t wgs_zkeep_one(wgs_ctx *ctx, int32_t ind, int32_t n_classes, const int32_t *ad_array,
+                      const float *class_means, int32_t *keep_out, int64_t cap, int64_t *n_kept);
+int32_t wgs_zmoments_list(wgs_ctx *ctx, int32_t ind, const int32_t *L_keep, int64_t mk, const float *A_vec,
+                          int32_t n_classes, const float *AD_factorial, const float *AD_like,
+                          const int32_t *AD_index, int32_t idx_rows, int32_t idx_cols,
+                          float *W_obs_out, float *W_l_out, float *W_var_out);
 
 /* Number of (site, individual) pairs of the last wgs_zscore call whose read depth exceeded
  * the dense class table (40 reads); such sites are treated as "class not kept", which is what

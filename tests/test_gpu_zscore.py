@@ -118,3 +118,47 @@ def test_exact_mean_variant_keeps_tallies(zs, zgold, monkeypatch):
         assert np.array_equal(sort_rows(r["AD_array"]), sort_rows(zgold["AD_array_%d" % j]))
         assert abs(float(r["w_obs"]) - comp[j, 0]) <= 2e-3 * abs(comp[j, 0])
         assert abs(float(r["z_mu"]) - comp[j, 1]) <= 2e-3 * abs(comp[j, 1])
+
+
+def test_per_individual_functions_match_reference_loop(zs, zgold, oracle_mod):
+    """The reference's own per-individual body (WGSassign.py:425-443) written against our
+    drop-in functions: dict keys in first-occurrence order, AD_array / L_keep / AD_index
+    bit-exact, class means and per-site W arrays within float32 rounding of the oracle."""
+    L, AD, IDs, af = zgold["L"], zgold["AD"].astype(np.int32), zgold["IDs"], zgold["af"]
+    pops = np.unique(IDs[:, 1])
+    kern = oracle_mod.kernels()
+    for i in (0, 5, 11):
+        k = int(np.argwhere(pops == IDs[i, 1])[0][0])
+        d, arr = zs.AD_summary(L, AD, i, 0, False)
+        d_o, arr_o = oracle_mod.AD_summary(L, AD, i, 0, False)
+        assert [tuple(int(x) for x in key) for key in d] == list(d_o)
+        assert arr.dtype == np.int32 and np.array_equal(arr, arr_o)
+        for key, key_o in zip(d, d_o):
+            assert d[key][0] == d_o[key_o][0]
+            assert d[key][1].dtype == np.float32 and np.allclose(d[key][1], d_o[key_o][1], rtol=1e-6, atol=1e-9)
+        keep, kept = zs.get_L_keep(L, AD, d, arr, i)
+        keep_o, kept_o = oracle_mod.get_L_keep(L, AD, d_o, arr_o, i)
+        assert keep.dtype == np.int32 and kept == kept_o and np.array_equal(keep, keep_o)
+        fac, like, idx = zs.get_factorials(arr, d, 0.01)
+        fac_o, like_o, idx_o = oracle_mod.get_factorials(arr_o, d_o, 0.01)
+        assert np.array_equal(fac, fac_o) and np.allclose(like, like_o, rtol=1e-6, atol=1e-9) and np.array_equal(idx, idx_o)
+        a = np.ascontiguousarray(af[keep, :][:, k].reshape(-1))
+        w_obs, w_l = zs.get_expected_W_l(L, keep, a, AD, arr, fac, like, idx, 1, i)
+        var = zs.get_var_W_l(L, keep, a, AD, arr, fac, like, idx, w_l, 1, i)
+        w_obs_arr_o, w_l_o, var_o = (np.zeros(kept, np.float32) for _ in range(3))
+        kern.expected_W_l(L, keep_o, a, AD, arr_o, fac_o, like_o, idx_o, 1, i, w_obs_arr_o, w_l_o)
+        kern.variance_W_l(L, keep_o, a, AD, arr_o, fac_o, like_o, idx_o, 1, i, var_o, w_l_o)
+        assert w_l.dtype == np.float32 and w_l.shape == (kept,)
+        assert np.max(np.abs(w_l - w_l_o)) <= 2e-6 * np.max(np.abs(w_l_o))
+        assert np.max(np.abs(var - var_o)) <= 1e-5 * np.max(np.abs(var_o))
+        assert abs(float(w_obs) - float(np.sum(w_obs_arr_o, dtype=np.float32))) <= 1e-6 * abs(float(np.sum(w_obs_arr_o)))
+        z = (w_obs - np.sum(w_l)) / np.sqrt(np.sum(var))
+        z_ref = float(str(zgold["z_assign_txt"]).split()[i])
+        w, mu, v = zgold["z_assign_components"][i][:3]
+        assert abs(float(z) - z_ref) <= 2e-6 * (abs(w) + abs(mu)) / np.sqrt(v) + 1e-5 * abs(z_ref)
+
+
+def test_per_individual_asserts_like_reference(zs, zgold):
+    L, AD = zgold["L"], zgold["AD"].astype(np.int32)
+    with pytest.raises(AssertionError, match="loci were kept"):
+        zs.AD_summary(L, AD, 0, 10 ** 9, False)

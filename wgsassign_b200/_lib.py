@@ -51,6 +51,9 @@ SYMBOLS = {
     "wgs_zscore": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _vp]),
     "wgs_zscore_classes": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "wgs_zscore_deep_sites": (_i64, [_vp]),
+    "wgs_zscore_table": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "wgs_zkeep_one": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "wgs_zmoments_list": (_i32, [_vp, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "wgs_beagle_open": (_i32, [ctypes.c_char_p, _i32, ctypes.POINTER(_vp)]),
     "wgs_beagle_last_error": (ctypes.c_char_p, []),
     "wgs_beagle_sites": (_i64, [_vp]),
@@ -258,6 +261,32 @@ class Context:
         n = ctypes.c_int32(0)
         self._ck(lib().wgs_zscore_classes(self._h, int(ind), max_rows, _ptr(buf), ctypes.byref(n)))
         return buf[:n.value].copy()
+
+    def zscore_table(self, ind, max_rows=4096):
+        buf = np.zeros((max_rows, 7), np.float32)
+        n = ctypes.c_int32(0)
+        self._ck(lib().wgs_zscore_table(self._h, int(ind), max_rows, _ptr(buf), ctypes.byref(n)))
+        return buf[:n.value].copy()
+
+    def zkeep_one(self, ind, ad_array, class_means):
+        ad = np.ascontiguousarray(ad_array, dtype=np.int32).reshape(-1, 4)
+        cm = np.ascontiguousarray(class_means, dtype=np.float32).reshape(-1, 3)
+        out = np.empty(self.M, np.int32)
+        n = ctypes.c_int64(0)
+        self._ck(lib().wgs_zkeep_one(self._h, int(ind), ad.shape[0], _ptr(ad), _ptr(cm), _ptr(out), self.M, ctypes.byref(n)))
+        return out[:n.value].copy()
+
+    def zmoments_list(self, ind, L_keep, A_vec, AD_factorial, AD_like, AD_index):
+        keep = _as(L_keep, np.int32, 1, "L_keep")
+        a = _as(A_vec, np.float32, 1, "A")
+        fac = _as(AD_factorial, np.float32, 2, "AD_factorial")
+        like = _as(AD_like, np.float32, 2, "AD_like")
+        idx = _as(AD_index, np.int32, 2, "AD_index")
+        mk = keep.shape[0]
+        w_obs, w_l, var = (np.empty(mk, np.float32) for _ in range(3))
+        self._ck(lib().wgs_zmoments_list(self._h, int(ind), _ptr(keep), mk, _ptr(a), fac.shape[0], _ptr(fac), _ptr(like), _ptr(idx),
+                                         idx.shape[0], idx.shape[1], _ptr(w_obs), _ptr(w_l), _ptr(var)))
+        return w_obs, w_l, var
 
     def zscore_deep_sites(self):
         return int(lib().wgs_zscore_deep_sites(self._h))

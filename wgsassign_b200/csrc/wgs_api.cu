@@ -63,6 +63,7 @@ struct wgs_ctx {
 
     // z-score class tables of the last call
     std::vector<std::vector<int>> zclasses;
+    std::vector<std::vector<float>> ztable;      // per individual: rows of (ref, alt, n_loci, mean0, mean1, mean2, kept) of every observed class
     long z_deep_sites = 0;
 
     // instrumentation
@@ -1137,6 +1138,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     if (!ctx->AD || ctx->M_ad != ctx->M()) return fail(ctx, "no allele depths resident (wgs_upload_ad)");
     if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for the z-score operators");
     if (ind_start < 0 || ind_end > ctx->N || ind_start >= ind_end) return fail(ctx, "individual range [%d,%d) outside [0,%d)", ind_start, ind_end, ctx->N);
+    if (mode < 0 || mode > 2) return fail(ctx, "mode must be 0 (assignment), 1 (reference) or 2 (preparation only)");
     if (mode == 0 && (!af || K != ctx->K)) return fail(ctx, "assignment mode needs af [M,%d]", ctx->K);
     const long M = ctx->M();
     const int ldg = ctx->ldg, N = ctx->N;
@@ -1208,6 +1210,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     std::vector<float> kmean(tab_n, 0.f);
     std::vector<float4> zlike(tab_n, make_float4(0.f, 0.f, 0.f, 0.f)), zfac(tab_n, make_float4(0.f, 0.f, 0.f, 0.f));
     ctx->zclasses.assign(N, std::vector<int>());
+    ctx->ztable.assign(N, std::vector<float>());
     std::vector<int> n_classes(N, 0);
     for (int i = ind_start; i < ind_end; ++i) {
         const int col = ctx->col_of_ind[i];
@@ -1242,7 +1245,19 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
                 ++n_classes[i];
             }
         }
-        if (n_classes[i] == 0) return fail(ctx, "individual %d: no read depth has all of its allele-count splits (zscore.py:36-39 leaves AD_array empty)", i);
+        {   // every observed class, for the AD_summary drop-in (zscore.py:20-22)
+            auto& tab = ctx->ztable[i];
+            for (int d = 0; d <= kZDepthCap; ++d)
+                for (int alt = 0; alt <= d; ++alt) {
+                    int id = zclass_id(d - alt, alt);
+                    if (t[id] <= 0) continue;
+                    size_t g = (size_t)col * kZClasses + id;
+                    float row[7] = {(float)(d - alt), (float)alt, (float)t[id], cmean[3 * g], cmean[3 * g + 1], cmean[3 * g + 2],
+                                    kmax[g] >= 0 ? 1.f : 0.f};
+                    tab.insert(tab.end(), row, row + 7);
+                }
+        }
+        if (n_classes[i] == 0 && mode != 2) return fail(ctx, "individual %d: no read depth has all of its allele-count splits (zscore.py:36-39 leaves AD_array empty)", i);
     }
 
     DevBuf dkmax, dkmean, dlike, dfac, dkeep, dkept;
@@ -1261,6 +1276,17 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     CU(cudaMemcpyAsync(kept.data(), dkept.p, ldg * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->fn) ctx->fn(kept.data(), ldg, WGS_I64, ctx->user);
+
+    if (mode == 2) {                                             // preparation only: tallies, class tables, kept-site counts
+        for (int i = ind_start; i < ind_end; ++i) {
+            wgs_zrow& r = out[i - ind_start];
+            r.z = r.w_obs = r.z_mu = r.z_var = std::numeric_limits<float>::quiet_NaN();
+            r.loci_kept = kept[ctx->col_of_ind[i]];
+            r.n_classes = n_classes[i];
+            r.em_iters = 0;
+        }
+        return 0;
+    }
 
     // ---- allele frequencies seen by each individual ----
     DevBuf dAF, dafcol;
@@ -1322,6 +1348,89 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         r.n_classes = n_classes[i];
         r.em_iters = mode == 1 ? em_iters[col] : 0;
     }
+    return 0;
+}
+
+int32_t wgs_zscore_table(wgs_ctx* ctx, int32_t ind, int32_t max_rows, float* rows_out, int32_t* n_rows)
+{
+    if (ind < 0 || ind >= (int)ctx->ztable.size()) return fail(ctx, "no class table for individual %d", ind);
+    const auto& v = ctx->ztable[ind];
+    int n = (int)v.size() / 7;
+    *n_rows = n;
+    for (int r = 0; r < std::min(n, max_rows); ++r) memcpy(rows_out + 7 * r, v.data() + 7 * r, 7 * sizeof(float));
+    return 0;
+}
+
+int32_t wgs_zkeep_one(wgs_ctx* ctx, int32_t ind, int32_t n_classes, const int32_t* ad_array, const float* class_means,
+                      int32_t* keep_out, int64_t cap, int64_t* n_kept)
+{
+    cudaSetDevice(ctx->device);
+    if (!ctx->G[0] || !ctx->AD) return fail(ctx, "GL matrix and allele depths must be resident");
+    if (ind < 0 || ind >= ctx->N) return fail(ctx, "individual %d outside [0,%d)", ind, ctx->N);
+    const long M = ctx->M();
+    const int ldg = ctx->ldg, col = ctx->col_of_ind[ind];
+    const size_t tab_n = (size_t)ldg * kZClasses;
+    std::vector<signed char> kmax(tab_n, -1);
+    std::vector<float> kmean(tab_n, 0.f);
+    for (int c = 0; c < n_classes; ++c) {
+        int ref = ad_array[4 * c], alt = ad_array[4 * c + 1];
+        if (ref < 0 || alt < 0 || ref + alt > kZDepthCap) continue;
+        const float* m = class_means + 3 * c;
+        int mx = 0; float mv = m[0];
+        if (m[1] > mv) { mx = 1; mv = m[1]; }
+        if (m[2] > mv) { mx = 2; mv = m[2]; }
+        size_t g = (size_t)col * kZClasses + zclass_id(ref, alt);
+        kmax[g] = (signed char)mx; kmean[g] = mv;
+    }
+    std::vector<unsigned char> sel(ldg, 0);
+    sel[col] = 1;
+    DevBuf dsel, dkmax, dkmean, dkeep, dkept;
+    if (buf_alloc(ctx, dsel, ldg) || buf_alloc(ctx, dkmax, tab_n) || buf_alloc(ctx, dkmean, tab_n * sizeof(float)) ||
+        buf_alloc(ctx, dkeep, (size_t)std::max<long>(M, 1) * ldg) || buf_alloc(ctx, dkept, ldg * sizeof(unsigned long long))) return 1;
+    CU(cudaMemcpyAsync(dsel.p, sel.data(), ldg, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dkmax.p, kmax.data(), tab_n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dkmean.p, kmean.data(), tab_n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(dkept.p, 0, ldg * sizeof(unsigned long long), ctx->stream));
+    LikeCfg c = like_cfg(ctx, M, 4);
+    LAUNCH("zkeep", zkeep_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
+           dkmax.as<signed char>(), dkmean.as<float>(), c.wx, c.sites_per_block, dkeep.as<unsigned char>(), dkept.as<unsigned long long>());
+    std::vector<unsigned char> colmask((size_t)std::max<long>(M, 1));
+    CU(cudaMemcpy2DAsync(colmask.data(), 1, dkeep.as<unsigned char>() + col, ldg, 1, (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    int64_t nk = 0;
+    for (long s = 0; s < M; ++s)
+        if (colmask[s]) { if (nk < cap) keep_out[nk] = (int32_t)s; ++nk; }
+    *n_kept = nk;
+    return 0;
+}
+
+int32_t wgs_zmoments_list(wgs_ctx* ctx, int32_t ind, const int32_t* L_keep, int64_t mk, const float* A_vec, int32_t n_classes,
+                          const float* AD_factorial, const float* AD_like, const int32_t* AD_index, int32_t idx_rows, int32_t idx_cols,
+                          float* W_obs_out, float* W_l_out, float* W_var_out)
+{
+    cudaSetDevice(ctx->device);
+    if (!ctx->G[0] || !ctx->AD) return fail(ctx, "GL matrix and allele depths must be resident");
+    if (ind < 0 || ind >= ctx->N) return fail(ctx, "individual %d outside [0,%d)", ind, ctx->N);
+    for (int64_t e = 0; e < mk; ++e) if (L_keep[e] < 0 || L_keep[e] >= ctx->M()) return fail(ctx, "L_keep[%lld] outside the matrix", (long long)e);
+    for (int e = 0; e < idx_rows * idx_cols; ++e) if (AD_index[e] < 0 || AD_index[e] >= n_classes) return fail(ctx, "AD_index entry outside the class tables");
+    const size_t nk = (size_t)std::max<int64_t>(mk, 1);
+    DevBuf dk, da, df, dl, di, d0, d1, d2;
+    if (buf_alloc(ctx, dk, nk * 4) || buf_alloc(ctx, da, nk * 4) || buf_alloc(ctx, df, (size_t)n_classes * 12) || buf_alloc(ctx, dl, (size_t)n_classes * 12) ||
+        buf_alloc(ctx, di, (size_t)idx_rows * idx_cols * 4) || buf_alloc(ctx, d0, nk * 4) || buf_alloc(ctx, d1, nk * 4) || buf_alloc(ctx, d2, nk * 4)) return 1;
+    CU(cudaMemcpyAsync(dk.p, L_keep, mk * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(da.p, A_vec, mk * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(df.p, AD_factorial, (size_t)n_classes * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dl.p, AD_like, (size_t)n_classes * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(di.p, AD_index, (size_t)idx_rows * idx_cols * 4, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH("zmoments", zmoments_list_kernel, grid_for(mk, 128, ctx->num_sm * 16), 128, 0, ctx->stream, ctx->G[0], ctx->AD, ctx->ldg,
+           ctx->col_of_ind[ind], dk.as<int>(), (long)mk, da.as<float>(), df.as<float>(), dl.as<float>(), di.as<int>(), idx_rows, idx_cols,
+           d0.as<float>(), d1.as<float>(), d2.as<float>());
+    if (W_obs_out) CU(cudaMemcpyAsync(W_obs_out, d0.p, mk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (W_l_out) CU(cudaMemcpyAsync(W_l_out, d1.p, mk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (W_var_out) CU(cudaMemcpyAsync(W_var_out, d2.p, mk * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
     return 0;
 }
 

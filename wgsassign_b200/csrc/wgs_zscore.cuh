@@ -318,4 +318,56 @@ zmoments_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// zmoments_list: the per-site arrays of zscore_cy.expected_W_l / variance_W_l for ONE
+// individual over an explicit list of kept sites, with the caller's own class tables
+// (zscore_cy.pyx:10-56, including the AD_index[Aa, Ar] lookup convention of :30).  One thread
+// per kept site; outputs are the float32 per-site vectors the Cython functions fill.
+// ---------------------------------------------------------------------------------------
+__global__ void zmoments_list_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, int col,
+                                     const int* __restrict__ L_keep, long mk, const float* __restrict__ Avec,
+                                     const float* __restrict__ AD_factorial, const float* __restrict__ AD_like,
+                                     const int* __restrict__ AD_index, int idx_rows, int idx_cols,
+                                     float* __restrict__ W_obs, float* __restrict__ W_l, float* __restrict__ W_var)
+{
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < mk; e += (long)gridDim.x * blockDim.x) {
+        const long s = L_keep[e];
+        const float2 g = G[s * (long)ldg + col];
+        const uchar2 ad = AD[s * (long)ldg + col];
+        const float a = Avec[e];
+        const float om = 1.0f - a;
+        const float P0 = om * om, P1 = 2.0f * om * a, P2 = a * a;
+        W_obs[e] = logf(fmaf(g.x, P0, fmaf(g.y, P1, third_gl(g.x, g.y) * P2)));
+        const int Dl = ad.x + ad.y;
+        float wl = 0.f;
+        for (int Aa = 0; Aa <= Dl; ++Aa) {
+            const int Ar = Dl - Aa;
+            int c = 0;
+            if (Aa < idx_rows && Ar < idx_cols) c = AD_index[Aa * idx_cols + Ar];
+            const float* l = AD_like + 3 * c;
+            const float* f = AD_factorial + 3 * c;
+            const float ee = logf(fmaf(l[0], P0, fmaf(l[1], P1, l[2] * P2)));
+            wl = __fadd_rn(wl, ee * P0 * f[0]);
+            wl = __fadd_rn(wl, ee * P1 * f[1]);
+            wl = __fadd_rn(wl, ee * P2 * f[2]);
+        }
+        float vr = 0.f;
+        for (int Aa = 0; Aa <= Dl; ++Aa) {
+            const int Ar = Dl - Aa;
+            int c = 0;
+            if (Aa < idx_rows && Ar < idx_cols) c = AD_index[Aa * idx_cols + Ar];
+            const float* l = AD_like + 3 * c;
+            const float* f = AD_factorial + 3 * c;
+            const float ee = logf(fmaf(l[0], P0, fmaf(l[1], P1, l[2] * P2)));
+            float dd = wl - ee;
+            dd = dd * dd;
+            vr = __fadd_rn(vr, dd * P0 * f[0]);
+            vr = __fadd_rn(vr, dd * P1 * f[1]);
+            vr = __fadd_rn(vr, dd * P2 * f[2]);
+        }
+        W_l[e] = wl;
+        W_var[e] = vr;
+    }
+}
+
 }  // namespace wgs
