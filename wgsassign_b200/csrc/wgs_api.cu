@@ -527,8 +527,7 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
     return 0;
 }
 
-struct LooLaunch { int block, rows_per_pass, passes, grid, U; bool big; size_t smem;
-                   int np2, strideA, strideB, grid_tma; size_t smem_tma; };
+struct LooLaunch { int block, rows_per_pass, passes, grid, U; bool big; size_t smem; bool v2; };
 
 // blocks of <= 384 threads are compiled for 3 resident blocks per SM (<= 56 registers), larger ones for 2
 template <int U> int loo_prepare_t(wgs_ctx* ctx, LooLaunch& L)
@@ -542,22 +541,13 @@ template <int U> int loo_prepare_t(wgs_ctx* ctx, LooLaunch& L)
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step_kernel<U, 384, 3>, L.block, L.smem));
     }
     L.grid = ctx->num_sm * std::max(occ, 1);
-    // the TMA-fed variant (pre-packed tiles, double buffered)
-    occ = 1;
-    if (L.big) {
-        if (L.smem_tma > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step_tma_kernel<U, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_tma));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step_tma_kernel<U, 512, 2>, L.block, L.smem_tma));
-    } else {
-        if (L.smem_tma > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step_tma_kernel<U, 384, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_tma));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step_tma_kernel<U, 384, 3>, L.block, L.smem_tma));
-    }
-    L.grid_tma = ctx->num_sm * std::max(occ, 1);
     return 0;
 }
 
-int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
+// the pair kernel (two problems per thread, one MUFU.RCP per evaluation): kept for A/B runs (WGS_LOO_V2=1)
+int loo_cfg_v2(wgs_ctx* ctx, int n, LooLaunch* out)
 {
-    LooLaunch best{0, 0, 1, 0, 4, false, 0, 0, 0, 0, 0, 0};
+    LooLaunch best{0, 0, 1, 0, 4, false, 0, true};
     const int npairs = (n + 1) / 2;                               // threads per site row (two problems each)
     double best_u = -1;
     for (int bd = 128; bd <= 512; bd += 32) {
@@ -582,11 +572,6 @@ int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
     best.passes = passes;
     best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float2);
     if (best.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", n);
-    best.np2 = (npu + 1) / 2 * 2;                               // packed row length: even, so both row segments are 16-byte multiples
-    best.strideA = best.np2 | 1;                                // 16-byte units, odd
-    best.strideB = best.np2 % 16 == 0 ? best.np2 + 2 : best.np2; // 8-byte units, even (16-byte aligned rows), never a multiple of 128 B
-    best.smem_tma = 2 * (size_t)best.rows_per_pass * passes * ((size_t)best.strideA * 16 + (size_t)best.strideB * 8)
-                    + (size_t)best.block * sizeof(float2);
     int rc = 0;
     switch (best.U) {
         case 4: rc = loo_prepare_t<4>(ctx, best); break;
@@ -595,6 +580,42 @@ int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
         default: rc = loo_prepare_t<7>(ctx, best); break;
     }
     if (rc) return rc;
+    *out = best;
+    return 0;
+}
+
+// the quad kernel (four problems per thread, one reciprocal per two evaluations): blocks of <= 256
+// threads are compiled for 3 resident blocks per SM, larger ones (populations of > 1024) for 1
+int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
+{
+    if (getenv("WGS_LOO_V2")) return loo_cfg_v2(ctx, n, out);
+    LooLaunch best{0, 0, 1, 0, 2, false, 0, false};
+    const int nq = (n + 3) / 4;                                   // threads per site row (four problems each)
+    double best_u = -1;
+    for (int bd = 128; bd <= 512; bd += 32) {
+        int rpp = bd / nq;
+        if (rpp < 1) continue;
+        double u = (double)(rpp * nq) / bd;
+        if (bd > 256 && best_u >= 0.88) break;                    // prefer the 3-blocks-per-SM variant unless it idles > 12 % of its threads
+        if (u > best_u + 1e-9) { best_u = u; best.block = bd; best.rows_per_pass = rpp; }
+    }
+    if (best.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (2048)", n);
+    best.big = best.block > 256;
+    const size_t row_bytes = (size_t)((3 * nq) | 1) * 16;
+    int passes = kLoo4MaxPasses;
+    while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 32 * 1024) --passes;
+    best.passes = passes;
+    best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float4);
+    if (best.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", n);
+    int occ = 1;
+    if (best.big) {
+        if (best.smem > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step4_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step4_kernel<512, 1>, best.block, best.smem));
+    } else {
+        if (best.smem > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step4_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step4_kernel<256, 3>, best.block, best.smem));
+    }
+    best.grid = ctx->num_sm * std::max(occ, 1);
     *out = best;
     return 0;
 }
@@ -615,32 +636,6 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         if (ctx->pops[k].n <= 1) continue;
         if (loo_cfg(ctx, ctx->pops[k].n, &cfgs[k])) return 1;
         nblocks = std::max(nblocks, cfgs[k].grid);
-    }
-    // pre-packed pair tiles for the TMA-fed kernel: 12 B per (site, individual); when the pool cannot
-    // provide them the in-kernel packing variant is used instead
-    std::vector<DevBuf> packA(K), packB(K);
-    // EXPERIMENTAL, opt-in (WGS_LOO_TMA=1): measured no faster than packing inside the step kernel
-    // (0.949 vs 0.935 ms per launch at 1 M x 50) for +50 % memory, and one small-population parity
-    // case still fails with it - kept for the next round, not used by default.
-    bool use_tma = getenv("WGS_LOO_TMA") != nullptr;
-    for (int k = 0; k < K && use_tma; ++k) {
-        if (ctx->pops[k].n <= 1) continue;
-        size_t ne = (size_t)std::max<long>(M, 1) * cfgs[k].np2;
-        packA[k].owner = ctx; packB[k].owner = ctx;
-        packA[k].p = pool_take(ctx, ne * 16);
-        packB[k].p = packA[k].p ? pool_take(ctx, ne * 8) : nullptr;
-        if (!packA[k].p || !packB[k].p) use_tma = false;
-    }
-    if (use_tma) {
-        for (int k = 0; k < K; ++k) {
-            if (ctx->pops[k].n <= 1) continue;
-            nblocks = std::max(nblocks, cfgs[k].grid_tma);
-            LAUNCH("loo_pack", loo_pack_kernel, grid_for(M * cfgs[k].np2, 256, ctx->num_sm * 16), 256, 0, ctx->stream, ctx->G[0], ldg, M,
-                   ctx->pops[k].col0, ctx->pops[k].n, cfgs[k].np2, packA[k].as<ulonglong2>(), packB[k].as<f32x2>());
-            add_work(ctx, "loo_pack", (double)M * ctx->pops[k].n * 8.0 + (double)M * cfgs[k].np2 * 24.0, (double)M * ctx->pops[k].n);
-        }
-    } else {
-        for (int k = 0; k < K; ++k) { buf_release(packA[k]); buf_release(packB[k]); }
     }
     EmState st;
     if (em_state_init(ctx, st, ldg, ldg, nblocks, active0)) return 1;
@@ -668,22 +663,21 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
             long ntiles = (M + TS - 1) / TS;
 #define LOO_LAUNCH(UU)                                                                                                          \
     do {                                                                                                                        \
-        if (use_tma && lc.big)                                                                                                  \
-            LAUNCH("loo_em", (loo_em_step_tma_kernel<UU, 512, 2>), lc.grid_tma, lc.block, lc.smem_tma, ctx->stream,               \
-                   packA[k].as<ulonglong2>(), packB[k].as<f32x2>(), lc.np2, M, ldg, pd.col0, pd.n, lc.rows_per_pass, lc.passes,   \
-                   lc.strideA, lc.strideB, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);                \
-        else if (use_tma)                                                                                                       \
-            LAUNCH("loo_em", (loo_em_step_tma_kernel<UU, 384, 3>), lc.grid_tma, lc.block, lc.smem_tma, ctx->stream,               \
-                   packA[k].as<ulonglong2>(), packB[k].as<f32x2>(), lc.np2, M, ldg, pd.col0, pd.n, lc.rows_per_pass, lc.passes,   \
-                   lc.strideA, lc.strideB, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);                \
-        else if (lc.big)                                                                                                        \
+        if (lc.big)                                                                                                             \
             LAUNCH("loo_em", (loo_em_step_kernel<UU, 512, 2>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n, \
                    lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);           \
         else                                                                                                                    \
             LAUNCH("loo_em", (loo_em_step_kernel<UU, 384, 3>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n, \
                    lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);           \
     } while (0)
-            switch (lc.U) {
+            if (!lc.v2) {
+                if (lc.big)
+                    LAUNCH("loo_em", (loo_em_step4_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
+                           lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
+                else
+                    LAUNCH("loo_em", (loo_em_step4_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
+                           lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
+            } else switch (lc.U) {
                 case 4: LOO_LAUNCH(4); break;
                 case 5: LOO_LAUNCH(5); break;
                 case 6: LOO_LAUNCH(6); break;
@@ -693,7 +687,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
             {   // the population's GL tile once + read/write of every active problem's f; n evaluations per active (site, problem)
                 double act = 0;
                 for (int j = 0; j < pd.n; ++j) act += st.h_active[pd.col0 + j] ? 1 : 0;
-                add_work(ctx, "loo_em", (double)M * pd.n * (use_tma ? 12.0 : 8.0) + (double)M * act * 8.0, (double)M * act * pd.n);
+                add_work(ctx, "loo_em", (double)M * pd.n * 8.0 + (double)M * act * 8.0, (double)M * act * pd.n);
             }
         }
         if (em_after_step(ctx, st, tole, it, d_count, (double)ctx->Mtot(), &n_active)) return 1;
@@ -1136,7 +1130,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     cudaSetDevice(ctx->device);
     if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
     if (!ctx->AD || ctx->M_ad != ctx->M()) return fail(ctx, "no allele depths resident (wgs_upload_ad)");
-    if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for the z-score operators");
+    if (!ctx->pops_set && mode != 2) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for the z-score operators");
     if (ind_start < 0 || ind_end > ctx->N || ind_start >= ind_end) return fail(ctx, "individual range [%d,%d) outside [0,%d)", ind_start, ind_end, ctx->N);
     if (mode < 0 || mode > 2) return fail(ctx, "mode must be 0 (assignment), 1 (reference) or 2 (preparation only)");
     if (mode == 0 && (!af || K != ctx->K)) return fail(ctx, "assignment mode needs af [M,%d]", ctx->K);
