@@ -70,7 +70,7 @@ SYMBOLS = {
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-lz"]
+              "--shared", "-Xcompiler", "-fPIC", "-lz", "-split-compile", "0"]
 
 
 def needs_build():

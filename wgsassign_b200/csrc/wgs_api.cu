@@ -592,7 +592,11 @@ int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
     LooLaunch best{0, 0, 1, 0, 2, false, 0, false};
     const int nq = (n + 3) / 4;                                   // threads per site row (four problems each)
     double best_u = -1;
-    for (int bd = 128; bd <= 512; bd += 32) {
+    // whole multiples of 4 warps only: 7 warps per block leave one scheduler of the SM with less work
+    // than the others (measured: 12 % slower than 8 warps, scripts/microbench/loo_quad_rate.cu)
+    const char* env_bd = getenv("WGS_LOO_BLOCK");
+    for (int bd = 128; bd <= 512; bd += 128) {
+        if (env_bd && atoi(env_bd) != bd) continue;
         int rpp = bd / nq;
         if (rpp < 1) continue;
         double u = (double)(rpp * nq) / bd;
@@ -601,18 +605,22 @@ int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
     }
     if (best.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (2048)", n);
     best.big = best.block > 256;
-    const size_t row_bytes = (size_t)((3 * nq) | 1) * 16;
+    // per tile row: two packed buffers (odd 16-byte stride) + the raw TMA landing row
+    const size_t row_bytes = 2 * (size_t)((3 * nq) | 1) * 16 + (size_t)nq * 32;
     int passes = kLoo4MaxPasses;
-    while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 32 * 1024) --passes;
+    while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 68 * 1024) --passes;
+    if (const char* env_p = getenv("WGS_LOO_PASSES")) passes = std::max(1, std::min(passes, atoi(env_p)));
     best.passes = passes;
     best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float4);
     if (best.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", n);
     int occ = 1;
     if (best.big) {
-        if (best.smem > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step4_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem));
+        CU(cudaFuncSetAttribute(loo_em_step4_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(loo_em_step4_kernel<512, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step4_kernel<512, 1>, best.block, best.smem));
     } else {
-        if (best.smem > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step4_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem));
+        CU(cudaFuncSetAttribute(loo_em_step4_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(loo_em_step4_kernel<256, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step4_kernel<256, 3>, best.block, best.smem));
     }
     best.grid = ctx->num_sm * std::max(occ, 1);

@@ -934,6 +934,11 @@ __device__ __forceinline__ void loo4_quad(const ulonglong2* __restrict__ q3, con
     }
 }
 
+// Staging: warp 0 streams the RAW slab rows of the next tile into shared memory with TMA bulk
+// copies (one per row, mbarrier-tracked) while the block computes the current tile; after its
+// own compute every thread repacks its share of the landed rows into the other packed buffer,
+// so the only block-wide barrier per tile sits where all warps have done the same work and no
+// warp ever waits on HBM latency.
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
@@ -945,11 +950,13 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
                     long ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar;
     const int nq = (n + 3) >> 2;                                // quads of individuals = threads per site row
     const int stride = (3 * nq) | 1;                            // 16-byte units, odd: rows never share a bank group
     const int TS = rows_per_pass * passes;
-    ulonglong2* tile = reinterpret_cast<ulonglong2*>(smem_raw);                 // [TS][stride]
-    float4* red = reinterpret_cast<float4*>(tile + (size_t)TS * stride);        // [blockDim.x]
+    ulonglong2* tile0 = reinterpret_cast<ulonglong2*>(smem_raw);                // [2][TS][stride]  packed quads
+    float4* raw = reinterpret_cast<float4*>(tile0 + 2 * (size_t)TS * stride);   // [TS][2 nq]       raw slab rows
+    float4* red = raw + (size_t)TS * 2 * nq;                                    // [blockDim.x]
 
     const int t = threadIdx.x;
     const int ti = t % nq, r = t / nq;                          // this thread's quad (problems 4ti..4ti+3) and row
@@ -966,10 +973,53 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
     const float inv_div = 1.0f / (float)(n - 1);
     float ssq[4] = {0.f, 0.f, 0.f, 0.f};
 
-    for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    if (t == 0) { mbar_init(&mbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    // warp 0: one TMA bulk copy per slab row of tile `tl` (rows are contiguous and 32-byte aligned)
+    auto issue = [&](long tl) {
+        if (tl < ntiles && t < 32) {
+            const long s0 = tl * TS;
+            const int rows = (int)min((long)TS, M - s0);
+            if (t == 0) mbar_expect_tx(&mbar, (unsigned)(rows * nq * 32));
+            __syncwarp();
+            for (int rr = t; rr < rows; rr += 32)
+                bulk_g2s(raw + (size_t)rr * 2 * nq, G + (s0 + rr) * (long)ldg + col0, (unsigned)(nq * 32), &mbar);
+        }
+    };
+    // raw rows -> packed quads of buffer `dst` (rows past M are never read by the compute phase)
+    auto repack = [&](ulonglong2* dst, long tl) {
+        const int rows = (int)min((long)TS, M - tl * TS);
+        for (int e = t; e < rows * nq; e += blockDim.x) {
+            const int sl = e / nq, q = e - sl * nq;
+            float4 ga = raw[(size_t)sl * 2 * nq + 2 * q], gc = raw[(size_t)sl * 2 * nq + 2 * q + 1];
+            if (4 * q + 1 >= n) { ga.z = 1.f; ga.w = 0.f; }     // slab padding: (1,0,0) contributes exactly 0
+            if (4 * q + 2 >= n) { gc.x = 1.f; gc.y = 0.f; }
+            if (4 * q + 3 >= n) { gc.z = 1.f; gc.w = 0.f; }
+            ulonglong2 v0, v1, v2;
+            v0.x = pack2(ga.x, ga.z);                           // g0 of (a,b)
+            v0.y = pack2(ga.y, ga.w);                           // g1 of (a,b)
+            v1.x = pack2(third_gl(ga.x, ga.y), third_gl(ga.z, ga.w));
+            v1.y = pack2(gc.x, gc.z);                           // g0 of (c,d)
+            v2.x = pack2(gc.y, gc.w);                           // g1 of (c,d)
+            v2.y = pack2(third_gl(gc.x, gc.y), third_gl(gc.z, gc.w));
+            ulonglong2* d = dst + sl * stride + 3 * q;
+            d[0] = v0; d[1] = v1; d[2] = v2;
+        }
+    };
+
+    unsigned phase = 0;
+    if (blockIdx.x < ntiles) {                                  // prologue: first tile packed, second in flight
+        issue(blockIdx.x);
+        mbar_wait(&mbar, phase); phase ^= 1u;
+        repack(tile0, blockIdx.x);
+        __syncthreads();
+        issue(blockIdx.x + (long)gridDim.x);
+    }
+    int cur = 0;
+    for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x, cur ^= 1) {
         const long s0 = tl * TS;
-        // this thread's f quad of the first pass: issued before the tile fill so that the latency overlaps it
-        // (the quad of pass p+1 is fetched while pass p computes)
+        const ulonglong2* tile = tile0 + (size_t)cur * TS * stride;
+        // this thread's f quad of pass p+1 is fetched while pass p computes
         unsigned ok_next;
         float4 f_next;
         auto fetch = [&](int p) {
@@ -983,30 +1033,6 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
             if (ok_next) f_next = *reinterpret_cast<const float4*>(&F[s * (long)ldf + c0]);
         };
         fetch(0);
-        __syncthreads();                                        // previous tile fully consumed
-        for (int e = t; e < TS * nq; e += blockDim.x) {
-            const int sl = e / nq, q = e - sl * nq;
-            const long s = s0 + sl;
-            float4 ga = make_float4(1.f, 0.f, 1.f, 0.f), gc = ga;   // (1,0,0): contributes exactly 0
-            if (s < M) {
-                const float4* src = reinterpret_cast<const float4*>(&G[s * (long)ldg + col0 + 4 * q]);
-                ga = ld_stream4(src);
-                gc = ld_stream4(src + 1);
-            }
-            if (4 * q + 1 >= n) { ga.z = 1.f; ga.w = 0.f; }     // slab padding: exactly-zero contributions
-            if (4 * q + 2 >= n) { gc.x = 1.f; gc.y = 0.f; }
-            if (4 * q + 3 >= n) { gc.z = 1.f; gc.w = 0.f; }
-            ulonglong2 v0, v1, v2;
-            v0.x = pack2(ga.x, ga.z);                           // g0 of (a,b)
-            v0.y = pack2(ga.y, ga.w);                           // g1 of (a,b)
-            v1.x = pack2(third_gl(ga.x, ga.y), third_gl(ga.z, ga.w));
-            v1.y = pack2(gc.x, gc.z);                           // g0 of (c,d)
-            v2.x = pack2(gc.y, gc.w);                           // g1 of (c,d)
-            v2.y = pack2(third_gl(gc.x, gc.y), third_gl(gc.z, gc.w));
-            ulonglong2* dst = tile + sl * stride + 3 * q;
-            dst[0] = v0; dst[1] = v1; dst[2] = v2;
-        }
-        __syncthreads();
 #pragma unroll 1
         for (int p = 0; p < passes; ++p) {
             const unsigned okp = ok_next;
@@ -1045,8 +1071,14 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
             }
             *reinterpret_cast<float4*>(&F[(s0 + sl) * (long)ldf + c0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
         }
+        const long nxt = tl + gridDim.x;
+        if (nxt < ntiles) {                                     // the next tile's raw rows landed while this one computed
+            mbar_wait(&mbar, phase); phase ^= 1u;
+            repack(tile0 + (size_t)(cur ^ 1) * TS * stride, nxt);
+        }
+        __syncthreads();                                        // packed[cur] consumed, packed[cur^1] complete, raw free
+        issue(nxt + gridDim.x);
     }
-    __syncthreads();
     red[t] = make_float4(ssq[0], ssq[1], ssq[2], ssq[3]);
     __syncthreads();
     if (t < n) {                                                // problem t = member (t & 3) of quad t / 4
