@@ -368,20 +368,30 @@ def main():
         return 0
 
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
-    # MUFU.RCP rate MEASURED on this pool's B200 (scripts/microbench/mufu_rate.cu, profiles/mufu_rate_r1.txt):
-    # 15.48 per clock per SM at 1,965 MHz = 4.50e12/s; scaled by the clock this run sustained
-    mufu_peak = 148 * 15.48 * sm_mhz * 1e6
+    # Issue-rate ceilings MEASURED on this pool's B200 (scripts/microbench/, profiles/issue_rates_r1.txt,
+    # profiles/mufu_rate_r1.txt), scaled by the clock this run sustained:
+    #   packed FP32 (FFMA2/FMUL2/FADD2): 1.687e13 lane-instructions/s at 1,965 MHz = 58.0 per clock per SM;
+    #   MUFU.RCP: 15.48 per clock per SM.
+    # The quad kernel spends 10 packed instructions and 2 reciprocals per 4 posterior evaluations, so the
+    # FP32 pipe binds (2.5 packed lane-instructions per evaluation), MUFU sits at 0.5 per evaluation.
+    fp32_peak = 148 * 58.0 * sm_mhz * 1e6 / 2.5
+    mufu_peak = 148 * 15.48 * sm_mhz * 1e6 / 0.5
     le = fam["loo_em"]
-    roofline = {"kernel": "loo_em_step_kernel", "bound": "hbm", "achieved": le["achieved_gbs"], "peak": hbm_peak,
+    roofline = {"kernel": "loo_em_step4_kernel", "bound": "hbm", "achieved": le["achieved_gbs"], "peak": hbm_peak,
                 "unit": "GB/s", "frac": le["hbm_frac"], "traffic": le.get("ncu_dram_bytes_per_launch"),
                 "algorithmic_bytes_per_launch": le.get("algorithmic_bytes_per_launch"), "peak_source": peak_src,
                 "ms_per_launch": le["ms_per_launch"], "launches": le["launches"],
                 "share_of_step": le["ms_total"] / (dt * 1e3),
                 "note": "by design NOT HBM-bound: each GL tile is read once per iteration and re-used for n^2 posterior "
-                        "evaluations from shared memory; the binding limit is the MUFU reciprocal rate (see `issue`); "
+                        "evaluations from shared memory; the binding limit is the packed-FP32 issue rate (see `issue`); "
                         "the HBM-bound kernels of the path are in `kernels` (em_pop, pop_like, fisher)",
-                "issue": {"bound": "mufu.rcp", "achieved": le["units_per_s"], "peak": mufu_peak, "peak_source": "measured 15.48 rcp/clk/SM (profiles/mufu_rate_r1.txt)", "unit": "posterior evals/s",
-                          "frac": le["units_per_s"] / mufu_peak, "sm_mhz": sm_mhz}}
+                "issue": {"bound": "fp32 pipe (FFMA2)", "achieved": le["units_per_s"], "peak": fp32_peak,
+                          "peak_source": "measured 58.0 packed FP32 lane-instructions/clk/SM (profiles/issue_rates_r1.txt), "
+                                         "2.5 per posterior evaluation",
+                          "unit": "posterior evals/s", "frac": le["units_per_s"] / fp32_peak, "sm_mhz": sm_mhz,
+                          "mufu_rcp_frac": le["units_per_s"] / mufu_peak,
+                          "inner_loop_ceiling": "5.2e12 evals/s for the bare inner loop from shared memory "
+                                                "(scripts/microbench/loo_quad_rate.cu)"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",

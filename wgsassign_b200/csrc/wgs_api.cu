@@ -394,6 +394,100 @@ int launch_loo_like_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, in
     return 0;
 }
 
+// ---- ratio-form likelihood kernel (pop_like2) --------------------------------------------------
+struct Like2Cfg { int R, gy; long spb; };
+const int kKT2[] = {4, 8, 10, 16, 20};
+int pick_KT2(int Krem)
+{
+    for (int kt : kKT2) if (kt >= Krem) return kt;
+    return 20;
+}
+// R sites between renormalisations: every per-site factor lies in [m/2, 1/(2m)]; R of them on a
+// mantissa in [1,2) must stay inside 2^+-120.  0 = margin too small for the ratio form.
+int pick_R2(float margin)
+{
+    if (!(margin >= 9.3132257e-10f)) return 0;                 // 2^-30 (also NaN / <= 0)
+    double bits = std::log2(1.0 / (double)margin) - 1.0;
+    if (bits < 1.0) bits = 1.0;
+    if (16.0 * bits <= 120.0) return 16;
+    if (8.0 * bits <= 120.0) return 8;
+    return 0;
+}
+Like2Cfg like2_cfg(wgs_ctx* ctx, long M, int R)
+{
+    Like2Cfg c;
+    c.R = R;
+    long target = (long)ctx->num_sm * 4;                          // ~2 waves of 2 resident blocks per SM
+    long spb = (M + target - 1) / target;
+    spb = std::max<long>(kPL2TS, (spb + kPL2TS - 1) / kPL2TS * kPL2TS);
+    spb = std::min<long>(spb, 256L * R);                          // 16-bit exponent fields: at most 256 renormalisations per thread
+    c.spb = spb;
+    c.gy = (int)std::max<long>(1, (M + spb - 1) / spb);
+    return c;
+}
+template <int KT, int I, int R>
+int launch_pop_like2_i(wgs_ctx* ctx, const float2* G, long M, const float* dA, int K, int k0, const Like2Cfg& c, double* partials)
+{
+    constexpr int KP = (KT + 1) / 2;
+    const int groups = (ctx->ldg + 32 * I - 1) / (32 * I);
+    // warps (column groups) per block: an exited warp keeps its registers until the whole block retires, so
+    // padding warps cost occupancy (9 groups in blocks of 4: 1.35 ms; in blocks of 1: 1.06 ms) - least padding wins
+    int wx = 1, best_waste = 1 << 30;
+    for (int w = 1; w <= 4; ++w) {
+        int waste = (groups + w - 1) / w * w - groups;
+        if (waste <= best_waste) { best_waste = waste; wx = w; }
+    }
+    if (const char* env_wx = getenv("WGS_PL2_WX")) wx = std::max(1, std::min(4, atoi(env_wx)));
+    const int gx = (groups + wx - 1) / wx;
+    // per-pass coefficient rows, padded to whole tiles so that the staging copies never run past the end
+    const long Mpad = (M + kPL2TS - 1) / kPL2TS * kPL2TS;
+    DevBuf xy;
+    if (buf_alloc(ctx, xy, (size_t)std::max<long>(Mpad, kPL2TS) * KP * sizeof(ulonglong2))) return 1;
+    LAUNCH("pop_like_xy", xy_precompute_kernel, grid_for(M * KP, 256, ctx->num_sm * 8), 256, 0, ctx->stream, dA, M, K, k0, KP, xy.as<ulonglong2>());
+    const size_t smem = (size_t)wx * 2 * kPL2TS * KP * sizeof(ulonglong2);
+    auto kern = pop_like2_kernel<KT, I, R>;
+    if (smem > 40 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    LAUNCH("pop_like", kern, dim3(gx, c.gy), wx * 32, smem, ctx->stream,
+           G, ctx->ldg, M, xy.as<ulonglong2>(), K, k0, c.spb, partials);
+    {   // algorithmic: every (g0,g1) pair once per pass + this pass's AF columns; one evaluation per (site, ind, pop)
+        int kt = std::min(KT, K - k0);
+        add_work(ctx, "pop_like", (double)M * ctx->N * 8.0 + (double)M * kt * 4.0, (double)M * ctx->N * kt);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));               // xy is released on return
+    return 0;
+}
+template <int KT, int I>
+int launch_pop_like2_r(wgs_ctx* ctx, const float2* G, long M, const float* dA, int K, int k0, const Like2Cfg& c, double* partials)
+{
+    if (c.R == 16) return launch_pop_like2_i<KT, I, 16>(ctx, G, M, dA, K, k0, c, partials);
+    return launch_pop_like2_i<KT, I, 8>(ctx, G, M, dA, K, k0, c, partials);
+}
+int launch_pop_like2(wgs_ctx* ctx, int KT, const float2* G, long M, const float* dA, int K, int k0, const Like2Cfg& c, double* partials)
+{
+    switch (KT) {
+        case 4: return launch_pop_like2_r<4, 2>(ctx, G, M, dA, K, k0, c, partials);
+        case 8: return launch_pop_like2_r<8, 2>(ctx, G, M, dA, K, k0, c, partials);
+        case 10: return launch_pop_like2_r<10, 2>(ctx, G, M, dA, K, k0, c, partials);
+        case 16: return launch_pop_like2_r<16, 1>(ctx, G, M, dA, K, k0, c, partials);
+        default: return launch_pop_like2_r<20, 1>(ctx, G, M, dA, K, k0, c, partials);
+    }
+}
+// sums[col][k] += sum over this rank's sites of log(2 a (1-a)) for population k
+int add_af_logsum(wgs_ctx* ctx, const float* dA, long M, int K, double* sums, long np)
+{
+    // blocks of a whole multiple of K threads: thread t only ever visits population t % K
+    const int block = K <= 256 ? K * (256 / K) : K;
+    const int grid = ctx->num_sm * 4;
+    const long T = (long)grid * block;
+    DevBuf per, C;
+    if (buf_alloc(ctx, per, (size_t)T * sizeof(double)) || buf_alloc(ctx, C, (size_t)K * sizeof(double))) return 1;
+    LAUNCH("af_logsum", af_logsum_kernel, grid, block, 0, ctx->stream, dA, M * K, per.as<double>());
+    LAUNCH("af_logsum", af_logsum_reduce_kernel, (K + 127) / 128, 128, 0, ctx->stream, per.as<double>(), T, K, C.as<double>());
+    LAUNCH("af_logsum", add_pop_const_kernel, grid_for(np, 256, ctx->num_sm * 4), 256, 0, ctx->stream, sums, np, K, C.as<double>());
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 #define DISPATCH_R(FN, KTV, R, ...)                                      \
     switch (R) {                                                         \
         case 8: rc_ = FN<KTV, 8>(__VA_ARGS__); break;                    \
@@ -415,7 +509,7 @@ int launch_loo_like_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, in
     } while (0)
 
 // margin of a device AF matrix -> renormalisation interval
-int af_R(wgs_ctx* ctx, const float* dA, long n, int* R_out)
+int af_R(wgs_ctx* ctx, const float* dA, long n, int* R_out, float* margin_out = nullptr)
 {
     DevBuf b;
     if (buf_alloc(ctx, b, sizeof(int))) return 1;
@@ -428,6 +522,7 @@ int af_R(wgs_ctx* ctx, const float* dA, long n, int* R_out)
     float m;
     memcpy(&m, &bits, 4);
     *R_out = pick_R(m);
+    if (margin_out) *margin_out = m;
     return 0;
 }
 
@@ -942,7 +1037,26 @@ int32_t wgs_pop_like_partial(wgs_ctx* ctx, const float* af, int32_t K, double* o
     if (buf_alloc(ctx, dA, (size_t)M * K * sizeof(float))) return 1;
     CU(cudaMemcpyAsync(dA.p, af, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     int R = 1;
-    if (af_R(ctx, dA.as<float>(), M * K, &R)) return 1;
+    float margin = 0.f;
+    if (af_R(ctx, dA.as<float>(), M * K, &R, &margin)) return 1;
+    const int R2 = getenv("WGS_POPLIKE_V1") ? 0 : pick_R2(margin);
+    if (R2 > 0) {
+        // ratio form (pop_like2): every AF inside [2^-16, 1-2^-16] - always true after the reference's clipping
+        Like2Cfg c2 = like2_cfg(ctx, M, R2);
+        size_t np2 = (size_t)ctx->ldg * K;
+        if (buf_alloc(ctx, partials, (size_t)c2.gy * np2 * sizeof(double)) || buf_alloc(ctx, sums, np2 * sizeof(double))) return 1;
+        for (int k0 = 0; k0 < K;) {
+            int KT = pick_KT2(K - k0);
+            if (launch_pop_like2(ctx, KT, ctx->G[0], M, dA.as<float>(), K, k0, c2, partials.as<double>())) return 1;
+            k0 += KT;
+        }
+        LAUNCH("reduce", reduce_partials_kernel, grid_for(np2, 256, ctx->num_sm * 4), 256, 0, ctx->stream, partials.as<double>(), c2.gy,
+               (long)np2, sums.as<double>());
+        if (add_af_logsum(ctx, dA.as<float>(), M, K, sums.as<double>(), (long)np2)) return 1;
+        if (cols_to_host(ctx, sums.as<double>(), K, out)) return 1;
+        CU(cudaGetLastError());
+        return 0;
+    }
     // one launch geometry for all passes: the widest tile decides the individuals per thread
     int I = pop_like_inds(pick_KT(K), ctx->ldg);
     LikeCfg c = like_cfg(ctx, M, 2, I);

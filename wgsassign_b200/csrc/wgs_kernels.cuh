@@ -479,6 +479,261 @@ pop_like_kernel(const float2* __restrict__ G, int ldg, long M,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// pop_like2: the same sums as pop_like in RATIO form - the kernel the drivers use whenever
+// every allele frequency lies inside [2^-30, 1-2^-30] (always, after the reference's clipping).
+//
+//   log(g0 (1-a)^2 + g1 2a(1-a) + g2 a^2) = log(2a(1-a)) + log(g0 x + g1 + g2 y),
+//   x = (1-a)/(2a),  y = a/(2(1-a))
+//
+// The first term does not depend on the individual: af_logsum_kernel sums it once per
+// population (exactly, same mantissa-product scheme).  What is left per evaluation is two
+// multiply-adds and the running-product multiply (was three + one), and the per-(site,
+// population pair) coefficients shrink from 24 to 16 bytes: ONE broadcast LDS.128 per two
+// evaluations, shared by the I individuals a thread carries.  Every per-site factor lies in
+// [m/2, 1/(2m)] (m = smallest min(a, 1-a)), a range symmetric in log scale and half as wide
+// as the [m^2, 1] of the direct form, so twice as many sites fit between renormalisations
+// (R = 4, 8 or 16, picked on the host from m).
+//
+// Exponent sums of a population PAIR share one register (two 16-bit fields, at most 255 per
+// renormalisation): a thread may renormalise at most 256 times, i.e. walks at most 256 R sites,
+// which the launch geometry guarantees (sites_per_block <= 256 R).
+//
+// Block = wx warps, each a different group of 32 I columns, all walking the same sites, so the
+// coefficient tile is built once per wx 32 I individuals.  partials[split][col][K] as pop_like.
+// ---------------------------------------------------------------------------------------
+template <int KT>
+struct LikeAccP {
+    static constexpr int KP = (KT + 1) / 2;
+    f32x2 prod[KP];
+    unsigned esum[KP];                       // lo 16 bits: slot 2q, hi 16 bits: slot 2q+1
+    unsigned zero_mask, nan_mask;
+    int nren;
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int q = 0; q < KP; ++q) { prod[q] = pack2(1.0f, 1.0f); esum[q] = 0u; }
+        zero_mask = nan_mask = 0u; nren = 0;
+    }
+    __device__ __forceinline__ float slow1(float p, int k, unsigned& field) {
+        const int b = __float_as_int(p);
+        if ((unsigned)(b - 0x00800000) < 0x7F000000u) { field = (unsigned)(b >> 23); return __int_as_float((b & 0x007fffff) | 0x3f800000); }
+        if (p == 0.0f || (b > 0 && b < 0x00800000)) zero_mask |= (1u << k);      // 0 or denormal
+        else nan_mask |= (1u << k);                                          // negative, inf, NaN
+        field = 127u;
+        return 1.0f;
+    }
+    __device__ __forceinline__ void renorm() {
+        unsigned worst = 0u;
+#pragma unroll
+        for (int q = 0; q < KP; ++q) {
+            const float2 v = unpack2(prod[q]);
+            worst = max(worst, max((unsigned)(__float_as_int(v.x) - 0x00800000), (unsigned)(__float_as_int(v.y) - 0x00800000)));
+        }
+        if (worst < 0x7F000000u) {                             // every product is a positive normal number
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                const float2 v = unpack2(prod[q]);
+                const unsigned b0 = __float_as_uint(v.x), b1 = __float_as_uint(v.y);
+                esum[q] += (b0 >> 23) + ((b1 >> 7) & 0xFFFF0000u);
+                prod[q] = pack2(__uint_as_float((b0 & 0x007fffffu) | 0x3f800000u), __uint_as_float((b1 & 0x007fffffu) | 0x3f800000u));
+            }
+        } else {                                               // rare: a zero / negative / NaN factor somewhere
+#pragma unroll
+            for (int q = 0; q < KP; ++q) {
+                const float2 v = unpack2(prod[q]);
+                unsigned f0, f1;
+                const float p0 = slow1(v.x, 2 * q, f0), p1 = slow1(v.y, 2 * q + 1, f1);
+                esum[q] += f0 + (f1 << 16);
+                prod[q] = pack2(p0, p1);
+            }
+        }
+        ++nren;
+    }
+    __device__ __forceinline__ double value(int k) const {     // natural-log sum of slot k
+        if (nan_mask & (1u << k)) return __longlong_as_double(0x7ff8000000000000LL);
+        if (zero_mask & (1u << k)) return __longlong_as_double(0xfff0000000000000LL);
+        const float2 v = unpack2(prod[k >> 1]);
+        const unsigned field = (k & 1) ? (esum[k >> 1] >> 16) : (esum[k >> 1] & 0xFFFFu);
+        const double e = (double)((int)field - 127 * nren);
+        return (e + log2((double)((k & 1) ? v.y : v.x))) * 0.693147180559945309417232121458;
+    }
+};
+
+constexpr int kPL2TS = 32;       // sites per coefficient tile (one warp-private tile)
+constexpr int kPL2PF = 8;        // sites prefetched per thread
+
+// XY[s][q] = {(x_a, x_b), (y_a, y_b)} for the population pair (k0+2q, k0+2q+1) of site s, computed
+// once per pass (16 bytes per two (site, population) cells); slots past K are (1/2, 1/2).
+__global__ void xy_precompute_kernel(const float* __restrict__ A, long M, int K, int k0, int KP, ulonglong2* __restrict__ XY)
+{
+    const long total = M * KP;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long s = e / KP;
+        const int q = (int)(e - s * KP);
+        float x[2], y[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = k0 + 2 * q + h;
+            x[h] = 0.5f; y[h] = 0.5f;                     // dummy slot: factor g0/2 + g1 + g2/2, never stored
+            if (k < K) {
+                const float a = __ldg(&A[s * K + k]);
+                const float om = 1.0f - a;
+                x[h] = om * fast_rcp(a + a);
+                y[h] = a * fast_rcp(om + om);
+            }
+        }
+        ulonglong2 v;
+        v.x = pack2(x[0], x[1]); v.y = pack2(y[0], y[1]);
+        XY[e] = v;
+    }
+}
+
+template <int KT, int I, int R, bool FULL>
+__device__ __forceinline__ void pop_like2_tile(const float2* const (&Gcol)[I], int ldg, long s0, long s_end,
+                                               const ulonglong2* __restrict__ XY, LikeAccP<KT> (&acc)[I])
+{
+    constexpr int KP = (KT + 1) / 2;
+    constexpr int CH = (R > kPL2PF) ? R : kPL2PF;              // sites per unrolled chunk
+    static_assert(kPL2TS % CH == 0, "tile must hold whole chunks");
+#pragma unroll 1
+    for (int c0 = 0; c0 < kPL2TS; c0 += CH) {
+#pragma unroll
+        for (int u0 = 0; u0 < CH; u0 += kPL2PF) {
+            float2 g[kPL2PF][I];
+            const float2* base[I];
+#pragma unroll
+            for (int i = 0; i < I; ++i) base[i] = Gcol[i] + (s0 + c0 + u0) * (long)ldg;
+#pragma unroll
+            for (int u = 0; u < kPL2PF; ++u) {
+                const long s = s0 + c0 + u0 + u;
+#pragma unroll
+                for (int i = 0; i < I; ++i) {
+                    if (FULL || s < s_end) g[u][i] = ld_stream2(base[i] + u * ldg);
+                    else g[u][i] = make_float2(1.0f, 0.0f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kPL2PF; ++u) {
+                const int sl = c0 + u0 + u;
+                if (FULL || s0 + sl < s_end) {                 // warp-uniform
+                    f32x2 g0[I], g1[I], g2[I];
+#pragma unroll
+                    for (int i = 0; i < I; ++i) {
+                        const float t = third_gl(g[u][i].x, g[u][i].y);
+                        g0[i] = pack2(g[u][i].x, g[u][i].x); g1[i] = pack2(g[u][i].y, g[u][i].y); g2[i] = pack2(t, t);
+                    }
+#pragma unroll
+                    for (int q = 0; q < KP; ++q) {
+                        const ulonglong2 xy = XY[sl * KP + q];
+#pragma unroll
+                        for (int i = 0; i < I; ++i)
+                            acc[i].prod[q] = fmul2(acc[i].prod[q], ffma2(g2[i], xy.y, ffma2(g0[i], xy.x, g1[i])));
+                    }
+                }
+                if (((u0 + u + 1) % R) == 0) {
+#pragma unroll
+                    for (int i = 0; i < I; ++i) acc[i].renorm();
+                }
+            }
+        }
+    }
+}
+
+// One WARP = one work unit (32 I columns x one site split): its coefficient tiles are private
+// (double-buffered LDGSTS copies of the precomputed XY rows), so there is no block-wide barrier
+// anywhere and warps drift freely - the block-shared tile with two barriers per 64 sites cost
+// 19 % at 9 warps per block.  A block is just up to 4 neighbouring column groups.
+template <int KT, int I, int R>
+__global__ void __launch_bounds__(128, 5)
+pop_like2_kernel(const float2* __restrict__ G, int ldg, long M,
+                 const ulonglong2* __restrict__ XYg,      // [M rounded up to kPL2TS][KP]
+                 int K, int k0,
+                 long sites_per_block,                    // multiple of kPL2TS, <= 256 R
+                 double* __restrict__ partials)
+{
+    constexpr int KP = (KT + 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ulonglong2* XY = reinterpret_cast<ulonglong2*>(smem_raw) + (size_t)warp * 2 * kPL2TS * KP;   // [2][TS][KP], this warp's
+
+    const int wx = blockDim.x >> 5;
+    const int col_base = (blockIdx.x * wx + warp) * 32 * I + lane;
+    if (col_base - lane >= ldg) return;                   // warp-uniform: nothing to do (no barriers below)
+    const float2* Gcol[I];
+    bool col_ok[I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        const int c = col_base + 32 * i;
+        col_ok[i] = c < ldg;
+        Gcol[i] = G + (col_ok[i] ? c : ldg - 1);         // out-of-range slots read a valid column and are never stored
+    }
+    const long s_begin = (long)blockIdx.y * sites_per_block;
+    const long s_end = min(M, s_begin + sites_per_block);
+
+    LikeAccP<KT> acc[I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) acc[i].init();
+
+    auto stage = [&](long s0, int buf) {                  // 32 rows of KP 16-byte cells: contiguous in XYg
+        const ulonglong2* src = XYg + s0 * KP;
+        ulonglong2* dst = XY + buf * (kPL2TS * KP);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) cp_async16(dst + lane + 32 * j, src + lane + 32 * j);
+        cp_async_commit();
+    };
+    if (s_begin < s_end) stage(s_begin, 0);
+    int buf = 0;
+    for (long s0 = s_begin; s0 < s_end; s0 += kPL2TS, buf ^= 1) {
+        if (s0 + kPL2TS < s_end) { stage(s0 + kPL2TS, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();
+        const ulonglong2* tile = XY + buf * (kPL2TS * KP);
+        if (s0 + kPL2TS <= s_end) pop_like2_tile<KT, I, R, true>(Gcol, ldg, s0, s_end, tile, acc);
+        else pop_like2_tile<KT, I, R, false>(Gcol, ldg, s0, s_end, tile, acc);
+        __syncwarp();                                     // everyone is done with `buf` before it is refilled
+    }
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+        acc[i].renorm();                                 // brings every slot to a known state
+        if (col_ok[i]) {
+#pragma unroll
+            for (int kk = 0; kk < KT; ++kk)
+                if (k0 + kk < K) partials[((long)blockIdx.y * ldg + col_base + 32 * i) * K + k0 + kk] = acc[i].value(kk);
+        }
+    }
+}
+
+// C[t] = sum over the elements e = t, t+T, ... of log(2 a_e (1 - a_e)), T = total threads, a multiple of K:
+// every element a thread visits belongs to population t % K.  Reduced per population in a fixed
+// order by af_logsum_reduce_kernel.  (The population-only term of the ratio form above.)
+__global__ void af_logsum_kernel(const float* __restrict__ A, long n, double* __restrict__ per_thread)
+{
+    const long T = (long)gridDim.x * blockDim.x, t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    LikeAcc<1> acc;
+    acc.init();
+    int cnt = 0;
+    for (long e = t; e < n; e += T) {
+        const float a = __ldg(&A[e]);
+        acc.prod[0] *= (a + a) * (1.0f - a);
+        if (++cnt == 2) { acc.renorm(); cnt = 0; }        // two factors >= 2^-29 each stay far above underflow
+    }
+    acc.renorm();
+    per_thread[t] = acc.value(0);
+}
+__global__ void af_logsum_reduce_kernel(const double* __restrict__ per_thread, long T, int K, double* __restrict__ C)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double v = 0.0;
+    for (long t = k; t < T; t += K) v += per_thread[t];
+    C[k] = v;
+}
+// sums[col][k] += C[k]
+__global__ void add_pop_const_kernel(double* __restrict__ sums, long n, int K, const double* __restrict__ C)
+{
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) sums[e] += C[e % K];
+}
+
 // out[col][k] = sum over splits (fixed order) of partials[split][col][k]
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int nsplit, long n, double* __restrict__ out)
 {
