@@ -1,0 +1,5 @@
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+B="timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extra"
+for d in 0 1; do
+WGS_LOO_DBG=$d $B > gpurun_out/b0.json 2>gpurun_out/b0.err; echo "dbg $d"; python scripts/bench_brief.py gpurun_out/b0.json | sed -n 1,2p; tail -1 gpurun_out/b0.err
+done

@@ -67,6 +67,57 @@ __global__ void __launch_bounds__(256, 3) probe(float* out, int nq, int rows, in
     out[blockIdx.x * blockDim.x + t] = s;
 }
 
+template <bool MUFU>
+__global__ void __launch_bounds__(256, 3) probe5(float* out, int nq, int rows, int iters, float f0)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ulonglong2* tile = reinterpret_cast<ulonglong2*>(smem_raw);
+    const int nc = (nq + 1) / 2, stride = (5 * nc) | 1;
+    for (int e = threadIdx.x; e < rows * stride; e += blockDim.x) {
+        ulonglong2 v; v.x = pack2(0.3f + 1e-3f * (e % 7), 0.2f); v.y = pack2(0.25f, 0.35f + 1e-3f * (e % 5));
+        tile[e] = v;
+    }
+    __syncthreads();
+    const int t = threadIdx.x, r = (t / nq) % rows;
+    Loo5Coef c[4];
+    f32x2 acc[4];
+    for (int k = 0; k < 4; ++k) { c[k] = loo5_coef(f0 + 0.01f * k + 1e-4f * (t & 7)); acc[k] = 0ull; }
+    const ulonglong2* row = tile + r * stride;
+    for (int it = 0; it < iters; ++it) {
+        const int nfull = nq >> 1;
+#pragma unroll 1
+        for (int cc = 0; cc < nfull; ++cc) {
+            const ulonglong2 v0 = row[5 * cc], v1 = row[5 * cc + 1], v2 = row[5 * cc + 2], v3 = row[5 * cc + 3], v4 = row[5 * cc + 4];
+            loo5_quad(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
+            loo5_quad(v2.y, v3.x, v3.y, v4.x, v4.y, c, acc);
+        }
+        if (nq & 1) {
+            const ulonglong2 v0 = row[5 * nfull], v1 = row[5 * nfull + 1], v2 = row[5 * nfull + 2];
+            loo5_quad(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
+        }
+    }
+    float s = 0.f;
+    for (int k = 0; k < 4; ++k) { float2 a = unpack2(acc[k]); s += a.x + a.y; }
+    out[blockIdx.x * blockDim.x + t] = s;
+}
+void run5(float* d, int block, int nq, int rows, int iters)
+{
+    const size_t smem = (size_t)rows * ((5 * ((nq + 1) / 2)) | 1) * 16;
+    cudaFuncSetAttribute(probe5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe5<true>, block, smem);
+    const int grid = 148 * occ;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    probe5<true><<<grid, block, smem>>>(d, nq, rows, 10, 0.3f);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    probe5<true><<<grid, block, smem>>>(d, nq, rows, iters, 0.3f);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double evals = (double)grid * block * iters * nq * 16.0;
+    printf("%-28s block %3d occ %d: %.3e evals/s  (%s)\n", "pair polynomials (step5)", block, occ, evals / (ms * 1e-3), cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int MODE> void run(const char* name, float* d, int block, int nq, int rows, int iters)
 {
     const size_t smem = (size_t)rows * ((3 * nq) | 1) * 16;
@@ -92,8 +143,7 @@ int main()
     for (int block : {128, 224, 256}) {
         run<0>("smem operands + MUFU", d, block, 13, 34, 2000);
         run<1>("smem operands, no MUFU", d, block, 13, 34, 2000);
-        run<2>("register operands + MUFU", d, block, 13, 34, 2000);
-        run<3>("register operands, no MUFU", d, block, 13, 34, 2000);
+        run5(d, block, 13, 34, 2000);
     }
     return 0;
 }

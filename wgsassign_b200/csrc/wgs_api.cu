@@ -622,70 +622,16 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
     return 0;
 }
 
-struct LooLaunch { int block, rows_per_pass, passes, grid, U; bool big; size_t smem; bool v2; };
+struct LooLaunch { int block, rows_per_pass, passes, grid; bool big; size_t smem; bool packed; int nc; };
 
-// blocks of <= 384 threads are compiled for 3 resident blocks per SM (<= 56 registers), larger ones for 2
-template <int U> int loo_prepare_t(wgs_ctx* ctx, LooLaunch& L)
+// Launch geometry of the leave-one-out EM step kernels (four problems per thread).  packed = the
+// pre-packed pair-polynomial kernel (loo_em_step5), else the in-kernel packing quad kernel (loo_em_step4).
+// Blocks of <= 256 threads are compiled for 3 resident blocks per SM, larger ones (populations of > 1024) for 1.
+int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
 {
-    int occ = 1;
-    if (L.big) {
-        if (L.smem > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step_kernel<U, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step_kernel<U, 512, 2>, L.block, L.smem));
-    } else {
-        if (L.smem > 40 * 1024) CU(cudaFuncSetAttribute(loo_em_step_kernel<U, 384, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step_kernel<U, 384, 3>, L.block, L.smem));
-    }
-    L.grid = ctx->num_sm * std::max(occ, 1);
-    return 0;
-}
-
-// the pair kernel (two problems per thread, one MUFU.RCP per evaluation): kept for A/B runs (WGS_LOO_V2=1)
-int loo_cfg_v2(wgs_ctx* ctx, int n, LooLaunch* out)
-{
-    LooLaunch best{0, 0, 1, 0, 4, false, 0, true};
-    const int npairs = (n + 1) / 2;                               // threads per site row (two problems each)
-    double best_u = -1;
-    for (int bd = 128; bd <= 512; bd += 32) {
-        int rpp = bd / npairs;
-        if (rpp < 1) continue;
-        double u = (double)(rpp * npairs) / bd;
-        if (bd > 384 && best_u >= 0.88) break;                    // prefer the 3-blocks-per-SM variant unless it idles > 12 % of its threads
-        if (u > best_u + 1e-9) { best_u = u; best.block = bd; best.rows_per_pass = rpp; }
-    }
-    if (best.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (1024)", n);
-    best.big = best.block > 384;
-    int np = (n + 1) / 2;
-    int pad_best = 1 << 30;
-    for (int U = 4; U <= 7; ++U) {                                // unroll factor that pads the pair loop least (ties: larger)
-        int pad = (np + U - 1) / U * U - np;
-        if (pad <= pad_best) { pad_best = pad; best.U = U; }
-    }
-    int npu = (np + best.U - 1) / best.U * best.U, stride = npu | 1;
-    size_t row_bytes = (size_t)stride * 24;                     // 16 B (g0,g1 pairs) + 8 B (g2 pair) per pair
-    int passes = kLooMaxPasses;
-    while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 24 * 1024) --passes;
-    best.passes = passes;
-    best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float2);
-    if (best.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", n);
-    int rc = 0;
-    switch (best.U) {
-        case 4: rc = loo_prepare_t<4>(ctx, best); break;
-        case 5: rc = loo_prepare_t<5>(ctx, best); break;
-        case 6: rc = loo_prepare_t<6>(ctx, best); break;
-        default: rc = loo_prepare_t<7>(ctx, best); break;
-    }
-    if (rc) return rc;
-    *out = best;
-    return 0;
-}
-
-// the quad kernel (four problems per thread, one reciprocal per two evaluations): blocks of <= 256
-// threads are compiled for 3 resident blocks per SM, larger ones (populations of > 1024) for 1
-int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
-{
-    if (getenv("WGS_LOO_V2")) return loo_cfg_v2(ctx, n, out);
-    LooLaunch best{0, 0, 1, 0, 2, false, 0, false};
+    LooLaunch best{0, 0, 1, 0, false, 0, packed, 0};
     const int nq = (n + 3) / 4;                                   // threads per site row (four problems each)
+    best.nc = (nq + 1) / 2;
     double best_u = -1;
     // whole multiples of 4 warps only: 7 warps per block leave one scheduler of the SM with less work
     // than the others (measured: 12 % slower than 8 warps, scripts/microbench/loo_quad_rate.cu)
@@ -700,24 +646,26 @@ int loo_cfg(wgs_ctx* ctx, int n, LooLaunch* out)
     }
     if (best.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (2048)", n);
     best.big = best.block > 256;
-    // per tile row: two packed buffers (odd 16-byte stride) + the raw TMA landing row
-    const size_t row_bytes = 2 * (size_t)((3 * nq) | 1) * 16 + (size_t)nq * 32;
-    int passes = kLoo4MaxPasses;
+    // per tile row - quad kernel: two packed buffers (odd 16-byte stride) + the raw TMA landing row;
+    //              - packed kernel: double-buffered packed cells (odd 16-byte stride) + double-buffered raw row
+    const size_t row_bytes = packed ? kLoo5Stages * (size_t)loo5_row_units(n) * 16
+                                    : 2 * (size_t)((3 * nq) | 1) * 16 + (size_t)nq * 32;
+    int passes = packed ? 1 : kLoo4MaxPasses;                   // the packed kernel's ring holds single row groups
     while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 68 * 1024) --passes;
     if (const char* env_p = getenv("WGS_LOO_PASSES")) passes = std::max(1, std::min(passes, atoi(env_p)));
     best.passes = passes;
     best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float4);
     if (best.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", n);
     int occ = 1;
-    if (best.big) {
-        CU(cudaFuncSetAttribute(loo_em_step4_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CU(cudaFuncSetAttribute(loo_em_step4_kernel<512, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step4_kernel<512, 1>, best.block, best.smem));
-    } else {
-        CU(cudaFuncSetAttribute(loo_em_step4_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CU(cudaFuncSetAttribute(loo_em_step4_kernel<256, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, loo_em_step4_kernel<256, 3>, best.block, best.smem));
-    }
+#define LOO_PREP(KERN)                                                                                               \
+    do {                                                                                                             \
+        CU(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                     \
+        CU(cudaFuncSetAttribute(KERN, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, best.block, best.smem));                        \
+    } while (0)
+    if (packed) { if (best.big) LOO_PREP((loo_em_step5_kernel<512, 1>)); else LOO_PREP((loo_em_step5_kernel<256, 3>)); }
+    else        { if (best.big) LOO_PREP((loo_em_step4_kernel<512, 1>)); else LOO_PREP((loo_em_step4_kernel<256, 3>)); }
+#undef LOO_PREP
     best.grid = ctx->num_sm * std::max(occ, 1);
     *out = best;
     return 0;
@@ -737,8 +685,29 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     int nblocks = 1;
     for (int k = 0; k < K; ++k) {
         if (ctx->pops[k].n <= 1) continue;
-        if (loo_cfg(ctx, ctx->pops[k].n, &cfgs[k])) return 1;
+        nblocks = std::max(nblocks, 1);
+    }
+    // pre-packed pair polynomials (loo_em_step5): 80 bytes per 8 individuals and site, written once per call;
+    // when the pool cannot provide them (or WGS_LOO_V4 is set) the in-kernel packing quad kernel runs instead
+    std::vector<DevBuf> pk(K);
+    const int loo_dbg = getenv("WGS_LOO_DBG") ? atoi(getenv("WGS_LOO_DBG")) : 0;
+    bool packed = getenv("WGS_LOO_V4") == nullptr;
+    for (int k = 0; k < K && packed; ++k) {
+        if (ctx->pops[k].n <= 1) continue;
+        pk[k].owner = ctx;
+        pk[k].p = pool_take(ctx, (size_t)std::max<long>(M, 1) * loo5_row_units(ctx->pops[k].n) * sizeof(ulonglong2));
+        if (!pk[k].p) packed = false;
+    }
+    if (!packed) for (int k = 0; k < K; ++k) buf_release(pk[k]);
+    for (int k = 0; k < K; ++k) {
+        if (ctx->pops[k].n <= 1) continue;
+        if (loo_cfg(ctx, ctx->pops[k].n, packed, &cfgs[k])) return 1;
         nblocks = std::max(nblocks, cfgs[k].grid);
+        if (packed) {
+            LAUNCH("loo_pack", loo_prepack_kernel, grid_for(M * cfgs[k].nc, 256, ctx->num_sm * 16), 256, 0, ctx->stream, ctx->G[0], ldg, M,
+                   ctx->pops[k].col0, ctx->pops[k].n, cfgs[k].nc, pk[k].as<ulonglong2>());
+            add_work(ctx, "loo_pack", (double)M * ctx->pops[k].n * 8.0 + (double)M * loo5_row_units(ctx->pops[k].n) * 16.0, (double)M * ctx->pops[k].n);
+        }
     }
     EmState st;
     if (em_state_init(ctx, st, ldg, ldg, nblocks, active0)) return 1;
@@ -764,33 +733,25 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
             const LooLaunch& lc = cfgs[k];
             int TS = lc.rows_per_pass * lc.passes;
             long ntiles = (M + TS - 1) / TS;
-#define LOO_LAUNCH(UU)                                                                                                          \
-    do {                                                                                                                        \
-        if (lc.big)                                                                                                             \
-            LAUNCH("loo_em", (loo_em_step_kernel<UU, 512, 2>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n, \
-                   lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);           \
-        else                                                                                                                    \
-            LAUNCH("loo_em", (loo_em_step_kernel<UU, 384, 3>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n, \
-                   lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);           \
-    } while (0)
-            if (!lc.v2) {
+            if (lc.packed) {
+                if (lc.big)
+                    LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
+                           pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, loo_dbg);
+                else
+                    LAUNCH("loo_em", (loo_em_step5_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
+                           pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, loo_dbg);
+            } else {
                 if (lc.big)
                     LAUNCH("loo_em", (loo_em_step4_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
                            lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
                 else
                     LAUNCH("loo_em", (loo_em_step4_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
                            lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
-            } else switch (lc.U) {
-                case 4: LOO_LAUNCH(4); break;
-                case 5: LOO_LAUNCH(5); break;
-                case 6: LOO_LAUNCH(6); break;
-                default: LOO_LAUNCH(7); break;
             }
-#undef LOO_LAUNCH
             {   // the population's GL tile once + read/write of every active problem's f; n evaluations per active (site, problem)
                 double act = 0;
                 for (int j = 0; j < pd.n; ++j) act += st.h_active[pd.col0 + j] ? 1 : 0;
-                add_work(ctx, "loo_em", (double)M * pd.n * 8.0 + (double)M * act * 8.0, (double)M * act * pd.n);
+                add_work(ctx, "loo_em", (double)M * (lc.packed ? loo5_row_units(pd.n) * 16.0 : pd.n * 8.0) + (double)M * act * 8.0, (double)M * act * pd.n);
             }
         }
         if (em_after_step(ctx, st, tole, it, d_count, (double)ctx->Mtot(), &n_active)) return 1;

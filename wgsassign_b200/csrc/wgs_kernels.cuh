@@ -105,6 +105,10 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
     unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(a), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(a) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile(
@@ -975,169 +979,34 @@ em_pop_step_kernel(const float2* __restrict__ G, int ldg, long M,
 }
 
 // ---------------------------------------------------------------------------------------
-// loo_em_step: ONE EM iteration of every still-active leave-one-out problem of ONE
-// population (glassy.py:65-78: emMAF on the population minus individual i, for every i).
+// Leave-one-out EM (glassy.py:65-78: emMAF on the population minus individual i, for every i).
+// ONE launch = ONE EM iteration of every still-active leave-one-out problem of ONE population.
 // Problem i at site s follows its own trajectory f_i, so each (site, i) evaluates all n
 // posterior terms at f_i: n^2 evaluations per site and iteration from ONE read of the
-// population's GL tile.  The tile is staged in shared memory by PAIRS of individuals,
-//   tA[site][pair] = {(g0_a,g0_b), (g1_a,g1_b)}   (128-bit)   tB[site][pair] = (g2_a,g2_b) (64-bit)
-// so that the four multiply-adds of two posterior terms issue as FMUL2 + 3 FFMA2; the two
-// reciprocals (MUFU.RCP) and the two accumulating FFMAs stay scalar.
+// population's GL tile, staged in shared memory.
 //
-// One thread owns TWO problems (the two members of pair ti) at one site and feeds both from
-// the same shared-memory read: a broadcast LDS still delivers its 24 bytes to every lane, and
-// with one problem per thread that delivered-byte rate (128 B/clk/SM) - not MUFU, not issue -
-// was the limit (83 % of it at 2.5e12 evaluations/s).  Two problems per read halve it and
-// leave the MUFU reciprocal rate (16 per clock per SM) as the binding unit.
+// History of the inner loop (each step measured on B200, 1 M sites x 50 individuals):
+//   pair kernel  - two problems per thread, FMUL2 + 3 FFMA2 + 2 MUFU.RCP + 2 FFMA per two evaluations:
+//                  0.936 ms, 57 % of the MUFU reciprocal rate, which bound it (removed);
+//   quad kernel  - loo_em_step4 below: ratio form, one reciprocal per two evaluations, four problems
+//                  per thread, TMA-staged rows: 0.776 ms;
+//   packed kernel - loo_em_step5: pre-packed pair polynomials, 8 packed instructions per four evaluations.
 //
 // The left-out individual's own term is removed after the loop.  (sum - own) can cancel to
-// exactly 0 when nobody else carries the allele, and an exact 0 (or 1) would turn the next
+// (nearly) 0 when nobody else carries the allele, and an exact 0 (or 1) would turn the next
 // iteration's 0 * inf into NaN where the reference stays finite, so f is kept inside
 // [1e-12, 1-2^-24]; both are far outside the clipping range applied afterwards
 // (glassy.py:80-85) and 7 orders below the 1e-5 parity tolerance.
 //
-// A thread keeps its two problems for the whole launch, so their squared changes are
+// A thread keeps its problems for the whole launch, so their squared changes are
 // registers; partials[block][col] are reduced in fixed order by em_ssq_reduce_kernel.
 // mask (optional): uchar keep[M][ldg] - sites whose squared change counts (reference
 // z-score runs the EM on kept sites only, WGSassign.py:358-359; a site outside the mask
 // cannot influence another site, so it is simply skipped).
 // ---------------------------------------------------------------------------------------
-constexpr int kLooMaxPasses = 4;
-struct LooCoef { f32x2 H0, H1, H2; float h0, h1, h2; };
-__device__ __forceinline__ LooCoef loo_coef(float f) {
-    LooCoef c;
-    const float om = 1.0f - f;
-    c.h0 = 2.0f * om * om; c.h1 = 2.0f * f * om; c.h2 = 2.0f * f * f;
-    c.H0 = pack2(c.h0, c.h0); c.H1 = pack2(c.h1, c.h1); c.H2 = pack2(c.h2, c.h2);
-    return c;
-}
-// U = pairs per unrolled inner-loop trip; the tile rows are padded with zero-contribution pairs to a
-// multiple of U (the host picks the U in {4,5,6,7} that pads least), so there is no remainder loop.
-template <int U, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-loo_em_step_kernel(const float2* __restrict__ G, int ldg, long M,
-                   int col0, int n, int rows_per_pass, int passes,
-                   float* __restrict__ F, int ldf,              // [M][ldf], in place
-                   const int* __restrict__ active,              // [ldg]
-                   const unsigned char* __restrict__ mask,      // [M][ldg] or null
-                   double* __restrict__ partials,               // [gridDim.x][ldg]
-                   long ntiles)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int np = (n + 1) >> 1;                                // pairs of individuals = threads per site row
-    const int npu = (np + U - 1) / U * U;                       // padded to the unroll factor
-    const int stride = npu | 1;                                 // odd: two rows never share a bank group
-    const int TS = rows_per_pass * passes;
-    ulonglong2* tA = reinterpret_cast<ulonglong2*>(smem_raw);                   // [TS][stride]
-    f32x2* tB = reinterpret_cast<f32x2*>(tA + (size_t)TS * stride);             // [TS][stride]
-    float2* red = reinterpret_cast<float2*>(tB + (size_t)TS * stride);          // [blockDim.x]
-
-    const int t = threadIdx.x;
-    const int Bp = rows_per_pass * np;
-    const int ti = t % np, r = t / np;                          // this thread's pair (problems 2ti, 2ti+1) and row
-    const bool worker = t < Bp;
-    const int cA = col0 + 2 * ti, cB = cA + 1;
-    const bool hasB = 2 * ti + 1 < n;
-    const bool actA = worker && active[cA] != 0;
-    const bool actB = worker && hasB && active[cB] != 0;
-    const bool any_act = actA || actB;
-    const float inv_div = 1.0f / (float)(n - 1);
-    float ssqA = 0.f, ssqB = 0.f;
-
-    for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
-        const long s0 = tl * TS;
-        // this thread's f pairs for the tile: issued before the tile fill so that the latency overlaps it
-        float2 fv[kLooMaxPasses];
-        bool okA[kLooMaxPasses], okB[kLooMaxPasses];
-#pragma unroll
-        for (int p = 0; p < kLooMaxPasses; ++p) {
-            const long s = s0 + p * rows_per_pass + r;
-            const bool in = any_act && p < passes && s < M;
-            okA[p] = in && actA; okB[p] = in && actB;
-            if (in && mask) {
-                okA[p] = okA[p] && mask[s * (long)ldg + cA] != 0;
-                okB[p] = okB[p] && mask[s * (long)ldg + cB] != 0;
-            }
-            fv[p] = make_float2(0.25f, 0.25f);
-            if (okA[p] || okB[p]) fv[p] = *reinterpret_cast<const float2*>(&F[s * (long)ldf + cA]);
-        }
-        __syncthreads();                                        // previous tile fully consumed
-        for (int e = t; e < TS * npu; e += blockDim.x) {
-            int sl = e / npu, q = e - sl * npu;
-            long s = s0 + sl;
-            float4 g = make_float4(1.f, 0.f, 1.f, 0.f);         // (1,0,0): contributes exactly 0
-            if (s < M && q < np) g = ld_stream4(reinterpret_cast<const float4*>(&G[s * (long)ldg + col0 + 2 * q]));
-            if (2 * q + 1 >= n) { g.z = 1.f; g.w = 0.f; }       // odd n: the pad partner contributes exactly 0
-            ulonglong2 a;
-            a.x = pack2(g.x, g.z);
-            a.y = pack2(g.y, g.w);
-            tA[sl * stride + q] = a;
-            tB[sl * stride + q] = pack2(third_gl(g.x, g.y), third_gl(g.z, g.w));
-        }
-        __syncthreads();
-#pragma unroll
-        for (int p = 0; p < kLooMaxPasses; ++p) {
-            if (!(okA[p] || okB[p])) continue;
-            const int sl = p * rows_per_pass + r;
-            const LooCoef ca = loo_coef(fv[p].x), cb = loo_coef(fv[p].y);
-            const ulonglong2* rowA = tA + sl * stride;
-            const f32x2* rowB = tB + sl * stride;
-            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-            for (int q0 = 0; q0 < npu; q0 += U) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const ulonglong2 ab = rowA[q0 + u];
-                    const f32x2 g2 = rowB[q0 + u];
-                    f32x2 numa = ffma2(ab.y, ca.H1, fmul2(g2, ca.H2));
-                    f32x2 numb = ffma2(ab.y, cb.H1, fmul2(g2, cb.H2));
-                    f32x2 dena = ffma2(ab.x, ca.H0, ffma2(ab.y, ca.H1, numa));
-                    f32x2 denb = ffma2(ab.x, cb.H0, ffma2(ab.y, cb.H1, numb));
-                    float2 na = unpack2(numa), da = unpack2(dena), nb = unpack2(numb), db = unpack2(denb);
-                    a0 = fmaf(na.x, fast_rcp(da.x), a0);
-                    a1 = fmaf(na.y, fast_rcp(da.y), a1);
-                    b0 = fmaf(nb.x, fast_rcp(db.x), b0);
-                    b1 = fmaf(nb.y, fast_rcp(db.y), b1);
-                }
-            }
-            // own terms (the two halves of pair ti), recomputed with the same operations so that they cancel
-            float ownA, ownB;
-            {
-                const ulonglong2 ab = rowA[ti];
-                const float2 g0 = unpack2(ab.x), g1 = unpack2(ab.y), g2 = unpack2(rowB[ti]);
-                float num = fmaf(g1.x, ca.h1, g2.x * ca.h2);
-                float den = fmaf(g0.x, ca.h0, fmaf(g1.x, ca.h1, num));
-                ownA = num * fast_rcp(den);
-                num = fmaf(g1.y, cb.h1, g2.y * cb.h2);
-                den = fmaf(g0.y, cb.h0, fmaf(g1.y, cb.h1, num));
-                ownB = num * fast_rcp(den);
-            }
-            float fa = ((a0 + a1) - ownA) * inv_div;
-            float fb = ((b0 + b1) - ownB) * inv_div;
-            if (fa < 1e-12f) fa = 1e-12f;                      // comparisons are false for NaN: NaN survives
-            if (fa > 0.99999994f) fa = 0.99999994f;
-            if (fb < 1e-12f) fb = 1e-12f;
-            if (fb > 0.99999994f) fb = 0.99999994f;
-            float* dst = &F[(s0 + sl) * (long)ldf + cA];
-            if (okA[p]) { float d = fa - fv[p].x; ssqA += d * d; dst[0] = fa; }
-            if (okB[p]) { float d = fb - fv[p].y; ssqB += d * d; dst[1] = fb; }
-        }
-    }
-    __syncthreads();
-    red[t] = make_float2(ssqA, ssqB);
-    __syncthreads();
-    if (t < n) {                                                // problem t = half (t & 1) of pair t / 2
-        double v = 0.0;
-        for (int q = 0; q < rows_per_pass; ++q) {
-            float2 x = red[q * np + (t >> 1)];
-            v += (double)((t & 1) ? x.y : x.x);
-        }
-        partials[(long)blockIdx.x * ldg + col0 + t] = v;
-    }
-}
-
 // ---------------------------------------------------------------------------------------
-// loo_em_step4: the same EM iteration as loo_em_step, re-derived so that the MUFU reciprocal
-// is no longer the binding unit (it was: 57 % of 16 RCP/clk/SM at 1 M x 50).
+// loo_em_step4: the EM iteration re-derived so that the MUFU reciprocal is no longer the
+// binding unit (it was: 57 % of 16 RCP/clk/SM at 1 M x 50).
 //
 //  * ratio form.  Dividing numerator and denominator of the posterior mean
 //        (p1 + 2 p2) / (2 (p0 + p1 + p2)),  p = (g0 (1-f)^2, 2 g1 f (1-f), g2 f^2)
@@ -1155,7 +1024,7 @@ loo_em_step_kernel(const float2* __restrict__ G, int ldg, long M,
 // Tile layout: tile[site][3 q + {0,1,2}] = {g0_ab, g1_ab}, {g2_ab, g0_cd}, {g1_cd, g2_cd}
 // (16-byte units, odd row stride).  Pad individuals are (1,0,0): num = 0 exactly.
 // The left-out individual's own term is subtracted after the loop as a plain n/d; unlike in
-// loo_em_step the cancellation is not bit-exact (the sum holds it inside a combined fraction),
+// the earlier pair kernel the cancellation is not bit-exact (the sum holds it inside a combined fraction),
 // so "nobody else carries the allele" gives |f| ~ 1e-8 instead of the 1e-12 floor - both are
 // orders of magnitude below the clipping bound applied afterwards (glassy.py:80-85).
 // ---------------------------------------------------------------------------------------
@@ -1334,6 +1203,254 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
         __syncthreads();                                        // packed[cur] consumed, packed[cur^1] complete, raw free
         issue(nxt + gridDim.x);
     }
+    red[t] = make_float4(ssq[0], ssq[1], ssq[2], ssq[3]);
+    __syncthreads();
+    if (t < n) {                                                // problem t = member (t & 3) of quad t / 4
+        double v = 0.0;
+        for (int q = 0; q < rows_per_pass; ++q) {
+            const float4 x = red[q * nq + (t >> 2)];
+            const int k = t & 3;
+            v += (double)(k == 0 ? x.x : k == 1 ? x.y : k == 2 ? x.z : x.w);
+        }
+        partials[(long)blockIdx.x * ldg + col0 + t] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// loo_em_step5: the quad iteration on PRE-PACKED pair polynomials.
+//
+// With d_i(b) = g0_i a + 2 g1_i + g2_i b and n_i(b) = g1_i + g2_i b (a = (1-f)/f = 1/b), the two posterior
+// terms of a PAIR of individuals are one fraction N/D whose numerator and denominator are Laurent
+// polynomials in b with coefficients that depend on the two individuals only:
+//     D = d_i d_j         = c0 a^2 + 2 c1 a + c2 + 2 c3 b + c4 b^2
+//     N = n_i d_j + n_j d_i =          c1 a + c2 + 3 c3 b + 2 c4 b^2
+//     c0 = g0 g0', c1 = g0 g1' + g1 g0', c2 = 4 g1 g1' + g0 g2' + g2 g0', c3 = g1 g2' + g2 g1', c4 = g2 g2'
+// (all terms non-negative: no cancellation anywhere).  The five coefficients are the same for all
+// ~15 iterations of all n problems, so loo_prepack_kernel writes them ONCE per call as planes
+// P = (c0, 2 c1, c2, 2 c3, c4), packed so that the two pairs (a,b), (c,d) of a quad sit in the two lanes
+// of an f32x2.  Per four evaluations the step kernel then issues 7 FFMA2 + 2 MUFU.RCP + 1 FFMA2
+// (the quad kernel: 10 packed + 2), reads 40 instead of 48 bytes of shared memory and has no packing
+// code at all: warp 0 streams packed rows and raw rows (for the left-out individual's own term)
+// straight into a double buffer with TMA bulk copies.
+// Cell = two quads (8 individuals) = 5 x 16 bytes: {P0A,P1A} {P2A,P3A} {P4A,P0B} {P1B,P2B} {P3B,P4B}.
+// A pad individual is (1,0,0): a pair of pads gives D = a^2, N = 0; one pad gives exactly the
+// other member's n/d.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void loo5_pair_coefs(float g0, float g1, float g2, float h0, float h1, float h2, float (&P)[5])
+{
+    P[0] = g0 * h0;
+    P[1] = 2.0f * fmaf(g0, h1, g1 * h0);
+    P[2] = fmaf(4.0f * g1, h1, fmaf(g0, h2, g2 * h0));
+    P[3] = 2.0f * fmaf(g1, h2, g2 * h1);
+    P[4] = g2 * h2;
+}
+// Row layout (16-byte units): [5 nc packed cells | 2 nq raw float4 (the slab's (g0,g1) pairs, for the own terms) | pad to an odd count]
+// - rows of consecutive sites are contiguous, so a whole group of rows is ONE bulk copy, and the odd row
+// length keeps the rows of a quarter-warp on different bank groups.
+__host__ __device__ __forceinline__ int loo5_row_units(int n) { const int nq = (n + 3) >> 2, nc = (nq + 1) >> 1; return (5 * nc + 2 * nq) | 1; }
+__global__ void loo_prepack_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n, int nc,
+                                   ulonglong2* __restrict__ PK)          // [M][loo5_row_units(n)]
+{
+    const int nq = (n + 3) >> 2;
+    const int ru = loo5_row_units(n);
+    const long total = M * (long)nc;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long s = e / nc;
+        const int c = (int)(e - s * nc);
+        ulonglong2* rowp = PK + s * (long)ru;
+        f32x2 P[2][5];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = 2 * c + h;
+            float4 ga = make_float4(1.f, 0.f, 1.f, 0.f), gc = ga;       // (1,0,0) pads
+            if (q < nq) {
+                const float4* src = reinterpret_cast<const float4*>(&G[s * (long)ldg + col0 + 4 * q]);
+                ga = ld_stream4(src);
+                gc = ld_stream4(src + 1);
+                float4* rawp = reinterpret_cast<float4*>(rowp + 5 * nc) + 2 * q;
+                rawp[0] = ga; rawp[1] = gc;
+            }
+            if (4 * q + 1 >= n) { ga.z = 1.f; ga.w = 0.f; }
+            if (4 * q + 2 >= n) { gc.x = 1.f; gc.y = 0.f; }
+            if (4 * q + 3 >= n) { gc.z = 1.f; gc.w = 0.f; }
+            float Pab[5], Pcd[5];
+            loo5_pair_coefs(ga.x, ga.y, third_gl(ga.x, ga.y), ga.z, ga.w, third_gl(ga.z, ga.w), Pab);
+            loo5_pair_coefs(gc.x, gc.y, third_gl(gc.x, gc.y), gc.z, gc.w, third_gl(gc.z, gc.w), Pcd);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) P[h][j] = pack2(Pab[j], Pcd[j]);
+        }
+        ulonglong2* dst = rowp + 5 * c;
+        ulonglong2 v;
+        v.x = P[0][0]; v.y = P[0][1]; dst[0] = v;
+        v.x = P[0][2]; v.y = P[0][3]; dst[1] = v;
+        v.x = P[0][4]; v.y = P[1][0]; dst[2] = v;
+        v.x = P[1][1]; v.y = P[1][2]; dst[3] = v;
+        v.x = P[1][3]; v.y = P[1][4]; dst[4] = v;
+        if (c == 0 && (5 * nc + 2 * nq) != ru) rowp[ru - 1] = make_ulonglong2(0ull, 0ull);   // the pad unit: defined bytes for the copy
+    }
+}
+
+struct Loo5Coef { f32x2 A, B, AH, B43, BH; float a, b; };
+__device__ __forceinline__ Loo5Coef loo5_coef(float f) {
+    Loo5Coef c;
+    const float om = 1.0f - f;
+    c.a = om * fast_rcp(f);
+    c.b = f * fast_rcp(om);
+    const float ah = 0.5f * c.a, b43 = 1.33333337f * c.b, bh = 1.5f * c.b;
+    c.A = pack2(c.a, c.a); c.B = pack2(c.b, c.b); c.AH = pack2(ah, ah); c.B43 = pack2(b43, b43); c.BH = pack2(bh, bh);
+    return c;
+}
+__device__ __forceinline__ float loo5_own(float g0, float g1, float g2, const Loo5Coef& c) {
+    const float num = fmaf(g2, c.b, g1);
+    const float den = fmaf(g0, c.a, g1 + num);
+    return num * fast_rcp(den);
+}
+__device__ __forceinline__ void loo5_quad(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3, f32x2 P4, const Loo5Coef (&c)[4], f32x2 (&acc)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const f32x2 u = ffma2(P0, c[k].A, P1);
+        const f32x2 v = ffma2(P4, c[k].B, P3);
+        const f32x2 D = ffma2(v, c[k].B, ffma2(u, c[k].A, P2));
+        const f32x2 t = ffma2(P4, c[k].B43, P3);
+        const f32x2 N = ffma2(t, c[k].BH, ffma2(P1, c[k].AH, P2));
+        const float2 dd = unpack2(D);
+        acc[k] = ffma2(N, pack2(fast_rcp(dd.x), fast_rcp(dd.y)), acc[k]);
+    }
+}
+
+// Pipeline: a ring of kLoo5Stages row groups (rows_per_pass site rows each) guarded by full/empty
+// mbarrier pairs - no block-wide barrier in the loop.  Every warp waits for "full", computes its rows
+// and arrives on "empty"; one lane of warp 0 additionally refills a slot with ONE TMA bulk copy (the rows
+// of a group are contiguous in the packed array) as soon as all warps have released it, kLoo5Stages-1
+// groups ahead of use.  (One copy per row from warp 0 made that warp 50 % slower than the others, and
+// every other warp then waited for it at "full": 23 % of all stall samples.)
+constexpr int kLoo5Stages = 3;
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
+                    int col0, int n, int rows_per_pass,
+                    float* __restrict__ F, int ldf,              // [M][ldf], in place
+                    const int* __restrict__ active,              // [ldg]
+                    const unsigned char* __restrict__ mask,      // [M][ldg] or null
+                    double* __restrict__ partials,               // [gridDim.x][ldg]
+                    long ntiles,                                 // groups of rows_per_pass rows
+                    int dbg)                                     // experiments: 1 = no restaging (stale tiles), 2 = staging only
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long full[kLoo5Stages], empty[kLoo5Stages];
+    const int nq = (n + 3) >> 2;                                // quads of individuals = threads per site row
+    const int nc = (nq + 1) >> 1;                               // cells (two quads) per row
+    const int ru = loo5_row_units(n);                           // row length in 16-byte units (odd)
+    const int TS = rows_per_pass;
+    ulonglong2* pk0 = reinterpret_cast<ulonglong2*>(smem_raw);                            // [S][TS][ru]  packed cells + raw pairs
+    float4* red = reinterpret_cast<float4*>(pk0 + kLoo5Stages * (size_t)TS * ru);         // [blockDim.x]
+
+    const int t = threadIdx.x, lane = t & 31;
+    const int ti = t % nq, r = t / nq;                          // this thread's quad (problems 4ti..4ti+3) and row
+    const bool worker = t < rows_per_pass * nq;
+    const int c0 = col0 + 4 * ti;
+    unsigned act = 0;                                           // bit k: problem 4ti+k exists and is still iterating
+    if (worker) {
+        const int4 a4 = *reinterpret_cast<const int4*>(&active[c0]);
+        act = (a4.x != 0 ? 1u : 0u) | (a4.y != 0 ? 2u : 0u) | (a4.z != 0 ? 4u : 0u) | (a4.w != 0 ? 8u : 0u);
+        if (4 * ti + 1 >= n) act &= 1u;
+        if (4 * ti + 2 >= n) act &= 3u;
+        if (4 * ti + 3 >= n) act &= 7u;
+    }
+    const float inv_div = 1.0f / (float)(n - 1);
+    float ssq[4] = {0.f, 0.f, 0.f, 0.f};
+
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < kLoo5Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], blockDim.x >> 5); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // thread 0: one TMA bulk copy for the whole group `tl` into ring slot `slot`
+    auto issue = [&](long tl, int slot) {
+        if (tl < ntiles && t == 0) {
+            const long s0 = tl * TS;
+            const int rows = (int)min((long)TS, M - s0);
+            const unsigned bytes = (unsigned)rows * (unsigned)ru * 16u;
+            mbar_expect_tx(&full[slot], bytes);
+            bulk_g2s(pk0 + (size_t)slot * TS * ru, PK + s0 * (long)ru, bytes, &full[slot]);
+        }
+    };
+    if (t < 32) {
+#pragma unroll
+        for (int s = 0; s < kLoo5Stages; ++s) issue(blockIdx.x + (long)s * gridDim.x, s);
+    }
+
+    // this thread's f quad of the next group is fetched while the current one computes
+    unsigned ok_next;
+    float4 f_next;
+    auto fetch = [&](long tl) {
+        const long s = tl * TS + r;
+        ok_next = (tl < ntiles && s < M) ? act : 0u;
+        if (ok_next && mask) {
+            const uchar4 mk = *reinterpret_cast<const uchar4*>(&mask[s * (long)ldg + c0]);
+            ok_next &= (mk.x ? 1u : 0u) | (mk.y ? 2u : 0u) | (mk.z ? 4u : 0u) | (mk.w ? 8u : 0u);
+        }
+        f_next = make_float4(0.25f, 0.25f, 0.25f, 0.25f);
+        if (ok_next) f_next = *reinterpret_cast<const float4*>(&F[s * (long)ldf + c0]);
+    };
+    fetch(blockIdx.x);
+    int slot = 0;
+    unsigned phase = 0;
+#pragma unroll 1
+    for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const unsigned okp = ok_next;
+        const float4 fq = f_next;
+        fetch(tl + gridDim.x);
+        const bool staged = dbg != 1 || tl < blockIdx.x + (long)kLoo5Stages * gridDim.x;
+        if (staged) mbar_wait(&full[slot], phase);              // this group has landed
+        if (okp && dbg != 2) {
+            const float fin[4] = {fq.x, fq.y, fq.z, fq.w};
+            Loo5Coef c[4];
+            f32x2 acc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { c[k] = loo5_coef(fin[k]); acc[k] = 0ull; }
+            const ulonglong2* row = pk0 + ((size_t)slot * TS + r) * ru;
+            const int nfull = nq >> 1;                          // cells with both quads
+#pragma unroll 1
+            for (int cc = 0; cc < nfull; ++cc) {
+                const ulonglong2 v0 = row[5 * cc], v1 = row[5 * cc + 1], v2 = row[5 * cc + 2], v3 = row[5 * cc + 3], v4 = row[5 * cc + 4];
+                loo5_quad(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
+                loo5_quad(v2.y, v3.x, v3.y, v4.x, v4.y, c, acc);
+            }
+            if (nq & 1) {
+                const ulonglong2 v0 = row[5 * nfull], v1 = row[5 * nfull + 1], v2 = row[5 * nfull + 2];
+                loo5_quad(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
+            }
+            // own terms: the four members of quad ti, from the raw pairs at the end of the row
+            const float4* rawrow = reinterpret_cast<const float4*>(row + 5 * nc);
+            const float4 ga = rawrow[2 * ti], gc = rawrow[2 * ti + 1];
+            const float own[4] = {loo5_own(ga.x, ga.y, third_gl(ga.x, ga.y), c[0]), loo5_own(ga.z, ga.w, third_gl(ga.z, ga.w), c[1]),
+                                  loo5_own(gc.x, gc.y, third_gl(gc.x, gc.y), c[2]), loo5_own(gc.z, gc.w, third_gl(gc.z, gc.w), c[3])};
+            float fo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 a = unpack2(acc[k]);
+                float fn = ((a.x + a.y) - own[k]) * inv_div;
+                if (fn < 1e-12f) fn = 1e-12f;                   // comparisons are false for NaN: NaN survives
+                if (fn > 0.99999994f) fn = 0.99999994f;
+                fo[k] = fin[k];                                 // frozen / masked problems keep their value
+                if (okp & (1u << k)) { const float d = fn - fin[k]; ssq[k] += d * d; fo[k] = fn; }
+            }
+            *reinterpret_cast<float4*>(&F[(tl * TS + r) * (long)ldf + c0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);               // this warp is done with the slot
+        if (t < 32) {                                           // warp 0 refills it once every warp has released it
+            const long nxt = tl + (long)kLoo5Stages * gridDim.x;
+            if (nxt < ntiles && dbg != 1) {
+                mbar_wait(&empty[slot], phase);
+                issue(nxt, slot);
+            }
+        }
+        if (++slot == kLoo5Stages) { slot = 0; phase ^= 1u; }
+    }
+    __syncthreads();
     red[t] = make_float4(ssq[0], ssq[1], ssq[2], ssq[3]);
     __syncthreads();
     if (t < n) {                                                // problem t = member (t & 3) of quad t / 4
