@@ -581,7 +581,17 @@ int em_after_step(wgs_ctx* ctx, EmState& st, double tole, int iteration, const d
     return 0;
 }
 
+// Stop rule of emMAF.py:21-25 with rmse1d's float divide / double sqrt (emMAF_cy.pyx:32-33).
+inline bool em_converged(double ssq, double count, double tole)
+{
+    float res = (float)ssq;
+    res = res / (float)count;
+    return std::sqrt((double)res) < tole;
+}
+
 // Per-population EM on the resident G: FT [K][M] (device, population-major) <- converged, UNclipped f.
+// Up to kEmChunk iterations per read of G (em_pop_multi_kernel); WGS_EM_STEP=1 selects the
+// one-iteration-per-launch kernel (same bits, 14 reads of G instead of 3).
 int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>& iters_out)
 {
     const long M = ctx->M();
@@ -595,29 +605,90 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
     while (R > 8 && 2 * (size_t)R * row16 * 16 > 110 * 1024) R /= 2;
     size_t smem = 2 * (size_t)R * row16 * 16;
     if (smem > 220 * 1024) return fail(ctx, "population of %d individuals exceeds the EM shared-memory tile", nmax);
+    const bool multi = getenv("WGS_EM_STEP") == nullptr;
     // always opt in: static + dynamic shared memory together may cross the 48 KB default limit
-    CU(cudaFuncSetAttribute(em_pop_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, em_pop_step_kernel, R * kEmT, smem));
+    if (multi) {
+        CU(cudaFuncSetAttribute(em_pop_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, em_pop_multi_kernel, R * kEmT, smem));
+    } else {
+        CU(cudaFuncSetAttribute(em_pop_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, em_pop_step_kernel, R * kEmT, smem));
+    }
     long ntiles = (M + R - 1) / R;
     // one full wave of persistent blocks: gx * K <= resident slots
     int gx = (int)std::max<long>(1, std::min<long>(ntiles, ((long)ctx->num_sm * std::max(occ, 1)) / K));
-    EmState st;
-    if (em_state_init(ctx, st, K, K, gx, std::vector<int>(K, 1))) return 1;
     LAUNCH("fill", fill_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, FT, M * K, 0.25f);
-    int n_active = K;
-    for (int it = 1; it <= iter && n_active > 0; ++it) {
-        LAUNCH("em_pop", em_pop_step_kernel, dim3(gx, K), R * kEmT, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT,
-               st.active.as<int>(), row16, st.partials.as<double>());
-        {   // 8 B per (site, individual of an active population) + f read/write
-            double inds = 0, act = 0;
-            for (int k = 0; k < K; ++k) if (st.h_active[k]) { inds += ctx->pops[k].n; act += 1; }
-            add_work(ctx, "em_pop", (double)M * inds * 8.0 + (double)M * act * 8.0, (double)M * inds);
+    iters_out.assign(K, 0);
+    if (!multi) {
+        EmState st;
+        if (em_state_init(ctx, st, K, K, gx, std::vector<int>(K, 1))) return 1;
+        int n_active = K;
+        for (int it = 1; it <= iter && n_active > 0; ++it) {
+            LAUNCH("em_pop", em_pop_step_kernel, dim3(gx, K), R * kEmT, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT,
+                   st.active.as<int>(), row16, st.partials.as<double>());
+            {   // 8 B per (site, individual of an active population) + f read/write
+                double inds = 0, act = 0;
+                for (int k = 0; k < K; ++k) if (st.h_active[k]) { inds += ctx->pops[k].n; act += 1; }
+                add_work(ctx, "em_pop", (double)M * inds * 8.0 + (double)M * act * 8.0, (double)M * inds);
+            }
+            if (em_after_step(ctx, st, tole, it, nullptr, (double)ctx->Mtot(), &n_active)) return 1;
         }
-        if (em_after_step(ctx, st, tole, it, nullptr, (double)ctx->Mtot(), &n_active)) return 1;
+        CU(cudaMemcpy(iters_out.data(), st.iters.p, K * sizeof(int), cudaMemcpyDeviceToHost));
+        CU(cudaGetLastError());
+        return 0;
     }
-    iters_out.resize(K);
-    CU(cudaMemcpy(iters_out.data(), st.iters.p, K * sizeof(int), cudaMemcpyDeviceToHost));
+
+    const int np = K * kEmChunk;
+    DevBuf FT1, partials, ssq, dcur, diters;
+    if (buf_alloc(ctx, FT1, (size_t)std::max<long>(M, 1) * K * sizeof(float)) || buf_alloc(ctx, partials, (size_t)gx * np * sizeof(double)) ||
+        buf_alloc(ctx, ssq, (size_t)np * sizeof(double)) || buf_alloc(ctx, dcur, K * sizeof(int)) || buf_alloc(ctx, diters, K * sizeof(int))) return 1;
+    std::vector<int> cur(K, 0), done(K, 0), replay(K, 0), run(K, 0);
+    std::vector<char> fin(K, 0);
+    std::vector<double> h(np);
+    for (;;) {
+        bool any = false;
+        for (int k = 0; k < K; ++k) {
+            run[k] = 0;
+            if (fin[k]) continue;
+            run[k] = replay[k] > 0 ? replay[k] : std::min(kEmChunk, iter - done[k]);
+            if (run[k] <= 0) { fin[k] = 1; run[k] = 0; continue; }           // iteration limit reached without convergence
+            any = true;
+        }
+        if (!any) break;
+        CU(cudaMemcpyAsync(dcur.p, cur.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(diters.p, run.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH("em_pop", em_pop_multi_kernel, dim3(gx, K), R * kEmT, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT,
+               FT1.as<float>(), dcur.as<int>(), diters.as<int>(), row16, partials.as<double>());
+        {   // 8 B per (site, individual of a running population) + f read/write, once per pass; one unit per (site, individual, iteration)
+            double inds = 0, act = 0, units = 0;
+            for (int k = 0; k < K; ++k) if (run[k] > 0) { inds += ctx->pops[k].n; act += 1; units += (double)ctx->pops[k].n * run[k]; }
+            add_work(ctx, "em_pop", (double)M * inds * 8.0 + (double)M * act * 8.0, (double)M * units);
+        }
+        LAUNCH("em_ssq_reduce", em_ssq_reduce_kernel, grid_for(np, 128, 64), 128, 0, ctx->stream, partials.as<double>(), gx, np, np, ssq.as<double>());
+        CU(cudaMemcpyAsync(h.data(), ssq.p, np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->fn) ctx->fn(h.data(), np, WGS_F64, ctx->user);
+        for (int k = 0; k < K; ++k) {
+            if (run[k] <= 0) continue;
+            if (replay[k] > 0) {                                            // exactly t* iterations from the chunk's start state
+                cur[k] ^= 1; done[k] += replay[k]; replay[k] = 0; fin[k] = 1; iters_out[k] = done[k];
+                continue;
+            }
+            int tstar = 0;
+            for (int u = 0; u < run[k] && !tstar; ++u)
+                if (em_converged(h[(size_t)k * kEmChunk + u], (double)ctx->Mtot(), tole)) tstar = u + 1;
+            if (tstar == 0 || tstar == run[k]) {                            // the state written by this pass is the one to keep
+                cur[k] ^= 1; done[k] += run[k];
+                if (tstar) { fin[k] = 1; iters_out[k] = done[k]; }
+            } else {
+                replay[k] = tstar;                                          // stop inside the chunk: replay from FT[cur]
+            }
+        }
+    }
+    for (int k = 0; k < K; ++k)
+        if (cur[k]) CU(cudaMemcpyAsync(FT + (size_t)k * M, FT1.as<float>() + (size_t)k * M, (size_t)M * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     return 0;
 }

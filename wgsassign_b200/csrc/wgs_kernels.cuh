@@ -979,6 +979,123 @@ em_pop_step_kernel(const float2* __restrict__ G, int ldg, long M,
 }
 
 // ---------------------------------------------------------------------------------------
+// em_pop_multi: up to kEmChunk EM iterations of every still-running population per read of G.
+// A site's trajectory depends on nothing but its own row; only the STOP decision is global (the
+// RMSE over all sites, emMAF.py:21-25).  So a tile that is already in shared memory is iterated
+// T times in place, each thread keeping one squared-change accumulator per iteration; the host
+// then finds the first iteration whose RMSE is below the tolerance.  If that iteration t* lies
+// inside the chunk, the population is replayed for exactly t* iterations from the chunk's start
+// state (FT[cur]) - still 3 reads of G for a 14-iteration EM instead of 14.  The arithmetic per
+// site and iteration, and the order of every sum, are those of em_pop_step: same bits.
+// cur[k] selects the buffer holding population k's current state; the result goes to the other.
+// ---------------------------------------------------------------------------------------
+constexpr int kEmChunk = 8;
+__global__ void __launch_bounds__(512)
+em_pop_multi_kernel(const float2* __restrict__ G, int ldg, long M,
+                    const PopDesc* __restrict__ pops, int K,
+                    float* __restrict__ FT0, float* __restrict__ FT1,   // [K][M] each
+                    const int* __restrict__ cur,          // [K] buffer that holds the start state
+                    const int* __restrict__ iters_k,      // [K] iterations to run now (0 = skip)
+                    int row16,                            // shared-memory row stride in 16-byte units (== kEmT mod 8: conflict-free)
+                    double* __restrict__ partials)        // [gridDim.x][K][kEmChunk]
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float red[512];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    const int k = blockIdx.y;
+    const int R = blockDim.x / kEmT;                      // rows (sites) per tile
+    const int t = threadIdx.x;
+    const int r = t / kEmT, h = t % kEmT;                 // row of this thread, its slice of the row
+    const int T = iters_k[k];
+    double* pout = partials + ((long)blockIdx.x * K + k) * kEmChunk;
+    if (T <= 0) {                                         // finished population: nothing to do
+        if (t < kEmChunk) pout[t] = 0.0;
+        return;
+    }
+    const PopDesc pd = pops[k];
+    const int cpr = (pd.n + 1) >> 1;                      // 16-byte chunks (pairs of individuals) per row that hold data
+    float4* ring = reinterpret_cast<float4*>(smem_raw);   // [2][R][row16]
+    const size_t stage = (size_t)R * row16;
+    const long ntiles = (M + R - 1) / R;
+    const float* Fsrc = (cur[k] ? FT1 : FT0) + (size_t)k * M;
+    float* Fdst = (cur[k] ? FT0 : FT1) + (size_t)k * M;
+
+    if (t == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    auto issue = [&](long tile, int buf) {
+        if (tile < ntiles && t < 32) {
+            const long s0 = tile * R;
+            const int rows = (int)min((long)R, M - s0);
+            if (t == 0) mbar_expect_tx(&mbar[buf], (unsigned)(rows * cpr * 16));
+            __syncwarp();
+            float4* dst = ring + buf * stage;
+            for (int rr = t; rr < rows; rr += 32)
+                bulk_g2s(dst + (size_t)rr * row16, G + (s0 + rr) * (long)ldg + pd.col0, (unsigned)(cpr * 16), &mbar[buf]);
+        }
+    };
+
+    float ssq[kEmChunk];
+#pragma unroll
+    for (int u = 0; u < kEmChunk; ++u) ssq[u] = 0.f;
+    const float fn = (float)pd.n;
+    const int full = pd.n >> 1;                           // complete pairs
+    issue(blockIdx.x, 0);
+    issue(blockIdx.x + (long)gridDim.x, 1);
+    int it = 0;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const long s = tile * R + r;
+        float f = 0.25f;
+        if (s < M) f = Fsrc[s];
+        mbar_wait(&mbar[buf], (unsigned)((it >> 1) & 1)); // this tile has landed
+        const float4* row = ring + buf * stage + (size_t)r * row16;
+#pragma unroll
+        for (int u = 0; u < kEmChunk; ++u) {
+            if (u < T) {                                  // block-uniform
+                const EmCoef c = em_coef(f);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                if (s < M) {
+                    int q = h;
+                    for (; q + kEmT < full; q += 2 * kEmT) {
+                        float4 v = row[q], w = row[q + kEmT];
+                        a0 += em_term(v.x, v.y, 1.0f - v.x - v.y, c);
+                        a1 += em_term(v.z, v.w, 1.0f - v.z - v.w, c);
+                        a2 += em_term(w.x, w.y, 1.0f - w.x - w.y, c);
+                        a3 += em_term(w.z, w.w, 1.0f - w.z - w.w, c);
+                    }
+                    if (q < full) {
+                        float4 v = row[q];
+                        a0 += em_term(v.x, v.y, 1.0f - v.x - v.y, c);
+                        a1 += em_term(v.z, v.w, 1.0f - v.z - v.w, c);
+                    }
+                    if ((pd.n & 1) && h == (full % kEmT)) { float4 v = row[full]; a2 += em_term(v.x, v.y, 1.0f - v.x - v.y, c); }
+                }
+                float sum = (a0 + a1) + (a2 + a3);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);    // the kEmT slices of a row sit in adjacent lanes
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                const float fnew = __fdiv_rn(sum, fn);          // identical in the kEmT lanes of a row
+                if (s < M && h == 0) { const float d = fnew - f; ssq[u] += d * d; }
+                f = fnew;
+            }
+        }
+        if (s < M && h == 0) Fdst[s] = f;
+        __syncthreads();                                  // everyone is done with this buffer before it is refilled
+        issue(tile + 2 * (long)gridDim.x, buf);
+    }
+#pragma unroll
+    for (int u = 0; u < kEmChunk; ++u) {
+        __syncthreads();
+        red[t] = ssq[u];
+        __syncthreads();
+        if (t == 0) {
+            double v = 0.0;
+            for (int q = 0; q < (int)blockDim.x; q += kEmT) v += (double)red[q];
+            pout[u] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Leave-one-out EM (glassy.py:65-78: emMAF on the population minus individual i, for every i).
 // ONE launch = ONE EM iteration of every still-active leave-one-out problem of ONE population.
 // Problem i at site s follows its own trajectory f_i, so each (site, i) evaluates all n
