@@ -355,6 +355,12 @@ def main():
             pl = ctx.pop_like_partial(af)
             fo = ctx.fisher_partial(af)
         extra = {k: family(ctx, k, hbm_peak, M_local) for k in ("pop_like", "fisher")}
+        aux = ctx.timing_get("pop_like_aux")                    # coefficient rows + population-only log term of the ratio form
+        if extra.get("pop_like") and aux["launches"]:
+            pl_ = extra["pop_like"]
+            pl_["aux_ms_per_call"] = aux["ms"] / pl_["launches"]
+            pl_["ms_per_call_with_aux"] = (pl_["ms_total"] + aux["ms"]) / pl_["launches"]
+            pl_["hbm_frac_with_aux"] = pl_["algorithmic_gb"] / ((pl_["ms_total"] + aux["ms"]) * 1e-3) / hbm_peak
         for mode, nm in ((0, "stream_flat"), (1, "stream_slab")):       # what a pure read of the same matrix achieves
             ms, nb = ctx.debug_stream(mode)
             extra[nm] = {"ms": ms, "gb": nb / 1e9, "achieved_gbs": nb / 1e9 / (ms * 1e-3)}
@@ -370,28 +376,28 @@ def main():
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
     # Issue-rate ceilings MEASURED on this pool's B200 (scripts/microbench/, profiles/issue_rates_r1.txt,
     # profiles/mufu_rate_r1.txt), scaled by the clock this run sustained:
-    #   packed FP32 (FFMA2/FMUL2/FADD2): 1.687e13 lane-instructions/s at 1,965 MHz = 58.0 per clock per SM;
+    #   packed FP32 (FFMA2): 1.687e13 lane-instructions/s at 1,965 MHz = 58.0 per clock per SM;
     #   MUFU.RCP: 15.48 per clock per SM.
-    # The quad kernel spends 10 packed instructions and 2 reciprocals per 4 posterior evaluations, so the
-    # FP32 pipe binds (2.5 packed lane-instructions per evaluation), MUFU sits at 0.5 per evaluation.
-    fp32_peak = 148 * 58.0 * sm_mhz * 1e6 / 2.5
+    # The packed kernel (loo_em_step5) spends 8 FFMA2 and 2 reciprocals per 4 posterior evaluations, so the
+    # FP32 pipe binds (2.0 packed lane-instructions per evaluation), MUFU sits at 0.5 per evaluation.
+    fp32_peak = 148 * 58.0 * sm_mhz * 1e6 / 2.0
     mufu_peak = 148 * 15.48 * sm_mhz * 1e6 / 0.5
     le = fam["loo_em"]
-    roofline = {"kernel": "loo_em_step4_kernel", "bound": "hbm", "achieved": le["achieved_gbs"], "peak": hbm_peak,
+    roofline = {"kernel": "loo_em_step5_kernel", "bound": "hbm", "achieved": le["achieved_gbs"], "peak": hbm_peak,
                 "unit": "GB/s", "frac": le["hbm_frac"], "traffic": le.get("ncu_dram_bytes_per_launch"),
                 "algorithmic_bytes_per_launch": le.get("algorithmic_bytes_per_launch"), "peak_source": peak_src,
                 "ms_per_launch": le["ms_per_launch"], "launches": le["launches"],
                 "share_of_step": le["ms_total"] / (dt * 1e3),
-                "note": "by design NOT HBM-bound: each GL tile is read once per iteration and re-used for n^2 posterior "
+                "note": "by design NOT HBM-bound: each packed row group is read once per iteration and re-used for n^2 posterior "
                         "evaluations from shared memory; the binding limit is the packed-FP32 issue rate (see `issue`); "
                         "the HBM-bound kernels of the path are in `kernels` (em_pop, pop_like, fisher)",
                 "issue": {"bound": "fp32 pipe (FFMA2)", "achieved": le["units_per_s"], "peak": fp32_peak,
                           "peak_source": "measured 58.0 packed FP32 lane-instructions/clk/SM (profiles/issue_rates_r1.txt), "
-                                         "2.5 per posterior evaluation",
+                                         "2.0 per posterior evaluation",
                           "unit": "posterior evals/s", "frac": le["units_per_s"] / fp32_peak, "sm_mhz": sm_mhz,
                           "mufu_rcp_frac": le["units_per_s"] / mufu_peak,
-                          "inner_loop_ceiling": "5.2e12 evals/s for the bare inner loop from shared memory "
-                                                "(scripts/microbench/loo_quad_rate.cu)"}}
+                          "inner_loop_ceiling": "6.3e12 evals/s for the bare inner loop from shared memory "
+                                                "(scripts/microbench/loo_quad_rate.cu, profiles/loo_quad_rate_r1.txt)"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",

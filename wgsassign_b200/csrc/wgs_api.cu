@@ -443,7 +443,7 @@ int launch_pop_like2_i(wgs_ctx* ctx, const float2* G, long M, const float* dA, i
     const long Mpad = (M + kPL2TS - 1) / kPL2TS * kPL2TS;
     DevBuf xy;
     if (buf_alloc(ctx, xy, (size_t)std::max<long>(Mpad, kPL2TS) * KP * sizeof(ulonglong2))) return 1;
-    LAUNCH("pop_like_xy", xy_precompute_kernel, grid_for(M * KP, 256, ctx->num_sm * 8), 256, 0, ctx->stream, dA, M, K, k0, KP, xy.as<ulonglong2>());
+    LAUNCH("pop_like_aux", xy_precompute_kernel, grid_for(M * KP, 256, ctx->num_sm * 8), 256, 0, ctx->stream, dA, M, K, k0, KP, xy.as<ulonglong2>());
     const size_t smem = (size_t)wx * 2 * kPL2TS * KP * sizeof(ulonglong2);
     auto kern = pop_like2_kernel<KT, I, R>;
     if (smem > 40 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -478,12 +478,11 @@ int add_af_logsum(wgs_ctx* ctx, const float* dA, long M, int K, double* sums, lo
     // blocks of a whole multiple of K threads: thread t only ever visits population t % K
     const int block = K <= 256 ? K * (256 / K) : K;
     const int grid = ctx->num_sm * 4;
-    const long T = (long)grid * block;
     DevBuf per, C;
-    if (buf_alloc(ctx, per, (size_t)T * sizeof(double)) || buf_alloc(ctx, C, (size_t)K * sizeof(double))) return 1;
-    LAUNCH("af_logsum", af_logsum_kernel, grid, block, 0, ctx->stream, dA, M * K, per.as<double>());
-    LAUNCH("af_logsum", af_logsum_reduce_kernel, (K + 127) / 128, 128, 0, ctx->stream, per.as<double>(), T, K, C.as<double>());
-    LAUNCH("af_logsum", add_pop_const_kernel, grid_for(np, 256, ctx->num_sm * 4), 256, 0, ctx->stream, sums, np, K, C.as<double>());
+    if (buf_alloc(ctx, per, (size_t)grid * K * sizeof(double)) || buf_alloc(ctx, C, (size_t)K * sizeof(double))) return 1;
+    LAUNCH("pop_like_aux", af_logsum_kernel, grid, block, block * sizeof(double), ctx->stream, dA, M * K, K, per.as<double>());
+    LAUNCH("pop_like_aux", af_logsum_reduce_kernel, (K + 127) / 128, 128, 0, ctx->stream, per.as<double>(), grid, K, C.as<double>());
+    LAUNCH("pop_like_aux", add_pop_const_kernel, grid_for(np, 256, ctx->num_sm * 4), 256, 0, ctx->stream, sums, np, K, C.as<double>());
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

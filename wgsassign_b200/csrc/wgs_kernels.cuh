@@ -707,11 +707,13 @@ pop_like2_kernel(const float2* __restrict__ G, int ldg, long M,
     }
 }
 
-// C[t] = sum over the elements e = t, t+T, ... of log(2 a_e (1 - a_e)), T = total threads, a multiple of K:
-// every element a thread visits belongs to population t % K.  Reduced per population in a fixed
-// order by af_logsum_reduce_kernel.  (The population-only term of the ratio form above.)
-__global__ void af_logsum_kernel(const float* __restrict__ A, long n, double* __restrict__ per_thread)
+// per_block[b][k] = sum over the elements block b visits of log(2 a_e (1 - a_e)) for population k.
+// T = total threads, a multiple of K (blockDim is): every element a thread visits (e = t, t+T, ...) belongs to
+// population t % K.  Block and grid sums are taken in a fixed order (af_logsum_reduce_kernel): deterministic.
+// (The population-only term of the ratio form above.)
+__global__ void af_logsum_kernel(const float* __restrict__ A, long n, int K, double* __restrict__ per_block)
 {
+    extern __shared__ double af_red[];                   // [blockDim.x]
     const long T = (long)gridDim.x * blockDim.x, t = blockIdx.x * (long)blockDim.x + threadIdx.x;
     LikeAcc<1> acc;
     acc.init();
@@ -722,14 +724,20 @@ __global__ void af_logsum_kernel(const float* __restrict__ A, long n, double* __
         if (++cnt == 2) { acc.renorm(); cnt = 0; }        // two factors >= 2^-29 each stay far above underflow
     }
     acc.renorm();
-    per_thread[t] = acc.value(0);
+    af_red[threadIdx.x] = acc.value(0);
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double v = 0.0;
+        for (int j = threadIdx.x; j < (int)blockDim.x; j += K) v += af_red[j];
+        per_block[(long)blockIdx.x * K + threadIdx.x] = v;
+    }
 }
-__global__ void af_logsum_reduce_kernel(const double* __restrict__ per_thread, long T, int K, double* __restrict__ C)
+__global__ void af_logsum_reduce_kernel(const double* __restrict__ per_block, int nblocks, int K, double* __restrict__ C)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     double v = 0.0;
-    for (long t = k; t < T; t += K) v += per_thread[t];
+    for (int b = 0; b < nblocks; ++b) v += per_block[(long)b * K + k];
     C[k] = v;
 }
 // sums[col][k] += C[k]
