@@ -692,14 +692,15 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
     return 0;
 }
 
-struct LooLaunch { int block, rows_per_pass, passes, grid; bool big; size_t smem; bool packed; int nc; };
+struct LooLaunch { int block, rows_per_pass, passes, grid; bool big; size_t smem; bool packed; int nc; int stages; };
 
 // Launch geometry of the leave-one-out EM step kernels (four problems per thread).  packed = the
 // pre-packed pair-polynomial kernel (loo_em_step5), else the in-kernel packing quad kernel (loo_em_step4).
-// Blocks of <= 256 threads are compiled for 3 resident blocks per SM, larger ones (populations of > 1024) for 1.
+// The packed kernel runs 2 blocks of 256 threads per SM at 112 registers (no spills): 12 % faster than 3 blocks at
+// the 80 registers that fit then (spills around the loop); populations of > 1024 use one block of 512.
 int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
 {
-    LooLaunch best{0, 0, 1, 0, false, 0, packed, 0};
+    LooLaunch best{0, 0, 1, 0, false, 0, packed, 0, 3};
     const int nq = (n + 3) / 4;                                   // threads per site row (four problems each)
     best.nc = (nq + 1) / 2;
     double best_u = -1;
@@ -718,13 +719,23 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
     best.big = best.block > 256;
     // per tile row - quad kernel: two packed buffers (odd 16-byte stride) + the raw TMA landing row;
     //              - packed kernel: double-buffered packed cells (odd 16-byte stride) + double-buffered raw row
-    const size_t row_bytes = packed ? kLoo5Stages * (size_t)loo5_row_units(n) * 16
-                                    : 2 * (size_t)((3 * nq) | 1) * 16 + (size_t)nq * 32;
-    int passes = packed ? 1 : kLoo4MaxPasses;                   // the packed kernel's ring holds single row groups
-    while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 68 * 1024) --passes;
-    if (const char* env_p = getenv("WGS_LOO_PASSES")) passes = std::max(1, std::min(passes, atoi(env_p)));
-    best.passes = passes;
-    best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float4);
+    if (packed) {
+        // ring of row groups: as many stages as fit in ~100 KB (two resident blocks per SM), at least 3
+        const size_t group_bytes = (size_t)best.rows_per_pass * loo5_row_units(n) * 16;
+        int stages = (int)std::min<size_t>(kLoo5MaxStages, (100 * 1024) / std::max<size_t>(group_bytes, 1));
+        if (const char* env_s = getenv("WGS_LOO_STAGES")) stages = atoi(env_s);
+        best.stages = std::max(3, std::min(stages, kLoo5MaxStages));
+        best.passes = 1;
+        best.smem = best.stages * group_bytes + (size_t)best.block * sizeof(float4);
+    } else {
+        // per tile row: two packed buffers (odd 16-byte stride) + the raw TMA landing row
+        const size_t row_bytes = 2 * (size_t)((3 * nq) | 1) * 16 + (size_t)nq * 32;
+        int passes = kLoo4MaxPasses;
+        while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 68 * 1024) --passes;
+        if (const char* env_p = getenv("WGS_LOO_PASSES")) passes = std::max(1, std::min(passes, atoi(env_p)));
+        best.passes = passes;
+        best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float4);
+    }
     if (best.smem > 200 * 1024) return fail(ctx, "population of %d individuals exceeds the LOO-EM shared-memory tile", n);
     int occ = 1;
 #define LOO_PREP(KERN)                                                                                               \
@@ -733,7 +744,7 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
         CU(cudaFuncSetAttribute(KERN, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, best.block, best.smem));                        \
     } while (0)
-    if (packed) { if (best.big) LOO_PREP((loo_em_step5_kernel<512, 1>)); else LOO_PREP((loo_em_step5_kernel<256, 3>)); }
+    if (packed) { if (best.big) LOO_PREP((loo_em_step5_kernel<512, 1>)); else if (getenv("WGS_LOO_OCC3")) LOO_PREP((loo_em_step5_kernel<256, 3>)); else LOO_PREP((loo_em_step5_kernel<256, 2>)); }
     else        { if (best.big) LOO_PREP((loo_em_step4_kernel<512, 1>)); else LOO_PREP((loo_em_step4_kernel<256, 3>)); }
 #undef LOO_PREP
     best.grid = ctx->num_sm * std::max(occ, 1);
@@ -806,10 +817,13 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
             if (lc.packed) {
                 if (lc.big)
                     LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
-                           pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, loo_dbg);
+                           pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
+                else if (!getenv("WGS_LOO_OCC3"))
+                    LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
+                           pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
                 else
                     LAUNCH("loo_em", (loo_em_step5_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
-                           pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, loo_dbg);
+                           pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
             } else {
                 if (lc.big)
                     LAUNCH("loo_em", (loo_em_step4_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,

@@ -1449,7 +1449,7 @@ __device__ __forceinline__ void loo5_quad(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3
 // of a group are contiguous in the packed array) as soon as all warps have released it, kLoo5Stages-1
 // groups ahead of use.  (One copy per row from warp 0 made that warp 50 % slower than the others, and
 // every other warp then waited for it at "full": 23 % of all stall samples.)
-constexpr int kLoo5Stages = 3;
+constexpr int kLoo5MaxStages = 6;
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
@@ -1459,16 +1459,17 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
                     const unsigned char* __restrict__ mask,      // [M][ldg] or null
                     double* __restrict__ partials,               // [gridDim.x][ldg]
                     long ntiles,                                 // groups of rows_per_pass rows
+                    int nstages,                                 // ring depth, 2..kLoo5MaxStages
                     int dbg)                                     // experiments: 1 = no restaging (stale tiles), 2 = staging only
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long full[kLoo5Stages], empty[kLoo5Stages];
+    __shared__ __align__(8) unsigned long long full[kLoo5MaxStages], empty[kLoo5MaxStages];
     const int nq = (n + 3) >> 2;                                // quads of individuals = threads per site row
     const int nc = (nq + 1) >> 1;                               // cells (two quads) per row
     const int ru = loo5_row_units(n);                           // row length in 16-byte units (odd)
     const int TS = rows_per_pass;
     ulonglong2* pk0 = reinterpret_cast<ulonglong2*>(smem_raw);                            // [S][TS][ru]  packed cells + raw pairs
-    float4* red = reinterpret_cast<float4*>(pk0 + kLoo5Stages * (size_t)TS * ru);         // [blockDim.x]
+    float4* red = reinterpret_cast<float4*>(pk0 + nstages * (size_t)TS * ru);         // [blockDim.x]
 
     const int t = threadIdx.x, lane = t & 31;
     const int ti = t % nq, r = t / nq;                          // this thread's quad (problems 4ti..4ti+3) and row
@@ -1486,8 +1487,7 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
     float ssq[4] = {0.f, 0.f, 0.f, 0.f};
 
     if (t == 0) {
-#pragma unroll
-        for (int s = 0; s < kLoo5Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], blockDim.x >> 5); }
+        for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], blockDim.x >> 5); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -1502,8 +1502,7 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
         }
     };
     if (t < 32) {
-#pragma unroll
-        for (int s = 0; s < kLoo5Stages; ++s) issue(blockIdx.x + (long)s * gridDim.x, s);
+        for (int s = 0; s < nstages; ++s) issue(blockIdx.x + (long)s * gridDim.x, s);
     }
 
     // this thread's f quad of the next group is fetched while the current one computes
@@ -1527,7 +1526,7 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
         const unsigned okp = ok_next;
         const float4 fq = f_next;
         fetch(tl + gridDim.x);
-        const bool staged = dbg != 1 || tl < blockIdx.x + (long)kLoo5Stages * gridDim.x;
+        const bool staged = dbg != 1 || tl < blockIdx.x + (long)nstages * gridDim.x;
         if (staged) mbar_wait(&full[slot], phase);              // this group has landed
         if (okp && dbg != 2) {
             const float fin[4] = {fq.x, fq.y, fq.z, fq.w};
@@ -1567,13 +1566,13 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);               // this warp is done with the slot
         if (t < 32) {                                           // warp 0 refills it once every warp has released it
-            const long nxt = tl + (long)kLoo5Stages * gridDim.x;
+            const long nxt = tl + (long)nstages * gridDim.x;
             if (nxt < ntiles && dbg != 1) {
                 mbar_wait(&empty[slot], phase);
                 issue(nxt, slot);
             }
         }
-        if (++slot == kLoo5Stages) { slot = 0; phase ^= 1u; }
+        if (++slot == nstages) { slot = 0; phase ^= 1u; }
     }
     __syncthreads();
     red[t] = make_float4(ssq[0], ssq[1], ssq[2], ssq[3]);
