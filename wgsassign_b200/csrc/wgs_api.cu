@@ -605,9 +605,32 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
     size_t smem = 2 * (size_t)R * row16 * 16;
     if (smem > 220 * 1024) return fail(ctx, "population of %d individuals exceeds the EM shared-memory tile", nmax);
     const bool multi = getenv("WGS_EM_STEP") == nullptr;
+    // register-tile variant (em_pop_multi2): TPR threads per row, up to 4 quads of individuals each (n <= 512)
+    int tpr = 4, qpt = 4;
+    {
+        const int nqmax = (nmax + 3) / 4;
+        if (nqmax <= 4) qpt = 1; else if (nqmax <= 8) qpt = 2; else qpt = 4;
+        while (tpr < 32 && tpr * qpt < nqmax) tpr *= 2;
+    }
+    const bool packed = multi && getenv("WGS_EM_MULTI1") == nullptr && tpr * qpt * 4 >= nmax;
+    int raw16 = (nmax + 3) / 4 * 2;                             // pairs per slab row, whole quads ...
+    if (raw16 % 4 == 0) raw16 += 2;                             // ... rows two apart land on different bank groups
+    const int R2 = 256 / tpr;
+    const size_t smem2 = 2 * (size_t)R2 * raw16 * 16;
     // always opt in: static + dynamic shared memory together may cross the 48 KB default limit
     int occ = 1;
-    if (multi) {
+#define EM2_CASE(TPRV, QPTV)                                                                                             \
+    do {                                                                                                                 \
+        CU(cudaFuncSetAttribute(em_pop_multi2_kernel<TPRV, QPTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024))); \
+        CU(cudaFuncSetAttribute(em_pop_multi2_kernel<TPRV, QPTV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, em_pop_multi2_kernel<TPRV, QPTV>, 256, smem));             \
+    } while (0)
+    if (packed) {
+        R = R2; smem = smem2;
+        if (tpr == 4 && qpt == 1) EM2_CASE(4, 1); else if (tpr == 4 && qpt == 2) EM2_CASE(4, 2); else if (tpr == 4) EM2_CASE(4, 4);
+        else if (tpr == 8) EM2_CASE(8, 4); else if (tpr == 16) EM2_CASE(16, 4); else EM2_CASE(32, 4);
+#undef EM2_CASE
+    } else if (multi) {
         CU(cudaFuncSetAttribute(em_pop_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, em_pop_multi_kernel, R * kEmT, smem));
     } else {
@@ -657,8 +680,17 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
         if (!any) break;
         CU(cudaMemcpyAsync(dcur.p, cur.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(diters.p, run.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCH("em_pop", em_pop_multi_kernel, dim3(gx, K), R * kEmT, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT,
-               FT1.as<float>(), dcur.as<int>(), diters.as<int>(), row16, partials.as<double>());
+#define EM2_LAUNCH(TPRV, QPTV)                                                                                          \
+    LAUNCH("em_pop", (em_pop_multi2_kernel<TPRV, QPTV>), dim3(gx, K), 256, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT, \
+           FT1.as<float>(), dcur.as<int>(), diters.as<int>(), raw16, partials.as<double>())
+        if (packed) {
+            if (tpr == 4 && qpt == 1) EM2_LAUNCH(4, 1); else if (tpr == 4 && qpt == 2) EM2_LAUNCH(4, 2); else if (tpr == 4) EM2_LAUNCH(4, 4);
+            else if (tpr == 8) EM2_LAUNCH(8, 4); else if (tpr == 16) EM2_LAUNCH(16, 4); else EM2_LAUNCH(32, 4);
+        }
+#undef EM2_LAUNCH
+        else
+            LAUNCH("em_pop", em_pop_multi_kernel, dim3(gx, K), R * kEmT, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT,
+                   FT1.as<float>(), dcur.as<int>(), diters.as<int>(), row16, partials.as<double>());
         {   // 8 B per (site, individual of a running population) + f read/write, once per pass; one unit per (site, individual, iteration)
             double inds = 0, act = 0, units = 0;
             for (int k = 0; k < K; ++k) if (run[k] > 0) { inds += ctx->pops[k].n; act += 1; units += (double)ctx->pops[k].n * run[k]; }

@@ -1104,6 +1104,139 @@ em_pop_multi_kernel(const float2* __restrict__ G, int ldg, long M,
 }
 
 // ---------------------------------------------------------------------------------------
+// em_pop_multi2: em_pop_multi with the tile in REGISTERS and the arithmetic of the leave-one-out
+// quad kernel.  One thread per (site row, slice) reads its QPT quads of individuals from the landed
+// raw rows ONCE, packs them ({g0_ab,g1_ab,g2_ab,g0_cd,g1_cd,g2_cd} per quad) and iterates up to 8
+// times without touching shared memory again: with one problem per thread a shared-memory tile
+// costs 12 bytes per posterior term and iteration, which bound the first packed version at
+// 0.3 ms per iteration.  Per four terms and iteration: 10 packed FP32 instructions + 2 MUFU.RCP
+// (ratio form, one reciprocal per two terms).  TPR threads share a row (TPR * QPT * 4 >= n).
+// f is kept inside [1e-12, 1-2^-24] (the ratio form divides by f and 1-f; a monomorphic site of
+// certain genotypes would otherwise reach exactly 0) - 7 orders below the parity tolerance and
+// far outside the clipping applied afterwards.
+// ---------------------------------------------------------------------------------------
+template <int TPR, int QPT>
+__global__ void __launch_bounds__(256)
+em_pop_multi2_kernel(const float2* __restrict__ G, int ldg, long M,
+                     const PopDesc* __restrict__ pops, int K,
+                     float* __restrict__ FT0, float* __restrict__ FT1,   // [K][M] each
+                     const int* __restrict__ cur,          // [K] buffer that holds the start state
+                     const int* __restrict__ iters_k,      // [K] iterations to run now (0 = skip)
+                     int raw16,                            // raw row stride, 16-byte units (an odd number of pairs of units)
+                     double* __restrict__ partials)        // [gridDim.x][K][kEmChunk]
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float red[256];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    const int k = blockIdx.y;
+    const int t = threadIdx.x;
+    const int R = blockDim.x / TPR;                       // rows (sites) per tile
+    const int r = t / TPR, h = t % TPR;                   // row of this thread, its slice of the row
+    const int T = iters_k[k];
+    double* pout = partials + ((long)blockIdx.x * K + k) * kEmChunk;
+    if (T <= 0) {                                         // finished population: nothing to do
+        if (t < kEmChunk) pout[t] = 0.0;
+        return;
+    }
+    const PopDesc pd = pops[k];
+    const int nq = (pd.n + 3) >> 2;                       // quads of individuals
+    float4* raw = reinterpret_cast<float4*>(smem_raw);    // [2][R][raw16]
+    const long ntiles = (M + R - 1) / R;
+    const float* Fsrc = (cur[k] ? FT1 : FT0) + (size_t)k * M;
+    float* Fdst = (cur[k] ? FT0 : FT1) + (size_t)k * M;
+
+    if (t == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    auto issue = [&](long tile, int buf) {                // warp 0: one TMA bulk copy per slab row
+        if (tile < ntiles && t < 32) {
+            const long s0 = tile * R;
+            const int rows = (int)min((long)R, M - s0);
+            if (t == 0) mbar_expect_tx(&mbar[buf], (unsigned)(rows * nq * 32));
+            __syncwarp();
+            float4* dst = raw + (size_t)buf * R * raw16;
+            for (int rr = t; rr < rows; rr += 32)
+                bulk_g2s(dst + (size_t)rr * raw16, G + (s0 + rr) * (long)ldg + pd.col0, (unsigned)(nq * 32), &mbar[buf]);
+        }
+    };
+
+    float ssq[kEmChunk];
+#pragma unroll
+    for (int u = 0; u < kEmChunk; ++u) ssq[u] = 0.f;
+    const float fn = (float)pd.n;
+    issue(blockIdx.x, 0);
+    issue(blockIdx.x + (long)gridDim.x, 1);
+    int it = 0;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const long s = tile * R + r;
+        float f = 0.25f;
+        if (s < M) f = Fsrc[s];
+        mbar_wait(&mbar[buf], (unsigned)((it >> 1) & 1)); // the raw rows of this tile have landed
+        // this thread's quads -> packed registers (pads and rows past M are (1,0,0): exactly zero terms)
+        f32x2 g0ab[QPT], g1ab[QPT], g2ab[QPT], g0cd[QPT], g1cd[QPT], g2cd[QPT];
+        {
+            const float4* src = raw + ((size_t)buf * R + r) * raw16;
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+                const int q = h + j * TPR;
+                float4 ga = make_float4(1.f, 0.f, 1.f, 0.f), gc = ga;
+                if (s < M && q < nq) { ga = src[2 * q]; gc = src[2 * q + 1]; }
+                if (4 * q + 1 >= pd.n) { ga.z = 1.f; ga.w = 0.f; }
+                if (4 * q + 2 >= pd.n) { gc.x = 1.f; gc.y = 0.f; }
+                if (4 * q + 3 >= pd.n) { gc.z = 1.f; gc.w = 0.f; }
+                g0ab[j] = pack2(ga.x, ga.z); g1ab[j] = pack2(ga.y, ga.w);
+                g2ab[j] = pack2(1.0f - ga.x - ga.y, 1.0f - ga.z - ga.w);
+                g0cd[j] = pack2(gc.x, gc.z); g1cd[j] = pack2(gc.y, gc.w);
+                g2cd[j] = pack2(1.0f - gc.x - gc.y, 1.0f - gc.z - gc.w);
+            }
+        }
+        __syncthreads();                                  // everyone has its registers: the raw buffer is free
+        issue(tile + 2 * (long)gridDim.x, buf);
+#pragma unroll
+        for (int u = 0; u < kEmChunk; ++u) {
+            if (u < T) {                                  // block-uniform
+                const float om = 1.0f - f;
+                const float ca = om * fast_rcp(f), cb = f * fast_rcp(om);
+                const f32x2 A = pack2(ca, ca), B = pack2(cb, cb);
+                f32x2 acc = 0ull;
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) {
+                    const f32x2 nu = ffma2(g2ab[j], B, g1ab[j]);
+                    const f32x2 nv = ffma2(g2cd[j], B, g1cd[j]);
+                    const f32x2 du = ffma2(g0ab[j], A, fadd2(g1ab[j], nu));
+                    const f32x2 dv = ffma2(g0cd[j], A, fadd2(g1cd[j], nv));
+                    const f32x2 m = fmul2(du, dv);
+                    const f32x2 x = ffma2(nv, du, fmul2(nu, dv));
+                    const float2 mm = unpack2(m);
+                    acc = ffma2(x, pack2(fast_rcp(mm.x), fast_rcp(mm.y)), acc);
+                }
+                const float2 a2 = unpack2(acc);
+                float sum = a2.x + a2.y;
+#pragma unroll
+                for (int o = 1; o < TPR; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);   // the TPR slices of a row sit in adjacent lanes
+                float fnew = __fdiv_rn(sum, fn);                // identical in the TPR lanes of a row
+                if (fnew < 1e-12f) fnew = 1e-12f;               // comparisons are false for NaN: NaN survives
+                if (fnew > 0.99999994f) fnew = 0.99999994f;
+                if (s < M && h == 0) { const float d = fnew - f; ssq[u] += d * d; }
+                f = fnew;
+            }
+        }
+        if (s < M && h == 0) Fdst[s] = f;
+    }
+#pragma unroll
+    for (int u = 0; u < kEmChunk; ++u) {
+        __syncthreads();
+        red[t] = ssq[u];
+        __syncthreads();
+        if (t == 0) {
+            double v = 0.0;
+            for (int q = 0; q < (int)blockDim.x; q += TPR) v += (double)red[q];
+            pout[u] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Leave-one-out EM (glassy.py:65-78: emMAF on the population minus individual i, for every i).
 // ONE launch = ONE EM iteration of every still-active leave-one-out problem of ONE population.
 // Problem i at site s follows its own trajectory f_i, so each (site, i) evaluates all n
