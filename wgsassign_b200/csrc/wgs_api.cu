@@ -487,6 +487,54 @@ int add_af_logsum(wgs_ctx* ctx, const float* dA, long M, int K, double* sums, lo
     return 0;
 }
 
+// ---- leave-one-out likelihoods with the state rows staged in shared memory (loo_like2) -----------
+struct LooLike2Cfg { int W, gx, gy, TS; long spb; size_t smem; };
+bool loo_like2_cfg(wgs_ctx* ctx, long M, int ldf, LooLike2Cfg* c)
+{
+    const int groups = (ctx->ldg + 31) / 32;
+    const int nb = (groups + 15) / 16;                            // blocks per site split: at most 16 warps each
+    c->W = (groups + nb - 1) / nb;
+    c->gx = nb;
+    int TS = (int)std::min<size_t>(kLL2MaxTS, (90 * 1024) / ((size_t)ldf * 20));   // 12 B of planes + 2 x 4 B of raw rows per state value
+    if (TS < 1) return false;
+    c->TS = TS;
+    c->smem = (size_t)TS * ldf * 20;
+    long target = std::max<long>(1, (long)ctx->num_sm * 2 / nb);  // ~2 resident blocks per SM, one wave
+    long spb = (M + target - 1) / target;
+    spb = std::max<long>(TS, (spb + TS - 1) / TS * TS);
+    c->spb = spb;
+    c->gy = (int)std::max<long>(1, (M + spb - 1) / spb);
+    return true;
+}
+template <int KT>
+int launch_loo_like2_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, int ldf, const int* rc, int K, int k0,
+                       const LooLike2Cfg& c, long pm, long pr, int R, double* partials)
+{
+    auto kern = loo_like2_kernel<KT>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LAUNCH("loo_like", kern, dim3(c.gx, c.gy), c.W * 32, c.smem, ctx->stream,
+           G, ctx->ldg, M, Fx, ldf, rc, K, k0, c.TS, c.spb, pm, pr, ctx->site_offset, R, partials);
+    {   // GL pairs once + the LOO state row (one float per individual) + full-data AF columns
+        int kt = std::min(KT, K - k0);
+        add_work(ctx, "loo_like", (double)M * ctx->N * 12.0 + (double)M * kt * 4.0, (double)M * ctx->N * kt);
+    }
+    return 0;
+}
+int launch_loo_like2(wgs_ctx* ctx, int KT, const float2* G, long M, const float* Fx, int ldf, const int* rc, int K, int k0,
+                     const LooLike2Cfg& c, long pm, long pr, int R, double* partials)
+{
+    switch (KT) {
+        case 2: return launch_loo_like2_t<2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        case 4: return launch_loo_like2_t<4>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        case 5: return launch_loo_like2_t<5>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        case 8: return launch_loo_like2_t<8>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        case 10: return launch_loo_like2_t<10>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        case 16: return launch_loo_like2_t<16>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        default: return launch_loo_like2_t<20>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+    }
+}
+
 #define DISPATCH_R(FN, KTV, R, ...)                                      \
     switch (R) {                                                         \
         case 8: rc_ = FN<KTV, 8>(__VA_ARGS__); break;                    \
@@ -1231,9 +1279,12 @@ int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole
         for (int k = 0; k < K; ++k) if (ctx->pops[k].n <= 1) R = 1;
     }
     LikeCfg c = like_cfg(ctx, M, 3);
+    LooLike2Cfg c2{};
+    const bool staged = getenv("WGS_LOOLIKE_V1") == nullptr && loo_like2_cfg(ctx, M, ldf, &c2);
+    const int n_split = staged ? c2.gy : c.gy;
     size_t np = (size_t)ldg * K;
     DevBuf partials, sums;
-    if (buf_alloc(ctx, partials, (size_t)c.gy * np * sizeof(double)) || buf_alloc(ctx, sums, np * sizeof(double))) return 1;
+    if (buf_alloc(ctx, partials, (size_t)n_split * np * sizeof(double)) || buf_alloc(ctx, sums, np * sizeof(double))) return 1;
     const float2* Gsrc = use_ds ? ctx->G[1] : ctx->G[0];
     std::vector<double> tmp((size_t)N * K);
     for (int pass = 0; pass < (parts > 1 ? parts + 1 : 1); ++pass) {
@@ -1241,12 +1292,13 @@ int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole
         for (int k0 = 0; k0 < K;) {
             int KT = pick_KT(K - k0);
             int rc_ = 0;
-            DISPATCH_KT(launch_loo_like_t, KT, R, ctx, Gsrc, M, F.as<float>(), ldf, drc.as<int>(), K, k0, c, pm, pr, partials.as<double>());
+            if (staged) rc_ = launch_loo_like2(ctx, KT, Gsrc, M, F.as<float>(), ldf, drc.as<int>(), K, k0, c2, pm, pr, R, partials.as<double>());
+            else DISPATCH_KT(launch_loo_like_t, KT, R, ctx, Gsrc, M, F.as<float>(), ldf, drc.as<int>(), K, k0, c, pm, pr, partials.as<double>());
             if (rc_) return rc_;
             k0 += KT;
         }
         LAUNCH("reduce", reduce_partials_kernel, grid_for(np, 256, ctx->num_sm * 4), 256, 0, ctx->stream, partials.as<double>(),
-               c.gy, (long)np, sums.as<double>());
+               n_split, (long)np, sums.as<double>());
         if (pass == 0) { if (cols_to_host(ctx, sums.as<double>(), K, ll)) return 1; }
         else {
             if (!ll_parts) return fail(ctx, "ll_parts is NULL but parts > 1");

@@ -850,6 +850,113 @@ loo_like_kernel(const float2* __restrict__ G, int ldg, long M,
 }
 
 // ---------------------------------------------------------------------------------------
+// loo_like2: loo_like with the leave-one-out state staged in shared memory.  The gather of
+// Fx[s][rc[c][j]] through L1 kept loo_like latency-bound (11 dependent global loads per site and
+// thread).  Here a block walks a range of sites with ALL its warps on the same site tile: the TS
+// state rows of the tile arrive by one TMA bulk copy (rows of consecutive sites are contiguous),
+// are turned once into HWE planes H01 = ((1-a)^2, 2a(1-a)) and H2 = a^2, and every (individual,
+// population) evaluation is then LDS.64 + LDS.32 + 3 multiply-adds + the running-product multiply.
+// Warps own 32 columns each and all sites of the block's split: no cross-warp reduction.
+// ---------------------------------------------------------------------------------------
+constexpr int kLL2MaxTS = 8;
+template <int KT>
+__global__ void __launch_bounds__(512)
+loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
+                 const float* __restrict__ Fx, int ldf,
+                 const int* __restrict__ rc, int K, int k0,
+                 int TS, long sites_per_block,                  // TS <= kLL2MaxTS; sites_per_block a multiple of TS
+                 long part_mod, long part_rem, long site_offset, int R,
+                 double* __restrict__ partials)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    float2* H01 = reinterpret_cast<float2*>(smem_raw);                      // [TS][ldf]
+    float* H2 = reinterpret_cast<float*>(H01 + (size_t)TS * ldf);           // [TS][ldf]
+    float* raw = H2 + (size_t)TS * ldf;                                     // [2][TS][ldf]
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int W = blockDim.x >> 5;
+    const int col = (blockIdx.x * W + warp) * 32 + lane;
+    const bool col_ok = col < ldg;
+    const bool warp_live = col - lane < ldg;
+    const long s_begin = (long)blockIdx.y * sites_per_block;
+    const long s_end = min(M, s_begin + sites_per_block);
+    const int ntiles = (int)((s_end - s_begin + TS - 1) / TS);
+
+    int rcol[KT];
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk)
+        rcol[kk] = (col_ok && k0 + kk < K) ? rc[(long)col * K + k0 + kk] : (ldf - 1);
+
+    if (t == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    auto issue = [&](int j, int buf) {                    // thread 0: one bulk copy for the tile's state rows
+        if (j < ntiles && t == 0) {
+            const long s0 = s_begin + (long)j * TS;
+            const unsigned bytes = (unsigned)min((long)TS, s_end - s0) * (unsigned)ldf * 4u;
+            mbar_expect_tx(&mbar[buf], bytes);
+            bulk_g2s(raw + (size_t)buf * TS * ldf, Fx + s0 * (long)ldf, bytes, &mbar[buf]);
+        }
+    };
+    issue(0, 0);
+    issue(1, 1);
+
+    LikeAcc<KT> acc;
+    acc.init();
+    int cnt = 0;
+    const float2* Gc = G + (col_ok ? col : ldg - 1);
+    for (int j = 0; j < ntiles; ++j) {
+        const int buf = j & 1;
+        const long s0 = s_begin + (long)j * TS;
+        const int rows = (int)min((long)TS, s_end - s0);
+        float2 g[kLL2MaxTS];                              // this thread's GL pairs of the tile, in flight during the transform
+#pragma unroll
+        for (int u = 0; u < kLL2MaxTS; ++u) {
+            g[u] = make_float2(1.0f, 0.0f);
+            if (u < rows && warp_live) g[u] = ld_stream2(Gc + (s0 + u) * (long)ldg);
+        }
+        mbar_wait(&mbar[buf], (unsigned)((j >> 1) & 1));
+        const float* src = raw + (size_t)buf * TS * ldf;
+        for (int e = t; e < rows * ldf; e += blockDim.x) {
+            const float a = src[e];
+            const float om = 1.0f - a;
+            H01[e] = make_float2(om * om, 2.0f * a * om);
+            H2[e] = a * a;
+        }
+        __syncthreads();                                  // planes complete, raw buffer free
+        issue(j + 2, buf);
+        // partition of the tile's first site (site indices fit 32 bits: the reference's sizes are C ints)
+        const unsigned tile_rem = part_mod > 1 ? (unsigned)(site_offset + s0) % (unsigned)part_mod : 0u;
+        if (warp_live) {
+#pragma unroll
+            for (int u = 0; u < kLL2MaxTS; ++u) {
+                if (u < rows) {                           // block-uniform
+                    const bool use = part_mod <= 1 || (tile_rem + (unsigned)u) % (unsigned)part_mod == (unsigned)part_rem;
+                    if (use) {
+                        const float g0 = g[u].x, g1 = g[u].y, g2 = third_gl(g0, g1);
+                        const float2* h01 = H01 + (size_t)u * ldf;
+                        const float* h2 = H2 + (size_t)u * ldf;
+#pragma unroll
+                        for (int kk = 0; kk < KT; ++kk) {
+                            const float2 h = h01[rcol[kk]];
+                            const float like = fmaf(g0, h.x, fmaf(g1, h.y, g2 * h2[rcol[kk]]));
+                            acc.prod[kk] *= like;
+                        }
+                        if (++cnt == R) { acc.renorm(); cnt = 0; }
+                    }
+                }
+            }
+        }
+        __syncthreads();                                  // everyone is done with the planes
+    }
+    acc.renorm();
+    if (col_ok) {
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk)
+            if (k0 + kk < K) partials[((long)blockIdx.y * ldg + col) * K + k0 + kk] = acc.value(kk);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // EM posterior term of one individual at allele frequency f (emMAF_cy.pyx:19-22):
 //   (p1 + 2 p2) / (2 (p0 + p1 + p2)),  p = GL * HWE(f)
 // with H0 = 2(1-f)^2, H1 = 2f(1-f), H2 = 2f^2 precomputed per (site, problem):
