@@ -488,30 +488,34 @@ int add_af_logsum(wgs_ctx* ctx, const float* dA, long M, int K, double* sums, lo
 }
 
 // ---- leave-one-out likelihoods with the state rows staged in shared memory (loo_like2) -----------
-struct LooLike2Cfg { int W, gx, gy, TS; long spb; size_t smem; };
-bool loo_like2_cfg(wgs_ctx* ctx, long M, int ldf, LooLike2Cfg* c)
+struct LooLike2Cfg { int W, gx, gy, TS; long spb; size_t smem; bool wide; };
+bool loo_like2_cfg(wgs_ctx* ctx, long M, int ldf, int K, LooLike2Cfg* c)
 {
     const int groups = (ctx->ldg + 31) / 32;
-    const int nb = (groups + 15) / 16;                            // blocks per site split: at most 16 warps each
+    const int nb = (groups + kLL2MaxW - 1) / kLL2MaxW;            // blocks per site split
     c->W = (groups + nb - 1) / nb;
     c->gx = nb;
-    int TS = (int)std::min<size_t>(kLL2MaxTS, (90 * 1024) / ((size_t)ldf * 20));   // 12 B of planes + 2 x 4 B of raw rows per state value
+    c->wide = K > 10;                                             // one block per SM, <= 4 sites per tile (see the kernel)
+    const size_t budget = c->wide ? 190 * 1024 : 100 * 1024;
+    // per site of a tile: 16 B plane cell + 4 B landing row per state value, 2 x 8 B per GL column of the block
+    const size_t per_site = (size_t)ldf * 20 + (size_t)c->W * 32 * 16;
+    int TS = (int)std::min<size_t>(c->wide ? 4 : 8, budget / per_site);
     if (TS < 1) return false;
     c->TS = TS;
-    c->smem = (size_t)TS * ldf * 20;
-    long target = std::max<long>(1, (long)ctx->num_sm * 2 / nb);  // ~2 resident blocks per SM, one wave
+    c->smem = (size_t)TS * per_site;
+    long target = std::max<long>(1, (long)ctx->num_sm * (c->wide ? 1 : 2) / nb);    // one wave of resident blocks
     long spb = (M + target - 1) / target;
     spb = std::max<long>(TS, (spb + TS - 1) / TS * TS);
     c->spb = spb;
     c->gy = (int)std::max<long>(1, (M + spb - 1) / spb);
     return true;
 }
-template <int KT>
+template <int KT, int TSMAX, int MINB>
 int launch_loo_like2_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, int ldf, const int* rc, int K, int k0,
                        const LooLike2Cfg& c, long pm, long pr, int R, double* partials)
 {
-    auto kern = loo_like2_kernel<KT>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    auto kern = loo_like2_kernel<KT, TSMAX, MINB>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     LAUNCH("loo_like", kern, dim3(c.gx, c.gy), c.W * 32, c.smem, ctx->stream,
            G, ctx->ldg, M, Fx, ldf, rc, K, k0, c.TS, c.spb, pm, pr, ctx->site_offset, R, partials);
@@ -521,17 +525,21 @@ int launch_loo_like2_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, i
     }
     return 0;
 }
+// population tile width of one pass: the narrow kernels take pick_KT's widths, the wide ones 16 or 20 (masked past K)
+int loo_like2_KT(const LooLike2Cfg& c, int remaining) { return c.wide ? (remaining > 16 ? 20 : 16) : pick_KT(remaining); }
 int launch_loo_like2(wgs_ctx* ctx, int KT, const float2* G, long M, const float* Fx, int ldf, const int* rc, int K, int k0,
                      const LooLike2Cfg& c, long pm, long pr, int R, double* partials)
 {
+    if (c.wide) {
+        if (KT == 16) return launch_loo_like2_t<16, 4, 1>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        return launch_loo_like2_t<20, 4, 1>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+    }
     switch (KT) {
-        case 2: return launch_loo_like2_t<2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        case 4: return launch_loo_like2_t<4>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        case 5: return launch_loo_like2_t<5>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        case 8: return launch_loo_like2_t<8>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        case 10: return launch_loo_like2_t<10>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        case 16: return launch_loo_like2_t<16>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        default: return launch_loo_like2_t<20>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        case 2: return launch_loo_like2_t<2, 8, 2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        case 4: return launch_loo_like2_t<4, 8, 2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        case 5: return launch_loo_like2_t<5, 8, 2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        case 8: return launch_loo_like2_t<8, 8, 2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        default: return launch_loo_like2_t<10, 8, 2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
     }
 }
 
@@ -1280,7 +1288,7 @@ int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole
     }
     LikeCfg c = like_cfg(ctx, M, 3);
     LooLike2Cfg c2{};
-    const bool staged = getenv("WGS_LOOLIKE_V1") == nullptr && loo_like2_cfg(ctx, M, ldf, &c2);
+    const bool staged = getenv("WGS_LOOLIKE_V1") == nullptr && loo_like2_cfg(ctx, M, ldf, K, &c2);
     const int n_split = staged ? c2.gy : c.gy;
     size_t np = (size_t)ldg * K;
     DevBuf partials, sums;
@@ -1290,7 +1298,7 @@ int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole
     for (int pass = 0; pass < (parts > 1 ? parts + 1 : 1); ++pass) {
         long pm = pass == 0 ? 1 : parts, pr = pass == 0 ? 0 : pass - 1;
         for (int k0 = 0; k0 < K;) {
-            int KT = pick_KT(K - k0);
+            int KT = staged ? loo_like2_KT(c2, K - k0) : pick_KT(K - k0);
             int rc_ = 0;
             if (staged) rc_ = launch_loo_like2(ctx, KT, Gsrc, M, F.as<float>(), ldf, drc.as<int>(), K, k0, c2, pm, pr, R, partials.as<double>());
             else DISPATCH_KT(launch_loo_like_t, KT, R, ctx, Gsrc, M, F.as<float>(), ldf, drc.as<int>(), K, k0, c, pm, pr, partials.as<double>());

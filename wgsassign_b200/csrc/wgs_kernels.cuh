@@ -854,99 +854,112 @@ loo_like_kernel(const float2* __restrict__ G, int ldg, long M,
 // Fx[s][rc[c][j]] through L1 kept loo_like latency-bound (11 dependent global loads per site and
 // thread).  Here a block walks a range of sites with ALL its warps on the same site tile: the TS
 // state rows of the tile arrive by one TMA bulk copy (rows of consecutive sites are contiguous),
-// are turned once into HWE planes H01 = ((1-a)^2, 2a(1-a)) and H2 = a^2, and every (individual,
-// population) evaluation is then LDS.64 + LDS.32 + 3 multiply-adds + the running-product multiply.
+// are turned once into 16-byte HWE cells ((1-a)^2, 2a(1-a), a^2, -), and every (individual,
+// population) evaluation is then one address add + LDS.128 + 3 multiply-adds + the running-product multiply.
+// The block's GL columns of the tile arrive the same way (one bulk copy per site row, double-buffered,
+// issued one tile ahead) so HBM latency hides behind the previous tile's arithmetic.
 // Warps own 32 columns each and all sites of the block's split: no cross-warp reduction.
 // ---------------------------------------------------------------------------------------
-constexpr int kLL2MaxTS = 8;
-template <int KT>
-__global__ void __launch_bounds__(512)
+// Up to 10 warps per block.  KT <= 10: two blocks per SM (<= 96 registers), tiles of up to 8 sites; wider
+// population tiles: one block per SM with up to 4 sites per tile (the 2 x KT accumulators need the registers).
+constexpr int kLL2MaxW = 10;
+template <int KT, int TSMAX, int MINB>
+__global__ void __launch_bounds__(kLL2MaxW * 32, MINB)
 loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
                  const float* __restrict__ Fx, int ldf,
                  const int* __restrict__ rc, int K, int k0,
-                 int TS, long sites_per_block,                  // TS <= kLL2MaxTS; sites_per_block a multiple of TS
+                 int TS, long sites_per_block,                  // TS <= TSMAX; sites_per_block a multiple of TS
                  long part_mod, long part_rem, long site_offset, int R,
                  double* __restrict__ partials)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long mbar[2];
-    float2* H01 = reinterpret_cast<float2*>(smem_raw);                      // [TS][ldf]
-    float* H2 = reinterpret_cast<float*>(H01 + (size_t)TS * ldf);           // [TS][ldf]
-    float* raw = H2 + (size_t)TS * ldf;                                     // [2][TS][ldf]
+    __shared__ __align__(8) unsigned long long mbar, mbar_g[2];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int W = blockDim.x >> 5;
-    const int col = (blockIdx.x * W + warp) * 32 + lane;
+    const int wcols = W * 32;                                               // GL columns of this block
+    float4* Hq = reinterpret_cast<float4*>(smem_raw);                       // [TS][ldf] planes ((1-a)^2, 2a(1-a), a^2, -)
+    float2* Gs = reinterpret_cast<float2*>(Hq + (size_t)TS * ldf);          // [2][TS][wcols] GL pairs, double-buffered
+    float* raw = reinterpret_cast<float*>(Gs + 2 * (size_t)TS * wcols);     // [TS][ldf] landing rows of the next tile's state
+    const int col0 = blockIdx.x * wcols;
+    const int col = col0 + t;
     const bool col_ok = col < ldg;
     const bool warp_live = col - lane < ldg;
+    const int lcol = min(col, ldg - 1) - col0;                              // a valid column for the padding lanes of a live warp
     const long s_begin = (long)blockIdx.y * sites_per_block;
     const long s_end = min(M, s_begin + sites_per_block);
     const int ntiles = (int)((s_end - s_begin + TS - 1) / TS);
 
-    int rcol[KT];
+    unsigned roff[KT];                                    // byte offset of this thread's state cell inside a plane row
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk)
-        rcol[kk] = (col_ok && k0 + kk < K) ? rc[(long)col * K + k0 + kk] : (ldf - 1);
+        roff[kk] = 16u * (unsigned)((col_ok && k0 + kk < K) ? rc[(long)col * K + k0 + kk] : (ldf - 1));
 
-    if (t == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
+    if (t == 0) { mbar_init(&mbar, 1); mbar_init(&mbar_g[0], 1); mbar_init(&mbar_g[1], 1); mbar_fence_init(); }
     __syncthreads();
-    auto issue = [&](int j, int buf) {                    // thread 0: one bulk copy for the tile's state rows
+    auto issue_state = [&](int j) {                       // thread 0: one bulk copy for the tile's state rows
         if (j < ntiles && t == 0) {
             const long s0 = s_begin + (long)j * TS;
             const unsigned bytes = (unsigned)min((long)TS, s_end - s0) * (unsigned)ldf * 4u;
-            mbar_expect_tx(&mbar[buf], bytes);
-            bulk_g2s(raw + (size_t)buf * TS * ldf, Fx + s0 * (long)ldf, bytes, &mbar[buf]);
+            mbar_expect_tx(&mbar, bytes);
+            bulk_g2s(raw, Fx + s0 * (long)ldf, bytes, &mbar);
         }
     };
-    issue(0, 0);
-    issue(1, 1);
+    auto issue_gl = [&](int j) {                          // thread 0: one bulk copy per site row of the block's GL columns
+        if (j < ntiles && t == 0) {
+            const int buf = j & 1;
+            const long s0 = s_begin + (long)j * TS;
+            const int rows = (int)min((long)TS, s_end - s0);
+            const unsigned wbytes = (unsigned)min(wcols, ldg - col0) * 8u;  // a multiple of 32: slabs are padded to 4 individuals
+            mbar_expect_tx(&mbar_g[buf], wbytes * (unsigned)rows);
+            for (int u = 0; u < rows; ++u)
+                bulk_g2s(Gs + ((size_t)buf * TS + u) * wcols, G + (s0 + u) * (long)ldg + col0, wbytes, &mbar_g[buf]);
+        }
+    };
+    issue_state(0);
+    issue_gl(0);
 
     LikeAcc<KT> acc;
     acc.init();
     int cnt = 0;
-    const float2* Gc = G + (col_ok ? col : ldg - 1);
+    const unsigned row_bytes = 16u * (unsigned)ldf;
     for (int j = 0; j < ntiles; ++j) {
-        const int buf = j & 1;
         const long s0 = s_begin + (long)j * TS;
         const int rows = (int)min((long)TS, s_end - s0);
-        float2 g[kLL2MaxTS];                              // this thread's GL pairs of the tile, in flight during the transform
-#pragma unroll
-        for (int u = 0; u < kLL2MaxTS; ++u) {
-            g[u] = make_float2(1.0f, 0.0f);
-            if (u < rows && warp_live) g[u] = ld_stream2(Gc + (s0 + u) * (long)ldg);
-        }
-        mbar_wait(&mbar[buf], (unsigned)((j >> 1) & 1));
-        const float* src = raw + (size_t)buf * TS * ldf;
+        issue_gl(j + 1);                                  // its buffer was released by the barrier that ended tile j-1
+        mbar_wait(&mbar, (unsigned)(j & 1));
         for (int e = t; e < rows * ldf; e += blockDim.x) {
-            const float a = src[e];
+            const float a = raw[e];
             const float om = 1.0f - a;
-            H01[e] = make_float2(om * om, 2.0f * a * om);
-            H2[e] = a * a;
+            Hq[e] = make_float4(om * om, 2.0f * a * om, a * a, 0.0f);
         }
-        __syncthreads();                                  // planes complete, raw buffer free
-        issue(j + 2, buf);
+        __syncthreads();                                  // planes complete, landing rows free: the next tile's copy overlaps the compute
+        issue_state(j + 1);
+        mbar_wait(&mbar_g[j & 1], (unsigned)((j >> 1) & 1));
         // partition of the tile's first site (site indices fit 32 bits: the reference's sizes are C ints)
         const unsigned tile_rem = part_mod > 1 ? (unsigned)(site_offset + s0) % (unsigned)part_mod : 0u;
         if (warp_live) {
+            const unsigned char* hrow = reinterpret_cast<const unsigned char*>(Hq);
+            const float2* grow = Gs + (size_t)(j & 1) * TS * wcols + lcol;
 #pragma unroll
-            for (int u = 0; u < kLL2MaxTS; ++u) {
+            for (int u = 0; u < TSMAX; ++u) {
                 if (u < rows) {                           // block-uniform
                     const bool use = part_mod <= 1 || (tile_rem + (unsigned)u) % (unsigned)part_mod == (unsigned)part_rem;
                     if (use) {
-                        const float g0 = g[u].x, g1 = g[u].y, g2 = third_gl(g0, g1);
-                        const float2* h01 = H01 + (size_t)u * ldf;
-                        const float* h2 = H2 + (size_t)u * ldf;
+                        const float2 gq = grow[(size_t)u * wcols];
+                        const float g0 = gq.x, g1 = gq.y, g2 = third_gl(g0, g1);
 #pragma unroll
                         for (int kk = 0; kk < KT; ++kk) {
-                            const float2 h = h01[rcol[kk]];
-                            const float like = fmaf(g0, h.x, fmaf(g1, h.y, g2 * h2[rcol[kk]]));
+                            const float4 h = *reinterpret_cast<const float4*>(hrow + roff[kk]);
+                            const float like = fmaf(g0, h.x, fmaf(g1, h.y, g2 * h.z));
                             acc.prod[kk] *= like;
                         }
                         if (++cnt == R) { acc.renorm(); cnt = 0; }
                     }
                 }
+                hrow += row_bytes;
             }
         }
-        __syncthreads();                                  // everyone is done with the planes
+        __syncthreads();                                  // everyone is done with the planes and this tile's GL buffer
     }
     acc.renorm();
     if (col_ok) {
