@@ -319,12 +319,22 @@ def main():
             n = min(chunk, M_local - s0)
             Lh[s0:s0 + n] = ctx.download(s0, n)
         ctx2 = ctx
+        af_pin = _lib.pinned_empty((M_local, N_POP), np.float32)      # host buffer the allele frequencies come back into
 
         def e2e_step():
+            """What the CLI does for `--get_reference_af --loo` on a freshly parsed matrix: queue the
+            upload (one strided DMA per population slab), then ONE fused call whose leave-one-out EM
+            starts on population 0 while the later slabs are still crossing PCIe; the allele
+            frequencies (for <out>.pop_af.npy) and the likelihoods come back to the host."""
             ctx2.set_pops(pop_of, N_POP)
-            ctx2.upload_gl(Lh)
             dist.attach(ctx2)
-            return step(host_af=True)
+            if os.environ.get("WGS_E2E_SERIAL"):            # the unpipelined form, for comparison
+                ctx2.upload_gl(Lh)
+                return step(host_af=True)
+            ctx2.upload_gl_async(Lh)
+            af_, its_, ll_, _, lits_, _ = ctx2.ref_af_loo(MAF_ITER, MAF_TOLE, af_out=af_pin)
+            dist.allreduce_sum(ll_)
+            return af_, ll_, its_, lits_
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -338,11 +348,14 @@ def main():
             tt = torch.tensor([dte], dtype=torch.float64, device="cuda")
             td.all_reduce(tt, op=td.ReduceOp.MAX)
             dte = float(tt.item())
-        h2d = Lh.nbytes + af2.nbytes + pop_of.nbytes
-        d2h = 2 * af2.nbytes + 2 * ll2.nbytes + 4 * (N_IND + N_POP)
+        serial = bool(os.environ.get("WGS_E2E_SERIAL"))
+        h2d = Lh.nbytes + pop_of.nbytes + (af2.nbytes if serial else 0)
+        d2h = (2 if serial else 1) * af2.nbytes + 2 * ll2.nbytes + 4 * (N_IND + N_POP)
         e2e = {"value": evals_step / (dte / n_e2e), "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
                "d2h_bytes_per_step": int(d2h * world), "ms_per_step": dte / n_e2e * 1e3, "steps": n_e2e,
-               "identical_to_resident": bool(np.array_equal(ll2, ll))}
+               "identical_to_resident": bool(np.array_equal(ll2, ll)),
+               "path": "wgs_upload_gl + wgs_ref_af + wgs_loo_partial" if serial else
+                       "wgs_upload_gl_async + wgs_ref_af_loo (leave-one-out EM of population k overlaps the upload of k+1..)"}
 
     # ---- extras: the other kernels of the path on the same resident matrix (untimed for `value`) ----
     extra = {}

@@ -71,6 +71,15 @@ int32_t wgs_set_pops(wgs_ctx *ctx, const int32_t *pop_of_ind, int32_t N, int32_t
  * glassy.loo scores against (glassy.py:96). */
 int32_t wgs_upload_gl(wgs_ctx *ctx, const float *L, int64_t M, int32_t N, int32_t which);
 
+/* Asynchronous form of wgs_upload_gl(which=0): queues one strided DMA per population slab (straight
+ * into the device layout, no staging pass) on a copy stream and returns at once.  L must stay valid
+ * and unchanged until wgs_upload_wait() or the next operator call returns; pinned memory
+ * (wgs_host_alloc) is needed for the copy to overlap anything.  Every operator waits for the whole
+ * matrix first, except wgs_ref_af_loo, which starts on population 0 while the others are in flight.
+ * ID files that interleave populations column by column fall back to the synchronous upload. */
+int32_t wgs_upload_gl_async(wgs_ctx *ctx, const float *L, int64_t M, int32_t N);
+int32_t wgs_upload_wait(wgs_ctx *ctx);
+
 /* Allele depths [M,2N] int32, packed on device to 2 x uint8 per individual
  * (counts above 254 are rejected with an error rather than clamped). */
 int32_t wgs_upload_ad(wgs_ctx *ctx, const int32_t *AD, int64_t M, int32_t N);
@@ -110,6 +119,17 @@ int32_t wgs_pop_like_partial(wgs_ctx *ctx, const float *af, int32_t K, double *o
  * af_inout may be NULL: the matrix left on the device by wgs_ref_af is used and updated in place. */
 int32_t wgs_loo_partial(wgs_ctx *ctx, float *af_inout, int32_t iter, double tole, int32_t use_ds,
                         int32_t parts, double *ll, double *ll_parts, int32_t *iters_out);
+
+/* `--get_reference_af --loo` in one call (WGSassign.py:225-242 followed by glassy.py:47-112): the
+ * same results as wgs_ref_af(af_out, af_iters_out) followed by wgs_loo_partial(NULL, ...), bit for
+ * bit.  After wgs_upload_gl_async the leave-one-out EM of population k runs while the slabs of the
+ * later populations are still crossing PCIe (it does not need the full-data frequencies); the
+ * per-population EM and the likelihood pass follow when the matrix is complete.  af_out [M,K] (the
+ * matrix the CLI saves as .pop_af.npy) and af_after_loo [M,K] (the state glassy.loo leaves in its
+ * `af` argument) may each be NULL. */
+int32_t wgs_ref_af_loo(wgs_ctx *ctx, int32_t iter, double tole, float *af_out, int32_t *af_iters_out,
+                       float *af_after_loo, int32_t use_ds, int32_t parts, double *ll, double *ll_parts,
+                       int32_t *loo_iters_out);
 
 /* fisher.fisher_obs + fisher.fisher_obs_ind in one pass (fisher.py:11-59 over
  * fisher_cy.pyx:12-65): f_obs, ne_obs [M,K] float32 (local sites); ne_ind_sum [N] float64 =

@@ -230,3 +230,80 @@ def test_determinism_and_partition_property_large(wgs):
     # individuals are most likely under their own population on depth-consistent data
     assert np.mean(np.argmax(ll1, 1) == pop_of) > 0.99
     ctx.close()
+
+
+@pytest.mark.parametrize("interleave,pinned", [(False, True), (False, False), (True, True)])
+def test_async_upload_roundtrip(wgs, interleave, pinned):
+    """wgs_upload_gl_async (one strided DMA per population slab, straight into the device layout) leaves
+    exactly the matrix wgs_upload_gl leaves: contiguous populations (slab path), pageable memory, and an
+    interleaved ID file (falls back to the chunked upload)."""
+    from wgsassign_b200 import synth
+    d = synth.synth(1201, 23, 4, seed=5, interleave=interleave, with_ad=False)
+    L = d["L"]
+    if pinned:
+        Lp = wgs.lib.pinned_empty(L.shape, np.float32)
+        Lp[...] = L
+    else:
+        Lp = L
+    pop_of, pops = wgs.session.pops_from_ids(d["IDs"])
+    ctx = wgs.lib.Context(0)
+    ctx.set_pops(pop_of, len(pops))
+    ctx.upload_gl_async(Lp)
+    L2 = ctx.download(0, 1201)               # every operator but ref_af_loo waits for the whole matrix
+    assert np.array_equal(L, L2)
+    ctx.upload_gl_async(Lp)
+    ctx.upload_wait()
+    assert np.array_equal(L[7:19], ctx.download(7, 12))
+    ctx.close()
+
+
+@pytest.mark.parametrize("m,n,k,interleave,parts,seed", [
+    (3000, 37, 3, False, 1, 31),
+    (1500, 64, 5, False, 3, 32),
+    (900, 21, 4, True, 1, 33),
+])
+def test_ref_af_loo_fused_is_bit_identical(wgs, m, n, k, interleave, parts, seed):
+    """wgs_ref_af_loo == wgs_ref_af followed by wgs_loo_partial, bit for bit, whether the matrix was
+    uploaded synchronously or is still arriving slab by slab (pipelined leave-one-out EM)."""
+    from wgsassign_b200 import synth
+    d = synth.synth(m, n, k, seed=seed, interleave=interleave, with_ad=False)
+    L = wgs.lib.pinned_empty(d["L"].shape, np.float32)
+    L[...] = d["L"]
+    pop_of, pops = wgs.session.pops_from_ids(d["IDs"])
+    ctx = wgs.lib.Context(0)
+    ctx.set_pops(pop_of, len(pops))
+    ctx.upload_gl(L)
+    af0, its0 = ctx.ref_af(200, 1e-4)
+    af_mut = af0.copy()
+    ll0, llp0, lits0 = ctx.loo_partial(af_mut, 200, 1e-4, parts=parts)
+    for use_async in (False, True):
+        ctx.set_pops(pop_of, len(pops))
+        if use_async:
+            ctx.upload_gl_async(L)
+        else:
+            ctx.upload_gl(L)
+        af1, its1, ll1, llp1, lits1, af_after = ctx.ref_af_loo(200, 1e-4, parts=parts, want_af_after=True)
+        assert np.array_equal(af1, af0) and list(its1) == list(its0)
+        assert np.array_equal(ll1, ll0) and np.array_equal(llp1, llp0)
+        assert list(lits1) == list(lits0)
+        assert np.array_equal(af_after, af_mut)
+    ctx.close()
+
+
+def test_ref_af_loo_fused_bundled(wgs, bundled):
+    """The fused call on the bundled breeding data against the reference's golden outputs."""
+    L, IDs = bundled["L_breeding"], bundled["IDs_breeding"]
+    Lp = wgs.lib.pinned_empty(L.shape, np.float32)
+    Lp[...] = L
+    pop_of, pops = wgs.session.pops_from_ids(IDs)
+    ctx = wgs.lib.Context(0)
+    ctx.set_pops(pop_of, len(pops))
+    ctx.upload_gl_async(Lp)
+    af, its, ll, _, lits, _ = ctx.ref_af_loo(200, 1e-4)
+    assert list(its) == list(bundled["c1_em_iters_ref"]) and list(lits) == list(bundled["c1_em_iters_loo"])
+    assert np.max(np.abs(af - bundled["c1_pop_af"])) < AF_ATOL
+    _, rows = parse_tsv(str(bundled["c1_loo_tsv"]))
+    gold = np.array([[float(x) for x in r[2:]] for r in rows])
+    assert rel_err(ll.astype(np.float32), gold) < 2e-6
+    assert np.array_equal(np.argmax(ll, 1), np.argmax(gold, 1))
+    ctx.close()

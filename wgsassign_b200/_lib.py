@@ -39,6 +39,8 @@ SYMBOLS = {
     "wgs_host_free": (None, [_vp]),
     "wgs_set_pops": (_i32, [_vp, _vp, _i32, _i32]),
     "wgs_upload_gl": (_i32, [_vp, _vp, _i64, _i32, _i32]),
+    "wgs_upload_gl_async": (_i32, [_vp, _vp, _i64, _i32]),
+    "wgs_upload_wait": (_i32, [_vp]),
     "wgs_upload_ad": (_i32, [_vp, _vp, _i64, _i32]),
     "wgs_set_shard": (_i32, [_vp, _i64, _i64, ALLREDUCE_FN, _vp]),
     "wgs_synth": (_i32, [_vp, _i64, _i32, ctypes.c_uint64, ctypes.c_float, _i32]),
@@ -47,6 +49,7 @@ SYMBOLS = {
     "wgs_ref_af": (_i32, [_vp, _i32, _f64, _vp, _vp]),
     "wgs_pop_like_partial": (_i32, [_vp, _vp, _i32, _vp]),
     "wgs_loo_partial": (_i32, [_vp, _vp, _i32, _f64, _i32, _i32, _vp, _vp, _vp]),
+    "wgs_ref_af_loo": (_i32, [_vp, _i32, _f64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "wgs_fisher_partial": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "wgs_zscore": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f64, _vp]),
     "wgs_zscore_classes": (_i32, [_vp, _i32, _i32, _vp, _vp]),
@@ -138,6 +141,7 @@ class Context:
         if L.wgs_create(int(device), ctypes.byref(self._h)) != 0:
             raise WgsError(L.wgs_last_error(None).decode())
         self.device = device
+        self._pending_L = None
         self.M = 0
         self.N = 0
         self.K = 0
@@ -170,6 +174,20 @@ class Context:
         self._ck(lib().wgs_upload_gl(self._h, _ptr(L), L.shape[0], L.shape[1] // 2, int(which)))
         if which == 0:
             self.M, self.N = L.shape[0], L.shape[1] // 2
+
+    def upload_gl_async(self, L):
+        """Queue the upload (one strided DMA per population slab) and return at once; the array is
+        kept referenced until the next operator (or upload_wait) has consumed it."""
+        _as(L, np.float32, 2, "L")
+        if L.shape[1] % 2:
+            raise ValueError("L must have 2 columns per individual")
+        self._pending_L = L
+        self._ck(lib().wgs_upload_gl_async(self._h, _ptr(L), L.shape[0], L.shape[1] // 2))
+        self.M, self.N = L.shape[0], L.shape[1] // 2
+
+    def upload_wait(self):
+        self._ck(lib().wgs_upload_wait(self._h))
+        self._pending_L = None
 
     def upload_ad(self, AD):
         _as(AD, np.int32, 2, "AD")
@@ -235,6 +253,24 @@ class Context:
         self._ck(lib().wgs_loo_partial(self._h, _ptr(af), int(iters), float(tole), int(bool(use_ds)), int(parts),
                                        _ptr(ll), _ptr(llp), _ptr(its)))
         return ll, llp, its
+
+    def ref_af_loo(self, iters, tole, use_ds=False, parts=1, want_af_after=False, af_out=None):
+        """`--get_reference_af --loo` in one call: (af [M,K], af_iters [K], ll [N,K] f64, ll_parts, loo_iters [N],
+        af_after_loo or None) - bit-identical to ref_af() followed by loo_partial(); after upload_gl_async the
+        leave-one-out EM overlaps the upload.  af_out: optional preallocated [M,K] float32 (e.g. pinned_empty) to
+        receive the allele frequencies."""
+        af = np.empty((self.M, self.K), np.float32) if af_out is None else _as(af_out, np.float32, 2, "af_out")
+        if af.shape != (self.M, self.K):
+            raise ValueError("af_out must be [M,K] = %s" % ((self.M, self.K),))
+        af_after = np.empty((self.M, self.K), np.float32) if want_af_after else None
+        its = np.zeros(self.K, np.int32)
+        ll = np.empty((self.N, self.K), np.float64)
+        llp = np.empty((self.N * parts, self.K), np.float64)
+        lits = np.zeros(self.N, np.int32)
+        self._ck(lib().wgs_ref_af_loo(self._h, int(iters), float(tole), _ptr(af), _ptr(its), _ptr(af_after),
+                                      int(bool(use_ds)), int(parts), _ptr(ll), _ptr(llp), _ptr(lits)))
+        self._pending_L = None
+        return af, its, ll, llp, lits, af_after
 
     def fisher_partial(self, af):
         _as(af, np.float32, 2, "af")

@@ -48,6 +48,16 @@ struct wgs_ctx {
     uchar2* AD = nullptr;
     long M_ad = 0;
 
+    // asynchronous upload (wgs_upload_gl_async): one event per population slab on stream2
+    bool upload_pending = false;
+    std::vector<cudaEvent_t> ev_pop;
+
+    // EM decisions come back through two mapped pinned slots ([0] = problems still active, [1..] = flags)
+    int* em_pin[2] = {nullptr, nullptr};
+    int* em_pin_dev[2] = {nullptr, nullptr};
+    size_t em_pin_cap = 0;
+    cudaEvent_t em_ev[2] = {nullptr, nullptr};
+
     // sharding
     long M_total = -1, site_offset = 0;
     wgs_allreduce_fn fn = nullptr;
@@ -266,8 +276,17 @@ int build_structure(wgs_ctx* ctx, const int32_t* pop_of_ind, int N, int K)
     return 0;
 }
 
+// Host-blocking end of an asynchronous upload: every operator but the pipelined one starts with it.
+void upload_fence(wgs_ctx* ctx)
+{
+    if (!ctx->upload_pending) return;
+    cudaStreamSynchronize(ctx->stream2);
+    ctx->upload_pending = false;
+}
+
 void drop_data(wgs_ctx* ctx)
 {
+    upload_fence(ctx);
     dev_free(ctx, ctx->G[0]); dev_free(ctx, ctx->G[1]); dev_free(ctx, ctx->AD); dev_free(ctx, ctx->d_af);
     ctx->Mg[0] = ctx->Mg[1] = ctx->M_ad = 0; ctx->af_rows = 0; ctx->af_cols = 0;
 }
@@ -597,16 +616,35 @@ struct EmState {
     int np = 0;                  // problems (columns of the partials)
     int ld = 0;                  // leading dimension of partials
     int nblocks = 0;
-    DevBuf partials, ssq, count, active, iters, nactive;
+    DevBuf partials, ssq, count, active, iters;
     std::vector<int> h_active, h_iters;
+    int slot_c0[2] = {0, 0}, slot_nc[2] = {0, 0};
 };
+
+// The decision kernels write straight into mapped pinned host memory (no copy to queue, nothing pageable on the
+// path); the slots live in the context because cudaHostAlloc / cudaFreeHost synchronise the device.
+int em_pin_reserve(wgs_ctx* ctx, size_t ints)
+{
+    if (ints <= ctx->em_pin_cap) return 0;
+    CU(cudaDeviceSynchronize());
+    size_t cap = std::max<size_t>(ints, 1 << 16);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->em_pin[b]) cudaFreeHost(ctx->em_pin[b]);
+        ctx->em_pin[b] = nullptr;
+        CU(cudaHostAlloc((void**)&ctx->em_pin[b], cap * sizeof(int), cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void**)&ctx->em_pin_dev[b], ctx->em_pin[b], 0));
+        if (!ctx->em_ev[b]) CU(cudaEventCreateWithFlags(&ctx->em_ev[b], cudaEventDisableTiming));
+    }
+    ctx->em_pin_cap = cap;
+    return 0;
+}
 
 int em_state_init(wgs_ctx* ctx, EmState& st, int np, int ld, int nblocks, const std::vector<int>& active0)
 {
     st.np = np; st.ld = ld; st.nblocks = nblocks;
     if (buf_alloc(ctx, st.partials, (size_t)nblocks * ld * sizeof(double)) || buf_alloc(ctx, st.ssq, (size_t)np * sizeof(double)) ||
-        buf_alloc(ctx, st.active, (size_t)np * sizeof(int)) || buf_alloc(ctx, st.iters, (size_t)np * sizeof(int)) ||
-        buf_alloc(ctx, st.nactive, sizeof(int))) return 1;
+        buf_alloc(ctx, st.active, (size_t)np * sizeof(int)) || buf_alloc(ctx, st.iters, (size_t)np * sizeof(int))) return 1;
+    if (em_pin_reserve(ctx, (size_t)np + 1)) return 1;
     CU(cudaMemsetAsync(st.partials.p, 0, (size_t)nblocks * ld * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(st.iters.p, 0, (size_t)np * sizeof(int), ctx->stream));
     st.h_active = active0;
@@ -617,23 +655,44 @@ int em_state_init(wgs_ctx* ctx, EmState& st, int np, int ld, int nblocks, const 
 
 // After a step kernel has written st.partials: reduce, (all-reduce across ranks), decide.
 // d_count: optional per-problem site counts (already global); else count_all.
-int em_after_step(wgs_ctx* ctx, EmState& st, double tole, int iteration, const double* d_count, double count_all, int* n_active)
+// [c0, c0 + nc) restricts the reduction, the decision and the active count to those problems (nc < 0: all) -
+// the pipelined leave-one-out EM advances one population at a time.
+// Two halves: em_after_step_queue puts reduce + decide + the read-back of the decision on the stream (into result
+// slot `slot`), em_after_step_wait blocks until that read-back has landed.  The caller may queue the NEXT
+// iteration's kernels in between: a problem that this decision freezes is skipped on the device (the step kernels
+// read the `active` flags), so a speculative launch never changes a result.
+int em_after_step_queue(wgs_ctx* ctx, EmState& st, double tole, int iteration, const double* d_count, double count_all,
+                        int slot, int c0 = 0, int nc = -1)
 {
-    LAUNCH("em_ssq_reduce", em_ssq_reduce_kernel, grid_for(st.np, 128, 64), 128, 0, ctx->stream,
-           st.partials.as<double>(), st.nblocks, st.np, st.ld, st.ssq.as<double>());
+    if (nc < 0) nc = st.np;
+    LAUNCH("em_ssq_reduce", em_ssq_reduce_kernel, (nc + 7) / 8, 256, 0, ctx->stream,
+           st.partials.as<double>() + c0, st.nblocks, nc, st.ld, st.ssq.as<double>() + c0);
     if (ctx->fn) {
-        std::vector<double> h(st.np);
-        CU(cudaMemcpyAsync(h.data(), st.ssq.p, st.np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<double> h(nc);
+        CU(cudaMemcpyAsync(h.data(), st.ssq.as<double>() + c0, nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        ctx->fn(h.data(), st.np, WGS_F64, ctx->user);
-        CU(cudaMemcpyAsync(st.ssq.p, h.data(), st.np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->fn(h.data(), nc, WGS_F64, ctx->user);
+        CU(cudaMemcpyAsync(st.ssq.as<double>() + c0, h.data(), nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));                  // h is a local
     }
-    LAUNCH("em_decide", em_decide_kernel, 1, 1024, 0, ctx->stream, st.ssq.as<double>(), d_count, count_all, st.np, tole,
-           iteration, st.active.as<int>(), st.iters.as<int>(), st.nactive.as<int>());
-    CU(cudaMemcpyAsync(n_active, st.nactive.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(st.h_active.data(), st.active.p, st.np * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    LAUNCH("em_decide", em_decide_kernel, 1, 1024, 0, ctx->stream, st.ssq.as<double>() + c0, d_count ? d_count + c0 : nullptr, count_all, nc, tole,
+           iteration, st.active.as<int>() + c0, st.iters.as<int>() + c0, ctx->em_pin_dev[slot]);
+    CU(cudaEventRecord(ctx->em_ev[slot], ctx->stream));
+    st.slot_c0[slot] = c0; st.slot_nc[slot] = nc;
     return 0;
+}
+int em_after_step_wait(wgs_ctx* ctx, EmState& st, int slot, int* n_active)
+{
+    CU(cudaEventSynchronize(ctx->em_ev[slot]));
+    *n_active = ctx->em_pin[slot][0];
+    memcpy(st.h_active.data() + st.slot_c0[slot], ctx->em_pin[slot] + 1, (size_t)st.slot_nc[slot] * sizeof(int));
+    return 0;
+}
+int em_after_step(wgs_ctx* ctx, EmState& st, double tole, int iteration, const double* d_count, double count_all, int* n_active,
+                  int c0 = 0, int nc = -1)
+{
+    if (em_after_step_queue(ctx, st, tole, iteration, d_count, count_all, 0, c0, nc)) return 1;
+    return em_after_step_wait(ctx, st, 0, n_active);
 }
 
 // Stop rule of emMAF.py:21-25 with rmse1d's float divide / double sqrt (emMAF_cy.pyx:32-33).
@@ -752,7 +811,7 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
             for (int k = 0; k < K; ++k) if (run[k] > 0) { inds += ctx->pops[k].n; act += 1; units += (double)ctx->pops[k].n * run[k]; }
             add_work(ctx, "em_pop", (double)M * inds * 8.0 + (double)M * act * 8.0, (double)M * units);
         }
-        LAUNCH("em_ssq_reduce", em_ssq_reduce_kernel, grid_for(np, 128, 64), 128, 0, ctx->stream, partials.as<double>(), gx, np, np, ssq.as<double>());
+        LAUNCH("em_ssq_reduce", em_ssq_reduce_kernel, (np + 7) / 8, 256, 0, ctx->stream, partials.as<double>(), gx, np, np, ssq.as<double>());
         CU(cudaMemcpyAsync(h.data(), ssq.p, np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         if (ctx->fn) ctx->fn(h.data(), np, WGS_F64, ctx->user);
@@ -842,8 +901,13 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
 
 // Leave-one-out EM for every individual on the resident G.  F [M][ldf] (device): columns
 // [0,ldg) <- converged UNclipped LOO estimates.  mask/d_count optional (reference z-score).
+// pop_ready (pipelined mode, wgs_ref_af_loo after wgs_upload_gl_async): one event per population, recorded when
+// that population's slab of G has arrived.  The populations then run one after the other - pre-pack and all
+// iterations of population k while the slabs of k+1.. are still in flight - instead of all together per
+// iteration.  Every problem sees exactly the same sequence of updates and decisions either way.
 int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const unsigned char* mask, const double* d_count,
-               std::vector<int>& iters_cols, const std::vector<unsigned char>* sel = nullptr)
+               std::vector<int>& iters_cols, const std::vector<unsigned char>* sel = nullptr,
+               const std::vector<cudaEvent_t>* pop_ready = nullptr)
 {
     const long M = ctx->M();
     const int ldg = ctx->ldg, K = ctx->K;
@@ -872,7 +936,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         if (ctx->pops[k].n <= 1) continue;
         if (loo_cfg(ctx, ctx->pops[k].n, packed, &cfgs[k])) return 1;
         nblocks = std::max(nblocks, cfgs[k].grid);
-        if (packed) {
+        if (packed && !pop_ready) {
             LAUNCH("loo_pack", loo_prepack_kernel, grid_for(M * cfgs[k].nc, 256, ctx->num_sm * 16), 256, 0, ctx->stream, ctx->G[0], ldg, M,
                    ctx->pops[k].col0, ctx->pops[k].n, cfgs[k].nc, pk[k].as<ulonglong2>());
             add_work(ctx, "loo_pack", (double)M * ctx->pops[k].n * 8.0 + (double)M * loo5_row_units(ctx->pops[k].n) * 16.0, (double)M * ctx->pops[k].n);
@@ -890,44 +954,95 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         LAUNCH("fill", bcast_row_kernel, grid_for(M * ldg, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F, ldf, ldg, M, drow.as<float>());
         CU(cudaStreamSynchronize(ctx->stream));
     }
-    int n_active = 0;
-    for (int a : active0) n_active += a;
-    for (int it = 1; it <= iter && n_active > 0; ++it) {
+    auto launch_step = [&](int k) -> int {
+        PopDesc pd = ctx->pops[k];
+        const LooLaunch& lc = cfgs[k];
+        int TS = lc.rows_per_pass * lc.passes;
+        long ntiles = (M + TS - 1) / TS;
+        if (lc.packed) {
+            if (lc.big)
+                LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
+                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
+            else if (!getenv("WGS_LOO_OCC3"))
+                LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
+                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
+            else
+                LAUNCH("loo_em", (loo_em_step5_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
+                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
+        } else {
+            if (lc.big)
+                LAUNCH("loo_em", (loo_em_step4_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
+                       lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
+            else
+                LAUNCH("loo_em", (loo_em_step4_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
+                       lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
+        }
+        return 0;
+    };
+    // algorithmic work of one iteration of population k, from the flags that were in force when it ran: the
+    // population's packed rows once + read/write of every active problem's f; n evaluations per active (site, problem)
+    auto account = [&](int k) {
+        PopDesc pd = ctx->pops[k];
+        double act = 0;
+        for (int j = 0; j < pd.n; ++j) act += st.h_active[pd.col0 + j] ? 1 : 0;
+        if (act > 0)
+            add_work(ctx, "loo_em", (double)M * (cfgs[k].packed ? loo5_row_units(pd.n) * 16.0 : pd.n * 8.0) + (double)M * act * 8.0, (double)M * act * pd.n);
+    };
+    auto pop_active = [&](int k) {
+        bool any = false;
+        for (int j = 0; j < ctx->pops[k].n; ++j) any = any || st.h_active[ctx->pops[k].col0 + j];
+        return any;
+    };
+    // Look-ahead: iteration t+1 is queued before the host has read the decision of iteration t (the device skips
+    // whatever that decision froze), so the GPU never idles on the round trip.  Not under site sharding, where the
+    // squared changes pass through the host for the all-reduce anyway.
+    const bool ahead = ctx->fn == nullptr && getenv("WGS_EM_NO_LOOKAHEAD") == nullptr;
+    const double count_all = (double)ctx->Mtot();
+    if (pop_ready) {
         for (int k = 0; k < K; ++k) {
             PopDesc pd = ctx->pops[k];
+            CU(cudaStreamWaitEvent(ctx->stream, (*pop_ready)[k], 0));       // device-side: the host keeps queueing
             if (pd.n <= 1) continue;
-            bool any = false;
-            for (int j = 0; j < pd.n; ++j) any = any || st.h_active[pd.col0 + j];
-            if (!any) continue;
-            const LooLaunch& lc = cfgs[k];
-            int TS = lc.rows_per_pass * lc.passes;
-            long ntiles = (M + TS - 1) / TS;
-            if (lc.packed) {
-                if (lc.big)
-                    LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
-                           pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
-                else if (!getenv("WGS_LOO_OCC3"))
-                    LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
-                           pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
-                else
-                    LAUNCH("loo_em", (loo_em_step5_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
-                           pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
-            } else {
-                if (lc.big)
-                    LAUNCH("loo_em", (loo_em_step4_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
-                           lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
-                else
-                    LAUNCH("loo_em", (loo_em_step4_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
-                           lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
+            if (packed) {
+                LAUNCH("loo_pack", loo_prepack_kernel, grid_for(M * cfgs[k].nc, 256, ctx->num_sm * 16), 256, 0, ctx->stream, ctx->G[0], ldg, M,
+                       pd.col0, pd.n, cfgs[k].nc, pk[k].as<ulonglong2>());
+                add_work(ctx, "loo_pack", (double)M * pd.n * 8.0 + (double)M * loo5_row_units(pd.n) * 16.0, (double)M * pd.n);
             }
-            {   // the population's GL tile once + read/write of every active problem's f; n evaluations per active (site, problem)
-                double act = 0;
-                for (int j = 0; j < pd.n; ++j) act += st.h_active[pd.col0 + j] ? 1 : 0;
-                add_work(ctx, "loo_em", (double)M * (lc.packed ? loo5_row_units(pd.n) * 16.0 : pd.n * 8.0) + (double)M * act * 8.0, (double)M * act * pd.n);
+            if (!pop_active(k) || iter < 1) continue;
+            if (launch_step(k) || em_after_step_queue(ctx, st, tole, 1, d_count, count_all, 1, pd.col0, pd.n)) return 1;
+            for (int it = 1; it <= iter; ++it) {
+                if (ahead && it < iter)
+                    if (launch_step(k) || em_after_step_queue(ctx, st, tole, it + 1, d_count, count_all, (it + 1) & 1, pd.col0, pd.n)) return 1;
+                int n_act = 0;
+                account(k);
+                if (em_after_step_wait(ctx, st, it & 1, &n_act)) return 1;
+                if (n_act == 0) break;
+                if (!ahead && it < iter)
+                    if (launch_step(k) || em_after_step_queue(ctx, st, tole, it + 1, d_count, count_all, (it + 1) & 1, pd.col0, pd.n)) return 1;
             }
         }
-        if (em_after_step(ctx, st, tole, it, d_count, (double)ctx->Mtot(), &n_active)) return 1;
+    } else {
+        auto queue_round = [&](int it) -> int {
+            for (int k = 0; k < K; ++k) {
+                if (ctx->pops[k].n <= 1 || !pop_active(k)) continue;
+                if (launch_step(k)) return 1;
+            }
+            return em_after_step_queue(ctx, st, tole, it, d_count, count_all, it & 1);
+        };
+        int n_active = 0;
+        for (int a : active0) n_active += a;
+        if (n_active > 0 && iter >= 1) {
+            if (queue_round(1)) return 1;
+            for (int it = 1; it <= iter; ++it) {
+                if (ahead && it < iter && queue_round(it + 1)) return 1;
+                for (int k = 0; k < K; ++k) if (ctx->pops[k].n > 1) account(k);
+                if (em_after_step_wait(ctx, st, it & 1, &n_active)) return 1;
+                if (n_active == 0) break;
+                if (!ahead && it < iter && queue_round(it + 1)) return 1;
+            }
+        }
     }
+    CU(cudaStreamSynchronize(ctx->stream));                      // a speculative round may still be running
     iters_cols.resize(ldg);
     CU(cudaMemcpy(iters_cols.data(), st.iters.p, ldg * sizeof(int), cudaMemcpyDeviceToHost));
     CU(cudaGetLastError());
@@ -978,6 +1093,7 @@ int32_t wgs_create(int32_t device, wgs_ctx** out)
     ctx->num_sm = prop.multiProcessorCount;
     cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    if (em_pin_reserve(ctx, 1)) { g_create_error = ctx->err; wgs_destroy(ctx); return 1; }
     *out = ctx;
     return 0;
 }
@@ -990,6 +1106,8 @@ void wgs_destroy(wgs_ctx* ctx)
     drop_data(ctx);
     dev_free(ctx, ctx->d_ind_of_col); dev_free(ctx, ctx->d_col_of_ind); dev_free(ctx, ctx->d_pop_of_col); dev_free(ctx, ctx->d_pops);
     pool_trim(ctx);
+    for (cudaEvent_t e : ctx->ev_pop) cudaEventDestroy(e);
+    for (int b = 0; b < 2; ++b) { if (ctx->em_pin[b]) cudaFreeHost(ctx->em_pin[b]); if (ctx->em_ev[b]) cudaEventDestroy(ctx->em_ev[b]); }
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
@@ -1005,6 +1123,7 @@ void wgs_host_free(void* p) { if (p) cudaFreeHost(p); }
 int32_t wgs_set_pops(wgs_ctx* ctx, const int32_t* pop_of_ind, int32_t N, int32_t K)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (N <= 0) return fail(ctx, "N must be positive");
     drop_data(ctx);
     ctx->pops_set = K > 0;
@@ -1020,6 +1139,7 @@ int32_t wgs_set_shard(wgs_ctx* ctx, int64_t M_total, int64_t site_offset, wgs_al
 int32_t wgs_upload_gl(wgs_ctx* ctx, const float* L, int64_t M, int32_t N, int32_t which)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (which < 0 || which > 1) return fail(ctx, "which must be 0 or 1");
     if (M < 0 || N <= 0) return fail(ctx, "bad shape");
     if (which == 0) { if (ensure_structure(ctx, N)) return 1; }
@@ -1034,9 +1154,69 @@ int32_t wgs_upload_gl(wgs_ctx* ctx, const float* L, int64_t M, int32_t N, int32_
     });
 }
 
+int32_t wgs_upload_gl_async(wgs_ctx* ctx, const float* L, int64_t M, int32_t N)
+{
+    cudaSetDevice(ctx->device);
+    upload_fence(ctx);
+    if (M < 0 || N <= 0) return fail(ctx, "bad shape");
+    if (ensure_structure(ctx, N)) return 1;
+    const int K = std::max(ctx->K, 1), ldg = ctx->ldg;
+    // runs of consecutive Beagle columns inside each population slab: one strided DMA each
+    struct Run { int col, ind, len; };
+    std::vector<std::vector<Run>> runs(K);
+    size_t nruns = 0;
+    for (int k = 0; k < K; ++k) {
+        const PopDesc pd = ctx->pops[k];
+        for (int j = 0; j < pd.n; ++j) {
+            const int c = pd.col0 + j, i = ctx->ind_of_col[c];
+            if (!runs[k].empty() && runs[k].back().ind + runs[k].back().len == i) ++runs[k].back().len;
+            else { runs[k].push_back(Run{c, i, 1}); ++nruns; }
+        }
+    }
+    // interleaved ID files (many short runs) are better served by the chunked upload + permutation kernel
+    if (nruns > (size_t)8 * K + 64 || getenv("WGS_UPLOAD_SYNC")) return wgs_upload_gl(ctx, L, M, N, 0);
+    dev_free(ctx, ctx->G[0]);
+    if (dev_alloc(ctx, &ctx->G[0], (size_t)std::max<long>(M, 1) * ldg)) return 1;
+    ctx->Mg[0] = M;
+    float2* G = ctx->G[0];
+    while ((int)ctx->ev_pop.size() < K) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_pop.push_back(e);
+    }
+    std::vector<int> pads;
+    for (int c = 0; c < ldg; ++c) if (ctx->ind_of_col[c] < 0) pads.push_back(c);
+    if (!pads.empty() && M > 0) {
+        DevBuf dp;
+        if (buf_alloc(ctx, dp, pads.size() * sizeof(int))) return 1;
+        CU(cudaMemcpyAsync(dp.p, pads.data(), pads.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH("repack", pad_fill_kernel, grid_for(M * (long)pads.size(), 256, ctx->num_sm * 8), 256, 0, ctx->stream, G, ldg, (long)M,
+               dp.as<int>(), (int)pads.size());
+        CU(cudaStreamSynchronize(ctx->stream));                 // pads in place (and dp released) before any consumer is queued
+    }
+    for (int k = 0; k < K; ++k) {
+        if (M > 0)
+            for (const Run& r : runs[k])
+                CU(cudaMemcpy2DAsync(G + r.col, (size_t)ldg * sizeof(float2), L + 2 * (size_t)r.ind, (size_t)N * sizeof(float2),
+                                     (size_t)r.len * sizeof(float2), (size_t)M, cudaMemcpyHostToDevice, ctx->stream2));
+        CU(cudaEventRecord(ctx->ev_pop[k], ctx->stream2));
+    }
+    ctx->upload_pending = true;
+    return 0;
+}
+
+int32_t wgs_upload_wait(wgs_ctx* ctx)
+{
+    cudaSetDevice(ctx->device);
+    upload_fence(ctx);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int32_t wgs_upload_ad(wgs_ctx* ctx, const int32_t* AD, int64_t M, int32_t N)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (N != ctx->N || M != ctx->Mg[0]) return fail(ctx, "allele-depth matrix must match the GL matrix shape (upload GL first)");
     dev_free(ctx, ctx->AD);
     if (dev_alloc(ctx, &ctx->AD, (size_t)std::max<long>(M, 1) * ctx->ldg)) return 1;
@@ -1060,6 +1240,7 @@ int32_t wgs_upload_ad(wgs_ctx* ctx, const int32_t* AD, int64_t M, int32_t N)
 int32_t wgs_synth(wgs_ctx* ctx, int64_t M, int32_t N, uint64_t seed, float depth, int32_t with_ad)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (ensure_structure(ctx, N)) return 1;
     drop_data(ctx);
     if (dev_alloc(ctx, &ctx->G[0], (size_t)M * ctx->ldg)) return 1;
@@ -1075,6 +1256,7 @@ int32_t wgs_synth(wgs_ctx* ctx, int64_t M, int32_t N, uint64_t seed, float depth
 int32_t wgs_download(wgs_ctx* ctx, int64_t site0, int64_t nsites, float* L_out, int32_t* AD_out)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (site0 < 0 || site0 + nsites > ctx->Mg[0]) return fail(ctx, "site range outside the resident matrix");
     const int N = ctx->N;
     if (L_out) {
@@ -1098,9 +1280,8 @@ int32_t wgs_download(wgs_ctx* ctx, int64_t site0, int64_t nsites, float* L_out, 
     return 0;
 }
 
-int32_t wgs_ref_af(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32_t* iters_out)
+static int ref_af_impl(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32_t* iters_out)
 {
-    cudaSetDevice(ctx->device);
     if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
     if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for reference-panel operators");
     const long M = ctx->M();
@@ -1132,9 +1313,17 @@ int32_t wgs_ref_af(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32
     return 0;
 }
 
+int32_t wgs_ref_af(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32_t* iters_out)
+{
+    cudaSetDevice(ctx->device);
+    upload_fence(ctx);
+    return ref_af_impl(ctx, iter, tole, af_out, iters_out);
+}
+
 int32_t wgs_emMAF(wgs_ctx* ctx, const float* L_pop, int64_t M, int32_t n, int32_t iter, double tole, float* f_out, int32_t* iters_out)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     wgs_ctx* sub = nullptr;
     if (wgs_create(ctx->device, &sub)) return fail(ctx, "%s", wgs_last_error(nullptr));
     sub->timing = false;
@@ -1163,6 +1352,7 @@ int32_t wgs_emMAF(wgs_ctx* ctx, const float* L_pop, int64_t M, int32_t n, int32_
 int32_t wgs_pop_like_partial(wgs_ctx* ctx, const float* af, int32_t K, double* out)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
     if (K <= 0) return fail(ctx, "K must be positive");
     const long M = ctx->M();
@@ -1210,10 +1400,13 @@ int32_t wgs_pop_like_partial(wgs_ctx* ctx, const float* af, int32_t K, double* o
     return 0;
 }
 
-int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, int32_t use_ds, int32_t parts,
-                        double* ll, double* ll_parts, int32_t* iters_out)
+// fused (wgs_ref_af_loo): the leave-one-out EM runs FIRST, population by population as the slabs of an
+// asynchronous upload arrive; the full-data EM + clipping follow once the matrix is complete, and only then
+// are the full-data columns of the LOO state filled in (the EM itself never reads them).
+struct FusedRef { float* af_out; int32_t* iters_out; };
+static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, int32_t use_ds, int32_t parts,
+                    double* ll, double* ll_parts, int32_t* iters_out, const FusedRef* fused)
 {
-    cudaSetDevice(ctx->device);
     if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
     if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for reference-panel operators");
     if (use_ds && !ctx->G[1]) return fail(ctx, "down-sampled GL matrix not resident (wgs_upload_gl which=1)");
@@ -1223,15 +1416,14 @@ int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole
     const int ldf = ldg + (K + 3) / 4 * 4;
     Trace tr("loo");
     DevBuf F, dcols;
-    if (!af_inout && !(ctx->d_af && ctx->af_rows == M && ctx->af_cols == K))
+    if (!fused && !af_inout && !(ctx->d_af && ctx->af_rows == M && ctx->af_cols == K))
         return fail(ctx, "af_inout is NULL but no allele-frequency matrix is resident (call wgs_ref_af first)");
-    if (af_inout) {
+    if (af_inout && !fused) {
         dev_free(ctx, ctx->d_af);
         if (dev_alloc(ctx, &ctx->d_af, (size_t)std::max<long>(M, 1) * K)) return 1;
         ctx->af_rows = M; ctx->af_cols = K;
         CU(cudaMemcpyAsync(ctx->d_af, af_inout, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     }
-    RawBuf dA{ctx->d_af};
     if (buf_alloc(ctx, F, (size_t)M * ldf * sizeof(float)) || buf_alloc(ctx, dcols, K * sizeof(int))) return 1;
     std::vector<int> ident(K);
     for (int k = 0; k < K; ++k) ident[k] = k;
@@ -1245,14 +1437,20 @@ int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole
                ldf - ldg, M, dpad.as<float>());
         CU(cudaStreamSynchronize(ctx->stream));
     }
-    LAUNCH("gather", gather_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, dA.as<float>(), K,
-           dcols.as<int>(), K, F.as<float>(), ldf, ldg, M);
-
     std::vector<int> its_cols;
     CU(cudaStreamSynchronize(ctx->stream));
     tr.lap("alloc+h2d+init");
-    if (run_em_loo(ctx, iter, tole, F.as<float>(), ldf, nullptr, nullptr, its_cols)) return 1;
+    if (run_em_loo(ctx, iter, tole, F.as<float>(), ldf, nullptr, nullptr, its_cols, nullptr,
+                   fused && ctx->upload_pending ? &ctx->ev_pop : nullptr)) return 1;
     tr.lap("em");
+    if (fused) {
+        upload_fence(ctx);                                       // every slab has been waited for on the device already
+        if (ref_af_impl(ctx, iter, tole, fused->af_out, fused->iters_out)) return 1;
+        tr.lap("ref_af");
+    }
+    RawBuf dA{ctx->d_af};
+    LAUNCH("gather", gather_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, dA.as<float>(), K,
+           dcols.as<int>(), K, F.as<float>(), ldf, ldg, M);
     for (int i = 0; i < N; ++i) iters_out[i] = its_cols[ctx->col_of_ind[i]];
 
     // clip to [1/(2n), 1-1/(2n)] with n = n_pop (glassy.py:80-85: n_pop-1 individuals were used)
@@ -1331,9 +1529,29 @@ int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole
     return 0;
 }
 
+int32_t wgs_loo_partial(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, int32_t use_ds, int32_t parts,
+                        double* ll, double* ll_parts, int32_t* iters_out)
+{
+    cudaSetDevice(ctx->device);
+    upload_fence(ctx);
+    return loo_impl(ctx, af_inout, iter, tole, use_ds, parts, ll, ll_parts, iters_out, nullptr);
+}
+
+int32_t wgs_ref_af_loo(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32_t* af_iters_out, float* af_after_loo,
+                       int32_t use_ds, int32_t parts, double* ll, double* ll_parts, int32_t* loo_iters_out)
+{
+    cudaSetDevice(ctx->device);                                  // no upload fence: the slabs are waited for one by one
+    if (!af_iters_out || !ll || !loo_iters_out) return fail(ctx, "af_iters_out, ll and loo_iters_out must not be NULL");
+    FusedRef fr{af_out, af_iters_out};
+    int rc = loo_impl(ctx, af_after_loo, iter, tole, use_ds, parts, ll, ll_parts, loo_iters_out, &fr);
+    upload_fence(ctx);                                           // error paths included: the host matrix is free again on return
+    return rc;
+}
+
 int32_t wgs_fisher_partial(wgs_ctx* ctx, const float* af, float* f_obs, float* ne_obs, double* ne_ind_sum)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
     if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for reference-panel operators");
     const long M = ctx->M();
@@ -1387,6 +1605,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
                    int32_t ind_start, int32_t ind_end, int32_t iter, double tole, wgs_zrow* out)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
     if (!ctx->AD || ctx->M_ad != ctx->M()) return fail(ctx, "no allele depths resident (wgs_upload_ad)");
     if (!ctx->pops_set && mode != 2) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for the z-score operators");
@@ -1618,6 +1837,7 @@ int32_t wgs_zkeep_one(wgs_ctx* ctx, int32_t ind, int32_t n_classes, const int32_
                       int32_t* keep_out, int64_t cap, int64_t* n_kept)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (!ctx->G[0] || !ctx->AD) return fail(ctx, "GL matrix and allele depths must be resident");
     if (ind < 0 || ind >= ctx->N) return fail(ctx, "individual %d outside [0,%d)", ind, ctx->N);
     const long M = ctx->M();
@@ -1663,6 +1883,7 @@ int32_t wgs_zmoments_list(wgs_ctx* ctx, int32_t ind, const int32_t* L_keep, int6
                           float* W_obs_out, float* W_l_out, float* W_var_out)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (!ctx->G[0] || !ctx->AD) return fail(ctx, "GL matrix and allele depths must be resident");
     if (ind < 0 || ind >= ctx->N) return fail(ctx, "individual %d outside [0,%d)", ind, ctx->N);
     for (int64_t e = 0; e < mk; ++e) if (L_keep[e] < 0 || L_keep[e] >= ctx->M()) return fail(ctx, "L_keep[%lld] outside the matrix", (long long)e);
@@ -1702,6 +1923,7 @@ int32_t wgs_zscore_classes(wgs_ctx* ctx, int32_t ind, int32_t max_rows, int32_t*
 int32_t wgs_debug_stream(wgs_ctx* ctx, int32_t mode, double* ms_out, double* bytes_out)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
     const long M = ctx->M();
     const int K = std::max(ctx->K, 1);
@@ -1733,6 +1955,7 @@ int64_t wgs_launch_count(const wgs_ctx* ctx) { return ctx->launches; }
 int32_t wgs_timing_reset(wgs_ctx* ctx, int32_t enable)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     fold_timing(ctx);
     ctx->tdone.clear();
     ctx->timing = enable != 0;
@@ -1742,6 +1965,7 @@ int32_t wgs_timing_reset(wgs_ctx* ctx, int32_t enable)
 int32_t wgs_timing_get(wgs_ctx* ctx, const char* name, double* ms, int64_t* launches)
 {
     cudaSetDevice(ctx->device);
+    upload_fence(ctx);
     fold_timing(ctx);
     auto it = ctx->tdone.find(name);
     *ms = it == ctx->tdone.end() ? 0.0 : it->second.ms;

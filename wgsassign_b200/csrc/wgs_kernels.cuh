@@ -151,6 +151,18 @@ __global__ void repack_kernel(const float2* __restrict__ stage, int N, float2* _
     }
 }
 
+// G[s][pad_cols[j]] <- (0,0) for the padding columns of the population slabs: the asynchronous upload
+// copies the individuals' columns straight into G (strided DMA), which leaves the pads to this kernel
+__global__ void pad_fill_kernel(float2* __restrict__ G, int ldg, long M, const int* __restrict__ pad_cols, int npad)
+{
+    const long total = M * (long)npad;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long s = e / npad;
+        const int j = (int)(e - s * npad);
+        G[s * (long)ldg + pad_cols[j]] = make_float2(0.f, 0.f);
+    }
+}
+
 // inverse of repack for wgs_download: G rows -> reference layout
 __global__ void unpack_kernel(const float2* __restrict__ G, int ldg, const int* __restrict__ col_of_ind, int N,
                               float2* __restrict__ out, long rows)
@@ -874,7 +886,7 @@ loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar, mbar_g[2];
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int t = threadIdx.x, lane = t & 31;
     const int W = blockDim.x >> 5;
     const int wcols = W * 32;                                               // GL columns of this block
     float4* Hq = reinterpret_cast<float4*>(smem_raw);                       // [TS][ldf] planes ((1-a)^2, 2a(1-a), a^2, -)
@@ -1736,6 +1748,12 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
         if (4 * ti + 2 >= n) act &= 3u;
         if (4 * ti + 3 >= n) act &= 7u;
     }
+    // a launch that finds every problem of the population frozen (the host queues one iteration ahead of the
+    // decisions it reads back) has nothing to stage or compute
+    if (__syncthreads_or(act != 0u) == 0) {
+        if (t < n) partials[(long)blockIdx.x * ldg + col0 + t] = 0.0;
+        return;
+    }
     const float inv_div = 1.0f / (float)(n - 1);
     float ssq[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -1841,47 +1859,53 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
     }
 }
 
-// ssq[p] = sum over blocks (fixed order) of partials[block][p]
-__global__ void em_ssq_reduce_kernel(const double* __restrict__ partials, int nblocks, int np, int ld,
-                                     double* __restrict__ ssq)
+// ssq[p] = sum over blocks of partials[block][p], in a fixed order: one warp per problem, lane l adds blocks
+// l, l+32, ... in sequence, then a shuffle tree - the same bits for a given number of blocks, and a few
+// microseconds instead of one thread walking every block (this kernel sits between two EM iterations).
+__global__ void __launch_bounds__(256)
+em_ssq_reduce_kernel(const double* __restrict__ partials, int nblocks, int np, int ld, double* __restrict__ ssq)
 {
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
-        double v = 0.0;
-        int b = 0;
-        for (; b + 8 <= nblocks; b += 8) {                      // 8 independent loads in flight, fixed add order
-            double x[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = partials[(long)(b + u) * ld + p];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v += x[u];
-        }
-        for (; b < nblocks; ++b) v += partials[(long)b * ld + p];
-        ssq[p] = v;
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= np) return;
+    double v = 0.0;
+    int b = lane;
+    for (; b + 96 < nblocks; b += 128) {                        // 4 independent loads in flight, fixed add order
+        const double x0 = partials[(long)b * ld + p], x1 = partials[(long)(b + 32) * ld + p];
+        const double x2 = partials[(long)(b + 64) * ld + p], x3 = partials[(long)(b + 96) * ld + p];
+        v += x0; v += x1; v += x2; v += x3;
     }
+    for (; b < nblocks; b += 32) v += partials[(long)b * ld + p];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) ssq[p] = v;
 }
 
 // Stop rule of emMAF.py:21-25 with rmse1d's float divide / double sqrt (emMAF_cy.pyx:32-33).
-// count[p] = number of sites in problem p's sum.  Single block.
+// count[p] = number of sites in problem p's sum.  Single block.  result (mapped pinned host memory):
+// [0] = problems still active, [1 + p] = the updated flag of problem p.
 __global__ void em_decide_kernel(const double* __restrict__ ssq, const double* __restrict__ count, double count_all,
                                  int np, double tole, int iteration,
-                                 int* __restrict__ active, int* __restrict__ iters, int* __restrict__ n_active)
+                                 int* __restrict__ active, int* __restrict__ iters, int* __restrict__ result)
 {
     __shared__ int sh_cnt;
     if (threadIdx.x == 0) sh_cnt = 0;
     __syncthreads();
     int mine = 0;
     for (int p = threadIdx.x; p < np; p += blockDim.x) {
-        if (!active[p]) continue;
-        double cnt = count ? count[p] : count_all;
-        float res = (float)ssq[p];
-        res = res / (float)cnt;
-        double diff = sqrt((double)res);
-        if (diff < tole) { active[p] = 0; iters[p] = iteration; }
-        else ++mine;
+        int a = active[p];
+        if (a) {
+            double cnt = count ? count[p] : count_all;
+            float res = (float)ssq[p];
+            res = res / (float)cnt;
+            double diff = sqrt((double)res);
+            if (diff < tole) { a = 0; active[p] = 0; iters[p] = iteration; }
+            else ++mine;
+        }
+        result[1 + p] = a;
     }
-    atomicAdd(&sh_cnt, mine);
+    if (mine) atomicAdd(&sh_cnt, mine);
     __syncthreads();
-    if (threadIdx.x == 0) *n_active = sh_cnt;
+    if (threadIdx.x == 0) result[0] = sh_cnt;
 }
 
 __global__ void fill_kernel(float* __restrict__ p, long n, float v)
