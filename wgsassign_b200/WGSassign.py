@@ -160,8 +160,18 @@ class _Run:
         pops = np.unique(IDs[:, 1])
         assert (self.L.shape[1] // 2 == IDs.shape[0]), "Number of individuals in beagle and reference ID file do not match!"
         pop_of, _ = session.pops_from_ids(IDs)
-        ctx = session.context(self.L, pop_of, len(pops))
-        af, iters = ctx.ref_af(a.maf_iter, a.maf_tole)
+        # with --loo both operators run as one fused device call whose leave-one-out EM overlaps the upload
+        ctx = session.context(self.L, pop_of, len(pops), async_upload=bool(a.loo))
+        loo_out = None
+        if a.loo:
+            if self.L_ds is not None:
+                session.with_downsampled(ctx, self.L_ds)
+            af, iters, ll, ll_parts, loo_iters = glassy.loo_fused(ctx, IDs, a.maf_iter, a.maf_tole,
+                                                                  downsampled=self.L_ds is not None,
+                                                                  num_partitions=a.partition_sites)
+            loo_out = (ll, ll_parts, loo_iters)
+        else:
+            af, iters = ctx.ref_af(a.maf_iter, a.maf_tole)
         for it in iters:
             if it > 0:
                 self.say("EM (MAF) converged at iteration: " + str(int(it)))
@@ -195,8 +205,13 @@ class _Run:
                 print("Save individual effective sample sizes as " + str(a.out) + ".ne_ind.txt")
         if a.loo:
             self.say("Performing leave-one-out cross validation.")
-            ll, ll_parts = glassy.loo(self.L, af, IDs, a.threads, a.maf_iter, a.maf_tole, downsampled_L=self.L_ds,
-                                      num_partitions=a.partition_sites)
+            ll, ll_parts, loo_iters = loo_out
+            self.say(str(IDs.shape[0]) + " individuals to assign to " + str(len(pops)) + " populations")
+            if self.L_ds is not None:
+                self.say("Using downsampled GLs for likelihood evaluation in LOO assignment.")
+            for it in loo_iters:
+                if it > 0:
+                    self.say("EM (MAF) converged at iteration: " + str(int(it)))
             if self.rank0:
                 suffix = "_downsampled" if self.L_ds is not None else ""
                 outfile = "%s.pop_like_LOO%s.tsv" % (a.out, suffix)

@@ -1571,14 +1571,36 @@ int32_t wgs_fisher_partial(wgs_ctx* ctx, const float* af, float* f_obs, float* n
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fisher_kernel, R * kEmT, smem));
     long ntiles = (M + R - 1) / R;
     int nblocks = (int)std::max<long>(1, std::min<long>(ntiles, ((long)ctx->num_sm * std::max(occ, 1)) / K));
+    // barrier-free register-tile kernel (fisher2) for populations of up to 512 individuals
+    int tpr = 2;
+    while (tpr < 32 && tpr * kFisherQ < (nmax + 1) / 2) tpr *= 2;
+    const bool v2 = getenv("WGS_FISHER_V1") == nullptr && tpr * kFisherQ >= (nmax + 1) / 2;
+    const size_t smem2 = (size_t)(256 / tpr) * 2 * tpr * kFisherQ * sizeof(float);
+    if (v2) {
+        int occ2 = 1;
+#define FISHER2_OCC(T) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, fisher2_kernel<T>, 256, smem2))
+        if (tpr == 2) FISHER2_OCC(2); else if (tpr == 4) FISHER2_OCC(4); else if (tpr == 8) FISHER2_OCC(8);
+        else if (tpr == 16) FISHER2_OCC(16); else FISHER2_OCC(32);
+#undef FISHER2_OCC
+        const long ntiles2 = (M + 256 / tpr - 1) / (256 / tpr);
+        nblocks = (int)std::max<long>(1, std::min<long>(ntiles2, ((long)ctx->num_sm * std::max(occ2, 1)) / K));
+    }
     DevBuf dA, dF, dNe, partials, sums;
     if (buf_alloc(ctx, dA, (size_t)M * K * sizeof(float)) || buf_alloc(ctx, dF, (size_t)M * K * sizeof(float)) ||
         buf_alloc(ctx, dNe, (size_t)M * K * sizeof(float)) || buf_alloc(ctx, partials, (size_t)nblocks * ldg * sizeof(double)) ||
         buf_alloc(ctx, sums, ldg * sizeof(double))) return 1;
     CU(cudaMemcpyAsync(dA.p, af, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(partials.p, 0, (size_t)nblocks * ldg * sizeof(double), ctx->stream));   // pad columns are never written
-    LAUNCH("fisher", fisher_kernel, dim3(nblocks, K), R * kEmT, smem, ctx->stream, ctx->G[0], ldg, M, ctx->d_pops, K, dA.as<float>(),
-           dF.as<float>(), dNe.as<float>(), row16, accw_ld, partials.as<double>());
+#define FISHER2_LAUNCH(T)                                                                                               \
+    LAUNCH("fisher", fisher2_kernel<T>, dim3(nblocks, K), 256, smem2, ctx->stream, ctx->G[0], ldg, M, ctx->d_pops, K, dA.as<float>(), \
+           dF.as<float>(), dNe.as<float>(), partials.as<double>())
+    if (v2) {
+        if (tpr == 2) FISHER2_LAUNCH(2); else if (tpr == 4) FISHER2_LAUNCH(4); else if (tpr == 8) FISHER2_LAUNCH(8);
+        else if (tpr == 16) FISHER2_LAUNCH(16); else FISHER2_LAUNCH(32);
+    } else
+        LAUNCH("fisher", fisher_kernel, dim3(nblocks, K), R * kEmT, smem, ctx->stream, ctx->G[0], ldg, M, ctx->d_pops, K, dA.as<float>(),
+               dF.as<float>(), dNe.as<float>(), row16, accw_ld, partials.as<double>());
+#undef FISHER2_LAUNCH
     add_work(ctx, "fisher", (double)M * ctx->N * 8.0 + (double)M * K * 12.0, (double)M * ctx->N);
     LAUNCH("reduce", reduce_partials_kernel, grid_for(ldg, 256, 64), 256, 0, ctx->stream, partials.as<double>(), nblocks, (long)ldg,
            sums.as<double>());
@@ -1615,6 +1637,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     const long M = ctx->M();
     const int ldg = ctx->ldg, N = ctx->N;
     const double e = 0.01;                                       // WGSassign.py:350, :430
+    Trace tr("zscore");
 
     std::vector<unsigned char> sel(ldg, 0);
     for (int i = ind_start; i < ind_end; ++i) sel[ctx->col_of_ind[i]] = 1;
@@ -1633,25 +1656,47 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         if (c.sites_per_block > cap) { c.sites_per_block = cap; c.gy = (int)((M + cap - 1) / cap); }
     }
     const double pairs = (double)M * (ind_end - ind_start);
-    // class counts and float32 class means, per (column, class)
-    std::vector<long long> ccnt(tab_n, 0);
-    std::vector<float> cmean(tab_n * 3, 0.f);
     // reference-faithful sequential float32 class means up to 2^18 sites on one GPU; the exact,
     // order-independent tally above that and whenever sites are sharded (see wgs_zscore.cuh)
     const char* env_exact = getenv("WGS_Z_EXACT_MEANS");
     bool exact_means = ctx->fn != nullptr || ctx->Mtot() > (1L << 18);
     if (env_exact && env_exact[0] == '1') exact_means = true;
     if (env_exact && env_exact[0] == '0' && !ctx->fn) exact_means = false;
+    DevBuf dmaxd;
+    if (buf_alloc(ctx, dmaxd, sizeof(int))) return 1;
+    CU(cudaMemsetAsync(dmaxd.p, 0, sizeof(int), ctx->stream));
     if (exact_means) {
         // order-independent fixed-point tally (shardable)
         LAUNCH("ztally", ztally_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
                c.wx, c.sites_per_block, dtable.as<ZTally>(), ddeep.as<unsigned long long>());
-        add_work(ctx, "ztally", pairs * 10.0, pairs);
-        std::vector<ZTally> table(tab_n);
-        CU(cudaMemcpyAsync(table.data(), dtable.p, tab_n * sizeof(ZTally), cudaMemcpyDeviceToHost, ctx->stream));
+        LAUNCH("zaux", zmaxdepth_kernel<ZTally>, ctx->num_sm * 4, 256, 0, ctx->stream, dtable.as<ZTally>(), (long)tab_n, dmaxd.as<int>());
+    } else {
+        // reference-faithful: sequential float32 sums in site order, float32 divide (numpy's float32 mean)
+        LAUNCH("ztally", ztally_seq_kernel, (ldg + 31) / 32, 32, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
+               dtable.as<ZTallyF>(), ddeep.as<unsigned long long>());
+        LAUNCH("zaux", zmaxdepth_kernel<ZTallyF>, ctx->num_sm * 4, 256, 0, ctx->stream, dtable.as<ZTallyF>(), (long)tab_n, dmaxd.as<int>());
+    }
+    add_work(ctx, "ztally", pairs * 10.0, pairs);
+    // Only the classes up to the deepest observed depth travel and are scanned: compact host tables [ldg][ncls].
+    // Under site sharding every rank must agree on the table shape, so the full table is kept there.
+    int dmax = kZDepthCap;
+    if (!ctx->fn) {
+        CU(cudaMemcpyAsync(&dmax, dmaxd.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        if (ctx->fn) ctx->fn(table.data(), (int64_t)tab_n * 4, WGS_I64, ctx->user);
-        for (size_t g = 0; g < tab_n; ++g) {
+        dmax = std::max(1, std::min(dmax, kZDepthCap));
+    }
+    const int ncls = (dmax + 1) * (dmax + 2) / 2;
+    const size_t ctab_n = (size_t)ldg * ncls;
+    // class counts and float32 class means, per (column, class)
+    std::vector<long long> ccnt(ctab_n, 0);
+    std::vector<float> cmean(ctab_n * 3, 0.f);
+    if (exact_means) {
+        std::vector<ZTally> table(ctab_n);
+        CU(cudaMemcpy2DAsync(table.data(), (size_t)ncls * sizeof(ZTally), dtable.p, (size_t)kZClasses * sizeof(ZTally),
+                             (size_t)ncls * sizeof(ZTally), (size_t)ldg, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->fn) ctx->fn(table.data(), (int64_t)ctab_n * 4, WGS_I64, ctx->user);
+        for (size_t g = 0; g < ctab_n; ++g) {
             ccnt[g] = table[g].cnt;
             if (table[g].cnt > 0) {
                 double n = (double)table[g].cnt;
@@ -1661,14 +1706,11 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
             }
         }
     } else {
-        // reference-faithful: sequential float32 sums in site order, float32 divide (numpy's float32 mean)
-        LAUNCH("ztally", ztally_seq_kernel, (ldg + 31) / 32, 32, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
-               dtable.as<ZTallyF>(), ddeep.as<unsigned long long>());
-        add_work(ctx, "ztally", pairs * 10.0, pairs);
-        std::vector<ZTallyF> table(tab_n);
-        CU(cudaMemcpyAsync(table.data(), dtable.p, tab_n * sizeof(ZTallyF), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<ZTallyF> table(ctab_n);
+        CU(cudaMemcpy2DAsync(table.data(), (size_t)ncls * sizeof(ZTallyF), dtable.p, (size_t)kZClasses * sizeof(ZTallyF),
+                             (size_t)ncls * sizeof(ZTallyF), (size_t)ldg, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        for (size_t g = 0; g < tab_n; ++g) {
+        for (size_t g = 0; g < ctab_n; ++g) {
             ccnt[g] = table[g].cnt;
             if (table[g].cnt > 0) {
                 float n = (float)table[g].cnt;
@@ -1677,53 +1719,60 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         }
     }
 
+    tr.lap("tally+d2h");
     // ---- class decisions on the host (zscore.py:23-39, :63-79): a few hundred rows per individual ----
-    std::vector<signed char> kmax(tab_n, -1);
-    std::vector<float> kmean(tab_n, 0.f);
-    std::vector<float4> zlike(tab_n, make_float4(0.f, 0.f, 0.f, 0.f)), zfac(tab_n, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<signed char> kmax(ctab_n, -1);
+    std::vector<float> kmean(ctab_n, 0.f);
+    std::vector<float4> zlike(ctab_n, make_float4(0.f, 0.f, 0.f, 0.f)), zfac(ctab_n, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<float4> fac_of_class(ncls);                     // binomial read probabilities: the same for every individual
+    for (int d = 0; d <= dmax; ++d)
+        for (int alt = 0; alt <= d; ++alt) {
+            const int ref = d - alt;
+            const double comb = binom(d, alt);
+            fac_of_class[zclass_id(ref, alt)] = make_float4((float)(comb * std::pow(1.0 - e, ref) * std::pow(e, alt)), (float)(comb * std::pow(0.5, d)),
+                                                            (float)(comb * std::pow(1.0 - e, alt) * std::pow(e, ref)), 0.f);
+        }
     ctx->zclasses.assign(N, std::vector<int>());
     ctx->ztable.assign(N, std::vector<float>());
     std::vector<int> n_classes(N, 0);
     for (int i = ind_start; i < ind_end; ++i) {
         const int col = ctx->col_of_ind[i];
-        const long long* t = ccnt.data() + (size_t)col * kZClasses;
-        std::vector<int> ids;                                     // classes passing the count filter
+        const long long* t = ccnt.data() + (size_t)col * ncls;
+        int n_pass = 0;                                           // classes passing the count filter
         int per_depth[kZDepthCap + 1] = {0};
-        for (int d = 0; d <= kZDepthCap; ++d)
+        for (int d = 0; d <= dmax; ++d)
             for (int alt = 0; alt <= d; ++alt) {
                 int id = zclass_id(d - alt, alt);
                 if (t[id] <= 0) continue;
                 bool pass = single_read ? (d == 1) : (t[id] > n_threshold && d != 0);
-                if (pass) { ids.push_back(id); ++per_depth[d]; }
+                if (pass) { ++n_pass; ++per_depth[d]; }
             }
-        if (ids.empty()) return fail(ctx, "No loci were kept! Too stringent filtering?");
-        if (ids.size() == 1) return fail(ctx, "Not enough loci were kept! Too stringent filtering?");
+        if (n_pass == 0) return fail(ctx, "No loci were kept! Too stringent filtering?");
+        if (n_pass == 1) return fail(ctx, "Not enough loci were kept! Too stringent filtering?");
         auto& rows = ctx->zclasses[i];
-        for (int d = 0; d <= kZDepthCap; ++d) {
+        for (int d = 0; d <= dmax; ++d) {
             if (!(d < per_depth[d])) continue;                   // zscore.py:38: depth kept iff all d+1 splits present
             for (int alt = 0; alt <= d; ++alt) {
                 int ref = d - alt, id = zclass_id(ref, alt);
-                size_t g = (size_t)col * kZClasses + id;
+                size_t g = (size_t)col * ncls + id;
                 float m0 = cmean[3 * g], m1 = cmean[3 * g + 1], m2 = cmean[3 * g + 2];
                 int mx = 0; float mv = m0;
                 if (m1 > mv) { mx = 1; mv = m1; }
                 if (m2 > mv) { mx = 2; mv = m2; }
                 kmax[g] = (signed char)mx; kmean[g] = mv;
                 zlike[g] = make_float4(m0, m1, m2, 0.f);
-                double comb = binom(d, alt);
-                zfac[g] = make_float4((float)(comb * std::pow(1.0 - e, ref) * std::pow(e, alt)), (float)(comb * std::pow(0.5, d)),
-                                      (float)(comb * std::pow(1.0 - e, alt) * std::pow(e, ref)), 0.f);
+                zfac[g] = fac_of_class[id];
                 rows.push_back(ref); rows.push_back(alt); rows.push_back(d); rows.push_back((int)t[id]);
                 ++n_classes[i];
             }
         }
         {   // every observed class, for the AD_summary drop-in (zscore.py:20-22)
             auto& tab = ctx->ztable[i];
-            for (int d = 0; d <= kZDepthCap; ++d)
+            for (int d = 0; d <= dmax; ++d)
                 for (int alt = 0; alt <= d; ++alt) {
                     int id = zclass_id(d - alt, alt);
                     if (t[id] <= 0) continue;
-                    size_t g = (size_t)col * kZClasses + id;
+                    size_t g = (size_t)col * ncls + id;
                     float row[7] = {(float)(d - alt), (float)alt, (float)t[id], cmean[3 * g], cmean[3 * g + 1], cmean[3 * g + 2],
                                     kmax[g] >= 0 ? 1.f : 0.f};
                     tab.insert(tab.end(), row, row + 7);
@@ -1732,14 +1781,20 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         if (n_classes[i] == 0 && mode != 2) return fail(ctx, "individual %d: no read depth has all of its allele-count splits (zscore.py:36-39 leaves AD_array empty)", i);
     }
 
+    tr.lap("class decisions");
     DevBuf dkmax, dkmean, dlike, dfac, dkeep, dkept;
     if (buf_alloc(ctx, dkmax, tab_n) || buf_alloc(ctx, dkmean, tab_n * sizeof(float)) || buf_alloc(ctx, dlike, tab_n * sizeof(float4)) ||
         buf_alloc(ctx, dfac, tab_n * sizeof(float4)) || buf_alloc(ctx, dkeep, (size_t)std::max<long>(M, 1) * ldg) ||
         buf_alloc(ctx, dkept, ldg * sizeof(unsigned long long))) return 1;
-    CU(cudaMemcpyAsync(dkmax.p, kmax.data(), tab_n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dkmean.p, kmean.data(), tab_n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dlike.p, zlike.data(), tab_n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dfac.p, zfac.data(), tab_n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    // compact host tables -> the dense device layout; classes deeper than dmax do not occur ("not kept" = -1)
+    CU(cudaMemsetAsync(dkmax.p, 0xFF, tab_n, ctx->stream));
+    CU(cudaMemcpy2DAsync(dkmax.p, (size_t)kZClasses, kmax.data(), (size_t)ncls, (size_t)ncls, (size_t)ldg, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpy2DAsync(dkmean.p, (size_t)kZClasses * sizeof(float), kmean.data(), (size_t)ncls * sizeof(float), (size_t)ncls * sizeof(float),
+                         (size_t)ldg, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpy2DAsync(dlike.p, (size_t)kZClasses * sizeof(float4), zlike.data(), (size_t)ncls * sizeof(float4), (size_t)ncls * sizeof(float4),
+                         (size_t)ldg, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpy2DAsync(dfac.p, (size_t)kZClasses * sizeof(float4), zfac.data(), (size_t)ncls * sizeof(float4), (size_t)ncls * sizeof(float4),
+                         (size_t)ldg, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(dkept.p, 0, ldg * sizeof(unsigned long long), ctx->stream));
     LAUNCH("zkeep", zkeep_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
            dkmax.as<signed char>(), dkmean.as<float>(), c.wx, c.sites_per_block, dkeep.as<unsigned char>(), dkept.as<unsigned long long>());
@@ -1749,6 +1804,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->fn) ctx->fn(kept.data(), ldg, WGS_I64, ctx->user);
 
+    tr.lap("tables h2d+keep");
     if (mode == 2) {                                             // preparation only: tallies, class tables, kept-site counts
         for (int i = ind_start; i < ind_end; ++i) {
             wgs_zrow& r = out[i - ind_start];
@@ -1791,6 +1847,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         for (int col = 0; col < ldg; ++col) afcol[col] = col;
     }
     CU(cudaMemcpyAsync(dafcol.p, afcol.data(), ldg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    tr.lap("af / loo em");
 
     DevBuf partials, sums;
     const size_t np3 = (size_t)ldg * 3;
@@ -1805,6 +1862,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     CU(cudaMemcpyAsync(deep.data(), ddeep.p, ldg * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
+    tr.lap("moments");
     if (ctx->fn) ctx->fn(h.data(), (int64_t)np3, WGS_F64, ctx->user);
     ctx->z_deep_sites = 0;
     for (int col = 0; col < ldg; ++col) ctx->z_deep_sites += (long)deep[col];

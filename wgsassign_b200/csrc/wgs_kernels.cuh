@@ -1978,13 +1978,21 @@ __global__ void gather_cols_kernel(const float* __restrict__ src, int lds, const
 // Per-individual sums live in a per-warp private shared-memory row (no atomics), reduced
 // over warps then over blocks in fixed order.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ float fisher_term(float g0, float g1, float th, float om)
+// H = ((1-th)^2, 2 th (1-th), th^2) is per (site, population): hoisted out of the individual loop.  The two
+// IEEE divisions of the reference (n1/u, n2/u) are one MUFU reciprocal + one Newton step shared by both
+// quotients (~1 ulp): the correctly-rounded __fdiv_rn pair was 3/4 of this kernel's instructions and kept an
+// HBM-bound pass issue-bound (ncu: 120 instructions per term, 20 % of DRAM bandwidth).
+struct FisherH { float h0, h1, h2, th; };
+__device__ __forceinline__ FisherH fisher_h(float th, float om) { return FisherH{om * om, 2.0f * th * om, th * th, th}; }
+__device__ __forceinline__ float fisher_term(float g0, float g1, const FisherH& H)
 {
     float g2 = third_gl(g0, g1);
-    float u = fmaf(g0, om * om, fmaf(g1, 2.0f * th * om, g2 * th * th));
+    float u = fmaf(g0, H.h0, fmaf(g1, H.h1, g2 * H.h2));
     float n1 = 2.0f * ((g0 + g2) - 2.0f * g1);
-    float n2 = fmaf(th, n1, 2.0f * (g1 - g0));
-    float x = __fdiv_rn(n2, u), y = __fdiv_rn(n1, u);
+    float n2 = fmaf(H.th, n1, 2.0f * (g1 - g0));
+    float r = fast_rcp(u);
+    r = r * fmaf(-u, r, 2.0f);
+    float x = n2 * r, y = n1 * r;
     return fmaf(x, x, -y);
 }
 
@@ -2039,6 +2047,7 @@ fisher_kernel(const float2* __restrict__ G, int ldg, long M,
         if (live) th = __ldg(&A[s * K + k]);
         const float om = 1.0f - th;
         const float w = live ? 0.5f * th * om : 0.f;
+        const FisherH H = fisher_h(th, om);
         mbar_wait(&mbar[buf], (unsigned)((it >> 1) & 1));
         const float4* row = ring + buf * stage + (size_t)r * row16;
         float sum = 0.f;
@@ -2047,8 +2056,8 @@ fisher_kernel(const float2* __restrict__ G, int ldg, long M,
             float ta = 0.f, tb = 0.f;
             if (live && q < cpr) {
                 float4 v = row[q];
-                ta = fisher_term(v.x, v.y, th, om);
-                if (2 * q + 1 < pd.n) tb = fisher_term(v.z, v.w, th, om);
+                ta = fisher_term(v.x, v.y, H);
+                if (2 * q + 1 < pd.n) tb = fisher_term(v.z, v.w, H);
             }
             sum += ta + tb;
             float ia = ta * w, ib = tb * w;                 // this row's contribution to individuals 2q, 2q+1
@@ -2073,6 +2082,86 @@ fisher_kernel(const float2* __restrict__ G, int ldg, long M,
         double v = 0.0;
         for (int w2 = 0; w2 < nwarp; ++w2) v += (double)accw[(size_t)w2 * accw_ld + j];
         ind_partials[(long)blockIdx.x * ldg + pd.col0 + j] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// fisher2: the same pass without shared-memory staging or block barriers.  The TMA-tile version above
+// spent its time at the per-tile __syncthreads (ncu: barrier 2.5 + wait 1.9 stall cycles per issue, 20-30 % of
+// HBM) - halving its instruction count did not move it.  Here TPR adjacent lanes own a site row and read it
+// straight from global memory, kFisherQ 16-byte loads per thread all in flight before the first use (a row is
+// one contiguous, sector-aligned run, so the TPR lanes of one load cover whole sectors); the row sum is a
+// shuffle over the TPR lanes, and the per-individual sums are REGISTER accumulators (a thread always serves
+// the same 2 x kFisherQ individuals), reduced over the rows of the block once, at the end, in fixed order.
+// ---------------------------------------------------------------------------------------
+constexpr int kFisherQ = 8;
+template <int TPR>
+__global__ void __launch_bounds__(256)
+fisher2_kernel(const float2* __restrict__ G, int ldg, long M,
+               const PopDesc* __restrict__ pops, int K,
+               const float* __restrict__ A,                 // [M][K]
+               float* __restrict__ f_obs, float* __restrict__ ne_obs,   // [M][K]
+               double* __restrict__ ind_partials)           // [gridDim.x][ldg]
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* red = reinterpret_cast<float*>(smem_raw);      // [R][2 * TPR * kFisherQ]
+    constexpr int R = 256 / TPR;
+    constexpr int RW = 2 * TPR * kFisherQ;
+    const int k = blockIdx.y;
+    const int t = threadIdx.x, r = t / TPR, h = t % TPR;
+    const PopDesc pd = pops[k];
+    const int cpr = (pd.n + 1) >> 1;                      // 16-byte units (pairs of individuals) per row
+    const long ntiles = (M + R - 1) / R;
+    float ia[kFisherQ], ib[kFisherQ];
+#pragma unroll
+    for (int j = 0; j < kFisherQ; ++j) { ia[j] = 0.f; ib[j] = 0.f; }
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long s = tile * R + r;
+        const bool live = s < M;
+        float4 v[kFisherQ];
+        const float4* row = reinterpret_cast<const float4*>(G + (live ? s : 0) * (long)ldg + pd.col0);
+#pragma unroll
+        for (int j = 0; j < kFisherQ; ++j) {
+            const int q = h + j * TPR;
+            v[j] = make_float4(1.f, 0.f, 1.f, 0.f);
+            if (live && q < cpr) v[j] = ld_stream4(row + q);
+        }
+        float th = 0.5f;
+        if (live) th = __ldg(&A[s * K + k]);
+        const float om = 1.0f - th;
+        const float w = live ? 0.5f * th * om : 0.f;
+        const FisherH H = fisher_h(th, om);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kFisherQ; ++j) {
+            const int q = h + j * TPR;
+            float ta = 0.f, tb = 0.f;
+            if (live && q < cpr) {
+                ta = fisher_term(v[j].x, v[j].y, H);
+                if (2 * q + 1 < pd.n) tb = fisher_term(v[j].z, v[j].w, H);
+            }
+            sum += ta + tb;
+            ia[j] = fmaf(ta, w, ia[j]);
+            ib[j] = fmaf(tb, w, ib[j]);
+        }
+#pragma unroll
+        for (int o = 1; o < TPR; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (live && h == 0) {
+            f_obs[s * K + k] = sum;
+            ne_obs[s * K + k] = 0.5f * sum * th * om;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kFisherQ; ++j) {
+        const int q = h + j * TPR;
+        red[r * RW + 2 * q] = ia[j];
+        red[r * RW + 2 * q + 1] = ib[j];
+    }
+    __syncthreads();
+    for (int j = t; j < pd.n; j += blockDim.x) {
+        double vsum = 0.0;
+        for (int rr = 0; rr < R; ++rr) vsum += (double)red[rr * RW + j];
+        ind_partials[(long)blockIdx.x * ldg + pd.col0 + j] = vsum;
     }
 }
 

@@ -195,6 +195,24 @@ ztally_seq_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
     if (ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
 }
 
+// Deepest read depth with a non-empty class in the tally table: the host then moves and scans only the
+// classes up to that depth (66 instead of 861 per individual at 10 reads) - the full-table copies and loops
+// were 40 % of a z-score call at 2,000 individuals.
+template <class T>
+__global__ void zmaxdepth_kernel(const T* __restrict__ table, long n, int* __restrict__ out)
+{
+    int best = 0;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        if (table[e].cnt > 0) {
+            const int id = (int)(e % kZClasses);
+            int d = 0;
+            while ((d + 1) * (d + 2) / 2 <= id) ++d;
+            best = max(best, d);
+        }
+    }
+    if (best > 0) atomicMax(out, best);
+}
+
 // Per-(individual, class) decision tables built on the host from the tallies:
 //   kmax[col][id]  : -1 class not kept, else argmax of the class mean (zscore.py:53)
 //   kmean[col][id] : the class mean at that argmax (float32)

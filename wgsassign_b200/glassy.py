@@ -37,3 +37,15 @@ def loo(L, af, IDs, t, maf_iter, maf_tole, downsampled_L=None, num_partitions=1)
     dist.allreduce_sum(llp)
     af[...] = af_work                                   # in-place side effect (glassy.py:89)
     return ll.astype(np.float32), llp.astype(np.float32)
+
+
+def loo_fused(ctx, IDs, maf_iter, maf_tole, downsampled=False, num_partitions=1):
+    """`--get_reference_af --loo` as ONE device call (`Context.ref_af_loo`): the per-population EM of
+    WGSassign.py:225-242 and glassy.loo (glassy.py:47-112) on a context whose matrix may still be
+    uploading.  Returns (af float32 [M,K] as saved to .pop_af.npy, em iterations [K],
+    logl_mat, logl_parts_mat float32, loo iterations [N]); the caller prints the messages in the
+    reference's order."""
+    af, its, ll, llp, lits, _ = ctx.ref_af_loo(maf_iter, maf_tole, use_ds=downsampled, parts=num_partitions)
+    dist.allreduce_sum(ll)
+    dist.allreduce_sum(llp)
+    return af, its, ll.astype(np.float32), llp.astype(np.float32), lits

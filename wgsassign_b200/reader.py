@@ -16,7 +16,12 @@ def readBeagle(beagle, threads=0):
         raise IOError(L.wgs_beagle_last_error().decode())
     try:
         m, n = L.wgs_beagle_sites(h), L.wgs_beagle_inds(h)
-        out = np.empty((m, 2 * n), np.float32)
+        # pinned host memory when a CUDA device is there (full-rate, asynchronous uploads); the parser itself
+        # is host code and also runs without one
+        try:
+            out = _lib.pinned_empty((m, 2 * n), np.float32)
+        except _lib.WgsError:
+            out = np.empty((m, 2 * n), np.float32)
         L.wgs_beagle_copy(h, ctypes.c_void_p(out.ctypes.data))
         samples = [L.wgs_beagle_sample(h, i).decode() for i in range(n)]
         sites = [L.wgs_beagle_site(h, s).decode() for s in range(m)]

@@ -34,8 +34,10 @@ def pops_from_ids(IDs):
     return inv.astype(np.int32), pops
 
 
-def context(L, pop_of_ind=None, K=0):
-    """Context holding `L` repacked for the given population assignment (None = flat)."""
+def context(L, pop_of_ind=None, K=0, async_upload=False):
+    """Context holding `L` repacked for the given population assignment (None = flat).
+    async_upload: queue the upload slab by slab and return at once (the next operator waits for
+    what it needs; `Context.ref_af_loo` overlaps its leave-one-out EM with the transfer)."""
     pkey = None if pop_of_ind is None else (int(K), np.asarray(pop_of_ind, np.int32).tobytes())
     key = (_sig(L), pkey)
     ctx = _state["ctx"]
@@ -52,7 +54,10 @@ def context(L, pop_of_ind=None, K=0):
         if len(pop_of_ind) != n:
             raise ValueError("Number of individuals in beagle and reference ID file do not match!")
         ctx.set_pops(pop_of_ind, K)
-    ctx.upload_gl(L, 0)
+    if async_upload and pop_of_ind is not None:
+        ctx.upload_gl_async(L)
+    else:
+        ctx.upload_gl(L, 0)
     dist.attach(ctx)
     _state["key"] = key
     _state["ds_key"] = None
