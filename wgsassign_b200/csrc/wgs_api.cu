@@ -1667,7 +1667,9 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     CU(cudaMemsetAsync(dmaxd.p, 0, sizeof(int), ctx->stream));
     if (exact_means) {
         // order-independent fixed-point tally (shardable)
-        LAUNCH("ztally", ztally_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
+        const size_t zsmem = (size_t)kZHotX * 7 * 256 * sizeof(int);
+        CU(cudaFuncSetAttribute(ztally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+        LAUNCH("ztally", ztally_kernel, dim3(c.gx, c.gy), 256, zsmem, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
                c.wx, c.sites_per_block, dtable.as<ZTally>(), ddeep.as<unsigned long long>());
         LAUNCH("zaux", zmaxdepth_kernel<ZTally>, ctx->num_sm * 4, 256, 0, ctx->stream, dtable.as<ZTally>(), (long)tab_n, dmaxd.as<int>());
     } else {
@@ -1723,7 +1725,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     // ---- class decisions on the host (zscore.py:23-39, :63-79): a few hundred rows per individual ----
     std::vector<signed char> kmax(ctab_n, -1);
     std::vector<float> kmean(ctab_n, 0.f);
-    std::vector<float4> zlike(ctab_n, make_float4(0.f, 0.f, 0.f, 0.f)), zfac(ctab_n, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<float4> zlike_t(ctab_n, make_float4(0.f, 0.f, 0.f, 0.f));     // class-major: [ncls][ldg]
     std::vector<float4> fac_of_class(ncls);                     // binomial read probabilities: the same for every individual
     for (int d = 0; d <= dmax; ++d)
         for (int alt = 0; alt <= d; ++alt) {
@@ -1760,8 +1762,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
                 if (m1 > mv) { mx = 1; mv = m1; }
                 if (m2 > mv) { mx = 2; mv = m2; }
                 kmax[g] = (signed char)mx; kmean[g] = mv;
-                zlike[g] = make_float4(m0, m1, m2, 0.f);
-                zfac[g] = fac_of_class[id];
+                zlike_t[(size_t)id * ldg + col] = make_float4(m0, m1, m2, 0.f);
                 rows.push_back(ref); rows.push_back(alt); rows.push_back(d); rows.push_back((int)t[id]);
                 ++n_classes[i];
             }
@@ -1783,18 +1784,16 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
 
     tr.lap("class decisions");
     DevBuf dkmax, dkmean, dlike, dfac, dkeep, dkept;
-    if (buf_alloc(ctx, dkmax, tab_n) || buf_alloc(ctx, dkmean, tab_n * sizeof(float)) || buf_alloc(ctx, dlike, tab_n * sizeof(float4)) ||
-        buf_alloc(ctx, dfac, tab_n * sizeof(float4)) || buf_alloc(ctx, dkeep, (size_t)std::max<long>(M, 1) * ldg) ||
+    if (buf_alloc(ctx, dkmax, tab_n) || buf_alloc(ctx, dkmean, tab_n * sizeof(float)) || buf_alloc(ctx, dlike, ctab_n * sizeof(float4)) ||
+        buf_alloc(ctx, dfac, (size_t)ncls * sizeof(float4)) || buf_alloc(ctx, dkeep, (size_t)std::max<long>(M, 1) * ldg) ||
         buf_alloc(ctx, dkept, ldg * sizeof(unsigned long long))) return 1;
     // compact host tables -> the dense device layout; classes deeper than dmax do not occur ("not kept" = -1)
     CU(cudaMemsetAsync(dkmax.p, 0xFF, tab_n, ctx->stream));
     CU(cudaMemcpy2DAsync(dkmax.p, (size_t)kZClasses, kmax.data(), (size_t)ncls, (size_t)ncls, (size_t)ldg, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpy2DAsync(dkmean.p, (size_t)kZClasses * sizeof(float), kmean.data(), (size_t)ncls * sizeof(float), (size_t)ncls * sizeof(float),
                          (size_t)ldg, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpy2DAsync(dlike.p, (size_t)kZClasses * sizeof(float4), zlike.data(), (size_t)ncls * sizeof(float4), (size_t)ncls * sizeof(float4),
-                         (size_t)ldg, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpy2DAsync(dfac.p, (size_t)kZClasses * sizeof(float4), zfac.data(), (size_t)ncls * sizeof(float4), (size_t)ncls * sizeof(float4),
-                         (size_t)ldg, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dlike.p, zlike_t.data(), ctab_n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dfac.p, fac_of_class.data(), (size_t)ncls * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(dkept.p, 0, ldg * sizeof(unsigned long long), ctx->stream));
     LAUNCH("zkeep", zkeep_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
            dkmax.as<signed char>(), dkmean.as<float>(), c.wx, c.sites_per_block, dkeep.as<unsigned char>(), dkept.as<unsigned long long>());
@@ -1852,8 +1851,9 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     DevBuf partials, sums;
     const size_t np3 = (size_t)ldg * 3;
     if (buf_alloc(ctx, partials, (size_t)c.gy * np3 * sizeof(double)) || buf_alloc(ctx, sums, np3 * sizeof(double))) return 1;
-    LAUNCH("zmoments", zmoments_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dkeep.as<unsigned char>(),
-           dAF.as<float>(), af_ld, dafcol.as<int>(), dlike.as<float4>(), dfac.as<float4>(), c.wx, c.sites_per_block, partials.as<double>());
+    LAUNCH("zmoments", zmoments_kernel, dim3(c.gx, c.gy), 256, (size_t)ncls * sizeof(float4), ctx->stream, ctx->G[0], ctx->AD, ldg, M,
+           dkeep.as<unsigned char>(), dAF.as<float>(), af_ld, dafcol.as<int>(), dlike.as<float4>(), dfac.as<float4>(), ncls, c.wx,
+           c.sites_per_block, partials.as<double>());
     add_work(ctx, "zmoments", pairs * 15.0, pairs);
     LAUNCH("reduce", reduce_partials_kernel, grid_for(np3, 256, 64), 256, 0, ctx->stream, partials.as<double>(), c.gy, (long)np3, sums.as<double>());
     std::vector<double> h(np3);

@@ -62,34 +62,39 @@ __device__ __forceinline__ void tally_flush(ZTally* t, int cnt, int h0, int l0, 
 // ---------------------------------------------------------------------------------------
 // ztally: per (individual, class) site count and fixed-point GL sums (zscore.py:13-22).
 // Thread = individual, warp = 32 consecutive columns of one site (coalesced 256 B GL +
-// 64 B AD requests).  The classes of depth <= 3 (86 % of sites at 2x) live in registers and
-// are updated by predicated integer adds - no atomics in the streaming loop; deeper
+// 64 B AD requests).  The classes of depth <= 3 (86 % of sites at 2x) live in thread-private
+// shared-memory counters - no atomics in the streaming loop; deeper
 // classes go straight to the table with 64-bit integer atomics.  A thread sees at most
 // 2047 sites per launch so the 32-bit register limb sums cannot overflow.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256)
 ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
               const unsigned char* __restrict__ sel,       // [ldg] 1 = individual requested
               int wx, long sites_per_block,
               ZTally* __restrict__ table,                  // [ldg][kZClasses]
               unsigned long long* __restrict__ deep)       // [ldg] sites with depth > kZDepthCap
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // thread-private histogram rows in shared memory: hot[class * 7 + field][thread] - consecutive threads hit
+    // consecutive banks, nobody else touches a thread's column (no atomics, no conflicts).  The first version kept
+    // these 70 counters in registers and updated them with 70 predicated adds per site at 2 sites in flight per
+    // thread: latency-bound at 10 % of HBM.
+    extern __shared__ int zhot[];                            // [kZHotX * 7][256]
+    const int t = threadIdx.x;
+    const int warp = t >> 5, lane = t & 31;
     const int wy_count = 8 / wx;
     const int cgx = warp % wx, wy = warp / wx;
     const int col = (blockIdx.x * wx + cgx) * 32 + lane;
     const bool on = col < ldg && sel[col];
     const long s_begin = (long)blockIdx.y * sites_per_block;
     const long s_end = min(M, s_begin + sites_per_block);
-    if (!on) return;
+    if (!on) return;                                          // no block-wide barrier below
 
-    int cnt[kZHotX], h0[kZHotX], l0[kZHotX], h1[kZHotX], l1[kZHotX], h2[kZHotX], l2[kZHotX];
 #pragma unroll
-    for (int c = 0; c < kZHotX; ++c) { cnt[c] = 0; h0[c] = l0[c] = h1[c] = l1[c] = h2[c] = l2[c] = 0; }
+    for (int c = 0; c < kZHotX * 7; ++c) zhot[c * 256 + t] = 0;
     int ndeep = 0;
     ZTally* mine = table + (size_t)col * kZClasses;
 
-    constexpr int PF = 2;                                     // sites in flight per thread
+    constexpr int PF = 8;                                     // sites in flight per thread
     for (long sb = s_begin + wy; sb < s_end; sb += (long)wy_count * PF) {
         float2 gq[PF];
         uchar2 aq[PF];
@@ -109,14 +114,9 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
             fix_limbs(g.y, vh1, vl1);
             fix_limbs(third_gl_np(g.x, g.y), vh2, vl2);
             if (d <= kZHotDepthX) {
-                int code = zclass_id(ref, alt);
-#pragma unroll
-                for (int c = 0; c < kZHotX; ++c) {
-                    if (code == c) {
-                        cnt[c] += 1;
-                        h0[c] += vh0; l0[c] += vl0; h1[c] += vh1; l1[c] += vl1; h2[c] += vh2; l2[c] += vl2;
-                    }
-                }
+                int* h = zhot + zclass_id(ref, alt) * 7 * 256 + t;
+                h[0] += 1;
+                h[256] += vh0; h[2 * 256] += vl0; h[3 * 256] += vh1; h[4 * 256] += vl1; h[5 * 256] += vh2; h[6 * 256] += vl2;
             } else if (d <= kZDepthCap) {
                 tally_flush(mine + zclass_id(ref, alt), 1, vh0, vl0, vh1, vl1, vh2, vl2);
             } else {
@@ -125,7 +125,10 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
         }
     }
 #pragma unroll
-    for (int c = 0; c < kZHotX; ++c) tally_flush(mine + c, cnt[c], h0[c], l0[c], h1[c], l1[c], h2[c], l2[c]);
+    for (int c = 0; c < kZHotX; ++c) {
+        const int* h = zhot + c * 7 * 256 + t;
+        tally_flush(mine + c, h[0], h[256], h[2 * 256], h[3 * 256], h[4 * 256], h[5 * 256], h[6 * 256]);
+    }
     if (ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
 }
 
@@ -270,15 +273,27 @@ zkeep_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ld
 // mode) or the individual's own leave-one-out state column (reference mode).
 // Per-thread float64 sums -> partials[split][col][3] -> fixed-order reduction.
 // ---------------------------------------------------------------------------------------
+// Table layout: the class means are CLASS-major, zlike_t[id][ldg] - the lanes of a warp are consecutive
+// individuals and mostly sit in the same few classes, so one load touches a handful of 512-byte rows instead of
+// 32 scattered lines (the individual-major table made this kernel L1-transaction bound: 4 scattered 16-byte
+// loads per class and pass = 41 ms at 500 k x 2,000).  The binomial read probabilities depend on the class
+// only: one [ncls] table staged in shared memory.  The per-class log terms of a site are kept in registers
+// for the variance pass (depths up to kZCacheDepth; deeper sites recompute them).
+constexpr int kZCacheDepth = 7;
 __global__ void __launch_bounds__(256)
 zmoments_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
                 const unsigned char* __restrict__ keep,
                 const float* __restrict__ afbase, int af_ld, const int* __restrict__ afcol,
-                const float4* __restrict__ zlike, const float4* __restrict__ zfac,
+                const float4* __restrict__ zlike_t,        // [ncls][ldg] class means (GL triple), class-major
+                const float4* __restrict__ zfac_c, int ncls,   // [ncls] binomial read probabilities per class
                 int wx, long sites_per_block,
                 double* __restrict__ partials)             // [gridDim.y][ldg][3]
 {
+    extern __shared__ __align__(16) unsigned char zsmem[];
+    float4* fac_s = reinterpret_cast<float4*>(zsmem);     // [ncls]
     __shared__ double red[8][32][3];
+    for (int e = threadIdx.x; e < ncls; e += blockDim.x) fac_s[e] = zfac_c[e];
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wy_count = 8 / wx;
     const int cgx = warp % wx, wy = warp / wx;
@@ -289,8 +304,7 @@ zmoments_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int
     double w_obs = 0.0, w_mu = 0.0, w_var = 0.0;
     if (col_ok) {
         const int ac = afcol[col];
-        const float4* lk = zlike + (size_t)col * kZClasses;
-        const float4* fc = zfac + (size_t)col * kZClasses;
+        const float4* lk = zlike_t + col;
         for (long s = s_begin + wy; s < s_end; s += wy_count) {
             if (!keep[s * (long)ldg + col]) continue;
             float2 g = ld_stream2(&G[s * (long)ldg + col]);
@@ -301,25 +315,52 @@ zmoments_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int
             float lobs = logf(fmaf(g.x, P0, fmaf(g.y, P1, third_gl(g.x, g.y) * P2)));   // :22-25
             int Dl = ad.x + ad.y;
             int base = Dl * (Dl + 1) / 2;
-            float wl = 0.f;
-            for (int x = 0; x <= Dl; ++x) {                 // class (ref = x, alt = Dl - x), the order of :28-30
-                int id = base + (Dl - x);
-                float4 l = lk[id], f = fc[id];
-                float e = logf(fmaf(l.x, P0, fmaf(l.y, P1, l.z * P2)));       // :31
-                wl = __fadd_rn(wl, e * P0 * f.x);                              // :32-34, float32 after every add
-                wl = __fadd_rn(wl, e * P1 * f.y);
-                wl = __fadd_rn(wl, e * P2 * f.z);
-            }
-            float vr = 0.f;
-            for (int x = 0; x <= Dl; ++x) {
-                int id = base + (Dl - x);
-                float4 l = lk[id], f = fc[id];
-                float e = logf(fmaf(l.x, P0, fmaf(l.y, P1, l.z * P2)));
-                float dd = wl - e;
-                dd = dd * dd;
-                vr = __fadd_rn(vr, dd * P0 * f.x);                             // :54-56
-                vr = __fadd_rn(vr, dd * P1 * f.y);
-                vr = __fadd_rn(vr, dd * P2 * f.z);
+            float wl = 0.f, vr = 0.f;
+            if (Dl <= kZCacheDepth) {
+                float ev[kZCacheDepth + 1];
+#pragma unroll
+                for (int x = 0; x <= kZCacheDepth; ++x) {   // class (ref = x, alt = Dl - x), the order of :28-30
+                    ev[x] = 0.f;
+                    if (x <= Dl) {
+                        int id = base + (Dl - x);
+                        float4 l = __ldg(&lk[(long)id * ldg]), f = fac_s[id];
+                        float e = logf(fmaf(l.x, P0, fmaf(l.y, P1, l.z * P2)));       // :31
+                        ev[x] = e;
+                        wl = __fadd_rn(wl, e * P0 * f.x);                              // :32-34, float32 after every add
+                        wl = __fadd_rn(wl, e * P1 * f.y);
+                        wl = __fadd_rn(wl, e * P2 * f.z);
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x <= kZCacheDepth; ++x) {
+                    if (x <= Dl) {
+                        float4 f = fac_s[base + (Dl - x)];
+                        float dd = wl - ev[x];
+                        dd = dd * dd;
+                        vr = __fadd_rn(vr, dd * P0 * f.x);                             // :54-56
+                        vr = __fadd_rn(vr, dd * P1 * f.y);
+                        vr = __fadd_rn(vr, dd * P2 * f.z);
+                    }
+                }
+            } else {
+                for (int x = 0; x <= Dl; ++x) {
+                    int id = base + (Dl - x);
+                    float4 l = __ldg(&lk[(long)id * ldg]), f = fac_s[id];
+                    float e = logf(fmaf(l.x, P0, fmaf(l.y, P1, l.z * P2)));
+                    wl = __fadd_rn(wl, e * P0 * f.x);
+                    wl = __fadd_rn(wl, e * P1 * f.y);
+                    wl = __fadd_rn(wl, e * P2 * f.z);
+                }
+                for (int x = 0; x <= Dl; ++x) {
+                    int id = base + (Dl - x);
+                    float4 l = __ldg(&lk[(long)id * ldg]), f = fac_s[id];
+                    float e = logf(fmaf(l.x, P0, fmaf(l.y, P1, l.z * P2)));
+                    float dd = wl - e;
+                    dd = dd * dd;
+                    vr = __fadd_rn(vr, dd * P0 * f.x);
+                    vr = __fadd_rn(vr, dd * P1 * f.y);
+                    vr = __fadd_rn(vr, dd * P2 * f.z);
+                }
             }
             w_obs += (double)lobs; w_mu += (double)wl; w_var += (double)vr;
         }
