@@ -515,13 +515,15 @@ bool loo_like2_cfg(wgs_ctx* ctx, long M, int ldf, int K, LooLike2Cfg* c)
     c->W = (groups + nb - 1) / nb;
     c->gx = nb;
     c->wide = K > 10;                                             // one block per SM, <= 4 sites per tile (see the kernel)
-    const size_t budget = c->wide ? 190 * 1024 : 100 * 1024;
+    const size_t budget = c->wide ? 210 * 1024 : 100 * 1024;
     // per site of a tile: 16 B plane cell + 4 B landing row per state value, 2 x 8 B per GL column of the block
     const size_t per_site = (size_t)ldf * 20 + (size_t)c->W * 32 * 16;
-    int TS = (int)std::min<size_t>(c->wide ? 4 : 8, budget / per_site);
+    const size_t fixed = (size_t)ldf * 8;                         // clamp bounds
+    if (budget <= fixed) return false;
+    int TS = (int)std::min<size_t>(c->wide ? 4 : 8, (budget - fixed) / per_site);
     if (TS < 1) return false;
     c->TS = TS;
-    c->smem = (size_t)TS * per_site;
+    c->smem = (size_t)TS * per_site + fixed;
     long target = std::max<long>(1, (long)ctx->num_sm * (c->wide ? 1 : 2) / nb);    // one wave of resident blocks
     long spb = (M + target - 1) / target;
     spb = std::max<long>(TS, (spb + TS - 1) / TS * TS);
@@ -530,14 +532,14 @@ bool loo_like2_cfg(wgs_ctx* ctx, long M, int ldf, int K, LooLike2Cfg* c)
     return true;
 }
 template <int KT, int TSMAX, int MINB>
-int launch_loo_like2_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, int ldf, const int* rc, int K, int k0,
-                       const LooLike2Cfg& c, long pm, long pr, int R, double* partials)
+int launch_loo_like2_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, int ldf, const float* clo, const float* chi,
+                       const int* rc, int K, int k0, const LooLike2Cfg& c, long pm, long pr, int R, double* partials)
 {
     auto kern = loo_like2_kernel<KT, TSMAX, MINB>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     LAUNCH("loo_like", kern, dim3(c.gx, c.gy), c.W * 32, c.smem, ctx->stream,
-           G, ctx->ldg, M, Fx, ldf, rc, K, k0, c.TS, c.spb, pm, pr, ctx->site_offset, R, partials);
+           G, ctx->ldg, M, Fx, ldf, clo, chi, rc, K, k0, c.TS, c.spb, pm, pr, ctx->site_offset, R, partials);
     {   // GL pairs once + the LOO state row (one float per individual) + full-data AF columns
         int kt = std::min(KT, K - k0);
         add_work(ctx, "loo_like", (double)M * ctx->N * 12.0 + (double)M * kt * 4.0, (double)M * ctx->N * kt);
@@ -546,19 +548,19 @@ int launch_loo_like2_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, i
 }
 // population tile width of one pass: the narrow kernels take pick_KT's widths, the wide ones 16 or 20 (masked past K)
 int loo_like2_KT(const LooLike2Cfg& c, int remaining) { return c.wide ? (remaining > 16 ? 20 : 16) : pick_KT(remaining); }
-int launch_loo_like2(wgs_ctx* ctx, int KT, const float2* G, long M, const float* Fx, int ldf, const int* rc, int K, int k0,
-                     const LooLike2Cfg& c, long pm, long pr, int R, double* partials)
+int launch_loo_like2(wgs_ctx* ctx, int KT, const float2* G, long M, const float* Fx, int ldf, const float* clo, const float* chi,
+                     const int* rc, int K, int k0, const LooLike2Cfg& c, long pm, long pr, int R, double* partials)
 {
     if (c.wide) {
-        if (KT == 16) return launch_loo_like2_t<16, 4, 1>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        return launch_loo_like2_t<20, 4, 1>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        if (KT == 16) return launch_loo_like2_t<16, 4, 1>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+        return launch_loo_like2_t<20, 4, 1>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
     }
     switch (KT) {
-        case 2: return launch_loo_like2_t<2, 8, 2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        case 4: return launch_loo_like2_t<4, 8, 2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        case 5: return launch_loo_like2_t<5, 8, 2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        case 8: return launch_loo_like2_t<8, 8, 2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
-        default: return launch_loo_like2_t<10, 8, 2>(ctx, G, M, Fx, ldf, rc, K, k0, c, pm, pr, R, partials);
+        case 2: return launch_loo_like2_t<2, 8, 2>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+        case 4: return launch_loo_like2_t<4, 8, 2>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+        case 5: return launch_loo_like2_t<5, 8, 2>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+        case 8: return launch_loo_like2_t<8, 8, 2>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+        default: return launch_loo_like2_t<10, 8, 2>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
     }
 }
 
@@ -777,7 +779,10 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
     }
 
     const int np = K * kEmChunk;
-    DevBuf FT1, partials, ssq, dcur, diters;
+    // the register-tile kernel also records the state after EVERY iteration of a pass (8 x 4 bytes per site and
+    // population - nothing next to the pass itself), so a stop inside a chunk needs no replay pass
+    DevBuf FT1, partials, ssq, dcur, diters, hist;
+    if (packed && buf_alloc(ctx, hist, (size_t)kEmChunk * std::max<long>(M, 1) * K * sizeof(float))) return 1;
     if (buf_alloc(ctx, FT1, (size_t)std::max<long>(M, 1) * K * sizeof(float)) || buf_alloc(ctx, partials, (size_t)gx * np * sizeof(double)) ||
         buf_alloc(ctx, ssq, (size_t)np * sizeof(double)) || buf_alloc(ctx, dcur, K * sizeof(int)) || buf_alloc(ctx, diters, K * sizeof(int))) return 1;
     std::vector<int> cur(K, 0), done(K, 0), replay(K, 0), run(K, 0);
@@ -797,7 +802,7 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
         CU(cudaMemcpyAsync(diters.p, run.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 #define EM2_LAUNCH(TPRV, QPTV)                                                                                          \
     LAUNCH("em_pop", (em_pop_multi2_kernel<TPRV, QPTV>), dim3(gx, K), 256, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT, \
-           FT1.as<float>(), dcur.as<int>(), diters.as<int>(), raw16, partials.as<double>())
+           FT1.as<float>(), dcur.as<int>(), diters.as<int>(), raw16, partials.as<double>(), hist.as<float>())
         if (packed) {
             if (tpr == 4 && qpt == 1) EM2_LAUNCH(4, 1); else if (tpr == 4 && qpt == 2) EM2_LAUNCH(4, 2); else if (tpr == 4) EM2_LAUNCH(4, 4);
             else if (tpr == 8) EM2_LAUNCH(8, 4); else if (tpr == 16) EM2_LAUNCH(16, 4); else EM2_LAUNCH(32, 4);
@@ -827,6 +832,11 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
             if (tstar == 0 || tstar == run[k]) {                            // the state written by this pass is the one to keep
                 cur[k] ^= 1; done[k] += run[k];
                 if (tstar) { fin[k] = 1; iters_out[k] = done[k]; }
+            } else if (packed) {                                            // stop inside the chunk: that iteration's state is in the history
+                float* dst = (cur[k] ? FT : FT1.as<float>()) + (size_t)k * M;
+                CU(cudaMemcpyAsync(dst, hist.as<float>() + ((size_t)(tstar - 1) * K + k) * M, (size_t)M * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+                cur[k] ^= 1; done[k] += tstar; fin[k] = 1; iters_out[k] = done[k];
             } else {
                 replay[k] = tstar;                                          // stop inside the chunk: replay from FT[cur]
             }
@@ -1454,14 +1464,20 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
     for (int i = 0; i < N; ++i) iters_out[i] = its_cols[ctx->col_of_ind[i]];
 
     // clip to [1/(2n), 1-1/(2n)] with n = n_pop (glassy.py:80-85: n_pop-1 individuals were used)
+    // The staged likelihood kernel (loo_like2) clamps while it builds its cells and the final gather clamps on the
+    // way out, so the state matrix itself is not rewritten; the gather-through-L1 fallback still clamps it in place.
     std::vector<float> lo, hi;
     clip_bounds(ctx, 1, lo, hi);
+    LooLike2Cfg c2{};
+    const bool staged = getenv("WGS_LOOLIKE_V1") == nullptr && loo_like2_cfg(ctx, M, ldf, K, &c2);
+    lo.resize(ldf, 0.0f); hi.resize(ldf, 1.0f);                  // full-data AF and pad columns: already inside [0, 1]
     DevBuf dlo, dhi;
-    if (buf_alloc(ctx, dlo, ldg * sizeof(float)) || buf_alloc(ctx, dhi, ldg * sizeof(float))) return 1;
-    CU(cudaMemcpyAsync(dlo.p, lo.data(), ldg * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dhi.p, hi.data(), ldg * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH("clip", clip_cols_kernel, grid_for(M * ldg, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F.as<float>(), ldf, ldg, M,
-           dlo.as<float>(), dhi.as<float>());
+    if (buf_alloc(ctx, dlo, ldf * sizeof(float)) || buf_alloc(ctx, dhi, ldf * sizeof(float))) return 1;
+    CU(cudaMemcpyAsync(dlo.p, lo.data(), ldf * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dhi.p, hi.data(), ldf * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (!staged)
+        LAUNCH("clip", clip_cols_kernel, grid_for(M * ldg, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F.as<float>(), ldf, ldg, M,
+               dlo.as<float>(), dhi.as<float>());
 
     // which column of F each (individual, population) pair reads (glassy.py:89 overwrite order)
     std::vector<int> rc((size_t)ldg * K, ldf - 1), last(K, -1);
@@ -1485,8 +1501,6 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
         for (int k = 0; k < K; ++k) if (ctx->pops[k].n <= 1) R = 1;
     }
     LikeCfg c = like_cfg(ctx, M, 3);
-    LooLike2Cfg c2{};
-    const bool staged = getenv("WGS_LOOLIKE_V1") == nullptr && loo_like2_cfg(ctx, M, ldf, K, &c2);
     const int n_split = staged ? c2.gy : c.gy;
     size_t np = (size_t)ldg * K;
     DevBuf partials, sums;
@@ -1498,7 +1512,8 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
         for (int k0 = 0; k0 < K;) {
             int KT = staged ? loo_like2_KT(c2, K - k0) : pick_KT(K - k0);
             int rc_ = 0;
-            if (staged) rc_ = launch_loo_like2(ctx, KT, Gsrc, M, F.as<float>(), ldf, drc.as<int>(), K, k0, c2, pm, pr, R, partials.as<double>());
+            if (staged) rc_ = launch_loo_like2(ctx, KT, Gsrc, M, F.as<float>(), ldf, dlo.as<float>(), dhi.as<float>(), drc.as<int>(), K, k0, c2, pm, pr, R,
+                                               partials.as<double>());
             else DISPATCH_KT(launch_loo_like_t, KT, R, ctx, Gsrc, M, F.as<float>(), ldf, drc.as<int>(), K, k0, c, pm, pr, partials.as<double>());
             if (rc_) return rc_;
             k0 += KT;
@@ -1521,7 +1536,7 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
     for (int j = 0; j < K; ++j) lastcol[j] = last[j] >= 0 ? ctx->col_of_ind[last[j]] : ldg + j;
     CU(cudaMemcpyAsync(dcols.p, lastcol.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH("gather", gather_cols_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F.as<float>(), ldf,
-           dcols.as<int>(), K, dA.as<float>(), K, 0, M);
+           dcols.as<int>(), K, dA.as<float>(), K, 0, M, staged ? dlo.as<float>() : nullptr, staged ? dhi.as<float>() : nullptr);
     if (af_inout) CU(cudaMemcpyAsync(af_inout, dA.p, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());

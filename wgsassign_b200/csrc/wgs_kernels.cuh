@@ -879,6 +879,7 @@ template <int KT, int TSMAX, int MINB>
 __global__ void __launch_bounds__(kLL2MaxW * 32, MINB)
 loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
                  const float* __restrict__ Fx, int ldf,
+                 const float* __restrict__ clip_lo, const float* __restrict__ clip_hi,   // [ldf] or null: clamp applied while staging
                  const int* __restrict__ rc, int K, int k0,
                  int TS, long sites_per_block,                  // TS <= TSMAX; sites_per_block a multiple of TS
                  long part_mod, long part_rem, long site_offset, int R,
@@ -892,6 +893,7 @@ loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
     float4* Hq = reinterpret_cast<float4*>(smem_raw);                       // [TS][ldf] planes ((1-a)^2, 2a(1-a), a^2, -)
     float2* Gs = reinterpret_cast<float2*>(Hq + (size_t)TS * ldf);          // [2][TS][wcols] GL pairs, double-buffered
     float* raw = reinterpret_cast<float*>(Gs + 2 * (size_t)TS * wcols);     // [TS][ldf] landing rows of the next tile's state
+    float* clip_s = raw + (size_t)TS * ldf;                                 // [2][ldf] clamp bounds per state column
     const int col0 = blockIdx.x * wcols;
     const int col = col0 + t;
     const bool col_ok = col < ldg;
@@ -906,6 +908,10 @@ loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
     for (int kk = 0; kk < KT; ++kk)
         roff[kk] = 16u * (unsigned)((col_ok && k0 + kk < K) ? rc[(long)col * K + k0 + kk] : (ldf - 1));
 
+    for (int c = t; c < ldf; c += blockDim.x) {           // without bounds: (-inf, +inf) leaves every value, NaN included, as it is
+        clip_s[c] = clip_lo ? clip_lo[c] : -INFINITY;
+        clip_s[ldf + c] = clip_lo ? clip_hi[c] : INFINITY;
+    }
     if (t == 0) { mbar_init(&mbar, 1); mbar_init(&mbar_g[0], 1); mbar_init(&mbar_g[1], 1); mbar_fence_init(); }
     __syncthreads();
     auto issue_state = [&](int j) {                       // thread 0: one bulk copy for the tile's state rows
@@ -939,10 +945,23 @@ loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
         const int rows = (int)min((long)TS, s_end - s0);
         issue_gl(j + 1);                                  // its buffer was released by the barrier that ended tile j-1
         mbar_wait(&mbar, (unsigned)(j & 1));
-        for (int e = t; e < rows * ldf; e += blockDim.x) {
-            const float a = raw[e];
-            const float om = 1.0f - a;
-            Hq[e] = make_float4(om * om, 2.0f * a * om, a * a, 0.0f);
+        // the clipping of glassy.py:80-85 happens here, on the way into the cells: the state matrix is never
+        // rewritten (a separate clamp pass over it was 1.4 ms at 1M x 500)
+        for (int c = t; c < ldf; c += blockDim.x) {       // a thread takes whole columns: its bounds are loaded once per tile
+            const float lo = clip_s[c], hi = clip_s[ldf + c];
+            float av[TSMAX];
+#pragma unroll
+            for (int u = 0; u < TSMAX; ++u) av[u] = u < rows ? raw[u * ldf + c] : 0.5f;
+#pragma unroll
+            for (int u = 0; u < TSMAX; ++u) {
+                if (u < rows) {
+                    float a = av[u];
+                    if (a < lo) a = lo;                   // comparisons are false for NaN: NaN survives (FMNMX.NAN)
+                    if (a > hi) a = hi;
+                    const float om = 1.0f - a;
+                    Hq[u * ldf + c] = make_float4(om * om, 2.0f * a * om, a * a, 0.0f);
+                }
+            }
         }
         __syncthreads();                                  // planes complete, landing rows free: the next tile's copy overlaps the compute
         issue_state(j + 1);
@@ -1255,14 +1274,15 @@ em_pop_multi2_kernel(const float2* __restrict__ G, int ldg, long M,
                      const int* __restrict__ cur,          // [K] buffer that holds the start state
                      const int* __restrict__ iters_k,      // [K] iterations to run now (0 = skip)
                      int raw16,                            // raw row stride, 16-byte units (an odd number of pairs of units)
-                     double* __restrict__ partials)        // [gridDim.x][K][kEmChunk]
+                     double* __restrict__ partials,        // [gridDim.x][K][kEmChunk]
+                     float* __restrict__ Fhist)            // [kEmChunk][K][M]: the state after every iteration of this pass
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float red[256];
-    __shared__ __align__(8) unsigned long long mbar[2];
     const int k = blockIdx.y;
-    const int t = threadIdx.x;
-    const int R = blockDim.x / TPR;                       // rows (sites) per tile
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int R = 256 / TPR;                          // rows (sites) per tile
+    constexpr int RW = 32 / TPR;                          // rows per warp: the warp stages and consumes exactly these
     const int r = t / TPR, h = t % TPR;                   // row of this thread, its slice of the row
     const int T = iters_k[k];
     double* pout = partials + ((long)blockIdx.x * K + k) * kEmChunk;
@@ -1272,38 +1292,45 @@ em_pop_multi2_kernel(const float2* __restrict__ G, int ldg, long M,
     }
     const PopDesc pd = pops[k];
     const int nq = (pd.n + 3) >> 2;                       // quads of individuals
+    const int nq2 = 2 * nq;                               // 16-byte units per slab row
     float4* raw = reinterpret_cast<float4*>(smem_raw);    // [2][R][raw16]
     const long ntiles = (M + R - 1) / R;
     const float* Fsrc = (cur[k] ? FT1 : FT0) + (size_t)k * M;
     float* Fdst = (cur[k] ? FT0 : FT1) + (size_t)k * M;
 
-    if (t == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
-    __syncthreads();
-    auto issue = [&](long tile, int buf) {                // warp 0: one TMA bulk copy per slab row
-        if (tile < ntiles && t < 32) {
-            const long s0 = tile * R;
-            const int rows = (int)min((long)R, M - s0);
-            if (t == 0) mbar_expect_tx(&mbar[buf], (unsigned)(rows * nq * 32));
-            __syncwarp();
-            float4* dst = raw + (size_t)buf * R * raw16;
-            for (int rr = t; rr < rows; rr += 32)
-                bulk_g2s(dst + (size_t)rr * raw16, G + (s0 + rr) * (long)ldg + pd.col0, (unsigned)(nq * 32), &mbar[buf]);
+    // Warp-private staging: every warp copies the RW slab rows it will consume with 16-byte LDGSTS into its own
+    // slice of a double buffer, one tile ahead - no block-wide barrier in the loop (the TMA + __syncthreads version
+    // stalled 3 cycles per issue at that barrier), warps drift freely.
+    auto stage = [&](long tile, int buf) {
+        if (tile < ntiles) {
+            const long s0 = tile * R + warp * RW;
+            float4* dst = raw + ((size_t)buf * R + warp * RW) * raw16;
+            int rr = 0, q = lane;
+            while (q >= nq2) { q -= nq2; ++rr; }
+            while (rr < RW) {
+                if (s0 + rr < M)
+                    cp_async16(dst + (size_t)rr * raw16 + q, reinterpret_cast<const float4*>(G + (s0 + rr) * (long)ldg + pd.col0) + q);
+                q += 32;
+                while (q >= nq2) { q -= nq2; ++rr; }
+            }
         }
+        cp_async_commit();
     };
 
     float ssq[kEmChunk];
 #pragma unroll
     for (int u = 0; u < kEmChunk; ++u) ssq[u] = 0.f;
     const float fn = (float)pd.n;
-    issue(blockIdx.x, 0);
-    issue(blockIdx.x + (long)gridDim.x, 1);
+    stage(blockIdx.x, 0);
     int it = 0;
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const long s = tile * R + r;
         float f = 0.25f;
         if (s < M) f = Fsrc[s];
-        mbar_wait(&mbar[buf], (unsigned)((it >> 1) & 1)); // the raw rows of this tile have landed
+        stage(tile + gridDim.x, buf ^ 1);                 // always commits a (possibly empty) group: wait<1> = this tile has landed
+        cp_async_wait<1>();
+        __syncwarp();
         // this thread's quads -> packed registers (pads and rows past M are (1,0,0): exactly zero terms)
         f32x2 g0ab[QPT], g1ab[QPT], g2ab[QPT], g0cd[QPT], g1cd[QPT], g2cd[QPT];
         {
@@ -1322,8 +1349,7 @@ em_pop_multi2_kernel(const float2* __restrict__ G, int ldg, long M,
                 g2cd[j] = pack2(1.0f - gc.x - gc.y, 1.0f - gc.z - gc.w);
             }
         }
-        __syncthreads();                                  // everyone has its registers: the raw buffer is free
-        issue(tile + 2 * (long)gridDim.x, buf);
+        __syncwarp();                                     // every lane has its registers: the slice may be refilled next time round
 #pragma unroll
         for (int u = 0; u < kEmChunk; ++u) {
             if (u < T) {                                  // block-uniform
@@ -1349,7 +1375,10 @@ em_pop_multi2_kernel(const float2* __restrict__ G, int ldg, long M,
                 float fnew = __fdiv_rn(sum, fn);                // identical in the TPR lanes of a row
                 if (fnew < 1e-12f) fnew = 1e-12f;               // comparisons are false for NaN: NaN survives
                 if (fnew > 0.99999994f) fnew = 0.99999994f;
-                if (s < M && h == 0) { const float d = fnew - f; ssq[u] += d * d; }
+                if (s < M && h == 0) {
+                    const float d = fnew - f; ssq[u] += d * d;
+                    Fhist[((size_t)u * K + k) * M + s] = fnew;      // the host picks the stop iteration's state: no replay pass
+                }
                 f = fnew;
             }
         }
@@ -1638,45 +1667,68 @@ __device__ __forceinline__ void loo5_pair_coefs(float g0, float g1, float g2, fl
 // - rows of consecutive sites are contiguous, so a whole group of rows is ONE bulk copy, and the odd row
 // length keeps the rows of a quarter-warp on different bank groups.
 __host__ __device__ __forceinline__ int loo5_row_units(int n) { const int nq = (n + 3) >> 2, nc = (nq + 1) >> 1; return (5 * nc + 2 * nq) | 1; }
-__global__ void loo_prepack_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n, int nc,
-                                   ulonglong2* __restrict__ PK)          // [M][loo5_row_units(n)]
+__global__ void __launch_bounds__(256)
+loo_prepack_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n, int nc,
+                   ulonglong2* __restrict__ PK)          // [M][loo5_row_units(n)]
 {
     const int nq = (n + 3) >> 2;
     const int ru = loo5_row_units(n);
     const long total = M * (long)nc;
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const long s = e / nc;
-        const int c = (int)(e - s * nc);
-        ulonglong2* rowp = PK + s * (long)ru;
-        f32x2 P[2][5];
+    const long T = (long)gridDim.x * blockDim.x;
+    // two cells per thread and trip: all eight 16-byte loads are issued before the first use (the one-cell version
+    // sat on its loads: 54 stall cycles per issue at 38 % of DRAM bandwidth)
+    for (long e0 = blockIdx.x * (long)blockDim.x + threadIdx.x; e0 < total; e0 += 2 * T) {
+        float4 ga[2][2], gc[2][2];
+        long sv[2]; int cv[2]; bool on[2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int q = 2 * c + h;
-            float4 ga = make_float4(1.f, 0.f, 1.f, 0.f), gc = ga;       // (1,0,0) pads
-            if (q < nq) {
-                const float4* src = reinterpret_cast<const float4*>(&G[s * (long)ldg + col0 + 4 * q]);
-                ga = ld_stream4(src);
-                gc = ld_stream4(src + 1);
-                float4* rawp = reinterpret_cast<float4*>(rowp + 5 * nc) + 2 * q;
-                rawp[0] = ga; rawp[1] = gc;
+        for (int w = 0; w < 2; ++w) {
+            const long e = e0 + w * T;
+            on[w] = e < total;
+            sv[w] = on[w] ? e / nc : 0;
+            cv[w] = on[w] ? (int)(e - sv[w] * nc) : 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = 2 * cv[w] + h;
+                ga[w][h] = make_float4(1.f, 0.f, 1.f, 0.f); gc[w][h] = ga[w][h];     // (1,0,0) pads
+                if (on[w] && q < nq) {
+                    const float4* src = reinterpret_cast<const float4*>(&G[sv[w] * (long)ldg + col0 + 4 * q]);
+                    ga[w][h] = ld_stream4(src);
+                    gc[w][h] = ld_stream4(src + 1);
+                }
             }
-            if (4 * q + 1 >= n) { ga.z = 1.f; ga.w = 0.f; }
-            if (4 * q + 2 >= n) { gc.x = 1.f; gc.y = 0.f; }
-            if (4 * q + 3 >= n) { gc.z = 1.f; gc.w = 0.f; }
-            float Pab[5], Pcd[5];
-            loo5_pair_coefs(ga.x, ga.y, third_gl(ga.x, ga.y), ga.z, ga.w, third_gl(ga.z, ga.w), Pab);
-            loo5_pair_coefs(gc.x, gc.y, third_gl(gc.x, gc.y), gc.z, gc.w, third_gl(gc.z, gc.w), Pcd);
-#pragma unroll
-            for (int j = 0; j < 5; ++j) P[h][j] = pack2(Pab[j], Pcd[j]);
         }
-        ulonglong2* dst = rowp + 5 * c;
-        ulonglong2 v;
-        v.x = P[0][0]; v.y = P[0][1]; dst[0] = v;
-        v.x = P[0][2]; v.y = P[0][3]; dst[1] = v;
-        v.x = P[0][4]; v.y = P[1][0]; dst[2] = v;
-        v.x = P[1][1]; v.y = P[1][2]; dst[3] = v;
-        v.x = P[1][3]; v.y = P[1][4]; dst[4] = v;
-        if (c == 0 && (5 * nc + 2 * nq) != ru) rowp[ru - 1] = make_ulonglong2(0ull, 0ull);   // the pad unit: defined bytes for the copy
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            if (!on[w]) continue;
+            const int c = cv[w];
+            ulonglong2* rowp = PK + sv[w] * (long)ru;
+            f32x2 P[2][5];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = 2 * c + h;
+                float4 a4 = ga[w][h], c4 = gc[w][h];
+                if (q < nq) {
+                    float4* rawp = reinterpret_cast<float4*>(rowp + 5 * nc) + 2 * q;
+                    rawp[0] = a4; rawp[1] = c4;
+                }
+                if (4 * q + 1 >= n) { a4.z = 1.f; a4.w = 0.f; }
+                if (4 * q + 2 >= n) { c4.x = 1.f; c4.y = 0.f; }
+                if (4 * q + 3 >= n) { c4.z = 1.f; c4.w = 0.f; }
+                float Pab[5], Pcd[5];
+                loo5_pair_coefs(a4.x, a4.y, third_gl(a4.x, a4.y), a4.z, a4.w, third_gl(a4.z, a4.w), Pab);
+                loo5_pair_coefs(c4.x, c4.y, third_gl(c4.x, c4.y), c4.z, c4.w, third_gl(c4.z, c4.w), Pcd);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) P[h][j] = pack2(Pab[j], Pcd[j]);
+            }
+            ulonglong2* dst = rowp + 5 * c;
+            ulonglong2 v;
+            v.x = P[0][0]; v.y = P[0][1]; dst[0] = v;
+            v.x = P[0][2]; v.y = P[0][3]; dst[1] = v;
+            v.x = P[0][4]; v.y = P[1][0]; dst[2] = v;
+            v.x = P[1][1]; v.y = P[1][2]; dst[3] = v;
+            v.x = P[1][3]; v.y = P[1][4]; dst[4] = v;
+            if (c == 0 && (5 * nc + 2 * nq) != ru) rowp[ru - 1] = make_ulonglong2(0ull, 0ull);   // the pad unit: defined bytes for the copy
+        }
     }
 }
 
@@ -1958,15 +2010,21 @@ __global__ void clip_transpose_kernel(const float* __restrict__ FT, long M, int 
 }
 
 // dst[s][j] = src[s][cols[j]] (j < nc): column gather between row-major float matrices
+// clip_lo / clip_hi (optional, indexed by SOURCE column): clamp on the way, like clip_cols_kernel
 __global__ void gather_cols_kernel(const float* __restrict__ src, int lds, const int* __restrict__ cols, int nc,
-                                   float* __restrict__ dst, int ldd, int dst_col0, long M)
+                                   float* __restrict__ dst, int ldd, int dst_col0, long M,
+                                   const float* __restrict__ clip_lo = nullptr, const float* __restrict__ clip_hi = nullptr)
 {
     long total = M * (long)nc;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         long s = e / nc;
         int j = (int)(e - s * nc);
         int c = cols[j];
-        if (c >= 0) dst[s * (long)ldd + dst_col0 + j] = src[s * (long)lds + c];
+        if (c >= 0) {
+            float v = src[s * (long)lds + c];
+            if (clip_lo) { if (v < clip_lo[c]) v = clip_lo[c]; if (v > clip_hi[c]) v = clip_hi[c]; }
+            dst[s * (long)ldd + dst_col0 + j] = v;
+        }
     }
 }
 
