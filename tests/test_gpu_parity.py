@@ -307,3 +307,60 @@ def test_ref_af_loo_fused_bundled(wgs, bundled):
     assert rel_err(ll.astype(np.float32), gold) < 2e-6
     assert np.array_equal(np.argmax(ll, 1), np.argmax(gold, 1))
     ctx.close()
+
+
+def test_fused_edge_cases(wgs, oracle_mod):
+    """Pipelined path on awkward shapes: a single-member population (NaN columns like the reference's 0/0), one
+    population only, and fewer sites than one tile."""
+    from wgsassign_b200 import synth
+    d = synth.synth(150, 11, 3, seed=41, with_ad=False)
+    L = wgs.lib.pinned_empty(d["L"].shape, np.float32)
+    L[...] = d["L"]
+    IDs = d["IDs"].copy()
+    IDs[:, 1] = "a"
+    IDs[4:8, 1] = "b"
+    IDs[10, 1] = "c"                                  # single member
+    for ids in (IDs, np.array([[x, "p"] for x in IDs[:, 0]])):
+        pop_of, pops = wgs.session.pops_from_ids(ids)
+        ctx = wgs.lib.Context(0)
+        ctx.set_pops(pop_of, len(pops))
+        ctx.upload_gl_async(L)
+        af, its, ll, _, lits, af_after = ctx.ref_af_loo(30, 1e-4, want_af_after=True)
+        af_o, _, its_o = oracle_mod.reference_af(d["L"], ids, 30, 1e-4, 1)
+        a1 = af_o.copy()
+        ll_o, _, lits_o = oracle_mod.loo(d["L"], a1, ids, 1, 30, 1e-4)
+        assert list(its) == list(its_o) and list(lits) == list(lits_o)
+        assert np.max(np.abs(af - af_o)) < AF_ATOL
+        assert np.array_equal(np.isnan(ll), np.isnan(ll_o))
+        ok = ~np.isnan(ll_o)
+        assert rel_err(ll[ok], ll_o[ok]) < LL_RTOL
+        fin = ~np.isnan(a1)
+        assert np.array_equal(np.isnan(af_after), np.isnan(a1)) and np.max(np.abs(af_after[fin] - a1[fin])) < AF_ATOL
+        ctx.close()
+
+
+def test_fallback_kernels_agree(wgs, monkeypatch):
+    """The kernels kept for shapes the fast ones do not cover (gather-through-L1 loo_like, TMA-tile Fisher,
+    one-iteration-per-launch EM) give the same answers as the fast ones on a shape both cover."""
+    from wgsassign_b200 import synth
+    d = synth.synth(2100, 45, 4, seed=43, with_ad=False)
+    pop_of, pops = wgs.session.pops_from_ids(d["IDs"])
+    ctx = wgs.lib.Context(0)
+    ctx.set_pops(pop_of, len(pops))
+    ctx.upload_gl(d["L"])
+    af, its = ctx.ref_af(200, 1e-4)
+    a0 = af.copy()
+    ll, _, lits = ctx.loo_partial(a0, 200, 1e-4)
+    f_obs, ne_obs, ind = ctx.fisher_partial(af)
+    for var in ("WGS_LOOLIKE_V1", "WGS_FISHER_V1", "WGS_EM_STEP", "WGS_EM_NO_LOOKAHEAD", "WGS_LOO_V4"):
+        monkeypatch.setenv(var, "1")
+    af2, its2 = ctx.ref_af(200, 1e-4)
+    a1 = af2.copy()
+    ll2, _, lits2 = ctx.loo_partial(a1, 200, 1e-4)
+    f2, ne2, ind2 = ctx.fisher_partial(af)
+    assert list(its) == list(its2) and list(lits) == list(lits2)
+    assert np.max(np.abs(af - af2)) < 1e-6 and np.max(np.abs(a0 - a1)) < AF_ATOL
+    assert rel_err(ll2, ll) < LL_RTOL and np.array_equal(np.argmax(ll, 1), np.argmax(ll2, 1))
+    assert np.max(np.abs(f2 - f_obs) / (np.abs(f_obs) + 1e-3 * np.abs(f_obs).max(0))) < 1e-4
+    assert rel_err(ind2, ind) < 1e-5
+    ctx.close()

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -708,13 +709,16 @@ inline bool em_converged(double ssq, double count, double tole)
 // Per-population EM on the resident G: FT [K][M] (device, population-major) <- converged, UNclipped f.
 // Up to kEmChunk iterations per read of G (em_pop_multi_kernel); WGS_EM_STEP=1 selects the
 // one-iteration-per-launch kernel (same bits, 14 reads of G instead of 3).
-int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>& iters_out)
+int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>& iters_out, int k0 = 0, int kn = -1)
 {
+    // populations [k0, k0 + kn) only (kn < 0: all): FT then points at THEIR block of the population-major state
     const long M = ctx->M();
-    const int K = std::max(ctx->K, 1);
+    const int K = kn < 0 ? std::max(ctx->K, 1) : kn;
+    const PopDesc* hpops = ctx->pops.data() + k0;
+    const PopDesc* dpops = ctx->d_pops + k0;
     if (K > kMaxKq * 32) return fail(ctx, "more than %d populations not supported", kMaxKq * 32);
     int nmax = 1;
-    for (int k = 0; k < K; ++k) nmax = std::max(nmax, ctx->pops[k].n);
+    for (int k = 0; k < K; ++k) nmax = std::max(nmax, hpops[k].n);
     int row16 = (nmax + 3) / 4 * 2;                             // widest slab in 16-byte units ...
     while (row16 % 8 != kEmT % 8) ++row16;                      // ... padded so that kEmT threads x 2 rows hit 8 distinct bank groups
     int R = 128;
@@ -764,11 +768,11 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
         if (em_state_init(ctx, st, K, K, gx, std::vector<int>(K, 1))) return 1;
         int n_active = K;
         for (int it = 1; it <= iter && n_active > 0; ++it) {
-            LAUNCH("em_pop", em_pop_step_kernel, dim3(gx, K), R * kEmT, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT,
+            LAUNCH("em_pop", em_pop_step_kernel, dim3(gx, K), R * kEmT, smem, ctx->stream, ctx->G[0], ctx->ldg, M, dpops, K, FT,
                    st.active.as<int>(), row16, st.partials.as<double>());
             {   // 8 B per (site, individual of an active population) + f read/write
                 double inds = 0, act = 0;
-                for (int k = 0; k < K; ++k) if (st.h_active[k]) { inds += ctx->pops[k].n; act += 1; }
+                for (int k = 0; k < K; ++k) if (st.h_active[k]) { inds += hpops[k].n; act += 1; }
                 add_work(ctx, "em_pop", (double)M * inds * 8.0 + (double)M * act * 8.0, (double)M * inds);
             }
             if (em_after_step(ctx, st, tole, it, nullptr, (double)ctx->Mtot(), &n_active)) return 1;
@@ -801,7 +805,7 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
         CU(cudaMemcpyAsync(dcur.p, cur.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(diters.p, run.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 #define EM2_LAUNCH(TPRV, QPTV)                                                                                          \
-    LAUNCH("em_pop", (em_pop_multi2_kernel<TPRV, QPTV>), dim3(gx, K), 256, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT, \
+    LAUNCH("em_pop", (em_pop_multi2_kernel<TPRV, QPTV>), dim3(gx, K), 256, smem, ctx->stream, ctx->G[0], ctx->ldg, M, dpops, K, FT, \
            FT1.as<float>(), dcur.as<int>(), diters.as<int>(), raw16, partials.as<double>(), hist.as<float>())
         if (packed) {
             if (tpr == 4 && qpt == 1) EM2_LAUNCH(4, 1); else if (tpr == 4 && qpt == 2) EM2_LAUNCH(4, 2); else if (tpr == 4) EM2_LAUNCH(4, 4);
@@ -809,11 +813,11 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
         }
 #undef EM2_LAUNCH
         else
-            LAUNCH("em_pop", em_pop_multi_kernel, dim3(gx, K), R * kEmT, smem, ctx->stream, ctx->G[0], ctx->ldg, M, ctx->d_pops, K, FT,
+            LAUNCH("em_pop", em_pop_multi_kernel, dim3(gx, K), R * kEmT, smem, ctx->stream, ctx->G[0], ctx->ldg, M, dpops, K, FT,
                    FT1.as<float>(), dcur.as<int>(), diters.as<int>(), row16, partials.as<double>());
         {   // 8 B per (site, individual of a running population) + f read/write, once per pass; one unit per (site, individual, iteration)
             double inds = 0, act = 0, units = 0;
-            for (int k = 0; k < K; ++k) if (run[k] > 0) { inds += ctx->pops[k].n; act += 1; units += (double)ctx->pops[k].n * run[k]; }
+            for (int k = 0; k < K; ++k) if (run[k] > 0) { inds += hpops[k].n; act += 1; units += (double)hpops[k].n * run[k]; }
             add_work(ctx, "em_pop", (double)M * inds * 8.0 + (double)M * act * 8.0, (double)M * units);
         }
         LAUNCH("em_ssq_reduce", em_ssq_reduce_kernel, (np + 7) / 8, 256, 0, ctx->stream, partials.as<double>(), gx, np, np, ssq.as<double>());
@@ -917,7 +921,7 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
 // iteration.  Every problem sees exactly the same sequence of updates and decisions either way.
 int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const unsigned char* mask, const double* d_count,
                std::vector<int>& iters_cols, const std::vector<unsigned char>* sel = nullptr,
-               const std::vector<cudaEvent_t>* pop_ready = nullptr)
+               const std::vector<cudaEvent_t>* pop_ready = nullptr, const std::function<int(int)>* on_pop = nullptr)
 {
     const long M = ctx->M();
     const int ldg = ctx->ldg, K = ctx->K;
@@ -1012,6 +1016,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         for (int k = 0; k < K; ++k) {
             PopDesc pd = ctx->pops[k];
             CU(cudaStreamWaitEvent(ctx->stream, (*pop_ready)[k], 0));       // device-side: the host keeps queueing
+            if (on_pop && (*on_pop)(k)) return 1;                           // the fused operator's full-data EM of this population
             if (pd.n <= 1) continue;
             if (packed) {
                 LAUNCH("loo_pack", loo_prepack_kernel, grid_for(M * cfgs[k].nc, 256, ctx->num_sm * 16), 256, 0, ctx->stream, ctx->G[0], ldg, M,
@@ -1290,36 +1295,59 @@ int32_t wgs_download(wgs_ctx* ctx, int64_t site0, int64_t nsites, float* L_out, 
     return 0;
 }
 
-static int ref_af_impl(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32_t* iters_out)
+// Per-population EM + clipping in three steps so that the fused operator can run the EM population by population
+// as the slabs of an asynchronous upload arrive: begin (buffers), em (all populations or one), finish (clip,
+// transpose to [M][K], copy out).
+struct RefAfRun { DevBuf FT; std::vector<int> its; };
+static int ref_af_begin(wgs_ctx* ctx, RefAfRun& run)
 {
     if (!ctx->G[0]) return fail(ctx, "no GL matrix resident");
     if (!ctx->pops_set) return fail(ctx, "wgs_set_pops must be called before wgs_upload_gl for reference-panel operators");
     const long M = ctx->M();
     const int K = ctx->K;
-    Trace tr("ref_af");
     dev_free(ctx, ctx->d_af);
     if (dev_alloc(ctx, &ctx->d_af, (size_t)std::max<long>(M, 1) * K)) return 1;
     ctx->af_rows = M; ctx->af_cols = K;
+    if (buf_alloc(ctx, run.FT, (size_t)std::max<long>(M, 1) * K * sizeof(float))) return 1;
+    run.its.assign(K, 0);
+    return 0;
+}
+static int ref_af_em_one(wgs_ctx* ctx, RefAfRun& run, int iter, double tole, int k)
+{
+    std::vector<int> it1;
+    if (run_em_pop(ctx, iter, tole, run.FT.as<float>() + (size_t)k * ctx->M(), it1, k, 1)) return 1;
+    run.its[k] = it1[0];
+    return 0;
+}
+static int ref_af_finish(wgs_ctx* ctx, RefAfRun& run, float* af_out, int32_t* iters_out)
+{
+    const long M = ctx->M();
+    const int K = ctx->K;
     float* F = ctx->d_af;
-    DevBuf FT;
-    if (buf_alloc(ctx, FT, (size_t)std::max<long>(M, 1) * K * sizeof(float))) return 1;
-    std::vector<int> its;
-    tr.lap("alloc");
-    if (run_em_pop(ctx, iter, tole, FT.as<float>(), its)) return 1;
-    tr.lap("em");
     std::vector<float> lo(K), hi(K);
     for (int k = 0; k < K; ++k) { double l = 1.0 / (2.0 * (ctx->pops[k].n + 1)); lo[k] = (float)l; hi[k] = (float)(1.0 - l); }
     DevBuf dlo, dhi;
     if (buf_alloc(ctx, dlo, K * sizeof(float)) || buf_alloc(ctx, dhi, K * sizeof(float))) return 1;
     CU(cudaMemcpyAsync(dlo.p, lo.data(), K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(dhi.p, hi.data(), K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH("clip", clip_transpose_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, FT.as<float>(), M, K,
+    LAUNCH("clip", clip_transpose_kernel, grid_for(M * K, 256, ctx->num_sm * 8), 256, 0, ctx->stream, run.FT.as<float>(), M, K,
            dlo.as<float>(), dhi.as<float>(), 1, F);
     if (af_out) CU(cudaMemcpyAsync(af_out, F, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
+    for (int k = 0; k < K; ++k) iters_out[k] = run.its[k];
+    return 0;
+}
+static int ref_af_impl(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32_t* iters_out)
+{
+    Trace tr("ref_af");
+    RefAfRun run;
+    if (ref_af_begin(ctx, run)) return 1;
+    tr.lap("alloc");
+    if (run_em_pop(ctx, iter, tole, run.FT.as<float>(), run.its)) return 1;
+    tr.lap("em");
+    if (ref_af_finish(ctx, run, af_out, iters_out)) return 1;
     tr.lap("clip+d2h");
-    for (int k = 0; k < K; ++k) iters_out[k] = its[k];
     return 0;
 }
 
@@ -1450,12 +1478,17 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
     std::vector<int> its_cols;
     CU(cudaStreamSynchronize(ctx->stream));
     tr.lap("alloc+h2d+init");
+    const bool pipelined = fused && ctx->upload_pending;
+    RefAfRun ref;
+    if (fused && ref_af_begin(ctx, ref)) return 1;
+    std::function<int(int)> on_pop = [&](int k) { return ref_af_em_one(ctx, ref, iter, tole, k); };
     if (run_em_loo(ctx, iter, tole, F.as<float>(), ldf, nullptr, nullptr, its_cols, nullptr,
-                   fused && ctx->upload_pending ? &ctx->ev_pop : nullptr)) return 1;
+                   pipelined ? &ctx->ev_pop : nullptr, pipelined ? &on_pop : nullptr)) return 1;
     tr.lap("em");
     if (fused) {
         upload_fence(ctx);                                       // every slab has been waited for on the device already
-        if (ref_af_impl(ctx, iter, tole, fused->af_out, fused->iters_out)) return 1;
+        if (!pipelined && run_em_pop(ctx, iter, tole, ref.FT.as<float>(), ref.its)) return 1;
+        if (ref_af_finish(ctx, ref, fused->af_out, fused->iters_out)) return 1;
         tr.lap("ref_af");
     }
     RawBuf dA{ctx->d_af};
