@@ -48,6 +48,23 @@ def main():
     zr = ctx.zscore(1, None, 0, False, 0, 12, 200, 1e-4)
     za = ctx.zscore(0, af, 0, False, 5, 20, 200, 1e-4)
     af_full, af_loo_full, f_full = dist.gather_rows(af), dist.gather_rows(af_in), dist.gather_rows(f_obs)
+    # the fused, pipelined call (asynchronous slab upload + wgs_ref_af_loo) on a second, population-contiguous data set
+    m2 = 30000
+    d2 = synth.synth(m2, 44, 4, seed=78, interleave=False, with_ad=False)
+    pops2, pop_of2 = np.unique(d2["IDs"][:, 1], return_inverse=True)
+    pop_of2 = pop_of2.astype(np.int32)
+    lo2, hi2 = dist.shard_range(m2, rank, world)
+    dist.enable(m2, lo2, device=torch.device("cuda", local))
+    L2 = _lib.pinned_empty((hi2 - lo2, d2["L"].shape[1]), np.float32)
+    L2[...] = d2["L"][lo2:hi2]
+    ctx2 = _lib.Context(local)
+    ctx2.set_pops(pop_of2, 4)
+    dist.attach(ctx2)
+    ctx2.upload_gl_async(L2)
+    faf, fits, fll, _, flits, _ = ctx2.ref_af_loo(200, 1e-4)
+    dist.allreduce_sum(fll)
+    faf_full = dist.gather_rows(faf)
+    dist.enable(m, lo, device=torch.device("cuda", local))
     ok = True
     if rank == 0:
         dist.disable()
@@ -64,9 +81,18 @@ def main():
         zr1 = one.zscore(1, None, 0, False, 0, 12, 200, 1e-4)
         za1 = one.zscore(0, af1, 0, False, 5, 20, 200, 1e-4)
 
+        one2 = _lib.Context(local)
+        one2.set_pops(pop_of2, 4)
+        one2.upload_gl(d2["L"])
+        gaf, gits = one2.ref_af(200, 1e-4)
+        gll, _, glits = one2.loo_partial(gaf.copy(), 200, 1e-4)
+
         def rel(a, b):
             return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
         checks = {
+            "fused iters": list(fits) == list(gits) and list(flits) == list(glits),
+            "fused af bitwise": np.array_equal(faf_full, gaf),
+            "fused ll": rel(fll, gll) < 1e-7,
             "ref_af iters": list(its) == list(its1),
             "ref_af bitwise": np.array_equal(af_full, af1),
             "loo iters": list(lits) == list(lits1),
