@@ -1755,8 +1755,13 @@ __device__ __forceinline__ void loo5_quad(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3
         const f32x2 D = ffma2(v, c[k].B, ffma2(u, c[k].A, P2));
         const f32x2 t = ffma2(P4, c[k].B43, P3);
         const f32x2 N = ffma2(t, c[k].BH, ffma2(P1, c[k].AH, P2));
-        const float2 dd = unpack2(D);
-        acc[k] = ffma2(N, pack2(fast_rcp(dd.x), fast_rcp(dd.y)), acc[k]);
+        // the two quotients are accumulated with scalar FFMAs: packing the two reciprocals into a register pair for
+        // one FFMA2 cost a move per reciprocal (12 of the 97 instructions of the cell loop) for the same FMA-pipe time
+        const float2 dd = unpack2(D), nn = unpack2(N);
+        float2 a = unpack2(acc[k]);
+        a.x = fmaf(nn.x, fast_rcp(dd.x), a.x);
+        a.y = fmaf(nn.y, fast_rcp(dd.y), a.y);
+        acc[k] = pack2(a.x, a.y);
     }
 }
 
