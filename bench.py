@@ -294,7 +294,7 @@ def main():
     barrier()
     dt = time.perf_counter() - t0
     launches = ctx.launch_count() - l0
-    fam = {k: family(ctx, k, hbm_peak, M_local) for k in ("loo_em", "em_pop", "loo_like")}
+    fam = {k: family(ctx, k, hbm_peak, M_local) for k in ("loo_em", "em_pop", "loo_like", "loo_pack")}
     ctx.timing_reset(False)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:

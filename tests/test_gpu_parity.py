@@ -352,7 +352,7 @@ def test_fallback_kernels_agree(wgs, monkeypatch):
     a0 = af.copy()
     ll, _, lits = ctx.loo_partial(a0, 200, 1e-4)
     f_obs, ne_obs, ind = ctx.fisher_partial(af)
-    for var in ("WGS_LOOLIKE_V1", "WGS_FISHER_V1", "WGS_EM_STEP", "WGS_EM_NO_LOOKAHEAD", "WGS_LOO_V4"):
+    for var in ("WGS_LOOLIKE_V1", "WGS_FISHER_V1", "WGS_EM_STEP", "WGS_EM_NO_LOOKAHEAD", "WGS_LOO_V4", "WGS_LOO_NOFIRST"):
         monkeypatch.setenv(var, "1")
     af2, its2 = ctx.ref_af(200, 1e-4)
     a1 = af2.copy()

@@ -993,9 +993,33 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         }
         return 0;
     };
+    // Iteration 1 starts every problem of a population from the same f: n evaluations per site serve all n problems
+    // (loo_first_kernel) instead of n^2.  Populations above 512 individuals take the general step kernel.
+    const bool use_first = getenv("WGS_LOO_NOFIRST") == nullptr;
+    auto first_tpr = [&](int k) {
+        int tpr = 2;
+        const int cpr = (ctx->pops[k].n + 1) / 2;
+        while (tpr < 32 && tpr * kFisherQ < cpr) tpr *= 2;
+        return tpr * kFisherQ >= cpr ? tpr : 0;
+    };
+    auto launch_iter = [&](int k, int it) -> int {
+        const int tpr = (it == 1 && use_first) ? first_tpr(k) : 0;
+        if (!tpr) return launch_step(k);
+        PopDesc pd = ctx->pops[k];
+        const size_t sm = (size_t)256 * 2 * kFisherQ * sizeof(float);
+#define LOO_FIRST(T)                                                                                             \
+    LAUNCH("loo_first", loo_first_kernel<T>, cfgs[k].grid, 256, sm, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n, F, ldf, \
+           st.active.as<int>(), mask, st.partials.as<double>())
+        if (tpr == 2) LOO_FIRST(2); else if (tpr == 4) LOO_FIRST(4); else if (tpr == 8) LOO_FIRST(8);
+        else if (tpr == 16) LOO_FIRST(16); else LOO_FIRST(32);
+#undef LOO_FIRST
+        add_work(ctx, "loo_first", (double)M * pd.n * 8.0 + (double)M * pd.n * 4.0, (double)M * pd.n);
+        return 0;
+    };
     // algorithmic work of one iteration of population k, from the flags that were in force when it ran: the
     // population's packed rows once + read/write of every active problem's f; n evaluations per active (site, problem)
-    auto account = [&](int k) {
+    auto account = [&](int k, int it) {
+        if (it == 1 && use_first && first_tpr(k)) return;           // accounted as "loo_first" at launch
         PopDesc pd = ctx->pops[k];
         double act = 0;
         for (int j = 0; j < pd.n; ++j) act += st.h_active[pd.col0 + j] ? 1 : 0;
@@ -1024,23 +1048,23 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
                 add_work(ctx, "loo_pack", (double)M * pd.n * 8.0 + (double)M * loo5_row_units(pd.n) * 16.0, (double)M * pd.n);
             }
             if (!pop_active(k) || iter < 1) continue;
-            if (launch_step(k) || em_after_step_queue(ctx, st, tole, 1, d_count, count_all, 1, pd.col0, pd.n)) return 1;
+            if (launch_iter(k, 1) || em_after_step_queue(ctx, st, tole, 1, d_count, count_all, 1, pd.col0, pd.n)) return 1;
             for (int it = 1; it <= iter; ++it) {
                 if (ahead && it < iter)
-                    if (launch_step(k) || em_after_step_queue(ctx, st, tole, it + 1, d_count, count_all, (it + 1) & 1, pd.col0, pd.n)) return 1;
+                    if (launch_iter(k, it + 1) || em_after_step_queue(ctx, st, tole, it + 1, d_count, count_all, (it + 1) & 1, pd.col0, pd.n)) return 1;
                 int n_act = 0;
-                account(k);
+                account(k, it);
                 if (em_after_step_wait(ctx, st, it & 1, &n_act)) return 1;
                 if (n_act == 0) break;
                 if (!ahead && it < iter)
-                    if (launch_step(k) || em_after_step_queue(ctx, st, tole, it + 1, d_count, count_all, (it + 1) & 1, pd.col0, pd.n)) return 1;
+                    if (launch_iter(k, it + 1) || em_after_step_queue(ctx, st, tole, it + 1, d_count, count_all, (it + 1) & 1, pd.col0, pd.n)) return 1;
             }
         }
     } else {
         auto queue_round = [&](int it) -> int {
             for (int k = 0; k < K; ++k) {
                 if (ctx->pops[k].n <= 1 || !pop_active(k)) continue;
-                if (launch_step(k)) return 1;
+                if (launch_iter(k, it)) return 1;
             }
             return em_after_step_queue(ctx, st, tole, it, d_count, count_all, it & 1);
         };
@@ -1050,7 +1074,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
             if (queue_round(1)) return 1;
             for (int it = 1; it <= iter; ++it) {
                 if (ahead && it < iter && queue_round(it + 1)) return 1;
-                for (int k = 0; k < K; ++k) if (ctx->pops[k].n > 1) account(k);
+                for (int k = 0; k < K; ++k) if (ctx->pops[k].n > 1) account(k, it);
                 if (em_after_step_wait(ctx, st, it & 1, &n_active)) return 1;
                 if (n_active == 0) break;
                 if (!ahead && it < iter && queue_round(it + 1)) return 1;

@@ -1916,6 +1916,107 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
     }
 }
 
+constexpr int kFisherQ = 8;   // 16-byte loads in flight per thread in the register-tile row kernels (loo_first, fisher2)
+// ---------------------------------------------------------------------------------------
+// loo_first: the FIRST leave-one-out EM iteration of one population.  Every problem starts from the same
+// f = 0.25 (emMAF.py:17), so the n posterior terms of a site are shared by all n problems: one pass of n
+// evaluations per site, f_j = (S - own_j) / (n - 1), instead of the n^2 of a general iteration - a whole
+// loo_em_step launch per population saved.  Same thread mapping as fisher2 (TPR adjacent lanes own a site row,
+// straight 16-byte loads from G, shuffle row sum, register accumulators for the per-problem squared changes);
+// same clamp, mask and `active` semantics and the same partials layout as the step kernels, whose grid it uses.
+// ---------------------------------------------------------------------------------------
+template <int TPR>
+__global__ void __launch_bounds__(256)
+loo_first_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n,
+                 float* __restrict__ F, int ldf,
+                 const int* __restrict__ active,            // [ldg]
+                 const unsigned char* __restrict__ mask,    // [M][ldg] or null
+                 double* __restrict__ partials)             // [gridDim.x][ldg]
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* red = reinterpret_cast<float*>(smem_raw);      // [R][2 * TPR * kFisherQ]
+    constexpr int R = 256 / TPR;
+    constexpr int RW = 2 * TPR * kFisherQ;
+    const int t = threadIdx.x, r = t / TPR, h = t % TPR;
+    const int cpr = (n + 1) >> 1;
+    const long ntiles = (M + R - 1) / R;
+    const float f0 = 0.25f;
+    const Loo5Coef c = loo5_coef(f0);
+    const float inv_div = 1.0f / (float)(n - 1);
+    unsigned act = 0;                                     // bit 2j / 2j+1: this thread's individuals (2q, 2q+1), q = h + j TPR, iterate
+#pragma unroll
+    for (int j = 0; j < kFisherQ; ++j) {
+        const int q = h + j * TPR;
+        if (q < cpr) {
+            if (active[col0 + 2 * q]) act |= 1u << (2 * j);
+            if (2 * q + 1 < n && active[col0 + 2 * q + 1]) act |= 2u << (2 * j);
+        }
+    }
+    float sa[kFisherQ], sb[kFisherQ];
+#pragma unroll
+    for (int j = 0; j < kFisherQ; ++j) { sa[j] = 0.f; sb[j] = 0.f; }
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long s = tile * R + r;
+        const bool live = s < M;
+        float4 v[kFisherQ];
+        const float4* row = reinterpret_cast<const float4*>(G + (live ? s : 0) * (long)ldg + col0);
+#pragma unroll
+        for (int j = 0; j < kFisherQ; ++j) {
+            const int q = h + j * TPR;
+            v[j] = make_float4(1.f, 0.f, 1.f, 0.f);         // (1,0,0): an exactly zero term
+            if (live && q < cpr) v[j] = ld_stream4(row + q);
+        }
+        float pa[kFisherQ], pb[kFisherQ];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kFisherQ; ++j) {
+            const int q = h + j * TPR;
+            pa[j] = 0.f; pb[j] = 0.f;
+            if (live && q < cpr) {
+                pa[j] = loo5_own(v[j].x, v[j].y, third_gl(v[j].x, v[j].y), c);
+                if (2 * q + 1 < n) pb[j] = loo5_own(v[j].z, v[j].w, third_gl(v[j].z, v[j].w), c);
+            }
+            sum += pa[j] + pb[j];
+        }
+#pragma unroll
+        for (int o = 1; o < TPR; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < kFisherQ; ++j) {
+                const int q = h + j * TPR;
+                if (q < cpr) {
+                    unsigned ok = (act >> (2 * j)) & 3u;
+                    if (ok && mask) {
+                        const uchar2 mk = *reinterpret_cast<const uchar2*>(&mask[s * (long)ldg + col0 + 2 * q]);
+                        ok &= (mk.x ? 1u : 0u) | (mk.y ? 2u : 0u);
+                    }
+                    float fa = (sum - pa[j]) * inv_div, fb = (sum - pb[j]) * inv_div;
+                    if (fa < 1e-12f) fa = 1e-12f;           // comparisons are false for NaN: NaN survives
+                    if (fa > 0.99999994f) fa = 0.99999994f;
+                    if (fb < 1e-12f) fb = 1e-12f;
+                    if (fb > 0.99999994f) fb = 0.99999994f;
+                    float2 out = make_float2(f0, f0);       // frozen / masked problems and the pad keep the start value
+                    if (ok & 1u) { const float d = fa - f0; sa[j] = fmaf(d, d, sa[j]); out.x = fa; }
+                    if (ok & 2u) { const float d = fb - f0; sb[j] = fmaf(d, d, sb[j]); out.y = fb; }
+                    if (ok) *reinterpret_cast<float2*>(&F[s * (long)ldf + col0 + 2 * q]) = out;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kFisherQ; ++j) {
+        const int q = h + j * TPR;
+        red[r * RW + 2 * q] = sa[j];
+        red[r * RW + 2 * q + 1] = sb[j];
+    }
+    __syncthreads();
+    for (int j = t; j < n; j += blockDim.x) {
+        double vsum = 0.0;
+        for (int rr = 0; rr < R; ++rr) vsum += (double)red[rr * RW + j];
+        partials[(long)blockIdx.x * ldg + col0 + j] = vsum;
+    }
+}
+
 // ssq[p] = sum over blocks of partials[block][p], in a fixed order: one warp per problem, lane l adds blocks
 // l, l+32, ... in sequence, then a shuffle tree - the same bits for a given number of blocks, and a few
 // microseconds instead of one thread walking every block (this kernel sits between two EM iterations).
@@ -2157,7 +2258,6 @@ fisher_kernel(const float2* __restrict__ G, int ldg, long M,
 // shuffle over the TPR lanes, and the per-individual sums are REGISTER accumulators (a thread always serves
 // the same 2 x kFisherQ individuals), reduced over the rows of the block once, at the end, in fixed order.
 // ---------------------------------------------------------------------------------------
-constexpr int kFisherQ = 8;
 template <int TPR>
 __global__ void __launch_bounds__(256)
 fisher2_kernel(const float2* __restrict__ G, int ldg, long M,
