@@ -929,6 +929,23 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     for (int c = 0; c < ldg; ++c)
         if (ctx->ind_of_col[c] >= 0 && ctx->pops[ctx->pop_of_col[c]].n > 1 && (!sel || (*sel)[c])) active0[c] = 1;
     std::vector<LooLaunch> cfgs(K);
+    // packed rows of population k: through a shared-memory tile of whole rows when at least one row fits a block
+    auto launch_prepack = [&](int k, ulonglong2* PKk) -> int {
+        const PopDesc pd = ctx->pops[k];
+        const int nc = cfgs[k].nc;
+        const size_t sm = (size_t)(256 / std::max(nc, 1)) * loo5_row_units(pd.n) * sizeof(ulonglong2);
+        if (nc <= 256 && sm <= 64 * 1024 && getenv("WGS_PREPACK_V1") == nullptr) {
+            CU(cudaFuncSetAttribute(loo_prepack2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            const long ntl = (M + 256 / nc - 1) / (256 / nc);
+            LAUNCH("loo_pack", loo_prepack2_kernel, (int)std::max<long>(1, std::min<long>(ntl, (long)ctx->num_sm * 5)), 256, sm, ctx->stream,
+                   ctx->G[0], ldg, M, pd.col0, pd.n, nc, PKk);
+        } else {
+            LAUNCH("loo_pack", loo_prepack_kernel, grid_for(M * nc, 256, ctx->num_sm * 16), 256, 0, ctx->stream, ctx->G[0], ldg, M,
+                   pd.col0, pd.n, nc, PKk);
+        }
+        add_work(ctx, "loo_pack", (double)M * pd.n * 8.0 + (double)M * loo5_row_units(pd.n) * 16.0, (double)M * pd.n);
+        return 0;
+    };
     int nblocks = 1;
     for (int k = 0; k < K; ++k) {
         if (ctx->pops[k].n <= 1) continue;
@@ -951,9 +968,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         if (loo_cfg(ctx, ctx->pops[k].n, packed, &cfgs[k])) return 1;
         nblocks = std::max(nblocks, cfgs[k].grid);
         if (packed && !pop_ready) {
-            LAUNCH("loo_pack", loo_prepack_kernel, grid_for(M * cfgs[k].nc, 256, ctx->num_sm * 16), 256, 0, ctx->stream, ctx->G[0], ldg, M,
-                   ctx->pops[k].col0, ctx->pops[k].n, cfgs[k].nc, pk[k].as<ulonglong2>());
-            add_work(ctx, "loo_pack", (double)M * ctx->pops[k].n * 8.0 + (double)M * loo5_row_units(ctx->pops[k].n) * 16.0, (double)M * ctx->pops[k].n);
+            if (launch_prepack(k, pk[k].as<ulonglong2>())) return 1;
         }
     }
     EmState st;
@@ -1043,9 +1058,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
             if (on_pop && (*on_pop)(k)) return 1;                           // the fused operator's full-data EM of this population
             if (pd.n <= 1) continue;
             if (packed) {
-                LAUNCH("loo_pack", loo_prepack_kernel, grid_for(M * cfgs[k].nc, 256, ctx->num_sm * 16), 256, 0, ctx->stream, ctx->G[0], ldg, M,
-                       pd.col0, pd.n, cfgs[k].nc, pk[k].as<ulonglong2>());
-                add_work(ctx, "loo_pack", (double)M * pd.n * 8.0 + (double)M * loo5_row_units(pd.n) * 16.0, (double)M * pd.n);
+                if (launch_prepack(k, pk[k].as<ulonglong2>())) return 1;
             }
             if (!pop_active(k) || iter < 1) continue;
             if (launch_iter(k, 1) || em_after_step_queue(ctx, st, tole, 1, d_count, count_all, 1, pd.col0, pd.n)) return 1;
