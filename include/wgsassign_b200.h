@@ -89,6 +89,15 @@ int32_t wgs_upload_ad(wgs_ctx *ctx, const int32_t *AD, int64_t M, int32_t N);
 int32_t wgs_set_shard(wgs_ctx *ctx, int64_t M_total, int64_t site_offset,
                       wgs_allreduce_fn fn, void *user);
 
+/* Optional NCCL communicator for the sharded EM stop rule.  Without it the per-iteration sums of squared
+ * changes pass through `fn` on the host (one round trip per iteration); with it they are all-gathered on the
+ * compute stream (NVLink) and added in rank order on the device, so a sharded EM runs with the same
+ * look-ahead launch schedule as a single GPU.  libnccl.so.2 is bound at run time (dlopen).  Rank 0 calls
+ * wgs_nccl_unique_id (128 bytes out) and distributes the id; every rank then calls wgs_nccl_init (collective).
+ * `fn` is still required (class tallies and final sums use it). */
+int32_t wgs_nccl_unique_id(void *id_out128);
+int32_t wgs_nccl_init(wgs_ctx *ctx, const void *id128, int32_t rank, int32_t world);
+
 /* Device-side seeded synthetic data of the SURVEY 8d model (benchmarks): fills the resident
  * GL (and AD when with_ad) for M sites x N individuals; requires wgs_set_pops first. */
 int32_t wgs_synth(wgs_ctx *ctx, int64_t M, int32_t N, uint64_t seed, float depth, int32_t with_ad);

@@ -39,6 +39,8 @@ SYMBOLS = {
     "wgs_host_free": (None, [_vp]),
     "wgs_set_pops": (_i32, [_vp, _vp, _i32, _i32]),
     "wgs_upload_gl": (_i32, [_vp, _vp, _i64, _i32, _i32]),
+    "wgs_nccl_unique_id": (_i32, [_vp]),
+    "wgs_nccl_init": (_i32, [_vp, _vp, _i32, _i32]),
     "wgs_upload_gl_async": (_i32, [_vp, _vp, _i64, _i32]),
     "wgs_upload_wait": (_i32, [_vp]),
     "wgs_upload_ad": (_i32, [_vp, _vp, _i64, _i32]),
@@ -205,6 +207,12 @@ class Context:
             self._cb = ALLREDUCE_FN(_tramp)
         self._ck(lib().wgs_set_shard(self._h, int(M_total), int(site_offset), self._cb, None))
 
+    def nccl_init(self, uid, rank, world):
+        """Collective: give this context an NCCL communicator for the sharded EM stop rule (uid: the 128 bytes
+        rank 0 obtained from nccl_unique_id())."""
+        buf = ctypes.create_string_buffer(bytes(uid), 128)
+        self._ck(lib().wgs_nccl_init(self._h, ctypes.cast(buf, ctypes.c_void_p), int(rank), int(world)))
+
     def synth(self, M, N, seed=0, depth=2.0, with_ad=False):
         self._ck(lib().wgs_synth(self._h, int(M), int(N), int(seed), float(depth), int(with_ad)))
         self.M, self.N = int(M), int(N)
@@ -348,6 +356,13 @@ class Context:
         u = ctypes.c_double(0)
         self._ck(lib().wgs_timing_work(self._h, name.encode(), ctypes.byref(b), ctypes.byref(u)))
         return dict(ms=ms.value, launches=n.value, bytes=b.value, units=u.value)
+
+
+def nccl_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    if lib().wgs_nccl_unique_id(ctypes.cast(buf, ctypes.c_void_p)) != 0:
+        raise WgsError(lib().wgs_last_error(None).decode())
+    return buf.raw
 
 
 def pinned_empty(shape, dtype):

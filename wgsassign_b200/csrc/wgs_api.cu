@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <limits>
 #include <functional>
 #include <map>
@@ -58,6 +59,11 @@ struct wgs_ctx {
     int* em_pin_dev[2] = {nullptr, nullptr};
     size_t em_pin_cap = 0;
     cudaEvent_t em_ev[2] = {nullptr, nullptr};
+
+    // NCCL communicator for the EM stop rule under site sharding (wgs_nccl_init): the squared changes are
+    // all-gathered on the compute stream, so the sharded EM keeps the single-GPU look-ahead schedule
+    void* nccl_comm = nullptr;
+    int nccl_rank = 0, nccl_world = 1;
 
     // sharding
     long M_total = -1, site_offset = 0;
@@ -106,6 +112,34 @@ int fail(wgs_ctx* c, const char* fmt, ...)
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// ---- NCCL, bound at run time (the process usually has torch's libnccl.so.2 loaded already) ----------------
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ struct NcclId128, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId128 { char internal[128]; };
+NcclApi g_nccl;
+bool nccl_load()
+{
+    if (g_nccl.lib) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId128, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) return false;
+    g_nccl.lib = h;
+    return true;
+}
+constexpr int kNcclFloat64 = 8;                                 // ncclDataType_t::ncclFloat64 (nccl.h)
 
 int name_id(wgs_ctx* ctx, const char* name)
 {
@@ -619,7 +653,7 @@ struct EmState {
     int np = 0;                  // problems (columns of the partials)
     int ld = 0;                  // leading dimension of partials
     int nblocks = 0;
-    DevBuf partials, ssq, count, active, iters;
+    DevBuf partials, ssq, count, active, iters, gathered;
     std::vector<int> h_active, h_iters;
     int slot_c0[2] = {0, 0}, slot_nc[2] = {0, 0};
 };
@@ -670,7 +704,14 @@ int em_after_step_queue(wgs_ctx* ctx, EmState& st, double tole, int iteration, c
     if (nc < 0) nc = st.np;
     LAUNCH("em_ssq_reduce", em_ssq_reduce_kernel, (nc + 7) / 8, 256, 0, ctx->stream,
            st.partials.as<double>() + c0, st.nblocks, nc, st.ld, st.ssq.as<double>() + c0);
-    if (ctx->fn) {
+    if (ctx->fn && ctx->nccl_comm) {
+        // all ranks' local sums, gathered on the stream and added in rank order: no host in the loop
+        if (!st.gathered.p && buf_alloc(ctx, st.gathered, (size_t)ctx->nccl_world * st.np * sizeof(double))) return 1;
+        int rc_ = g_nccl.AllGather(st.ssq.as<double>() + c0, st.gathered.p, (size_t)nc, kNcclFloat64, ctx->nccl_comm, ctx->stream);
+        if (rc_) return fail(ctx, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc_) : "?");
+        LAUNCH("em_ssq_reduce", em_rank_sum_kernel, grid_for(nc, 128, 64), 128, 0, ctx->stream, st.gathered.as<double>(), ctx->nccl_world, nc,
+               st.ssq.as<double>() + c0);
+    } else if (ctx->fn) {
         std::vector<double> h(nc);
         CU(cudaMemcpyAsync(h.data(), st.ssq.as<double>() + c0, nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -1049,7 +1090,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     // Look-ahead: iteration t+1 is queued before the host has read the decision of iteration t (the device skips
     // whatever that decision froze), so the GPU never idles on the round trip.  Not under site sharding, where the
     // squared changes pass through the host for the all-reduce anyway.
-    const bool ahead = ctx->fn == nullptr && getenv("WGS_EM_NO_LOOKAHEAD") == nullptr;
+    const bool ahead = (ctx->fn == nullptr || ctx->nccl_comm != nullptr) && getenv("WGS_EM_NO_LOOKAHEAD") == nullptr;
     const double count_all = (double)ctx->Mtot();
     if (pop_ready) {
         for (int k = 0; k < K; ++k) {
@@ -1158,6 +1199,7 @@ void wgs_destroy(wgs_ctx* ctx)
     drop_data(ctx);
     dev_free(ctx, ctx->d_ind_of_col); dev_free(ctx, ctx->d_col_of_ind); dev_free(ctx, ctx->d_pop_of_col); dev_free(ctx, ctx->d_pops);
     pool_trim(ctx);
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     for (cudaEvent_t e : ctx->ev_pop) cudaEventDestroy(e);
     for (int b = 0; b < 2; ++b) { if (ctx->em_pin[b]) cudaFreeHost(ctx->em_pin[b]); if (ctx->em_ev[b]) cudaEventDestroy(ctx->em_ev[b]); }
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
@@ -1180,6 +1222,30 @@ int32_t wgs_set_pops(wgs_ctx* ctx, const int32_t* pop_of_ind, int32_t N, int32_t
     drop_data(ctx);
     ctx->pops_set = K > 0;
     return build_structure(ctx, pop_of_ind, N, K);
+}
+
+int32_t wgs_nccl_unique_id(void* id_out)
+{
+    if (!nccl_load()) return fail(nullptr, "libnccl.so.2 could not be loaded");
+    int rc = g_nccl.GetUniqueId(id_out);
+    if (rc) return fail(nullptr, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return 0;
+}
+
+int32_t wgs_nccl_init(wgs_ctx* ctx, const void* id, int32_t rank, int32_t world)
+{
+    cudaSetDevice(ctx->device);
+    upload_fence(ctx);
+    if (!nccl_load()) return fail(ctx, "libnccl.so.2 could not be loaded");
+    if (ctx->nccl_comm) { g_nccl.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+    if (world <= 1) return 0;
+    NcclId128 uid;
+    memcpy(&uid, id, sizeof uid);
+    void* comm = nullptr;
+    int rc = g_nccl.CommInitRank(&comm, world, uid, rank);
+    if (rc) return fail(ctx, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    ctx->nccl_comm = comm; ctx->nccl_rank = rank; ctx->nccl_world = world;
+    return 0;
 }
 
 int32_t wgs_set_shard(wgs_ctx* ctx, int64_t M_total, int64_t site_offset, wgs_allreduce_fn fn, void* user)

@@ -2109,6 +2109,17 @@ em_ssq_reduce_kernel(const double* __restrict__ partials, int nblocks, int np, i
     if (lane == 0) ssq[p] = v;
 }
 
+// ssq[p] = sum over ranks, IN RANK ORDER, of gathered[rank][p] (the output of an NCCL all-gather of every rank's
+// local sums): every rank computes the same bits, and they do not depend on how NCCL would have reduced.
+__global__ void em_rank_sum_kernel(const double* __restrict__ gathered, int world, int np, double* __restrict__ ssq)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        double v = 0.0;
+        for (int r = 0; r < world; ++r) v += gathered[(long)r * np + p];
+        ssq[p] = v;
+    }
+}
+
 // Stop rule of emMAF.py:21-25 with rmse1d's float divide / double sqrt (emMAF_cy.pyx:32-33).
 // count[p] = number of sites in problem p's sum.  Single block.  result (mapped pinned host memory):
 // [0] = problems still active, [1 + p] = the updated flag of problem p.

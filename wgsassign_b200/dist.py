@@ -90,8 +90,18 @@ def gather_rows(arr):
 
 
 def attach(ctx):
-    """Give a Context the shard geometry and the all-reduce callback."""
+    """Give a Context the shard geometry, the all-reduce callback and - on GPUs - its own NCCL communicator
+    for the EM stop rule (the id is created by rank 0 and broadcast through torch.distributed)."""
     if enabled():
         ctx.set_shard(_cfg["M_total"], _cfg["offset"], allreduce_sum)
+        import os
+        import torch.distributed as td
+        if _cfg["device"] is not None and td.get_backend() == "nccl" and not os.environ.get("WGS_NO_NCCL") \
+                and not getattr(ctx, "_nccl_ready", False):
+            from . import _lib
+            box = [_lib.nccl_unique_id() if _cfg["rank"] == 0 else None]
+            td.broadcast_object_list(box, src=0)
+            ctx.nccl_init(box[0], _cfg["rank"], _cfg["world"])
+            ctx._nccl_ready = True
     else:
         ctx.set_shard(-1, 0, None)
