@@ -1234,8 +1234,7 @@ int32_t wgs_nccl_unique_id(void* id_out)
 
 int32_t wgs_nccl_init(wgs_ctx* ctx, const void* id, int32_t rank, int32_t world)
 {
-    cudaSetDevice(ctx->device);
-    upload_fence(ctx);
+    cudaSetDevice(ctx->device);                                  // no upload fence: the communicator does not touch the matrix
     if (!nccl_load()) return fail(ctx, "libnccl.so.2 could not be loaded");
     if (ctx->nccl_comm) { g_nccl.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
     if (world <= 1) return 0;

@@ -225,6 +225,22 @@ __global__ void af_margin_kernel(const float* __restrict__ A, long n, int* __res
     if ((threadIdx.x & 31) == 0) atomicMin(out_bits, __float_as_int(m));   // m >= 0: int order == float order
 }
 
+// Explicit shared-space accesses with 32-bit addresses.  (nvcc re-derives the shared window base - S2UR
+// SR_CgaCtaId, UMOV, ULEA - around every generic-pointer store into dynamic shared memory it cannot hoist: 5 of the
+// 17 instructions per element of loo_like2's cell staging.)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts128(unsigned addr, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float lds32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+// max / min that return NaN when the first operand is NaN (the second never is): `if (a < lo) a = lo` in one instruction
+__device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
 // ---------------------------------------------------------------------------------------
 // Likelihood accumulation without a logarithm per evaluation.
 //
@@ -939,7 +955,8 @@ loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
     LikeAcc<KT> acc;
     acc.init();
     int cnt = 0;
-    const unsigned row_bytes = 16u * (unsigned)ldf;
+    const unsigned row_bytes = 16u * (unsigned)ldf, row_bytes_raw = 4u * (unsigned)ldf;
+    const unsigned hq_a = smem_u32(Hq), raw_a = smem_u32(raw);
     for (int j = 0; j < ntiles; ++j) {
         const long s0 = s_begin + (long)j * TS;
         const int rows = (int)min((long)TS, s_end - s0);
@@ -949,17 +966,16 @@ loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
         // rewritten (a separate clamp pass over it was 1.4 ms at 1M x 500)
         for (int c = t; c < ldf; c += blockDim.x) {       // a thread takes whole columns: its bounds are loaded once per tile
             const float lo = clip_s[c], hi = clip_s[ldf + c];
+            const unsigned ra = raw_a + 4u * (unsigned)c, ha = hq_a + 16u * (unsigned)c;
             float av[TSMAX];
 #pragma unroll
-            for (int u = 0; u < TSMAX; ++u) av[u] = u < rows ? raw[u * ldf + c] : 0.5f;
+            for (int u = 0; u < TSMAX; ++u) av[u] = u < rows ? lds32(ra + (unsigned)u * row_bytes_raw) : 0.5f;
 #pragma unroll
             for (int u = 0; u < TSMAX; ++u) {
                 if (u < rows) {
-                    float a = av[u];
-                    if (a < lo) a = lo;                   // comparisons are false for NaN: NaN survives (FMNMX.NAN)
-                    if (a > hi) a = hi;
+                    const float a = fmin_nan(fmax_nan(av[u], lo), hi);      // NaN survives, like the reference's compare-and-assign
                     const float om = 1.0f - a;
-                    Hq[u * ldf + c] = make_float4(om * om, 2.0f * a * om, a * a, 0.0f);
+                    sts128(ha + (unsigned)u * row_bytes, om * om, (a + a) * om, a * a, 0.0f);
                 }
             }
         }
@@ -980,8 +996,10 @@ loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
                         const float g0 = gq.x, g1 = gq.y, g2 = third_gl(g0, g1);
 #pragma unroll
                         for (int kk = 0; kk < KT; ++kk) {
-                            const float4 h = *reinterpret_cast<const float4*>(hrow + roff[kk]);
-                            const float like = fmaf(g0, h.x, fmaf(g1, h.y, g2 * h.z));
+                            // 8 + 4 bytes: 3 shared-memory wavefronts per warp instead of the 4 of one LDS.128
+                            const float2 h = *reinterpret_cast<const float2*>(hrow + roff[kk]);
+                            const float hz = *reinterpret_cast<const float*>(hrow + roff[kk] + 8);
+                            const float like = fmaf(g0, h.x, fmaf(g1, h.y, g2 * hz));
                             acc.prod[kk] *= like;
                         }
                         if (++cnt == R) { acc.renorm(); cnt = 0; }
@@ -1807,8 +1825,9 @@ struct Loo5Coef { f32x2 A, B, AH, B43, BH; float a, b; };
 __device__ __forceinline__ Loo5Coef loo5_coef(float f) {
     Loo5Coef c;
     const float om = 1.0f - f;
-    c.a = om * fast_rcp(f);
-    c.b = f * fast_rcp(om);
+    const float r = fast_rcp(f * om);                   // one reciprocal for both ratios (the XU pipe is co-critical here)
+    c.a = om * om * r;
+    c.b = f * f * r;
     const float ah = 0.5f * c.a, b43 = 1.33333337f * c.b, bh = 1.5f * c.b;
     c.A = pack2(c.a, c.a); c.B = pack2(c.b, c.b); c.AH = pack2(ah, ah); c.B43 = pack2(b43, b43); c.BH = pack2(bh, bh);
     return c;
