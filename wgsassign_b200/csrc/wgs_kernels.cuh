@@ -1319,18 +1319,31 @@ em_pop_multi2_kernel(const float2* __restrict__ G, int ldg, long M,
     // Warp-private staging: every warp copies the RW slab rows it will consume with 16-byte LDGSTS into its own
     // slice of a double buffer, one tile ahead - no block-wide barrier in the loop (the TMA + __syncthreads version
     // stalled 3 cycles per issue at that barrier), warps drift freely.
+    // The (row, unit) each lane copies is the same for every tile: worked out once, as a shared-memory offset and a
+    // global offset (in 16-byte units) per copy - the copy loop itself is then 8 predicated LDGSTS.  (Walking the
+    // row/unit counters in the loop was a quarter of this kernel's instructions.)
+    constexpr int kCopies = (RW * 2 * TPR * QPT + 31) / 32;        // units of the warp's RW rows / 32 lanes, at most 8
+    int so[kCopies], go[kCopies];
+    {
+        int rr = 0, q = lane;
+#pragma unroll
+        for (int i = 0; i < kCopies; ++i) {
+            while (q >= nq2 && rr < RW) { q -= nq2; ++rr; }
+            so[i] = rr < RW ? rr * raw16 + q : -1;
+            go[i] = rr < RW ? rr * (ldg >> 1) + q : 0;              // a row of G is ldg pairs = ldg / 2 units
+            q += 32;
+        }
+    }
+    const float4* Gslab = reinterpret_cast<const float4*>(G + pd.col0);
     auto stage = [&](long tile, int buf) {
         if (tile < ntiles) {
             const long s0 = tile * R + warp * RW;
             float4* dst = raw + ((size_t)buf * R + warp * RW) * raw16;
-            int rr = 0, q = lane;
-            while (q >= nq2) { q -= nq2; ++rr; }
-            while (rr < RW) {
-                if (s0 + rr < M)
-                    cp_async16(dst + (size_t)rr * raw16 + q, reinterpret_cast<const float4*>(G + (s0 + rr) * (long)ldg + pd.col0) + q);
-                q += 32;
-                while (q >= nq2) { q -= nq2; ++rr; }
-            }
+            const float4* src = Gslab + s0 * (long)(ldg >> 1);
+            const int rows_ok = (int)min((long)RW, M - s0);       // rows of this warp's slice that exist (<= 0: none)
+#pragma unroll
+            for (int i = 0; i < kCopies; ++i)
+                if (so[i] >= 0 && (rows_ok >= RW || so[i] < rows_ok * raw16)) cp_async16(dst + so[i], src + go[i]);
         }
         cp_async_commit();
     };
@@ -1374,7 +1387,7 @@ em_pop_multi2_kernel(const float2* __restrict__ G, int ldg, long M,
                 const float om = 1.0f - f;
                 const float ca = om * fast_rcp(f), cb = f * fast_rcp(om);
                 const f32x2 A = pack2(ca, ca), B = pack2(cb, cb);
-                f32x2 acc = 0ull;
+                float accx = 0.f, accy = 0.f;                 // scalar accumulation: no register-pair packing of the reciprocals
 #pragma unroll
                 for (int j = 0; j < QPT; ++j) {
                     const f32x2 nu = ffma2(g2ab[j], B, g1ab[j]);
@@ -1383,11 +1396,11 @@ em_pop_multi2_kernel(const float2* __restrict__ G, int ldg, long M,
                     const f32x2 dv = ffma2(g0cd[j], A, fadd2(g1cd[j], nv));
                     const f32x2 m = fmul2(du, dv);
                     const f32x2 x = ffma2(nv, du, fmul2(nu, dv));
-                    const float2 mm = unpack2(m);
-                    acc = ffma2(x, pack2(fast_rcp(mm.x), fast_rcp(mm.y)), acc);
+                    const float2 mm = unpack2(m), xx = unpack2(x);
+                    accx = fmaf(xx.x, fast_rcp(mm.x), accx);
+                    accy = fmaf(xx.y, fast_rcp(mm.y), accy);
                 }
-                const float2 a2 = unpack2(acc);
-                float sum = a2.x + a2.y;
+                float sum = accx + accy;
 #pragma unroll
                 for (int o = 1; o < TPR; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);   // the TPR slices of a row sit in adjacent lanes
                 float fnew = __fdiv_rn(sum, fn);                // identical in the TPR lanes of a row
