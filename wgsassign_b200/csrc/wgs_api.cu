@@ -1911,7 +1911,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
                 int mx = 0; float mv = m0;
                 if (m1 > mv) { mx = 1; mv = m1; }
                 if (m2 > mv) { mx = 2; mv = m2; }
-                kmax[g] = (signed char)mx; kmean[g] = mv;
+                kmax[(size_t)id * ldg + col] = (signed char)mx; kmean[(size_t)id * ldg + col] = mv;
                 zlike_t[(size_t)id * ldg + col] = make_float4(m0, m1, m2, 0.f);
                 rows.push_back(ref); rows.push_back(alt); rows.push_back(d); rows.push_back((int)t[id]);
                 ++n_classes[i];
@@ -1925,7 +1925,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
                     if (t[id] <= 0) continue;
                     size_t g = (size_t)col * ncls + id;
                     float row[7] = {(float)(d - alt), (float)alt, (float)t[id], cmean[3 * g], cmean[3 * g + 1], cmean[3 * g + 2],
-                                    kmax[g] >= 0 ? 1.f : 0.f};
+                                    kmax[(size_t)id * ldg + col] >= 0 ? 1.f : 0.f};
                     tab.insert(tab.end(), row, row + 7);
                 }
         }
@@ -1934,19 +1934,17 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
 
     tr.lap("class decisions");
     DevBuf dkmax, dkmean, dlike, dfac, dkeep, dkept;
-    if (buf_alloc(ctx, dkmax, tab_n) || buf_alloc(ctx, dkmean, tab_n * sizeof(float)) || buf_alloc(ctx, dlike, ctab_n * sizeof(float4)) ||
+    if (buf_alloc(ctx, dkmax, ctab_n) || buf_alloc(ctx, dkmean, ctab_n * sizeof(float)) || buf_alloc(ctx, dlike, ctab_n * sizeof(float4)) ||
         buf_alloc(ctx, dfac, (size_t)ncls * sizeof(float4)) || buf_alloc(ctx, dkeep, (size_t)std::max<long>(M, 1) * ldg) ||
         buf_alloc(ctx, dkept, ldg * sizeof(unsigned long long))) return 1;
-    // compact host tables -> the dense device layout; classes deeper than dmax do not occur ("not kept" = -1)
-    CU(cudaMemsetAsync(dkmax.p, 0xFF, tab_n, ctx->stream));
-    CU(cudaMemcpy2DAsync(dkmax.p, (size_t)kZClasses, kmax.data(), (size_t)ncls, (size_t)ncls, (size_t)ldg, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpy2DAsync(dkmean.p, (size_t)kZClasses * sizeof(float), kmean.data(), (size_t)ncls * sizeof(float), (size_t)ncls * sizeof(float),
-                         (size_t)ldg, cudaMemcpyHostToDevice, ctx->stream));
+    // class-major host tables [ncls][ldg] go up as they are; classes deeper than dmax do not occur (the kernels treat them as "not kept")
+    CU(cudaMemcpyAsync(dkmax.p, kmax.data(), ctab_n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dkmean.p, kmean.data(), ctab_n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(dlike.p, zlike_t.data(), ctab_n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(dfac.p, fac_of_class.data(), (size_t)ncls * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(dkept.p, 0, ldg * sizeof(unsigned long long), ctx->stream));
     LAUNCH("zkeep", zkeep_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
-           dkmax.as<signed char>(), dkmean.as<float>(), c.wx, c.sites_per_block, dkeep.as<unsigned char>(), dkept.as<unsigned long long>());
+           dkmax.as<signed char>(), dkmean.as<float>(), ncls, c.wx, c.sites_per_block, dkeep.as<unsigned char>(), dkept.as<unsigned long long>());
     add_work(ctx, "zkeep", pairs * 11.0, pairs);
     std::vector<long long> kept(ldg);
     CU(cudaMemcpyAsync(kept.data(), dkept.p, ldg * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2060,7 +2058,7 @@ int32_t wgs_zkeep_one(wgs_ctx* ctx, int32_t ind, int32_t n_classes, const int32_
         int mx = 0; float mv = m[0];
         if (m[1] > mv) { mx = 1; mv = m[1]; }
         if (m[2] > mv) { mx = 2; mv = m[2]; }
-        size_t g = (size_t)col * kZClasses + zclass_id(ref, alt);
+        size_t g = (size_t)zclass_id(ref, alt) * ldg + col;     // class-major, like wgs_zscore's tables
         kmax[g] = (signed char)mx; kmean[g] = mv;
     }
     std::vector<unsigned char> sel(ldg, 0);
@@ -2074,7 +2072,7 @@ int32_t wgs_zkeep_one(wgs_ctx* ctx, int32_t ind, int32_t n_classes, const int32_
     CU(cudaMemsetAsync(dkept.p, 0, ldg * sizeof(unsigned long long), ctx->stream));
     LikeCfg c = like_cfg(ctx, M, 4);
     LAUNCH("zkeep", zkeep_kernel, dim3(c.gx, c.gy), 256, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
-           dkmax.as<signed char>(), dkmean.as<float>(), c.wx, c.sites_per_block, dkeep.as<unsigned char>(), dkept.as<unsigned long long>());
+           dkmax.as<signed char>(), dkmean.as<float>(), kZClasses, c.wx, c.sites_per_block, dkeep.as<unsigned char>(), dkept.as<unsigned long long>());
     std::vector<unsigned char> colmask((size_t)std::max<long>(M, 1));
     CU(cudaMemcpy2DAsync(colmask.data(), 1, dkeep.as<unsigned char>() + col, ldg, 1, (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

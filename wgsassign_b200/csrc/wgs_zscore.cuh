@@ -217,8 +217,8 @@ __global__ void zmaxdepth_kernel(const T* __restrict__ table, long n, int* __res
 }
 
 // Per-(individual, class) decision tables built on the host from the tallies:
-//   kmax[col][id]  : -1 class not kept, else argmax of the class mean (zscore.py:53)
-//   kmean[col][id] : the class mean at that argmax (float32)
+//   kmax[id][col]  : -1 class not kept, else argmax of the class mean (zscore.py:53)
+//   kmean[id][col] : the class mean at that argmax (float32)
 //   zlike/zfac[col][id] : class mean GL triple (AD_like) and binomial read probabilities
 //                         (AD_factorial), zscore.py:63-79
 // ---------------------------------------------------------------------------------------
@@ -228,7 +228,7 @@ __global__ void zmaxdepth_kernel(const T* __restrict__ table, long n, int* __res
 __global__ void __launch_bounds__(256)
 zkeep_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
              const unsigned char* __restrict__ sel,
-             const signed char* __restrict__ kmax, const float* __restrict__ kmean,
+             const signed char* __restrict__ kmax, const float* __restrict__ kmean, int ncls,   // [ncls][ldg]
              int wx, long sites_per_block,
              unsigned char* __restrict__ keep,             // [M][ldg]
              unsigned long long* __restrict__ kept)        // [ldg]
@@ -241,8 +241,8 @@ zkeep_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ld
     const long s_begin = (long)blockIdx.y * sites_per_block;
     const long s_end = min(M, s_begin + sites_per_block);
     if (col >= ldg) return;
-    const signed char* km = kmax + (size_t)col * kZClasses;
-    const float* kv = kmean + (size_t)col * kZClasses;
+    const signed char* km = kmax + col;                     // class-major tables [class][ldg]: the lanes of a warp (consecutive
+    const float* kv = kmean + col;                          // individuals, mostly the same few classes) share cache lines
     int nk = 0;
     for (long s = s_begin + wy; s < s_end; s += wy_count) {
         unsigned char k = 0;
@@ -251,11 +251,11 @@ zkeep_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ld
             int ref = ad.x, alt = ad.y;
             if (ref + alt <= kZDepthCap) {
                 int id = zclass_id(ref, alt);
-                int mx = km[id];
+                int mx = id < ncls ? km[(long)id * ldg] : -1;
                 if (mx >= 0) {
                     float2 g = ld_stream2(&G[s * (long)ldg + col]);
                     float gl = mx == 0 ? g.x : (mx == 1 ? g.y : third_gl_np(g.x, g.y));
-                    float diff = fabsf(__fsub_rn(kv[id], gl));
+                    float diff = fabsf(__fsub_rn(kv[(long)id * ldg], gl));
                     k = !(diff > 0.01f);
                 }
             }
