@@ -53,6 +53,7 @@ struct wgs_ctx {
     // asynchronous upload (wgs_upload_gl_async): one event per population slab on stream2
     bool upload_pending = false;
     std::vector<cudaEvent_t> ev_pop;
+    std::vector<int> upload_order;               // populations in the order their slabs were queued (smallest first)
 
     // EM decisions come back through two mapped pinned slots ([0] = problems still active, [1..] = flags)
     int* em_pin[2] = {nullptr, nullptr};
@@ -1093,7 +1094,8 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     const bool ahead = (ctx->fn == nullptr || ctx->nccl_comm != nullptr) && getenv("WGS_EM_NO_LOOKAHEAD") == nullptr;
     const double count_all = (double)ctx->Mtot();
     if (pop_ready) {
-        for (int k = 0; k < K; ++k) {
+        for (int ko = 0; ko < K; ++ko) {
+            const int k = (int)ctx->upload_order.size() == K ? ctx->upload_order[ko] : ko;   // the order the slabs arrive in
             PopDesc pd = ctx->pops[k];
             CU(cudaStreamWaitEvent(ctx->stream, (*pop_ready)[k], 0));       // device-side: the host keeps queueing
             if (on_pop && (*on_pop)(k)) return 1;                           // the fused operator's full-data EM of this population
@@ -1311,7 +1313,11 @@ int32_t wgs_upload_gl_async(wgs_ctx* ctx, const float* L, int64_t M, int32_t N)
                dp.as<int>(), (int)pads.size());
         CU(cudaStreamSynchronize(ctx->stream));                 // pads in place (and dp released) before any consumer is queued
     }
-    for (int k = 0; k < K; ++k) {
+    // smallest population first: the pipelined operator starts working after the shortest possible wait
+    ctx->upload_order.resize(K);
+    for (int k = 0; k < K; ++k) ctx->upload_order[k] = k;
+    std::stable_sort(ctx->upload_order.begin(), ctx->upload_order.end(), [&](int a, int b) { return ctx->pops[a].n < ctx->pops[b].n; });
+    for (int k : ctx->upload_order) {
         if (M > 0)
             for (const Run& r : runs[k])
                 CU(cudaMemcpy2DAsync(G + r.col, (size_t)ldg * sizeof(float2), L + 2 * (size_t)r.ind, (size_t)N * sizeof(float2),
