@@ -1868,6 +1868,26 @@ __device__ __forceinline__ void loo5_quad(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3
     }
 }
 
+// The first pair (low lanes) of a quad only, in scalar arithmetic: the same fused operations on half the lanes.
+// For a quad whose second pair is padding (n mod 4 = 1 or 2) this is half the FMA-pipe time and one reciprocal
+// instead of two per problem.
+__device__ __forceinline__ void loo5_pair_lo(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3, f32x2 P4, const Loo5Coef (&c)[4], f32x2 (&acc)[4]) {
+    const float p0 = unpack2(P0).x, p1 = unpack2(P1).x, p2 = unpack2(P2).x, p3 = unpack2(P3).x, p4 = unpack2(P4).x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = c[k].a, b = c[k].b;
+        const float ah = unpack2(c[k].AH).x, b43 = unpack2(c[k].B43).x, bh = unpack2(c[k].BH).x;
+        const float u = fmaf(p0, a, p1);
+        const float v = fmaf(p4, b, p3);
+        const float D = fmaf(v, b, fmaf(u, a, p2));
+        const float t = fmaf(p4, b43, p3);
+        const float N = fmaf(t, bh, fmaf(p1, ah, p2));
+        float2 ac = unpack2(acc[k]);
+        ac.x = fmaf(N, fast_rcp(D), ac.x);
+        acc[k] = pack2(ac.x, ac.y);
+    }
+}
+
 // Pipeline: a ring of kLoo5Stages row groups (rows_per_pass site rows each) guarded by full/empty
 // mbarrier pairs - no block-wide barrier in the loop.  Every warp waits for "full", computes its rows
 // and arrives on "empty"; one lane of warp 0 additionally refills a slot with ONE TMA bulk copy (the rows
@@ -1915,6 +1935,7 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
         return;
     }
     const float inv_div = 1.0f / (float)(n - 1);
+    const bool last_pair_only = ((n - 1) & 3) < 2;              // n mod 4 is 1 or 2: the last quad holds one real pair
     float ssq[4] = {0.f, 0.f, 0.f, 0.f};
 
     if (t == 0) {
@@ -1975,7 +1996,8 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
             }
             if (nq & 1) {
                 const ulonglong2 v0 = row[5 * nfull], v1 = row[5 * nfull + 1], v2 = row[5 * nfull + 2];
-                loo5_quad(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
+                if (last_pair_only) loo5_pair_lo(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);   // the quad's second pair is padding
+                else loo5_quad(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
             }
             // own terms: the four members of quad ti, from the raw pairs at the end of the row
             const float4* rawrow = reinterpret_cast<const float4*>(row + 5 * nc);
