@@ -1015,7 +1015,23 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     }
     EmState st;
     if (em_state_init(ctx, st, ldg, ldg, nblocks, active0)) return 1;
-    {   // f = 0.25 everywhere; NaN for the (degenerate) single-member populations, like 0/0 in the reference
+    // When every real column is an active problem of a population that loo_first serves, iteration 1 writes all of
+    // them without reading the start state: only the padding columns need a value (the step kernels load whole quads).
+    bool pads_only = !mask && !sel && iter >= 1 && getenv("WGS_LOO_NOFIRST") == nullptr && getenv("WGS_LOO_FULLFILL") == nullptr;
+    for (int k = 0; k < K; ++k)
+        if (ctx->pops[k].n <= 1 || (ctx->pops[k].n + 1) / 2 > 32 * kFisherQ) pads_only = false;
+    if (pads_only) {
+        std::vector<int> pads;
+        for (int c = 0; c < ldg; ++c) if (ctx->ind_of_col[c] < 0) pads.push_back(c);
+        if (!pads.empty() && M > 0) {
+            DevBuf dp;
+            if (buf_alloc(ctx, dp, pads.size() * sizeof(int))) return 1;
+            CU(cudaMemcpyAsync(dp.p, pads.data(), pads.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            LAUNCH("fill", fill_cols_kernel, grid_for(M * (long)pads.size(), 256, ctx->num_sm * 8), 256, 0, ctx->stream, F, ldf, M,
+                   dp.as<int>(), (int)pads.size(), 0.25f);
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+    } else {   // f = 0.25 everywhere; NaN for the (degenerate) single-member populations, like 0/0 in the reference
         std::vector<float> row(ldg, 0.25f);
         for (int c = 0; c < ldg; ++c)
             if (ctx->ind_of_col[c] >= 0 && ctx->pops[ctx->pop_of_col[c]].n <= 1) row[c] = std::numeric_limits<float>::quiet_NaN();

@@ -2207,6 +2207,16 @@ __global__ void fill_kernel(float* __restrict__ p, long n, float v)
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = v;
 }
 
+// F[s][cols[j]] <- v: the start value of the padding columns only (every real column is written by loo_first)
+__global__ void fill_cols_kernel(float* __restrict__ F, int ld, long M, const int* __restrict__ cols, int ncols, float v)
+{
+    const long total = M * (long)ncols;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long s = e / ncols;
+        F[s * (long)ld + cols[(int)(e - s * ncols)]] = v;
+    }
+}
+
 // F[s][c] <- row[c] for c < ncols: start state of the leave-one-out EM
 __global__ void bcast_row_kernel(float* __restrict__ F, int ld, int ncols, long M, const float* __restrict__ row)
 {
