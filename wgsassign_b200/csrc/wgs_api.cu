@@ -543,15 +543,17 @@ int add_af_logsum(wgs_ctx* ctx, const float* dA, long M, int K, double* sums, lo
 }
 
 // ---- leave-one-out likelihoods with the state rows staged in shared memory (loo_like2) -----------
-struct LooLike2Cfg { int W, gx, gy, TS; long spb; size_t smem; bool wide; };
+struct LooLike2Cfg { int W, gx, gy, TS; long spb; size_t smem; bool wide, big; };
 bool loo_like2_cfg(wgs_ctx* ctx, long M, int ldf, int K, LooLike2Cfg* c)
 {
     const int groups = (ctx->ldg + 31) / 32;
-    const int nb = (groups + kLL2MaxW - 1) / kLL2MaxW;            // blocks per site split
+    c->wide = K > 10;                                             // one block per SM, <= 4 sites per tile (see the kernel)
+    // 11..18 column groups and a narrow population tile: one big block per SM and site split builds the cells once
+    c->big = !c->wide && groups > kLL2MaxW && groups <= kLL2BigW && getenv("WGS_LOOLIKE_SMALLBLOCK") == nullptr;
+    const int nb = c->big ? 1 : (groups + kLL2MaxW - 1) / kLL2MaxW;   // blocks per site split
     c->W = (groups + nb - 1) / nb;
     c->gx = nb;
-    c->wide = K > 10;                                             // one block per SM, <= 4 sites per tile (see the kernel)
-    const size_t budget = c->wide ? 210 * 1024 : 100 * 1024;
+    const size_t budget = (c->wide || c->big) ? 210 * 1024 : 100 * 1024;
     // per site of a tile: 16 B plane cell + 4 B landing row per state value, 2 x 8 B per GL column of the block
     const size_t per_site = (size_t)ldf * 20 + (size_t)c->W * 32 * 16;
     const size_t fixed = (size_t)ldf * 8;                         // clamp bounds
@@ -560,18 +562,18 @@ bool loo_like2_cfg(wgs_ctx* ctx, long M, int ldf, int K, LooLike2Cfg* c)
     if (TS < 1) return false;
     c->TS = TS;
     c->smem = (size_t)TS * per_site + fixed;
-    long target = std::max<long>(1, (long)ctx->num_sm * (c->wide ? 1 : 2) / nb);    // one wave of resident blocks
+    long target = std::max<long>(1, (long)ctx->num_sm * ((c->wide || c->big) ? 1 : 2) / nb);    // one wave of resident blocks
     long spb = (M + target - 1) / target;
     spb = std::max<long>(TS, (spb + TS - 1) / TS * TS);
     c->spb = spb;
     c->gy = (int)std::max<long>(1, (M + spb - 1) / spb);
     return true;
 }
-template <int KT, int TSMAX, int MINB>
+template <int KT, int TSMAX, int MINB, int MAXW = kLL2MaxW>
 int launch_loo_like2_t(wgs_ctx* ctx, const float2* G, long M, const float* Fx, int ldf, const float* clo, const float* chi,
                        const int* rc, int K, int k0, const LooLike2Cfg& c, long pm, long pr, int R, double* partials)
 {
-    auto kern = loo_like2_kernel<KT, TSMAX, MINB>;
+    auto kern = loo_like2_kernel<KT, TSMAX, MINB, MAXW>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     LAUNCH("loo_like", kern, dim3(c.gx, c.gy), c.W * 32, c.smem, ctx->stream,
@@ -590,6 +592,15 @@ int launch_loo_like2(wgs_ctx* ctx, int KT, const float2* G, long M, const float*
     if (c.wide) {
         if (KT == 16) return launch_loo_like2_t<16, 4, 1>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
         return launch_loo_like2_t<20, 4, 1>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+    }
+    if (c.big) {
+        switch (KT) {
+            case 2: return launch_loo_like2_t<2, 8, 1, kLL2BigW>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+            case 4: return launch_loo_like2_t<4, 8, 1, kLL2BigW>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+            case 5: return launch_loo_like2_t<5, 8, 1, kLL2BigW>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+            case 8: return launch_loo_like2_t<8, 8, 1, kLL2BigW>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+            default: return launch_loo_like2_t<10, 8, 1, kLL2BigW>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+        }
     }
     switch (KT) {
         case 2: return launch_loo_like2_t<2, 8, 2>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);

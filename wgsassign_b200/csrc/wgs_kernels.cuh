@@ -890,9 +890,12 @@ loo_like_kernel(const float2* __restrict__ G, int ldg, long M,
 // ---------------------------------------------------------------------------------------
 // Up to 10 warps per block.  KT <= 10: two blocks per SM (<= 96 registers), tiles of up to 8 sites; wider
 // population tiles: one block per SM with up to 4 sites per tile (the 2 x KT accumulators need the registers).
+// A third shape, <KT, 8, 1, kLL2BigW>: when the individuals fill 11..18 warps ONE block of up to 18 warps per SM takes
+// all columns of its site split, so the cells of a state row are built once per tile instead of once per block.
 constexpr int kLL2MaxW = 10;
-template <int KT, int TSMAX, int MINB>
-__global__ void __launch_bounds__(kLL2MaxW * 32, MINB)
+constexpr int kLL2BigW = 18;
+template <int KT, int TSMAX, int MINB, int MAXW = kLL2MaxW>
+__global__ void __launch_bounds__(MAXW * 32, MINB)
 loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
                  const float* __restrict__ Fx, int ldf,
                  const float* __restrict__ clip_lo, const float* __restrict__ clip_hi,   // [ldf] or null: clamp applied while staging
