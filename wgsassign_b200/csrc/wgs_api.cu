@@ -548,9 +548,11 @@ bool loo_like2_cfg(wgs_ctx* ctx, long M, int ldf, int K, LooLike2Cfg* c)
 {
     const int groups = (ctx->ldg + 31) / 32;
     c->wide = K > 10;                                             // one block per SM, <= 4 sites per tile (see the kernel)
-    // 11..18 column groups and a narrow population tile: one big block per SM and site split builds the cells once
-    c->big = !c->wide && groups > kLL2MaxW && groups <= kLL2BigW && getenv("WGS_LOOLIKE_SMALLBLOCK") == nullptr;
-    const int nb = c->big ? 1 : (groups + kLL2MaxW - 1) / kLL2MaxW;   // blocks per site split
+    // more than 10 column groups and a narrow population tile: big blocks (up to 18 warps, one per SM) build the cells of
+    // a state row once per 18 warps of individuals instead of once per 10
+    c->big = !c->wide && groups > kLL2MaxW && getenv("WGS_LOOLIKE_SMALLBLOCK") == nullptr;
+    const int maxw = c->wide ? kLL2WideW : (c->big ? kLL2BigW : kLL2MaxW);
+    const int nb = (groups + maxw - 1) / maxw;                    // blocks per site split
     c->W = (groups + nb - 1) / nb;
     c->gx = nb;
     const size_t budget = (c->wide || c->big) ? 210 * 1024 : 100 * 1024;
@@ -590,8 +592,8 @@ int launch_loo_like2(wgs_ctx* ctx, int KT, const float2* G, long M, const float*
                      const int* rc, int K, int k0, const LooLike2Cfg& c, long pm, long pr, int R, double* partials)
 {
     if (c.wide) {
-        if (KT == 16) return launch_loo_like2_t<16, 4, 1>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
-        return launch_loo_like2_t<20, 4, 1>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+        if (KT == 16) return launch_loo_like2_t<16, 4, 1, kLL2WideW>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
+        return launch_loo_like2_t<20, 4, 1, kLL2WideW>(ctx, G, M, Fx, ldf, clo, chi, rc, K, k0, c, pm, pr, R, partials);
     }
     if (c.big) {
         switch (KT) {

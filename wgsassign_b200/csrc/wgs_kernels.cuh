@@ -894,6 +894,7 @@ loo_like_kernel(const float2* __restrict__ G, int ldg, long M,
 // all columns of its site split, so the cells of a state row are built once per tile instead of once per block.
 constexpr int kLL2MaxW = 10;
 constexpr int kLL2BigW = 18;
+constexpr int kLL2WideW = 16;   // wide population tiles (K > 10): 16 warps at 128 registers
 template <int KT, int TSMAX, int MINB, int MAXW = kLL2MaxW>
 __global__ void __launch_bounds__(MAXW * 32, MINB)
 loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
