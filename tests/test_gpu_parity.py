@@ -364,3 +364,22 @@ def test_fallback_kernels_agree(wgs, monkeypatch):
     assert np.max(np.abs(f2 - f_obs) / (np.abs(f_obs) + 1e-3 * np.abs(f_obs).max(0))) < 1e-4
     assert rel_err(ind2, ind) < 1e-5
     ctx.close()
+
+
+def test_loo_like_block_shapes_agree(wgs, monkeypatch):
+    """The three launch shapes of the staged leave-one-out likelihood kernel (two small blocks per SM, big blocks of up
+    to 18 warps, the gather-through-L1 fallback) on a panel wide enough (22 warps of individuals) to split big blocks."""
+    ctx = wgs.lib.Context(0)
+    n, k, m = 700, 4, 3000
+    pop_of = ((np.arange(n) * k) // n).astype(np.int32)
+    ctx.set_pops(pop_of, k)
+    ctx.synth(m, n, seed=11)
+    af, _ = ctx.ref_af(50, 1e-4)
+    ll0, _, its0 = ctx.loo_partial(af.copy(), 50, 1e-4)
+    assert np.mean(np.argmax(ll0, 1) == pop_of) > 0.99
+    for var in ("WGS_LOOLIKE_SMALLBLOCK", "WGS_LOOLIKE_V1"):
+        monkeypatch.setenv(var, "1")
+        ll1, _, its1 = ctx.loo_partial(af.copy(), 50, 1e-4)
+        assert list(its1) == list(its0)
+        assert rel_err(ll1, ll0) < 1e-7 and np.array_equal(np.argmax(ll1, 1), np.argmax(ll0, 1))
+    ctx.close()
