@@ -98,10 +98,17 @@ def attach(ctx):
         import torch.distributed as td
         if _cfg["device"] is not None and td.get_backend() == "nccl" and not os.environ.get("WGS_NO_NCCL") \
                 and not getattr(ctx, "_nccl_ready", False):
+            import sys
             from . import _lib
-            box = [_lib.nccl_unique_id() if _cfg["rank"] == 0 else None]
+            try:
+                box = [_lib.nccl_unique_id() if _cfg["rank"] == 0 else None]
+            except _lib.WgsError as e:                       # no loadable libnccl: the stop rule keeps the host callback
+                box = [None]
+                if _cfg["rank"] == 0:
+                    print("wgsassign_b200: NCCL stop rule disabled (%s)" % e, file=sys.stderr)
             td.broadcast_object_list(box, src=0)
-            ctx.nccl_init(box[0], _cfg["rank"], _cfg["world"])
+            if box[0] is not None:
+                ctx.nccl_init(box[0], _cfg["rank"], _cfg["world"])
             ctx._nccl_ready = True
     else:
         ctx.set_shard(-1, 0, None)
