@@ -383,3 +383,32 @@ def test_loo_like_block_shapes_agree(wgs, monkeypatch):
         assert list(its1) == list(its0)
         assert rel_err(ll1, ll0) < 1e-7 and np.array_equal(np.argmax(ll1, 1), np.argmax(ll0, 1))
     ctx.close()
+
+
+def test_large_population_paths_vs_oracle(wgs, oracle_mod):
+    """A population of more than 512 individuals takes the kernels kept for that size (TMA-tile population EM with
+    replay, 512-thread leave-one-out blocks with a general first iteration, TMA-tile Fisher pass)."""
+    from wgsassign_b200 import synth
+    n_big, n_small, m = 522, 10, 120
+    d = synth.synth(m, n_big + n_small, 2, seed=51, with_ad=False)
+    L, IDs = d["L"], d["IDs"].copy()
+    IDs[:n_big, 1] = "big"
+    IDs[n_big:, 1] = "small"
+    af_o, _, its_o = oracle_mod.reference_af(L, IDs, 200, 1e-4, 4)
+    pop_of, pops = wgs.session.pops_from_ids(IDs)
+    ctx = wgs.lib.Context(0)
+    ctx.set_pops(pop_of, len(pops))
+    ctx.upload_gl(L)
+    af_g, its_g = ctx.ref_af(200, 1e-4)
+    assert list(its_g) == list(its_o)
+    assert np.max(np.abs(af_g - af_o)) < AF_ATOL
+    a1, a2 = af_o.copy(), af_o.copy()
+    ll_o, _, lits_o = oracle_mod.loo(L, a1, IDs, 4, 200, 1e-4)
+    ll_g, _, lits_g = ctx.loo_partial(a2, 200, 1e-4)
+    assert list(lits_g) == list(lits_o)
+    assert rel_err(ll_g, ll_o) < LL_RTOL and np.array_equal(np.argmax(ll_g, 1), np.argmax(ll_o, 1))
+    assert np.max(np.abs(a1 - a2)) < AF_ATOL
+    f_o, _ = oracle_mod.fisher_obs(L, af_o, IDs, 4)
+    f_g, _, ind_g = ctx.fisher_partial(af_o)
+    assert np.max(np.abs(f_g - f_o) / (np.abs(f_o) + 1e-3 * np.abs(f_o).max(0))) < 1e-4
+    ctx.close()

@@ -1659,14 +1659,14 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
     }
     red[t] = make_float4(ssq[0], ssq[1], ssq[2], ssq[3]);
     __syncthreads();
-    if (t < n) {                                                // problem t = member (t & 3) of quad t / 4
+    for (int p = t; p < n; p += blockDim.x) {                   // problem p = member (p & 3) of quad p / 4 (n may exceed the block)
         double v = 0.0;
         for (int q = 0; q < rows_per_pass; ++q) {
-            const float4 x = red[q * nq + (t >> 2)];
-            const int k = t & 3;
+            const float4 x = red[q * nq + (p >> 2)];
+            const int k = p & 3;
             v += (double)(k == 0 ? x.x : k == 1 ? x.y : k == 2 ? x.z : x.w);
         }
-        partials[(long)blockIdx.x * ldg + col0 + t] = v;
+        partials[(long)blockIdx.x * ldg + col0 + p] = v;
     }
 }
 
@@ -1935,7 +1935,7 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
     // a launch that finds every problem of the population frozen (the host queues one iteration ahead of the
     // decisions it reads back) has nothing to stage or compute
     if (__syncthreads_or(act != 0u) == 0) {
-        if (t < n) partials[(long)blockIdx.x * ldg + col0 + t] = 0.0;
+        for (int p = t; p < n; p += blockDim.x) partials[(long)blockIdx.x * ldg + col0 + p] = 0.0;
         return;
     }
     const float inv_div = 1.0f / (float)(n - 1);
@@ -2034,14 +2034,14 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
     __syncthreads();
     red[t] = make_float4(ssq[0], ssq[1], ssq[2], ssq[3]);
     __syncthreads();
-    if (t < n) {                                                // problem t = member (t & 3) of quad t / 4
+    for (int p = t; p < n; p += blockDim.x) {                   // problem p = member (p & 3) of quad p / 4 (n may exceed the block)
         double v = 0.0;
         for (int q = 0; q < rows_per_pass; ++q) {
-            const float4 x = red[q * nq + (t >> 2)];
-            const int k = t & 3;
+            const float4 x = red[q * nq + (p >> 2)];
+            const int k = p & 3;
             v += (double)(k == 0 ? x.x : k == 1 ? x.y : k == 2 ? x.z : x.w);
         }
-        partials[(long)blockIdx.x * ldg + col0 + t] = v;
+        partials[(long)blockIdx.x * ldg + col0 + p] = v;
     }
 }
 
