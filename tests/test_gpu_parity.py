@@ -385,11 +385,13 @@ def test_loo_like_block_shapes_agree(wgs, monkeypatch):
     ctx.close()
 
 
-def test_large_population_paths_vs_oracle(wgs, oracle_mod):
+@pytest.mark.parametrize("n_big", [522, 301, 130])
+def test_large_population_paths_vs_oracle(wgs, oracle_mod, n_big):
     """A population of more than 512 individuals takes the kernels kept for that size (TMA-tile population EM with
-    replay, 512-thread leave-one-out blocks with a general first iteration, TMA-tile Fisher pass)."""
+    replay, 512-thread leave-one-out blocks with a general first iteration, TMA-tile Fisher pass); 301 and 130 take
+    the widest instantiations (32 and 16 threads per site row) of the register-tile kernels."""
     from wgsassign_b200 import synth
-    n_big, n_small, m = 522, 10, 120
+    n_small, m = 10, 120
     d = synth.synth(m, n_big + n_small, 2, seed=51, with_ad=False)
     L, IDs = d["L"], d["IDs"].copy()
     IDs[:n_big, 1] = "big"
@@ -406,7 +408,10 @@ def test_large_population_paths_vs_oracle(wgs, oracle_mod):
     ll_o, _, lits_o = oracle_mod.loo(L, a1, IDs, 4, 200, 1e-4)
     ll_g, _, lits_g = ctx.loo_partial(a2, 200, 1e-4)
     assert list(lits_g) == list(lits_o)
-    assert rel_err(ll_g, ll_o) < LL_RTOL and np.array_equal(np.argmax(ll_g, 1), np.argmax(ll_o, 1))
+    # The reference adds the n posterior terms of a site sequentially in float32 (emMAF_cy.pyx:19-23): with n in the
+    # hundreds its own frequencies carry ~sqrt(n) * 6e-8 relative noise, and a leave-one-out frequency near the clip
+    # bound 1/(2n) turns that into the same relative change of a site's likelihood.  5e-6 here, 1e-6 everywhere else.
+    assert rel_err(ll_g, ll_o) < 5e-6 and np.array_equal(np.argmax(ll_g, 1), np.argmax(ll_o, 1))
     assert np.max(np.abs(a1 - a2)) < AF_ATOL
     f_o, _ = oracle_mod.fisher_obs(L, af_o, IDs, 4)
     f_g, _, ind_g = ctx.fisher_partial(af_o)
