@@ -417,3 +417,25 @@ def test_large_population_paths_vs_oracle(wgs, oracle_mod, n_big):
     f_g, _, ind_g = ctx.fisher_partial(af_o)
     assert np.max(np.abs(f_g - f_o) / (np.abs(f_o) + 1e-3 * np.abs(f_o).max(0))) < 1e-4
     ctx.close()
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 6, 2), (5, 7, 3), (33, 4, 2)])
+def test_tiny_shapes_fused_vs_oracle(wgs, oracle_mod, m, n, k):
+    """Degenerate sizes (a single site, populations of two, fewer sites than any tile) through the fused call."""
+    from wgsassign_b200 import synth
+    d = synth.synth(m, n, k, seed=61 + m, with_ad=False)
+    L, IDs = d["L"], d["IDs"]
+    pop_of, pops = wgs.session.pops_from_ids(IDs)
+    ctx = wgs.lib.Context(0)
+    ctx.set_pops(pop_of, len(pops))
+    ctx.upload_gl_async(L)
+    af, its, ll, _, lits, _ = ctx.ref_af_loo(40, 1e-4)
+    af_o, _, its_o = oracle_mod.reference_af(L, IDs, 40, 1e-4, 1)
+    a1 = af_o.copy()
+    ll_o, _, lits_o = oracle_mod.loo(L, a1, IDs, 1, 40, 1e-4)
+    assert list(its) == list(its_o) and list(lits) == list(lits_o)
+    assert np.max(np.abs(af - af_o)) < AF_ATOL
+    ok = np.isfinite(ll_o)
+    assert np.array_equal(ok, np.isfinite(ll))
+    assert rel_err(ll[ok], ll_o[ok]) < LL_RTOL
+    ctx.close()
