@@ -53,6 +53,13 @@ const char *wgs_last_error(const wgs_ctx *ctx); /* ctx may be NULL: last create(
 int32_t wgs_create(int32_t device, wgs_ctx **out);
 void    wgs_destroy(wgs_ctx *ctx);
 
+/* Run-time switches (fallback kernels, experiments, numerics variants such as "z_exact_means"): the library never
+ * reads environment variables on a call path - a result cannot depend on the ambient environment.  Unknown names
+ * are an error.  (With WGS_DEBUG set in the environment, wgs_create seeds the table once from WGS_<NAME>=<int>.)
+ * The names and their meaning are listed in csrc/wgs_api.cu (kOptionNames). */
+int32_t wgs_set_option(wgs_ctx *ctx, const char *name, int32_t value);
+int32_t wgs_get_option(const wgs_ctx *ctx, const char *name, int32_t *value);
+
 /* Pinned host buffers for full-rate H2D (optional). */
 void *wgs_host_alloc(int64_t bytes);
 void  wgs_host_free(void *p);
@@ -80,14 +87,27 @@ int32_t wgs_upload_gl(wgs_ctx *ctx, const float *L, int64_t M, int32_t N, int32_
 int32_t wgs_upload_gl_async(wgs_ctx *ctx, const float *L, int64_t M, int32_t N);
 int32_t wgs_upload_wait(wgs_ctx *ctx);
 
-/* Allele depths [M,2N] int32, packed on device to 2 x uint8 per individual
- * (counts above 254 are rejected with an error rather than clamped). */
+/* Allele depths [M,2N] int32, packed on device to 2 x uint8 per individual.  A count above 254 is stored as the
+ * sentinel "deeper than any class table": the site joins the deep sites (wgs_zscore_deep_sites) and is never kept,
+ * exactly what the reference does with a depth whose depth+1 splits were not all observed (zscore.py:36-39).
+ * Negative counts are an error. */
 int32_t wgs_upload_ad(wgs_ctx *ctx, const int32_t *AD, int64_t M, int32_t N);
 
 /* Multi-GPU site sharding: global number of sites, global index of this shard's first site,
  * and the cross-rank sum used for the EM stop rule and the z-score class tallies. */
 int32_t wgs_set_shard(wgs_ctx *ctx, int64_t M_total, int64_t site_offset,
                       wgs_allreduce_fn fn, void *user);
+
+/* Position of this context in the site order of the ranks (rank r holds the r-th contiguous site range).  Needed
+ * by the operators whose arithmetic is ORDER dependent in the reference - the sequential float32 class means of
+ * the z-score (zscore.py:22) and the sequential float32 stop-rule sum (emMAF_cy.pyx:26-33) - which are chained
+ * from rank to rank.  wgs_nccl_init sets it as well. */
+int32_t wgs_set_rank(wgs_ctx *ctx, int32_t rank, int32_t world);
+
+/* 1 when the operators below return sums that are ALREADY combined over the ranks (a communicator is attached:
+ * all-gather over NVLink + rank-ordered sum on the device), 0 when they are local partial sums that the caller
+ * must add in rank order (no communicator: single GPU, or the host callback only). */
+int32_t wgs_partials_combined(const wgs_ctx *ctx);
 
 /* Optional NCCL communicator for the sharded EM stop rule.  Without it the per-iteration sums of squared
  * changes pass through `fn` on the host (one round trip per iteration); with it they are all-gathered on the
@@ -209,6 +229,11 @@ void        wgs_beagle_close(wgs_beagle *b);
  * read of the whole matrix, mode 1 = one population slab at a time (the access pattern of the
  * per-population kernels).  Returns the device time of one pass and the bytes it read. */
 int32_t wgs_debug_stream(wgs_ctx *ctx, int32_t mode, double *ms_out, double *bytes_out);
+
+/* Diagnostic: the device's order-exact float32 summation (the primitive behind the EM stop rule, rmse1d of
+ * emMAF_cy.pyx:26-33): *out = ((carry_in + x[0]) + x[1]) + ... in float32, computed with the blocked integer
+ * scheme of warp_seqsum32 (csrc/wgs_kernels.cuh).  Tests compare it bit for bit with a serial loop. */
+int32_t wgs_debug_seqsum(wgs_ctx *ctx, const float *x, int64_t n, float carry_in, float *out);
 
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */

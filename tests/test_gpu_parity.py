@@ -352,8 +352,8 @@ def test_fallback_kernels_agree(wgs, monkeypatch):
     a0 = af.copy()
     ll, _, lits = ctx.loo_partial(a0, 200, 1e-4)
     f_obs, ne_obs, ind = ctx.fisher_partial(af)
-    for var in ("WGS_LOOLIKE_V1", "WGS_FISHER_V1", "WGS_EM_STEP", "WGS_EM_NO_LOOKAHEAD", "WGS_LOO_V4", "WGS_LOO_NOFIRST"):
-        monkeypatch.setenv(var, "1")
+    for name in ("loolike_v1", "fisher_v1", "em_step", "em_no_lookahead", "loo_v4", "loo_nofirst"):
+        ctx.set_option(name, 1)
     af2, its2 = ctx.ref_af(200, 1e-4)
     a1 = af2.copy()
     ll2, _, lits2 = ctx.loo_partial(a1, 200, 1e-4)
@@ -377,8 +377,9 @@ def test_loo_like_block_shapes_agree(wgs, monkeypatch):
     af, _ = ctx.ref_af(50, 1e-4)
     ll0, _, its0 = ctx.loo_partial(af.copy(), 50, 1e-4)
     assert np.mean(np.argmax(ll0, 1) == pop_of) > 0.99
-    for var in ("WGS_LOOLIKE_SMALLBLOCK", "WGS_LOOLIKE_V1"):
-        monkeypatch.setenv(var, "1")
+    ctx.set_option("loolike_v2", 1)                     # the staged state-row kernel itself (population-contiguous panels take loo_like3)
+    for name in ("loolike_smallblock", "loolike_v1"):
+        ctx.set_option(name, 1)
         ll1, _, its1 = ctx.loo_partial(af.copy(), 50, 1e-4)
         assert list(its1) == list(its0)
         assert rel_err(ll1, ll0) < 1e-7 and np.array_equal(np.argmax(ll1, 1), np.argmax(ll0, 1))

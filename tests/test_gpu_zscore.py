@@ -97,21 +97,44 @@ def test_zscore_errors(zs, zgold):
     pops = np.unique(IDs[:, 1])
     with pytest.raises(AssertionError, match="loci were kept"):
         zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops, n_threshold=10 ** 6)
-    big = AD.copy()
-    big[0, 0] = 300
-    with pytest.raises(Exception, match="254"):
-        zs.zscore_all(L, big, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops)
+    neg = AD.copy()
+    neg[0, 0] = -1
+    with pytest.raises(Exception, match="negative"):
+        zs.zscore_all(L, neg, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops)
+    with pytest.raises(ValueError, match="af must be"):
+        zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=np.ascontiguousarray(af[:-3]), pops=pops)
 
 
-def test_exact_mean_variant_keeps_tallies(zs, zgold, monkeypatch):
-    """The order-independent fixed-point tally used under site sharding: identical integer
+def test_extreme_depths_do_not_abort(zs, zgold, oracle_mod):
+    """A few sites with hundreds of reads (common in real depth files): the reference gives each its own class,
+    which is never kept; here they are stored as "deeper than the class table".  Same tallies, kept loci and scores
+    as the oracle on the same matrix - for the individual that has them and for everybody else."""
+    L, AD, IDs, af = zgold["L"], zgold["AD"].astype(np.int32).copy(), zgold["IDs"], zgold["af"]
+    pops = np.unique(IDs[:, 1])
+    AD[3, 0], AD[3, 1] = 300, 2            # individual 0
+    AD[7, 2], AD[7, 3] = 90, 1000          # individual 1
+    AD[9, 0], AD[9, 1] = 30, 25            # depth 55: above the table's cap of 40, below the uint8 limit
+    got = zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops, ind_start=0, ind_end=4)
+    ref = oracle_mod.zscore_assignment(L, AD, af, IDs, pops, ind_start=0, ind_end=4)
+    check_rows(got, [float(r["z"]) for r in ref], [(float(r["w_obs"]), float(r["z_mu"]), float(r["z_var"])) for r in ref],
+               [r["loci_kept"] for r in ref], [r["AD_array"] for r in ref])
+    from wgsassign_b200 import session
+    assert session._state["ctx"].zscore_deep_sites() == 3
+
+
+def test_exact_mean_variant_keeps_tallies(zs, zgold):
+    """The order-independent fixed-point tally (option z_exact_means, NOT the default): identical integer
     tallies; class means differ from numpy's sequential float32 mean only by that mean's own
     accumulation error (4e-6 relative at 400 sites), which can move a site sitting on the 0.01
     keep threshold, so loci kept agree to a couple of sites and the sums to ~1e-3."""
     L, AD, IDs, af = zgold["L"], zgold["AD"].astype(np.int32), zgold["IDs"], zgold["af"]
     pops = np.unique(IDs[:, 1])
-    monkeypatch.setenv("WGS_Z_EXACT_MEANS", "1")
-    got = zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops)
+    from wgsassign_b200 import session
+    session.set_option("z_exact_means", 1)
+    try:
+        got = zs.zscore_all(L, AD, IDs, zs.MODE_ASSIGNMENT, A=af, pops=pops)
+    finally:
+        session.set_option("z_exact_means", 0)
     comp = zgold["z_assign_components"]
     for j, r in enumerate(got):
         assert abs(r["loci_kept"] - int(comp[j, 3])) <= 3

@@ -35,6 +35,10 @@ SYMBOLS = {
     "wgs_last_error": (ctypes.c_char_p, [_vp]),
     "wgs_create": (_i32, [_i32, ctypes.POINTER(_vp)]),
     "wgs_destroy": (None, [_vp]),
+    "wgs_set_option": (_i32, [_vp, ctypes.c_char_p, _i32]),
+    "wgs_get_option": (_i32, [_vp, ctypes.c_char_p, _vp]),
+    "wgs_set_rank": (_i32, [_vp, _i32, _i32]),
+    "wgs_partials_combined": (_i32, [_vp]),
     "wgs_host_alloc": (_vp, [_i64]),
     "wgs_host_free": (None, [_vp]),
     "wgs_set_pops": (_i32, [_vp, _vp, _i32, _i32]),
@@ -68,6 +72,7 @@ SYMBOLS = {
     "wgs_beagle_copy": (_i32, [_vp, _vp]),
     "wgs_beagle_close": (None, [_vp]),
     "wgs_debug_stream": (_i32, [_vp, _i32, _vp, _vp]),
+    "wgs_debug_seqsum": (_i32, [_vp, _vp, _i64, ctypes.c_float, _vp]),
     "wgs_launch_count": (_i64, [_vp]),
     "wgs_timing_reset": (_i32, [_vp, _i32]),
     "wgs_timing_get": (_i32, [_vp, ctypes.c_char_p, _vp, _vp]),
@@ -162,6 +167,24 @@ class Context:
     def _ck(self, rc):
         if rc != 0:
             raise WgsError(lib().wgs_last_error(self._h).decode())
+
+    # ---- options ----
+    def set_option(self, name, value):
+        """Run-time switch of the library (fallback kernels, numerics variants); see kOptionNames in csrc/wgs_api.cu."""
+        self._ck(lib().wgs_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = ctypes.c_int32(0)
+        if lib().wgs_get_option(self._h, name.encode(), ctypes.byref(v)) != 0:
+            raise KeyError(name)
+        return v.value
+
+    def set_rank(self, rank, world):
+        self._ck(lib().wgs_set_rank(self._h, int(rank), int(world)))
+
+    def partials_combined(self):
+        """True when the operators' per-individual sums are already summed over the ranks (NCCL on the device)."""
+        return bool(lib().wgs_partials_combined(self._h))
 
     # ---- residency ----
     def set_pops(self, pop_of_ind, K):
@@ -296,6 +319,8 @@ class Context:
         K = 0 if af is None else af.shape[1]
         if af is not None:
             _as(af, np.float32, 2, "af")
+            if af.shape != (self.M, self.K):          # the reference raises IndexError on a short AF file; never read past the buffer
+                raise ValueError("af must be [M,K] = %s, got %s" % ((self.M, self.K), af.shape))
         self._ck(lib().wgs_zscore(self._h, int(mode), _ptr(af), K, int(n_threshold), int(bool(single_read)),
                                   int(ind_start), int(ind_end), int(iters), float(tole), ctypes.byref(rows)))
         return [rows[i] for i in range(n)]
@@ -335,6 +360,13 @@ class Context:
     def zscore_deep_sites(self):
         return int(lib().wgs_zscore_deep_sites(self._h))
 
+    def debug_seqsum(self, x, carry_in=0.0):
+        """Order-exact float32 sum of `x` on the device (the stop rule's primitive); float32 scalar."""
+        x = _as(np.ascontiguousarray(x, dtype=np.float32), np.float32, 1, "x")
+        out = ctypes.c_float(0)
+        self._ck(lib().wgs_debug_seqsum(self._h, _ptr(x), x.shape[0], float(carry_in), ctypes.byref(out)))
+        return np.float32(out.value)
+
     def debug_stream(self, mode):
         ms = ctypes.c_double(0)
         nb = ctypes.c_double(0)
@@ -366,26 +398,15 @@ def nccl_unique_id():
 
 
 def pinned_empty(shape, dtype):
-    """A numpy array in pinned host memory (full-rate H2D).  Freed when garbage-collected."""
+    """A numpy array in pinned host memory (full-rate, asynchronous H2D).  The pages are released
+    (cudaFreeHost) when the last view of the buffer is garbage-collected."""
+    import weakref
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
     p = lib().wgs_host_alloc(max(nbytes, 1))
     if not p:
         raise WgsError("cudaHostAlloc failed")
-    buf = (ctypes.c_char * nbytes).from_address(p)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                lib().wgs_host_free(self.ptr)
-            except Exception:
-                pass
-    _PINNED[id(buf)] = (_Owner(p), buf)
-    return arr
-
-
-_PINNED = {}
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(p)
+    # every array made from `buf` keeps it alive through .base; the finalizer runs when `buf` itself dies
+    weakref.finalize(buf, lib().wgs_host_free, p)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

@@ -6,6 +6,7 @@
 #include "wgs_zscore.cuh"
 
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -67,6 +68,7 @@ struct wgs_ctx {
     int nccl_rank = 0, nccl_world = 1;
 
     // sharding
+    int rank = 0, world = 1;                     // wgs_set_rank (or wgs_nccl_init): position in the site order of the ranks
     long M_total = -1, site_offset = 0;
     wgs_allreduce_fn fn = nullptr;
     void* user = nullptr;
@@ -83,6 +85,11 @@ struct wgs_ctx {
     std::vector<std::vector<int>> zclasses;
     std::vector<std::vector<float>> ztable;      // per individual: rows of (ref, alt, n_loci, mean0, mean1, mean2, kept) of every observed class
     long z_deep_sites = 0;
+    long ad_saturated = 0;                       // (site, individual) pairs of the resident depths with a count above 254
+
+    // run-time options (wgs_set_option): experiment / fallback switches, read at call entry.  Environment variables
+    // are NOT consulted on any call path; with WGS_DEBUG set, wgs_create imports WGS_<NAME>=<int> once.
+    std::map<std::string, int> opts;
 
     // instrumentation
     long launches = 0;
@@ -96,6 +103,34 @@ struct wgs_ctx {
 };
 
 namespace {
+
+int opt(const wgs_ctx* c, const char* name, int def = 0)
+{
+    auto it = c->opts.find(name);
+    return it == c->opts.end() ? def : it->second;
+}
+
+// every option the library reads, with its meaning (wgs_set_option rejects anything else)
+const char* const kOptionNames[] = {
+    "trace",              // 1: wall-clock of the host-side phases of every call on stderr
+    "pl2_wx",             // pop_like2: warps per block (1..4), 0 = least padding
+    "poplike_v1",         // 1: direct-form likelihood kernel even where the ratio form applies
+    "loolike_v1",         // 1: gather-through-L1 leave-one-out likelihood kernel
+    "loolike_v2",         // 1: staged state-row kernel (loo_like2) even where loo_like3 applies
+    "loolike_smallblock", // 1: loo_like2 in two small blocks per SM
+    "fisher_v1",          // 1: TMA-tile Fisher kernel
+    "em_step",            // 1: population EM with one iteration per launch
+    "em_multi1",          // 1: shared-memory-tile multi-iteration population EM
+    "em_no_lookahead",    // 1: read every stop decision before queueing the next iteration
+    "loo_v4", "loo_nofirst", "loo_fullfill", "loo_block", "loo_stages", "loo_passes", "loo_occ3", "loo_dbg", "prepack_v1",
+    "loo_by_pop",         // 1: leave-one-out EM population by population (one packed-row buffer at a time); -1: never
+    "loo_variant",        // inner-loop variant of the packed leave-one-out step kernel (experiments)
+    "upload_sync",        // 1: wgs_upload_gl_async falls back to the chunked synchronous upload
+    "z_exact_means",      // 1: order-independent fixed-point class means (NOT the reference's float32 means)
+    "rmse_exact",         // 0: stop rule on the float64 sum only (no sequential float32 tie-break)
+    "rmse_band_ppm",      // half-width of the tie-break band around the tolerance, parts per million of the RMSE (0 = automatic)
+    "nccl_sums",          // 0: final sums through the host callback even when a communicator is attached
+};
 
 int fail(wgs_ctx* c, const char* fmt, ...)
 {
@@ -120,6 +155,9 @@ struct NcclApi {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ struct NcclId128, int) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -134,13 +172,18 @@ bool nccl_load()
     g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void**, int, NcclId128, int))dlsym(h, "ncclCommInitRank");
     g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclBroadcast");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) return false;
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy || !g_nccl.Send || !g_nccl.Recv ||
+        !g_nccl.Broadcast) return false;
     g_nccl.lib = h;
     return true;
 }
 constexpr int kNcclFloat64 = 8;                                 // ncclDataType_t::ncclFloat64 (nccl.h)
+constexpr int kNcclInt64 = 4, kNcclChar = 0;
 
 int name_id(wgs_ctx* ctx, const char* name)
 {
@@ -187,10 +230,10 @@ void fold_timing(wgs_ctx* ctx)
     ctx->timed.clear();
 }
 
-// WGS_TRACE=1: wall-clock of the host-side phases of every API call on stderr
+// option "trace": wall-clock of the host-side phases of every API call on stderr
 struct Trace {
     const char* what; std::chrono::steady_clock::time_point t0; bool on;
-    explicit Trace(const char* w) : what(w), t0(std::chrono::steady_clock::now()) { static int en = getenv("WGS_TRACE") ? 1 : 0; on = en; }
+    Trace(const wgs_ctx* c, const char* w) : what(w), t0(std::chrono::steady_clock::now()), on(opt(c, "trace") != 0) {}
     void lap(const char* phase) {
         if (!on) return;
         auto t1 = std::chrono::steady_clock::now();
@@ -425,8 +468,6 @@ int launch_pop_like_i(wgs_ctx* ctx, const float2* G, long M, const float* dA, in
 constexpr int pop_like_imax(int KT) { return KT <= 10 ? 2 : 1; }
 int pop_like_inds(int KT, int ldg)
 {
-    const char* e = getenv("WGS_POPLIKE_I");      // experiment switch: 1 forces one individual per thread
-    if (e && e[0] == '1') return 1;
     return ldg > 64 ? pop_like_imax(KT) : 1;
 }
 template <int KT, int R>
@@ -492,7 +533,7 @@ int launch_pop_like2_i(wgs_ctx* ctx, const float2* G, long M, const float* dA, i
         int waste = (groups + w - 1) / w * w - groups;
         if (waste <= best_waste) { best_waste = waste; wx = w; }
     }
-    if (const char* env_wx = getenv("WGS_PL2_WX")) wx = std::max(1, std::min(4, atoi(env_wx)));
+    if (int o = opt(ctx, "pl2_wx", 0)) wx = std::max(1, std::min(4, o));
     const int gx = (groups + wx - 1) / wx;
     // per-pass coefficient rows, padded to whole tiles so that the staging copies never run past the end
     const long Mpad = (M + kPL2TS - 1) / kPL2TS * kPL2TS;
@@ -550,7 +591,7 @@ bool loo_like2_cfg(wgs_ctx* ctx, long M, int ldf, int K, LooLike2Cfg* c)
     c->wide = K > 10;                                             // one block per SM, <= 4 sites per tile (see the kernel)
     // more than 10 column groups and a narrow population tile: big blocks (up to 18 warps, one per SM) build the cells of
     // a state row once per 18 warps of individuals instead of once per 10
-    c->big = !c->wide && groups > kLL2MaxW && getenv("WGS_LOOLIKE_SMALLBLOCK") == nullptr;
+    c->big = !c->wide && groups > kLL2MaxW && !opt(ctx, "loolike_smallblock");
     const int maxw = c->wide ? kLL2WideW : (c->big ? kLL2BigW : kLL2MaxW);
     const int nb = (groups + maxw - 1) / maxw;                    // blocks per site split
     c->W = (groups + nb - 1) / nb;
@@ -651,9 +692,28 @@ int af_R(wgs_ctx* ctx, const float* dA, long n, int* R_out, float* margin_out = 
     return 0;
 }
 
-// partial sums [ldg][K] on device -> host [N][K] in Beagle order
-int cols_to_host(wgs_ctx* ctx, const double* d_colsums, int K, double* out)
+// Cross-rank sums of the small per-individual / per-population results, on the device: the ranks' local values are
+// all-gathered over the context's own communicator (NVLink) and added IN RANK ORDER, so every rank holds the same
+// bits and they do not depend on NCCL's reduction schedule.  Without a communicator (or with option nccl_sums = 0)
+// the operators return local partial sums and the caller combines them (wgs_partials_combined() tells which).
+bool nccl_sums(const wgs_ctx* ctx) { return ctx->fn && ctx->nccl_comm && opt(ctx, "nccl_sums", 1) != 0; }
+int dev_all_sum(wgs_ctx* ctx, void* dbuf, size_t n, int dtype)
 {
+    DevBuf g;
+    if (buf_alloc(ctx, g, (size_t)ctx->nccl_world * n * 8)) return 1;
+    int rc_ = g_nccl.AllGather(dbuf, g.p, n, dtype == WGS_F64 ? kNcclFloat64 : kNcclInt64, ctx->nccl_comm, ctx->stream);
+    if (rc_) return fail(ctx, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc_) : "?");
+    if (dtype == WGS_F64)
+        LAUNCH("rank_sum", em_rank_sum_kernel, grid_for((long)n, 128, ctx->num_sm * 4), 128, 0, ctx->stream, g.as<double>(), ctx->nccl_world, (int)n, (double*)dbuf);
+    else
+        LAUNCH("rank_sum", rank_sum_i64_kernel, grid_for((long)n, 128, ctx->num_sm * 4), 128, 0, ctx->stream, g.as<long long>(), ctx->nccl_world, (int)n, (long long*)dbuf);
+    return 0;
+}
+
+// partial sums [ldg][K] on device -> host [N][K] in Beagle order (summed over the ranks first when the context has a communicator)
+int cols_to_host(wgs_ctx* ctx, double* d_colsums, int K, double* out)
+{
+    if (nccl_sums(ctx) && dev_all_sum(ctx, d_colsums, (size_t)ctx->ldg * K, WGS_F64)) return 1;
     std::vector<double> h((size_t)ctx->ldg * K);
     CU(cudaMemcpyAsync(h.data(), d_colsums, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -670,7 +730,35 @@ struct EmState {
     DevBuf partials, ssq, count, active, iters, gathered;
     std::vector<int> h_active, h_iters;
     int slot_c0[2] = {0, 0}, slot_nc[2] = {0, 0};
+    // exact stop rule (the reference's sequential float32 sum, emMAF_cy.pyx:26-33) for checks that land inside the
+    // band in which the exact FP64 sum cannot decide: D2 [M][ldg] = the squared changes of the last iteration
+    DevBuf d2, serial, carry, uncertain;
+    bool exact = false;
+    bool chain_on = false, chain_always = false, missed = false;   // site-sharded runs: the rank chain is queued only near convergence
+    double band_override = 0.0;
 };
+
+// The reference's stop sum is sequential float32; `exact` runs keep what is needed to reproduce it (option
+// rmse_exact = 0 decides on the FP64 sums alone).  rmse_band_ppm: 0 = the rigorous band for the number of addends,
+// > 0 = that many parts per million of the tolerance, < 0 = every check is resolved sequentially (tests).
+double band_override_of(const wgs_ctx* ctx)
+{
+    const int ppm = opt(ctx, "rmse_band_ppm", 0);
+    return ppm == 0 ? 0.0 : (ppm < 0 ? -1.0 : ppm * 1e-6);
+}
+// host mirror of em_band (wgs_kernels.cuh)
+bool em_uncertain(double ssq, double count, double tole, double band_override)
+{
+    float res = (float)ssq;
+    res = res / (float)count;
+    const double diff = std::sqrt((double)res);
+    double band = band_override;
+    if (band == 0.0) {
+        const double ku = count * 5.9604644775390625e-08;
+        band = ku >= 0.5 ? -1.0 : 0.5 * ku / (1.0 - ku) + 1e-4;
+    }
+    return band < 0.0 || std::fabs(diff - tole) <= band * tole;
+}
 
 // The decision kernels write straight into mapped pinned host memory (no copy to queue, nothing pageable on the
 // path); the slots live in the context because cudaHostAlloc / cudaFreeHost synchronise the device.
@@ -690,17 +778,64 @@ int em_pin_reserve(wgs_ctx* ctx, size_t ints)
     return 0;
 }
 
-int em_state_init(wgs_ctx* ctx, EmState& st, int np, int ld, int nblocks, const std::vector<int>& active0)
+int em_state_init(wgs_ctx* ctx, EmState& st, int np, int ld, int nblocks, const std::vector<int>& active0, bool exact = false)
 {
     st.np = np; st.ld = ld; st.nblocks = nblocks;
     if (buf_alloc(ctx, st.partials, (size_t)nblocks * ld * sizeof(double)) || buf_alloc(ctx, st.ssq, (size_t)np * sizeof(double)) ||
         buf_alloc(ctx, st.active, (size_t)np * sizeof(int)) || buf_alloc(ctx, st.iters, (size_t)np * sizeof(int))) return 1;
-    if (em_pin_reserve(ctx, (size_t)np + 1)) return 1;
+    if (em_pin_reserve(ctx, (size_t)np + 3)) return 1;
     CU(cudaMemsetAsync(st.partials.p, 0, (size_t)nblocks * ld * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(st.iters.p, 0, (size_t)np * sizeof(int), ctx->stream));
     st.h_active = active0;
     st.h_iters.assign(np, 0);
     CU(cudaMemcpyAsync(st.active.p, st.h_active.data(), (size_t)np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    st.exact = exact;
+    st.band_override = band_override_of(ctx);
+    if (exact) {
+        const long M = ctx->M();
+        if (buf_alloc(ctx, st.d2, (size_t)std::max<long>(M, 1) * ctx->ldg * sizeof(float)) || buf_alloc(ctx, st.serial, (size_t)np * sizeof(float)) ||
+            buf_alloc(ctx, st.carry, (size_t)np * sizeof(float)) || buf_alloc(ctx, st.uncertain, (size_t)np * sizeof(int))) return 1;
+        CU(cudaMemsetAsync(st.d2.p, 0, (size_t)std::max<long>(M, 1) * ctx->ldg * sizeof(float), ctx->stream));   // masked sites are never written: + 0
+        CU(cudaMemsetAsync(st.serial.p, 0, (size_t)np * sizeof(float), ctx->stream));
+    }
+    return 0;
+}
+
+constexpr int kNcclFloat32 = 7;
+
+// Hand `n` floats from rank to rank in site order: every rank runs launch(carry_in) - which must leave its running
+// values in `vals` - after it has received the previous rank's; the last rank's values are then broadcast, so every
+// rank returns with the whole-file values in `vals`.  With a communicator everything is queued on the compute
+// stream (no host synchronisation); through the host callback the ranks take turns (one blocking round each).
+template <class Launch>
+int chain_floats(wgs_ctx* ctx, float* vals, float* carry, size_t n, Launch&& launch)
+{
+    if (!ctx->fn || ctx->world <= 1) return launch((const float*)nullptr);
+    const int r = ctx->rank, W = ctx->world;
+    if (ctx->nccl_comm) {
+        int rc_ = 0;
+        if (r > 0) rc_ = g_nccl.Recv(carry, n, kNcclFloat32, r - 1, ctx->nccl_comm, ctx->stream);
+        if (!rc_ && launch(r > 0 ? (const float*)carry : (const float*)nullptr)) return 1;
+        if (!rc_ && r < W - 1) rc_ = g_nccl.Send(vals, n, kNcclFloat32, r + 1, ctx->nccl_comm, ctx->stream);
+        if (!rc_) rc_ = g_nccl.Broadcast(vals, vals, n, kNcclFloat32, W - 1, ctx->nccl_comm, ctx->stream);
+        if (rc_) return fail(ctx, "NCCL hand-over of the sequential sums failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc_) : "?");
+        return 0;
+    }
+    std::vector<long long> h(n);                                 // float bits travel as integers: a sum with one contributor is exact
+    std::vector<float> hv(n);
+    for (int q = 0; q < W; ++q) {
+        if (q == r) {
+            if (launch(q > 0 ? (const float*)carry : (const float*)nullptr)) return 1;
+            CU(cudaMemcpyAsync(hv.data(), vals, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (size_t e = 0; e < n; ++e) { unsigned b; memcpy(&b, &hv[e], 4); h[e] = (long long)b; }
+        } else std::fill(h.begin(), h.end(), 0LL);
+        ctx->fn(h.data(), (int64_t)n, WGS_I64, ctx->user);
+        for (size_t e = 0; e < n; ++e) { unsigned b = (unsigned)h[e]; memcpy(&hv[e], &b, 4); }
+        float* dst = (q + 1 == W) ? vals : carry;
+        if (q + 1 == r || q + 1 == W) CU(cudaMemcpyAsync(dst, hv.data(), n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));                  // hv is reused next round
+    }
     return 0;
 }
 
@@ -733,8 +868,47 @@ int em_after_step_queue(wgs_ctx* ctx, EmState& st, double tole, int iteration, c
         CU(cudaMemcpyAsync(st.ssq.as<double>() + c0, h.data(), nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));                  // h is a local
     }
+    const int* d_unc = nullptr;
+    const float* d_serial = nullptr;
+    if (st.exact) {
+        // checks inside the band where the FP64 sum cannot decide are resolved with the reference's own sequential
+        // float32 sum, rebuilt from D2 (warp_seqsum32); under site sharding the running sums pass from rank to rank
+        const double* cnt = d_count ? d_count + c0 : nullptr;
+        auto resolve = [&](const float* carry_in, bool sums) -> int {
+            LAUNCH("em_resolve", em_resolve_kernel, std::max(1, std::min((nc + 7) / 8, ctx->num_sm * 2)), 256, 0, ctx->stream,
+                   st.ssq.as<double>() + c0, cnt, count_all, nc, tole, st.band_override, st.active.as<int>() + c0,
+                   sums ? st.d2.as<float>() + c0 : (const float*)nullptr, ctx->ldg, ctx->M(), carry_in, st.serial.as<float>() + c0,
+                   st.uncertain.as<int>() + c0);
+            return 0;
+        };
+        const bool sharded = ctx->fn && ctx->world > 1;
+        bool have_sums = true;
+        if (!sharded) {
+            if (resolve(nullptr, true)) return 1;
+        } else if (ctx->nccl_comm) {
+            if (st.chain_on || st.chain_always) {
+                if (chain_floats(ctx, st.serial.as<float>() + c0, st.carry.as<float>() + c0, (size_t)nc,
+                                 [&](const float* cin) { return resolve(cin, true); })) return 1;
+            } else {                                             // far from convergence: flags only (a flag raised here restarts the EM, see run_em_loo)
+                if (resolve(nullptr, false)) return 1;
+                have_sums = false;
+            }
+        } else {
+            // host callback: the sums already pass through the host every iteration - look at the flags first
+            if (resolve(nullptr, false)) return 1;
+            std::vector<int> hu(nc);
+            CU(cudaMemcpyAsync(hu.data(), st.uncertain.as<int>() + c0, nc * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            bool any = false;
+            for (int v : hu) any = any || v;
+            if (any && chain_floats(ctx, st.serial.as<float>() + c0, st.carry.as<float>() + c0, (size_t)nc,
+                                    [&](const float* cin) { return resolve(cin, true); })) return 1;
+        }
+        d_unc = st.uncertain.as<int>() + c0;
+        d_serial = have_sums ? st.serial.as<float>() + c0 : nullptr;
+    }
     LAUNCH("em_decide", em_decide_kernel, 1, 1024, 0, ctx->stream, st.ssq.as<double>() + c0, d_count ? d_count + c0 : nullptr, count_all, nc, tole,
-           iteration, st.active.as<int>() + c0, st.iters.as<int>() + c0, ctx->em_pin_dev[slot]);
+           iteration, st.active.as<int>() + c0, st.iters.as<int>() + c0, ctx->em_pin_dev[slot], d_unc, d_serial, 1 + nc);
     CU(cudaEventRecord(ctx->em_ev[slot], ctx->stream));
     st.slot_c0[slot] = c0; st.slot_nc[slot] = nc;
     return 0;
@@ -743,7 +917,10 @@ int em_after_step_wait(wgs_ctx* ctx, EmState& st, int slot, int* n_active)
 {
     CU(cudaEventSynchronize(ctx->em_ev[slot]));
     *n_active = ctx->em_pin[slot][0];
-    memcpy(st.h_active.data() + st.slot_c0[slot], ctx->em_pin[slot] + 1, (size_t)st.slot_nc[slot] * sizeof(int));
+    const int nc = st.slot_nc[slot];
+    memcpy(st.h_active.data() + st.slot_c0[slot], ctx->em_pin[slot] + 1, (size_t)nc * sizeof(int));
+    st.chain_on = ctx->em_pin[slot][1 + nc] != 0;                 // some problem is within 30x of the tolerance: queue the rank chain from now on
+    if (ctx->em_pin[slot][2 + nc]) st.missed = true;              // a check needed the chain before it was on
     return 0;
 }
 int em_after_step(wgs_ctx* ctx, EmState& st, double tole, int iteration, const double* d_count, double count_all, int* n_active,
@@ -780,7 +957,7 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
     while (R > 8 && 2 * (size_t)R * row16 * 16 > 110 * 1024) R /= 2;
     size_t smem = 2 * (size_t)R * row16 * 16;
     if (smem > 220 * 1024) return fail(ctx, "population of %d individuals exceeds the EM shared-memory tile", nmax);
-    const bool multi = getenv("WGS_EM_STEP") == nullptr;
+    const bool multi = !opt(ctx, "em_step");
     // register-tile variant (em_pop_multi2): TPR threads per row, up to 4 quads of individuals each (n <= 512)
     int tpr = 4, qpt = 4;
     {
@@ -788,7 +965,7 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
         if (nqmax <= 4) qpt = 1; else if (nqmax <= 8) qpt = 2; else qpt = 4;
         while (tpr < 32 && tpr * qpt < nqmax) tpr *= 2;
     }
-    const bool packed = multi && getenv("WGS_EM_MULTI1") == nullptr && tpr * qpt * 4 >= nmax;
+    const bool packed = multi && !opt(ctx, "em_multi1") && tpr * qpt * 4 >= nmax;
     int raw16 = (nmax + 3) / 4 * 2;                             // pairs per slab row, whole quads ...
     if (raw16 % 4 == 0) raw16 += 2;                             // ... rows two apart land on different bank groups
     const int R2 = 256 / tpr;
@@ -847,6 +1024,11 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
     std::vector<int> cur(K, 0), done(K, 0), replay(K, 0), run(K, 0);
     std::vector<char> fin(K, 0);
     std::vector<double> h(np);
+    // exact stop rule (see EmState): the register-tile kernel's per-iteration history holds what the sequential sum needs
+    const bool exact = packed && opt(ctx, "rmse_exact", 1) != 0;
+    const double band_ov = band_override_of(ctx);
+    DevBuf dser, dcarry;
+    if (exact && (buf_alloc(ctx, dser, sizeof(float)) || buf_alloc(ctx, dcarry, sizeof(float)))) return 1;
     for (;;) {
         bool any = false;
         for (int k = 0; k < K; ++k) {
@@ -876,9 +1058,10 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
             add_work(ctx, "em_pop", (double)M * inds * 8.0 + (double)M * act * 8.0, (double)M * units);
         }
         LAUNCH("em_ssq_reduce", em_ssq_reduce_kernel, (np + 7) / 8, 256, 0, ctx->stream, partials.as<double>(), gx, np, np, ssq.as<double>());
+        if (nccl_sums(ctx) && dev_all_sum(ctx, ssq.p, np, WGS_F64)) return 1;
         CU(cudaMemcpyAsync(h.data(), ssq.p, np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        if (ctx->fn) ctx->fn(h.data(), np, WGS_F64, ctx->user);
+        if (ctx->fn && !nccl_sums(ctx)) ctx->fn(h.data(), np, WGS_F64, ctx->user);
         for (int k = 0; k < K; ++k) {
             if (run[k] <= 0) continue;
             if (replay[k] > 0) {                                            // exactly t* iterations from the chunk's start state
@@ -886,8 +1069,26 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
                 continue;
             }
             int tstar = 0;
-            for (int u = 0; u < run[k] && !tstar; ++u)
-                if (em_converged(h[(size_t)k * kEmChunk + u], (double)ctx->Mtot(), tole)) tstar = u + 1;
+            for (int u = 0; u < run[k] && !tstar; ++u) {
+                const double ssq_u = h[(size_t)k * kEmChunk + u];
+                bool conv = em_converged(ssq_u, (double)ctx->Mtot(), tole);
+                if (exact && em_uncertain(ssq_u, (double)ctx->Mtot(), tole, band_ov)) {
+                    // inside the band where the exact sum cannot decide: the reference's sequential float32 sum of this
+                    // iteration's squared changes, from the state history (ranks chained in site order)
+                    const float* curp = hist.as<float>() + ((size_t)u * K + k) * M;
+                    const float* prevp = u == 0 ? (cur[k] ? FT1.as<float>() : FT) + (size_t)k * M : hist.as<float>() + ((size_t)(u - 1) * K + k) * M;
+                    if (chain_floats(ctx, dser.as<float>(), dcarry.as<float>(), 1, [&](const float* cin) {
+                            LAUNCH("em_resolve", seqsum_pair_kernel, 1, 32, 0, ctx->stream, curp, prevp, M, cin, dser.as<float>());
+                            return 0;
+                        })) return 1;
+                    float ser = 0.f;
+                    CU(cudaMemcpyAsync(&ser, dser.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                    float res = ser / (float)ctx->Mtot();
+                    conv = std::sqrt((double)res) < tole;
+                }
+                if (conv) tstar = u + 1;
+            }
             if (tstar == 0 || tstar == run[k]) {                            // the state written by this pass is the one to keep
                 cur[k] ^= 1; done[k] += run[k];
                 if (tstar) { fin[k] = 1; iters_out[k] = done[k]; }
@@ -922,9 +1123,9 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
     double best_u = -1;
     // whole multiples of 4 warps only: 7 warps per block leave one scheduler of the SM with less work
     // than the others (measured: 12 % slower than 8 warps, scripts/microbench/loo_quad_rate.cu)
-    const char* env_bd = getenv("WGS_LOO_BLOCK");
+    const int opt_bd = opt(ctx, "loo_block", 0);
     for (int bd = 128; bd <= 512; bd += 128) {
-        if (env_bd && atoi(env_bd) != bd) continue;
+        if (opt_bd && opt_bd != bd) continue;
         int rpp = bd / nq;
         if (rpp < 1) continue;
         double u = (double)(rpp * nq) / bd;
@@ -939,7 +1140,7 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
         // ring of row groups: as many stages as fit in ~100 KB (two resident blocks per SM), at least 3
         const size_t group_bytes = (size_t)best.rows_per_pass * loo5_row_units(n) * 16;
         int stages = (int)std::min<size_t>(kLoo5MaxStages, (100 * 1024) / std::max<size_t>(group_bytes, 1));
-        if (const char* env_s = getenv("WGS_LOO_STAGES")) stages = atoi(env_s);
+        if (int o = opt(ctx, "loo_stages", 0)) stages = o;
         best.stages = std::max(3, std::min(stages, kLoo5MaxStages));
         best.passes = 1;
         best.smem = best.stages * group_bytes + (size_t)best.block * sizeof(float4);
@@ -948,7 +1149,7 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
         const size_t row_bytes = 2 * (size_t)((3 * nq) | 1) * 16 + (size_t)nq * 32;
         int passes = kLoo4MaxPasses;
         while (passes > 1 && (size_t)best.rows_per_pass * passes * row_bytes > 68 * 1024) --passes;
-        if (const char* env_p = getenv("WGS_LOO_PASSES")) passes = std::max(1, std::min(passes, atoi(env_p)));
+        if (int o = opt(ctx, "loo_passes", 0)) passes = std::max(1, std::min(passes, o));
         best.passes = passes;
         best.smem = (size_t)best.rows_per_pass * passes * row_bytes + (size_t)best.block * sizeof(float4);
     }
@@ -960,7 +1161,7 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
         CU(cudaFuncSetAttribute(KERN, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, best.block, best.smem));                        \
     } while (0)
-    if (packed) { if (best.big) LOO_PREP((loo_em_step5_kernel<512, 1>)); else if (getenv("WGS_LOO_OCC3")) LOO_PREP((loo_em_step5_kernel<256, 3>)); else LOO_PREP((loo_em_step5_kernel<256, 2>)); }
+    if (packed) { if (best.big) LOO_PREP((loo_em_step5_kernel<512, 1>)); else if (opt(ctx, "loo_occ3")) LOO_PREP((loo_em_step5_kernel<256, 3>)); else LOO_PREP((loo_em_step5_kernel<256, 2>)); }
     else        { if (best.big) LOO_PREP((loo_em_step4_kernel<512, 1>)); else LOO_PREP((loo_em_step4_kernel<256, 3>)); }
 #undef LOO_PREP
     best.grid = ctx->num_sm * std::max(occ, 1);
@@ -976,7 +1177,8 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
 // iteration.  Every problem sees exactly the same sequence of updates and decisions either way.
 int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const unsigned char* mask, const double* d_count,
                std::vector<int>& iters_cols, const std::vector<unsigned char>* sel = nullptr,
-               const std::vector<cudaEvent_t>* pop_ready = nullptr, const std::function<int(int)>* on_pop = nullptr)
+               const std::vector<cudaEvent_t>* pop_ready = nullptr, const std::function<int(int)>* on_pop = nullptr,
+               bool force_chain = false)
 {
     const long M = ctx->M();
     const int ldg = ctx->ldg, K = ctx->K;
@@ -989,7 +1191,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         const PopDesc pd = ctx->pops[k];
         const int nc = cfgs[k].nc;
         const size_t sm = (size_t)(256 / std::max(nc, 1)) * loo5_row_units(pd.n) * sizeof(ulonglong2);
-        if (nc <= 256 && sm <= 64 * 1024 && getenv("WGS_PREPACK_V1") == nullptr) {
+        if (nc <= 256 && sm <= 64 * 1024 && !opt(ctx, "prepack_v1")) {
             CU(cudaFuncSetAttribute(loo_prepack2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             const long ntl = (M + 256 / nc - 1) / (256 / nc);
             LAUNCH("loo_pack", loo_prepack2_kernel, (int)std::max<long>(1, std::min<long>(ntl, (long)ctx->num_sm * 5)), 256, sm, ctx->stream,
@@ -1009,8 +1211,8 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     // pre-packed pair polynomials (loo_em_step5): 80 bytes per 8 individuals and site, written once per call;
     // when the pool cannot provide them (or WGS_LOO_V4 is set) the in-kernel packing quad kernel runs instead
     std::vector<DevBuf> pk(K);
-    const int loo_dbg = getenv("WGS_LOO_DBG") ? atoi(getenv("WGS_LOO_DBG")) : 0;
-    bool packed = getenv("WGS_LOO_V4") == nullptr;
+    const int loo_dbg = opt(ctx, "loo_dbg", 0);
+    bool packed = !opt(ctx, "loo_v4");
     for (int k = 0; k < K && packed; ++k) {
         if (ctx->pops[k].n <= 1) continue;
         pk[k].owner = ctx;
@@ -1027,10 +1229,12 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         }
     }
     EmState st;
-    if (em_state_init(ctx, st, ldg, ldg, nblocks, active0)) return 1;
+    if (em_state_init(ctx, st, ldg, ldg, nblocks, active0, opt(ctx, "rmse_exact", 1) != 0)) return 1;
+    st.chain_always = force_chain;
+    float* const D2 = st.d2.as<float>();                         // null when the exact stop rule is switched off
     // When every real column is an active problem of a population that loo_first serves, iteration 1 writes all of
     // them without reading the start state: only the padding columns need a value (the step kernels load whole quads).
-    bool pads_only = !mask && !sel && iter >= 1 && getenv("WGS_LOO_NOFIRST") == nullptr && getenv("WGS_LOO_FULLFILL") == nullptr;
+    bool pads_only = !mask && !sel && iter >= 1 && !opt(ctx, "loo_nofirst") && !opt(ctx, "loo_fullfill");
     for (int k = 0; k < K; ++k)
         if (ctx->pops[k].n <= 1 || (ctx->pops[k].n + 1) / 2 > 32 * kFisherQ) pads_only = false;
     if (pads_only) {
@@ -1062,26 +1266,26 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         if (lc.packed) {
             if (lc.big)
                 LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
-                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
-            else if (!getenv("WGS_LOO_OCC3"))
+                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
+            else if (!opt(ctx, "loo_occ3"))
                 LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
-                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
+                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
             else
                 LAUNCH("loo_em", (loo_em_step5_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
-                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg);
+                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
         } else {
             if (lc.big)
                 LAUNCH("loo_em", (loo_em_step4_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
-                       lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
+                       lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, D2);
             else
                 LAUNCH("loo_em", (loo_em_step4_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n,
-                       lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles);
+                       lc.rows_per_pass, lc.passes, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, D2);
         }
         return 0;
     };
     // Iteration 1 starts every problem of a population from the same f: n evaluations per site serve all n problems
     // (loo_first_kernel) instead of n^2.  Populations above 512 individuals take the general step kernel.
-    const bool use_first = getenv("WGS_LOO_NOFIRST") == nullptr;
+    const bool use_first = !opt(ctx, "loo_nofirst");
     auto first_tpr = [&](int k) {
         int tpr = 2;
         const int cpr = (ctx->pops[k].n + 1) / 2;
@@ -1095,7 +1299,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         const size_t sm = (size_t)256 * 2 * kFisherQ * sizeof(float);
 #define LOO_FIRST(T)                                                                                             \
     LAUNCH("loo_first", loo_first_kernel<T>, cfgs[k].grid, 256, sm, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n, F, ldf, \
-           st.active.as<int>(), mask, st.partials.as<double>())
+           st.active.as<int>(), mask, st.partials.as<double>(), D2)
         if (tpr == 2) LOO_FIRST(2); else if (tpr == 4) LOO_FIRST(4); else if (tpr == 8) LOO_FIRST(8);
         else if (tpr == 16) LOO_FIRST(16); else LOO_FIRST(32);
 #undef LOO_FIRST
@@ -1120,7 +1324,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     // Look-ahead: iteration t+1 is queued before the host has read the decision of iteration t (the device skips
     // whatever that decision froze), so the GPU never idles on the round trip.  Not under site sharding, where the
     // squared changes pass through the host for the all-reduce anyway.
-    const bool ahead = (ctx->fn == nullptr || ctx->nccl_comm != nullptr) && getenv("WGS_EM_NO_LOOKAHEAD") == nullptr;
+    const bool ahead = (ctx->fn == nullptr || ctx->nccl_comm != nullptr) && !opt(ctx, "em_no_lookahead");
     const double count_all = (double)ctx->Mtot();
     if (pop_ready) {
         for (int ko = 0; ko < K; ++ko) {
@@ -1167,6 +1371,14 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         }
     }
     CU(cudaStreamSynchronize(ctx->stream));                      // a speculative round may still be running
+    if (st.missed && !force_chain) {
+        // A stop check landed inside the undecidable band while the rank chain was not queued (a population that
+        // converges by more than 30x within two iterations): run again with the chain on from the first iteration.
+        // The EM is deterministic, so nothing but time is lost.
+        for (auto& b : pk) buf_release(b);
+        buf_release(st.d2);
+        return run_em_loo(ctx, iter, tole, F, ldf, mask, d_count, iters_cols, sel, pop_ready, on_pop, true);
+    }
     iters_cols.resize(ldg);
     CU(cudaMemcpy(iters_cols.data(), st.iters.p, ldg * sizeof(int), cudaMemcpyDeviceToHost));
     CU(cudaGetLastError());
@@ -1218,6 +1430,12 @@ int32_t wgs_create(int32_t device, wgs_ctx** out)
     cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     if (em_pin_reserve(ctx, 1)) { g_create_error = ctx->err; wgs_destroy(ctx); return 1; }
+    if (getenv("WGS_DEBUG"))                                     // debugging only: WGS_<OPTION>=<int> seeds the option table once
+        for (const char* nm : kOptionNames) {
+            std::string env = "WGS_";
+            for (const char* p = nm; *p; ++p) env += (char)toupper(*p);
+            if (const char* v = getenv(env.c_str())) ctx->opts[nm] = atoi(v);
+        }
     *out = ctx;
     return 0;
 }
@@ -1235,6 +1453,20 @@ void wgs_destroy(wgs_ctx* ctx)
     for (int b = 0; b < 2; ++b) { if (ctx->em_pin[b]) cudaFreeHost(ctx->em_pin[b]); if (ctx->em_ev[b]) cudaEventDestroy(ctx->em_ev[b]); }
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
     delete ctx;
+}
+
+int32_t wgs_set_option(wgs_ctx* ctx, const char* name, int32_t value)
+{
+    for (const char* nm : kOptionNames)
+        if (!strcmp(nm, name)) { ctx->opts[name] = value; return 0; }
+    return fail(ctx, "unknown option '%s'", name);
+}
+
+int32_t wgs_get_option(const wgs_ctx* ctx, const char* name, int32_t* value)
+{
+    for (const char* nm : kOptionNames)
+        if (!strcmp(nm, name)) { *value = opt(ctx, name, 0); return 0; }
+    return 1;
 }
 
 void* wgs_host_alloc(int64_t bytes)
@@ -1275,6 +1507,14 @@ int32_t wgs_nccl_init(wgs_ctx* ctx, const void* id, int32_t rank, int32_t world)
     int rc = g_nccl.CommInitRank(&comm, world, uid, rank);
     if (rc) return fail(ctx, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     ctx->nccl_comm = comm; ctx->nccl_rank = rank; ctx->nccl_world = world;
+    ctx->rank = rank; ctx->world = world;
+    return 0;
+}
+
+int32_t wgs_set_rank(wgs_ctx* ctx, int32_t rank, int32_t world)
+{
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, "rank %d outside [0,%d)", rank, world);
+    ctx->rank = rank; ctx->world = world;
     return 0;
 }
 
@@ -1322,7 +1562,7 @@ int32_t wgs_upload_gl_async(wgs_ctx* ctx, const float* L, int64_t M, int32_t N)
         }
     }
     // interleaved ID files (many short runs) are better served by the chunked upload + permutation kernel
-    if (nruns > (size_t)8 * K + 64 || getenv("WGS_UPLOAD_SYNC")) return wgs_upload_gl(ctx, L, M, N, 0);
+    if (nruns > (size_t)8 * K + 64 || opt(ctx, "upload_sync")) return wgs_upload_gl(ctx, L, M, N, 0);
     dev_free(ctx, ctx->G[0]);
     if (dev_alloc(ctx, &ctx->G[0], (size_t)std::max<long>(M, 1) * ldg)) return 1;
     ctx->Mg[0] = M;
@@ -1374,8 +1614,8 @@ int32_t wgs_upload_ad(wgs_ctx* ctx, const int32_t* AD, int64_t M, int32_t N)
     if (dev_alloc(ctx, &ctx->AD, (size_t)std::max<long>(M, 1) * ctx->ldg)) return 1;
     ctx->M_ad = M;
     DevBuf flag;
-    if (buf_alloc(ctx, flag, sizeof(int))) return 1;
-    CU(cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
+    if (buf_alloc(ctx, flag, 2 * sizeof(int))) return 1;
+    CU(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     uchar2* dst = ctx->AD;
     int rc = upload_rows<int2>(ctx, (const int2*)AD, M, N, [&](int2* stage, long r0, long rows, cudaStream_t st) {
@@ -1383,9 +1623,10 @@ int32_t wgs_upload_ad(wgs_ctx* ctx, const int32_t* AD, int64_t M, int32_t N)
                dst + (size_t)r0 * ctx->ldg, ctx->ldg, ctx->d_ind_of_col, rows, flag.as<int>());
     });
     if (rc) return rc;
-    int bad = 0;
-    CU(cudaMemcpy(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (bad) return fail(ctx, "allele depth outside [0,254]: the packed uint8 layout cannot hold it");
+    int bad[2] = {0, 0};
+    CU(cudaMemcpy(bad, flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad[0]) return fail(ctx, "negative allele depth in the depth matrix");
+    ctx->ad_saturated = bad[1];                                  // stored as the "deeper than any class" sentinel
     return 0;
 }
 
@@ -1477,7 +1718,7 @@ static int ref_af_finish(wgs_ctx* ctx, RefAfRun& run, float* af_out, int32_t* it
 }
 static int ref_af_impl(wgs_ctx* ctx, int32_t iter, double tole, float* af_out, int32_t* iters_out)
 {
-    Trace tr("ref_af");
+    Trace tr(ctx, "ref_af");
     RefAfRun run;
     if (ref_af_begin(ctx, run)) return 1;
     tr.lap("alloc");
@@ -1537,7 +1778,7 @@ int32_t wgs_pop_like_partial(wgs_ctx* ctx, const float* af, int32_t K, double* o
     int R = 1;
     float margin = 0.f;
     if (af_R(ctx, dA.as<float>(), M * K, &R, &margin)) return 1;
-    const int R2 = getenv("WGS_POPLIKE_V1") ? 0 : pick_R2(margin);
+    const int R2 = opt(ctx, "poplike_v1") ? 0 : pick_R2(margin);
     if (R2 > 0) {
         // ratio form (pop_like2): every AF inside [2^-16, 1-2^-16] - always true after the reference's clipping
         Like2Cfg c2 = like2_cfg(ctx, M, R2);
@@ -1589,7 +1830,7 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
     const long M = ctx->M();
     const int K = ctx->K, ldg = ctx->ldg, N = ctx->N;
     const int ldf = ldg + (K + 3) / 4 * 4;
-    Trace tr("loo");
+    Trace tr(ctx, "loo");
     DevBuf F, dcols;
     if (!fused && !af_inout && !(ctx->d_af && ctx->af_rows == M && ctx->af_cols == K))
         return fail(ctx, "af_inout is NULL but no allele-frequency matrix is resident (call wgs_ref_af first)");
@@ -1639,7 +1880,7 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
     std::vector<float> lo, hi;
     clip_bounds(ctx, 1, lo, hi);
     LooLike2Cfg c2{};
-    const bool staged = getenv("WGS_LOOLIKE_V1") == nullptr && loo_like2_cfg(ctx, M, ldf, K, &c2);
+    const bool staged = !opt(ctx, "loolike_v1") && loo_like2_cfg(ctx, M, ldf, K, &c2);
     lo.resize(ldf, 0.0f); hi.resize(ldf, 1.0f);                  // full-data AF and pad columns: already inside [0, 1]
     DevBuf dlo, dhi;
     if (buf_alloc(ctx, dlo, ldf * sizeof(float)) || buf_alloc(ctx, dhi, ldf * sizeof(float))) return 1;
@@ -1759,7 +2000,7 @@ int32_t wgs_fisher_partial(wgs_ctx* ctx, const float* af, float* f_obs, float* n
     // barrier-free register-tile kernel (fisher2) for populations of up to 512 individuals
     int tpr = 2;
     while (tpr < 32 && tpr * kFisherQ < (nmax + 1) / 2) tpr *= 2;
-    const bool v2 = getenv("WGS_FISHER_V1") == nullptr && tpr * kFisherQ >= (nmax + 1) / 2;
+    const bool v2 = !opt(ctx, "fisher_v1") && tpr * kFisherQ >= (nmax + 1) / 2;
     const size_t smem2 = (size_t)(256 / tpr) * 2 * tpr * kFisherQ * sizeof(float);
     if (v2) {
         int occ2 = 1;
@@ -1791,6 +2032,7 @@ int32_t wgs_fisher_partial(wgs_ctx* ctx, const float* af, float* f_obs, float* n
            sums.as<double>());
     CU(cudaMemcpyAsync(f_obs, dF.p, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(ne_obs, dNe.p, (size_t)M * K * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nccl_sums(ctx) && dev_all_sum(ctx, sums.p, ldg, WGS_F64)) return 1;
     std::vector<double> h(ldg);
     CU(cudaMemcpyAsync(h.data(), sums.p, ldg * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1822,7 +2064,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
     const long M = ctx->M();
     const int ldg = ctx->ldg, N = ctx->N;
     const double e = 0.01;                                       // WGSassign.py:350, :430
-    Trace tr("zscore");
+    Trace tr(ctx, "zscore");
 
     std::vector<unsigned char> sel(ldg, 0);
     for (int i = ind_start; i < ind_end; ++i) sel[ctx->col_of_ind[i]] = 1;
@@ -1841,12 +2083,14 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         if (c.sites_per_block > cap) { c.sites_per_block = cap; c.gy = (int)((M + cap - 1) / cap); }
     }
     const double pairs = (double)M * (ind_end - ind_start);
-    // reference-faithful sequential float32 class means up to 2^18 sites on one GPU; the exact,
-    // order-independent tally above that and whenever sites are sharded (see wgs_zscore.cuh)
-    const char* env_exact = getenv("WGS_Z_EXACT_MEANS");
-    bool exact_means = ctx->fn != nullptr || ctx->Mtot() > (1L << 18);
-    if (env_exact && env_exact[0] == '1') exact_means = true;
-    if (env_exact && env_exact[0] == '0' && !ctx->fn) exact_means = false;
+    // The reference's class means are SEQUENTIAL float32 sums in site order (zscore.py:22); ztally_seq2 reproduces
+    // them for any number of sites, and under site sharding the ranks run it one after the other in site order,
+    // handing the table on (carry-in / carry-out).  Option z_exact_means = 1 selects the order-independent
+    // fixed-point tally instead (one pass, no chain; NOT the reference's means).
+    const bool exact_means = opt(ctx, "z_exact_means") != 0;
+    const bool sharded = ctx->fn != nullptr;
+    if (sharded && !exact_means && ctx->world <= 1)
+        return fail(ctx, "site-sharded z-score: wgs_set_rank (or wgs_nccl_init) must give this context its rank first");
     DevBuf dmaxd;
     if (buf_alloc(ctx, dmaxd, sizeof(int))) return 1;
     CU(cudaMemsetAsync(dmaxd.p, 0, sizeof(int), ctx->stream));
@@ -1858,16 +2102,49 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
                c.wx, c.sites_per_block, dtable.as<ZTally>(), ddeep.as<unsigned long long>());
         LAUNCH("zaux", zmaxdepth_kernel<ZTally>, ctx->num_sm * 4, 256, 0, ctx->stream, dtable.as<ZTally>(), (long)tab_n, dmaxd.as<int>());
     } else {
-        // reference-faithful: sequential float32 sums in site order, float32 divide (numpy's float32 mean)
-        LAUNCH("ztally", ztally_seq_kernel, (ldg + 31) / 32, 32, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M, dsel.as<unsigned char>(),
-               dtable.as<ZTallyF>(), ddeep.as<unsigned long long>());
+        CU(cudaFuncSetAttribute(ztally_seq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZSeqSmem));
+        const size_t tbytes = tab_n * sizeof(ZTallyF);
+        auto run_seq = [&]() -> int {
+            LAUNCH("ztally", ztally_seq2_kernel, (ldg + 31) / 32, 32, kZSeqSmem, ctx->stream, ctx->G[0], ctx->AD, ldg, M,
+                   dsel.as<unsigned char>(), dtable.as<ZTallyF>(), ddeep.as<unsigned long long>());
+            return 0;
+        };
+        if (!sharded) {
+            if (run_seq()) return 1;
+        } else if (ctx->nccl_comm) {
+            // rank r: receive the table from r-1, add this rank's sites, send it on; the last rank's table is the
+            // whole file's and is broadcast back (everything on the compute stream, over NVLink)
+            const int r = ctx->rank, W = ctx->world;
+            int rc_ = 0;
+            if (r > 0) rc_ = g_nccl.Recv(dtable.p, tbytes, kNcclChar, r - 1, ctx->nccl_comm, ctx->stream);
+            if (!rc_ && run_seq()) return 1;
+            if (!rc_ && r < W - 1) rc_ = g_nccl.Send(dtable.p, tbytes, kNcclChar, r + 1, ctx->nccl_comm, ctx->stream);
+            if (!rc_) rc_ = g_nccl.Broadcast(dtable.p, dtable.p, tbytes, kNcclChar, W - 1, ctx->nccl_comm, ctx->stream);
+            if (rc_) return fail(ctx, "NCCL table hand-over failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc_) : "?");
+        } else {
+            // no communicator: the same chain through the host callback - round q leaves rank q's table on every
+            // rank (an integer sum in which only rank q contributes: exact bits)
+            std::vector<long long> h(tbytes / 8);
+            for (int q = 0; q < ctx->world; ++q) {
+                if (q == ctx->rank) {
+                    if (run_seq()) return 1;
+                    CU(cudaMemcpyAsync(h.data(), dtable.p, tbytes, cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                } else std::fill(h.begin(), h.end(), 0LL);
+                ctx->fn(h.data(), (int64_t)h.size(), WGS_I64, ctx->user);
+                if (q + 1 == ctx->rank || q + 1 == ctx->world)
+                    CU(cudaMemcpyAsync(dtable.p, h.data(), tbytes, cudaMemcpyHostToDevice, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+            }
+        }
         LAUNCH("zaux", zmaxdepth_kernel<ZTallyF>, ctx->num_sm * 4, 256, 0, ctx->stream, dtable.as<ZTallyF>(), (long)tab_n, dmaxd.as<int>());
     }
     add_work(ctx, "ztally", pairs * 10.0, pairs);
     // Only the classes up to the deepest observed depth travel and are scanned: compact host tables [ldg][ncls].
-    // Under site sharding every rank must agree on the table shape, so the full table is kept there.
+    // The sequential tally leaves the same (whole-file) table on every rank; the fixed-point tally is summed on the
+    // host below, so under sharding every rank must keep the full table shape there.
     int dmax = kZDepthCap;
-    if (!ctx->fn) {
+    if (!sharded || !exact_means) {
         CU(cudaMemcpyAsync(&dmax, dmaxd.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         dmax = std::max(1, std::min(dmax, kZDepthCap));
@@ -1906,6 +2183,15 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         }
     }
 
+    // sites deeper than the class table (or saturated on upload): whole-file counts per individual, for the reference's
+    // class-count asserts below and for wgs_zscore_deep_sites
+    std::vector<unsigned long long> deep(ldg);
+    if (nccl_sums(ctx) && dev_all_sum(ctx, ddeep.p, ldg, WGS_I64)) return 1;
+    CU(cudaMemcpyAsync(deep.data(), ddeep.p, ldg * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->fn && !nccl_sums(ctx)) ctx->fn(deep.data(), (int64_t)ldg, WGS_I64, ctx->user);
+    ctx->z_deep_sites = 0;
+    for (int col = 0; col < ldg; ++col) ctx->z_deep_sites += (long)deep[col];
     tr.lap("tally+d2h");
     // ---- class decisions on the host (zscore.py:23-39, :63-79): a few hundred rows per individual ----
     std::vector<signed char> kmax(ctab_n, -1);
@@ -1934,6 +2220,10 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
                 bool pass = single_read ? (d == 1) : (t[id] > n_threshold && d != 0);
                 if (pass) { ++n_pass; ++per_depth[d]; }
             }
+        // In the reference every distinct (ref, alt) pair is a class, however deep: a site deeper than our table is
+        // at least one more class that passes a zero count threshold (it can never be KEPT: its depth would need
+        // all depth+1 splits) - it only matters for these two asserts (zscore.py:34-35).
+        if (!single_read && n_threshold <= 0 && deep[col] > 0) ++n_pass;
         if (n_pass == 0) return fail(ctx, "No loci were kept! Too stringent filtering?");
         if (n_pass == 1) return fail(ctx, "Not enough loci were kept! Too stringent filtering?");
         auto& rows = ctx->zclasses[i];
@@ -1982,9 +2272,10 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
            dkmax.as<signed char>(), dkmean.as<float>(), ncls, c.wx, c.sites_per_block, dkeep.as<unsigned char>(), dkept.as<unsigned long long>());
     add_work(ctx, "zkeep", pairs * 11.0, pairs);
     std::vector<long long> kept(ldg);
+    if (nccl_sums(ctx) && dev_all_sum(ctx, dkept.p, ldg, WGS_I64)) return 1;
     CU(cudaMemcpyAsync(kept.data(), dkept.p, ldg * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    if (ctx->fn) ctx->fn(kept.data(), ldg, WGS_I64, ctx->user);
+    if (ctx->fn && !nccl_sums(ctx)) ctx->fn(kept.data(), ldg, WGS_I64, ctx->user);
 
     tr.lap("tables h2d+keep");
     if (mode == 2) {                                             // preparation only: tallies, class tables, kept-site counts
@@ -2039,16 +2330,13 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
            c.sites_per_block, partials.as<double>());
     add_work(ctx, "zmoments", pairs * 15.0, pairs);
     LAUNCH("reduce", reduce_partials_kernel, grid_for(np3, 256, 64), 256, 0, ctx->stream, partials.as<double>(), c.gy, (long)np3, sums.as<double>());
+    if (nccl_sums(ctx) && dev_all_sum(ctx, sums.p, np3, WGS_F64)) return 1;
     std::vector<double> h(np3);
     CU(cudaMemcpyAsync(h.data(), sums.p, np3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    std::vector<unsigned long long> deep(ldg);
-    CU(cudaMemcpyAsync(deep.data(), ddeep.p, ldg * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     tr.lap("moments");
-    if (ctx->fn) ctx->fn(h.data(), (int64_t)np3, WGS_F64, ctx->user);
-    ctx->z_deep_sites = 0;
-    for (int col = 0; col < ldg; ++col) ctx->z_deep_sites += (long)deep[col];
+    if (ctx->fn && !nccl_sums(ctx)) ctx->fn(h.data(), (int64_t)np3, WGS_F64, ctx->user);
 
     for (int i = ind_start; i < ind_end; ++i) {
         const int col = ctx->col_of_ind[i];
@@ -2191,7 +2479,23 @@ int32_t wgs_debug_stream(wgs_ctx* ctx, int32_t mode, double* ms_out, double* byt
     return 0;
 }
 
+int32_t wgs_debug_seqsum(wgs_ctx* ctx, const float* x, int64_t n, float carry_in, float* out)
+{
+    cudaSetDevice(ctx->device);
+    DevBuf dx, dc, dout;
+    if (buf_alloc(ctx, dx, (size_t)std::max<int64_t>(n, 1) * sizeof(float)) || buf_alloc(ctx, dc, sizeof(float)) || buf_alloc(ctx, dout, sizeof(float))) return 1;
+    CU(cudaMemcpyAsync(dx.p, x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dc.p, &carry_in, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH("em_resolve", seqsum_vec_kernel, 1, 32, 0, ctx->stream, dx.as<float>(), (long)n, dc.as<float>(), dout.as<float>());
+    CU(cudaMemcpyAsync(out, dout.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int64_t wgs_launch_count(const wgs_ctx* ctx) { return ctx->launches; }
+
+int32_t wgs_partials_combined(const wgs_ctx* ctx) { return nccl_sums(ctx) ? 1 : 0; }
 
 int32_t wgs_timing_reset(wgs_ctx* ctx, int32_t enable)
 {

@@ -175,12 +175,15 @@ __global__ void unpack_kernel(const float2* __restrict__ G, int ldg, const int* 
     }
 }
 
-// allele depths: int32 [rows][2N] -> uchar2 [rows][ldg]; *overflow |= 1 if a count > 254
+// allele depths: int32 [rows][2N] -> uchar2 [rows][ldg].  A count above 254 cannot be held: the pair is stored as the
+// sentinel (255, 255) = "deeper than any class table" - such a site can never be kept by the reference either (its
+// depth would need all depth+1 splits observed, zscore.py:36-39) - and counted in flags[1]; a NEGATIVE count is
+// invalid input: flags[0] |= 1.
 __global__ void repack_ad_kernel(const int2* __restrict__ stage, int N, uchar2* __restrict__ AD, int ldg,
-                                 const int* __restrict__ ind_of_col, long rows, int* __restrict__ overflow)
+                                 const int* __restrict__ ind_of_col, long rows, int* __restrict__ flags)
 {
     long total = rows * (long)ldg;
-    int bad = 0;
+    int bad = 0, sat = 0;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         long r = e / ldg;
         int c = (int)(e - r * ldg);
@@ -188,12 +191,14 @@ __global__ void repack_ad_kernel(const int2* __restrict__ stage, int N, uchar2* 
         uchar2 v = make_uchar2(0, 0);
         if (src >= 0) {
             int2 a = stage[r * (long)N + src];
-            if (a.x < 0 || a.x > 254 || a.y < 0 || a.y > 254) bad = 1;
-            v = make_uchar2((unsigned char)a.x, (unsigned char)a.y);
+            if (a.x < 0 || a.y < 0) bad = 1;
+            if (a.x > 254 || a.y > 254) { ++sat; v = make_uchar2(255, 255); }
+            else v = make_uchar2((unsigned char)a.x, (unsigned char)a.y);
         }
         AD[e] = v;
     }
-    if (bad) atomicOr(overflow, 1);
+    if (bad) atomicOr(&flags[0], 1);
+    if (sat) atomicAdd(&flags[1], sat);
 }
 
 __global__ void unpack_ad_kernel(const uchar2* __restrict__ AD, int ldg, const int* __restrict__ col_of_ind, int N,
@@ -1525,7 +1530,8 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
                     const int* __restrict__ active,              // [ldg]
                     const unsigned char* __restrict__ mask,      // [M][ldg] or null
                     double* __restrict__ partials,               // [gridDim.x][ldg]
-                    long ntiles)
+                    long ntiles,
+                    float* __restrict__ D2)                      // [M][ldg] or null: this iteration's squared change per (site, problem)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -1637,7 +1643,7 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
             const float2 g0cd = unpack2(v1.y), g1cd = unpack2(v2.x), g2cd = unpack2(v2.y);
             const float own[4] = {loo4_own(g0ab.x, g1ab.x, g2ab.x, c[0]), loo4_own(g0ab.y, g1ab.y, g2ab.y, c[1]),
                                   loo4_own(g0cd.x, g1cd.x, g2cd.x, c[2]), loo4_own(g0cd.y, g1cd.y, g2cd.y, c[3])};
-            float fo[4];
+            float fo[4], dq[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float2 a = unpack2(acc[k]);
@@ -1645,9 +1651,16 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
                 if (fn < 1e-12f) fn = 1e-12f;                   // comparisons are false for NaN: NaN survives
                 if (fn > 0.99999994f) fn = 0.99999994f;
                 fo[k] = fin[k];                                 // frozen / masked problems keep their value
-                if (okp & (1u << k)) { const float d = fn - fin[k]; ssq[k] += d * d; fo[k] = fn; }
+                dq[k] = 0.f;
+                if (okp & (1u << k)) {
+                    const float d = __fsub_rn(fn, fin[k]);
+                    dq[k] = __fmul_rn(d, d);
+                    ssq[k] = __fadd_rn(ssq[k], dq[k]);
+                    fo[k] = fn;
+                }
             }
             *reinterpret_cast<float4*>(&F[(s0 + sl) * (long)ldf + c0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
+            if (D2) *reinterpret_cast<float4*>(&D2[(s0 + sl) * (long)ldg + c0]) = make_float4(dq[0], dq[1], dq[2], dq[3]);
         }
         const long nxt = tl + gridDim.x;
         if (nxt < ntiles) {                                     // the next tile's raw rows landed while this one computed
@@ -1909,7 +1922,8 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
                     double* __restrict__ partials,               // [gridDim.x][ldg]
                     long ntiles,                                 // groups of rows_per_pass rows
                     int nstages,                                 // ring depth, 2..kLoo5MaxStages
-                    int dbg)                                     // experiments: 1 = no restaging (stale tiles), 2 = staging only
+                    int dbg,                                     // experiments: 1 = no restaging (stale tiles), 2 = staging only
+                    float* __restrict__ D2)                      // [M][ldg] or null: this iteration's squared change per (site, problem)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full[kLoo5MaxStages], empty[kLoo5MaxStages];
@@ -2008,7 +2022,7 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
             const float4 ga = rawrow[2 * ti], gc = rawrow[2 * ti + 1];
             const float own[4] = {loo5_own(ga.x, ga.y, third_gl(ga.x, ga.y), c[0]), loo5_own(ga.z, ga.w, third_gl(ga.z, ga.w), c[1]),
                                   loo5_own(gc.x, gc.y, third_gl(gc.x, gc.y), c[2]), loo5_own(gc.z, gc.w, third_gl(gc.z, gc.w), c[3])};
-            float fo[4];
+            float fo[4], dq[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float2 a = unpack2(acc[k]);
@@ -2016,9 +2030,16 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
                 if (fn < 1e-12f) fn = 1e-12f;                   // comparisons are false for NaN: NaN survives
                 if (fn > 0.99999994f) fn = 0.99999994f;
                 fo[k] = fin[k];                                 // frozen / masked problems keep their value
-                if (okp & (1u << k)) { const float d = fn - fin[k]; ssq[k] += d * d; fo[k] = fn; }
+                dq[k] = 0.f;
+                if (okp & (1u << k)) {                          // (v1 - v2) * (v1 - v2) as rmse1d forms it (emMAF_cy.pyx:31): no FMA
+                    const float d = __fsub_rn(fn, fin[k]);
+                    dq[k] = __fmul_rn(d, d);
+                    ssq[k] = __fadd_rn(ssq[k], dq[k]);
+                    fo[k] = fn;
+                }
             }
             *reinterpret_cast<float4*>(&F[(tl * TS + r) * (long)ldf + c0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
+            if (D2) *reinterpret_cast<float4*>(&D2[(tl * TS + r) * (long)ldg + c0]) = make_float4(dq[0], dq[1], dq[2], dq[3]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);               // this warp is done with the slot
@@ -2060,7 +2081,8 @@ loo_first_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n,
                  float* __restrict__ F, int ldf,
                  const int* __restrict__ active,            // [ldg]
                  const unsigned char* __restrict__ mask,    // [M][ldg] or null
-                 double* __restrict__ partials)             // [gridDim.x][ldg]
+                 double* __restrict__ partials,             // [gridDim.x][ldg]
+                 float* __restrict__ D2)                    // [M][ldg] or null: squared change per (site, problem)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* red = reinterpret_cast<float*>(smem_raw);      // [R][2 * TPR * kFisherQ]
@@ -2125,9 +2147,13 @@ loo_first_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n,
                     if (fb < 1e-12f) fb = 1e-12f;
                     if (fb > 0.99999994f) fb = 0.99999994f;
                     float2 out = make_float2(f0, f0);       // frozen / masked problems and the pad keep the start value
-                    if (ok & 1u) { const float d = fa - f0; sa[j] = fmaf(d, d, sa[j]); out.x = fa; }
-                    if (ok & 2u) { const float d = fb - f0; sb[j] = fmaf(d, d, sb[j]); out.y = fb; }
-                    if (ok) *reinterpret_cast<float2*>(&F[s * (long)ldf + col0 + 2 * q]) = out;
+                    float2 dq = make_float2(0.f, 0.f);
+                    if (ok & 1u) { const float d = __fsub_rn(fa, f0); dq.x = __fmul_rn(d, d); sa[j] = __fadd_rn(sa[j], dq.x); out.x = fa; }
+                    if (ok & 2u) { const float d = __fsub_rn(fb, f0); dq.y = __fmul_rn(d, d); sb[j] = __fadd_rn(sb[j], dq.y); out.y = fb; }
+                    if (ok) {
+                        *reinterpret_cast<float2*>(&F[s * (long)ldf + col0 + 2 * q]) = out;
+                        if (D2) *reinterpret_cast<float2*>(&D2[s * (long)ldg + col0 + 2 * q]) = dq;
+                    }
                 }
             }
         }
@@ -2178,32 +2204,166 @@ __global__ void em_rank_sum_kernel(const double* __restrict__ gathered, int worl
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Sequential float32 summation, exactly, at warp speed.
+//
+// The reference's stop rule adds the squared changes of ALL sites into ONE float32 accumulator, left to right
+// (rmse1d, emMAF_cy.pyx:29-32).  At millions of sites that sum differs from the exact one by up to
+// n 2^-24 relative (-0.4 % measured at 5 M sites, -2.3 % at 20 M: addends below half an ulp of the accumulator
+// vanish), enough to move the stop iteration.  Its bits depend on the order, so it cannot be a tree reduction - but
+// it does not have to be one addition at a time either: while the accumulator res = S u stays inside one binade
+// (u = its ulp, S a 24-bit integer), adding x >= 0 gives RN(S u + x) = (S + RN(x / u)) u unless x / u lies exactly
+// half-way between two integers (then the tie goes to the even S).  So over a block of 256 addends with no tie and
+// no binade crossing the accumulator simply advances by the INTEGER sum of the RN(x_i / u) - order-free, one REDUX
+// per block.  Ties (about one per 2^20 addends here) and binade crossings (~25 per sum) are detected, and that block
+// is then added one element at a time in order with real float32 additions.  The result is bit-identical to the
+// serial loop for every input (negative, NaN and infinite addends take the in-order path).
+// get(i): the i-th addend, 0 <= i < n; element order inside a block is i = base + 32 j + lane.
+// ---------------------------------------------------------------------------------------
+template <class Get>
+__device__ __forceinline__ float warp_seqsum32(float res, long n, Get get)
+{
+    const int lane = threadIdx.x & 31;
+    for (long base = 0; base < n; base += 256) {
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long i = base + 32 * j + lane;
+            x[j] = i < n ? get(i) : 0.0f;                    // + 0.0f never changes a float32 accumulator that started at +0
+        }
+        const unsigned bits = __float_as_uint(res);
+        const int eb = (int)(bits >> 23);                   // sign bit included: a negative accumulator fails the range test
+        bool bad = !(eb >= 30 && eb <= 250);
+        int qsum = 0;
+        if (!bad) {
+            const float scale = __uint_as_float((unsigned)(277 - eb) << 23);   // 1 / ulp(res), a power of two: x * scale is exact
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = x[j] * scale;
+                bad = bad || !(t >= 0.0f && t < 1048576.0f);                   // also NaN
+                const float fl = floorf(t);
+                bad = bad || (t - fl == 0.5f);                                 // a tie: its rounding depends on the parity of S
+                qsum += __float2int_rn(t);
+            }
+        }
+        const bool anybad = __any_sync(0xffffffffu, bad);
+        bool done = false;
+        if (!anybad) {
+            const unsigned Q = (unsigned)__reduce_add_sync(0xffffffffu, qsum);
+            const unsigned S = (bits & 0x007fffffu) | 0x00800000u;
+            if (S + Q < 0x01000000u) {                      // still inside the binade: no step in between rounded differently
+                res = __uint_as_float(((unsigned)eb << 23) | ((S + Q) & 0x007fffffu));
+                done = true;
+            }
+        }
+        if (!done) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) res = __fadd_rn(res, __shfl_sync(0xffffffffu, x[j], l));
+        }
+    }
+    return res;
+}
+
+// Stop-rule tie-break, part 1: one warp per problem.  A problem is UNCERTAIN when the RMSE from the exact (FP64)
+// sum of squared changes lies within `band` (relative) of the tolerance - band = the worst-case distance between
+// the exact sum and the reference's sequential float32 sum for that many addends (or the caller's override;
+// band < 0: every active problem).  For those, the float32 sum is reproduced from the squared changes the step
+// kernels left in D2[M][ldd] (column col0 + p; zero where a site is masked out), starting from carry_in[p]
+// (site-sharded runs chain the ranks in site order).  em_decide_kernel then decides on serial[p].
+__device__ __forceinline__ double em_band(double cnt, double band_override)
+{
+    if (band_override != 0.0) return band_override;         // < 0: always resolve
+    const double ku = cnt * 5.9604644775390625e-08;        // n 2^-24: Higham's gamma_n for recursive summation
+    if (ku >= 0.5) return -1.0;
+    return 0.5 * ku / (1.0 - ku) + 1e-4;                     // half of it on the square root, plus the FP32 per-thread partials of the FP64 sum
+}
+__global__ void __launch_bounds__(256)
+em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ count, double count_all, int np, double tole,
+                  double band_override, const int* __restrict__ active,
+                  const float* __restrict__ D2, int ldd, long M,
+                  const float* __restrict__ carry_in,       // [np] or null (first rank)
+                  float* __restrict__ serial,               // [np] out: the running float32 sum after this rank's sites
+                  int* __restrict__ uncertain)              // [np] out
+{
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < np; p += warps) {
+        int unc = 0;
+        if (active[p]) {
+            const double cnt = count ? count[p] : count_all;
+            float res = (float)ssq[p];
+            res = res / (float)cnt;
+            const double diff = sqrt((double)res);
+            const double band = em_band(cnt, band_override);
+            unc = (band < 0.0 || fabs(diff - tole) <= band * tole) ? 1 : 0;
+        }
+        if (unc && D2) {                                     // D2 == null: flags only
+            const float* col = D2 + p;
+            const float r = warp_seqsum32(carry_in ? carry_in[p] : 0.0f, M, [&](long i) { return __ldg(col + i * (long)ldd); });
+            if (lane == 0) serial[p] = r;
+        }
+        if (lane == 0) uncertain[p] = unc;
+    }
+}
+
+// the same float32 sum for a contiguous pair of state vectors (population EM: the per-iteration history): x_i = (cur_i - prev_i)^2
+__global__ void __launch_bounds__(32)
+seqsum_pair_kernel(const float* __restrict__ cur, const float* __restrict__ prev, long M, const float* __restrict__ carry_in,
+                   float* __restrict__ out)
+{
+    const float r = warp_seqsum32(carry_in ? carry_in[0] : 0.0f, M, [&](long i) { const float d = __fsub_rn(cur[i], prev[i]); return __fmul_rn(d, d); });
+    if (threadIdx.x == 0) out[0] = r;
+}
+__global__ void __launch_bounds__(32)
+seqsum_vec_kernel(const float* __restrict__ x, long n, const float* __restrict__ carry_in, float* __restrict__ out)
+{
+    const float r = warp_seqsum32(carry_in ? carry_in[0] : 0.0f, n, [&](long i) { return x[i]; });
+    if (threadIdx.x == 0) out[0] = r;
+}
+
+__global__ void rank_sum_i64_kernel(const long long* __restrict__ gathered, int world, int np, long long* __restrict__ out)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+        long long v = 0;
+        for (int r = 0; r < world; ++r) v += gathered[(long)r * np + p];
+        out[p] = v;
+    }
+}
+
 // Stop rule of emMAF.py:21-25 with rmse1d's float divide / double sqrt (emMAF_cy.pyx:32-33).
 // count[p] = number of sites in problem p's sum.  Single block.  result (mapped pinned host memory):
 // [0] = problems still active, [1 + p] = the updated flag of problem p.
 __global__ void em_decide_kernel(const double* __restrict__ ssq, const double* __restrict__ count, double count_all,
                                  int np, double tole, int iteration,
-                                 int* __restrict__ active, int* __restrict__ iters, int* __restrict__ result)
+                                 int* __restrict__ active, int* __restrict__ iters, int* __restrict__ result,
+                                 const int* __restrict__ uncertain = nullptr,   // [np] em_resolve_kernel's flags, or null: FP64 sums only
+                                 const float* __restrict__ serial = nullptr,    // [np] the sequential float32 sums of the uncertain problems
+                                 int near_slot = -1)                            // result[near_slot]: 1 if a problem still active is within 30x of the tolerance
 {
-    __shared__ int sh_cnt;
-    if (threadIdx.x == 0) sh_cnt = 0;
+    __shared__ int sh_cnt, sh_near, sh_missed;
+    if (threadIdx.x == 0) { sh_cnt = 0; sh_near = 0; sh_missed = 0; }
     __syncthreads();
-    int mine = 0;
+    int mine = 0, near = 0;
     for (int p = threadIdx.x; p < np; p += blockDim.x) {
         int a = active[p];
         if (a) {
             double cnt = count ? count[p] : count_all;
-            float res = (float)ssq[p];
+            const bool unc = uncertain && uncertain[p];
+            if (unc && !serial) atomicOr(&sh_missed, 1);    // needed the sequential sum, but the rank chain was not queued: the caller restarts
+            float res = (unc && serial) ? serial[p] : (float)ssq[p];
             res = res / (float)cnt;
             double diff = sqrt((double)res);
             if (diff < tole) { a = 0; active[p] = 0; iters[p] = iteration; }
-            else ++mine;
+            else { ++mine; if (diff <= 30.0 * tole) near = 1; }
         }
         result[1 + p] = a;
     }
     if (mine) atomicAdd(&sh_cnt, mine);
+    if (near) atomicOr(&sh_near, 1);
     __syncthreads();
-    if (threadIdx.x == 0) result[0] = sh_cnt;
+    if (threadIdx.x == 0) { result[0] = sh_cnt; if (near_slot >= 0) { result[near_slot] = sh_near; result[near_slot + 1] = sh_missed; } }
 }
 
 __global__ void fill_kernel(float* __restrict__ p, long n, float v)

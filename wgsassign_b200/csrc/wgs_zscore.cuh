@@ -198,6 +198,144 @@ ztally_seq_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
     if (ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
 }
 
+// ---------------------------------------------------------------------------------------
+// ztally_seq2: the same sequential float32 sums as ztally_seq - the reference's class means
+// (zscore.py:22) bit for bit - restructured so that it is the tally of EVERY run: any number
+// of sites, and any number of site-sharded ranks.
+//
+//  * The table is read as the CARRY-IN state and left as the carry-out: under site sharding
+//    the ranks run this kernel one after the other in site order and hand the table on
+//    (wgs_zscore: ncclSend / ncclRecv over NVLink, 16 bytes per (individual, class)), so the
+//    order of every addition is the reference's over the whole file.
+//  * One warp = 32 individuals, lane = individual (coalesced rows).  The (GL, AD) rows of 32
+//    sites per stage are streamed into an 8-stage shared-memory ring by the warp's own
+//    16-byte / 8-byte LDGSTS copies: ~80 KB in flight per warp, because with N / 32 warps on
+//    the whole GPU it is bytes in flight per warp, not resident warps, that cover HBM latency
+//    (8 register-prefetched sites per thread left ztally_seq latency-bound at ~1 us per 8 sites).
+//  * The accumulators of all classes up to depth 9 (55 classes: > 99.9 % of the sites at 2x)
+//    are thread-private float4 cells {s0, s1, s2, count} in shared memory, cell[class][lane]:
+//    one conflict-free LDS.128 / STS.128 per site whatever the class mix inside the warp
+//    (15 register accumulators with predicated adds cost 75 issue slots per site).  Two sites
+//    are in flight per thread: both cells are loaded first and the second site takes the
+//    first one's result when the classes coincide - the additions of a class stay in site
+//    order, the load latency is paid once per pair.  Deeper classes are read-modify-written
+//    in the individual's own table row (no other thread touches it).
+// ---------------------------------------------------------------------------------------
+constexpr int kZSeqHotDepth = 9;
+constexpr int kZSeqHot = (kZSeqHotDepth + 1) * (kZSeqHotDepth + 2) / 2;  // 55
+constexpr int kZSeqSB = 32;                                          // sites per ring stage
+constexpr int kZSeqStages = 8;
+constexpr size_t kZSeqSmem = (size_t)kZSeqHot * 32 * sizeof(float4) + (size_t)kZSeqStages * kZSeqSB * 32 * (sizeof(float2) + sizeof(uchar2));
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem));
+}
+
+__global__ void __launch_bounds__(32)
+ztally_seq2_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
+                   const unsigned char* __restrict__ sel,
+                   ZTallyF* __restrict__ table,            // [ldg][kZClasses]: carry-in, updated in place
+                   unsigned long long* __restrict__ deep)
+{
+    extern __shared__ __align__(16) unsigned char zs_raw[];
+    float4* cell = reinterpret_cast<float4*>(zs_raw);                          // [kZSeqHot][32]
+    float2* Gs = reinterpret_cast<float2*>(cell + kZSeqHot * 32);              // [stages][SB][32]
+    uchar2* As = reinterpret_cast<uchar2*>(Gs + kZSeqStages * kZSeqSB * 32);   // [stages][SB][32]
+    const int lane = threadIdx.x;
+    const int col0 = blockIdx.x * 32, col = col0 + lane;
+    const bool on = col < ldg && sel[col];
+    if (__ballot_sync(0xffffffffu, on) == 0u) return;
+    const int ncols = min(32, ldg - col0);                  // a multiple of 4: slabs are padded to 4 individuals
+    ZTallyF* mine = table + (size_t)(on ? col : col0) * kZClasses;
+    for (int c = 0; c < kZSeqHot; ++c) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) { const ZTallyF t = mine[c]; v = make_float4(t.s0, t.s1, t.s2, __int_as_float(t.cnt)); }
+        cell[c * 32 + lane] = v;
+    }
+    float4* const mycell = cell + lane;
+    const int gc = ncols >> 1, ac = ncols >> 2;             // 16-byte GL chunks / 8-byte AD chunks per site row
+    auto stage_load = [&](long s0, int st) {
+        const int rows = (int)min((long)kZSeqSB, M - s0);
+        if (rows > 0) {
+            float2* gd = Gs + (size_t)st * kZSeqSB * 32;
+            uchar2* ad = As + (size_t)st * kZSeqSB * 32;
+            if (ncols == 32) {
+                for (int e = lane; e < rows * 16; e += 32) { const int r = e >> 4, c = e & 15; cp_async16(gd + r * 32 + 2 * c, G + (s0 + r) * (long)ldg + col0 + 2 * c); }
+                for (int e = lane; e < rows * 8; e += 32) { const int r = e >> 3, c = e & 7; cp_async8(ad + r * 32 + 4 * c, AD + (s0 + r) * (long)ldg + col0 + 4 * c); }
+            } else {
+                for (int e = lane; e < rows * gc; e += 32) { const int r = e / gc, c = e - r * gc; cp_async16(gd + r * 32 + 2 * c, G + (s0 + r) * (long)ldg + col0 + 2 * c); }
+                for (int e = lane; e < rows * ac; e += 32) { const int r = e / ac, c = e - r * ac; cp_async8(ad + r * 32 + 4 * c, AD + (s0 + r) * (long)ldg + col0 + 4 * c); }
+            }
+        }
+        cp_async_commit();                                  // always: the wait below counts groups
+    };
+    const long nst = (M + kZSeqSB - 1) / kZSeqSB;
+    for (int p = 0; p < kZSeqStages - 1; ++p) stage_load((long)p * kZSeqSB, p);
+    int ndeep = 0;
+    ZTallyF* cold = table + (size_t)col * kZClasses;
+    for (long j = 0; j < nst; ++j) {
+        const int st = (int)(j % kZSeqStages);
+        cp_async_wait<kZSeqStages - 2>();                   // stage j has landed
+        __syncwarp();
+        stage_load((j + kZSeqStages - 1) * kZSeqSB, (int)((j + kZSeqStages - 1) % kZSeqStages));   // refills the slot consumed at j-1
+        const long s0 = j * kZSeqSB;
+        const int rows = (int)min((long)kZSeqSB, M - s0);
+        if (on) {
+            const float2* gs = Gs + (size_t)st * kZSeqSB * 32 + lane;
+            const uchar2* as = As + (size_t)st * kZSeqSB * 32 + lane;
+#pragma unroll 2
+            for (int u = 0; u < rows; u += 2) {
+                const bool two = u + 1 < rows;
+                const uchar2 a1 = as[u * 32], a2 = two ? as[(u + 1) * 32] : make_uchar2(255, 255);
+                const float2 g1 = gs[u * 32], g2 = two ? gs[(u + 1) * 32] : make_float2(0.f, 0.f);
+                const int d1 = a1.x + a1.y, d2 = a2.x + a2.y;
+                const int c1 = d1 * (d1 + 1) / 2 + a1.y, c2 = d2 * (d2 + 1) / 2 + a2.y;
+                const bool h1 = d1 <= kZSeqHotDepth, h2 = two && d2 <= kZSeqHotDepth;
+                float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1;
+                if (h1) v1 = mycell[c1 * 32];
+                if (h2) v2 = mycell[c2 * 32];
+                const float t1 = third_gl_np(g1.x, g1.y), t2 = third_gl_np(g2.x, g2.y);
+                if (h1) {
+                    v1.x = __fadd_rn(v1.x, g1.x); v1.y = __fadd_rn(v1.y, g1.y); v1.z = __fadd_rn(v1.z, t1);
+                    v1.w = __int_as_float(__float_as_int(v1.w) + 1);
+                }
+                if (h1 && h2 && c1 == c2) v2 = v1;           // same class twice in a row: the second addition sees the first
+                if (h2) {
+                    v2.x = __fadd_rn(v2.x, g2.x); v2.y = __fadd_rn(v2.y, g2.y); v2.z = __fadd_rn(v2.z, t2);
+                    v2.w = __int_as_float(__float_as_int(v2.w) + 1);
+                }
+                if (h1) mycell[c1 * 32] = v1;                 // program order: when the classes coincide the second store wins
+                if (h2) mycell[c2 * 32] = v2;
+                if (!h1) {                                  // rare: deeper than the shared-memory cells
+                    if (d1 <= kZDepthCap) {
+                        ZTallyF v = cold[c1];
+                        v.s0 = __fadd_rn(v.s0, g1.x); v.s1 = __fadd_rn(v.s1, g1.y); v.s2 = __fadd_rn(v.s2, t1); v.cnt += 1;
+                        cold[c1] = v;
+                    } else ++ndeep;
+                }
+                if (two && !h2) {
+                    if (d2 <= kZDepthCap) {
+                        ZTallyF v = cold[c2];
+                        v.s0 = __fadd_rn(v.s0, g2.x); v.s1 = __fadd_rn(v.s1, g2.y); v.s2 = __fadd_rn(v.s2, t2); v.cnt += 1;
+                        cold[c2] = v;
+                    } else ++ndeep;
+                }
+            }
+        }
+        __syncwarp();                                       // everyone is done with stage j before a later load refills it
+    }
+    cp_async_wait<0>();
+    if (on) {
+        for (int c = 0; c < kZSeqHot; ++c) {
+            const float4 v = cell[c * 32 + lane];
+            ZTallyF t; t.s0 = v.x; t.s1 = v.y; t.s2 = v.z; t.cnt = __float_as_int(v.w);
+            mine[c] = t;
+        }
+        if (ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
+    }
+}
+
 // Deepest read depth with a non-empty class in the tally table: the host then moves and scans only the
 // classes up to that depth (66 instead of 861 per individual at 10 reads) - the full-table copies and loops
 // were 40 % of a z-score call at 2,000 individuals.

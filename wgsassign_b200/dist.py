@@ -70,6 +70,14 @@ def allreduce_sum(arr):
     return arr
 
 
+def combine(ctx, arr):
+    """Cross-rank sum of an operator's per-individual partial sums: nothing to do when the context has already
+    combined them on the device (its own NCCL communicator), else the rank-ordered host sum."""
+    if ctx is not None and ctx.partials_combined():
+        return arr
+    return allreduce_sum(arr)
+
+
 def gather_rows(arr):
     """Concatenate per-rank row blocks (per-site outputs such as the AF matrix) on every rank."""
     if not enabled():
@@ -89,15 +97,16 @@ def gather_rows(arr):
     return np.concatenate(out, axis=0)
 
 
-def attach(ctx):
-    """Give a Context the shard geometry, the all-reduce callback and - on GPUs - its own NCCL communicator
-    for the EM stop rule (the id is created by rank 0 and broadcast through torch.distributed)."""
+def attach(ctx, nccl=True):
+    """Give a Context the shard geometry, its rank, the all-reduce callback and - on GPUs - its own NCCL
+    communicator (the id is created by rank 0 and broadcast through torch.distributed): with it the EM stop rule,
+    the z-score table hand-over and every small cross-rank sum stay on the device (NVLink); without it
+    (nccl=False, or no loadable libnccl) they pass through the host callback."""
     if enabled():
         ctx.set_shard(_cfg["M_total"], _cfg["offset"], allreduce_sum)
-        import os
+        ctx.set_rank(_cfg["rank"], _cfg["world"])
         import torch.distributed as td
-        if _cfg["device"] is not None and td.get_backend() == "nccl" and not os.environ.get("WGS_NO_NCCL") \
-                and not getattr(ctx, "_nccl_ready", False):
+        if nccl and _cfg["device"] is not None and td.get_backend() == "nccl" and not getattr(ctx, "_nccl_ready", False):
             import sys
             from . import _lib
             try:

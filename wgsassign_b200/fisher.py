@@ -15,7 +15,7 @@ def _run(L, af, IDs):
     ctx = session.context(L, pop_of_ind, len(pops))
     af32 = np.ascontiguousarray(af, dtype=np.float32)
     f_obs, ne_obs, ind_sum = ctx.fisher_partial(af32)
-    dist.allreduce_sum(ind_sum)
+    dist.combine(ctx, ind_sum)
     ne_ind = (ind_sum / float(dist.total_sites(L.shape[0]))).astype(np.float32)
     _last["key"] = (session._sig(L), session._sig(af32), IDs[:, 1].tobytes())
     _last["ne_ind"] = ne_ind

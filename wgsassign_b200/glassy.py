@@ -11,7 +11,7 @@ def assignLL(L, af, t):
     print(str(n) + " individuals to assign to " + str(k) + " populations")
     ctx = session.context(L)
     part = ctx.pop_like_partial(np.ascontiguousarray(af, dtype=np.float32))
-    dist.allreduce_sum(part)
+    dist.combine(ctx, part)
     return part.astype(np.float32)
 
 
@@ -33,8 +33,8 @@ def loo(L, af, IDs, t, maf_iter, maf_tole, downsampled_L=None, num_partitions=1)
     for it in its:
         if it > 0:
             print("EM (MAF) converged at iteration: " + str(int(it)))
-    dist.allreduce_sum(ll)
-    dist.allreduce_sum(llp)
+    dist.combine(ctx, ll)
+    dist.combine(ctx, llp)
     af[...] = af_work                                   # in-place side effect (glassy.py:89)
     return ll.astype(np.float32), llp.astype(np.float32)
 
@@ -46,6 +46,6 @@ def loo_fused(ctx, IDs, maf_iter, maf_tole, downsampled=False, num_partitions=1)
     logl_mat, logl_parts_mat float32, loo iterations [N]); the caller prints the messages in the
     reference's order."""
     af, its, ll, llp, lits, _ = ctx.ref_af_loo(maf_iter, maf_tole, use_ds=downsampled, parts=num_partitions)
-    dist.allreduce_sum(ll)
-    dist.allreduce_sum(llp)
+    dist.combine(ctx, ll)
+    dist.combine(ctx, llp)
     return af, its, ll.astype(np.float32), llp.astype(np.float32), lits

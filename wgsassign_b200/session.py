@@ -3,8 +3,15 @@
 The reference's drivers take the GL matrix as a NumPy array on every call.  Re-uploading
 it for each of `--get_reference_af`, `--ne_obs` and `--loo` would triple the PCIe traffic,
 so the entry points ask this module for a :class:`~wgsassign_b200._lib.Context` that
-already holds the matrix; it is re-uploaded only when the array (address, shape, sampled
-checksum) or the population assignment changes.
+already holds the matrix; it is re-uploaded only when the array or the population
+assignment changes.
+
+How "the array changed" is decided (`_sig`): address, shape, dtype and a checksum of the
+contents - over EVERY byte for arrays up to `FULL_CHECK_BYTES` (64 MB: a few milliseconds)
+and always when `strict(True)` is set; above that a 65,536-element strided sample plus the
+first and last 4 KB, because a full pass over a 4 GB matrix costs several uploads.  A caller
+that edits a large matrix in place between two entry-point calls must therefore call
+`invalidate()` (or run with `strict(True)`); the CLI never does that.
 """
 import os
 
@@ -14,6 +21,29 @@ from . import _lib
 from . import dist
 
 _state = {"ctx": None, "key": None, "ds_key": None, "ad_key": None}
+_options = {}                     # library switches applied to every context this module creates (set_option)
+FULL_CHECK_BYTES = 64 << 20
+_strict = [bool(os.environ.get("WGS_SESSION_STRICT"))]
+
+
+def strict(on=True):
+    """Full-content checksum for every array, whatever its size (debug mode)."""
+    _strict[0] = bool(on)
+
+
+def invalidate():
+    """Forget what is resident: the next entry-point call re-uploads its arrays.  Call this after
+    modifying a matrix in place."""
+    _state.update(key=None, ds_key=None, ad_key=None)
+    from . import fisher
+    fisher._last.update(key=None, ne_ind=None)
+
+
+def set_option(name, value):
+    """Library switch (`Context.set_option`) for the cached context and every later one."""
+    _options[name] = int(value)
+    if _state["ctx"] is not None:
+        _state["ctx"].set_option(name, value)
 
 
 def device_index():
@@ -21,11 +51,22 @@ def device_index():
 
 
 def _sig(a):
-    """Cheap identity of an array's contents: address, shape and a strided sample."""
+    """Identity of an array's contents: address, shape, dtype and a checksum (see the module docstring)."""
+    a = np.asarray(a)
+    head = (a.ctypes.data, a.shape, a.dtype.str)
+    if not a.flags.c_contiguous or a.nbytes == 0:
+        return head + (float(np.sum(a, dtype=np.float64)),)
+    raw = a.reshape(-1).view(np.uint8)
+    if _strict[0] or a.nbytes <= FULL_CHECK_BYTES:
+        n8 = raw.shape[0] // 8 * 8
+        words = raw[:n8].view(np.uint64)
+        # order-sensitive: a weighted sum (index mod 2^16 + 1) catches swapped elements as well as changed ones
+        w = (np.arange(words.shape[0], dtype=np.uint64) & np.uint64(0xFFFF)) + np.uint64(1)
+        return head + (int(np.sum(words * w, dtype=np.uint64)), int(np.sum(raw[n8:], dtype=np.uint64)))
     flat = a.reshape(-1)
-    step = max(1, flat.shape[0] // 4096)
-    sample = flat[::step]
-    return (a.ctypes.data, a.shape, a.dtype.str, float(np.sum(sample, dtype=np.float64)))
+    step = max(1, flat.shape[0] // 65536)
+    return head + (float(np.sum(flat[::step], dtype=np.float64)), int(np.sum(raw[:4096], dtype=np.uint64)),
+                   int(np.sum(raw[-4096:], dtype=np.uint64)))
 
 
 def pops_from_ids(IDs):
@@ -45,6 +86,8 @@ def context(L, pop_of_ind=None, K=0, async_upload=False):
         return ctx
     if ctx is None:
         ctx = _lib.Context(device_index())
+        for name, value in _options.items():
+            ctx.set_option(name, value)
         _state["ctx"] = ctx
     n = L.shape[1] // 2
     _state.update(key=None, ds_key=None, ad_key=None)      # nothing is trusted until the upload has succeeded
