@@ -366,6 +366,24 @@ def test_fallback_kernels_agree(wgs, monkeypatch):
     ctx.close()
 
 
+def test_loo_population_by_population_is_bitwise_identical(wgs):
+    """One packed-row buffer, populations one after the other (what a shard too large for all packed rows at once
+    runs): the same updates and decisions, hence the same bits, as all populations per iteration."""
+    from wgsassign_b200 import synth
+    d = synth.synth(3100, 52, 4, seed=47, with_ad=False)
+    pop_of, pops = wgs.session.pops_from_ids(d["IDs"])
+    ctx = wgs.lib.Context(0)
+    ctx.set_pops(pop_of, len(pops))
+    ctx.upload_gl(d["L"])
+    af, _ = ctx.ref_af(200, 1e-4)
+    a0, a1 = af.copy(), af.copy()
+    ll0, _, its0 = ctx.loo_partial(a0, 200, 1e-4)
+    ctx.set_option("loo_by_pop", 1)
+    ll1, _, its1 = ctx.loo_partial(a1, 200, 1e-4)
+    assert list(its0) == list(its1) and np.array_equal(a0, a1) and np.array_equal(ll0, ll1)
+    ctx.close()
+
+
 def test_loo_like_block_shapes_agree(wgs, monkeypatch):
     """The three launch shapes of the staged leave-one-out likelihood kernel (two small blocks per SM, big blocks of up
     to 18 warps, the gather-through-L1 fallback) on a panel wide enough (22 warps of individuals) to split big blocks."""

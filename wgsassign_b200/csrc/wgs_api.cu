@@ -654,6 +654,77 @@ int launch_loo_like2(wgs_ctx* ctx, int KT, const float2* G, long M, const float*
     }
 }
 
+// ---- leave-one-out likelihoods of a run-ordered panel (loo_like3) -----------------------------------------
+struct LooLike3Plan {
+    int KT = 0, KP = 0, R = 0, r_own = 1, wx = 1, gx = 1;
+    Like2Cfg c2{};
+    std::vector<int> slot_of_col, pop_of_slot, lastcol_of_slot;
+};
+// populations in contiguous runs of the ID file, at least two members each, K <= 20, and every frequency the kernel
+// can read far enough from 0 and 1 for the ratio form (margin): else the general kernels take the call
+bool plan_loo_like3(wgs_ctx* ctx, long M, float margin, int r_own, LooLike3Plan* p)
+{
+    const int K = ctx->K, N = ctx->N, ldg = ctx->ldg;
+    if (K < 2 || K > 20 || opt(ctx, "loolike_v1") || opt(ctx, "loolike_v2")) return false;
+    std::vector<int> slot_of_pop(K, -1), last_ind(K, -1);
+    int nslots = 0;
+    for (int i = 0; i < N; ++i) {
+        const int k = ctx->pop_of_ind[i];
+        if (slot_of_pop[k] < 0) slot_of_pop[k] = nslots++;
+        else if (ctx->pop_of_ind[i - 1] != k) return false;       // population k resumes after another one: not run-ordered
+        last_ind[k] = i;
+    }
+    if (nslots != K) return false;
+    for (int k = 0; k < K; ++k) if (ctx->pops[k].n < 2) return false;
+    p->R = pick_R2(margin);
+    if (p->R == 0) return false;
+    p->r_own = std::max(1, r_own);
+    p->KT = pick_KT2(K); p->KP = (p->KT + 1) / 2;
+    p->pop_of_slot.assign(K, 0); p->lastcol_of_slot.assign(K, 0);
+    for (int k = 0; k < K; ++k) { p->pop_of_slot[slot_of_pop[k]] = k; p->lastcol_of_slot[slot_of_pop[k]] = ctx->col_of_ind[last_ind[k]]; }
+    p->slot_of_col.assign(ldg, 0);
+    for (int c = 0; c < ldg; ++c) p->slot_of_col[c] = slot_of_pop[ctx->pop_of_col[c]];
+    const int groups = (ldg + 63) / 64;                           // 64 columns per warp (two adjacent columns per thread)
+    const int wmax = p->KT > 10 ? 2 : 4;                          // 20 KB of coefficient tiles per warp at KT = 20
+    int best_waste = 1 << 30;
+    for (int w = 1; w <= wmax; ++w) {
+        const int waste = (groups + w - 1) / w * w - groups;
+        if (waste <= best_waste) { best_waste = waste; p->wx = w; }
+    }
+    p->gx = (groups + p->wx - 1) / p->wx;
+    p->c2 = like2_cfg(ctx, M, p->R);
+    return true;
+}
+template <int KT, int R>
+int launch_loo_like3_t(wgs_ctx* ctx, const LooLike3Plan& p, const float2* G, long M, const float* F, int ldf, const float* clo, const float* chi,
+                       const ulonglong2* XY, const int* d_slot_of_col, const int* d_pop_of_slot, long pm, long pr, double* partials)
+{
+    constexpr int KP = (KT + 1) / 2;
+    const size_t smem = (size_t)p.wx * 2 * kPL2TS * 2 * KP * sizeof(ulonglong2);
+    auto kern = loo_like3_kernel<KT, R>;
+    if (smem > 40 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    LAUNCH("loo_like", kern, dim3(p.gx, p.c2.gy), p.wx * 32, smem, ctx->stream, G, ctx->ldg, M, F, ldf, clo, chi, XY, d_slot_of_col,
+           d_pop_of_slot, ctx->K, p.c2.spb, pm, pr, ctx->site_offset, p.r_own, partials);
+    // GL pairs once + the leave-one-out state (one float per individual) + the 2K shared frequencies of the site
+    add_work(ctx, "loo_like", (double)M * ctx->N * 12.0 + (double)M * ctx->K * 8.0, (double)M * ctx->N * ctx->K);
+    return 0;
+}
+int launch_loo_like3(wgs_ctx* ctx, const LooLike3Plan& p, const float2* G, long M, const float* F, int ldf, const float* clo, const float* chi,
+                     const ulonglong2* XY, const int* dsc, const int* dps, long pm, long pr, double* partials)
+{
+#define LL3(KTV)                                                                                                               \
+    return p.R == 16 ? launch_loo_like3_t<KTV, 16>(ctx, p, G, M, F, ldf, clo, chi, XY, dsc, dps, pm, pr, partials)             \
+                     : launch_loo_like3_t<KTV, 8>(ctx, p, G, M, F, ldf, clo, chi, XY, dsc, dps, pm, pr, partials)
+    switch (p.KT) {
+        case 4: LL3(4);
+        case 8: LL3(8);
+        case 10: LL3(10);
+        case 16: LL3(16);
+        default: LL3(20);
+    }
+#undef LL3
+}
+
 #define DISPATCH_R(FN, KTV, R, ...)                                      \
     switch (R) {                                                         \
         case 8: rc_ = FN<KTV, 8>(__VA_ARGS__); break;                    \
@@ -1210,22 +1281,56 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     }
     // pre-packed pair polynomials (loo_em_step5): 80 bytes per 8 individuals and site, written once per call;
     // when the pool cannot provide them (or WGS_LOO_V4 is set) the in-kernel packing quad kernel runs instead
+    // by_pop: ONE packed-row buffer, the populations run one after the other (pre-pack k, all iterations of k, then
+    // k+1) - what the pipelined mode does anyway, and what a matrix too large for all packed rows at once (a 2.5 M
+    // x 2,000 shard would need 92 GB of them) falls back to before giving up the packed kernel.  Every problem sees
+    // the same updates and decisions either way.
     std::vector<DevBuf> pk(K);
     const int loo_dbg = opt(ctx, "loo_dbg", 0);
     bool packed = !opt(ctx, "loo_v4");
-    for (int k = 0; k < K && packed; ++k) {
-        if (ctx->pops[k].n <= 1) continue;
-        pk[k].owner = ctx;
-        pk[k].p = pool_take(ctx, (size_t)std::max<long>(M, 1) * loo5_row_units(ctx->pops[k].n) * sizeof(ulonglong2));
-        if (!pk[k].p) packed = false;
+    bool by_pop = pop_ready != nullptr;
+    if (packed) {
+        size_t total_pk = 0, max_pk = 0, cached = 0, freeb = 0, totalb = 0;
+        for (int k = 0; k < K; ++k) {
+            if (ctx->pops[k].n <= 1) continue;
+            const size_t b = (size_t)std::max<long>(M, 1) * loo5_row_units(ctx->pops[k].n) * sizeof(ulonglong2);
+            total_pk += b; max_pk = std::max(max_pk, b);
+        }
+        for (auto& kv : ctx->pool_free) cached += kv.first;
+        cudaMemGetInfo(&freeb, &totalb);
+        const size_t d2b = opt(ctx, "rmse_exact", 1) ? (size_t)std::max<long>(M, 1) * ldg * sizeof(float) : 0;
+        const size_t avail = freeb + cached, slack = (size_t)2 << 30;
+        const int o = opt(ctx, "loo_by_pop", 0);
+        if (!pop_ready && o >= 0 && (o > 0 || total_pk + d2b + slack > avail)) by_pop = true;
+        if (by_pop && !pop_ready) {
+            pk[0].owner = ctx;
+            pk[0].p = pool_take(ctx, std::max<size_t>(max_pk, 16));
+            if (!pk[0].p) packed = false;
+        } else if (!by_pop) {
+            for (int k = 0; k < K && packed; ++k) {
+                if (ctx->pops[k].n <= 1) continue;
+                pk[k].owner = ctx;
+                pk[k].p = pool_take(ctx, (size_t)std::max<long>(M, 1) * loo5_row_units(ctx->pops[k].n) * sizeof(ulonglong2));
+                if (!pk[k].p) packed = false;
+            }
+        } else {                                                  // pipelined upload: all buffers (the populations overlap the transfer)
+            for (int k = 0; k < K && packed; ++k) {
+                if (ctx->pops[k].n <= 1) continue;
+                pk[k].owner = ctx;
+                pk[k].p = pool_take(ctx, (size_t)std::max<long>(M, 1) * loo5_row_units(ctx->pops[k].n) * sizeof(ulonglong2));
+                if (!pk[k].p) packed = false;
+            }
+        }
+        if (!packed) for (int k = 0; k < K; ++k) buf_release(pk[k]);
     }
-    if (!packed) for (int k = 0; k < K; ++k) buf_release(pk[k]);
+    const bool shared_pk = packed && by_pop && !pop_ready;       // every population uses pk[0]
+    auto pk_of = [&](int k) { return (shared_pk ? pk[0] : pk[k]).as<ulonglong2>(); };
     for (int k = 0; k < K; ++k) {
         if (ctx->pops[k].n <= 1) continue;
         if (loo_cfg(ctx, ctx->pops[k].n, packed, &cfgs[k])) return 1;
         nblocks = std::max(nblocks, cfgs[k].grid);
-        if (packed && !pop_ready) {
-            if (launch_prepack(k, pk[k].as<ulonglong2>())) return 1;
+        if (packed && !by_pop) {
+            if (launch_prepack(k, pk_of(k))) return 1;
         }
     }
     EmState st;
@@ -1265,13 +1370,13 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         long ntiles = (M + TS - 1) / TS;
         if (lc.packed) {
             if (lc.big)
-                LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
+                LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
                        pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
             else if (!opt(ctx, "loo_occ3"))
-                LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
+                LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
                        pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
             else
-                LAUNCH("loo_em", (loo_em_step5_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, pk[k].as<ulonglong2>(), ldg, M,
+                LAUNCH("loo_em", (loo_em_step5_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
                        pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
         } else {
             if (lc.big)
@@ -1326,15 +1431,15 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     // squared changes pass through the host for the all-reduce anyway.
     const bool ahead = (ctx->fn == nullptr || ctx->nccl_comm != nullptr) && !opt(ctx, "em_no_lookahead");
     const double count_all = (double)ctx->Mtot();
-    if (pop_ready) {
+    if (by_pop) {
         for (int ko = 0; ko < K; ++ko) {
-            const int k = (int)ctx->upload_order.size() == K ? ctx->upload_order[ko] : ko;   // the order the slabs arrive in
+            const int k = (pop_ready && (int)ctx->upload_order.size() == K) ? ctx->upload_order[ko] : ko;   // the order the slabs arrive in
             PopDesc pd = ctx->pops[k];
-            CU(cudaStreamWaitEvent(ctx->stream, (*pop_ready)[k], 0));       // device-side: the host keeps queueing
+            if (pop_ready) CU(cudaStreamWaitEvent(ctx->stream, (*pop_ready)[k], 0));   // device-side: the host keeps queueing
             if (on_pop && (*on_pop)(k)) return 1;                           // the fused operator's full-data EM of this population
             if (pd.n <= 1) continue;
             if (packed) {
-                if (launch_prepack(k, pk[k].as<ulonglong2>())) return 1;
+                if (launch_prepack(k, pk_of(k))) return 1;
             }
             if (!pop_active(k) || iter < 1) continue;
             if (launch_iter(k, 1) || em_after_step_queue(ctx, st, tole, 1, d_count, count_all, 1, pd.col0, pd.n)) return 1;
@@ -1880,7 +1985,7 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
     std::vector<float> lo, hi;
     clip_bounds(ctx, 1, lo, hi);
     LooLike2Cfg c2{};
-    const bool staged = !opt(ctx, "loolike_v1") && loo_like2_cfg(ctx, M, ldf, K, &c2);
+    const bool staged = !opt(ctx, "loolike_v1") && loo_like2_cfg(ctx, M, ldf, K, &c2);   // staged also means: clamp on the way, F not rewritten
     lo.resize(ldf, 0.0f); hi.resize(ldf, 1.0f);                  // full-data AF and pad columns: already inside [0, 1]
     DevBuf dlo, dhi;
     if (buf_alloc(ctx, dlo, ldf * sizeof(float)) || buf_alloc(ctx, dhi, ldf * sizeof(float))) return 1;
@@ -1903,16 +2008,37 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
     CU(cudaMemcpyAsync(drc.p, rc.data(), rc.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 
     int R = 1;
+    float margin_all = 0.5f;
     {   // margin over everything the likelihood can read: clipped LOO columns and the full-data AF
         int Ra = 1;
-        if (af_R(ctx, dA.as<float>(), M * K, &Ra)) return 1;
+        float ma = 0.f;
+        if (af_R(ctx, dA.as<float>(), M * K, &Ra, &ma)) return 1;
         float mlo = 0.5f;
         for (int c = 0; c < ldg; ++c) if (ctx->ind_of_col[c] >= 0) mlo = std::min(mlo, lo[c]);
         R = std::min(Ra, pick_R(mlo));
         for (int k = 0; k < K; ++k) if (ctx->pops[k].n <= 1) R = 1;
+        margin_all = std::min(ma, mlo);
+    }
+    // run-ordered panels: 2K shared frequencies per site + each individual's own state value (loo_like3)
+    LooLike3Plan p3;
+    const bool v3 = staged && plan_loo_like3(ctx, M, margin_all, R, &p3);
+    DevBuf dA2, dXY2, dsc, dps, dlc, dper, dC;
+    if (v3) {
+        const int W2 = 4 * p3.KP;
+        const long Mpad = (std::max<long>(M, 1) + kPL2TS - 1) / kPL2TS * kPL2TS;
+        if (buf_alloc(ctx, dA2, (size_t)std::max<long>(M, 1) * W2 * sizeof(float)) || buf_alloc(ctx, dXY2, (size_t)Mpad * 2 * p3.KP * sizeof(ulonglong2)) ||
+            buf_alloc(ctx, dsc, ldg * sizeof(int)) || buf_alloc(ctx, dps, K * sizeof(int)) || buf_alloc(ctx, dlc, K * sizeof(int)) ||
+            buf_alloc(ctx, dper, (size_t)ctx->num_sm * 4 * W2 * sizeof(double)) || buf_alloc(ctx, dC, (size_t)W2 * sizeof(double))) return 1;
+        CU(cudaMemcpyAsync(dsc.p, p3.slot_of_col.data(), ldg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dps.p, p3.pop_of_slot.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dlc.p, p3.lastcol_of_slot.data(), K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH("loo_like_aux", loo_shared_af_kernel, grid_for(M * W2, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F.as<float>(), ldf, ldg, M, K, p3.KP,
+               dlc.as<int>(), dps.as<int>(), dlo.as<float>(), dhi.as<float>(), dA2.as<float>());
+        LAUNCH("loo_like_aux", xy_precompute_kernel, grid_for(M * 2 * p3.KP, 256, ctx->num_sm * 8), 256, 0, ctx->stream, dA2.as<float>(), M, W2, 0,
+               2 * p3.KP, dXY2.as<ulonglong2>());
     }
     LikeCfg c = like_cfg(ctx, M, 3);
-    const int n_split = staged ? c2.gy : c.gy;
+    const int n_split = v3 ? p3.c2.gy : (staged ? c2.gy : c.gy);
     size_t np = (size_t)ldg * K;
     DevBuf partials, sums;
     if (buf_alloc(ctx, partials, (size_t)n_split * np * sizeof(double)) || buf_alloc(ctx, sums, np * sizeof(double))) return 1;
@@ -1920,7 +2046,20 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
     std::vector<double> tmp((size_t)N * K);
     for (int pass = 0; pass < (parts > 1 ? parts + 1 : 1); ++pass) {
         long pm = pass == 0 ? 1 : parts, pr = pass == 0 ? 0 : pass - 1;
-        for (int k0 = 0; k0 < K;) {
+        if (v3) {
+            if (launch_loo_like3(ctx, p3, Gsrc, M, F.as<float>(), ldf, dlo.as<float>(), dhi.as<float>(), dXY2.as<ulonglong2>(), dsc.as<int>(),
+                                 dps.as<int>(), pm, pr, partials.as<double>())) return 1;
+            LAUNCH("reduce", reduce_partials_kernel, grid_for(np, 256, ctx->num_sm * 4), 256, 0, ctx->stream, partials.as<double>(),
+                   n_split, (long)np, sums.as<double>());
+            // + the population-only term log(2a(1-a)) of the ratio form, summed over this pass's sites per shared frequency
+            const int W2 = 4 * p3.KP, block = W2 * (256 / W2), grid = ctx->num_sm * 4;
+            LAUNCH("loo_like_aux", af_logsum_kernel, grid, block, block * sizeof(double), ctx->stream, dA2.as<float>(), M * W2, W2, dper.as<double>(),
+                   pm, pr, ctx->site_offset);
+            LAUNCH("loo_like_aux", af_logsum_reduce_kernel, (W2 + 127) / 128, 128, 0, ctx->stream, dper.as<double>(), grid, W2, dC.as<double>());
+            LAUNCH("loo_like_aux", add_loo_const_kernel, grid_for(np, 256, ctx->num_sm * 4), 256, 0, ctx->stream, sums.as<double>(), ldg, K, p3.KP,
+                   dsc.as<int>(), dps.as<int>(), dC.as<double>());
+        }
+        for (int k0 = 0; k0 < K && !v3;) {
             int KT = staged ? loo_like2_KT(c2, K - k0) : pick_KT(K - k0);
             int rc_ = 0;
             if (staged) rc_ = launch_loo_like2(ctx, KT, Gsrc, M, F.as<float>(), ldf, dlo.as<float>(), dhi.as<float>(), drc.as<int>(), K, k0, c2, pm, pr, R,
@@ -1929,8 +2068,9 @@ static int loo_impl(wgs_ctx* ctx, float* af_inout, int32_t iter, double tole, in
             if (rc_) return rc_;
             k0 += KT;
         }
-        LAUNCH("reduce", reduce_partials_kernel, grid_for(np, 256, ctx->num_sm * 4), 256, 0, ctx->stream, partials.as<double>(),
-               n_split, (long)np, sums.as<double>());
+        if (!v3)
+            LAUNCH("reduce", reduce_partials_kernel, grid_for(np, 256, ctx->num_sm * 4), 256, 0, ctx->stream, partials.as<double>(),
+                   n_split, (long)np, sums.as<double>());
         if (pass == 0) { if (cols_to_host(ctx, sums.as<double>(), K, ll)) return 1; }
         else {
             if (!ll_parts) return fail(ctx, "ll_parts is NULL but parts > 1");

@@ -744,7 +744,8 @@ pop_like2_kernel(const float2* __restrict__ G, int ldg, long M,
 // T = total threads, a multiple of K (blockDim is): every element a thread visits (e = t, t+T, ...) belongs to
 // population t % K.  Block and grid sums are taken in a fixed order (af_logsum_reduce_kernel): deterministic.
 // (The population-only term of the ratio form above.)
-__global__ void af_logsum_kernel(const float* __restrict__ A, long n, int K, double* __restrict__ per_block)
+__global__ void af_logsum_kernel(const float* __restrict__ A, long n, int K, double* __restrict__ per_block,
+                                 long part_mod = 1, long part_rem = 0, long site_offset = 0)   // only sites with (site_offset + s) % part_mod == part_rem
 {
     extern __shared__ double af_red[];                   // [blockDim.x]
     const long T = (long)gridDim.x * blockDim.x, t = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -752,6 +753,7 @@ __global__ void af_logsum_kernel(const float* __restrict__ A, long n, int K, dou
     acc.init();
     int cnt = 0;
     for (long e = t; e < n; e += T) {
+        if (part_mod > 1 && (site_offset + e / K) % part_mod != part_rem) continue;
         const float a = __ldg(&A[e]);
         acc.prod[0] *= (a + a) * (1.0f - a);
         if (++cnt == 2) { acc.renorm(); cnt = 0; }        // two factors >= 2^-29 each stay far above underflow
@@ -1024,6 +1026,183 @@ loo_like2_kernel(const float2* __restrict__ G, int ldg, long M,
 #pragma unroll
         for (int kk = 0; kk < KT; ++kk)
             if (k0 + kk < K) partials[((long)blockIdx.y * ldg + col) * K + k0 + kk] = acc.value(kk);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// loo_like3: the leave-one-out likelihoods for reference panels whose populations are CONTIGUOUS runs of the ID
+// file (the usual layout; anything else takes loo_like2).  The reference overwrites af[:, pop(i)] with individual
+// i's leave-one-out estimate and never restores it (glassy.py:89), so for a run-ordered panel the column that
+// individual i of population p reads for population j is
+//     j == p            : i's own leave-one-out estimate,
+//     run(j) before p   : the estimate of the LAST member of j (the file has passed all of j),
+//     run(j) after p    : the caller's full-data frequency of j (nobody of j has been seen yet).
+// Per site that is 2K shared values and one private value per individual - not an ldf-wide gather table.  The 2K
+// shared values are turned once per call into ratio-form coefficient pairs XY2[s][{last, full}][pair] (the
+// pop_like2 scheme, slots in RUN order, their log(2a(1-a)) sums added afterwards per individual), staged per warp
+// with LDGSTS into a private double buffer; a lane picks `last` or `full` per pair with a per-thread offset (two
+// distinct shared-memory addresses per warp at most).  The own term is the direct form on the individual's own
+// clipped state value, read coalesced next to the GL pair, with its own running product.
+// No block-wide barrier; 12 bytes per (site, individual) from HBM + 32 KP bytes per site.
+// partials[split][col][K] in POPULATION order (slot -> pop_of_slot); the own slot carries the own-term sum.
+// ---------------------------------------------------------------------------------------
+template <int KT, int R, bool FULL>
+__device__ __forceinline__ void loo_like3_tile(const float4* Gp, const float2* Fp, int ldg2, int ldf2,
+                                               float lo0, float hi0, float lo1, float hi1, long s0, long s_end,
+                                               long part_mod, long part_rem, long site_offset, int r_own,
+                                               const ulonglong2* __restrict__ XY, const int (&qoff)[(KT + 1) / 2],
+                                               LikeAccP<KT> (&acc)[2], LikeAcc<1> (&own)[2], int& cnt, int& cnt_own)
+{
+    constexpr int KP = (KT + 1) / 2;
+    constexpr int PF = KT > 10 ? 4 : 8;                   // sites prefetched per thread (registers)
+#pragma unroll 1
+    for (int c0 = 0; c0 < kPL2TS; c0 += PF) {
+        float4 g[PF];
+        float2 fo[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const long s = s0 + c0 + u;
+            if (FULL || s < s_end) { g[u] = ld_stream4(Gp + s * (long)ldg2); fo[u] = __ldg(Fp + s * (long)ldf2); }
+            else { g[u] = make_float4(1.0f, 0.0f, 1.0f, 0.0f); fo[u] = make_float2(0.5f, 0.5f); }
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int sl = c0 + u;
+            bool use = FULL || s0 + sl < s_end;           // warp-uniform
+            if (part_mod > 1) use = use && ((site_offset + s0 + sl) % part_mod == part_rem);
+            if (use) {
+                const float ta = third_gl(g[u].x, g[u].y), tb = third_gl(g[u].z, g[u].w);
+                const f32x2 g0a = pack2(g[u].x, g[u].x), g1a = pack2(g[u].y, g[u].y), g2a = pack2(ta, ta);
+                const f32x2 g0b = pack2(g[u].z, g[u].z), g1b = pack2(g[u].w, g[u].w), g2b = pack2(tb, tb);
+                {   // own terms (direct form): the clipping of glassy.py:80-85 happens here, NaN survives it
+                    const float a = fmin_nan(fmax_nan(fo[u].x, lo0), hi0), oa = 1.0f - a;
+                    const float b = fmin_nan(fmax_nan(fo[u].y, lo1), hi1), ob = 1.0f - b;
+                    own[0].prod[0] *= fmaf(g[u].x, oa * oa, fmaf(g[u].y, (a + a) * oa, ta * (a * a)));
+                    own[1].prod[0] *= fmaf(g[u].z, ob * ob, fmaf(g[u].w, (b + b) * ob, tb * (b * b)));
+                }
+#pragma unroll
+                for (int q = 0; q < KP; ++q) {
+                    const ulonglong2 xy = XY[sl * (2 * KP) + qoff[q]];
+                    acc[0].prod[q] = fmul2(acc[0].prod[q], ffma2(g2a, xy.y, ffma2(g0a, xy.x, g1a)));
+                    acc[1].prod[q] = fmul2(acc[1].prod[q], ffma2(g2b, xy.y, ffma2(g0b, xy.x, g1b)));
+                }
+                if (++cnt == R) { cnt = 0; acc[0].renorm(); acc[1].renorm(); }
+                if (++cnt_own == r_own) { cnt_own = 0; own[0].renorm(); own[1].renorm(); }
+            }
+        }
+    }
+}
+
+// Thread = TWO ADJACENT columns (2 lane, 2 lane + 1 of the warp's 64): slabs are padded to 4 columns, so the two always
+// belong to the same population and share every coefficient load; their GL pairs are one 16-byte load, their state
+// values one 8-byte load.
+template <int KT, int R>
+__global__ void __launch_bounds__(128, 4)
+loo_like3_kernel(const float2* __restrict__ G, int ldg, long M,
+                 const float* __restrict__ F, int ldf,          // leave-one-out state: column c = the estimate without individual c
+                 const float* __restrict__ clip_lo, const float* __restrict__ clip_hi,   // [ldf]
+                 const ulonglong2* __restrict__ XYg,            // [M rounded up to kPL2TS][2 KP]: {last pairs | full pairs}, slots in run order
+                 const int* __restrict__ slot_of_col,           // [ldg] run-order slot of the column's population
+                 const int* __restrict__ pop_of_slot,           // [K]
+                 int K, long sites_per_block,                   // multiple of kPL2TS, <= 256 R
+                 long part_mod, long part_rem, long site_offset, int r_own,
+                 double* __restrict__ partials)
+{
+    constexpr int KP = (KT + 1) / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ulonglong2* XY = reinterpret_cast<ulonglong2*>(smem_raw) + (size_t)warp * 2 * kPL2TS * 2 * KP;   // [2][TS][2 KP], this warp's
+
+    const int wx = blockDim.x >> 5;
+    const int wcol = (blockIdx.x * wx + warp) * 64;
+    if (wcol >= ldg) return;                              // warp-uniform: nothing to do (no barriers below)
+    const int col = wcol + 2 * lane;
+    const bool col_ok = col < ldg;                        // ldg is a multiple of 4: col + 1 < ldg as well
+    const int cc = col_ok ? col : ldg - 2;                // out-of-range lanes read a valid pair and are never stored
+    const float4* Gp = reinterpret_cast<const float4*>(G + cc);
+    const float2* Fp = reinterpret_cast<const float2*>(F + cc);
+    const float lo0 = clip_lo[cc], hi0 = clip_hi[cc], lo1 = clip_lo[cc + 1], hi1 = clip_hi[cc + 1];
+    const int slot = slot_of_col[cc];
+    // pair q (slots 2q, 2q+1) comes from the `last` set when its slots lie at or before the own slot (the own slot's
+    // value is never used), else from the `full` set
+    int qoff[KP];
+#pragma unroll
+    for (int q = 0; q < KP; ++q) qoff[q] = (2 * q + 1 <= slot) ? q : KP + q;
+    const long s_begin = (long)blockIdx.y * sites_per_block;
+    const long s_end = min(M, s_begin + sites_per_block);
+
+    LikeAccP<KT> acc[2];
+    LikeAcc<1> own[2];
+    acc[0].init(); acc[1].init(); own[0].init(); own[1].init();
+    int cnt = 0, cnt_own = 0;
+
+    auto stage = [&](long s0, int buf) {                  // 32 rows of 2 KP 16-byte cells: contiguous in XYg
+        const ulonglong2* src = XYg + s0 * (2 * KP);
+        ulonglong2* dst = XY + buf * (kPL2TS * 2 * KP);
+#pragma unroll
+        for (int j = 0; j < 2 * KP; ++j) cp_async16(dst + lane + 32 * j, src + lane + 32 * j);
+        cp_async_commit();
+    };
+    if (s_begin < s_end) stage(s_begin, 0);
+    int buf = 0;
+    for (long s0 = s_begin; s0 < s_end; s0 += kPL2TS, buf ^= 1) {
+        if (s0 + kPL2TS < s_end) { stage(s0 + kPL2TS, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();
+        const ulonglong2* tile = XY + buf * (kPL2TS * 2 * KP);
+        if (s0 + kPL2TS <= s_end)
+            loo_like3_tile<KT, R, true>(Gp, Fp, ldg >> 1, ldf >> 1, lo0, hi0, lo1, hi1, s0, s_end, part_mod, part_rem, site_offset, r_own, tile, qoff, acc, own, cnt, cnt_own);
+        else
+            loo_like3_tile<KT, R, false>(Gp, Fp, ldg >> 1, ldf >> 1, lo0, hi0, lo1, hi1, s0, s_end, part_mod, part_rem, site_offset, r_own, tile, qoff, acc, own, cnt, cnt_own);
+        __syncwarp();                                     // everyone is done with `buf` before it is refilled
+    }
+    acc[0].renorm(); acc[1].renorm(); own[0].renorm(); own[1].renorm();   // brings every slot to a known state
+    if (col_ok) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double* out = partials + ((long)blockIdx.y * ldg + col + i) * K;
+#pragma unroll
+            for (int kk = 0; kk < KT; ++kk)
+                if (kk < K) out[pop_of_slot[kk]] = (kk == slot) ? own[i].value(0) : acc[i].value(kk);
+        }
+    }
+}
+
+// sums[col][pop_of_slot[kk]] += C[(kk before the column's own slot ? last : full)][kk] for kk != own slot: the
+// population-only log(2a(1-a)) sums of the ratio form; C = [2 KP | 2 KP] doubles (last set, full set), run-order slots
+__global__ void add_loo_const_kernel(double* __restrict__ sums, int ldg, int K, int KP, const int* __restrict__ slot_of_col,
+                                     const int* __restrict__ pop_of_slot, const double* __restrict__ C)
+{
+    const long total = (long)ldg * K;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int col = (int)(e / K), kk = (int)(e - (long)col * K);
+        const int own = slot_of_col[col];
+        if (kk == own) continue;
+        const int q = kk >> 1;
+        sums[(long)col * K + pop_of_slot[kk]] += (2 * q + 1 <= own) ? C[kk] : C[2 * KP + kk];
+    }
+}
+
+// A2[s][{last set: 2 KP | full set: 2 KP}] in run-order slots: the clipped leave-one-out estimate of each population's
+// LAST member and the caller's full-data frequency; slots past K are 0.5 (a harmless dummy)
+__global__ void loo_shared_af_kernel(const float* __restrict__ F, int ldf, int ldg, long M, int K, int KP,
+                                     const int* __restrict__ lastcol_of_slot, const int* __restrict__ pop_of_slot,
+                                     const float* __restrict__ clip_lo, const float* __restrict__ clip_hi, float* __restrict__ A2)
+{
+    const int W = 4 * KP;
+    const long total = M * W;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long s = e / W;
+        const int j = (int)(e - s * W);
+        const int set = j >= 2 * KP, kk = set ? j - 2 * KP : j;
+        float a = 0.5f;
+        if (kk < K) {
+            if (!set) {
+                const int c = lastcol_of_slot[kk];
+                a = fmin_nan(fmax_nan(F[s * (long)ldf + c], clip_lo[c]), clip_hi[c]);
+            } else a = F[s * (long)ldf + ldg + pop_of_slot[kk]];
+        }
+        A2[e] = a;
     }
 }
 
