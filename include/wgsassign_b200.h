@@ -232,7 +232,7 @@ int32_t wgs_debug_stream(wgs_ctx *ctx, int32_t mode, double *ms_out, double *byt
 
 /* Diagnostic: the device's order-exact float32 summation (the primitive behind the EM stop rule, rmse1d of
  * emMAF_cy.pyx:26-33): *out = ((carry_in + x[0]) + x[1]) + ... in float32, computed with the blocked integer
- * scheme of warp_seqsum32 (csrc/wgs_kernels.cuh).  Tests compare it bit for bit with a serial loop. */
+ * scheme of block_seqsum32 (csrc/wgs_kernels.cuh).  Tests compare it bit for bit with a serial loop. */
 int32_t wgs_debug_seqsum(wgs_ctx *ctx, const float *x, int64_t n, float carry_in, float *out);
 
 /* ---- instrumentation --------------------------------------------------------------------- */

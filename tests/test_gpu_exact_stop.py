@@ -1,7 +1,7 @@
 """The EM stop rule at scale: the reference adds the squared changes of all sites into ONE float32 accumulator,
 left to right (rmse1d, emMAF_cy.pyx:26-33).  At millions of sites that sum is biased against the exact one (-0.4 %
 at 5 M sites), enough to move the stop iteration, so checks that land inside the band where the exact
-FP64 sum cannot decide are resolved on the device with an order-exact emulation of that loop (warp_seqsum32).
+FP64 sum cannot decide are resolved on the device with an order-exact emulation of that loop (block_seqsum32).
 
   * the primitive against a serial float32 loop, bit for bit, on adversarial vectors;
   * `--get_reference_af` + `--loo` on 6 M device-generated sites against the oracle run on the downloaded matrix:

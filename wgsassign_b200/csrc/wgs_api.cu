@@ -943,10 +943,10 @@ int em_after_step_queue(wgs_ctx* ctx, EmState& st, double tole, int iteration, c
     const float* d_serial = nullptr;
     if (st.exact) {
         // checks inside the band where the FP64 sum cannot decide are resolved with the reference's own sequential
-        // float32 sum, rebuilt from D2 (warp_seqsum32); under site sharding the running sums pass from rank to rank
+        // float32 sum, rebuilt from D2 (block_seqsum32); under site sharding the running sums pass from rank to rank
         const double* cnt = d_count ? d_count + c0 : nullptr;
         auto resolve = [&](const float* carry_in, bool sums) -> int {
-            LAUNCH("em_resolve", em_resolve_kernel, std::max(1, std::min((nc + 7) / 8, ctx->num_sm * 2)), 256, 0, ctx->stream,
+            LAUNCH("em_resolve", em_resolve_kernel, std::max(1, std::min(nc, ctx->num_sm * 16)), kSeqWarps * 32, 0, ctx->stream,
                    st.ssq.as<double>() + c0, cnt, count_all, nc, tole, st.band_override, st.active.as<int>() + c0,
                    sums ? st.d2.as<float>() + c0 : (const float*)nullptr, ctx->ldg, ctx->M(), carry_in, st.serial.as<float>() + c0,
                    st.uncertain.as<int>() + c0);
@@ -1149,7 +1149,7 @@ int run_em_pop(wgs_ctx* ctx, int iter, double tole, float* FT, std::vector<int>&
                     const float* curp = hist.as<float>() + ((size_t)u * K + k) * M;
                     const float* prevp = u == 0 ? (cur[k] ? FT1.as<float>() : FT) + (size_t)k * M : hist.as<float>() + ((size_t)(u - 1) * K + k) * M;
                     if (chain_floats(ctx, dser.as<float>(), dcarry.as<float>(), 1, [&](const float* cin) {
-                            LAUNCH("em_resolve", seqsum_pair_kernel, 1, 32, 0, ctx->stream, curp, prevp, M, cin, dser.as<float>());
+                            LAUNCH("em_resolve", seqsum_pair_kernel, 1, kSeqWarps * 32, 0, ctx->stream, curp, prevp, M, cin, dser.as<float>());
                             return 0;
                         })) return 1;
                     float ser = 0.f;
@@ -2626,7 +2626,7 @@ int32_t wgs_debug_seqsum(wgs_ctx* ctx, const float* x, int64_t n, float carry_in
     if (buf_alloc(ctx, dx, (size_t)std::max<int64_t>(n, 1) * sizeof(float)) || buf_alloc(ctx, dc, sizeof(float)) || buf_alloc(ctx, dout, sizeof(float))) return 1;
     CU(cudaMemcpyAsync(dx.p, x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(dc.p, &carry_in, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH("em_resolve", seqsum_vec_kernel, 1, 32, 0, ctx->stream, dx.as<float>(), (long)n, dc.as<float>(), dout.as<float>());
+    LAUNCH("em_resolve", seqsum_vec_kernel, 1, kSeqWarps * 32, 0, ctx->stream, dx.as<float>(), (long)n, dc.as<float>(), dout.as<float>());
     CU(cudaMemcpyAsync(out, dout.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());

@@ -2397,58 +2397,91 @@ __global__ void em_rank_sum_kernel(const double* __restrict__ gathered, int worl
 // per block.  Ties (about one per 2^20 addends here) and binade crossings (~25 per sum) are detected, and that block
 // is then added one element at a time in order with real float32 additions.  The result is bit-identical to the
 // serial loop for every input (negative, NaN and infinite addends take the in-order path).
-// get(i): the i-th addend, 0 <= i < n; element order inside a block is i = base + 32 j + lane.
+// get(i): the i-th addend, 0 <= i < n; element order inside a chunk of 256 is i = base + 32 j + lane.
 // ---------------------------------------------------------------------------------------
+// One BLOCK per sum (kSeqWarps warps): a single warp would be bound by load latency (256 addends per ~1 us round trip,
+// 4 ms per million).  Per round every warp takes one chunk of 256 addends - the next round's are already in flight -
+// and works out its integer advance Q for the binade the accumulator is in at the start of the round; the chunks are
+// then folded IN ORDER by every thread redundantly (a handful of integer instructions each).  A chunk with a tie, or
+// one that would leave the binade, is added one element at a time, in order, by the warp that holds it; when that
+// moved the accumulator to another binade the remaining chunks of the round are re-derived for the new one.
+constexpr int kSeqWarps = 32;
 template <class Get>
-__device__ __forceinline__ float warp_seqsum32(float res, long n, Get get)
+__device__ __forceinline__ float block_seqsum32(float res, long n, Get get)
 {
-    const int lane = threadIdx.x & 31;
-    for (long base = 0; base < n; base += 256) {
-        float x[8];
+    __shared__ unsigned sh_q[kSeqWarps];
+    __shared__ int sh_bad[kSeqWarps];
+    __shared__ float sh_res;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long per_round = 256L * kSeqWarps;
+    float x[8], xn[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const long i = base + 32 * j + lane;
-            x[j] = i < n ? get(i) : 0.0f;                    // + 0.0f never changes a float32 accumulator that started at +0
+    for (int j = 0; j < 8; ++j) { const long i = (long)warp * 256 + 32 * j + lane; x[j] = i < n ? get(i) : 0.0f; }
+    for (long r0 = 0; r0 < n; r0 += per_round) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                        // next round: in flight while this one is folded
+            const long i = r0 + per_round + (long)warp * 256 + 32 * j + lane;
+            xn[j] = i < n ? get(i) : 0.0f;                   // + 0.0f never changes a float32 accumulator that started at +0
         }
-        const unsigned bits = __float_as_uint(res);
-        const int eb = (int)(bits >> 23);                   // sign bit included: a negative accumulator fails the range test
-        bool bad = !(eb >= 30 && eb <= 250);
-        int qsum = 0;
-        if (!bad) {
-            const float scale = __uint_as_float((unsigned)(277 - eb) << 23);   // 1 / ulp(res), a power of two: x * scale is exact
+        int wdone = 0;
+        for (;;) {
+            const unsigned bits0 = __float_as_uint(res);
+            const int eb = (int)(bits0 >> 23);               // sign bit included: a negative accumulator fails the range test
+            if (warp >= wdone) {
+                bool bad = !(eb >= 30 && eb <= 250);
+                int qsum = 0;
+                if (!bad) {
+                    const float scale = __uint_as_float((unsigned)(277 - eb) << 23);   // 1 / ulp(res), a power of two: x * scale is exact
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float t = x[j] * scale;
-                bad = bad || !(t >= 0.0f && t < 1048576.0f);                   // also NaN
-                const float fl = floorf(t);
-                bad = bad || (t - fl == 0.5f);                                 // a tie: its rounding depends on the parity of S
-                qsum += __float2int_rn(t);
+                    for (int j = 0; j < 8; ++j) {
+                        const float t = x[j] * scale;
+                        bad = bad || !(t >= 0.0f && t < 1048576.0f);           // also NaN
+                        bad = bad || (t - floorf(t) == 0.5f);                  // a tie: its rounding depends on the parity of S
+                        qsum += __float2int_rn(t);
+                    }
+                }
+                const bool anybad = __any_sync(0xffffffffu, bad);
+                const unsigned Q = (unsigned)__reduce_add_sync(0xffffffffu, anybad ? 0 : qsum);
+                if (lane == 0) { sh_q[warp] = Q; sh_bad[warp] = anybad ? 1 : 0; }
             }
-        }
-        const bool anybad = __any_sync(0xffffffffu, bad);
-        bool done = false;
-        if (!anybad) {
-            const unsigned Q = (unsigned)__reduce_add_sync(0xffffffffu, qsum);
-            const unsigned S = (bits & 0x007fffffu) | 0x00800000u;
-            if (S + Q < 0x01000000u) {                      // still inside the binade: no step in between rounded differently
-                res = __uint_as_float(((unsigned)eb << 23) | ((S + Q) & 0x007fffffu));
-                done = true;
-            }
-        }
-        if (!done) {
+            __syncthreads();
+            bool redo = false;
+            int w = wdone;
+            for (; w < kSeqWarps; ++w) {                     // every thread folds the chunks in order: uniform control flow
+                if (r0 + (long)w * 256 >= n) { w = kSeqWarps; break; }
+                const unsigned b = __float_as_uint(res);
+                const unsigned S = (b & 0x007fffffu) | 0x00800000u;
+                if (!sh_bad[w] && (int)(b >> 23) == eb && S + sh_q[w] < 0x01000000u) {
+                    res = __uint_as_float(((unsigned)eb << 23) | ((S + sh_q[w]) & 0x007fffffu));
+                } else {
+                    if (warp == w) {
+                        float r = res;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+                        for (int j = 0; j < 8; ++j)
 #pragma unroll 8
-                for (int l = 0; l < 32; ++l) res = __fadd_rn(res, __shfl_sync(0xffffffffu, x[j], l));
+                            for (int l = 0; l < 32; ++l) r = __fadd_rn(r, __shfl_sync(0xffffffffu, x[j], l));
+                        if (lane == 0) sh_res = r;
+                    }
+                    __syncthreads();
+                    res = sh_res;
+                    __syncthreads();
+                    if ((int)(__float_as_uint(res) >> 23) != eb) { ++w; redo = true; break; }   // the later chunks were scaled for the old binade
+                }
+            }
+            wdone = w;
+            __syncthreads();                                 // sh_q / sh_bad are rewritten next
+            if (!redo || wdone >= kSeqWarps) break;
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = xn[j];
     }
     return res;
 }
 
-// Stop-rule tie-break, part 1: one warp per problem.  A problem is UNCERTAIN when the RMSE from the exact (FP64)
+// Stop-rule tie-break, part 1: one block per problem.  A problem is UNCERTAIN when the RMSE from the exact (FP64)
 // sum of squared changes lies within `band` (relative) of the tolerance - band = the worst-case distance between
 // the exact sum and the reference's sequential float32 sum for that many addends (or the caller's override;
-// band < 0: every active problem).  For those, the float32 sum is reproduced from the squared changes the step
+// band < 0: every active problem).  For those, the float32 sum is reproduced (block_seqsum32) from the squared changes the step
 // kernels left in D2[M][ldd] (column col0 + p; zero where a site is masked out), starting from carry_in[p]
 // (site-sharded runs chain the ranks in site order).  em_decide_kernel then decides on serial[p].
 __device__ __forceinline__ double em_band(double cnt, double band_override)
@@ -2458,7 +2491,7 @@ __device__ __forceinline__ double em_band(double cnt, double band_override)
     if (ku >= 0.5) return -1.0;
     return 0.5 * ku / (1.0 - ku) + 1e-4;                     // half of it on the square root, plus the FP32 per-thread partials of the FP64 sum
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSeqWarps * 32)
 em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ count, double count_all, int np, double tole,
                   double band_override, const int* __restrict__ active,
                   const float* __restrict__ D2, int ldd, long M,
@@ -2466,9 +2499,7 @@ em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ cou
                   float* __restrict__ serial,               // [np] out: the running float32 sum after this rank's sites
                   int* __restrict__ uncertain)              // [np] out
 {
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < np; p += warps) {
+    for (int p = blockIdx.x; p < np; p += gridDim.x) {      // block-uniform
         int unc = 0;
         if (active[p]) {
             const double cnt = count ? count[p] : count_all;
@@ -2480,25 +2511,25 @@ em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ cou
         }
         if (unc && D2) {                                     // D2 == null: flags only
             const float* col = D2 + p;
-            const float r = warp_seqsum32(carry_in ? carry_in[p] : 0.0f, M, [&](long i) { return __ldg(col + i * (long)ldd); });
-            if (lane == 0) serial[p] = r;
+            const float r = block_seqsum32(carry_in ? carry_in[p] : 0.0f, M, [&](long i) { return __ldg(col + i * (long)ldd); });
+            if (threadIdx.x == 0) serial[p] = r;
         }
-        if (lane == 0) uncertain[p] = unc;
+        if (threadIdx.x == 0) uncertain[p] = unc;
     }
 }
 
 // the same float32 sum for a contiguous pair of state vectors (population EM: the per-iteration history): x_i = (cur_i - prev_i)^2
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kSeqWarps * 32)
 seqsum_pair_kernel(const float* __restrict__ cur, const float* __restrict__ prev, long M, const float* __restrict__ carry_in,
                    float* __restrict__ out)
 {
-    const float r = warp_seqsum32(carry_in ? carry_in[0] : 0.0f, M, [&](long i) { const float d = __fsub_rn(cur[i], prev[i]); return __fmul_rn(d, d); });
+    const float r = block_seqsum32(carry_in ? carry_in[0] : 0.0f, M, [&](long i) { const float d = __fsub_rn(cur[i], prev[i]); return __fmul_rn(d, d); });
     if (threadIdx.x == 0) out[0] = r;
 }
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kSeqWarps * 32)
 seqsum_vec_kernel(const float* __restrict__ x, long n, const float* __restrict__ carry_in, float* __restrict__ out)
 {
-    const float r = warp_seqsum32(carry_in ? carry_in[0] : 0.0f, n, [&](long i) { return x[i]; });
+    const float r = block_seqsum32(carry_in ? carry_in[0] : 0.0f, n, [&](long i) { return x[i]; });
     if (threadIdx.x == 0) out[0] = r;
 }
 
