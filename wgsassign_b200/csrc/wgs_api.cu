@@ -2223,7 +2223,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         if (c.sites_per_block > cap) { c.sites_per_block = cap; c.gy = (int)((M + cap - 1) / cap); }
     }
     const double pairs = (double)M * (ind_end - ind_start);
-    // The reference's class means are SEQUENTIAL float32 sums in site order (zscore.py:22); ztally_seq2 reproduces
+    // The reference's class means are SEQUENTIAL float32 sums in site order (zscore.py:22); ztally_ord reproduces
     // them for any number of sites, and under site sharding the ranks run it one after the other in site order,
     // handing the table on (carry-in / carry-out).  Option z_exact_means = 1 selects the order-independent
     // fixed-point tally instead (one pass, no chain; NOT the reference's means).
@@ -2242,10 +2242,9 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
                c.wx, c.sites_per_block, dtable.as<ZTally>(), ddeep.as<unsigned long long>());
         LAUNCH("zaux", zmaxdepth_kernel<ZTally>, ctx->num_sm * 4, 256, 0, ctx->stream, dtable.as<ZTally>(), (long)tab_n, dmaxd.as<int>());
     } else {
-        CU(cudaFuncSetAttribute(ztally_seq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZSeqSmem));
         const size_t tbytes = tab_n * sizeof(ZTallyF);
         auto run_seq = [&]() -> int {
-            LAUNCH("ztally", ztally_seq2_kernel, (ldg + 31) / 32, 32, kZSeqSmem, ctx->stream, ctx->G[0], ctx->AD, ldg, M,
+            LAUNCH("ztally", ztally_ord_kernel, (ldg + kZOrdWarps - 1) / kZOrdWarps, kZOrdWarps * 32, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M,
                    dsel.as<unsigned char>(), dtable.as<ZTallyF>(), ddeep.as<unsigned long long>());
             return 0;
         };

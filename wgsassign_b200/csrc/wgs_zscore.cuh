@@ -133,207 +133,111 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
 }
 
 // ---------------------------------------------------------------------------------------
-// ztally_seq: the reference-faithful tally.  The reference's class mean is numpy's float32
-// mean over the class's rows (zscore.py:22), i.e. a SEQUENTIAL float32 sum in site order
-// whose rounding error grows with the class size (already 4e-6 relative at 400 sites) and
-// feeds both the 0.01 keep test and the expected log-likelihood.  Reproducing its bits
-// needs the same order: one thread per individual walks all sites in order (a warp = 32
-// individuals, so loads stay coalesced; 8 sites are prefetched ahead).  Hot classes are
-// float accumulators in registers updated by predicated adds; the rest are read-modify-
-// written in the individual's own table row (no other thread touches it).
-// Used on a single GPU up to 2^18 sites (it is serial in the site index: ~0.8 us per site);
-// larger and site-sharded runs use the order-independent ztally_kernel above (at that scale the
-// reference's own float32 mean has lost its precision anyway).  WGS_Z_EXACT_MEANS=0/1 overrides.
+// ztally_ord: the reference-faithful tally.  The reference's class mean is numpy's float32 mean over the class's
+// rows (zscore.py:22), i.e. a SEQUENTIAL float32 sum in site order whose rounding error grows with the class size
+// (already 4e-6 relative at 400 sites) and feeds both the 0.01 keep test and the expected log-likelihood.
+// Reproducing its bits needs its order - but only WITHIN a class: sums of different classes, components and
+// individuals are independent chains.
+//
+//  * One WARP = one individual, lane = site: a batch of 32 consecutive sites is classified at once, lanes of the
+//    same (ref, alt) class find each other with MATCH.ANY, and the class's running sum is handed from member to
+//    member in lane (= site) order with shuffles - as many rounds as the most frequent class has members in the
+//    batch (~10 of 32 at 2x).  ~4.5 warp instructions per site, and N warps instead of N / 32: the first version
+//    (one thread per individual walking the sites) had a dependent shared-memory round trip per site and N / 32
+//    warps on the whole GPU - 100 ns per site, 3 % of HBM.
+//  * The accumulators of all classes up to depth 9 (55 classes: > 99.9 % of the sites at 2x) live in the warp's
+//    shared-memory cells {s0, s1, s2, count}; deeper classes are read-modify-written in the individual's own table
+//    row (nobody else touches it).
+//  * A block = 8 adjacent individuals: their 8-byte GL pairs of a site are 64 contiguous bytes, so the strided
+//    per-lane loads of the 8 warps hit the same sectors (L1), and 4 batches per warp are in flight.
+//  * The table is read as the CARRY-IN state and left as the carry-out: under site sharding the ranks run this
+//    kernel one after the other in site order and hand the table on (wgs_zscore: ncclSend / ncclRecv over NVLink,
+//    16 bytes per (individual, class)), so the order of every addition is the reference's over the whole file.
 // ---------------------------------------------------------------------------------------
 struct ZTallyF { float s0, s1, s2; int cnt; };
-
-__global__ void __launch_bounds__(32)
-ztally_seq_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
-                  const unsigned char* __restrict__ sel,
-                  ZTallyF* __restrict__ table,             // [ldg][kZClasses], zeroed
-                  unsigned long long* __restrict__ deep)
-{
-    const int col = blockIdx.x * 32 + threadIdx.x;
-    if (col >= ldg || !sel[col]) return;
-    int cnt[kZHot];
-    float a0[kZHot], a1[kZHot], a2[kZHot];
-#pragma unroll
-    for (int c = 0; c < kZHot; ++c) { cnt[c] = 0; a0[c] = a1[c] = a2[c] = 0.f; }
-    int ndeep = 0;
-    ZTallyF* mine = table + (size_t)col * kZClasses;
-    for (long sb = 0; sb < M; sb += 8) {
-        float2 g[8];
-        uchar2 ad[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            g[u] = make_float2(0.f, 0.f); ad[u] = make_uchar2(255, 255);
-            if (sb + u < M) { g[u] = ld_stream2(&G[(sb + u) * (long)ldg + col]); ad[u] = AD[(sb + u) * (long)ldg + col]; }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (sb + u >= M) break;
-            int ref = ad[u].x, alt = ad[u].y, d = ref + alt;
-            float g0 = g[u].x, g1 = g[u].y, g2 = third_gl_np(g0, g1);
-            if (d <= kZHotDepth) {
-                int code = zclass_id(ref, alt);
-#pragma unroll
-                for (int c = 0; c < kZHot; ++c) {
-                    if (code == c) {
-                        cnt[c] += 1;
-                        a0[c] = __fadd_rn(a0[c], g0); a1[c] = __fadd_rn(a1[c], g1); a2[c] = __fadd_rn(a2[c], g2);
-                    }
-                }
-            } else if (d <= kZDepthCap) {
-                ZTallyF* t = mine + zclass_id(ref, alt);
-                ZTallyF v = *t;
-                v.s0 = __fadd_rn(v.s0, g0); v.s1 = __fadd_rn(v.s1, g1); v.s2 = __fadd_rn(v.s2, g2); v.cnt += 1;
-                *t = v;
-            } else {
-                ++ndeep;
-            }
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < kZHot; ++c) { ZTallyF v; v.s0 = a0[c]; v.s1 = a1[c]; v.s2 = a2[c]; v.cnt = cnt[c]; mine[c] = v; }
-    if (ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
-}
-
-// ---------------------------------------------------------------------------------------
-// ztally_seq2: the same sequential float32 sums as ztally_seq - the reference's class means
-// (zscore.py:22) bit for bit - restructured so that it is the tally of EVERY run: any number
-// of sites, and any number of site-sharded ranks.
-//
-//  * The table is read as the CARRY-IN state and left as the carry-out: under site sharding
-//    the ranks run this kernel one after the other in site order and hand the table on
-//    (wgs_zscore: ncclSend / ncclRecv over NVLink, 16 bytes per (individual, class)), so the
-//    order of every addition is the reference's over the whole file.
-//  * One warp = 32 individuals, lane = individual (coalesced rows).  The (GL, AD) rows of 32
-//    sites per stage are streamed into an 8-stage shared-memory ring by the warp's own
-//    16-byte / 8-byte LDGSTS copies: ~80 KB in flight per warp, because with N / 32 warps on
-//    the whole GPU it is bytes in flight per warp, not resident warps, that cover HBM latency
-//    (8 register-prefetched sites per thread left ztally_seq latency-bound at ~1 us per 8 sites).
-//  * The accumulators of all classes up to depth 9 (55 classes: > 99.9 % of the sites at 2x)
-//    are thread-private float4 cells {s0, s1, s2, count} in shared memory, cell[class][lane]:
-//    one conflict-free LDS.128 / STS.128 per site whatever the class mix inside the warp
-//    (15 register accumulators with predicated adds cost 75 issue slots per site).  Two sites
-//    are in flight per thread: both cells are loaded first and the second site takes the
-//    first one's result when the classes coincide - the additions of a class stay in site
-//    order, the load latency is paid once per pair.  Deeper classes are read-modify-written
-//    in the individual's own table row (no other thread touches it).
-// ---------------------------------------------------------------------------------------
 constexpr int kZSeqHotDepth = 9;
 constexpr int kZSeqHot = (kZSeqHotDepth + 1) * (kZSeqHotDepth + 2) / 2;  // 55
-constexpr int kZSeqSB = 32;                                          // sites per ring stage
-constexpr int kZSeqStages = 8;
-constexpr size_t kZSeqSmem = (size_t)kZSeqHot * 32 * sizeof(float4) + (size_t)kZSeqStages * kZSeqSB * 32 * (sizeof(float2) + sizeof(uchar2));
+constexpr int kZOrdWarps = 8;
+constexpr int kZOrdPF = 4;                                               // batches of 32 sites in flight per warp
 
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem));
+__device__ __forceinline__ void ztally_ord_batch(float2 g, uchar2 a, bool valid, int lane, float4* __restrict__ cell,
+                                                 ZTallyF* __restrict__ mine, int& ndeep)
+{
+    const int d = a.x + a.y;
+    const int code = d * (d + 1) / 2 + a.y;
+    const bool deepf = valid && d > kZDepthCap;
+    const bool act = valid && !deepf;
+    ndeep += __popc(__ballot_sync(0xffffffffu, deepf));      // same value in every lane; lane 0 reports it
+    const unsigned peers = __match_any_sync(0xffffffffu, act ? code : -1 - lane);   // lanes of the same class (inactive lanes: alone)
+    const unsigned lt = peers & ((1u << lane) - 1u);
+    const int rank = __popc(lt);                             // this site's position inside its class, in site order
+    const int prev = rank ? 31 - __clz(lt) : lane;           // the class member just before it
+    const bool last = ((peers >> lane) >> 1) == 0u;
+    const int maxrank = __reduce_max_sync(0xffffffffu, act ? rank : 0);
+    const bool hot = d <= kZSeqHotDepth;
+    const float g2 = third_gl_np(g.x, g.y);
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (act && rank == 0) {
+        if (hot) { const float4 c = cell[code]; v0 = c.x; v1 = c.y; v2 = c.z; }
+        else { const ZTallyF t = mine[code]; v0 = t.s0; v1 = t.s1; v2 = t.s2; }
+        v0 = __fadd_rn(v0, g.x); v1 = __fadd_rn(v1, g.y); v2 = __fadd_rn(v2, g2);
+    }
+    for (int r = 1; r <= maxrank; ++r) {                     // warp-uniform trip count
+        const float t0 = __shfl_sync(0xffffffffu, v0, prev), t1 = __shfl_sync(0xffffffffu, v1, prev), t2 = __shfl_sync(0xffffffffu, v2, prev);
+        if (act && rank == r) { v0 = __fadd_rn(t0, g.x); v1 = __fadd_rn(t1, g.y); v2 = __fadd_rn(t2, g2); }
+    }
+    if (act && last) {                                       // the class's last member of the batch stores the running sums
+        const int n = __popc(peers);
+        if (hot) { const float w = cell[code].w; cell[code] = make_float4(v0, v1, v2, __int_as_float(__float_as_int(w) + n)); }
+        else { ZTallyF t; t.s0 = v0; t.s1 = v1; t.s2 = v2; t.cnt = mine[code].cnt + n; mine[code] = t; }
+    }
+    __syncwarp();                                            // the cells are read by other lanes in the next batch
 }
 
-__global__ void __launch_bounds__(32)
-ztally_seq2_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
-                   const unsigned char* __restrict__ sel,
-                   ZTallyF* __restrict__ table,            // [ldg][kZClasses]: carry-in, updated in place
-                   unsigned long long* __restrict__ deep)
+__global__ void __launch_bounds__(kZOrdWarps * 32)
+ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
+                  const unsigned char* __restrict__ sel,
+                  ZTallyF* __restrict__ table,             // [ldg][kZClasses]: carry-in, updated in place
+                  unsigned long long* __restrict__ deep)
 {
-    extern __shared__ __align__(16) unsigned char zs_raw[];
-    float4* cell = reinterpret_cast<float4*>(zs_raw);                          // [kZSeqHot][32]
-    float2* Gs = reinterpret_cast<float2*>(cell + kZSeqHot * 32);              // [stages][SB][32]
-    uchar2* As = reinterpret_cast<uchar2*>(Gs + kZSeqStages * kZSeqSB * 32);   // [stages][SB][32]
-    const int lane = threadIdx.x;
-    const int col0 = blockIdx.x * 32, col = col0 + lane;
-    const bool on = col < ldg && sel[col];
-    if (__ballot_sync(0xffffffffu, on) == 0u) return;
-    const int ncols = min(32, ldg - col0);                  // a multiple of 4: slabs are padded to 4 individuals
-    ZTallyF* mine = table + (size_t)(on ? col : col0) * kZClasses;
-    for (int c = 0; c < kZSeqHot; ++c) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on) { const ZTallyF t = mine[c]; v = make_float4(t.s0, t.s1, t.s2, __int_as_float(t.cnt)); }
-        cell[c * 32 + lane] = v;
+    __shared__ float4 cells[kZOrdWarps][kZSeqHot];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x * kZOrdWarps + warp;
+    if (col >= ldg || !sel[col]) return;                     // warp-uniform; no block-wide barrier below
+    float4* cell = cells[warp];
+    ZTallyF* mine = table + (size_t)col * kZClasses;
+    for (int c = lane; c < kZSeqHot; c += 32) { const ZTallyF t = mine[c]; cell[c] = make_float4(t.s0, t.s1, t.s2, __int_as_float(t.cnt)); }
+    __syncwarp();
+    const float2* Gc = G + col;
+    const uchar2* Ac = AD + col;
+    float2 gq[kZOrdPF];
+    uchar2 aq[kZOrdPF];
+#pragma unroll
+    for (int p = 0; p < kZOrdPF; ++p) {
+        const long s = (long)p * 32 + lane;
+        gq[p] = make_float2(0.f, 0.f); aq[p] = make_uchar2(0, 0);
+        if (s < M) { gq[p] = __ldg(Gc + s * (long)ldg); aq[p] = __ldg(Ac + s * (long)ldg); }
     }
-    float4* const mycell = cell + lane;
-    const int gc = ncols >> 1, ac = ncols >> 2;             // 16-byte GL chunks / 8-byte AD chunks per site row
-    auto stage_load = [&](long s0, int st) {
-        const int rows = (int)min((long)kZSeqSB, M - s0);
-        if (rows > 0) {
-            float2* gd = Gs + (size_t)st * kZSeqSB * 32;
-            uchar2* ad = As + (size_t)st * kZSeqSB * 32;
-            if (ncols == 32) {
-                for (int e = lane; e < rows * 16; e += 32) { const int r = e >> 4, c = e & 15; cp_async16(gd + r * 32 + 2 * c, G + (s0 + r) * (long)ldg + col0 + 2 * c); }
-                for (int e = lane; e < rows * 8; e += 32) { const int r = e >> 3, c = e & 7; cp_async8(ad + r * 32 + 4 * c, AD + (s0 + r) * (long)ldg + col0 + 4 * c); }
-            } else {
-                for (int e = lane; e < rows * gc; e += 32) { const int r = e / gc, c = e - r * gc; cp_async16(gd + r * 32 + 2 * c, G + (s0 + r) * (long)ldg + col0 + 2 * c); }
-                for (int e = lane; e < rows * ac; e += 32) { const int r = e / ac, c = e - r * ac; cp_async8(ad + r * 32 + 4 * c, AD + (s0 + r) * (long)ldg + col0 + 4 * c); }
-            }
-        }
-        cp_async_commit();                                  // always: the wait below counts groups
-    };
-    const long nst = (M + kZSeqSB - 1) / kZSeqSB;
-    for (int p = 0; p < kZSeqStages - 1; ++p) stage_load((long)p * kZSeqSB, p);
     int ndeep = 0;
-    ZTallyF* cold = table + (size_t)col * kZClasses;
-    for (long j = 0; j < nst; ++j) {
-        const int st = (int)(j % kZSeqStages);
-        cp_async_wait<kZSeqStages - 2>();                   // stage j has landed
-        __syncwarp();
-        stage_load((j + kZSeqStages - 1) * kZSeqSB, (int)((j + kZSeqStages - 1) % kZSeqStages));   // refills the slot consumed at j-1
-        const long s0 = j * kZSeqSB;
-        const int rows = (int)min((long)kZSeqSB, M - s0);
-        if (on) {
-            const float2* gs = Gs + (size_t)st * kZSeqSB * 32 + lane;
-            const uchar2* as = As + (size_t)st * kZSeqSB * 32 + lane;
-#pragma unroll 2
-            for (int u = 0; u < rows; u += 2) {
-                const bool two = u + 1 < rows;
-                const uchar2 a1 = as[u * 32], a2 = two ? as[(u + 1) * 32] : make_uchar2(255, 255);
-                const float2 g1 = gs[u * 32], g2 = two ? gs[(u + 1) * 32] : make_float2(0.f, 0.f);
-                const int d1 = a1.x + a1.y, d2 = a2.x + a2.y;
-                const int c1 = d1 * (d1 + 1) / 2 + a1.y, c2 = d2 * (d2 + 1) / 2 + a2.y;
-                const bool h1 = d1 <= kZSeqHotDepth, h2 = two && d2 <= kZSeqHotDepth;
-                float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1;
-                if (h1) v1 = mycell[c1 * 32];
-                if (h2) v2 = mycell[c2 * 32];
-                const float t1 = third_gl_np(g1.x, g1.y), t2 = third_gl_np(g2.x, g2.y);
-                if (h1) {
-                    v1.x = __fadd_rn(v1.x, g1.x); v1.y = __fadd_rn(v1.y, g1.y); v1.z = __fadd_rn(v1.z, t1);
-                    v1.w = __int_as_float(__float_as_int(v1.w) + 1);
-                }
-                if (h1 && h2 && c1 == c2) v2 = v1;           // same class twice in a row: the second addition sees the first
-                if (h2) {
-                    v2.x = __fadd_rn(v2.x, g2.x); v2.y = __fadd_rn(v2.y, g2.y); v2.z = __fadd_rn(v2.z, t2);
-                    v2.w = __int_as_float(__float_as_int(v2.w) + 1);
-                }
-                if (h1) mycell[c1 * 32] = v1;                 // program order: when the classes coincide the second store wins
-                if (h2) mycell[c2 * 32] = v2;
-                if (!h1) {                                  // rare: deeper than the shared-memory cells
-                    if (d1 <= kZDepthCap) {
-                        ZTallyF v = cold[c1];
-                        v.s0 = __fadd_rn(v.s0, g1.x); v.s1 = __fadd_rn(v.s1, g1.y); v.s2 = __fadd_rn(v.s2, t1); v.cnt += 1;
-                        cold[c1] = v;
-                    } else ++ndeep;
-                }
-                if (two && !h2) {
-                    if (d2 <= kZDepthCap) {
-                        ZTallyF v = cold[c2];
-                        v.s0 = __fadd_rn(v.s0, g2.x); v.s1 = __fadd_rn(v.s1, g2.y); v.s2 = __fadd_rn(v.s2, t2); v.cnt += 1;
-                        cold[c2] = v;
-                    } else ++ndeep;
-                }
+    for (long s0 = 0; s0 < M; s0 += 32 * kZOrdPF) {
+#pragma unroll
+        for (int p = 0; p < kZOrdPF; ++p) {
+            const long b = s0 + (long)p * 32;
+            if (b < M) {                                     // warp-uniform
+                const float2 g = gq[p];
+                const uchar2 a = aq[p];
+                const long sn = b + 32 * kZOrdPF + lane;     // refill this slot: in flight while the next batches are folded
+                if (sn < M) { gq[p] = __ldg(Gc + sn * (long)ldg); aq[p] = __ldg(Ac + sn * (long)ldg); }
+                ztally_ord_batch(g, a, b + lane < M, lane, cell, mine, ndeep);
             }
         }
-        __syncwarp();                                       // everyone is done with stage j before a later load refills it
     }
-    cp_async_wait<0>();
-    if (on) {
-        for (int c = 0; c < kZSeqHot; ++c) {
-            const float4 v = cell[c * 32 + lane];
-            ZTallyF t; t.s0 = v.x; t.s1 = v.y; t.s2 = v.z; t.cnt = __float_as_int(v.w);
-            mine[c] = t;
-        }
-        if (ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
+    for (int c = lane; c < kZSeqHot; c += 32) {
+        const float4 v = cell[c];
+        ZTallyF t; t.s0 = v.x; t.s1 = v.y; t.s2 = v.z; t.cnt = __float_as_int(v.w);
+        mine[c] = t;
     }
+    if (lane == 0 && ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
 }
 
 // Deepest read depth with a non-empty class in the tally table: the host then moves and scans only the
