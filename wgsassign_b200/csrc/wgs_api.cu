@@ -2243,8 +2243,9 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         LAUNCH("zaux", zmaxdepth_kernel<ZTally>, ctx->num_sm * 4, 256, 0, ctx->stream, dtable.as<ZTally>(), (long)tab_n, dmaxd.as<int>());
     } else {
         const size_t tbytes = tab_n * sizeof(ZTallyF);
+        CU(cudaFuncSetAttribute(ztally_ord_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZOrdSmem));
         auto run_seq = [&]() -> int {
-            LAUNCH("ztally", ztally_ord_kernel, (ldg + kZOrdWarps - 1) / kZOrdWarps, kZOrdWarps * 32, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M,
+            LAUNCH("ztally", ztally_ord_kernel, (ldg + kZOrdWarps - 1) / kZOrdWarps, kZOrdWarps * 32, kZOrdSmem, ctx->stream, ctx->G[0], ctx->AD, ldg, M,
                    dsel.as<unsigned char>(), dtable.as<ZTallyF>(), ddeep.as<unsigned long long>());
             return 0;
         };

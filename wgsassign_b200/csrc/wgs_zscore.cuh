@@ -157,9 +157,21 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
 struct ZTallyF { float s0, s1, s2; int cnt; };
 constexpr int kZSeqHotDepth = 9;
 constexpr int kZSeqHot = (kZSeqHotDepth + 1) * (kZSeqHotDepth + 2) / 2;  // 55
-constexpr int kZOrdWarps = 8;
-constexpr int kZOrdPF = 4;                                               // batches of 32 sites in flight per warp
+constexpr int kZOrdWarps = 16;                                           // individuals per block: 128-byte GL rows, one sector of depths
+constexpr int kZOrdTile = 128;                                           // sites per staged tile (4 batches of 32)
+constexpr int kZOrdGS = 18;                                              // tile row strides (float2 / uchar2 units): 16-byte aligned rows whose
+constexpr int kZOrdAS = 20;                                              //   column reads (lane = row) spread over the banks
+constexpr size_t kZOrdSmem = (size_t)kZOrdWarps * kZSeqHot * sizeof(float4) + 2 * (size_t)kZOrdTile * (kZOrdGS * sizeof(float2) + kZOrdAS * sizeof(uchar2));
 
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem));
+}
+
+// One batch = 32 consecutive sites of one individual (lane = site).  The LEADER of a class (its first member in the
+// batch) reads the class's running sums and adds its members' GLs in lane (= site) order, fetching them with
+// shuffles whose sources do not depend on the running sum: the only dependent chain is the float32 additions
+// themselves.  The trip count is the size of the largest class in the batch (warp-uniform).
 __device__ __forceinline__ void ztally_ord_batch(float2 g, uchar2 a, bool valid, int lane, float4* __restrict__ cell,
                                                  ZTallyF* __restrict__ mine, int& ndeep)
 {
@@ -169,27 +181,28 @@ __device__ __forceinline__ void ztally_ord_batch(float2 g, uchar2 a, bool valid,
     const bool act = valid && !deepf;
     ndeep += __popc(__ballot_sync(0xffffffffu, deepf));      // same value in every lane; lane 0 reports it
     const unsigned peers = __match_any_sync(0xffffffffu, act ? code : -1 - lane);   // lanes of the same class (inactive lanes: alone)
-    const unsigned lt = peers & ((1u << lane) - 1u);
-    const int rank = __popc(lt);                             // this site's position inside its class, in site order
-    const int prev = rank ? 31 - __clz(lt) : lane;           // the class member just before it
-    const bool last = ((peers >> lane) >> 1) == 0u;
-    const int maxrank = __reduce_max_sync(0xffffffffu, act ? rank : 0);
+    const bool leader = act && (peers & ((1u << lane) - 1u)) == 0u;
+    const int maxn = __reduce_max_sync(0xffffffffu, act ? __popc(peers) : 0);
     const bool hot = d <= kZSeqHotDepth;
     const float g2 = third_gl_np(g.x, g.y);
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (act && rank == 0) {
-        if (hot) { const float4 c = cell[code]; v0 = c.x; v1 = c.y; v2 = c.z; }
-        else { const ZTallyF t = mine[code]; v0 = t.s0; v1 = t.s1; v2 = t.s2; }
+    int cnt = 0;
+    if (leader) {
+        if (hot) { const float4 c = cell[code]; v0 = c.x; v1 = c.y; v2 = c.z; cnt = __float_as_int(c.w); }
+        else { const ZTallyF t = mine[code]; v0 = t.s0; v1 = t.s1; v2 = t.s2; cnt = t.cnt; }
         v0 = __fadd_rn(v0, g.x); v1 = __fadd_rn(v1, g.y); v2 = __fadd_rn(v2, g2);
     }
-    for (int r = 1; r <= maxrank; ++r) {                     // warp-uniform trip count
-        const float t0 = __shfl_sync(0xffffffffu, v0, prev), t1 = __shfl_sync(0xffffffffu, v1, prev), t2 = __shfl_sync(0xffffffffu, v2, prev);
-        if (act && rank == r) { v0 = __fadd_rn(t0, g.x); v1 = __fadd_rn(t1, g.y); v2 = __fadd_rn(t2, g2); }
+    unsigned rem = leader ? (peers & (peers - 1u)) : 0u;     // the members after the leader
+    for (int r = 1; r < maxn; ++r) {                         // warp-uniform trip count
+        const int src = rem ? __ffs(rem) - 1 : lane;
+        const float t0 = __shfl_sync(0xffffffffu, g.x, src), t1 = __shfl_sync(0xffffffffu, g.y, src), t2 = __shfl_sync(0xffffffffu, g2, src);
+        if (rem) { v0 = __fadd_rn(v0, t0); v1 = __fadd_rn(v1, t1); v2 = __fadd_rn(v2, t2); }
+        rem &= rem - 1u;
     }
-    if (act && last) {                                       // the class's last member of the batch stores the running sums
-        const int n = __popc(peers);
-        if (hot) { const float w = cell[code].w; cell[code] = make_float4(v0, v1, v2, __int_as_float(__float_as_int(w) + n)); }
-        else { ZTallyF t; t.s0 = v0; t.s1 = v1; t.s2 = v2; t.cnt = mine[code].cnt + n; mine[code] = t; }
+    if (leader) {
+        cnt += __popc(peers);
+        if (hot) cell[code] = make_float4(v0, v1, v2, __int_as_float(cnt));
+        else { ZTallyF t; t.s0 = v0; t.s1 = v1; t.s2 = v2; t.cnt = cnt; mine[code] = t; }
     }
     __syncwarp();                                            // the cells are read by other lanes in the next batch
 }
@@ -200,44 +213,63 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
                   ZTallyF* __restrict__ table,             // [ldg][kZClasses]: carry-in, updated in place
                   unsigned long long* __restrict__ deep)
 {
-    __shared__ float4 cells[kZOrdWarps][kZSeqHot];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int col = blockIdx.x * kZOrdWarps + warp;
-    if (col >= ldg || !sel[col]) return;                     // warp-uniform; no block-wide barrier below
-    float4* cell = cells[warp];
-    ZTallyF* mine = table + (size_t)col * kZClasses;
-    for (int c = lane; c < kZSeqHot; c += 32) { const ZTallyF t = mine[c]; cell[c] = make_float4(t.s0, t.s1, t.s2, __int_as_float(t.cnt)); }
-    __syncwarp();
-    const float2* Gc = G + col;
-    const uchar2* Ac = AD + col;
-    float2 gq[kZOrdPF];
-    uchar2 aq[kZOrdPF];
-#pragma unroll
-    for (int p = 0; p < kZOrdPF; ++p) {
-        const long s = (long)p * 32 + lane;
-        gq[p] = make_float2(0.f, 0.f); aq[p] = make_uchar2(0, 0);
-        if (s < M) { gq[p] = __ldg(Gc + s * (long)ldg); aq[p] = __ldg(Ac + s * (long)ldg); }
-    }
+    extern __shared__ __align__(16) unsigned char zs_raw[];
+    float4* cells = reinterpret_cast<float4*>(zs_raw);                                        // [warps][kZSeqHot]
+    float2* Gt = reinterpret_cast<float2*>(cells + kZOrdWarps * kZSeqHot);                    // [2][tile][kZOrdGS]
+    uchar2* At = reinterpret_cast<uchar2*>(Gt + 2 * kZOrdTile * kZOrdGS);                     // [2][tile][kZOrdAS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col0 = blockIdx.x * kZOrdWarps;
+    const int ncols = min(kZOrdWarps, ldg - col0);           // a multiple of 4: slabs are padded to 4 individuals
+    const int col = col0 + warp;
+    const bool on = warp < ncols && sel[col];                // warp-uniform
+    float4* cell = cells + warp * kZSeqHot;
+    ZTallyF* mine = table + (size_t)(warp < ncols ? col : col0) * kZClasses;
+    if (on) for (int c = lane; c < kZSeqHot; c += 32) { const ZTallyF t = mine[c]; cell[c] = make_float4(t.s0, t.s1, t.s2, __int_as_float(t.cnt)); }
+    const int gc = ncols >> 1, ac = ncols >> 2;             // 16-byte GL chunks / 8-byte depth chunks per site row
+    auto stage = [&](long t, int buf) {                      // the block's columns of sites [128 t, 128 t + 128): coalesced rows
+        const long s0 = t * kZOrdTile;
+        const int rows = (int)max(0L, min((long)kZOrdTile, M - s0));
+        float2* gd = Gt + (size_t)buf * kZOrdTile * kZOrdGS;
+        uchar2* ad = At + (size_t)buf * kZOrdTile * kZOrdAS;
+        for (int e = tid; e < rows * gc; e += kZOrdWarps * 32) { const int r = e / gc, c = e - r * gc; cp_async16(gd + r * kZOrdGS + 2 * c, G + (s0 + r) * (long)ldg + col0 + 2 * c); }
+        for (int e = tid; e < rows * ac; e += kZOrdWarps * 32) { const int r = e / ac, c = e - r * ac; cp_async8(ad + r * kZOrdAS + 4 * c, AD + (s0 + r) * (long)ldg + col0 + 4 * c); }
+        cp_async_commit();                                  // always: the wait below counts groups
+    };
+    const long ntiles = (M + kZOrdTile - 1) / kZOrdTile;
     int ndeep = 0;
-    for (long s0 = 0; s0 < M; s0 += 32 * kZOrdPF) {
+    stage(0, 0);
+    for (long t = 0; t < ntiles; ++t) {
+        const int buf = (int)(t & 1);
+        stage(t + 1, buf ^ 1);                              // its buffer was released by the barrier that ended tile t-1
+        cp_async_wait<1>();
+        __syncthreads();                                    // tile t complete, for every thread's copies
+        if (on) {
+            const long s0 = t * kZOrdTile;
+            const float2* gs = Gt + (size_t)buf * kZOrdTile * kZOrdGS + warp;
+            const uchar2* as = At + (size_t)buf * kZOrdTile * kZOrdAS + warp;
 #pragma unroll
-        for (int p = 0; p < kZOrdPF; ++p) {
-            const long b = s0 + (long)p * 32;
-            if (b < M) {                                     // warp-uniform
-                const float2 g = gq[p];
-                const uchar2 a = aq[p];
-                const long sn = b + 32 * kZOrdPF + lane;     // refill this slot: in flight while the next batches are folded
-                if (sn < M) { gq[p] = __ldg(Gc + sn * (long)ldg); aq[p] = __ldg(Ac + sn * (long)ldg); }
-                ztally_ord_batch(g, a, b + lane < M, lane, cell, mine, ndeep);
+            for (int p = 0; p < kZOrdTile / 32; ++p) {
+                const long b = s0 + p * 32;
+                if (b < M) {                                 // warp-uniform
+                    const int row = p * 32 + lane;
+                    const bool valid = b + lane < M;
+                    const float2 g = valid ? gs[row * kZOrdGS] : make_float2(0.f, 0.f);
+                    const uchar2 a = valid ? as[row * kZOrdAS] : make_uchar2(0, 0);
+                    ztally_ord_batch(g, a, valid, lane, cell, mine, ndeep);
+                }
             }
         }
+        __syncthreads();                                    // everyone is done with tile t before its buffer is refilled
     }
-    for (int c = lane; c < kZSeqHot; c += 32) {
-        const float4 v = cell[c];
-        ZTallyF t; t.s0 = v.x; t.s1 = v.y; t.s2 = v.z; t.cnt = __float_as_int(v.w);
-        mine[c] = t;
+    cp_async_wait<0>();
+    if (on) {
+        for (int c = lane; c < kZSeqHot; c += 32) {
+            const float4 v = cell[c];
+            ZTallyF tt; tt.s0 = v.x; tt.s1 = v.y; tt.s2 = v.z; tt.cnt = __float_as_int(v.w);
+            mine[c] = tt;
+        }
+        if (lane == 0 && ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
     }
-    if (lane == 0 && ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
 }
 
 // Deepest read depth with a non-empty class in the tally table: the host then moves and scans only the
