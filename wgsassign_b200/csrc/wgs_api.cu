@@ -126,6 +126,7 @@ const char* const kOptionNames[] = {
     "loo_by_pop",         // 1: leave-one-out EM population by population (one packed-row buffer at a time); -1: never
     "loo_variant",        // inner-loop variant of the packed leave-one-out step kernel (experiments)
     "upload_sync",        // 1: wgs_upload_gl_async falls back to the chunked synchronous upload
+    "ztally_groups",      // column groups of the rank-chained class tally (default 8)
     "z_exact_means",      // 1: order-independent fixed-point class means (NOT the reference's float32 means)
     "rmse_exact",         // 0: stop rule on the float64 sum only (no sequential float32 tie-break)
     "rmse_band_ppm",      // half-width of the tie-break band around the tolerance, parts per million of the RMSE (0 = automatic)
@@ -2242,23 +2243,37 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
                c.wx, c.sites_per_block, dtable.as<ZTally>(), ddeep.as<unsigned long long>());
         LAUNCH("zaux", zmaxdepth_kernel<ZTally>, ctx->num_sm * 4, 256, 0, ctx->stream, dtable.as<ZTally>(), (long)tab_n, dmaxd.as<int>());
     } else {
-        const size_t tbytes = tab_n * sizeof(ZTallyF);
-        CU(cudaFuncSetAttribute(ztally_ord_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZOrdSmem));
-        auto run_seq = [&]() -> int {
-            LAUNCH("ztally", ztally_ord_kernel, (ldg + kZOrdWarps - 1) / kZOrdWarps, kZOrdWarps * 32, kZOrdSmem, ctx->stream, ctx->G[0], ctx->AD, ldg, M,
-                   dsel.as<unsigned char>(), dtable.as<ZTallyF>(), ddeep.as<unsigned long long>());
+        // Column groups: a launch covers the blocks of one group; under sharding the groups pipeline through the ranks
+        // (rank r works on group g while rank r+1 works on group g-1), so the chain costs (W + G - 1) / G tallies
+        // instead of W.
+        const int nblk = (ldg + kZOrdWarps - 1) / kZOrdWarps;
+        const bool sharded_nccl = sharded && ctx->nccl_comm;
+        const int ngroups = sharded_nccl ? std::max(1, std::min(opt(ctx, "ztally_groups", 8), nblk)) : 1;
+        auto run_group = [&](int g) -> int {
+            const int b0 = (int)((long)nblk * g / ngroups), b1 = (int)((long)nblk * (g + 1) / ngroups);
+            if (b1 <= b0) return 0;
+            LAUNCH("ztally", ztally_ord_kernel, b1 - b0, kZOrdWarps * 32, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M,
+                   dsel.as<unsigned char>(), b0 * kZOrdWarps, std::min(ldg, b1 * kZOrdWarps), dtable.as<ZTallyF>(), ddeep.as<unsigned long long>());
             return 0;
         };
+        const size_t tbytes = tab_n * sizeof(ZTallyF);
         if (!sharded) {
-            if (run_seq()) return 1;
+            if (run_group(0)) return 1;
         } else if (ctx->nccl_comm) {
-            // rank r: receive the table from r-1, add this rank's sites, send it on; the last rank's table is the
-            // whole file's and is broadcast back (everything on the compute stream, over NVLink)
+            // rank r: receive a group's table rows from r-1, add this rank's sites, send them on; the last rank's table is
+            // the whole file's and is broadcast back (everything on the compute stream, over NVLink)
             const int r = ctx->rank, W = ctx->world;
             int rc_ = 0;
-            if (r > 0) rc_ = g_nccl.Recv(dtable.p, tbytes, kNcclChar, r - 1, ctx->nccl_comm, ctx->stream);
-            if (!rc_ && run_seq()) return 1;
-            if (!rc_ && r < W - 1) rc_ = g_nccl.Send(dtable.p, tbytes, kNcclChar, r + 1, ctx->nccl_comm, ctx->stream);
+            for (int g = 0; g < ngroups && !rc_; ++g) {
+                const int b0 = (int)((long)nblk * g / ngroups), b1 = (int)((long)nblk * (g + 1) / ngroups);
+                const size_t c_lo = (size_t)b0 * kZOrdWarps, c_hi = std::min<size_t>(ldg, (size_t)b1 * kZOrdWarps);
+                if (c_hi <= c_lo) continue;
+                char* slice = (char*)dtable.p + c_lo * kZClasses * sizeof(ZTallyF);
+                const size_t sbytes = (c_hi - c_lo) * kZClasses * sizeof(ZTallyF);
+                if (r > 0) rc_ = g_nccl.Recv(slice, sbytes, kNcclChar, r - 1, ctx->nccl_comm, ctx->stream);
+                if (!rc_ && run_group(g)) return 1;
+                if (!rc_ && r < W - 1) rc_ = g_nccl.Send(slice, sbytes, kNcclChar, r + 1, ctx->nccl_comm, ctx->stream);
+            }
             if (!rc_) rc_ = g_nccl.Broadcast(dtable.p, dtable.p, tbytes, kNcclChar, W - 1, ctx->nccl_comm, ctx->stream);
             if (rc_) return fail(ctx, "NCCL table hand-over failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc_) : "?");
         } else {
@@ -2267,7 +2282,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
             std::vector<long long> h(tbytes / 8);
             for (int q = 0; q < ctx->world; ++q) {
                 if (q == ctx->rank) {
-                    if (run_seq()) return 1;
+                    if (run_group(0)) return 1;
                     CU(cudaMemcpyAsync(h.data(), dtable.p, tbytes, cudaMemcpyDeviceToHost, ctx->stream));
                     CU(cudaStreamSynchronize(ctx->stream));
                 } else std::fill(h.begin(), h.end(), 0LL);

@@ -139,104 +139,78 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
 // Reproducing its bits needs its order - but only WITHIN a class: sums of different classes, components and
 // individuals are independent chains.
 //
-//  * One WARP = one individual, lane = site: a batch of 32 consecutive sites is classified at once, lanes of the
-//    same (ref, alt) class find each other with MATCH.ANY, and the class's running sum is handed from member to
-//    member in lane (= site) order with shuffles - as many rounds as the most frequent class has members in the
-//    batch (~10 of 32 at 2x).  ~4.5 warp instructions per site, and N warps instead of N / 32: the first version
-//    (one thread per individual walking the sites) had a dependent shared-memory round trip per site and N / 32
-//    warps on the whole GPU - 100 ns per site, 3 % of HBM.
-//  * The accumulators of all classes up to depth 9 (55 classes: > 99.9 % of the sites at 2x) live in the warp's
-//    shared-memory cells {s0, s1, s2, count}; deeper classes are read-modify-written in the individual's own table
-//    row (nobody else touches it).
-//  * A block = 8 adjacent individuals: their 8-byte GL pairs of a site are 64 contiguous bytes, so the strided
-//    per-lane loads of the 8 warps hit the same sectors (L1), and 4 batches per warp are in flight.
+//  * One WARP = one individual, LANE = CLASS: lane c keeps the running sums {s0, s1, s2, count} of classes c and
+//    c + 32 in registers (the 64 classes cover every depth up to 9 and most of 10; > 99.99 % of the sites at 2x).
+//    A batch of 32 consecutive sites is laid out in the warp's shared-memory strip as {g0, g1, g2, class} and every
+//    lane walks it IN SITE ORDER with broadcast LDS.128s, adding a site when it is of its class: ~6 instructions per
+//    site and warp, no dependent shared-memory round trip, no cross-lane hand-over - the additions of a class are
+//    the only dependent chain.  Batches without a class >= 32 (91 % at 2x) take a loop with one compare per site.
+//    (First version: one thread per individual walking the sites - a shared-memory read-modify-write per site on
+//    N / 32 warps: 100 ns per site, 3 % of HBM.  Second: MATCH.ANY + leader chains: 30 ns per site.)
+//  * Deeper classes are read-modify-written in the individual's own table row by lane 0, in site order.
+//  * A block = kZOrdWarps adjacent individuals: their rows of a site tile arrive with coalesced 16-byte / 8-byte LDGSTS
+//    copies, double-buffered.
 //  * The table is read as the CARRY-IN state and left as the carry-out: under site sharding the ranks run this
 //    kernel one after the other in site order and hand the table on (wgs_zscore: ncclSend / ncclRecv over NVLink,
 //    16 bytes per (individual, class)), so the order of every addition is the reference's over the whole file.
+//    [col_lo, col_hi) restricts a launch to a column group: the groups pipeline through the ranks.
 // ---------------------------------------------------------------------------------------
 struct ZTallyF { float s0, s1, s2; int cnt; };
-constexpr int kZSeqHotDepth = 9;
-constexpr int kZSeqHot = (kZSeqHotDepth + 1) * (kZSeqHotDepth + 2) / 2;  // 55
-constexpr int kZOrdWarps = 16;                                           // individuals per block: 128-byte GL rows, one sector of depths
+constexpr int kZOrdWarps = 4;                                            // individuals per block: 32-byte GL rows = one sector
 constexpr int kZOrdTile = 128;                                           // sites per staged tile (4 batches of 32)
-constexpr int kZOrdGS = 18;                                              // tile row strides (float2 / uchar2 units): 16-byte aligned rows whose
-constexpr int kZOrdAS = 20;                                              //   column reads (lane = row) spread over the banks
-constexpr size_t kZOrdSmem = (size_t)kZOrdWarps * kZSeqHot * sizeof(float4) + 2 * (size_t)kZOrdTile * (kZOrdGS * sizeof(float2) + kZOrdAS * sizeof(uchar2));
+constexpr int kZOrdGS = 6;                                               // tile row strides (float2 / uchar2 units): 16- / 8-byte aligned rows
+constexpr int kZOrdAS = 4;
+constexpr int kZOrdLaneClasses = 64;
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem));
 }
 
-// One batch = 32 consecutive sites of one individual (lane = site).  The LEADER of a class (its first member in the
-// batch) reads the class's running sums and adds its members' GLs in lane (= site) order, fetching them with
-// shuffles whose sources do not depend on the running sum: the only dependent chain is the float32 additions
-// themselves.  The trip count is the size of the largest class in the batch (warp-uniform).
-__device__ __forceinline__ void ztally_ord_batch(float2 g, uchar2 a, bool valid, int lane, float4* __restrict__ cell,
-                                                 ZTallyF* __restrict__ mine, int& ndeep)
+template <int H>
+__device__ __forceinline__ void ztally_ord_fold(const float4* __restrict__ wb, int lane, float (&a0)[2], float (&a1)[2], float (&a2)[2], int (&n)[2])
 {
-    const int d = a.x + a.y;
-    const int code = d * (d + 1) / 2 + a.y;
-    const bool deepf = valid && d > kZDepthCap;
-    const bool act = valid && !deepf;
-    ndeep += __popc(__ballot_sync(0xffffffffu, deepf));      // same value in every lane; lane 0 reports it
-    const unsigned peers = __match_any_sync(0xffffffffu, act ? code : -1 - lane);   // lanes of the same class (inactive lanes: alone)
-    const bool leader = act && (peers & ((1u << lane) - 1u)) == 0u;
-    const int maxn = __reduce_max_sync(0xffffffffu, act ? __popc(peers) : 0);
-    const bool hot = d <= kZSeqHotDepth;
-    const float g2 = third_gl_np(g.x, g.y);
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    int cnt = 0;
-    if (leader) {
-        if (hot) { const float4 c = cell[code]; v0 = c.x; v1 = c.y; v2 = c.z; cnt = __float_as_int(c.w); }
-        else { const ZTallyF t = mine[code]; v0 = t.s0; v1 = t.s1; v2 = t.s2; cnt = t.cnt; }
-        v0 = __fadd_rn(v0, g.x); v1 = __fadd_rn(v1, g.y); v2 = __fadd_rn(v2, g2);
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {                           // site order
+        const float4 v = wb[s];                              // broadcast: every lane reads the same 16 bytes
+        const int c = __float_as_int(v.w);
+        if (c == lane) { a0[0] = __fadd_rn(a0[0], v.x); a1[0] = __fadd_rn(a1[0], v.y); a2[0] = __fadd_rn(a2[0], v.z); ++n[0]; }
+        if (H == 2 && c == lane + 32) { a0[1] = __fadd_rn(a0[1], v.x); a1[1] = __fadd_rn(a1[1], v.y); a2[1] = __fadd_rn(a2[1], v.z); ++n[1]; }
     }
-    unsigned rem = leader ? (peers & (peers - 1u)) : 0u;     // the members after the leader
-    for (int r = 1; r < maxn; ++r) {                         // warp-uniform trip count
-        const int src = rem ? __ffs(rem) - 1 : lane;
-        const float t0 = __shfl_sync(0xffffffffu, g.x, src), t1 = __shfl_sync(0xffffffffu, g.y, src), t2 = __shfl_sync(0xffffffffu, g2, src);
-        if (rem) { v0 = __fadd_rn(v0, t0); v1 = __fadd_rn(v1, t1); v2 = __fadd_rn(v2, t2); }
-        rem &= rem - 1u;
-    }
-    if (leader) {
-        cnt += __popc(peers);
-        if (hot) cell[code] = make_float4(v0, v1, v2, __int_as_float(cnt));
-        else { ZTallyF t; t.s0 = v0; t.s1 = v1; t.s2 = v2; t.cnt = cnt; mine[code] = t; }
-    }
-    __syncwarp();                                            // the cells are read by other lanes in the next batch
 }
 
 __global__ void __launch_bounds__(kZOrdWarps * 32)
 ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int ldg, long M,
-                  const unsigned char* __restrict__ sel,
+                  const unsigned char* __restrict__ sel, int col_lo, int col_hi,
                   ZTallyF* __restrict__ table,             // [ldg][kZClasses]: carry-in, updated in place
                   unsigned long long* __restrict__ deep)
 {
-    extern __shared__ __align__(16) unsigned char zs_raw[];
-    float4* cells = reinterpret_cast<float4*>(zs_raw);                                        // [warps][kZSeqHot]
-    float2* Gt = reinterpret_cast<float2*>(cells + kZOrdWarps * kZSeqHot);                    // [2][tile][kZOrdGS]
-    uchar2* At = reinterpret_cast<uchar2*>(Gt + 2 * kZOrdTile * kZOrdGS);                     // [2][tile][kZOrdAS]
+    __shared__ __align__(16) float4 wbuf[kZOrdWarps][32];
+    __shared__ __align__(16) float2 Gt[2][kZOrdTile][kZOrdGS];
+    __shared__ __align__(16) uchar2 At[2][kZOrdTile][kZOrdAS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int col0 = blockIdx.x * kZOrdWarps;
-    const int ncols = min(kZOrdWarps, ldg - col0);           // a multiple of 4: slabs are padded to 4 individuals
+    const int col0 = col_lo + blockIdx.x * kZOrdWarps;
+    const int ncols = min(kZOrdWarps, col_hi - col0);        // a multiple of 4: slabs are padded to 4 individuals
     const int col = col0 + warp;
     const bool on = warp < ncols && sel[col];                // warp-uniform
-    float4* cell = cells + warp * kZSeqHot;
     ZTallyF* mine = table + (size_t)(warp < ncols ? col : col0) * kZClasses;
-    if (on) for (int c = lane; c < kZSeqHot; c += 32) { const ZTallyF t = mine[c]; cell[c] = make_float4(t.s0, t.s1, t.s2, __int_as_float(t.cnt)); }
+    float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f}, a2[2] = {0.f, 0.f};
+    int n[2] = {0, 0};
+    if (on) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { const ZTallyF t = mine[lane + 32 * h]; a0[h] = t.s0; a1[h] = t.s1; a2[h] = t.s2; n[h] = t.cnt; }
+    }
     const int gc = ncols >> 1, ac = ncols >> 2;             // 16-byte GL chunks / 8-byte depth chunks per site row
     auto stage = [&](long t, int buf) {                      // the block's columns of sites [128 t, 128 t + 128): coalesced rows
         const long s0 = t * kZOrdTile;
         const int rows = (int)max(0L, min((long)kZOrdTile, M - s0));
-        float2* gd = Gt + (size_t)buf * kZOrdTile * kZOrdGS;
-        uchar2* ad = At + (size_t)buf * kZOrdTile * kZOrdAS;
-        for (int e = tid; e < rows * gc; e += kZOrdWarps * 32) { const int r = e / gc, c = e - r * gc; cp_async16(gd + r * kZOrdGS + 2 * c, G + (s0 + r) * (long)ldg + col0 + 2 * c); }
-        for (int e = tid; e < rows * ac; e += kZOrdWarps * 32) { const int r = e / ac, c = e - r * ac; cp_async8(ad + r * kZOrdAS + 4 * c, AD + (s0 + r) * (long)ldg + col0 + 4 * c); }
+        for (int e = tid; e < rows * gc; e += kZOrdWarps * 32) { const int r = e / gc, c = e - r * gc; cp_async16(&Gt[buf][r][2 * c], G + (s0 + r) * (long)ldg + col0 + 2 * c); }
+        for (int e = tid; e < rows * ac; e += kZOrdWarps * 32) { const int r = e / ac, c = e - r * ac; cp_async8(&At[buf][r][4 * c], AD + (s0 + r) * (long)ldg + col0 + 4 * c); }
         cp_async_commit();                                  // always: the wait below counts groups
     };
     const long ntiles = (M + kZOrdTile - 1) / kZOrdTile;
     int ndeep = 0;
+    float4* wb = wbuf[warp];
     stage(0, 0);
     for (long t = 0; t < ntiles; ++t) {
         const int buf = (int)(t & 1);
@@ -245,29 +219,43 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
         __syncthreads();                                    // tile t complete, for every thread's copies
         if (on) {
             const long s0 = t * kZOrdTile;
-            const float2* gs = Gt + (size_t)buf * kZOrdTile * kZOrdGS + warp;
-            const uchar2* as = At + (size_t)buf * kZOrdTile * kZOrdAS + warp;
-#pragma unroll
+#pragma unroll 1
             for (int p = 0; p < kZOrdTile / 32; ++p) {
                 const long b = s0 + p * 32;
-                if (b < M) {                                 // warp-uniform
-                    const int row = p * 32 + lane;
-                    const bool valid = b + lane < M;
-                    const float2 g = valid ? gs[row * kZOrdGS] : make_float2(0.f, 0.f);
-                    const uchar2 a = valid ? as[row * kZOrdAS] : make_uchar2(0, 0);
-                    ztally_ord_batch(g, a, valid, lane, cell, mine, ndeep);
+                if (b >= M) break;                           // warp-uniform
+                const int row = p * 32 + lane;
+                const bool valid = b + lane < M;
+                const float2 g = valid ? Gt[buf][row][warp] : make_float2(0.f, 0.f);
+                const uchar2 a = valid ? At[buf][row][warp] : make_uchar2(0, 0);
+                const int d = a.x + a.y;
+                const bool deepf = valid && d > kZDepthCap;
+                const int code = (valid && !deepf) ? d * (d + 1) / 2 + a.y : -1;
+                wb[lane] = make_float4(g.x, g.y, third_gl_np(g.x, g.y), __int_as_float(code));
+                ndeep += __popc(__ballot_sync(0xffffffffu, deepf));          // same value in every lane; lane 0 reports it
+                const unsigned hi = __ballot_sync(0xffffffffu, code >= 32);
+                unsigned cold = __ballot_sync(0xffffffffu, code >= kZOrdLaneClasses);
+                __syncwarp();
+                if (hi == 0u) ztally_ord_fold<1>(wb, lane, a0, a1, a2, n);
+                else ztally_ord_fold<2>(wb, lane, a0, a1, a2, n);
+                if (cold && lane == 0) {                     // rare: deeper than the lanes' classes - in site order, in the table row
+                    while (cold) {
+                        const int s = __ffs(cold) - 1;
+                        cold &= cold - 1u;
+                        const float4 v = wb[s];
+                        ZTallyF tt = mine[__float_as_int(v.w)];
+                        tt.s0 = __fadd_rn(tt.s0, v.x); tt.s1 = __fadd_rn(tt.s1, v.y); tt.s2 = __fadd_rn(tt.s2, v.z); tt.cnt += 1;
+                        mine[__float_as_int(v.w)] = tt;
+                    }
                 }
+                __syncwarp();                                // everyone has read the strip before the next batch overwrites it
             }
         }
         __syncthreads();                                    // everyone is done with tile t before its buffer is refilled
     }
     cp_async_wait<0>();
     if (on) {
-        for (int c = lane; c < kZSeqHot; c += 32) {
-            const float4 v = cell[c];
-            ZTallyF tt; tt.s0 = v.x; tt.s1 = v.y; tt.s2 = v.z; tt.cnt = __float_as_int(v.w);
-            mine[c] = tt;
-        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { ZTallyF tt; tt.s0 = a0[h]; tt.s1 = a1[h]; tt.s2 = a2[h]; tt.cnt = n[h]; mine[lane + 32 * h] = tt; }
         if (lane == 0 && ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
     }
 }
