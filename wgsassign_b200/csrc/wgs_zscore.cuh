@@ -141,10 +141,11 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
 //
 //  * One WARP = one individual, LANE = CLASS: lane c keeps the running sums {s0, s1, s2, count} of classes c and
 //    c + 32 in registers (the 64 classes cover every depth up to 9 and most of 10; > 99.99 % of the sites at 2x).
-//    A batch of 32 consecutive sites is laid out in the warp's shared-memory strip as {g0, g1, g2, class} and every
-//    lane walks it IN SITE ORDER with broadcast LDS.128s, adding a site when it is of its class: ~6 instructions per
-//    site and warp, no dependent shared-memory round trip, no cross-lane hand-over - the additions of a class are
-//    the only dependent chain.  Batches without a class >= 32 (91 % at 2x) take a loop with one compare per site.
+//    A batch of 32 consecutive sites is laid out in the warp's shared-memory strip (class codes as bytes + GL
+//    triples) and every lane walks the codes IN SITE ORDER, loading and adding a site's triple only when it is of
+//    its class: ~7 instructions and ~1.25 shared-memory wavefronts per site and warp, no dependent shared-memory
+//    round trip, no cross-lane hand-over - the additions of a class are the only dependent chain.  Batches without
+//    a class >= 32 (91 % at 2x) take a loop with one compare per site.
 //    (First version: one thread per individual walking the sites - a shared-memory read-modify-write per site on
 //    N / 32 warps: 100 ns per site, 3 % of HBM.  Second: MATCH.ANY + leader chains: 30 ns per site.)
 //  * Deeper classes are read-modify-written in the individual's own table row by lane 0, in site order.
@@ -167,15 +168,21 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem));
 }
 
+// The strip of a batch: the 32 class codes as BYTES (two broadcast LDS.128 bring all of them into registers) and the
+// 32 {g0, g1, g2} triples, of which a lane loads only the ones of its own class (a one-lane LDS.128 = one wavefront).
+// A broadcast LDS.128 per site for every lane made the first lane-per-class version shared-memory bound (4 wavefronts
+// per site and warp: 14 ms per 500 k x 2,000 whatever else was done).
 template <int H>
-__device__ __forceinline__ void ztally_ord_fold(const float4* __restrict__ wb, int lane, float (&a0)[2], float (&a1)[2], float (&a2)[2], int (&n)[2])
+__device__ __forceinline__ void ztally_ord_fold(const uint4* __restrict__ cb, const float4* __restrict__ gv, int lane,
+                                                f32x2 (&a01)[2], float (&a2)[2], int (&n)[2])
 {
+    const uint4 c0 = cb[0], c1 = cb[1];
+    const unsigned w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
     for (int s = 0; s < 32; ++s) {                           // site order
-        const float4 v = wb[s];                              // broadcast: every lane reads the same 16 bytes
-        const int c = __float_as_int(v.w);
-        if (c == lane) { a0[0] = __fadd_rn(a0[0], v.x); a1[0] = __fadd_rn(a1[0], v.y); a2[0] = __fadd_rn(a2[0], v.z); ++n[0]; }
-        if (H == 2 && c == lane + 32) { a0[1] = __fadd_rn(a0[1], v.x); a1[1] = __fadd_rn(a1[1], v.y); a2[1] = __fadd_rn(a2[1], v.z); ++n[1]; }
+        const int c = (int)((w[s >> 2] >> (8 * (s & 3))) & 0xffu);
+        if (c == lane) { const float4 v = gv[s]; a01[0] = fadd2(a01[0], pack2(v.x, v.y)); a2[0] = __fadd_rn(a2[0], v.z); ++n[0]; }
+        if (H == 2 && c == lane + 32) { const float4 v = gv[s]; a01[1] = fadd2(a01[1], pack2(v.x, v.y)); a2[1] = __fadd_rn(a2[1], v.z); ++n[1]; }
     }
 }
 
@@ -185,7 +192,8 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
                   ZTallyF* __restrict__ table,             // [ldg][kZClasses]: carry-in, updated in place
                   unsigned long long* __restrict__ deep)
 {
-    __shared__ __align__(16) float4 wbuf[kZOrdWarps][32];
+    __shared__ __align__(16) float4 gbuf[kZOrdWarps][32];
+    __shared__ __align__(16) unsigned char cbuf[kZOrdWarps][32];
     __shared__ __align__(16) float2 Gt[2][kZOrdTile][kZOrdGS];
     __shared__ __align__(16) uchar2 At[2][kZOrdTile][kZOrdAS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -194,11 +202,12 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
     const int col = col0 + warp;
     const bool on = warp < ncols && sel[col];                // warp-uniform
     ZTallyF* mine = table + (size_t)(warp < ncols ? col : col0) * kZClasses;
-    float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f}, a2[2] = {0.f, 0.f};
+    f32x2 a01[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
+    float a2[2] = {0.f, 0.f};
     int n[2] = {0, 0};
     if (on) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) { const ZTallyF t = mine[lane + 32 * h]; a0[h] = t.s0; a1[h] = t.s1; a2[h] = t.s2; n[h] = t.cnt; }
+        for (int h = 0; h < 2; ++h) { const ZTallyF t = mine[lane + 32 * h]; a01[h] = pack2(t.s0, t.s1); a2[h] = t.s2; n[h] = t.cnt; }
     }
     const int gc = ncols >> 1, ac = ncols >> 2;             // 16-byte GL chunks / 8-byte depth chunks per site row
     auto stage = [&](long t, int buf) {                      // the block's columns of sites [128 t, 128 t + 128): coalesced rows
@@ -210,7 +219,8 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
     };
     const long ntiles = (M + kZOrdTile - 1) / kZOrdTile;
     int ndeep = 0;
-    float4* wb = wbuf[warp];
+    float4* gv = gbuf[warp];
+    unsigned char* cb = cbuf[warp];
     stage(0, 0);
     for (long t = 0; t < ntiles; ++t) {
         const int buf = (int)(t & 1);
@@ -230,18 +240,19 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
                 const int d = a.x + a.y;
                 const bool deepf = valid && d > kZDepthCap;
                 const int code = (valid && !deepf) ? d * (d + 1) / 2 + a.y : -1;
-                wb[lane] = make_float4(g.x, g.y, third_gl_np(g.x, g.y), __int_as_float(code));
+                gv[lane] = make_float4(g.x, g.y, third_gl_np(g.x, g.y), __int_as_float(code));
+                cb[lane] = (unsigned char)((code >= 0 && code < kZOrdLaneClasses) ? code : 255);
                 ndeep += __popc(__ballot_sync(0xffffffffu, deepf));          // same value in every lane; lane 0 reports it
-                const unsigned hi = __ballot_sync(0xffffffffu, code >= 32);
+                const unsigned hi = __ballot_sync(0xffffffffu, code >= 32 && code < kZOrdLaneClasses);
                 unsigned cold = __ballot_sync(0xffffffffu, code >= kZOrdLaneClasses);
                 __syncwarp();
-                if (hi == 0u) ztally_ord_fold<1>(wb, lane, a0, a1, a2, n);
-                else ztally_ord_fold<2>(wb, lane, a0, a1, a2, n);
+                if (hi == 0u) ztally_ord_fold<1>(reinterpret_cast<const uint4*>(cb), gv, lane, a01, a2, n);
+                else ztally_ord_fold<2>(reinterpret_cast<const uint4*>(cb), gv, lane, a01, a2, n);
                 if (cold && lane == 0) {                     // rare: deeper than the lanes' classes - in site order, in the table row
                     while (cold) {
                         const int s = __ffs(cold) - 1;
                         cold &= cold - 1u;
-                        const float4 v = wb[s];
+                        const float4 v = gv[s];
                         ZTallyF tt = mine[__float_as_int(v.w)];
                         tt.s0 = __fadd_rn(tt.s0, v.x); tt.s1 = __fadd_rn(tt.s1, v.y); tt.s2 = __fadd_rn(tt.s2, v.z); tt.cnt += 1;
                         mine[__float_as_int(v.w)] = tt;
@@ -255,7 +266,7 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
     cp_async_wait<0>();
     if (on) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) { ZTallyF tt; tt.s0 = a0[h]; tt.s1 = a1[h]; tt.s2 = a2[h]; tt.cnt = n[h]; mine[lane + 32 * h] = tt; }
+        for (int h = 0; h < 2; ++h) { const float2 v = unpack2(a01[h]); ZTallyF tt; tt.s0 = v.x; tt.s1 = v.y; tt.s2 = a2[h]; tt.cnt = n[h]; mine[lane + 32 * h] = tt; }
         if (lane == 0 && ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
     }
 }
