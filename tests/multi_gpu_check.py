@@ -106,6 +106,7 @@ def main():
         pl1 = one.pop_like_partial(af1)
         f1, ne1, ind1 = one.fisher_partial(af1)
         zr1 = one.zscore(1, None, 0, False, 0, 12, 200, 1e-4)
+        zr1_cls = [one.zscore_classes(i) for i in range(0, 12)]
         za1 = one.zscore(0, af1, 0, False, 5, 20, 200, 1e-4)
 
         one2 = _lib.Context(local)
@@ -142,7 +143,7 @@ def main():
             "host-callback path == nccl path": host_same,
             "z ref == oracle": z_vs_oracle(zr, zr_cls, zr_o) and [r.em_iters for r in zr] == [o["em_iter"] for o in zr_o],
             "z asg == oracle": z_vs_oracle(za, za_cls, za_o),
-            "z 1gpu == oracle": z_vs_oracle(zr1, [one.zscore_classes(i) for i in range(0, 12)], zr_o),
+            "z 1gpu == oracle": z_vs_oracle(zr1, zr1_cls, zr_o),
             "fused iters": list(fits) == list(gits) and list(flits) == list(glits),
             "fused af bitwise": np.array_equal(faf_full, gaf),
             "fused ll": rel(fll, gll) < 1e-7,

@@ -157,7 +157,7 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
 //    [col_lo, col_hi) restricts a launch to a column group: the groups pipeline through the ranks.
 // ---------------------------------------------------------------------------------------
 struct ZTallyF { float s0, s1, s2; int cnt; };
-constexpr int kZOrdWarps = 4;                                            // individuals per block: 32-byte GL rows = one sector
+constexpr int kZOrdWarps = 4;                                            // individuals per block: 32-byte GL rows = one sector (the staging code relies on 4)
 constexpr int kZOrdTile = 128;                                           // sites per staged tile (4 batches of 32)
 constexpr int kZOrdGS = 6;                                               // tile row strides (float2 / uchar2 units): 16- / 8-byte aligned rows
 constexpr int kZOrdAS = 4;
@@ -178,11 +178,24 @@ __device__ __forceinline__ void ztally_ord_fold(const uint4* __restrict__ cb, co
 {
     const uint4 c0 = cb[0], c1 = cb[1];
     const unsigned w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    // eight sites at a time: all (predicated) triple loads first, then the additions - the shared-memory latency is
+    // paid once per eight sites even by a warp that has a scheduler to itself (the column groups of a sharded run)
 #pragma unroll
-    for (int s = 0; s < 32; ++s) {                           // site order
-        const int c = (int)((w[s >> 2] >> (8 * (s & 3))) & 0xffu);
-        if (c == lane) { const float4 v = gv[s]; a01[0] = fadd2(a01[0], pack2(v.x, v.y)); a2[0] = __fadd_rn(a2[0], v.z); ++n[0]; }
-        if (H == 2 && c == lane + 32) { const float4 v = gv[s]; a01[1] = fadd2(a01[1], pack2(v.x, v.y)); a2[1] = __fadd_rn(a2[1], v.z); ++n[1]; }
+    for (int s0 = 0; s0 < 32; s0 += 8) {
+        float4 v[8];
+        int c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int s = s0 + j;
+            c[j] = (int)__byte_perm(w[s >> 2], 0u, 0x4440u + (unsigned)(s & 3));
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c[j] == lane || (H == 2 && c[j] == lane + 32)) v[j] = gv[s];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                       // site order
+            if (c[j] == lane) { a01[0] = fadd2(a01[0], pack2(v[j].x, v[j].y)); a2[0] = __fadd_rn(a2[0], v[j].z); ++n[0]; }
+            if (H == 2 && c[j] == lane + 32) { a01[1] = fadd2(a01[1], pack2(v[j].x, v[j].y)); a2[1] = __fadd_rn(a2[1], v[j].z); ++n[1]; }
+        }
     }
 }
 
@@ -209,12 +222,13 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
 #pragma unroll
         for (int h = 0; h < 2; ++h) { const ZTallyF t = mine[lane + 32 * h]; a01[h] = pack2(t.s0, t.s1); a2[h] = t.s2; n[h] = t.cnt; }
     }
-    const int gc = ncols >> 1, ac = ncols >> 2;             // 16-byte GL chunks / 8-byte depth chunks per site row
-    auto stage = [&](long t, int buf) {                      // the block's columns of sites [128 t, 128 t + 128): coalesced rows
+    // the block's 4 columns of sites [128 t, 128 t + 128): per row two 16-byte GL chunks and one 8-byte depth chunk
+    // (ldg is a multiple of 4 and col0 of kZOrdWarps = 4: every block has exactly 4 columns, all chunks aligned)
+    auto stage = [&](long t, int buf) {
         const long s0 = t * kZOrdTile;
         const int rows = (int)max(0L, min((long)kZOrdTile, M - s0));
-        for (int e = tid; e < rows * gc; e += kZOrdWarps * 32) { const int r = e / gc, c = e - r * gc; cp_async16(&Gt[buf][r][2 * c], G + (s0 + r) * (long)ldg + col0 + 2 * c); }
-        for (int e = tid; e < rows * ac; e += kZOrdWarps * 32) { const int r = e / ac, c = e - r * ac; cp_async8(&At[buf][r][4 * c], AD + (s0 + r) * (long)ldg + col0 + 4 * c); }
+        for (int e = tid; e < rows * 2; e += kZOrdWarps * 32) { const int r = e >> 1, c = e & 1; cp_async16(&Gt[buf][r][2 * c], G + (s0 + r) * (long)ldg + col0 + 2 * c); }
+        for (int r = tid; r < rows; r += kZOrdWarps * 32) cp_async8(&At[buf][r][0], AD + (s0 + r) * (long)ldg + col0);
         cp_async_commit();                                  // always: the wait below counts groups
     };
     const long ntiles = (M + kZOrdTile - 1) / kZOrdTile;
