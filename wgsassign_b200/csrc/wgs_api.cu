@@ -2247,12 +2247,13 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         // (rank r works on group g while rank r+1 works on group g-1), so the chain costs (W + G - 1) / G tallies
         // instead of W.
         const int nblk = (ldg + kZOrdWarps - 1) / kZOrdWarps;
+        CU(cudaFuncSetAttribute(ztally_ord_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZOrdSmem));
         const bool sharded_nccl = sharded && ctx->nccl_comm;
         const int ngroups = sharded_nccl ? std::max(1, std::min(opt(ctx, "ztally_groups", 8), nblk)) : 1;
         auto run_group = [&](int g) -> int {
             const int b0 = (int)((long)nblk * g / ngroups), b1 = (int)((long)nblk * (g + 1) / ngroups);
             if (b1 <= b0) return 0;
-            LAUNCH("ztally", ztally_ord_kernel, b1 - b0, kZOrdWarps * 32, 0, ctx->stream, ctx->G[0], ctx->AD, ldg, M,
+            LAUNCH("ztally", ztally_ord_kernel, b1 - b0, kZOrdWarps * 32, kZOrdSmem, ctx->stream, ctx->G[0], ctx->AD, ldg, M,
                    dsel.as<unsigned char>(), b0 * kZOrdWarps, std::min(ldg, b1 * kZOrdWarps), dtable.as<ZTallyF>(), ddeep.as<unsigned long long>());
             return 0;
         };

@@ -157,10 +157,14 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
 //    [col_lo, col_hi) restricts a launch to a column group: the groups pipeline through the ranks.
 // ---------------------------------------------------------------------------------------
 struct ZTallyF { float s0, s1, s2; int cnt; };
-constexpr int kZOrdWarps = 4;                                            // individuals per block: 32-byte GL rows = one sector (the staging code relies on 4)
+constexpr int kZOrdWarps = 16;                                           // individuals per block: 128-byte GL rows (one line), 32 bytes of depths
 constexpr int kZOrdTile = 128;                                           // sites per staged tile (4 batches of 32)
-constexpr int kZOrdGS = 6;                                               // tile row strides (float2 / uchar2 units): 16- / 8-byte aligned rows
-constexpr int kZOrdAS = 4;
+constexpr int kZOrdStages = 4;                                           // ring depth: 3 tiles (60 KB) in flight per block - with two, the pass ran at
+                                                                         //   0.55 TB/s whatever the arithmetic: bytes in flight, not instructions
+constexpr int kZOrdGS = 18;                                              // tile row strides (float2 / uchar2 units): 16- / 8-byte aligned rows whose
+constexpr int kZOrdAS = 20;                                              //   column reads (lane = row) spread over the banks
+constexpr size_t kZOrdSmem = (size_t)kZOrdWarps * 32 * (sizeof(float4) + 1) +
+                             (size_t)kZOrdStages * kZOrdTile * (kZOrdGS * sizeof(float2) + kZOrdAS * sizeof(uchar2));
 constexpr int kZOrdLaneClasses = 64;
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
@@ -205,10 +209,11 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
                   ZTallyF* __restrict__ table,             // [ldg][kZClasses]: carry-in, updated in place
                   unsigned long long* __restrict__ deep)
 {
-    __shared__ __align__(16) float4 gbuf[kZOrdWarps][32];
-    __shared__ __align__(16) unsigned char cbuf[kZOrdWarps][32];
-    __shared__ __align__(16) float2 Gt[2][kZOrdTile][kZOrdGS];
-    __shared__ __align__(16) uchar2 At[2][kZOrdTile][kZOrdAS];
+    extern __shared__ __align__(16) unsigned char zs_raw[];
+    float4* gbuf = reinterpret_cast<float4*>(zs_raw);                                          // [warps][32] GL triples of a batch
+    float2* Gt = reinterpret_cast<float2*>(gbuf + kZOrdWarps * 32);                            // [stages][tile][kZOrdGS]
+    uchar2* At = reinterpret_cast<uchar2*>(Gt + (size_t)kZOrdStages * kZOrdTile * kZOrdGS);    // [stages][tile][kZOrdAS]
+    unsigned char* cbuf = reinterpret_cast<unsigned char*>(At + (size_t)kZOrdStages * kZOrdTile * kZOrdAS);   // [warps][32] class codes
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = col_lo + blockIdx.x * kZOrdWarps;
     const int ncols = min(kZOrdWarps, col_hi - col0);        // a multiple of 4: slabs are padded to 4 individuals
@@ -222,24 +227,32 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
 #pragma unroll
         for (int h = 0; h < 2; ++h) { const ZTallyF t = mine[lane + 32 * h]; a01[h] = pack2(t.s0, t.s1); a2[h] = t.s2; n[h] = t.cnt; }
     }
-    // the block's 4 columns of sites [128 t, 128 t + 128): per row two 16-byte GL chunks and one 8-byte depth chunk
-    // (ldg is a multiple of 4 and col0 of kZOrdWarps = 4: every block has exactly 4 columns, all chunks aligned)
-    auto stage = [&](long t, int buf) {
+    // the block's columns of sites [128 t, 128 t + 128): coalesced rows, 16-byte GL chunks and 8-byte depth chunks
+    const int gc = ncols >> 1, ac = ncols >> 2;
+    auto stage = [&](long t) {
+        const int buf = (int)(t % kZOrdStages);
         const long s0 = t * kZOrdTile;
         const int rows = (int)max(0L, min((long)kZOrdTile, M - s0));
-        for (int e = tid; e < rows * 2; e += kZOrdWarps * 32) { const int r = e >> 1, c = e & 1; cp_async16(&Gt[buf][r][2 * c], G + (s0 + r) * (long)ldg + col0 + 2 * c); }
-        for (int r = tid; r < rows; r += kZOrdWarps * 32) cp_async8(&At[buf][r][0], AD + (s0 + r) * (long)ldg + col0);
+        float2* gd = Gt + (size_t)buf * kZOrdTile * kZOrdGS;
+        uchar2* ad = At + (size_t)buf * kZOrdTile * kZOrdAS;
+        if (ncols == kZOrdWarps) {
+            for (int e = tid; e < rows * 8; e += kZOrdWarps * 32) { const int r = e >> 3, c = e & 7; cp_async16(gd + r * kZOrdGS + 2 * c, G + (s0 + r) * (long)ldg + col0 + 2 * c); }
+            for (int e = tid; e < rows * 4; e += kZOrdWarps * 32) { const int r = e >> 2, c = e & 3; cp_async8(ad + r * kZOrdAS + 4 * c, AD + (s0 + r) * (long)ldg + col0 + 4 * c); }
+        } else {
+            for (int e = tid; e < rows * gc; e += kZOrdWarps * 32) { const int r = e / gc, c = e - r * gc; cp_async16(gd + r * kZOrdGS + 2 * c, G + (s0 + r) * (long)ldg + col0 + 2 * c); }
+            for (int e = tid; e < rows * ac; e += kZOrdWarps * 32) { const int r = e / ac, c = e - r * ac; cp_async8(ad + r * kZOrdAS + 4 * c, AD + (s0 + r) * (long)ldg + col0 + 4 * c); }
+        }
         cp_async_commit();                                  // always: the wait below counts groups
     };
     const long ntiles = (M + kZOrdTile - 1) / kZOrdTile;
     int ndeep = 0;
-    float4* gv = gbuf[warp];
-    unsigned char* cb = cbuf[warp];
-    stage(0, 0);
+    float4* gv = gbuf + warp * 32;
+    unsigned char* cb = cbuf + warp * 32;
+    for (int p = 0; p < kZOrdStages - 1; ++p) stage(p);
     for (long t = 0; t < ntiles; ++t) {
-        const int buf = (int)(t & 1);
-        stage(t + 1, buf ^ 1);                              // its buffer was released by the barrier that ended tile t-1
-        cp_async_wait<1>();
+        const int buf = (int)(t % kZOrdStages);
+        stage(t + kZOrdStages - 1);                         // into the slot tile t-1 used: released by the barrier that ended it
+        cp_async_wait<kZOrdStages - 1>();
         __syncthreads();                                    // tile t complete, for every thread's copies
         if (on) {
             const long s0 = t * kZOrdTile;
@@ -249,8 +262,8 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
                 if (b >= M) break;                           // warp-uniform
                 const int row = p * 32 + lane;
                 const bool valid = b + lane < M;
-                const float2 g = valid ? Gt[buf][row][warp] : make_float2(0.f, 0.f);
-                const uchar2 a = valid ? At[buf][row][warp] : make_uchar2(0, 0);
+                const float2 g = valid ? Gt[((size_t)buf * kZOrdTile + row) * kZOrdGS + warp] : make_float2(0.f, 0.f);
+                const uchar2 a = valid ? At[((size_t)buf * kZOrdTile + row) * kZOrdAS + warp] : make_uchar2(0, 0);
                 const int d = a.x + a.y;
                 const bool deepf = valid && d > kZDepthCap;
                 const int code = (valid && !deepf) ? d * (d + 1) / 2 + a.y : -1;
