@@ -163,44 +163,58 @@ constexpr int kZOrdStages = 4;                                           // ring
                                                                          //   0.55 TB/s whatever the arithmetic: bytes in flight, not instructions
 constexpr int kZOrdGS = 18;                                              // tile row strides (float2 / uchar2 units): 16- / 8-byte aligned rows whose
 constexpr int kZOrdAS = 20;                                              //   column reads (lane = row) spread over the banks
-constexpr size_t kZOrdSmem = (size_t)kZOrdWarps * 32 * (sizeof(float4) + 1) +
+constexpr int kZOrdCellsDecl = 66;
+constexpr size_t kZOrdSmem = (size_t)kZOrdWarps * (32 + kZOrdCellsDecl) * sizeof(float4) +
                              (size_t)kZOrdStages * kZOrdTile * (kZOrdGS * sizeof(float2) + kZOrdAS * sizeof(uchar2));
-constexpr int kZOrdLaneClasses = 64;
+constexpr int kZOrdCells = 66;                                           // classes with shared-memory cells: every depth up to 10
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmem));
 }
 
-// The strip of a batch: the 32 class codes as BYTES (two broadcast LDS.128 bring all of them into registers) and the
-// 32 {g0, g1, g2} triples, of which a lane loads only the ones of its own class (a one-lane LDS.128 = one wavefront).
-// A broadcast LDS.128 per site for every lane made the first lane-per-class version shared-memory bound (4 wavefronts
-// per site and warp: 14 ms per 500 k x 2,000 whatever else was done).
-template <int H>
-__device__ __forceinline__ void ztally_ord_fold(const uint4* __restrict__ cb, const float4* __restrict__ gv, int lane,
-                                                f32x2 (&a01)[2], float (&a2)[2], int (&n)[2])
+// One batch = 32 consecutive sites of one individual, lane = site.  Lanes of the same (ref, alt) class find each other
+// with MATCH.ANY; the class's first member (the LEADER) reads the class's running sums from the warp's cells and adds
+// the members' GL triples in lane (= site) order, reading them from the warp's strip - the only dependent chain is the
+// float32 additions themselves.  The trip count is the size of the largest class in the batch (warp-uniform, ~10 of 32
+// at 2x): ~4 warp instructions per site.
+__device__ __forceinline__ void ztally_ord_batch(float2 g, uchar2 a, bool valid, int lane, float4* __restrict__ strip,
+                                                 float4* __restrict__ cell, ZTallyF* __restrict__ mine, int& ndeep)
 {
-    const uint4 c0 = cb[0], c1 = cb[1];
-    const unsigned w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    // eight sites at a time: all (predicated) triple loads first, then the additions - the shared-memory latency is
-    // paid once per eight sites even by a warp that has a scheduler to itself (the column groups of a sharded run)
-#pragma unroll
-    for (int s0 = 0; s0 < 32; s0 += 8) {
-        float4 v[8];
-        int c[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int s = s0 + j;
-            c[j] = (int)__byte_perm(w[s >> 2], 0u, 0x4440u + (unsigned)(s & 3));
-            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c[j] == lane || (H == 2 && c[j] == lane + 32)) v[j] = gv[s];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {                       // site order
-            if (c[j] == lane) { a01[0] = fadd2(a01[0], pack2(v[j].x, v[j].y)); a2[0] = __fadd_rn(a2[0], v[j].z); ++n[0]; }
-            if (H == 2 && c[j] == lane + 32) { a01[1] = fadd2(a01[1], pack2(v[j].x, v[j].y)); a2[1] = __fadd_rn(a2[1], v[j].z); ++n[1]; }
+    const int d = a.x + a.y;
+    const int code = d * (d + 1) / 2 + a.y;
+    const bool deepf = valid && d > kZDepthCap;
+    const bool act = valid && !deepf;
+    strip[lane] = make_float4(g.x, g.y, third_gl_np(g.x, g.y), 0.f);
+    ndeep += __popc(__ballot_sync(0xffffffffu, deepf));      // same value in every lane; lane 0 reports it
+    const unsigned peers = __match_any_sync(0xffffffffu, act ? code : -1 - lane);   // lanes of the same class (inactive lanes: alone)
+    const bool leader = act && (peers & ((1u << lane) - 1u)) == 0u;
+    const int maxn = __reduce_max_sync(0xffffffffu, act ? __popc(peers) : 0);
+    const bool hot = code < kZOrdCells;
+    f32x2 v01 = pack2(0.f, 0.f);
+    float v2 = 0.f;
+    int cnt = 0;
+    unsigned rem = leader ? peers : 0u;                      // members still to add, the leader itself first
+    if (leader) {
+        if (hot) { const float4 c = cell[code]; v01 = pack2(c.x, c.y); v2 = c.z; cnt = __float_as_int(c.w); }
+        else { const ZTallyF t = mine[code]; v01 = pack2(t.s0, t.s1); v2 = t.s2; cnt = t.cnt; }
+        cnt += __popc(peers);
+    }
+    __syncwarp();                                            // the strip is complete
+    for (int r = 0; r < maxn; ++r) {                         // warp-uniform trip count
+        if (rem) {
+            const float4 t = strip[__ffs(rem) - 1];
+            v01 = fadd2(v01, pack2(t.x, t.y));
+            v2 = __fadd_rn(v2, t.z);
+            rem &= rem - 1u;
         }
     }
+    if (leader) {
+        const float2 v = unpack2(v01);
+        if (hot) cell[code] = make_float4(v.x, v.y, v2, __int_as_float(cnt));
+        else { ZTallyF t; t.s0 = v.x; t.s1 = v.y; t.s2 = v2; t.cnt = cnt; mine[code] = t; }
+    }
+    __syncwarp();                                            // cells and strip are reused by the next batch
 }
 
 __global__ void __launch_bounds__(kZOrdWarps * 32)
@@ -211,22 +225,17 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
 {
     extern __shared__ __align__(16) unsigned char zs_raw[];
     float4* gbuf = reinterpret_cast<float4*>(zs_raw);                                          // [warps][32] GL triples of a batch
-    float2* Gt = reinterpret_cast<float2*>(gbuf + kZOrdWarps * 32);                            // [stages][tile][kZOrdGS]
+    float4* cells = gbuf + kZOrdWarps * 32;                                                    // [warps][kZOrdCells] running sums
+    float2* Gt = reinterpret_cast<float2*>(cells + kZOrdWarps * kZOrdCells);                   // [stages][tile][kZOrdGS]
     uchar2* At = reinterpret_cast<uchar2*>(Gt + (size_t)kZOrdStages * kZOrdTile * kZOrdGS);    // [stages][tile][kZOrdAS]
-    unsigned char* cbuf = reinterpret_cast<unsigned char*>(At + (size_t)kZOrdStages * kZOrdTile * kZOrdAS);   // [warps][32] class codes
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = col_lo + blockIdx.x * kZOrdWarps;
     const int ncols = min(kZOrdWarps, col_hi - col0);        // a multiple of 4: slabs are padded to 4 individuals
     const int col = col0 + warp;
     const bool on = warp < ncols && sel[col];                // warp-uniform
     ZTallyF* mine = table + (size_t)(warp < ncols ? col : col0) * kZClasses;
-    f32x2 a01[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
-    float a2[2] = {0.f, 0.f};
-    int n[2] = {0, 0};
-    if (on) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) { const ZTallyF t = mine[lane + 32 * h]; a01[h] = pack2(t.s0, t.s1); a2[h] = t.s2; n[h] = t.cnt; }
-    }
+    float4* cell = cells + warp * kZOrdCells;
+    if (on) for (int c = lane; c < kZOrdCells; c += 32) { const ZTallyF t = mine[c]; cell[c] = make_float4(t.s0, t.s1, t.s2, __int_as_float(t.cnt)); }
     // the block's columns of sites [128 t, 128 t + 128): coalesced rows, 16-byte GL chunks and 8-byte depth chunks
     const int gc = ncols >> 1, ac = ncols >> 2;
     auto stage = [&](long t) {
@@ -246,8 +255,7 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
     };
     const long ntiles = (M + kZOrdTile - 1) / kZOrdTile;
     int ndeep = 0;
-    float4* gv = gbuf + warp * 32;
-    unsigned char* cb = cbuf + warp * 32;
+    float4* strip = gbuf + warp * 32;
     for (int p = 0; p < kZOrdStages - 1; ++p) stage(p);
     for (long t = 0; t < ntiles; ++t) {
         const int buf = (int)(t % kZOrdStages);
@@ -264,36 +272,19 @@ ztally_ord_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, i
                 const bool valid = b + lane < M;
                 const float2 g = valid ? Gt[((size_t)buf * kZOrdTile + row) * kZOrdGS + warp] : make_float2(0.f, 0.f);
                 const uchar2 a = valid ? At[((size_t)buf * kZOrdTile + row) * kZOrdAS + warp] : make_uchar2(0, 0);
-                const int d = a.x + a.y;
-                const bool deepf = valid && d > kZDepthCap;
-                const int code = (valid && !deepf) ? d * (d + 1) / 2 + a.y : -1;
-                gv[lane] = make_float4(g.x, g.y, third_gl_np(g.x, g.y), __int_as_float(code));
-                cb[lane] = (unsigned char)((code >= 0 && code < kZOrdLaneClasses) ? code : 255);
-                ndeep += __popc(__ballot_sync(0xffffffffu, deepf));          // same value in every lane; lane 0 reports it
-                const unsigned hi = __ballot_sync(0xffffffffu, code >= 32 && code < kZOrdLaneClasses);
-                unsigned cold = __ballot_sync(0xffffffffu, code >= kZOrdLaneClasses);
-                __syncwarp();
-                if (hi == 0u) ztally_ord_fold<1>(reinterpret_cast<const uint4*>(cb), gv, lane, a01, a2, n);
-                else ztally_ord_fold<2>(reinterpret_cast<const uint4*>(cb), gv, lane, a01, a2, n);
-                if (cold && lane == 0) {                     // rare: deeper than the lanes' classes - in site order, in the table row
-                    while (cold) {
-                        const int s = __ffs(cold) - 1;
-                        cold &= cold - 1u;
-                        const float4 v = gv[s];
-                        ZTallyF tt = mine[__float_as_int(v.w)];
-                        tt.s0 = __fadd_rn(tt.s0, v.x); tt.s1 = __fadd_rn(tt.s1, v.y); tt.s2 = __fadd_rn(tt.s2, v.z); tt.cnt += 1;
-                        mine[__float_as_int(v.w)] = tt;
-                    }
-                }
-                __syncwarp();                                // everyone has read the strip before the next batch overwrites it
+                ztally_ord_batch(g, a, valid, lane, strip, cell, mine, ndeep);
             }
         }
         __syncthreads();                                    // everyone is done with tile t before its buffer is refilled
     }
     cp_async_wait<0>();
     if (on) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) { const float2 v = unpack2(a01[h]); ZTallyF tt; tt.s0 = v.x; tt.s1 = v.y; tt.s2 = a2[h]; tt.cnt = n[h]; mine[lane + 32 * h] = tt; }
+        __syncwarp();
+        for (int c = lane; c < kZOrdCells; c += 32) {
+            const float4 v = cell[c];
+            ZTallyF tt; tt.s0 = v.x; tt.s1 = v.y; tt.s2 = v.z; tt.cnt = __float_as_int(v.w);
+            mine[c] = tt;
+        }
         if (lane == 0 && ndeep) atomicAdd(&deep[col], (unsigned long long)ndeep);
     }
 }
