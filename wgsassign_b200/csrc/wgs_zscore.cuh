@@ -201,13 +201,17 @@ __device__ __forceinline__ void ztally_ord_batch(float2 g, uchar2 a, bool valid,
         cnt += __popc(peers);
     }
     __syncwarp();                                            // the strip is complete
+    // branch-free rounds (a divergent `if` per round cost a convergence barrier pair and doubled the instruction count):
+    // a lane with nothing left re-reads its own strip entry and adds +0 to nothing
+#pragma unroll 1
     for (int r = 0; r < maxn; ++r) {                         // warp-uniform trip count
-        if (rem) {
-            const float4 t = strip[__ffs(rem) - 1];
-            v01 = fadd2(v01, pack2(t.x, t.y));
-            v2 = __fadd_rn(v2, t.z);
-            rem &= rem - 1u;
-        }
+        const bool more = rem != 0u;
+        const float4 t = strip[more ? __ffs(rem) - 1 : lane];
+        const f32x2 n01 = fadd2(v01, pack2(t.x, t.y));
+        const float n2 = __fadd_rn(v2, t.z);
+        v01 = more ? n01 : v01;
+        v2 = more ? n2 : v2;
+        rem &= rem - 1u;                                     // 0 stays 0
     }
     if (leader) {
         const float2 v = unpack2(v01);
