@@ -803,11 +803,12 @@ struct EmState {
     std::vector<int> h_active, h_iters;
     int slot_c0[2] = {0, 0}, slot_nc[2] = {0, 0};
     // exact stop rule (the reference's sequential float32 sum, emMAF_cy.pyx:26-33) for checks that land inside the
-    // band in which the exact FP64 sum cannot decide: D2 [M][ldg] = the squared changes of the last iteration
+    // band in which the exact FP64 sum cannot decide: D2 [ldg][M] (problem-major) = the squared changes of the last iteration
     DevBuf d2, serial, carry, uncertain;
     bool exact = false;
     bool chain_on = false, chain_always = false, missed = false;   // site-sharded runs: the rank chain is queued only near convergence
     double band_override = 0.0;
+    double near_factor = 30.0;   // "near": within this factor of the tolerance (two iterations of a 0.3x contraction above the band)
 };
 
 // The reference's stop sum is sequential float32; `exact` runs keep what is needed to reproduce it (option
@@ -863,6 +864,16 @@ int em_state_init(wgs_ctx* ctx, EmState& st, int np, int ld, int nblocks, const 
     CU(cudaMemcpyAsync(st.active.p, st.h_active.data(), (size_t)np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     st.exact = exact;
     st.band_override = band_override_of(ctx);
+    {   // the band for the whole-file site count decides how early the rank chain has to be queued; a band that cannot
+        // be bounded (>= 2^23 addends) or "always" means every check is resolved: the chain is on from the first iteration
+        double band = st.band_override;
+        if (band == 0.0) {
+            const double ku = (double)ctx->Mtot() * 5.9604644775390625e-08;
+            band = ku >= 0.5 ? -1.0 : 0.5 * ku / (1.0 - ku) + 1e-4;
+        }
+        if (band < 0.0) st.chain_always = true;
+        else st.near_factor = 12.0 * (1.0 + band);
+    }
     if (exact) {
         const long M = ctx->M();
         if (buf_alloc(ctx, st.d2, (size_t)std::max<long>(M, 1) * ctx->ldg * sizeof(float)) || buf_alloc(ctx, st.serial, (size_t)np * sizeof(float)) ||
@@ -949,7 +960,7 @@ int em_after_step_queue(wgs_ctx* ctx, EmState& st, double tole, int iteration, c
         auto resolve = [&](const float* carry_in, bool sums) -> int {
             LAUNCH("em_resolve", em_resolve_kernel, std::max(1, std::min(nc, ctx->num_sm * 16)), kSeqWarps * 32, 0, ctx->stream,
                    st.ssq.as<double>() + c0, cnt, count_all, nc, tole, st.band_override, st.active.as<int>() + c0,
-                   sums ? st.d2.as<float>() + c0 : (const float*)nullptr, ctx->ldg, ctx->M(), carry_in, st.serial.as<float>() + c0,
+                   sums ? st.d2.as<float>() + (size_t)c0 * std::max<long>(ctx->M(), 1) : (const float*)nullptr, ctx->M(), carry_in, st.serial.as<float>() + c0,
                    st.uncertain.as<int>() + c0);
             return 0;
         };
@@ -980,7 +991,7 @@ int em_after_step_queue(wgs_ctx* ctx, EmState& st, double tole, int iteration, c
         d_serial = have_sums ? st.serial.as<float>() + c0 : nullptr;
     }
     LAUNCH("em_decide", em_decide_kernel, 1, 1024, 0, ctx->stream, st.ssq.as<double>() + c0, d_count ? d_count + c0 : nullptr, count_all, nc, tole,
-           iteration, st.active.as<int>() + c0, st.iters.as<int>() + c0, ctx->em_pin_dev[slot], d_unc, d_serial, 1 + nc);
+           iteration, st.active.as<int>() + c0, st.iters.as<int>() + c0, ctx->em_pin_dev[slot], d_unc, d_serial, 1 + nc, st.near_factor);
     CU(cudaEventRecord(ctx->em_ev[slot], ctx->stream));
     st.slot_c0[slot] = c0; st.slot_nc[slot] = nc;
     return 0;
@@ -1336,7 +1347,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     }
     EmState st;
     if (em_state_init(ctx, st, ldg, ldg, nblocks, active0, opt(ctx, "rmse_exact", 1) != 0)) return 1;
-    st.chain_always = force_chain;
+    if (force_chain) st.chain_always = true;
     float* const D2 = st.d2.as<float>();                         // null when the exact stop rule is switched off
     // When every real column is an active problem of a population that loo_first serves, iteration 1 writes all of
     // them without reading the start state: only the padding columns need a value (the step kernels load whole quads).

@@ -1710,7 +1710,7 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
                     const unsigned char* __restrict__ mask,      // [M][ldg] or null
                     double* __restrict__ partials,               // [gridDim.x][ldg]
                     long ntiles,
-                    float* __restrict__ D2)                      // [M][ldg] or null: this iteration's squared change per (site, problem)
+                    float* __restrict__ D2)                      // [ldg][M] (problem-major) or null: this iteration's squared change per (problem, site)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -1839,7 +1839,10 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
                 }
             }
             *reinterpret_cast<float4*>(&F[(s0 + sl) * (long)ldf + c0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
-            if (D2) *reinterpret_cast<float4*>(&D2[(s0 + sl) * (long)ldg + c0]) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+            if (D2) {
+                float* d2p = D2 + (long)c0 * M + (s0 + sl);
+                d2p[0] = dq[0]; d2p[M] = dq[1]; d2p[2 * M] = dq[2]; d2p[3 * M] = dq[3];
+            }
         }
         const long nxt = tl + gridDim.x;
         if (nxt < ntiles) {                                     // the next tile's raw rows landed while this one computed
@@ -2102,7 +2105,7 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
                     long ntiles,                                 // groups of rows_per_pass rows
                     int nstages,                                 // ring depth, 2..kLoo5MaxStages
                     int dbg,                                     // experiments: 1 = no restaging (stale tiles), 2 = staging only
-                    float* __restrict__ D2)                      // [M][ldg] or null: this iteration's squared change per (site, problem)
+                    float* __restrict__ D2)                      // [ldg][M] (problem-major) or null: this iteration's squared change per (problem, site)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full[kLoo5MaxStages], empty[kLoo5MaxStages];
@@ -2218,7 +2221,10 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
                 }
             }
             *reinterpret_cast<float4*>(&F[(tl * TS + r) * (long)ldf + c0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
-            if (D2) *reinterpret_cast<float4*>(&D2[(tl * TS + r) * (long)ldg + c0]) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+            if (D2) {                                           // problem-major: a problem's squared changes are contiguous in site order
+                float* d2p = D2 + (long)c0 * M + (tl * TS + r);
+                d2p[0] = dq[0]; d2p[M] = dq[1]; d2p[2 * M] = dq[2]; d2p[3 * M] = dq[3];
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);               // this warp is done with the slot
@@ -2261,7 +2267,7 @@ loo_first_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n,
                  const int* __restrict__ active,            // [ldg]
                  const unsigned char* __restrict__ mask,    // [M][ldg] or null
                  double* __restrict__ partials,             // [gridDim.x][ldg]
-                 float* __restrict__ D2)                    // [M][ldg] or null: squared change per (site, problem)
+                 float* __restrict__ D2)                    // [ldg][M] (problem-major) or null: squared change per (problem, site)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* red = reinterpret_cast<float*>(smem_raw);      // [R][2 * TPR * kFisherQ]
@@ -2331,7 +2337,7 @@ loo_first_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n,
                     if (ok & 2u) { const float d = __fsub_rn(fb, f0); dq.y = __fmul_rn(d, d); sb[j] = __fadd_rn(sb[j], dq.y); out.y = fb; }
                     if (ok) {
                         *reinterpret_cast<float2*>(&F[s * (long)ldf + col0 + 2 * q]) = out;
-                        if (D2) *reinterpret_cast<float2*>(&D2[s * (long)ldg + col0 + 2 * q]) = dq;
+                        if (D2) { float* d2p = D2 + (long)(col0 + 2 * q) * M + s; d2p[0] = dq.x; d2p[M] = dq.y; }
                     }
                 }
             }
@@ -2414,14 +2420,18 @@ __device__ __forceinline__ float block_seqsum32(float res, long n, Get get)
     __shared__ float sh_res;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long per_round = 256L * kSeqWarps;
-    float x[8], xn[8];
+    float x[8], xn[8], xnn[8];                               // this round, and the next two already in flight
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const long i = (long)warp * 256 + 32 * j + lane; x[j] = i < n ? get(i) : 0.0f; }
+    for (int j = 0; j < 8; ++j) {
+        const long i = (long)warp * 256 + 32 * j + lane;
+        x[j] = i < n ? get(i) : 0.0f;
+        xn[j] = i + per_round < n ? get(i + per_round) : 0.0f;
+    }
     for (long r0 = 0; r0 < n; r0 += per_round) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                        // next round: in flight while this one is folded
-            const long i = r0 + per_round + (long)warp * 256 + 32 * j + lane;
-            xn[j] = i < n ? get(i) : 0.0f;                   // + 0.0f never changes a float32 accumulator that started at +0
+        for (int j = 0; j < 8; ++j) {
+            const long i = r0 + 2 * per_round + (long)warp * 256 + 32 * j + lane;
+            xnn[j] = i < n ? get(i) : 0.0f;                  // + 0.0f never changes a float32 accumulator that started at +0
         }
         int wdone = 0;
         for (;;) {
@@ -2473,7 +2483,7 @@ __device__ __forceinline__ float block_seqsum32(float res, long n, Get get)
             if (!redo || wdone >= kSeqWarps) break;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = xn[j];
+        for (int j = 0; j < 8; ++j) { x[j] = xn[j]; xn[j] = xnn[j]; }
     }
     return res;
 }
@@ -2482,7 +2492,7 @@ __device__ __forceinline__ float block_seqsum32(float res, long n, Get get)
 // sum of squared changes lies within `band` (relative) of the tolerance - band = the worst-case distance between
 // the exact sum and the reference's sequential float32 sum for that many addends (or the caller's override;
 // band < 0: every active problem).  For those, the float32 sum is reproduced (block_seqsum32) from the squared changes the step
-// kernels left in D2[M][ldd] (column col0 + p; zero where a site is masked out), starting from carry_in[p]
+// kernels left in D2[problem][M] (zero where a site is masked out), starting from carry_in[p]
 // (site-sharded runs chain the ranks in site order).  em_decide_kernel then decides on serial[p].
 __device__ __forceinline__ double em_band(double cnt, double band_override)
 {
@@ -2494,7 +2504,7 @@ __device__ __forceinline__ double em_band(double cnt, double band_override)
 __global__ void __launch_bounds__(kSeqWarps * 32)
 em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ count, double count_all, int np, double tole,
                   double band_override, const int* __restrict__ active,
-                  const float* __restrict__ D2, int ldd, long M,
+                  const float* __restrict__ D2, long M,        // [np][M] problem-major (offset to the first problem applied by the caller)
                   const float* __restrict__ carry_in,       // [np] or null (first rank)
                   float* __restrict__ serial,               // [np] out: the running float32 sum after this rank's sites
                   int* __restrict__ uncertain)              // [np] out
@@ -2510,8 +2520,8 @@ em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ cou
             unc = (band < 0.0 || fabs(diff - tole) <= band * tole) ? 1 : 0;
         }
         if (unc && D2) {                                     // D2 == null: flags only
-            const float* col = D2 + p;
-            const float r = block_seqsum32(carry_in ? carry_in[p] : 0.0f, M, [&](long i) { return __ldg(col + i * (long)ldd); });
+            const float* col = D2 + (long)p * M;
+            const float r = block_seqsum32(carry_in ? carry_in[p] : 0.0f, M, [&](long i) { return __ldg(col + i); });
             if (threadIdx.x == 0) serial[p] = r;
         }
         if (threadIdx.x == 0) uncertain[p] = unc;
@@ -2550,7 +2560,8 @@ __global__ void em_decide_kernel(const double* __restrict__ ssq, const double* _
                                  int* __restrict__ active, int* __restrict__ iters, int* __restrict__ result,
                                  const int* __restrict__ uncertain = nullptr,   // [np] em_resolve_kernel's flags, or null: FP64 sums only
                                  const float* __restrict__ serial = nullptr,    // [np] the sequential float32 sums of the uncertain problems
-                                 int near_slot = -1)                            // result[near_slot]: 1 if a problem still active is within 30x of the tolerance
+                                 int near_slot = -1,                            // result[near_slot]: 1 if a problem still active is within near_factor x of the tolerance
+                                 double near_factor = 30.0)
 {
     __shared__ int sh_cnt, sh_near, sh_missed;
     if (threadIdx.x == 0) { sh_cnt = 0; sh_near = 0; sh_missed = 0; }
@@ -2566,7 +2577,7 @@ __global__ void em_decide_kernel(const double* __restrict__ ssq, const double* _
             res = res / (float)cnt;
             double diff = sqrt((double)res);
             if (diff < tole) { a = 0; active[p] = 0; iters[p] = iteration; }
-            else { ++mine; if (diff <= 30.0 * tole) near = 1; }
+            else { ++mine; if (diff <= near_factor * tole) near = 1; }
         }
         result[1 + p] = a;
     }
