@@ -87,11 +87,22 @@ int32_t wgs_upload_gl(wgs_ctx *ctx, const float *L, int64_t M, int32_t N, int32_
 int32_t wgs_upload_gl_async(wgs_ctx *ctx, const float *L, int64_t M, int32_t N);
 int32_t wgs_upload_wait(wgs_ctx *ctx);
 
+/* The same upload for a matrix that is still being parsed (the streaming Beagle reader): begin allocates for up to
+ * M_capacity rows, rows() queues the DMAs of a finished row block straight into the device layout and returns at once
+ * (the block must stay valid and unchanged until wgs_upload_wait or the next operator returns), end() fixes the row
+ * count.  Parsing block b+1 overlaps the transfer of block b. */
+int32_t wgs_upload_gl_begin(wgs_ctx *ctx, int64_t M_capacity, int32_t N);
+int32_t wgs_upload_gl_rows(wgs_ctx *ctx, const float *L_rows, int64_t row0, int64_t nrows);
+int32_t wgs_upload_gl_end(wgs_ctx *ctx, int64_t M_final);
+
 /* Allele depths [M,2N] int32, packed on device to 2 x uint8 per individual.  A count above 254 is stored as the
  * sentinel "deeper than any class table": the site joins the deep sites (wgs_zscore_deep_sites) and is never kept,
  * exactly what the reference does with a depth whose depth+1 splits were not all observed (zscore.py:36-39).
  * Negative counts are an error. */
 int32_t wgs_upload_ad(wgs_ctx *ctx, const int32_t *AD, int64_t M, int32_t N);
+/* The same from saturating uint8 pairs [M,2N] (255 = "255 reads or more"), the form wgs_ad_stream_next_u8 parses into:
+ * a quarter of the host memory and PCIe bytes of the int32 matrix. */
+int32_t wgs_upload_ad_u8(wgs_ctx *ctx, const uint8_t *AD, int64_t M, int32_t N);
 
 /* Multi-GPU site sharding: global number of sites, global index of this shard's first site,
  * and the cross-rank sum used for the EM stop rule and the z-score class tallies. */
@@ -212,9 +223,44 @@ int32_t wgs_zmoments_list(wgs_ctx *ctx, int32_t ind, const int32_t *L_keep, int6
  * the reference does unless every one of the depth+1 splits of that depth was observed. */
 int64_t wgs_zscore_deep_sites(const wgs_ctx *ctx);
 
-/* ---- host-side Beagle reader (reader_cy.pyx:16-77) ---------------------------------------- */
-/* Parses a gzipped Beagle GL file with `threads` parser threads (<= 0: all cores).  The matrix
- * equals the reference reader's bit for bit ((float)atof of the first two GLs of each triple). */
+/* ---- host-side readers of the text inputs ---------------------------------------------------------- */
+/* Beagle genotype likelihoods (reader_cy.pyx:16-77): gzip text -> float32 [M, 2N], equal to the reference reader's
+ * matrix bit for bit ((float)atof of the first two GLs of each triple), plus sample and site names.
+ * Streaming form: a background thread inflates while a persistent pool of `threads` parser threads (<= 0: all cores)
+ * converts the rows of the current block STRAIGHT INTO THE CALLER'S BUFFER (pinned memory in the CLI: no intermediate
+ * copy), so a block can be uploaded while the next one is parsed.  wgs_beagle_stream_keep restricts conversion to a
+ * row range (site-sharded ranks keep only their own rows; the rest is counted and named, never converted);
+ * wgs_beagle_stream_next returns the number of rows written (0 at end of file, -1 on error). */
+typedef struct wgs_beagle_stream wgs_beagle_stream;
+int32_t     wgs_beagle_stream_open(const char *path, int32_t threads, wgs_beagle_stream **out);
+int32_t     wgs_beagle_stream_inds(const wgs_beagle_stream *s);
+const char *wgs_beagle_stream_sample(const wgs_beagle_stream *s, int32_t i);
+int32_t     wgs_beagle_stream_keep(wgs_beagle_stream *s, int64_t row_lo, int64_t row_hi);  /* row_hi < 0: to the end */
+int32_t     wgs_beagle_stream_names(wgs_beagle_stream *s, int32_t keep);   /* 0: do not collect site names (and stop at row_hi) */
+int64_t     wgs_beagle_stream_next(wgs_beagle_stream *s, float *out, int64_t max_rows);
+int64_t     wgs_beagle_stream_rows_seen(const wgs_beagle_stream *s);
+const char *wgs_beagle_stream_site(const wgs_beagle_stream *s, int64_t row);               /* rows seen so far */
+int64_t     wgs_beagle_stream_estimate_rows(const wgs_beagle_stream *s);                   /* total rows, from the bytes read so far */
+int32_t     wgs_beagle_stream_stats(const wgs_beagle_stream *s, double *inflate_s, double *parse_s,
+                                    int64_t *compressed_bytes, int64_t *uncompressed_bytes);
+void        wgs_beagle_stream_close(wgs_beagle_stream *s);
+
+/* Allele depths of the z-score modes (WGSassign.py:320, :399: np.loadtxt of an [M, 2N] integer text matrix, plain or
+ * gzipped): the same pipeline, converting to saturating uint8 pairs (255 = "255 reads or more", the device layout of
+ * wgs_upload_ad_u8) or to the reference's int32. */
+typedef struct wgs_ad_stream wgs_ad_stream;
+int32_t wgs_ad_stream_open(const char *path, int32_t threads, wgs_ad_stream **out);
+int32_t wgs_ad_stream_inds(const wgs_ad_stream *s);
+int32_t wgs_ad_stream_keep(wgs_ad_stream *s, int64_t row_lo, int64_t row_hi);
+int64_t wgs_ad_stream_next_u8(wgs_ad_stream *s, uint8_t *out, int64_t max_rows);
+int64_t wgs_ad_stream_next_i32(wgs_ad_stream *s, int32_t *out, int64_t max_rows);
+int64_t wgs_ad_stream_rows_seen(const wgs_ad_stream *s);
+int64_t wgs_ad_stream_estimate_rows(const wgs_ad_stream *s);
+int32_t wgs_ad_stream_stats(const wgs_ad_stream *s, double *inflate_s, double *parse_s, int64_t *compressed_bytes,
+                            int64_t *uncompressed_bytes);
+void    wgs_ad_stream_close(wgs_ad_stream *s);
+
+/* Whole-file form of the Beagle reader (one call, like reader_cy.readBeagle). */
 typedef struct wgs_beagle wgs_beagle;
 int32_t     wgs_beagle_open(const char *path, int32_t threads, wgs_beagle **out);
 const char *wgs_beagle_last_error(void);

@@ -86,6 +86,74 @@ def test_reader_roundtrip_and_formats(lib, tmp_path):
         reader.readBeagle(str(tmp_path / "missing.gz"))
 
 
+def test_reader_row_ranges_blocks_and_whole_file_form(lib, tmp_path):
+    """A site-sharded rank converts only its own rows (names and the row count still cover the whole file); blocks
+    are reported as they complete; the one-call C form gives the same matrix; files spanning several inflate
+    blocks (> 32 MB of text) keep their row order."""
+    import ctypes
+    from wgsassign_b200 import reader, synth
+    m, n = 3001, 9
+    d = synth.synth(m, n, 3, seed=5, with_ad=False)
+    L = d["L"]
+    sites = ["c%d_%d" % (s % 5, s) for s in range(m)]
+    names = ["i%d" % i for i in range(n)]
+    p = str(tmp_path / "r.beagle.gz")
+    synth.write_beagle(p, L, names, sites)
+    mm, nn, ss = reader.count_rows(p, threads=2)
+    assert mm == m and nn == names and ss == sites
+    for lo, hi in ((0, 1000), (1000, 2000), (2000, m), (m, m), (17, 18)):
+        seen = []
+        Lr, n2, s2 = reader.readBeagle(p, threads=3, rows=(lo, hi), on_block=lambda a, r0, r1: seen.append((r0, r1)))
+        assert Lr.shape == (hi - lo, 2 * n) and np.array_equal(Lr, L[lo:hi]) and n2 == names and s2 == sites
+        assert (not seen and hi == lo) or (seen[0][0] == 0 and seen[-1][1] == hi - lo)
+    Lc = lib.lib()
+    h = ctypes.c_void_p(0)
+    assert Lc.wgs_beagle_open(p.encode(), 2, ctypes.byref(h)) == 0
+    out = np.empty((Lc.wgs_beagle_sites(h), 2 * Lc.wgs_beagle_inds(h)), np.float32)
+    Lc.wgs_beagle_copy(h, ctypes.c_void_p(out.ctypes.data))
+    assert Lc.wgs_beagle_site(h, m - 1).decode() == sites[-1]
+    Lc.wgs_beagle_close(h)
+    assert np.array_equal(out, L)
+    # ~40 MB of text: two inflate blocks, rows split across the block boundary
+    m2, n2_ = 2600, 600
+    big = np.round(np.random.default_rng(3).random((m2, 2 * n2_)) * 0.5, 6).astype(np.float32)
+    p2 = str(tmp_path / "big.beagle.gz")
+    synth.write_beagle(p2, big, ["s%d" % i for i in range(n2_)], ["x_%d" % s for s in range(m2)])
+    Lb, _, sb = reader.readBeagle(p2, threads=4)
+    assert np.array_equal(Lb, big) and sb[-1] == "x_%d" % (m2 - 1)
+    assert reader.last_stats["beagle"]["uncompressed_bytes"] > (32 << 20)
+
+
+def test_allele_depth_reader(lib, tmp_path):
+    """--ind_ad_file: plain or gzipped integer text -> the reference's int32 matrix (np.loadtxt) or saturating uint8."""
+    from wgsassign_b200 import reader
+    rng = np.random.default_rng(8)
+    AD = rng.poisson(2.0, size=(1234, 2 * 11)).astype(np.int32)
+    AD[5, 3], AD[9, 0] = 255, 1000
+    p = str(tmp_path / "ad.txt")
+    np.savetxt(p, AD, fmt="%d")
+    pz = str(tmp_path / "ad.txt.gz")
+    with gzip.open(pz, "wt") as fh:
+        fh.write(open(p).read())
+    ref = np.loadtxt(p, dtype=np.int32)
+    for path in (p, pz):
+        a32 = reader.readAD(path, threads=3, dtype=np.int32)
+        assert a32.dtype == np.int32 and np.array_equal(a32, ref)
+        a8 = reader.readAD(path, threads=2)
+        assert a8.dtype == np.uint8 and np.array_equal(a8, np.minimum(ref, 255).astype(np.uint8))
+        part = reader.readAD(path, rows=(100, 300))
+        assert np.array_equal(part, np.minimum(ref[100:300], 255).astype(np.uint8))
+    np.save(str(tmp_path / "ad.npy"), AD)
+    assert np.array_equal(reader.readAD(str(tmp_path / "ad.npy")), AD)
+    bad = str(tmp_path / "bad.txt")
+    open(bad, "w").write("1 2 3 4\n1 2 3\n")
+    with pytest.raises(IOError):
+        reader.readAD(bad)
+    open(bad, "w").write("1 2 3\n")
+    with pytest.raises(IOError, match="two counts"):
+        reader.readAD(bad)
+
+
 def test_reader_matches_reference_reader_on_bundled_files(lib, bundled):
     ref = "/root/reference/data/amre.breeding.ind85.ds_2x.sites-filter.top_50_each.beagle.gz"
     if not os.path.exists(ref):
@@ -111,6 +179,23 @@ def test_writers_and_mixture(bundled, tmp_path):
         utils.write_ass_mats(out, vals[:3], list(bundled["samples_breeding"]), bundled["c1_pop_names"])
     v = np.arange(10, dtype=np.float32)
     assert np.array_equal(utils.partition_loglikes(v, 3), np.array([0 + 3 + 6 + 9, 1 + 4 + 7, 2 + 5 + 8], np.float32))
+
+
+def test_em_mix_logsumexp_option(bundled):
+    """--em_mix_logsumexp: the same proportions as the reference's arithmetic where that is finite, finite ones where it is
+    not (log-likelihoods of a genome-scale run underflow exp())."""
+    from wgsassign_b200 import mixture
+    rng = np.random.default_rng(2)
+    ll = -(rng.random((30, 4)) * 40 + 400)                      # bundled-data scale: exp() is finite
+    idx = np.stack([np.arange(30).astype("U4"), np.array(["a", "b", "c"])[np.arange(30) % 3]], axis=1)
+    a = mixture.em_mix(ll, idx, 200)
+    b = mixture.em_mix(ll, idx, 200, logsumexp=True)
+    assert np.array_equal(a[:, 0], b[:, 0]) and np.allclose(a[:, 1:].astype(float), b[:, 1:].astype(float), rtol=1e-5, atol=1e-7)
+    big = ll * 1e4                                              # genome scale: the reference's form is NaN, the hardened one is not
+    with np.errstate(all="ignore"):
+        assert np.all(np.isnan(mixture.em_mix(big, idx, 50)[:, 1:].astype(float)))
+    c = mixture.em_mix(big, idx, 50, logsumexp=True)[:, 1:].astype(float)
+    assert np.all(np.isfinite(c)) and np.allclose(c.sum(1), 1.0, atol=1e-5)
 
 
 def test_cli_surface():

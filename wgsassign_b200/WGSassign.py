@@ -52,6 +52,9 @@ def build_parser():
     p.add_argument("--get_em_mix", action="store_true", help="Estimate mixture proportions with EM algorithm")
     p.add_argument("--get_mcmc_mix", action="store_true", help="Estimate mixture proportions with MCMC algorithm")
     p.add_argument("--mixture_iter", metavar="INT", type=int, default=200, help="Maximum iterations mixture estimation - EM (200)")
+    p.add_argument("--em_mix_logsumexp", action="store_true",
+                   help="(not in the reference) subtract each individual's largest log likelihood before exponentiating in --get_em_mix: "
+                        "finite mixture proportions for genome-scale log likelihoods, identical results where the reference's are finite")
     return p
 
 
@@ -98,15 +101,23 @@ class _Run:
             self.rank0 = td.get_rank() == 0
             self._device = torch.device("cuda", local) if use_cuda else None
 
-    def shard(self, X):
-        """Keep this rank's contiguous site range of a per-site matrix."""
-        if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
-            return X
+    def _world(self):
+        return int(os.environ.get("WORLD_SIZE", "1"))
+
+    def _range(self, M):
+        """This rank's contiguous site range of an M-site input (and the shard geometry for the library)."""
         import torch.distributed as td
-        lo, hi = self.dist.shard_range(X.shape[0], td.get_rank(), td.get_world_size())
+        lo, hi = self.dist.shard_range(M, td.get_rank(), td.get_world_size())
         if self.M_total is None:
-            self.M_total = X.shape[0]
+            self.M_total = M
             self.dist.enable(self.M_total, lo, device=self._device)
+        return lo, hi
+
+    def shard(self, X):
+        """Keep this rank's contiguous site range of a per-site matrix that was read whole."""
+        if self._world() <= 1:
+            return X
+        lo, hi = self._range(X.shape[0])
         return self.np.ascontiguousarray(X[lo:hi])
 
     def full(self, X):
@@ -117,15 +128,41 @@ class _Run:
         if self.rank0:
             print(*a)
 
+    def _first_layout(self):
+        """Population layout of the first mode that will use the matrix: (pop_of_ind, K) or (None, 0) for the flat one.
+        The streamed upload puts the matrix on the device in that layout while the file is still being parsed."""
+        np, a = self.np, self.args
+        from . import session
+        try:
+            if a.get_reference_af or (a.get_reference_z_score and not a.get_pop_like):
+                IDs = np.loadtxt(a.pop_af_IDs, delimiter="\t", dtype="str")
+                pop_of, pops = session.pops_from_ids(IDs)
+                return pop_of, len(pops)
+        except Exception:
+            pass                                                   # the mode itself reports a missing / malformed ID file
+        return None, 0
+
     # -- input ----------------------------------------------------------------------------
     def parse_inputs(self):
-        from . import reader, utils
+        from . import reader, session, utils
         a = self.args
         if a.beagle is not None:
             self.say("Parsing Beagle file.")
             assert os.path.isfile(a.beagle), "Beagle file doesn't exist!"
-            self.L, self.sample_names, self.site_names = reader.readBeagle(a.beagle, a.threads)
-            m, n = self.L.shape[0], self.L.shape[1] // 2
+            if a.loo_downsampled_beagle is None:
+                # streamed: a background thread inflates, a thread pool parses straight into pinned memory, every finished
+                # block is queued for upload while the next is parsed; a site-sharded rank converts only its own rows
+                rows = None
+                if self._world() > 1:
+                    m_all, _, _ = reader.count_rows(a.beagle, a.threads)      # one inflate pass, nothing converted
+                    rows = self._range(m_all)
+                pop_of, K = self._first_layout()
+                _, self.L, self.sample_names, self.site_names = session.stream_context(a.beagle, pop_of, K, a.threads, rows=rows)
+                self._L_sharded = True
+                m, n = len(self.site_names), self.L.shape[1] // 2
+            else:
+                self.L, self.sample_names, self.site_names = reader.readBeagle(a.beagle, a.threads)
+                m, n = self.L.shape[0], self.L.shape[1] // 2
             self.say("Loaded " + str(m) + " sites and " + str(n) + " individuals.")
             if self.rank0:
                 utils.print_sample_and_site_summary(self.sample_names, self.site_names)
@@ -147,7 +184,7 @@ class _Run:
             if self.site_names != sites_ds:
                 raise ValueError("Site names in full and downsampled Beagle do not match after filtering.")
             self.L_ds = self.shard(self.np.ascontiguousarray(L_ds))
-        if self.L is not None:
+        if self.L is not None and not getattr(self, "_L_sharded", False):
             self.L = self.shard(self.np.ascontiguousarray(self.L))
 
     # -- --get_reference_af (+ --ne_obs, --loo) ------------------------------------------------
@@ -252,8 +289,18 @@ class _Run:
             A = self.shard(np.load(a.pop_af_file))
         self.say("Parsing individual allele depths file.")
         assert os.path.isfile(a.ind_ad_file), "Individual allele depths file does not exist!"
-        AD = np.load(a.ind_ad_file) if a.ind_ad_file.endswith(".npy") else np.loadtxt(a.ind_ad_file, dtype=np.int32)
-        AD = self.shard(np.ascontiguousarray(AD, dtype=np.int32))
+        from . import reader
+        rows = None
+        if self._world() > 1:
+            rows = self._range(self.M_total if self.M_total is not None else self.L.shape[0])
+        # text (plain or gzipped) through the streaming parser, straight to saturating uint8 pairs; a rank reads only its rows
+        AD = reader.readAD(a.ind_ad_file, a.threads, rows=rows)
+        if AD.dtype != np.uint8:
+            AD = np.ascontiguousarray(AD, dtype=np.int32)
+        deep = int(np.count_nonzero(AD >= 255)) if AD.dtype == np.uint8 else int(np.count_nonzero(AD > 254))
+        if deep and self.rank0:
+            print("Note: " + str(deep) + " allele depths of 255 or more: those sites are treated as deeper than any depth class "
+                  "(the reference never keeps them either)")
         assert os.path.isfile(a.pop_names), "Population names file does not exist!!"
         pops = np.loadtxt(a.pop_names, dtype="str")
         n = self.L.shape[1] // 2
@@ -298,7 +345,7 @@ class _Run:
         ll = np.loadtxt(a.pop_like)
         index = np.loadtxt(a.pop_like_IDs, delimiter="\t", dtype="str")
         print("Calculating mixture proportions with EM")
-        res = (mixture.mcmc_mix if mcmc else mixture.em_mix)(ll, index, a.mixture_iter)
+        res = mixture.mcmc_mix(ll, index, a.mixture_iter) if mcmc else mixture.em_mix(ll, index, a.mixture_iter, logsumexp=a.em_mix_logsumexp)
         np.savetxt(a.out + ".em_mix.txt", res, fmt="%s")       # the reference writes .em_mix.txt in both modes (WGSassign.py:470)
         if mcmc:
             print("Saved MCMC mixture proportions " + str(a.out) + ".mcmc_mix.txt (text)")

@@ -47,6 +47,9 @@ SYMBOLS = {
     "wgs_nccl_init": (_i32, [_vp, _vp, _i32, _i32]),
     "wgs_upload_gl_async": (_i32, [_vp, _vp, _i64, _i32]),
     "wgs_upload_wait": (_i32, [_vp]),
+    "wgs_upload_gl_begin": (_i32, [_vp, _i64, _i32]),
+    "wgs_upload_gl_rows": (_i32, [_vp, _vp, _i64, _i64]),
+    "wgs_upload_gl_end": (_i32, [_vp, _i64]),
     "wgs_upload_ad": (_i32, [_vp, _vp, _i64, _i32]),
     "wgs_set_shard": (_i32, [_vp, _i64, _i64, ALLREDUCE_FN, _vp]),
     "wgs_synth": (_i32, [_vp, _i64, _i32, ctypes.c_uint64, ctypes.c_float, _i32]),
@@ -63,6 +66,27 @@ SYMBOLS = {
     "wgs_zscore_table": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "wgs_zkeep_one": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "wgs_zmoments_list": (_i32, [_vp, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "wgs_upload_ad_u8": (_i32, [_vp, _vp, _i64, _i32]),
+    "wgs_beagle_stream_open": (_i32, [ctypes.c_char_p, _i32, ctypes.POINTER(_vp)]),
+    "wgs_beagle_stream_inds": (_i32, [_vp]),
+    "wgs_beagle_stream_sample": (ctypes.c_char_p, [_vp, _i32]),
+    "wgs_beagle_stream_keep": (_i32, [_vp, _i64, _i64]),
+    "wgs_beagle_stream_names": (_i32, [_vp, _i32]),
+    "wgs_beagle_stream_next": (_i64, [_vp, _vp, _i64]),
+    "wgs_beagle_stream_rows_seen": (_i64, [_vp]),
+    "wgs_beagle_stream_site": (ctypes.c_char_p, [_vp, _i64]),
+    "wgs_beagle_stream_estimate_rows": (_i64, [_vp]),
+    "wgs_beagle_stream_stats": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "wgs_beagle_stream_close": (None, [_vp]),
+    "wgs_ad_stream_open": (_i32, [ctypes.c_char_p, _i32, ctypes.POINTER(_vp)]),
+    "wgs_ad_stream_inds": (_i32, [_vp]),
+    "wgs_ad_stream_keep": (_i32, [_vp, _i64, _i64]),
+    "wgs_ad_stream_next_u8": (_i64, [_vp, _vp, _i64]),
+    "wgs_ad_stream_next_i32": (_i64, [_vp, _vp, _i64]),
+    "wgs_ad_stream_rows_seen": (_i64, [_vp]),
+    "wgs_ad_stream_estimate_rows": (_i64, [_vp]),
+    "wgs_ad_stream_stats": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "wgs_ad_stream_close": (None, [_vp]),
     "wgs_beagle_open": (_i32, [ctypes.c_char_p, _i32, ctypes.POINTER(_vp)]),
     "wgs_beagle_last_error": (ctypes.c_char_p, []),
     "wgs_beagle_sites": (_i64, [_vp]),
@@ -210,11 +234,31 @@ class Context:
         self._ck(lib().wgs_upload_gl_async(self._h, _ptr(L), L.shape[0], L.shape[1] // 2))
         self.M, self.N = L.shape[0], L.shape[1] // 2
 
+    def upload_gl_begin(self, M_capacity, N):
+        """Row-block upload of a matrix that is still being parsed: begin / rows / end (see the header)."""
+        self._ck(lib().wgs_upload_gl_begin(self._h, int(M_capacity), int(N)))
+        self.N = int(N)
+
+    def upload_gl_rows(self, L, row0, row1):
+        """Queue rows [row0, row1) of the float32 [*, 2N] array L (kept referenced until the upload is waited for)."""
+        self._pending_L = L
+        self._ck(lib().wgs_upload_gl_rows(self._h, ctypes.c_void_p(L.ctypes.data + row0 * L.shape[1] * 4), int(row0), int(row1 - row0)))
+
+    def upload_gl_end(self, M_final):
+        self._ck(lib().wgs_upload_gl_end(self._h, int(M_final)))
+        self.M = int(M_final)
+
     def upload_wait(self):
         self._ck(lib().wgs_upload_wait(self._h))
         self._pending_L = None
 
     def upload_ad(self, AD):
+        """AD: int32 [M,2N] (the reference's matrix) or uint8 [M,2N] with 255 = "255 reads or more" (what the
+        streaming depth reader produces: a quarter of the bytes)."""
+        if isinstance(AD, np.ndarray) and AD.dtype == np.uint8:
+            _as(AD, np.uint8, 2, "AD")
+            self._ck(lib().wgs_upload_ad_u8(self._h, _ptr(AD), AD.shape[0], AD.shape[1] // 2))
+            return
         _as(AD, np.int32, 2, "AD")
         self._ck(lib().wgs_upload_ad(self._h, _ptr(AD), AD.shape[0], AD.shape[1] // 2))
 

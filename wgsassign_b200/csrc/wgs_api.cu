@@ -53,6 +53,7 @@ struct wgs_ctx {
 
     // asynchronous upload (wgs_upload_gl_async): one event per population slab on stream2
     bool upload_pending = false;
+    long upload_capacity = 0;                    // rows the GL buffer was allocated for (wgs_upload_gl_begin)
     std::vector<cudaEvent_t> ev_pop;
     std::vector<int> upload_order;               // populations in the order their slabs were queued (smallest first)
 
@@ -126,7 +127,7 @@ const char* const kOptionNames[] = {
     "loo_by_pop",         // 1: leave-one-out EM population by population (one packed-row buffer at a time); -1: never
     "loo_variant",        // inner-loop variant of the packed leave-one-out step kernel (experiments)
     "upload_sync",        // 1: wgs_upload_gl_async falls back to the chunked synchronous upload
-    "ztally_groups",      // column groups of the rank-chained class tally (default 8)
+    "ztally_groups",      // column groups of the rank-chained class tally (default 1: a group launch is latency-bound and takes as long as the full one)
     "z_exact_means",      // 1: order-independent fixed-point class means (NOT the reference's float32 means)
     "rmse_exact",         // 0: stop rule on the float64 sum only (no sequential float32 tie-break)
     "rmse_band_ppm",      // half-width of the tie-break band around the tolerance, parts per million of the RMSE (0 = automatic)
@@ -1714,6 +1715,64 @@ int32_t wgs_upload_gl_async(wgs_ctx* ctx, const float* L, int64_t M, int32_t N)
     return 0;
 }
 
+// Row-block form of the asynchronous upload, for a matrix that is still being parsed: begin (allocate for up to
+// M_capacity rows), rows (queue the strided DMAs of a finished row block - one per population slab run - and return
+// at once), end (the final row count; from then on the context behaves as after wgs_upload_gl_async).
+int32_t wgs_upload_gl_begin(wgs_ctx* ctx, int64_t M_capacity, int32_t N)
+{
+    cudaSetDevice(ctx->device);
+    upload_fence(ctx);
+    if (M_capacity < 0 || N <= 0) return fail(ctx, "bad shape");
+    if (ensure_structure(ctx, N)) return 1;
+    const int ldg = ctx->ldg;
+    dev_free(ctx, ctx->G[0]);
+    if (dev_alloc(ctx, &ctx->G[0], (size_t)std::max<long>(M_capacity, 1) * ldg)) return 1;
+    ctx->Mg[0] = 0;
+    ctx->upload_capacity = M_capacity;
+    // the padding columns of the slabs are not part of any DMA: zero the whole buffer once (device-side, cheap)
+    CU(cudaMemsetAsync(ctx->G[0], 0, (size_t)std::max<long>(M_capacity, 1) * ldg * sizeof(float2), ctx->stream2));
+    return 0;
+}
+
+int32_t wgs_upload_gl_rows(wgs_ctx* ctx, const float* L_rows, int64_t row0, int64_t nrows)
+{
+    cudaSetDevice(ctx->device);
+    if (!ctx->G[0] || row0 < 0 || row0 + nrows > ctx->upload_capacity) return fail(ctx, "row block outside the capacity given to wgs_upload_gl_begin");
+    const int K = std::max(ctx->K, 1), ldg = ctx->ldg, N = ctx->N;
+    float2* G = ctx->G[0] + (size_t)row0 * ldg;
+    for (int k = 0; k < K && nrows > 0; ++k) {
+        const PopDesc pd = ctx->pops[k];
+        int j = 0;
+        while (j < pd.n) {                                       // runs of consecutive Beagle columns inside the slab
+            const int c = pd.col0 + j, i = ctx->ind_of_col[c];
+            int len = 1;
+            while (j + len < pd.n && ctx->ind_of_col[c + len] == i + len) ++len;
+            CU(cudaMemcpy2DAsync(G + c, (size_t)ldg * sizeof(float2), L_rows + 2 * (size_t)i, (size_t)N * sizeof(float2),
+                                 (size_t)len * sizeof(float2), (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream2));
+            j += len;
+        }
+    }
+    ctx->upload_pending = true;
+    return 0;
+}
+
+int32_t wgs_upload_gl_end(wgs_ctx* ctx, int64_t M_final)
+{
+    cudaSetDevice(ctx->device);
+    if (!ctx->G[0] || M_final < 0 || M_final > ctx->upload_capacity) return fail(ctx, "final row count outside the capacity given to wgs_upload_gl_begin");
+    const int K = std::max(ctx->K, 1);
+    ctx->Mg[0] = M_final;
+    while ((int)ctx->ev_pop.size() < K) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_pop.push_back(e);
+    }
+    ctx->upload_order.resize(K);
+    for (int k = 0; k < K; ++k) { ctx->upload_order[k] = k; CU(cudaEventRecord(ctx->ev_pop[k], ctx->stream2)); }
+    ctx->upload_pending = true;
+    return 0;
+}
+
 int32_t wgs_upload_wait(wgs_ctx* ctx)
 {
     cudaSetDevice(ctx->device);
@@ -1744,6 +1803,30 @@ int32_t wgs_upload_ad(wgs_ctx* ctx, const int32_t* AD, int64_t M, int32_t N)
     CU(cudaMemcpy(bad, flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
     if (bad[0]) return fail(ctx, "negative allele depth in the depth matrix");
     ctx->ad_saturated = bad[1];                                  // stored as the "deeper than any class" sentinel
+    return 0;
+}
+
+int32_t wgs_upload_ad_u8(wgs_ctx* ctx, const uint8_t* AD, int64_t M, int32_t N)
+{
+    cudaSetDevice(ctx->device);
+    upload_fence(ctx);
+    if (N != ctx->N || M != ctx->Mg[0]) return fail(ctx, "allele-depth matrix must match the GL matrix shape (upload GL first)");
+    dev_free(ctx, ctx->AD);
+    if (dev_alloc(ctx, &ctx->AD, (size_t)std::max<long>(M, 1) * ctx->ldg)) return 1;
+    ctx->M_ad = M;
+    DevBuf flag;
+    if (buf_alloc(ctx, flag, 2 * sizeof(int))) return 1;
+    CU(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    uchar2* dst = ctx->AD;
+    int rc = upload_rows<uchar2>(ctx, (const uchar2*)AD, M, N, [&](uchar2* stage, long r0, long rows, cudaStream_t st) {
+        LAUNCH("repack", repack_ad_u8_kernel, grid_for(rows * ctx->ldg, 256, ctx->num_sm * 16), 256, 0, st, stage, N,
+               dst + (size_t)r0 * ctx->ldg, ctx->ldg, ctx->d_ind_of_col, rows, flag.as<int>());
+    });
+    if (rc) return rc;
+    int bad[2] = {0, 0};
+    CU(cudaMemcpy(bad, flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    ctx->ad_saturated = bad[1];
     return 0;
 }
 
@@ -2260,7 +2343,7 @@ int32_t wgs_zscore(wgs_ctx* ctx, int32_t mode, const float* af, int32_t K, int32
         const int nblk = (ldg + kZOrdWarps - 1) / kZOrdWarps;
         CU(cudaFuncSetAttribute(ztally_ord_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kZOrdSmem));
         const bool sharded_nccl = sharded && ctx->nccl_comm;
-        const int ngroups = sharded_nccl ? std::max(1, std::min(opt(ctx, "ztally_groups", 8), nblk)) : 1;
+        const int ngroups = sharded_nccl ? std::max(1, std::min(opt(ctx, "ztally_groups", 1), nblk)) : 1;
         auto run_group = [&](int g) -> int {
             const int b0 = (int)((long)nblk * g / ngroups), b1 = (int)((long)nblk * (g + 1) / ngroups);
             if (b1 <= b0) return 0;

@@ -201,6 +201,26 @@ __global__ void repack_ad_kernel(const int2* __restrict__ stage, int N, uchar2* 
     if (sat) atomicAdd(&flags[1], sat);
 }
 
+// the same from saturating uint8 pairs (255 = "255 reads or more"): a count of 255 becomes the sentinel pair
+__global__ void repack_ad_u8_kernel(const uchar2* __restrict__ stage, int N, uchar2* __restrict__ AD, int ldg,
+                                    const int* __restrict__ ind_of_col, long rows, int* __restrict__ flags)
+{
+    long total = rows * (long)ldg;
+    int sat = 0;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long r = e / ldg;
+        int c = (int)(e - r * ldg);
+        int src = ind_of_col[c];
+        uchar2 v = make_uchar2(0, 0);
+        if (src >= 0) {
+            v = stage[r * (long)N + src];
+            if (v.x == 255 || v.y == 255) { ++sat; v = make_uchar2(255, 255); }
+        }
+        AD[e] = v;
+    }
+    if (sat) atomicAdd(&flags[1], sat);
+}
+
 __global__ void unpack_ad_kernel(const uchar2* __restrict__ AD, int ldg, const int* __restrict__ col_of_ind, int N,
                                  int2* __restrict__ out, long rows)
 {

@@ -1,37 +1,41 @@
-// Host-side Beagle genotype-likelihood reader (replaces reader_cy.pyx:16-77).
+// Host-side readers of the two big text inputs:
+//   * the Beagle genotype-likelihood file (replaces reader_cy.pyx:16-77), and
+//   * the allele-depth matrix of the z-score modes (the reference's np.loadtxt, WGSassign.py:320, :399).
 //
-// Format (reader_cy.pyx:31-68): gzip text, fields separated by runs of tab/space; header
+// Beagle format (reader_cy.pyx:31-68): gzip text, fields separated by runs of tab/space; header
 // `marker allele1 allele2` then every sample name three times; each data row: site id, two
 // allele codes (ignored), then three GLs per individual of which the third is dropped.
 // Output contract: float32 [M, 2N] whose values equal (float)atof(token) bit for bit, plus
 // the sample and site name lists.
 //
-// inflate is inherently serial (one gzip stream); parsing is not: each decompressed block
-// is cut at line boundaries and its lines are parsed by a pool of threads straight into
-// the row-major output.  Plain "digits.digits" tokens (what ANGSD writes) are converted
-// exactly: an integer below 2^53 divided by an exact power of ten is one correctly rounded
-// double operation, i.e. the same double strtod returns; anything else goes to strtod.
+// Pipeline (GzLines): inflate is inherently serial (one gzip stream) - a dedicated thread runs it
+// and hands decompressed blocks, cut at line boundaries, through a bounded queue, so inflating
+// block b+1.. overlaps the parsing of block b.  Parsing is not serial: a persistent pool of
+// threads converts the lines of a block straight into the CALLER's row-major output (pinned
+// memory in the CLI - no intermediate copy), and rows outside the caller's keep range (another
+// rank's sites) are counted and named but never converted.  Plain "digits.digits" tokens (what
+// ANGSD writes) are converted exactly: an integer below 2^53 divided by an exact power of ten is
+// one correctly rounded double operation, i.e. the same double strtod returns; anything else
+// goes to strtod.
 #include "../../include/wgsassign_b200.h"
 
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 namespace {
-
-struct Beagle {
-    std::vector<std::string> samples, sites;
-    std::vector<std::vector<float>> blocks;   // row-major pieces, concatenated on copy-out
-    std::vector<long> block_rows;
-    int n_ind = 0;
-    long rows = 0;
-    std::string err;
-};
 
 std::string g_reader_error;
 
@@ -65,8 +69,154 @@ inline float parse_float(const char* p, const char* q)
     return (float)atof(tmp.c_str());
 }
 
-// parse one data line [p, e) into out[0 .. 2n); returns false on a short line
-bool parse_line(const char* p, const char* e, int n_ind, float* out, std::string* site)
+bool blank(const char* p, const char* e)
+{
+    for (; p < e; ++p) if (!is_delim(*p)) return false;
+    return true;
+}
+
+// ---- persistent worker pool: run(n, fn) calls fn(i) for i in [0, n) on all threads, chunks handed out dynamically ----
+class Pool {
+public:
+    explicit Pool(int threads) : n_(std::max(1, threads)) {
+        for (int t = 1; t < n_; ++t) th_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void run(long n, long grain, const std::function<void(long, long)>& fn) {
+        if (n <= 0) return;
+        if (n_ == 1 || n <= grain) { fn(0, n); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn; total_ = n; grain_ = grain; next_.store(0); pending_ = n_ - 1; ++gen_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    int size() const { return n_; }
+private:
+    void work() {
+        for (;;) {
+            const long a = next_.fetch_add(grain_);
+            if (a >= total_) break;
+            (*fn_)(a, std::min(total_, a + grain_));
+        }
+    }
+    void loop() {
+        unsigned long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            work();
+            { std::lock_guard<std::mutex> lk(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(long, long)>* fn_ = nullptr;
+    long total_ = 0, grain_ = 1;
+    std::atomic<long> next_{0};
+    int pending_ = 0;
+    unsigned long gen_ = 0;
+    bool stop_ = false;
+};
+
+// ---- gzip text -> blocks of whole lines, inflated by a background thread ----
+struct Block { std::vector<char> data; size_t end = 0; };
+
+class GzLines {
+public:
+    bool open(const char* path, std::string* err) {
+        gz_ = gzopen(path, "rb");
+        if (!gz_) { *err = std::string("cannot open ") + path; return false; }
+        gzbuffer(gz_, 1 << 20);
+        FILE* f = fopen(path, "rb");
+        if (f) { fseek(f, 0, SEEK_END); compressed_size_ = ftell(f); fclose(f); }
+        th_ = std::thread([this] { inflate_loop(); });
+        return true;
+    }
+    ~GzLines() {
+        { std::lock_guard<std::mutex> lk(m_); abort_ = true; }
+        cv_space_.notify_all();
+        if (th_.joinable()) th_.join();
+        if (gz_) gzclose(gz_);
+    }
+    // next block of whole lines; false at end of file or on error (failed())
+    bool next(Block* out) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_data_.wait(lk, [this] { return !q_.empty() || eof_ || failed_; });
+        if (q_.empty()) return false;
+        *out = std::move(q_.front());
+        q_.pop_front();
+        lk.unlock();
+        cv_space_.notify_one();
+        return true;
+    }
+    bool failed() const { return failed_; }
+    long compressed_size() const { return compressed_size_; }
+    long compressed_pos() const { return compressed_pos_.load(); }
+    long uncompressed_bytes() const { return uncompressed_.load(); }
+    double inflate_seconds() const { return inflate_s_.load(); }
+private:
+    void inflate_loop() {
+        const size_t CH = (size_t)32 << 20;
+        std::string carry;
+        bool eof = false;
+        while (!eof) {
+            Block b;
+            b.data.assign(carry.begin(), carry.end());
+            const size_t off = b.data.size();
+            b.data.resize(off + CH);
+            const auto t0 = std::chrono::steady_clock::now();
+            const int got = gzread(gz_, b.data.data() + off, (unsigned)CH);
+            inflate_s_.store(inflate_s_.load() + std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+            if (got < 0) { std::lock_guard<std::mutex> lk(m_); failed_ = true; cv_data_.notify_all(); return; }
+            b.data.resize(off + (size_t)got);
+            uncompressed_.fetch_add(got);
+            compressed_pos_.store((long)gzoffset(gz_));
+            eof = (size_t)got < CH;
+            size_t end = b.data.size();
+            if (!eof) {
+                while (end > 0 && b.data[end - 1] != '\n') --end;
+                if (end == 0) { carry.assign(b.data.begin(), b.data.end()); continue; }   // one line longer than the block
+            }
+            carry.assign(b.data.begin() + end, b.data.end());
+            b.end = end;
+            std::unique_lock<std::mutex> lk(m_);
+            cv_space_.wait(lk, [this] { return q_.size() < 3 || abort_; });
+            if (abort_) return;
+            q_.push_back(std::move(b));
+            lk.unlock();
+            cv_data_.notify_one();
+        }
+        { std::lock_guard<std::mutex> lk(m_); eof_ = true; }
+        cv_data_.notify_all();
+    }
+    gzFile gz_ = nullptr;
+    std::thread th_;
+    std::mutex m_;
+    std::condition_variable cv_data_, cv_space_;
+    std::deque<Block> q_;
+    bool eof_ = false, failed_ = false, abort_ = false;
+    long compressed_size_ = 0;
+    std::atomic<long> compressed_pos_{0}, uncompressed_{0};
+    std::atomic<double> inflate_s_{0.0};
+};
+
+// parse one Beagle data line [p, e) into out[0 .. 2n); returns false on a short line
+bool parse_line(const char* p, const char* e, int n_ind, float* out)
 {
     auto next = [&](const char*& a, const char*& b) -> bool {
         while (p < e && is_delim(*p)) ++p;
@@ -77,124 +227,319 @@ bool parse_line(const char* p, const char* e, int n_ind, float* out, std::string
         return true;
     };
     const char *a, *b;
-    if (!next(a, b)) return false;
-    site->assign(a, b);
-    if (!next(a, b) || !next(a, b)) return false;     // allele1, allele2
+    if (!next(a, b)) return false;                        // site id (kept by the caller)
+    if (!next(a, b) || !next(a, b)) return false;         // allele1, allele2
     for (int i = 0; i < n_ind; ++i) {
         if (!next(a, b)) return false;
         out[2 * i] = parse_float(a, b);
         if (!next(a, b)) return false;
         out[2 * i + 1] = parse_float(a, b);
-        if (!next(a, b)) return false;                // third GL: dropped (reader_cy.pyx:62-63)
+        if (!next(a, b)) return false;                    // third GL: dropped (reader_cy.pyx:62-63)
     }
     return true;
 }
 
-bool blank(const char* p, const char* e)
+// one allele-depth row: 2n non-negative integers -> saturating uint8 (255 = "255 or more") or int32
+template <class T>
+bool parse_ad_line(const char* p, const char* e, int ncol, T* out, bool* negative)
 {
-    for (; p < e; ++p) if (!is_delim(*p)) return false;
+    for (int c = 0; c < ncol; ++c) {
+        while (p < e && is_delim(*p)) ++p;
+        if (p >= e) return false;
+        bool neg = false;
+        if (*p == '-') { neg = true; ++p; } else if (*p == '+') ++p;
+        long v = 0;
+        bool any = false;
+        while (p < e && *p >= '0' && *p <= '9') { v = std::min(v * 10 + (*p - '0'), 2000000000L); ++p; any = true; }
+        if (p < e && *p == '.') { ++p; while (p < e && *p >= '0' && *p <= '9') ++p; }   // "3.0" as np.loadtxt(dtype=int32) would refuse; accept the integer part
+        if (!any || (p < e && !is_delim(*p))) return false;
+        if (neg && v != 0) *negative = true;
+        if (sizeof(T) == 1) out[c] = (T)std::min(v, 255L);
+        else out[c] = (T)(neg ? -v : v);
+    }
+    while (p < e && is_delim(*p)) ++p;
+    return p >= e;                                         // no extra columns
+}
+
+struct LineRef { const char *p, *e; };
+
+// ---- streaming state shared by the two readers ----
+struct Stream {
+    GzLines gz;
+    Pool* pool = nullptr;
+    int n_ind = 0, ncol = 0;                              // Beagle: individuals; AD: columns (2N)
+    bool is_ad = false, header_done = false;
+    std::vector<std::string> samples;
+    Block cur;                                            // block being consumed
+    std::vector<LineRef> lines;
+    size_t line_pos = 0;
+    long rows_seen = 0;                                   // data rows handed out or skipped so far
+    long keep_lo = 0, keep_hi = -1;                       // rows to convert (keep_hi < 0: all)
+    std::vector<std::string> sites;                       // Beagle: names of ALL rows seen (cheap; the CLI prints and intersects them)
+    bool keep_names = true;
+    double parse_s = 0.0;
+    ~Stream() { delete pool; }
+};
+
+bool index_block(Stream* S)
+{
+    S->lines.clear();
+    S->line_pos = 0;
+    const char* p = S->cur.data.data();
+    const char* e = p + S->cur.end;
+    if (!S->is_ad && !S->header_done) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+        const char* he = nl ? nl : e;
+        int tok = 0;
+        const char* q = p;
+        while (q < he) {
+            while (q < he && is_delim(*q)) ++q;
+            if (q >= he) break;
+            const char* a = q;
+            while (q < he && !is_delim(*q)) ++q;
+            ++tok;
+            if (tok > 3 && (tok - 3) % 3 == 1) S->samples.emplace_back(a, q);   // every 3rd GL column names a sample
+        }
+        if (tok < 6) { g_reader_error = "Beagle header has fewer than 6 columns"; return false; }
+        S->n_ind = (tok - 3) / 3;
+        S->header_done = true;
+        p = nl ? nl + 1 : e;
+    }
+    while (p < e) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+        const char* le = nl ? nl : e;
+        if (!blank(p, le)) {
+            if (S->is_ad && !S->header_done) {                // width of the matrix from its first row
+                int tok = 0;
+                const char* q = p;
+                while (q < le) { while (q < le && is_delim(*q)) ++q; if (q >= le) break; while (q < le && !is_delim(*q)) ++q; ++tok; }
+                S->ncol = tok;
+                S->header_done = true;
+            }
+            S->lines.push_back(LineRef{p, le});
+        }
+        p = nl ? nl + 1 : e;
+    }
     return true;
+}
+
+// make sure a block with unread lines is current; false at end of input
+bool ensure_lines(Stream* S)
+{
+    while (S->line_pos >= S->lines.size()) {
+        if (!S->gz.next(&S->cur)) {
+            if (S->gz.failed()) g_reader_error = "gzread failed (corrupt gzip stream?)";
+            return false;
+        }
+        if (!index_block(S)) return false;
+    }
+    return true;
+}
+
+Stream* open_stream(const char* path, int threads, bool is_ad)
+{
+    Stream* S = new Stream();
+    S->is_ad = is_ad;
+    if (!S->gz.open(path, &g_reader_error)) { delete S; return nullptr; }
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    S->pool = new Pool(std::min(threads, 64));
+    g_reader_error.clear();
+    if (!ensure_lines(S) && !S->header_done) {
+        if (g_reader_error.empty()) g_reader_error = is_ad ? "empty allele-depth file" : "empty Beagle file";
+        delete S;
+        return nullptr;
+    }
+    return S;
+}
+
+// convert up to max_rows of the rows inside the keep range into out (row-major, `width` elements per row);
+// rows outside the range are consumed without conversion.  Returns rows written, 0 at end of input, -1 on error.
+template <class T, class ParseFn>
+long stream_next(Stream* S, T* out, long max_rows, int width, ParseFn parse)
+{
+    long written = 0;
+    while (written < max_rows) {
+        if (!ensure_lines(S)) { if (!g_reader_error.empty()) return -1; break; }
+        const long avail = (long)(S->lines.size() - S->line_pos);
+        // rows of this block before the keep range: skip (names only)
+        long skip = 0;
+        if (S->rows_seen < S->keep_lo) skip = std::min(avail, S->keep_lo - S->rows_seen);
+        const bool past = S->keep_hi >= 0 && S->rows_seen + skip >= S->keep_hi;
+        long take = past ? 0 : avail - skip;
+        if (S->keep_hi >= 0) take = std::min(take, std::max(0L, S->keep_hi - (S->rows_seen + skip)));
+        take = std::min(take, max_rows - written);
+        const long consume = past ? avail : skip + take;
+        if (!S->is_ad && S->keep_names) {
+            const size_t base = S->sites.size();
+            S->sites.resize(base + (size_t)consume);
+            S->pool->run(consume, 4096, [&](long a, long b) {
+                for (long r = a; r < b; ++r) {
+                    const LineRef& ln = S->lines[S->line_pos + (size_t)r];
+                    const char* p = ln.p;
+                    while (p < ln.e && is_delim(*p)) ++p;
+                    const char* q = p;
+                    while (q < ln.e && !is_delim(*q)) ++q;
+                    S->sites[base + (size_t)r].assign(p, q);
+                }
+            });
+        }
+        if (take > 0) {
+            std::atomic<int> bad{0};
+            const auto t0 = std::chrono::steady_clock::now();
+            const size_t first = S->line_pos + (size_t)skip;
+            S->pool->run(take, 16, [&](long a, long b) {
+                for (long r = a; r < b; ++r) {
+                    const LineRef& ln = S->lines[first + (size_t)r];
+                    if (!parse(ln.p, ln.e, out + (size_t)(written + r) * width)) bad.store(1);
+                }
+            });
+            S->parse_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (bad.load()) {
+                g_reader_error = std::string(S->is_ad ? "allele-depth row" : "Beagle row") + " with a wrong number of columns or a malformed field near row " +
+                                 std::to_string(S->rows_seen + skip);
+                return -1;
+            }
+        }
+        S->line_pos += (size_t)consume;
+        S->rows_seen += consume;
+        written += take;
+        if (past && !S->keep_names) {                      // nothing more to keep and nobody wants the names: stop reading
+            break;
+        }
+    }
+    return written;
 }
 
 }  // namespace
 
 extern "C" {
 
-typedef struct wgs_beagle wgs_beagle;
-
 const char* wgs_beagle_last_error(void) { return g_reader_error.c_str(); }
+
+// ---- streaming interface ----
+int32_t wgs_beagle_stream_open(const char* path, int32_t threads, wgs_beagle_stream** out)
+{
+    *out = nullptr;
+    Stream* S = open_stream(path, threads, false);
+    if (!S) return 1;
+    S->ncol = 2 * S->n_ind;
+    *out = (wgs_beagle_stream*)S;
+    return 0;
+}
+int32_t wgs_beagle_stream_inds(const wgs_beagle_stream* s) { return ((const Stream*)s)->n_ind; }
+const char* wgs_beagle_stream_sample(const wgs_beagle_stream* s, int32_t i) { return ((const Stream*)s)->samples[(size_t)i].c_str(); }
+int32_t wgs_beagle_stream_keep(wgs_beagle_stream* s, int64_t row_lo, int64_t row_hi)
+{
+    Stream* S = (Stream*)s;
+    S->keep_lo = row_lo; S->keep_hi = row_hi;
+    return 0;
+}
+int32_t wgs_beagle_stream_names(wgs_beagle_stream* s, int32_t keep) { ((Stream*)s)->keep_names = keep != 0; return 0; }
+int64_t wgs_beagle_stream_next(wgs_beagle_stream* s, float* out, int64_t max_rows)
+{
+    Stream* S = (Stream*)s;
+    const int n = S->n_ind;
+    return stream_next<float>(S, out, max_rows, 2 * n, [n](const char* p, const char* e, float* o) { return parse_line(p, e, n, o); });
+}
+int64_t wgs_beagle_stream_rows_seen(const wgs_beagle_stream* s) { return ((const Stream*)s)->rows_seen; }
+const char* wgs_beagle_stream_site(const wgs_beagle_stream* s, int64_t row) { return ((const Stream*)s)->sites[(size_t)row].c_str(); }
+// estimate of the total number of data rows from what has been read so far (exact once the stream is exhausted):
+// compressed size x the compression ratio and bytes per row seen so far
+int64_t wgs_beagle_stream_estimate_rows(const wgs_beagle_stream* s)
+{
+    const Stream* S = (const Stream*)s;
+    const long cpos = S->gz.compressed_pos(), csize = S->gz.compressed_size(), ubytes = S->gz.uncompressed_bytes();
+    // rows indexed so far: those handed out plus the rest of the current block; the queue holds more bytes than rows we counted, so use the block sizes
+    const long rows_indexed = S->rows_seen + (long)(S->lines.size() - S->line_pos);
+    if (cpos <= 0 || ubytes <= 0 || rows_indexed <= 0 || csize <= 0) return -1;
+    // bytes per row from the CURRENT block only (its size is known exactly)
+    const double bpr = S->lines.empty() ? 0.0 : (double)S->cur.end / (double)S->lines.size();
+    if (bpr <= 0.0) return -1;
+    const double total_u = (double)ubytes * ((double)csize / (double)cpos);
+    return (int64_t)(total_u / bpr) + 1;
+}
+int32_t wgs_beagle_stream_stats(const wgs_beagle_stream* s, double* inflate_s, double* parse_s, int64_t* compressed_bytes, int64_t* uncompressed_bytes)
+{
+    const Stream* S = (const Stream*)s;
+    *inflate_s = S->gz.inflate_seconds(); *parse_s = S->parse_s;
+    *compressed_bytes = S->gz.compressed_size(); *uncompressed_bytes = S->gz.uncompressed_bytes();
+    return 0;
+}
+void wgs_beagle_stream_close(wgs_beagle_stream* s) { delete (Stream*)s; }
+
+// ---- allele depths: whitespace-separated integers, optionally gzipped (zlib reads plain text transparently) ----
+int32_t wgs_ad_stream_open(const char* path, int32_t threads, wgs_ad_stream** out)
+{
+    *out = nullptr;
+    Stream* S = open_stream(path, threads, true);
+    if (!S) return 1;
+    if (S->ncol <= 0 || (S->ncol & 1)) { g_reader_error = "allele-depth rows must hold two counts per individual"; delete S; return 1; }
+    S->n_ind = S->ncol / 2;
+    *out = (wgs_ad_stream*)S;
+    return 0;
+}
+int32_t wgs_ad_stream_inds(const wgs_ad_stream* s) { return ((const Stream*)s)->n_ind; }
+int32_t wgs_ad_stream_keep(wgs_ad_stream* s, int64_t row_lo, int64_t row_hi) { return wgs_beagle_stream_keep((wgs_beagle_stream*)s, row_lo, row_hi); }
+int64_t wgs_ad_stream_next_u8(wgs_ad_stream* s, uint8_t* out, int64_t max_rows)
+{
+    Stream* S = (Stream*)s;
+    const int nc = S->ncol;
+    bool negative = false;
+    const long r = stream_next<uint8_t>(S, out, max_rows, nc, [nc, &negative](const char* p, const char* e, uint8_t* o) { return parse_ad_line<uint8_t>(p, e, nc, o, &negative); });
+    if (r >= 0 && negative) { g_reader_error = "negative allele depth"; return -1; }
+    return r;
+}
+int64_t wgs_ad_stream_next_i32(wgs_ad_stream* s, int32_t* out, int64_t max_rows)
+{
+    Stream* S = (Stream*)s;
+    const int nc = S->ncol;
+    bool negative = false;
+    return stream_next<int32_t>(S, out, max_rows, nc, [nc, &negative](const char* p, const char* e, int32_t* o) { return parse_ad_line<int32_t>(p, e, nc, o, &negative); });
+}
+int64_t wgs_ad_stream_rows_seen(const wgs_ad_stream* s) { return ((const Stream*)s)->rows_seen; }
+int64_t wgs_ad_stream_estimate_rows(const wgs_ad_stream* s) { return wgs_beagle_stream_estimate_rows((const wgs_beagle_stream*)s); }
+int32_t wgs_ad_stream_stats(const wgs_ad_stream* s, double* inflate_s, double* parse_s, int64_t* compressed_bytes, int64_t* uncompressed_bytes)
+{
+    return wgs_beagle_stream_stats((const wgs_beagle_stream*)s, inflate_s, parse_s, compressed_bytes, uncompressed_bytes);
+}
+void wgs_ad_stream_close(wgs_ad_stream* s) { delete (Stream*)s; }
+
+// ---- whole-file interface (kept for callers that want the reference's one-call behaviour) ----
+struct Beagle {
+    std::vector<std::string> samples, sites;
+    std::vector<std::vector<float>> blocks;               // row-major pieces, concatenated on copy-out
+    int n_ind = 0;
+    long rows = 0;
+};
 
 int32_t wgs_beagle_open(const char* path, int32_t threads, wgs_beagle** out)
 {
     *out = nullptr;
-    gzFile gz = gzopen(path, "rb");
-    if (!gz) { g_reader_error = std::string("cannot open ") + path; return 1; }
-    gzbuffer(gz, 1 << 20);
+    wgs_beagle_stream* st = nullptr;
+    if (wgs_beagle_stream_open(path, threads, &st)) return 1;
+    Stream* S = (Stream*)st;
     Beagle* B = new Beagle();
-    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    threads = std::min(threads, 64);
-
-    const size_t CH = (size_t)64 << 20;
-    std::vector<char> buf;
-    std::string carry;
-    bool header_done = false, eof = false;
-    while (!eof) {
-        buf.assign(carry.begin(), carry.end());
-        size_t off = buf.size();
-        buf.resize(off + CH);
-        int got = gzread(gz, buf.data() + off, (unsigned)CH);
-        if (got < 0) { g_reader_error = "gzread failed (corrupt gzip stream?)"; gzclose(gz); delete B; return 1; }
-        buf.resize(off + (size_t)got);
-        eof = (size_t)got < CH;
-        // cut at the last newline unless this is the final block
-        size_t end = buf.size();
-        if (!eof) {
-            while (end > 0 && buf[end - 1] != '\n') --end;
-            if (end == 0) { carry.assign(buf.begin(), buf.end()); continue; }   // one line longer than the block
-        }
-        carry.assign(buf.begin() + end, buf.end());
-        const char* p = buf.data();
-        const char* e = buf.data() + end;
-        if (!header_done) {
-            const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
-            const char* he = nl ? nl : e;
-            int tok = 0;
-            const char* q = p;
-            while (q < he) {
-                while (q < he && is_delim(*q)) ++q;
-                if (q >= he) break;
-                const char* a = q;
-                while (q < he && !is_delim(*q)) ++q;
-                ++tok;
-                if (tok > 3 && (tok - 3) % 3 == 1) B->samples.emplace_back(a, q);   // every 3rd GL column names a sample
-            }
-            if (tok < 6) { g_reader_error = "Beagle header has fewer than 6 columns"; gzclose(gz); delete B; return 1; }
-            B->n_ind = (tok - 3) / 3;
-            header_done = true;
-            p = nl ? nl + 1 : e;
-        }
-        // index the lines of this block
-        std::vector<std::pair<const char*, const char*>> lines;
-        while (p < e) {
-            const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
-            const char* le = nl ? nl : e;
-            if (!blank(p, le)) lines.emplace_back(p, le);
-            p = nl ? nl + 1 : e;
-        }
-        if (lines.empty()) continue;
-        const long nl_ = (long)lines.size();
-        const int n = B->n_ind;
-        B->blocks.emplace_back((size_t)nl_ * 2 * n);
-        B->block_rows.push_back(nl_);
-        float* dst = B->blocks.back().data();
-        std::vector<std::string> names((size_t)nl_);
-        std::vector<int> bad(threads, 0);
-        auto work = [&](int t) {
-            for (long r = t; r < nl_; r += threads)
-                if (!parse_line(lines[r].first, lines[r].second, n, dst + (size_t)r * 2 * n, &names[r])) bad[t] = 1;
-        };
-        if (threads == 1 || nl_ < 64) { for (int t = 0; t < threads; ++t) work(t); }
-        else {
-            std::vector<std::thread> pool;
-            for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
-            for (auto& th : pool) th.join();
-        }
-        for (int t = 0; t < threads; ++t) if (bad[t]) {
-            g_reader_error = "Beagle row with fewer columns than the header near site " + std::to_string(B->rows);
-            gzclose(gz); delete B; return 1;
-        }
-        for (auto& s : names) B->sites.push_back(std::move(s));
-        B->rows += nl_;
+    B->n_ind = S->n_ind;
+    const long chunk = std::max<long>(1, ((long)64 << 20) / std::max(1, 8 * S->n_ind));
+    for (;;) {
+        std::vector<float> blk((size_t)chunk * 2 * S->n_ind);
+        const long r = wgs_beagle_stream_next(st, blk.data(), chunk);
+        if (r < 0) { wgs_beagle_stream_close(st); delete B; return 1; }
+        if (r == 0) break;
+        blk.resize((size_t)r * 2 * S->n_ind);
+        B->blocks.push_back(std::move(blk));
+        B->rows += r;
     }
-    gzclose(gz);
-    if (!header_done) { g_reader_error = "empty Beagle file"; delete B; return 1; }
+    B->samples = S->samples;
+    B->sites = std::move(S->sites);
+    wgs_beagle_stream_close(st);
     *out = (wgs_beagle*)B;
     return 0;
 }
 
 int64_t wgs_beagle_sites(const wgs_beagle* b) { return ((const Beagle*)b)->rows; }
 int32_t wgs_beagle_inds(const wgs_beagle* b) { return ((const Beagle*)b)->n_ind; }
-const char* wgs_beagle_sample(const wgs_beagle* b, int32_t i) { return ((const Beagle*)b)->samples[i].c_str(); }
+const char* wgs_beagle_sample(const wgs_beagle* b, int32_t i) { return ((const Beagle*)b)->samples[(size_t)i].c_str(); }
 const char* wgs_beagle_site(const wgs_beagle* b, int64_t s) { return ((const Beagle*)b)->sites[(size_t)s].c_str(); }
 
 int32_t wgs_beagle_copy(const wgs_beagle* b, float* L_out)

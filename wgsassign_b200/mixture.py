@@ -7,14 +7,23 @@ including the un-normalised ``exp(loglik)`` (mixture.py:29-30).
 import numpy as np
 
 
-def em_mix(L_mat, L_mat_index, iter):
+def em_mix(L_mat, L_mat_index, iter, logsumexp=False):
     """Fixed-iteration EM per harvest group (mixture.py:10-39).  Returns a string array
-    [groups, 1 + sources]: group name, then the mixing proportions of the last iteration."""
+    [groups, 1 + sources]: group name, then the mixing proportions of the last iteration.
+
+    logsumexp=False is the reference: ``exp(loglik)`` un-normalised (mixture.py:29-30), which underflows to 0 for
+    genome-scale log-likelihoods (every entry below about -745) and then yields NaN rows.  logsumexp=True
+    (``--em_mix_logsumexp``) subtracts each individual's largest log-likelihood first: the assignment probabilities
+    ``like * pi / sum(like * pi)`` are invariant under a per-row factor, so wherever the reference's arithmetic is
+    finite the two agree to rounding, and the hardened form stays finite everywhere."""
     n_source = L_mat.shape[1]
     groups = np.unique(L_mat_index[:, 1])
     props = np.empty((len(groups), n_source), np.float32)
     for g, name in enumerate(groups):
-        like = np.exp(np.ascontiguousarray(L_mat[np.flatnonzero(L_mat_index[:, 1] == name), :]))
+        ll = np.ascontiguousarray(L_mat[np.flatnonzero(L_mat_index[:, 1] == name), :])
+        if logsumexp:
+            ll = ll - np.max(ll, axis=1, keepdims=True)
+        like = np.exp(ll)
         pi = np.full(n_source, 1.0 / n_source)
         for _ in range(iter):
             post = like * pi                                  # == like @ diag(pi)

@@ -108,6 +108,45 @@ def context(L, pop_of_ind=None, K=0, async_upload=False):
     return ctx
 
 
+def stream_context(beagle, pop_of_ind=None, K=0, threads=0, rows=None):
+    """Parse a Beagle file straight into a resident context: every finished row block is queued for upload while the
+    next one is parsed (`readBeagle(on_block=...)` + `Context.upload_gl_begin/rows/end`).  Returns
+    (ctx, L, sample_names, site_names); the context is registered for L, so the entry points that are later called
+    with this array find it resident.  pop_of_ind must already be known (the device layout is population-sorted)."""
+    from . import reader
+    ctx = _state["ctx"]
+    if ctx is None:
+        ctx = _lib.Context(device_index())
+        for name, value in _options.items():
+            ctx.set_option(name, value)
+        _state["ctx"] = ctx
+    _state.update(key=None, ds_key=None, ad_key=None)
+    state = {"begun": False, "cap": 0}
+
+    def on_block(arr, r0, r1):
+        n = arr.shape[1] // 2
+        if not state["begun"] or arr.shape[0] != state["cap"]:      # first block, or the reader grew its buffer: start over
+            if pop_of_ind is None:
+                ctx.set_pops(np.zeros(n, np.int32), 0)
+            else:
+                if len(pop_of_ind) != n:
+                    raise ValueError("Number of individuals in beagle and reference ID file do not match!")
+                ctx.set_pops(pop_of_ind, K)
+            dist.attach(ctx)
+            ctx.upload_gl_begin(arr.shape[0], n)
+            state.update(begun=True, cap=arr.shape[0])
+            if r0 > 0:
+                ctx.upload_gl_rows(arr, 0, r0)
+        ctx.upload_gl_rows(arr, r0, r1)
+    L, samples, sites = reader.readBeagle(beagle, threads, rows=rows, on_block=on_block)
+    if state["begun"]:
+        ctx.upload_gl_end(L.shape[0])
+        ctx._pending_L = L
+        pkey = None if pop_of_ind is None else (int(K), np.asarray(pop_of_ind, np.int32).tobytes())
+        _state["key"] = (_sig(L), pkey)
+    return ctx, L, samples, sites
+
+
 def with_downsampled(ctx, L_ds):
     key = _sig(L_ds)
     if _state["ds_key"] != key:
@@ -121,7 +160,8 @@ def with_ad(ctx, AD):
     key = _sig(AD)
     if _state["ad_key"] != key:
         _state["ad_key"] = None                            # a failed upload must not leave a stale key behind
-        ctx.upload_ad(np.ascontiguousarray(AD, dtype=np.int32))
+        # uint8 (255 = "255 reads or more", the streaming reader's form) goes up as it is; anything else as the reference's int32
+        ctx.upload_ad(np.ascontiguousarray(AD) if AD.dtype == np.uint8 else np.ascontiguousarray(AD, dtype=np.int32))
         _state["ad_key"] = key
     return ctx
 
