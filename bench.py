@@ -293,6 +293,64 @@ def family(ctx, name, peak_gbs, sites=None, with_traffic=True):
     return out
 
 
+def ingest_probe(cfg, ctx_device):
+    """Throughput of the text ingestion (timed separately from the metric, as BASELINE.json asks): a synthetic Beagle file
+    and allele-depth file of this configuration's width - ~200 MB of text each, gzip level 1, built from one 200-row
+    block repeated as separate gzip members (rows are longer than deflate's window, so the ratio is that of real data) -
+    through the streaming readers, and the Beagle file once more straight into a resident context (parse + upload
+    overlapped, what the CLI does)."""
+    import gzip, io, tempfile
+    from wgsassign_b200 import reader, session, synth
+    n = cfg["n_ind"]
+    rows_blk = 200
+    d = synth.synth(rows_blk, n, cfg["n_pop"], seed=7, with_ad=True)
+    g2 = np.abs(np.round(1.0 - d["L"][:, 0::2].astype(np.float64) - d["L"][:, 1::2], 6))
+    cells = np.empty((rows_blk, 3 * n))
+    cells[:, 0::3], cells[:, 1::3], cells[:, 2::3] = d["L"][:, 0::2], d["L"][:, 1::2], g2
+    buf = io.StringIO()
+    np.savetxt(buf, cells, fmt="%.6f", delimiter="\t")
+    body = "".join("chr1_%d\t0\t1\t%s\n" % (i, ln) for i, ln in enumerate(buf.getvalue().splitlines())).encode()
+    reps = max(1, int(200e6 / len(body)))
+    header = ("marker\tallele1\tallele2" + "".join("\t%s\t%s\t%s" % (("s%d" % i,) * 3) for i in range(n)) + "\n").encode()
+    tmp = tempfile.mkdtemp()
+    pb, pa = os.path.join(tmp, "x.beagle.gz"), os.path.join(tmp, "x.ad.txt.gz")
+    with open(pb, "wb") as fh:
+        fh.write(gzip.compress(header, 1))
+        member = gzip.compress(body, 1)
+        for _ in range(reps):
+            fh.write(member)
+    abuf = io.StringIO()
+    np.savetxt(abuf, d["AD"], fmt="%d")
+    abody = abuf.getvalue().encode()
+    areps = max(1, int(100e6 / len(abody)))
+    with open(pa, "wb") as fh:
+        member = gzip.compress(abody, 1)
+        for _ in range(areps):
+            fh.write(member)
+    threads = os.cpu_count() or 1
+    out = {"threads": threads, "note": "timed separately from the metric; parse = (float)atof-exact conversion into pinned memory"}
+    t0 = time.perf_counter()
+    L, _, sites = reader.readBeagle(pb, threads)
+    out["beagle"] = dict(reader.last_stats["beagle"], shape=[int(L.shape[0]), int(L.shape[1])])
+    del L
+    session.reset()
+    t0 = time.perf_counter()
+    ctx, L, _, _ = session.stream_context(pb, pop_assignment(cfg), cfg["n_pop"], threads)
+    ctx.upload_wait()
+    wall = time.perf_counter() - t0
+    st = reader.last_stats["beagle"]
+    out["beagle_to_device"] = {"wall_s": wall, "compressed_mb_per_s": st["compressed_bytes"] / 1e6 / wall,
+                               "uncompressed_mb_per_s": st["uncompressed_bytes"] / 1e6 / wall, "matrix_gb_per_s": L.nbytes / 1e9 / wall,
+                               "path": "readBeagle(on_block) + wgs_upload_gl_begin/rows/end: the upload of block b overlaps the parsing of block b+1"}
+    session.reset()
+    AD = reader.readAD(pa, threads)
+    out["allele_depths"] = dict(reader.last_stats["ad"], shape=[int(AD.shape[0]), int(AD.shape[1])], dtype=str(AD.dtype))
+    for f in (pb, pa):
+        os.unlink(f)
+    os.rmdir(tmp)
+    return out
+
+
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
@@ -533,6 +591,11 @@ def main():
             ms, nb = ctx.debug_stream(mode)
             extra[nm] = {"ms": ms, "gb": nb / 1e9, "achieved_gbs": nb / 1e9 / (ms * 1e-3)}
         ctx.timing_reset(False)
+        if world == 1:
+            try:
+                extra["ingest"] = ingest_probe(cfg, local)
+            except Exception as e:                              # never let the side measurement take the line down
+                extra["ingest"] = {"error": repr(e)}
 
     # ---- CPU baseline + parity on the same slice (rank 0, one GPU) ----
     cpu_b, parity = None, None

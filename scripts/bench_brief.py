@@ -4,6 +4,11 @@ e = d.get("e2e") or {}
 print("value %.3e  ms/step %.1f  e2e %.3e (%.1f ms)  launches %d  n_gpus %d  %s" % (d["value"], d["ms_per_step"], e.get("value", 0), e.get("ms_per_step", 0), d["gpu_launches"], d["n_gpus"], d["config"]["workload"][:40]))
 for k, v in d["kernels"].items():
     if not v: continue
+    if k == "ingest":
+        for kk, vv in v.items():
+            if isinstance(vv, dict): print("  ingest %-16s %7.1f MB/s compressed  %7.1f MB/s text  wall %.2f s" % (kk, vv.get("compressed_mb_per_s", 0), vv.get("uncompressed_mb_per_s", 0), vv.get("wall_s", 0)))
+            else: print("  ingest", kk, vv)
+        continue
     if "launches" not in v: print("  %-14s %.3f ms  %.0f GB/s" % (k, v["ms"], v["achieved_gbs"]))
     else:
         extra = " | with aux %.3f ms/call (%.3f of HBM)" % (v["ms_per_call_with_aux"], v["hbm_frac_with_aux"]) if "ms_per_call_with_aux" in v else ""

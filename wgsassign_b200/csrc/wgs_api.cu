@@ -1223,7 +1223,8 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
     if (packed) {
         // ring of row groups: as many stages as fit in ~100 KB (two resident blocks per SM), at least 3
         const size_t group_bytes = (size_t)best.rows_per_pass * loo5_row_units(n) * 16;
-        int stages = (int)std::min<size_t>(kLoo5MaxStages, (100 * 1024) / std::max<size_t>(group_bytes, 1));
+        const size_t ring_budget = (opt(ctx, "loo_variant", 0) == 1 && !best.big) ? 64 * 1024 : 100 * 1024;   // 3 or 2 resident blocks per SM
+        int stages = (int)std::min<size_t>(kLoo5MaxStages, ring_budget / std::max<size_t>(group_bytes, 1));
         if (int o = opt(ctx, "loo_stages", 0)) stages = o;
         best.stages = std::max(3, std::min(stages, kLoo5MaxStages));
         best.passes = 1;
@@ -1245,7 +1246,12 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
         CU(cudaFuncSetAttribute(KERN, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, best.block, best.smem));                        \
     } while (0)
-    if (packed) { if (best.big) LOO_PREP((loo_em_step5_kernel<512, 1>)); else if (opt(ctx, "loo_occ3")) LOO_PREP((loo_em_step5_kernel<256, 3>)); else LOO_PREP((loo_em_step5_kernel<256, 2>)); }
+    if (packed) {
+        if (best.big) LOO_PREP((loo_em_step5_kernel<512, 1>));
+        else if (opt(ctx, "loo_variant", 0) == 1) LOO_PREP((loo_em_step5_kernel<256, 3, 2>));
+        else if (opt(ctx, "loo_occ3")) LOO_PREP((loo_em_step5_kernel<256, 3>));
+        else LOO_PREP((loo_em_step5_kernel<256, 2>));
+    }
     else        { if (best.big) LOO_PREP((loo_em_step4_kernel<512, 1>)); else LOO_PREP((loo_em_step4_kernel<256, 3>)); }
 #undef LOO_PREP
     best.grid = ctx->num_sm * std::max(occ, 1);
@@ -1384,6 +1390,9 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         if (lc.packed) {
             if (lc.big)
                 LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
+                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
+            else if (opt(ctx, "loo_variant", 0) == 1)
+                LAUNCH("loo_em", (loo_em_step5_kernel<256, 3, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
                        pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
             else if (!opt(ctx, "loo_occ3"))
                 LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,

@@ -2069,9 +2069,10 @@ __device__ __forceinline__ float loo5_own(float g0, float g1, float g2, const Lo
     const float den = fmaf(g0, c.a, g1 + num);
     return num * fast_rcp(den);
 }
-__device__ __forceinline__ void loo5_quad(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3, f32x2 P4, const Loo5Coef (&c)[4], f32x2 (&acc)[4]) {
+template <int NP>
+__device__ __forceinline__ void loo5_quad(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3, f32x2 P4, const Loo5Coef (&c)[NP], f32x2 (&acc)[NP]) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NP; ++k) {
         const f32x2 u = ffma2(P0, c[k].A, P1);
         const f32x2 v = ffma2(P4, c[k].B, P3);
         const f32x2 D = ffma2(v, c[k].B, ffma2(u, c[k].A, P2));
@@ -2090,10 +2091,11 @@ __device__ __forceinline__ void loo5_quad(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3
 // The first pair (low lanes) of a quad only, in scalar arithmetic: the same fused operations on half the lanes.
 // For a quad whose second pair is padding (n mod 4 = 1 or 2) this is half the FMA-pipe time and one reciprocal
 // instead of two per problem.
-__device__ __forceinline__ void loo5_pair_lo(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3, f32x2 P4, const Loo5Coef (&c)[4], f32x2 (&acc)[4]) {
+template <int NP>
+__device__ __forceinline__ void loo5_pair_lo(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3, f32x2 P4, const Loo5Coef (&c)[NP], f32x2 (&acc)[NP]) {
     const float p0 = unpack2(P0).x, p1 = unpack2(P1).x, p2 = unpack2(P2).x, p3 = unpack2(P3).x, p4 = unpack2(P4).x;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NP; ++k) {
         const float a = c[k].a, b = c[k].b;
         const float ah = unpack2(c[k].AH).x, b43 = unpack2(c[k].B43).x, bh = unpack2(c[k].BH).x;
         const float u = fmaf(p0, a, p1);
@@ -2114,7 +2116,10 @@ __device__ __forceinline__ void loo5_pair_lo(f32x2 P0, f32x2 P1, f32x2 P2, f32x2
 // groups ahead of use.  (One copy per row from warp 0 made that warp 50 % slower than the others, and
 // every other warp then waited for it at "full": 23 % of all stall samples.)
 constexpr int kLoo5MaxStages = 6;
-template <int MAXT, int MINB>
+// NP = problems evaluated per pass over a site row: 4 (one pass, 124 registers, 2 blocks of 256 per SM) or 2 (two passes
+// over the same shared-memory row with half the coefficient registers: <= 85 registers, 3 blocks per SM - the FMA pipe
+// was only 57 % busy at 16 warps per SM, ncu r2).
+template <int MAXT, int MINB, int NP = 4>
 __global__ void __launch_bounds__(MAXT, MINB)
 loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
                     int col0, int n, int rows_per_pass,
@@ -2202,42 +2207,49 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
         if (staged) mbar_wait(&full[slot], phase);              // this group has landed
         if (okp && dbg != 2) {
             const float fin[4] = {fq.x, fq.y, fq.z, fq.w};
-            Loo5Coef c[4];
-            f32x2 acc[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { c[k] = loo5_coef(fin[k]); acc[k] = 0ull; }
             const ulonglong2* row = pk0 + ((size_t)slot * TS + r) * ru;
             const int nfull = nq >> 1;                          // cells with both quads
-#pragma unroll 1
-            for (int cc = 0; cc < nfull; ++cc) {
-                const ulonglong2 v0 = row[5 * cc], v1 = row[5 * cc + 1], v2 = row[5 * cc + 2], v3 = row[5 * cc + 3], v4 = row[5 * cc + 4];
-                loo5_quad(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
-                loo5_quad(v2.y, v3.x, v3.y, v4.x, v4.y, c, acc);
-            }
-            if (nq & 1) {
-                const ulonglong2 v0 = row[5 * nfull], v1 = row[5 * nfull + 1], v2 = row[5 * nfull + 2];
-                if (last_pair_only) loo5_pair_lo(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);   // the quad's second pair is padding
-                else loo5_quad(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
-            }
             // own terms: the four members of quad ti, from the raw pairs at the end of the row
             const float4* rawrow = reinterpret_cast<const float4*>(row + 5 * nc);
             const float4 ga = rawrow[2 * ti], gc = rawrow[2 * ti + 1];
-            const float own[4] = {loo5_own(ga.x, ga.y, third_gl(ga.x, ga.y), c[0]), loo5_own(ga.z, ga.w, third_gl(ga.z, ga.w), c[1]),
-                                  loo5_own(gc.x, gc.y, third_gl(gc.x, gc.y), c[2]), loo5_own(gc.z, gc.w, third_gl(gc.z, gc.w), c[3])};
+            const float og0[4] = {ga.x, ga.z, gc.x, gc.z}, og1[4] = {ga.y, ga.w, gc.y, gc.w};
             float fo[4], dq[4];
+#pragma unroll 1
+            for (int h0 = 0; h0 < 4; h0 += NP) {
+                Loo5Coef c[NP];
+                f32x2 acc[NP];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 a = unpack2(acc[k]);
-                float fn = ((a.x + a.y) - own[k]) * inv_div;
-                if (fn < 1e-12f) fn = 1e-12f;                   // comparisons are false for NaN: NaN survives
-                if (fn > 0.99999994f) fn = 0.99999994f;
-                fo[k] = fin[k];                                 // frozen / masked problems keep their value
-                dq[k] = 0.f;
-                if (okp & (1u << k)) {                          // (v1 - v2) * (v1 - v2) as rmse1d forms it (emMAF_cy.pyx:31): no FMA
-                    const float d = __fsub_rn(fn, fin[k]);
-                    dq[k] = __fmul_rn(d, d);
-                    ssq[k] = __fadd_rn(ssq[k], dq[k]);
-                    fo[k] = fn;
+                for (int k = 0; k < NP; ++k) { c[k] = loo5_coef(NP == 4 ? fin[k] : (h0 ? fin[2 + k] : fin[k])); acc[k] = 0ull; }
+#pragma unroll 1
+                for (int cc = 0; cc < nfull; ++cc) {
+                    const ulonglong2 v0 = row[5 * cc], v1 = row[5 * cc + 1], v2 = row[5 * cc + 2], v3 = row[5 * cc + 3], v4 = row[5 * cc + 4];
+                    loo5_quad<NP>(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
+                    loo5_quad<NP>(v2.y, v3.x, v3.y, v4.x, v4.y, c, acc);
+                }
+                if (nq & 1) {
+                    const ulonglong2 v0 = row[5 * nfull], v1 = row[5 * nfull + 1], v2 = row[5 * nfull + 2];
+                    if (last_pair_only) loo5_pair_lo<NP>(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);   // the quad's second pair is padding
+                    else loo5_quad<NP>(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
+                }
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    const int kk = NP == 4 ? k : (h0 ? 2 + k : k);          // member of the quad
+                    const float g0 = NP == 4 ? og0[k] : (h0 ? og0[2 + k] : og0[k]), g1 = NP == 4 ? og1[k] : (h0 ? og1[2 + k] : og1[k]);
+                    const float own = loo5_own(g0, g1, third_gl(g0, g1), c[k]);
+                    const float f_in = NP == 4 ? fin[k] : (h0 ? fin[2 + k] : fin[k]);
+                    const float2 a = unpack2(acc[k]);
+                    float fn = ((a.x + a.y) - own) * inv_div;
+                    if (fn < 1e-12f) fn = 1e-12f;               // comparisons are false for NaN: NaN survives
+                    if (fn > 0.99999994f) fn = 0.99999994f;
+                    float fo_k = f_in, dq_k = 0.f;              // frozen / masked problems keep their value
+                    if (okp & (1u << kk)) {                     // (v1 - v2) * (v1 - v2) as rmse1d forms it (emMAF_cy.pyx:31): no FMA
+                        const float d = __fsub_rn(fn, f_in);
+                        dq_k = __fmul_rn(d, d);
+                        fo_k = fn;
+                    }
+                    if (NP == 4) { fo[k] = fo_k; dq[k] = dq_k; ssq[k] = __fadd_rn(ssq[k], dq_k); }
+                    else if (h0 == 0) { fo[k] = fo_k; dq[k] = dq_k; ssq[k] = __fadd_rn(ssq[k], dq_k); }
+                    else { fo[2 + k] = fo_k; dq[2 + k] = dq_k; ssq[2 + k] = __fadd_rn(ssq[2 + k], dq_k); }
                 }
             }
             *reinterpret_cast<float4*>(&F[(tl * TS + r) * (long)ldf + c0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
