@@ -556,6 +556,25 @@ def main():
                         "cfg5": "wgs_upload_gl + wgs_fisher_partial + wgs_pop_like_partial"}[args.config]}
         if args.config == "cfg3":
             e2e["identical_to_resident"] = bool(np.array_equal(r2["ll"], full_res["ll"]))
+            # the upload alone, every rank at once: one strided DMA per population slab (what e2e uses) against the chunked
+            # contiguous copy + permutation kernel - shows what the host memory system gives N concurrent uploads
+            up = {}
+            for name, fn in (("slab_dma", lambda: (ctx2.upload_gl_async(Lh), ctx2.upload_wait())), ("chunked_repack", lambda: ctx2.upload_gl(Lh))):
+                ctx2.set_pops(pop_of, N_POP)
+                fn()
+                barrier()
+                t0 = time.perf_counter()
+                fn()
+                barrier()
+                dtu = time.perf_counter() - t0
+                if world > 1:
+                    tt = torch.tensor([dtu], dtype=torch.float64, device="cuda")
+                    td.all_reduce(tt, op=td.ReduceOp.MAX)
+                    dtu = float(tt.item())
+                up[name] = {"ms": dtu * 1e3, "gb_per_s_per_gpu": Lh.nbytes / 1e9 / dtu, "gb_per_s_all": Lh.nbytes * world / 1e9 / dtu}
+            e2e["upload_only"] = up
+            dist.attach(ctx2)
+            ctx2.upload_gl(Lh)
         else:
             e2e["note"] = ("bounded sample: %d of the %d sites per GPU (the full host matrices, %.0f GB per rank, do not fit N times in host memory)"
                            % (M_e, M_local, (Lh.nbytes + (ADh.nbytes if ADh is not None else 0)) * M_local / M_e / 1e9))

@@ -125,7 +125,6 @@ const char* const kOptionNames[] = {
     "em_no_lookahead",    // 1: read every stop decision before queueing the next iteration
     "loo_v4", "loo_nofirst", "loo_fullfill", "loo_block", "loo_stages", "loo_passes", "loo_occ3", "loo_dbg", "prepack_v1",
     "loo_by_pop",         // 1: leave-one-out EM population by population (one packed-row buffer at a time); -1: never
-    "loo_variant",        // inner-loop variant of the packed leave-one-out step kernel (experiments)
     "upload_sync",        // 1: wgs_upload_gl_async falls back to the chunked synchronous upload
     "ztally_groups",      // column groups of the rank-chained class tally (default 1: a group launch is latency-bound and takes as long as the full one)
     "z_exact_means",      // 1: order-independent fixed-point class means (NOT the reference's float32 means)
@@ -852,7 +851,7 @@ int em_pin_reserve(wgs_ctx* ctx, size_t ints)
     return 0;
 }
 
-int em_state_init(wgs_ctx* ctx, EmState& st, int np, int ld, int nblocks, const std::vector<int>& active0, bool exact = false)
+int em_state_init(wgs_ctx* ctx, EmState& st, int np, int ld, int nblocks, const std::vector<int>& active0, bool exact = false, bool zero_d2 = true)
 {
     st.np = np; st.ld = ld; st.nblocks = nblocks;
     if (buf_alloc(ctx, st.partials, (size_t)nblocks * ld * sizeof(double)) || buf_alloc(ctx, st.ssq, (size_t)np * sizeof(double)) ||
@@ -879,7 +878,8 @@ int em_state_init(wgs_ctx* ctx, EmState& st, int np, int ld, int nblocks, const 
         const long M = ctx->M();
         if (buf_alloc(ctx, st.d2, (size_t)std::max<long>(M, 1) * ctx->ldg * sizeof(float)) || buf_alloc(ctx, st.serial, (size_t)np * sizeof(float)) ||
             buf_alloc(ctx, st.carry, (size_t)np * sizeof(float)) || buf_alloc(ctx, st.uncertain, (size_t)np * sizeof(int))) return 1;
-        CU(cudaMemsetAsync(st.d2.p, 0, (size_t)std::max<long>(M, 1) * ctx->ldg * sizeof(float), ctx->stream));   // masked sites are never written: + 0
+        if (zero_d2)                                             // masked sites are never written and must read as + 0; without a
+            CU(cudaMemsetAsync(st.d2.p, 0, (size_t)std::max<long>(M, 1) * ctx->ldg * sizeof(float), ctx->stream));   // mask every entry of an active problem is rewritten each iteration
         CU(cudaMemsetAsync(st.serial.p, 0, (size_t)np * sizeof(float), ctx->stream));
     }
     return 0;
@@ -1223,8 +1223,7 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
     if (packed) {
         // ring of row groups: as many stages as fit in ~100 KB (two resident blocks per SM), at least 3
         const size_t group_bytes = (size_t)best.rows_per_pass * loo5_row_units(n) * 16;
-        const size_t ring_budget = (opt(ctx, "loo_variant", 0) == 1 && !best.big) ? 64 * 1024 : 100 * 1024;   // 3 or 2 resident blocks per SM
-        int stages = (int)std::min<size_t>(kLoo5MaxStages, ring_budget / std::max<size_t>(group_bytes, 1));
+        int stages = (int)std::min<size_t>(kLoo5MaxStages, (100 * 1024) / std::max<size_t>(group_bytes, 1));
         if (int o = opt(ctx, "loo_stages", 0)) stages = o;
         best.stages = std::max(3, std::min(stages, kLoo5MaxStages));
         best.passes = 1;
@@ -1248,7 +1247,6 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
     } while (0)
     if (packed) {
         if (best.big) LOO_PREP((loo_em_step5_kernel<512, 1>));
-        else if (opt(ctx, "loo_variant", 0) == 1) LOO_PREP((loo_em_step5_kernel<256, 3, 2>));
         else if (opt(ctx, "loo_occ3")) LOO_PREP((loo_em_step5_kernel<256, 3>));
         else LOO_PREP((loo_em_step5_kernel<256, 2>));
     }
@@ -1353,7 +1351,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         }
     }
     EmState st;
-    if (em_state_init(ctx, st, ldg, ldg, nblocks, active0, opt(ctx, "rmse_exact", 1) != 0)) return 1;
+    if (em_state_init(ctx, st, ldg, ldg, nblocks, active0, opt(ctx, "rmse_exact", 1) != 0, mask != nullptr)) return 1;
     if (force_chain) st.chain_always = true;
     float* const D2 = st.d2.as<float>();                         // null when the exact stop rule is switched off
     // When every real column is an active problem of a population that loo_first serves, iteration 1 writes all of
@@ -1390,9 +1388,6 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         if (lc.packed) {
             if (lc.big)
                 LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
-                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
-            else if (opt(ctx, "loo_variant", 0) == 1)
-                LAUNCH("loo_em", (loo_em_step5_kernel<256, 3, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
                        pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
             else if (!opt(ctx, "loo_occ3"))
                 LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,

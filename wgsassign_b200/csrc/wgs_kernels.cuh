@@ -2116,9 +2116,10 @@ __device__ __forceinline__ void loo5_pair_lo(f32x2 P0, f32x2 P1, f32x2 P2, f32x2
 // groups ahead of use.  (One copy per row from warp 0 made that warp 50 % slower than the others, and
 // every other warp then waited for it at "full": 23 % of all stall samples.)
 constexpr int kLoo5MaxStages = 6;
-// NP = problems evaluated per pass over a site row: 4 (one pass, 124 registers, 2 blocks of 256 per SM) or 2 (two passes
-// over the same shared-memory row with half the coefficient registers: <= 85 registers, 3 blocks per SM - the FMA pipe
-// was only 57 % busy at 16 warps per SM, ncu r2).
+// NP = problems evaluated per pass over a site row: 4 (one pass, 124 registers, 2 blocks of 256 per SM).  NP = 2 (two
+// passes over the same shared-memory row with half the coefficient registers: 80 registers, 3 blocks per SM) was tried
+// because the FMA pipe is only 57 % busy at 16 warps per SM (ncu r2): the kernel ran at HALF the speed, like every
+// other attempt to fit this loop into 80 registers - it is not instantiated.
 template <int MAXT, int MINB, int NP = 4>
 __global__ void __launch_bounds__(MAXT, MINB)
 loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
