@@ -803,7 +803,7 @@ struct EmState {
     std::vector<int> h_active, h_iters;
     int slot_c0[2] = {0, 0}, slot_nc[2] = {0, 0};
     // exact stop rule (the reference's sequential float32 sum, emMAF_cy.pyx:26-33) for checks that land inside the
-    // band in which the exact FP64 sum cannot decide: D2 [ldg][M] (problem-major) = the squared changes of the last iteration
+    // band in which the exact FP64 sum cannot decide: D2 [ldg / 4][M][4] (quad-major) = the squared changes of the last iteration
     DevBuf d2, serial, carry, uncertain;
     bool exact = false;
     bool chain_on = false, chain_always = false, missed = false;   // site-sharded runs: the rank chain is queued only near convergence

@@ -1730,7 +1730,7 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
                     const unsigned char* __restrict__ mask,      // [M][ldg] or null
                     double* __restrict__ partials,               // [gridDim.x][ldg]
                     long ntiles,
-                    float* __restrict__ D2)                      // [ldg][M] (problem-major) or null: this iteration's squared change per (problem, site)
+                    float* __restrict__ D2)                      // [ldg / 4][M][4] (quad-major) or null: this iteration's squared change per (problem, site)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -1859,10 +1859,7 @@ loo_em_step4_kernel(const float2* __restrict__ G, int ldg, long M,
                 }
             }
             *reinterpret_cast<float4*>(&F[(s0 + sl) * (long)ldf + c0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
-            if (D2) {
-                float* d2p = D2 + (long)c0 * M + (s0 + sl);
-                d2p[0] = dq[0]; d2p[M] = dq[1]; d2p[2 * M] = dq[2]; d2p[3 * M] = dq[3];
-            }
+            if (D2) *reinterpret_cast<float4*>(&D2[((long)(c0 >> 2) * M + (s0 + sl)) * 4]) = make_float4(dq[0], dq[1], dq[2], dq[3]);
         }
         const long nxt = tl + gridDim.x;
         if (nxt < ntiles) {                                     // the next tile's raw rows landed while this one computed
@@ -2131,7 +2128,7 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
                     long ntiles,                                 // groups of rows_per_pass rows
                     int nstages,                                 // ring depth, 2..kLoo5MaxStages
                     int dbg,                                     // experiments: 1 = no restaging (stale tiles), 2 = staging only
-                    float* __restrict__ D2)                      // [ldg][M] (problem-major) or null: this iteration's squared change per (problem, site)
+                    float* __restrict__ D2)                      // [ldg / 4][M][4] (quad-major) or null: this iteration's squared change per (problem, site)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long full[kLoo5MaxStages], empty[kLoo5MaxStages];
@@ -2254,10 +2251,9 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
                 }
             }
             *reinterpret_cast<float4*>(&F[(tl * TS + r) * (long)ldf + c0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
-            if (D2) {                                           // problem-major: a problem's squared changes are contiguous in site order
-                float* d2p = D2 + (long)c0 * M + (tl * TS + r);
-                d2p[0] = dq[0]; d2p[M] = dq[1]; d2p[2 * M] = dq[2]; d2p[3 * M] = dq[3];
-            }
+            // quad-major [ldg / 4][M][4]: one 16-byte store per thread, the sites of a quad contiguous (a purely problem-major
+            // layout cost four scattered 4-byte stores per thread: +14 % on this kernel at 2.5 M sites)
+            if (D2) *reinterpret_cast<float4*>(&D2[((long)(c0 >> 2) * M + (tl * TS + r)) * 4]) = make_float4(dq[0], dq[1], dq[2], dq[3]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);               // this warp is done with the slot
@@ -2300,7 +2296,7 @@ loo_first_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n,
                  const int* __restrict__ active,            // [ldg]
                  const unsigned char* __restrict__ mask,    // [M][ldg] or null
                  double* __restrict__ partials,             // [gridDim.x][ldg]
-                 float* __restrict__ D2)                    // [ldg][M] (problem-major) or null: squared change per (problem, site)
+                 float* __restrict__ D2)                    // [ldg / 4][M][4] (quad-major) or null: squared change per (problem, site)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* red = reinterpret_cast<float*>(smem_raw);      // [R][2 * TPR * kFisherQ]
@@ -2370,7 +2366,7 @@ loo_first_kernel(const float2* __restrict__ G, int ldg, long M, int col0, int n,
                     if (ok & 2u) { const float d = __fsub_rn(fb, f0); dq.y = __fmul_rn(d, d); sb[j] = __fadd_rn(sb[j], dq.y); out.y = fb; }
                     if (ok) {
                         *reinterpret_cast<float2*>(&F[s * (long)ldf + col0 + 2 * q]) = out;
-                        if (D2) { float* d2p = D2 + (long)(col0 + 2 * q) * M + s; d2p[0] = dq.x; d2p[M] = dq.y; }
+                        if (D2) { const int p = col0 + 2 * q; *reinterpret_cast<float2*>(&D2[((long)(p >> 2) * M + s) * 4 + (p & 3)]) = dq; }
                     }
                 }
             }
@@ -2439,15 +2435,34 @@ __global__ void em_rank_sum_kernel(const double* __restrict__ gathered, int worl
 // get(i): the i-th addend, 0 <= i < n; element order inside a chunk of 256 is i = base + 32 j + lane.
 // ---------------------------------------------------------------------------------------
 // One BLOCK per sum (kSeqWarps warps): a single warp would be bound by load latency (256 addends per ~1 us round trip,
-// 4 ms per million).  Per round every warp takes one chunk of 256 addends - the next round's are already in flight -
-// and works out its integer advance Q for the binade the accumulator is in at the start of the round; the chunks are
-// then folded IN ORDER by every thread redundantly (a handful of integer instructions each).  A chunk with a tie, or
-// one that would leave the binade, is added one element at a time, in order, by the warp that holds it; when that
-// moved the accumulator to another binade the remaining chunks of the round are re-derived for the new one.
+// 4 ms per million).  Per round every warp takes one chunk of 256 addends - the next two rounds' are already in flight -
+// leaves them in shared memory and works out the chunk's integer advance Q for the binade the accumulator is in at the
+// start of the round.  Warp 0 then folds the 32 chunks IN ORDER (a handful of integer instructions each; when every
+// thread did this redundantly the fold itself was the cost: 2.5 ms per million addends).  A chunk with a tie, or one
+// that would leave the binade, is added one element at a time, in order, from shared memory; when that moved the
+// accumulator to another binade the remaining chunks of the round are re-derived for the new one.
 constexpr int kSeqWarps = 32;
+__device__ __forceinline__ void seq_chunk_q(const float (&x)[8], int eb, unsigned& Q, bool& anybad)
+{
+    bool bad = !(eb >= 30 && eb <= 250);
+    int qsum = 0;
+    if (!bad) {
+        const float scale = __uint_as_float((unsigned)(277 - eb) << 23);   // 1 / ulp(res), a power of two: x * scale is exact
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = x[j] * scale;
+            bad = bad || !(t >= 0.0f && t < 1048576.0f);           // also NaN
+            bad = bad || (t - floorf(t) == 0.5f);                  // a tie: its rounding depends on the parity of S
+            qsum += __float2int_rn(t);
+        }
+    }
+    anybad = __any_sync(0xffffffffu, bad);
+    Q = (unsigned)__reduce_add_sync(0xffffffffu, anybad ? 0 : qsum);
+}
 template <class Get>
 __device__ __forceinline__ float block_seqsum32(float res, long n, Get get)
 {
+    __shared__ float sh_x[kSeqWarps][256];
     __shared__ unsigned sh_q[kSeqWarps];
     __shared__ int sh_bad[kSeqWarps];
     __shared__ float sh_res;
@@ -2466,55 +2481,52 @@ __device__ __forceinline__ float block_seqsum32(float res, long n, Get get)
             const long i = r0 + 2 * per_round + (long)warp * 256 + 32 * j + lane;
             xnn[j] = i < n ? get(i) : 0.0f;                  // + 0.0f never changes a float32 accumulator that started at +0
         }
-        int wdone = 0;
-        for (;;) {
-            const unsigned bits0 = __float_as_uint(res);
-            const int eb = (int)(bits0 >> 23);               // sign bit included: a negative accumulator fails the range test
-            if (warp >= wdone) {
-                bool bad = !(eb >= 30 && eb <= 250);
-                int qsum = 0;
-                if (!bad) {
-                    const float scale = __uint_as_float((unsigned)(277 - eb) << 23);   // 1 / ulp(res), a power of two: x * scale is exact
+        const int eb0 = (int)(__float_as_uint(res) >> 23);   // sign bit included: a negative accumulator fails the range test
+        {
+            unsigned Q; bool anybad;
+            seq_chunk_q(x, eb0, Q, anybad);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float t = x[j] * scale;
-                        bad = bad || !(t >= 0.0f && t < 1048576.0f);           // also NaN
-                        bad = bad || (t - floorf(t) == 0.5f);                  // a tie: its rounding depends on the parity of S
-                        qsum += __float2int_rn(t);
-                    }
-                }
-                const bool anybad = __any_sync(0xffffffffu, bad);
-                const unsigned Q = (unsigned)__reduce_add_sync(0xffffffffu, anybad ? 0 : qsum);
-                if (lane == 0) { sh_q[warp] = Q; sh_bad[warp] = anybad ? 1 : 0; }
-            }
-            __syncthreads();
-            bool redo = false;
-            int w = wdone;
-            for (; w < kSeqWarps; ++w) {                     // every thread folds the chunks in order: uniform control flow
-                if (r0 + (long)w * 256 >= n) { w = kSeqWarps; break; }
+            for (int j = 0; j < 8; ++j) sh_x[warp][32 * j + lane] = x[j];
+            if (lane == 0) { sh_q[warp] = Q; sh_bad[warp] = anybad ? 1 : 0; }
+        }
+        __syncthreads();
+        if (warp == 0) {                                     // the fold: serial over the chunks, one warp
+            int eb = eb0;
+            for (int w = 0; w < kSeqWarps; ++w) {
+                if (r0 + (long)w * 256 >= n) break;
                 const unsigned b = __float_as_uint(res);
                 const unsigned S = (b & 0x007fffffu) | 0x00800000u;
                 if (!sh_bad[w] && (int)(b >> 23) == eb && S + sh_q[w] < 0x01000000u) {
                     res = __uint_as_float(((unsigned)eb << 23) | ((S + sh_q[w]) & 0x007fffffu));
-                } else {
-                    if (warp == w) {
-                        float r = res;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
+                    continue;
+                }
+                float r = res;                               // in order, one real float32 addition per element
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) {
+                    const float xv = sh_x[w][32 * j + lane];
 #pragma unroll 8
-                            for (int l = 0; l < 32; ++l) r = __fadd_rn(r, __shfl_sync(0xffffffffu, x[j], l));
-                        if (lane == 0) sh_res = r;
+                    for (int l = 0; l < 32; ++l) r = __fadd_rn(r, __shfl_sync(0xffffffffu, xv, l));
+                }
+                res = r;
+                const int eb_new = (int)(__float_as_uint(res) >> 23);
+                if (eb_new != eb) {                          // the later chunks were scaled for the old binade: re-derive them
+                    eb = eb_new;
+                    for (int v = w + 1; v < kSeqWarps; ++v) {
+                        float xv[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) xv[j] = sh_x[v][32 * j + lane];
+                        unsigned Q; bool anybad;
+                        seq_chunk_q(xv, eb, Q, anybad);
+                        if (lane == 0) { sh_q[v] = Q; sh_bad[v] = anybad ? 1 : 0; }
                     }
-                    __syncthreads();
-                    res = sh_res;
-                    __syncthreads();
-                    if ((int)(__float_as_uint(res) >> 23) != eb) { ++w; redo = true; break; }   // the later chunks were scaled for the old binade
+                    __syncwarp();
                 }
             }
-            wdone = w;
-            __syncthreads();                                 // sh_q / sh_bad are rewritten next
-            if (!redo || wdone >= kSeqWarps) break;
+            if (lane == 0) sh_res = res;
         }
+        __syncthreads();
+        res = sh_res;
+        __syncthreads();                                     // sh_x / sh_q / sh_res are rewritten next round
 #pragma unroll
         for (int j = 0; j < 8; ++j) { x[j] = xn[j]; xn[j] = xnn[j]; }
     }
@@ -2525,7 +2537,7 @@ __device__ __forceinline__ float block_seqsum32(float res, long n, Get get)
 // sum of squared changes lies within `band` (relative) of the tolerance - band = the worst-case distance between
 // the exact sum and the reference's sequential float32 sum for that many addends (or the caller's override;
 // band < 0: every active problem).  For those, the float32 sum is reproduced (block_seqsum32) from the squared changes the step
-// kernels left in D2[problem][M] (zero where a site is masked out), starting from carry_in[p]
+// kernels left in D2 (quad-major; zero where a site is masked out), starting from carry_in[p]
 // (site-sharded runs chain the ranks in site order).  em_decide_kernel then decides on serial[p].
 __device__ __forceinline__ double em_band(double cnt, double band_override)
 {
@@ -2537,7 +2549,7 @@ __device__ __forceinline__ double em_band(double cnt, double band_override)
 __global__ void __launch_bounds__(kSeqWarps * 32)
 em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ count, double count_all, int np, double tole,
                   double band_override, const int* __restrict__ active,
-                  const float* __restrict__ D2, long M,        // [np][M] problem-major (offset to the first problem applied by the caller)
+                  const float* __restrict__ D2, long M,        // [np / 4][M][4] quad-major (offset to the first problem, a multiple of 4, applied by the caller)
                   const float* __restrict__ carry_in,       // [np] or null (first rank)
                   float* __restrict__ serial,               // [np] out: the running float32 sum after this rank's sites
                   int* __restrict__ uncertain)              // [np] out
@@ -2553,8 +2565,8 @@ em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ cou
             unc = (band < 0.0 || fabs(diff - tole) <= band * tole) ? 1 : 0;
         }
         if (unc && D2) {                                     // D2 == null: flags only
-            const float* col = D2 + (long)p * M;
-            const float r = block_seqsum32(carry_in ? carry_in[p] : 0.0f, M, [&](long i) { return __ldg(col + i); });
+            const float* col = D2 + (long)(p >> 2) * M * 4 + (p & 3);   // quad-major: this problem's addends are 16 bytes apart
+            const float r = block_seqsum32(carry_in ? carry_in[p] : 0.0f, M, [&](long i) { return __ldg(col + 4 * i); });
             if (threadIdx.x == 0) serial[p] = r;
         }
         if (threadIdx.x == 0) uncertain[p] = unc;
