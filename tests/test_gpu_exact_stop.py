@@ -85,12 +85,14 @@ def test_stop_iterations_match_oracle_at_6m_sites(lib, oracle_mod):
     af, its = ctx.ref_af(200, 1e-4)
     a_gpu = af.copy()
     ll, _, lits = ctx.loo_partial(a_gpu, 200, 1e-4)
-    # every check resolved sequentially: the band shortcut must not change a single decision
-    ctx.set_option("rmse_band_ppm", -1)
-    af_all, its_all = ctx.ref_af(200, 1e-4)
-    a_all = af_all.copy()
-    ll_all, _, lits_all = ctx.loo_partial(a_all, 200, 1e-4)
-    assert list(its_all) == list(its) and list(lits_all) == list(lits) and np.array_equal(af_all, af) and np.array_equal(a_all, a_gpu)
+    # every check resolved sequentially (-1), and the rigorous summation bound as the band (-2): the default band
+    # (8x the measured float32 bias) must not change a single decision
+    for band in (-1, -2):
+        ctx.set_option("rmse_band_ppm", band)
+        af_all, its_all = ctx.ref_af(200, 1e-4)
+        a_all = af_all.copy()
+        ll_all, _, lits_all = ctx.loo_partial(a_all, 200, 1e-4)
+        assert list(its_all) == list(its) and list(lits_all) == list(lits) and np.array_equal(af_all, af) and np.array_equal(a_all, a_gpu)
     # the FP64-only rule, for the record (it may or may not differ on this seed)
     ctx.set_option("rmse_band_ppm", 0)
     ctx.set_option("rmse_exact", 0)

@@ -129,7 +129,8 @@ const char* const kOptionNames[] = {
     "ztally_groups",      // column groups of the rank-chained class tally (default 1: a group launch is latency-bound and takes as long as the full one)
     "z_exact_means",      // 1: order-independent fixed-point class means (NOT the reference's float32 means)
     "rmse_exact",         // 0: stop rule on the float64 sum only (no sequential float32 tie-break)
-    "rmse_band_ppm",      // half-width of the tie-break band around the tolerance, parts per million of the RMSE (0 = automatic)
+    "rmse_band_ppm",      // tie-break band around the tolerance: 0 = 8x the measured float32 bias (default), > 0 = ppm of the RMSE,
+                          //   -1 = every check is resolved sequentially, -2 = the rigorous summation bound
     "nccl_sums",          // 0: final sums through the host callback even when a communicator is attached
 };
 
@@ -812,24 +813,20 @@ struct EmState {
 };
 
 // The reference's stop sum is sequential float32; `exact` runs keep what is needed to reproduce it (option
-// rmse_exact = 0 decides on the FP64 sums alone).  rmse_band_ppm: 0 = the rigorous band for the number of addends,
-// > 0 = that many parts per million of the tolerance, < 0 = every check is resolved sequentially (tests).
+// rmse_exact = 0 decides on the FP64 sums alone).  rmse_band_ppm selects the band inside which a check is resolved
+// sequentially (em_band, wgs_kernels.cuh): 0 = 8x the measured bias of the float32 sum, > 0 = ppm of the tolerance,
+// -1 = every check (tests), -2 = the rigorous summation bound.
 double band_override_of(const wgs_ctx* ctx)
 {
     const int ppm = opt(ctx, "rmse_band_ppm", 0);
-    return ppm == 0 ? 0.0 : (ppm < 0 ? -1.0 : ppm * 1e-6);
+    return ppm == 0 ? 0.0 : (ppm < 0 ? (double)ppm : ppm * 1e-6);   // -1: every check, -2: the rigorous bound (see em_band)
 }
-// host mirror of em_band (wgs_kernels.cuh)
 bool em_uncertain(double ssq, double count, double tole, double band_override)
 {
     float res = (float)ssq;
     res = res / (float)count;
     const double diff = std::sqrt((double)res);
-    double band = band_override;
-    if (band == 0.0) {
-        const double ku = count * 5.9604644775390625e-08;
-        band = ku >= 0.5 ? -1.0 : 0.5 * ku / (1.0 - ku) + 1e-4;
-    }
+    const double band = em_band(count, band_override);
     return band < 0.0 || std::fabs(diff - tole) <= band * tole;
 }
 
@@ -864,13 +861,9 @@ int em_state_init(wgs_ctx* ctx, EmState& st, int np, int ld, int nblocks, const 
     CU(cudaMemcpyAsync(st.active.p, st.h_active.data(), (size_t)np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     st.exact = exact;
     st.band_override = band_override_of(ctx);
-    {   // the band for the whole-file site count decides how early the rank chain has to be queued; a band that cannot
-        // be bounded (>= 2^23 addends) or "always" means every check is resolved: the chain is on from the first iteration
-        double band = st.band_override;
-        if (band == 0.0) {
-            const double ku = (double)ctx->Mtot() * 5.9604644775390625e-08;
-            band = ku >= 0.5 ? -1.0 : 0.5 * ku / (1.0 - ku) + 1e-4;
-        }
+    {   // the band for the whole-file site count decides how early the rank chain has to be queued; "every check" means
+        // the chain is on from the first iteration
+        const double band = em_band((double)ctx->Mtot(), st.band_override);
         if (band < 0.0) st.chain_always = true;
         else st.near_factor = 12.0 * (1.0 + band);
     }

@@ -2437,8 +2437,9 @@ __global__ void em_rank_sum_kernel(const double* __restrict__ gathered, int worl
 // One BLOCK per sum (kSeqWarps warps): a single warp would be bound by load latency (256 addends per ~1 us round trip,
 // 4 ms per million).  Per round every warp takes one chunk of 256 addends - the next two rounds' are already in flight -
 // leaves them in shared memory and works out the chunk's integer advance Q for the binade the accumulator is in at the
-// start of the round.  Warp 0 then folds the 32 chunks IN ORDER (a handful of integer instructions each; when every
-// thread did this redundantly the fold itself was the cost: 2.5 ms per million addends).  A chunk with a tie, or one
+// start of the round.  Warp 0 then folds the round: all 32 chunks at once when none has a tie and the round stays in the
+// binade, else chunk by chunk IN ORDER (when every thread folded every chunk redundantly, and later when warp 0 walked the
+// chunks one by one every round, the fold itself was the cost: 2.5 and 0.8 ms per million addends).  A chunk with a tie, or one
 // that would leave the binade, is added one element at a time, in order, from shared memory; when that moved the
 // accumulator to another binade the remaining chunks of the round are re-derived for the new one.
 constexpr int kSeqWarps = 32;
@@ -2451,7 +2452,7 @@ __device__ __forceinline__ void seq_chunk_q(const float (&x)[8], int eb, unsigne
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float t = x[j] * scale;
-            bad = bad || !(t >= 0.0f && t < 1048576.0f);           // also NaN
+            bad = bad || !(t >= 0.0f && t < 32768.0f);             // also NaN; 2^15: the Q of a whole round (8192 addends) fits 32 bits
             bad = bad || (t - floorf(t) == 0.5f);                  // a tie: its rounding depends on the parity of S
             qsum += __float2int_rn(t);
         }
@@ -2490,9 +2491,18 @@ __device__ __forceinline__ float block_seqsum32(float res, long n, Get get)
             if (lane == 0) { sh_q[warp] = Q; sh_bad[warp] = anybad ? 1 : 0; }
         }
         __syncthreads();
-        if (warp == 0) {                                     // the fold: serial over the chunks, one warp
+        if (warp == 0) {
+            // the fold.  Whole round at once when no chunk has a tie and the round stays inside the binade (then so does
+            // every prefix: the advances are non-negative) - the usual case: one vote, one REDUX.
+            const unsigned bits = __float_as_uint(res);
+            const unsigned S0 = (bits & 0x007fffffu) | 0x00800000u;
+            const bool anyb = __any_sync(0xffffffffu, sh_bad[lane] != 0);
+            const unsigned tot = (unsigned)__reduce_add_sync(0xffffffffu, sh_q[lane]);
             int eb = eb0;
-            for (int w = 0; w < kSeqWarps; ++w) {
+            if (!anyb && S0 + tot < 0x01000000u) {
+                res = __uint_as_float(((unsigned)eb << 23) | ((S0 + tot) & 0x007fffffu));
+            } else
+            for (int w = 0; w < kSeqWarps; ++w) {            // chunk by chunk, in order
                 if (r0 + (long)w * 256 >= n) break;
                 const unsigned b = __float_as_uint(res);
                 const unsigned S = (b & 0x007fffffu) | 0x00800000u;
@@ -2539,12 +2549,20 @@ __device__ __forceinline__ float block_seqsum32(float res, long n, Get get)
 // band < 0: every active problem).  For those, the float32 sum is reproduced (block_seqsum32) from the squared changes the step
 // kernels left in D2 (quad-major; zero where a site is masked out), starting from carry_in[p]
 // (site-sharded runs chain the ranks in site order).  em_decide_kernel then decides on serial[p].
-__device__ __forceinline__ double em_band(double cnt, double band_override)
+// Half-width (relative, on the RMSE) of the band around the tolerance inside which the FP64 sum is not trusted to
+// decide like the reference's sequential float32 sum.  Default: 8x the measured bias of that sum - SURVEY.md 7.1c:
+// -0.04 % of the sum at 1 M addends, -0.4 % at 5 M, -2.3 % at 20 M, i.e. 4e-4 (n / 1e6)^1.35, half of that on the square
+// root - but never more than the rigorous bound gamma_n / 2 of recursive summation (Higham), plus 1e-4 for the FP32
+// per-thread partials of the FP64 sum.  Overrides: -1 = every active problem (no band at all), -2 = the rigorous bound
+// alone (every check once n >= 2^23), > 0 = that relative half-width.
+__host__ __device__ __forceinline__ double em_band(double cnt, double band_override)
 {
-    if (band_override != 0.0) return band_override;         // < 0: always resolve
-    const double ku = cnt * 5.9604644775390625e-08;        // n 2^-24: Higham's gamma_n for recursive summation
-    if (ku >= 0.5) return -1.0;
-    return 0.5 * ku / (1.0 - ku) + 1e-4;                     // half of it on the square root, plus the FP32 per-thread partials of the FP64 sum
+    if (band_override == -1.0 || band_override > 0.0) return band_override;
+    const double ku = cnt * 5.9604644775390625e-08;        // n 2^-24
+    const double rigorous = ku >= 0.5 ? -1.0 : 0.5 * ku / (1.0 - ku) + 1e-4;
+    if (band_override == -2.0) return rigorous;
+    const double measured = 8.0 * 0.5 * 4e-4 * pow(cnt * 1e-6, 1.35) + 1e-4;
+    return (rigorous >= 0.0 && rigorous < measured) ? rigorous : measured;
 }
 __global__ void __launch_bounds__(kSeqWarps * 32)
 em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ count, double count_all, int np, double tole,
