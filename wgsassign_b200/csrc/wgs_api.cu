@@ -951,35 +951,33 @@ int em_after_step_queue(wgs_ctx* ctx, EmState& st, double tole, int iteration, c
         // checks inside the band where the FP64 sum cannot decide are resolved with the reference's own sequential
         // float32 sum, rebuilt from D2 (block_seqsum32); under site sharding the running sums pass from rank to rank
         const double* cnt = d_count ? d_count + c0 : nullptr;
-        auto resolve = [&](const float* carry_in, bool sums) -> int {
+        auto resolve = [&](const float* carry_in, bool sums, int* any_flag = nullptr) -> int {
             LAUNCH("em_resolve", em_resolve_kernel, std::max(1, std::min(nc, ctx->num_sm * 16)), kSeqWarps * 32, 0, ctx->stream,
                    st.ssq.as<double>() + c0, cnt, count_all, nc, tole, st.band_override, st.active.as<int>() + c0,
                    sums ? st.d2.as<float>() + (size_t)c0 * std::max<long>(ctx->M(), 1) : (const float*)nullptr, ctx->M(), carry_in, st.serial.as<float>() + c0,
-                   st.uncertain.as<int>() + c0);
+                   st.uncertain.as<int>() + c0, any_flag);
             return 0;
         };
         const bool sharded = ctx->fn && ctx->world > 1;
         bool have_sums = true;
         if (!sharded) {
             if (resolve(nullptr, true)) return 1;
-        } else if (ctx->nccl_comm) {
-            if (st.chain_on || st.chain_always) {
-                if (chain_floats(ctx, st.serial.as<float>() + c0, st.carry.as<float>() + c0, (size_t)nc,
-                                 [&](const float* cin) { return resolve(cin, true); })) return 1;
-            } else {                                             // far from convergence: flags only (a flag raised here restarts the EM, see run_em_loo)
-                if (resolve(nullptr, false)) return 1;
-                have_sums = false;
-            }
-        } else {
-            // host callback: the sums already pass through the host every iteration - look at the flags first
+        } else if (ctx->nccl_comm && !(st.chain_on || st.chain_always)) {
+            // far from convergence: flags only, nothing leaves the device (a flag raised here restarts the EM, see run_em_loo)
             if (resolve(nullptr, false)) return 1;
-            std::vector<int> hu(nc);
-            CU(cudaMemcpyAsync(hu.data(), st.uncertain.as<int>() + c0, nc * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            have_sums = false;
+        } else {
+            // Near convergence (or through the host callback, where the sums pass through the host anyway): look at the flags
+            // first - they are the same on every rank, being derived from the whole-file FP64 sums - and run the rank chain
+            // only for a check that needs it.  The read-back costs one stream synchronisation (the look-ahead launch is
+            // already queued behind it); a chain costs a hop per rank.
+            int* any_dev = ctx->em_pin_dev[slot] + (ctx->em_pin_cap - 1);         // last word of the slot: never used by a decision
+            int* any_host = ctx->em_pin[slot] + (ctx->em_pin_cap - 1);
+            *any_host = 0;
+            if (resolve(nullptr, false, any_dev)) return 1;
             CU(cudaStreamSynchronize(ctx->stream));
-            bool any = false;
-            for (int v : hu) any = any || v;
-            if (any && chain_floats(ctx, st.serial.as<float>() + c0, st.carry.as<float>() + c0, (size_t)nc,
-                                    [&](const float* cin) { return resolve(cin, true); })) return 1;
+            if (*any_host && chain_floats(ctx, st.serial.as<float>() + c0, st.carry.as<float>() + c0, (size_t)nc,
+                                          [&](const float* cin) { return resolve(cin, true); })) return 1;
         }
         d_unc = st.uncertain.as<int>() + c0;
         d_serial = have_sums ? st.serial.as<float>() + c0 : nullptr;

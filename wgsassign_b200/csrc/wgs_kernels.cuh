@@ -2570,7 +2570,8 @@ em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ cou
                   const float* __restrict__ D2, long M,        // [np / 4][M][4] quad-major (offset to the first problem, a multiple of 4, applied by the caller)
                   const float* __restrict__ carry_in,       // [np] or null (first rank)
                   float* __restrict__ serial,               // [np] out: the running float32 sum after this rank's sites
-                  int* __restrict__ uncertain)              // [np] out
+                  int* __restrict__ uncertain,              // [np] out
+                  int* __restrict__ any_uncertain = nullptr)   // optional: set to 1 when some problem is uncertain
 {
     for (int p = blockIdx.x; p < np; p += gridDim.x) {      // block-uniform
         int unc = 0;
@@ -2587,7 +2588,7 @@ em_resolve_kernel(const double* __restrict__ ssq, const double* __restrict__ cou
             const float r = block_seqsum32(carry_in ? carry_in[p] : 0.0f, M, [&](long i) { return __ldg(col + 4 * i); });
             if (threadIdx.x == 0) serial[p] = r;
         }
-        if (threadIdx.x == 0) uncertain[p] = unc;
+        if (threadIdx.x == 0) { uncertain[p] = unc; if (unc && any_uncertain) *any_uncertain = 1; }
     }
 }
 
