@@ -4,7 +4,7 @@ The reference ships no allele-depth file and no large data set, so tests and ben
 this generator: per-population allele frequencies, Hardy-Weinberg genotypes, Poisson read
 depth, binomial alt reads with sequencing error e, and ANGSD-style genotype likelihoods
 rounded to the 6 decimals a Beagle text file carries.  The device-side generator in
-``csrc/wgs_synth.cu`` follows the same model with a counter-based hash so that any slice
+``csrc/wgs_kernels.cuh`` (``synth_kernel``) follows the same model with a counter-based hash so that any slice
 can be produced in place on the GPU; this NumPy version is for host-sized inputs.
 """
 import numpy as np
