@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 
 AF_ATOL = 1e-5
 LL_RTOL = 1e-6
+FISHER_TOL = 2e-5       # relative to |value| + 1e-3 of the column scale; the reference itself: 0.7e-6 .. 5.4e-6 (see test_config1)
 
 
 @pytest.fixture(scope="module")
@@ -129,8 +130,10 @@ def test_config1_fisher_bundled(wgs, bundled):
     ne_ind = wgs.fisher.fisher_obs_ind(L, af, IDs, 1)
     gf, gn = bundled["c1_fisher_obs"], bundled["c1_ne_obs"]
     scale_f, scale_n = np.abs(gf).max(0), np.abs(gn).max(0)
-    assert np.max(np.abs(f_obs - gf) / (np.abs(gf) + 1e-3 * scale_f)) < 1e-4
-    assert np.max(np.abs(ne_obs - gn) / (np.abs(gn) + 1e-3 * scale_n)) < 1e-4
+    # FISHER_TOL: the reference's own float32 result is 0.7e-6 .. 5.4e-6 away from a float64 restatement under this metric
+    # (populations of 8 .. 522; scripts/reference_noise.py, profiles/reference_noise_r2.txt)
+    assert np.max(np.abs(f_obs - gf) / (np.abs(gf) + 1e-3 * scale_f)) < FISHER_TOL
+    assert np.max(np.abs(ne_obs - gn) / (np.abs(gn) + 1e-3 * scale_n)) < FISHER_TOL
     assert rel_err(ne_obs.mean(0), gn.mean(0)) < 1e-5
     gold_ind = np.array([float(x) for x in str(bundled["c1_ne_ind_txt"]).split()])
     assert rel_err(ne_ind, gold_ind) < 1e-5
@@ -160,7 +163,7 @@ def test_synthetic_vs_oracle(wgs, oracle_mod, m, n, k, interleave, seed):
     # fisher
     f_o, ne_o = oracle_mod.fisher_obs(L, af_o, IDs, 2)
     f_g, ne_g = wgs.fisher.fisher_obs(L, af_o, IDs, 1)
-    assert np.max(np.abs(f_g - f_o) / (np.abs(f_o) + 1e-3 * np.abs(f_o).max(0))) < 1e-4
+    assert np.max(np.abs(f_g - f_o) / (np.abs(f_o) + 1e-3 * np.abs(f_o).max(0))) < FISHER_TOL
     assert rel_err(wgs.fisher.fisher_obs_ind(L, af_o, IDs, 1), oracle_mod.fisher_obs_ind(L, af_o, IDs, 2)) < 1e-5
     # LOO
     if n <= 40:
@@ -361,7 +364,7 @@ def test_fallback_kernels_agree(wgs, monkeypatch):
     assert list(its) == list(its2) and list(lits) == list(lits2)
     assert np.max(np.abs(af - af2)) < 1e-6 and np.max(np.abs(a0 - a1)) < AF_ATOL
     assert rel_err(ll2, ll) < LL_RTOL and np.array_equal(np.argmax(ll, 1), np.argmax(ll2, 1))
-    assert np.max(np.abs(f2 - f_obs) / (np.abs(f_obs) + 1e-3 * np.abs(f_obs).max(0))) < 1e-4
+    assert np.max(np.abs(f2 - f_obs) / (np.abs(f_obs) + 1e-3 * np.abs(f_obs).max(0))) < FISHER_TOL
     assert rel_err(ind2, ind) < 1e-5
     ctx.close()
 
@@ -427,14 +430,16 @@ def test_large_population_paths_vs_oracle(wgs, oracle_mod, n_big):
     ll_o, _, lits_o = oracle_mod.loo(L, a1, IDs, 4, 200, 1e-4)
     ll_g, _, lits_g = ctx.loo_partial(a2, 200, 1e-4)
     assert list(lits_g) == list(lits_o)
-    # The reference adds the n posterior terms of a site sequentially in float32 (emMAF_cy.pyx:19-23): with n in the
-    # hundreds its own frequencies carry ~sqrt(n) * 6e-8 relative noise, and a leave-one-out frequency near the clip
-    # bound 1/(2n) turns that into the same relative change of a site's likelihood.  5e-6 here, 1e-6 everywhere else.
+    # The reference adds the n posterior terms of a site sequentially in float32 (emMAF_cy.pyx:19-23).  Measured
+    # (scripts/reference_noise.py, profiles/reference_noise_r2.txt): against a float64 restatement of its own formulas its
+    # leave-one-out frequencies are off by 1.0e-6 / 2.8e-6 / 6.3e-6 at n = 130 / 301 / 522 and its own-population
+    # log-likelihoods by 1.3e-7 / 4.6e-7 / 5.6e-7 relative; a frequency near the clip bound 1/(2n) passes its error on to the
+    # other populations' likelihoods undamped.  5e-6 here (about 9x the reference's own noise), 1e-6 everywhere else.
     assert rel_err(ll_g, ll_o) < 5e-6 and np.array_equal(np.argmax(ll_g, 1), np.argmax(ll_o, 1))
     assert np.max(np.abs(a1 - a2)) < AF_ATOL
     f_o, _ = oracle_mod.fisher_obs(L, af_o, IDs, 4)
     f_g, _, ind_g = ctx.fisher_partial(af_o)
-    assert np.max(np.abs(f_g - f_o) / (np.abs(f_o) + 1e-3 * np.abs(f_o).max(0))) < 1e-4
+    assert np.max(np.abs(f_g - f_o) / (np.abs(f_o) + 1e-3 * np.abs(f_o).max(0))) < FISHER_TOL
     ctx.close()
 
 
