@@ -107,7 +107,7 @@ def test_cli_zscores(cli, zgold, tmp_path, capsys):
     z = np.loadtxt(out + ".z_ind.txt")
     gz = np.array([float(x) for x in str(zgold["z_assign_txt"]).split()])
     # z = (W_obs - z_mu) / sqrt(z_var) subtracts two sums of magnitude ~|W|: the 1e-6 relative tolerance of the components
-    # propagates to 2e-6 (|W_obs| + |z_mu|) / sqrt(z_var) on z (hard part 4) - at most 1.9e-4 on this fixture
+    # propagates to 2e-6 (|W_obs| + |z_mu|) / sqrt(z_var) on z (hard part 4) - at most 4e-4 on this fixture
     comp = zgold["z_assign_components"]
     tol = 2e-6 * (np.abs(comp[:, 0]) + np.abs(comp[:, 1])) / np.sqrt(comp[:, 2]) + 1e-5 * np.abs(gz)
     assert np.all(np.abs(z - gz) <= tol) and z.shape == (12,)

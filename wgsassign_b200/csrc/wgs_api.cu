@@ -1199,8 +1199,8 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
     // whole multiples of 4 warps only: 7 warps per block leave one scheduler of the SM with less work
     // than the others (measured: 12 % slower than 8 warps, scripts/microbench/loo_quad_rate.cu)
     const int opt_bd = opt(ctx, "loo_block", 0);
-    for (int bd = 128; bd <= 512; bd += 128) {
-        if (opt_bd && opt_bd != bd) continue;
+    for (int bd : {128, 256, 320, 384, 512}) {
+        if (opt_bd ? opt_bd != bd : bd == 320) continue;             // 320 (2 blocks of 10 warps at <= 102 registers): only on request
         int rpp = bd / nq;
         if (rpp < 1) continue;
         double u = (double)(rpp * nq) / bd;
@@ -1208,7 +1208,7 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
         if (u > best_u + 1e-9) { best_u = u; best.block = bd; best.rows_per_pass = rpp; }
     }
     if (best.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (2048)", n);
-    best.big = best.block > 256;
+    best.big = best.block > 320;
     // per tile row - quad kernel: two packed buffers (odd 16-byte stride) + the raw TMA landing row;
     //              - packed kernel: double-buffered packed cells (odd 16-byte stride) + double-buffered raw row
     if (packed) {
@@ -1238,6 +1238,7 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
     } while (0)
     if (packed) {
         if (best.big) LOO_PREP((loo_em_step5_kernel<512, 1>));
+        else if (best.block == 320) LOO_PREP((loo_em_step5_kernel<320, 2>));
         else if (opt(ctx, "loo_occ3")) LOO_PREP((loo_em_step5_kernel<256, 3>));
         else LOO_PREP((loo_em_step5_kernel<256, 2>));
     }
@@ -1379,6 +1380,9 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         if (lc.packed) {
             if (lc.big)
                 LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
+                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
+            else if (lc.block == 320)
+                LAUNCH("loo_em", (loo_em_step5_kernel<320, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
                        pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
             else if (!opt(ctx, "loo_occ3"))
                 LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,

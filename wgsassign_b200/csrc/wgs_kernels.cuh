@@ -2207,10 +2207,6 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
             const float fin[4] = {fq.x, fq.y, fq.z, fq.w};
             const ulonglong2* row = pk0 + ((size_t)slot * TS + r) * ru;
             const int nfull = nq >> 1;                          // cells with both quads
-            // own terms: the four members of quad ti, from the raw pairs at the end of the row
-            const float4* rawrow = reinterpret_cast<const float4*>(row + 5 * nc);
-            const float4 ga = rawrow[2 * ti], gc = rawrow[2 * ti + 1];
-            const float og0[4] = {ga.x, ga.z, gc.x, gc.z}, og1[4] = {ga.y, ga.w, gc.y, gc.w};
             float fo[4], dq[4];
 #pragma unroll 1
             for (int h0 = 0; h0 < 4; h0 += NP) {
@@ -2229,6 +2225,11 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
                     if (last_pair_only) loo5_pair_lo<NP>(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);   // the quad's second pair is padding
                     else loo5_quad<NP>(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
                 }
+                // own terms: the four members of quad ti, from the raw pairs at the end of the row (loaded after the cell
+                // loop: eight fewer registers live across it)
+                const float4* rawrow = reinterpret_cast<const float4*>(row + 5 * nc);
+                const float4 ga = rawrow[2 * ti], gc = rawrow[2 * ti + 1];
+                const float og0[4] = {ga.x, ga.z, gc.x, gc.z}, og1[4] = {ga.y, ga.w, gc.y, gc.w};
 #pragma unroll
                 for (int k = 0; k < NP; ++k) {
                     const int kk = NP == 4 ? k : (h0 ? 2 + k : k);          // member of the quad
