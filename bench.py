@@ -63,15 +63,20 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  The process is started BEFORE the warm-up
+    (its start-up initialises the driver's management library, which stalls the CUDA calls of other processes for tens
+    of milliseconds - inside a 0.5 s timed region that showed as 10..45 ms per step); only the samples stamped between
+    begin() and end() are used."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_ms=200):
         self.gpu = gpu_index
+        self.period_ms = period_ms
         self.proc = None
         self.path = None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -79,10 +84,24 @@ class ClockSampler:
             os.close(fd)
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def begin(self):
+        self.t_begin = time.time()
+
+    def end(self):
+        self.t_end = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -94,23 +113,27 @@ class ClockSampler:
         except Exception:
             pass
         self.fh.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                rows.append((self._stamp(f[0]), float(f[2]), float(f[3]), [nm for nm, v in zip(names, f[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.path)
-        if sm:
+        lo = (self.t_begin or 0.0) - 0.05
+        hi = (self.t_end or float("inf")) + 0.05
+        inside = [r for r in rows if r[0] is not None and lo <= r[0] <= hi]
+        if not inside:                                             # a timed region shorter than the sampling period: nearest samples
+            inside = [r for r in rows if r[0] is not None and lo - 0.2 <= r[0] <= hi + 0.2] or rows
+        if inside:
+            sm = [r[1] for r in inside]
             load = [x for x in sm if x >= 0.5 * max(sm)]
-            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            reasons = sorted({nm for r in inside for nm in r[3]})
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(r[2] for r in inside), reasons=reasons, samples=len(inside))
         return out
 
 
@@ -365,6 +388,7 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--sites", type=int, default=None, help="sites per GPU (weak) or in total (strong); default: the configuration's")
+    ap.add_argument("--clock-period-ms", type=int, default=200, help="nvidia-smi sampling period during the run (0: no sampling; diagnosis only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the per-kernel extras")
@@ -449,12 +473,13 @@ def main():
         mix = mixture.em_mix(pl.astype(np.float32), state["mix_ids"], 200) if rank == 0 else None
         return dict(ll=pl, ne_ind=ind / float(M_total), f_obs=f_obs, ne_obs=ne_obs, mix=mix)
 
+    sampler = ClockSampler(local, args.clock_period_ms)
+    if rank == 0 and args.clock_period_ms > 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.begin()
     ctx.timing_reset(True)
     l0 = ctx.launch_count()
     t0 = time.perf_counter()
@@ -462,11 +487,13 @@ def main():
         res = step()
     barrier()
     dt = time.perf_counter() - t0
+    sampler.end()
     launches = ctx.launch_count() - l0
     fam_names = {"cfg3": ("loo_em", "loo_first", "em_pop", "loo_like", "loo_like_aux", "loo_pack", "em_resolve"),
                  "cfg4": ("pop_like", "pop_like_aux", "ztally", "zkeep", "zmoments", "loo_em", "loo_first", "loo_pack", "em_resolve"),
                  "cfg5": ("fisher", "pop_like", "pop_like_aux")}[args.config]
     fam = {k: family(ctx, k, hbm_peak, M_local) for k in fam_names}
+    gaps = {k: ctx.timing_get(k) for k in ("gap", "gap_long")}     # idle time of the stream between consecutive launches
     ctx.timing_reset(False)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -726,7 +753,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": conf, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "kernels": {**fam, **extra}, "cpu_baseline": cpu_b, "parity": parity}
+            "kernels": {**fam, **extra}, "cpu_baseline": cpu_b, "parity": parity,
+            "stream_idle": {"ms_per_step": gaps["gap"]["ms"] / args.steps, "gaps_per_step": gaps["gap"]["launches"] / args.steps,
+                            "long_ms_per_step": gaps["gap_long"]["ms"] / args.steps, "long_gaps_per_step": gaps["gap_long"]["launches"] / args.steps,
+                            "note": "time the stream sat idle between consecutive kernels of the timed steps (long: gaps above 50 us)"}}
     print(json.dumps(line))
     return 0
 

@@ -18,3 +18,4 @@ if r: print("  roofline: %s bound=%s frac=%.4f achieved=%.4g peak=%.4g share=%.3
 if d.get("cpu_baseline"): print("  cpu:", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"], d["cpu_baseline"]["kind"])
 if d.get("parity"): print("  parity:", {k: v for k, v in d["parity"].items() if k != "against"})
 print("  clocks:", d["clocks"])
+if d.get("stream_idle"): print("  stream idle:", {k: (round(v, 2) if isinstance(v, float) else v) for k, v in d["stream_idle"].items() if k != "note"})

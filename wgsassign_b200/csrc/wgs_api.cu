@@ -26,7 +26,7 @@ namespace {
 std::string g_create_error;
 constexpr int kNumSM_fallback = 148;
 
-struct TimedLaunch { int name_id; cudaEvent_t a, b; };
+struct TimedLaunch { int name_id; cudaEvent_t a, b; cudaStream_t st; };
 struct FamilyStat { double ms = 0, bytes = 0, units = 0; long launches = 0; };
 
 }  // namespace
@@ -92,6 +92,10 @@ struct wgs_ctx {
     // are NOT consulted on any call path; with WGS_DEBUG set, wgs_create imports WGS_<NAME>=<int> once.
     std::map<std::string, int> opts;
 
+    // device_free_bytes(): free device memory at the pool's last change
+    long pool_epoch = 0, mem_epoch_seen = -1;
+    size_t mem_free_seen = 0;
+
     // instrumentation
     long launches = 0;
     bool timing = false;
@@ -124,6 +128,8 @@ const char* const kOptionNames[] = {
     "em_multi1",          // 1: shared-memory-tile multi-iteration population EM
     "em_no_lookahead",    // 1: read every stop decision before queueing the next iteration
     "loo_v4", "loo_nofirst", "loo_fullfill", "loo_block", "loo_stages", "loo_passes", "loo_occ3", "loo_dbg", "prepack_v1",
+    "loo_first_bpsm",     // blocks per SM of the first leave-one-out iteration (default 2)
+    "loo_big_margin_pm",  // per mille of thread utilisation a 512-thread block must gain over two 256-thread ones to be chosen (default 0: chosen on a tie)
     "loo_by_pop",         // 1: leave-one-out EM population by population (one packed-row buffer at a time); -1: never
     "upload_sync",        // 1: wgs_upload_gl_async falls back to the chunked synchronous upload
     "ztally_groups",      // column groups of the rank-chained class tally (default 1: a group launch is latency-bound and takes as long as the full one)
@@ -200,6 +206,7 @@ struct LaunchScope {
         ++ctx->launches;
         if (on) {
             tl.name_id = name_id(ctx, name);
+            tl.st = st;
             cudaEventCreate(&tl.a); cudaEventCreate(&tl.b);
             cudaEventRecord(tl.a, st);
         }
@@ -219,16 +226,27 @@ void add_work(wgs_ctx* ctx, const char* name, double bytes, double units)
     slot.bytes += bytes; slot.units += units;
 }
 
+// Besides the per-family kernel time, the idle time of the stream between consecutive timed launches is kept under
+// "gap" (all of it) and "gap_long" (the gaps above 50 us: host round trips, allocations, copies in between).
 void fold_timing(wgs_ctx* ctx)
 {
-    for (auto& t : ctx->timed) {
+    for (size_t i = 0; i < ctx->timed.size(); ++i) {
+        auto& t = ctx->timed[i];
         cudaEventSynchronize(t.b);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, t.a, t.b);
         auto& slot = ctx->tdone[ctx->tnames[t.name_id]];
         slot.ms += ms; slot.launches += 1;
-        cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+        if (i > 0 && ctx->timed[i - 1].st == t.st) {
+            float gap = 0.f;
+            if (cudaEventElapsedTime(&gap, ctx->timed[i - 1].b, t.a) == cudaSuccess && gap > 0.f) {
+                auto& g = ctx->tdone["gap"];
+                g.ms += gap; g.launches += 1;
+                if (gap > 0.05f) { auto& gl = ctx->tdone["gap_long"]; gl.ms += gap; gl.launches += 1; }
+            }
+        }
     }
+    for (auto& t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     ctx->timed.clear();
 }
 
@@ -253,7 +271,23 @@ size_t pool_round(size_t bytes) { return bytes < (1u << 20) ? ((bytes + 511) / 5
 void pool_trim(wgs_ctx* ctx)
 {
     for (auto& kv : ctx->pool_free) cudaFree(kv.second);
+    if (!ctx->pool_free.empty()) ++ctx->pool_epoch;
     ctx->pool_free.clear();
+}
+
+// Free device memory as of the pool's last cudaMalloc / cudaFree.  cudaMemGetInfo is a driver round trip that takes
+// 0.5 .. 12 ms (measured inside the leave-one-out call, the stream idle meanwhile), so it is asked again only after
+// the pool itself changed what is allocated; memory another allocator of the process takes in between shows up as a
+// failed allocation, which every caller handles.
+size_t device_free_bytes(wgs_ctx* ctx)
+{
+    if (ctx->mem_epoch_seen != ctx->pool_epoch) {
+        size_t freeb = 0, totalb = 0;
+        cudaMemGetInfo(&freeb, &totalb);
+        ctx->mem_free_seen = freeb;
+        ctx->mem_epoch_seen = ctx->pool_epoch;
+    }
+    return ctx->mem_free_seen;
 }
 
 void* pool_take(wgs_ctx* ctx, size_t bytes)
@@ -273,6 +307,7 @@ void* pool_take(wgs_ctx* ctx, size_t bytes)
         if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     }
     ctx->pool_size[p] = bytes;
+    ++ctx->pool_epoch;
     return p;
 }
 
@@ -280,7 +315,7 @@ void pool_give(wgs_ctx* ctx, void* p)
 {
     if (!p) return;
     auto it = ctx->pool_size.find(p);
-    if (it == ctx->pool_size.end()) { cudaFree(p); return; }
+    if (it == ctx->pool_size.end()) { cudaFree(p); ++ctx->pool_epoch; return; }
     ctx->pool_free.insert({it->second, p});
     ctx->pool_size.erase(it);
 }
@@ -1208,13 +1243,21 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
         if (u > best_u + 1e-9) { best_u = u; best.block = bd; best.rows_per_pass = rpp; }
     }
     if (best.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (2048)", n);
+    // one block of 16 warps (one ring of up to 190 KB) instead of two of 8 unless that idles more threads: measured
+    // 0.517 against 0.554 ms per launch at n = 50 (507 of 512 against 247 of 256 working threads) and 0.383 against
+    // 0.395 ms at n = 100 (the same 500 of 512 / 250 of 256)
+    if (packed && !opt_bd && best.block <= 256 && 512 / nq >= 1) {
+        const double u512 = (double)((512 / nq) * nq) / 512;
+        if (u512 + 1e-9 >= best_u + opt(ctx, "loo_big_margin_pm", 0) * 1e-3) { best_u = u512; best.block = 512; best.rows_per_pass = 512 / nq; }
+    }
     best.big = best.block > 320;
     // per tile row - quad kernel: two packed buffers (odd 16-byte stride) + the raw TMA landing row;
     //              - packed kernel: double-buffered packed cells (odd 16-byte stride) + double-buffered raw row
     if (packed) {
         // ring of row groups: as many stages as fit in ~100 KB (two resident blocks per SM), at least 3
         const size_t group_bytes = (size_t)best.rows_per_pass * loo5_row_units(n) * 16;
-        int stages = (int)std::min<size_t>(kLoo5MaxStages, (100 * 1024) / std::max<size_t>(group_bytes, 1));
+        const size_t ring_budget = (best.big ? 190 : opt(ctx, "loo_occ3") ? 68 : 100) * 1024;   // one / three / two resident blocks per SM
+        int stages = (int)std::min<size_t>(kLoo5MaxStages, ring_budget / std::max<size_t>(group_bytes, 1));
         if (int o = opt(ctx, "loo_stages", 0)) stages = o;
         best.stages = std::max(3, std::min(stages, kLoo5MaxStages));
         best.passes = 1;
@@ -1294,19 +1337,21 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     // k+1) - what the pipelined mode does anyway, and what a matrix too large for all packed rows at once (a 2.5 M
     // x 2,000 shard would need 92 GB of them) falls back to before giving up the packed kernel.  Every problem sees
     // the same updates and decisions either way.
+    Trace tr(ctx, "em_loo");
     std::vector<DevBuf> pk(K);
     const int loo_dbg = opt(ctx, "loo_dbg", 0);
     bool packed = !opt(ctx, "loo_v4");
     bool by_pop = pop_ready != nullptr;
     if (packed) {
-        size_t total_pk = 0, max_pk = 0, cached = 0, freeb = 0, totalb = 0;
+        size_t total_pk = 0, max_pk = 0, cached = 0;
         for (int k = 0; k < K; ++k) {
             if (ctx->pops[k].n <= 1) continue;
             const size_t b = (size_t)std::max<long>(M, 1) * loo5_row_units(ctx->pops[k].n) * sizeof(ulonglong2);
             total_pk += b; max_pk = std::max(max_pk, b);
         }
         for (auto& kv : ctx->pool_free) cached += kv.first;
-        cudaMemGetInfo(&freeb, &totalb);
+        const size_t freeb = device_free_bytes(ctx);
+        tr.lap("meminfo");
         const size_t d2b = opt(ctx, "rmse_exact", 1) ? (size_t)std::max<long>(M, 1) * ldg * sizeof(float) : 0;
         const size_t avail = freeb + cached, slack = (size_t)2 << 30;
         const int o = opt(ctx, "loo_by_pop", 0);
@@ -1332,19 +1377,25 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         }
         if (!packed) for (int k = 0; k < K; ++k) buf_release(pk[k]);
     }
+    // iteration 1 (loo_first, 256-thread blocks) has its own grid; rows of the per-block squared-change table that only
+    // it wrote are cleared before iteration 2's reduction (launch_iter)
+    const int first_grid = ctx->num_sm * std::max(1, opt(ctx, "loo_first_bpsm", 2));
+    tr.lap("packed alloc");
     const bool shared_pk = packed && by_pop && !pop_ready;       // every population uses pk[0]
     auto pk_of = [&](int k) { return (shared_pk ? pk[0] : pk[k]).as<ulonglong2>(); };
     for (int k = 0; k < K; ++k) {
         if (ctx->pops[k].n <= 1) continue;
         if (loo_cfg(ctx, ctx->pops[k].n, packed, &cfgs[k])) return 1;
-        nblocks = std::max(nblocks, cfgs[k].grid);
+        nblocks = std::max(nblocks, std::max(cfgs[k].grid, first_grid));
         if (packed && !by_pop) {
             if (launch_prepack(k, pk_of(k))) return 1;
         }
     }
+    tr.lap("cfg+prepack");
     EmState st;
     if (em_state_init(ctx, st, ldg, ldg, nblocks, active0, opt(ctx, "rmse_exact", 1) != 0, mask != nullptr)) return 1;
     if (force_chain) st.chain_always = true;
+    tr.lap("state init");
     float* const D2 = st.d2.as<float>();                         // null when the exact stop rule is switched off
     // When every real column is an active problem of a population that loo_first serves, iteration 1 writes all of
     // them without reading the start state: only the padding columns need a value (the step kernels load whole quads).
@@ -1372,6 +1423,7 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         LAUNCH("fill", bcast_row_kernel, grid_for(M * ldg, 256, ctx->num_sm * 8), 256, 0, ctx->stream, F, ldf, ldg, M, drow.as<float>());
         CU(cudaStreamSynchronize(ctx->stream));
     }
+    tr.lap("start fill");
     auto launch_step = [&](int k) -> int {
         PopDesc pd = ctx->pops[k];
         const LooLaunch& lc = cfgs[k];
@@ -1411,11 +1463,16 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
     };
     auto launch_iter = [&](int k, int it) -> int {
         const int tpr = (it == 1 && use_first) ? first_tpr(k) : 0;
-        if (!tpr) return launch_step(k);
         PopDesc pd = ctx->pops[k];
+        if (!tpr) {
+            if (it == 2 && use_first && first_tpr(k) && first_grid > cfgs[k].grid)
+                CU(cudaMemset2DAsync(st.partials.as<double>() + (size_t)cfgs[k].grid * ldg + pd.col0, (size_t)ldg * sizeof(double), 0,
+                                     (size_t)pd.n * sizeof(double), first_grid - cfgs[k].grid, ctx->stream));
+            return launch_step(k);
+        }
         const size_t sm = (size_t)256 * 2 * kFisherQ * sizeof(float);
 #define LOO_FIRST(T)                                                                                             \
-    LAUNCH("loo_first", loo_first_kernel<T>, cfgs[k].grid, 256, sm, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n, F, ldf, \
+    LAUNCH("loo_first", loo_first_kernel<T>, first_grid, 256, sm, ctx->stream, ctx->G[0], ldg, M, pd.col0, pd.n, F, ldf, \
            st.active.as<int>(), mask, st.partials.as<double>(), D2)
         if (tpr == 2) LOO_FIRST(2); else if (tpr == 4) LOO_FIRST(4); else if (tpr == 8) LOO_FIRST(8);
         else if (tpr == 16) LOO_FIRST(16); else LOO_FIRST(32);
@@ -1487,7 +1544,9 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
             }
         }
     }
+    tr.lap("iterations");
     CU(cudaStreamSynchronize(ctx->stream));                      // a speculative round may still be running
+    tr.lap("drain");
     if (st.missed && !force_chain) {
         // A stop check landed inside the undecidable band while the rank chain was not queued (a population that
         // converges by more than 30x within two iterations): run again with the chain on from the first iteration.
