@@ -12,7 +12,8 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libwgsassign_b200.so")
+# WGS_B200_LIB: load another build of the same library (kernel variants compiled with different -D switches)
+LIB_PATH = os.environ.get("WGS_B200_LIB") or os.path.join(_PKG, "libwgsassign_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "wgs_api.cu"), os.path.join(_PKG, "csrc", "wgs_reader.cpp")]
 HEADERS = [os.path.join(_PKG, "csrc", "wgs_kernels.cuh"), os.path.join(_PKG, "csrc", "wgs_zscore.cuh"),
            os.path.join(_ROOT, "include", "wgsassign_b200.h")]

@@ -139,18 +139,19 @@ ztally_kernel(const float2* __restrict__ G, const uchar2* __restrict__ AD, int l
 // Reproducing its bits needs its order - but only WITHIN a class: sums of different classes, components and
 // individuals are independent chains.
 //
-//  * One WARP = one individual, LANE = CLASS: lane c keeps the running sums {s0, s1, s2, count} of classes c and
-//    c + 32 in registers (the 64 classes cover every depth up to 9 and most of 10; > 99.99 % of the sites at 2x).
-//    A batch of 32 consecutive sites is laid out in the warp's shared-memory strip (class codes as bytes + GL
-//    triples) and every lane walks the codes IN SITE ORDER, loading and adding a site's triple only when it is of
-//    its class: ~7 instructions and ~1.25 shared-memory wavefronts per site and warp, no dependent shared-memory
-//    round trip, no cross-lane hand-over - the additions of a class are the only dependent chain.  Batches without
-//    a class >= 32 (91 % at 2x) take a loop with one compare per site.
-//    (First version: one thread per individual walking the sites - a shared-memory read-modify-write per site on
-//    N / 32 warps: 100 ns per site, 3 % of HBM.  Second: MATCH.ANY + leader chains: 30 ns per site.)
-//  * Deeper classes are read-modify-written in the individual's own table row by lane 0, in site order.
+//  * One WARP = one individual, LANE = SITE: a batch is 32 consecutive sites.  Lanes whose sites fall in the same
+//    (ref, alt) class find each other with MATCH.ANY; the class's first lane (the leader) takes the class's running
+//    sums {s0, s1, s2, count} from the warp's shared-memory cells and adds its members' GL triples in lane (= site)
+//    order from the warp's strip, in branch-free rounds (trip count = the largest class of the batch, ~10 of 32 at
+//    2x).  The float32 additions of one class are the only dependent chain; different classes run in different lanes.
+//    Measured designs, 1M sites x 2,000 individuals: one thread per individual walking the sites 49 ms; lane = class
+//    with register accumulators 17..20 ms (every lane walks all 32 codes); MATCH + divergent leader loops 20 ms;
+//    MATCH + branch-free rounds 15.3 ms (this one) - the pass is instruction-bound (9.3 warp instructions per site
+//    and individual before, ~6 now), not HBM-bound: profiles/ncu_summary_r2_zscore_v7.txt.
+//  * The kZOrdCells = 66 classes of depth <= 10 have cells in shared memory (> 99.99 % of the sites at 2x).
+//  * Deeper classes (up to the depth cap) are read-modify-written in the individual's own table row by their leader.
 //  * A block = kZOrdWarps adjacent individuals: their rows of a site tile arrive with coalesced 16-byte / 8-byte LDGSTS
-//    copies, double-buffered.
+//    copies into a ring of kZOrdStages tiles.
 //  * The table is read as the CARRY-IN state and left as the carry-out: under site sharding the ranks run this
 //    kernel one after the other in site order and hand the table on (wgs_zscore: ncclSend / ncclRecv over NVLink,
 //    16 bytes per (individual, class)), so the order of every addition is the reference's over the whole file.
@@ -163,10 +164,13 @@ constexpr int kZOrdStages = 4;                                           // ring
                                                                          //   0.55 TB/s whatever the arithmetic: bytes in flight, not instructions
 constexpr int kZOrdGS = 18;                                              // tile row strides (float2 / uchar2 units): 16- / 8-byte aligned rows whose
 constexpr int kZOrdAS = 20;                                              //   column reads (lane = row) spread over the banks
-constexpr int kZOrdCellsDecl = 66;
-constexpr size_t kZOrdSmem = (size_t)kZOrdWarps * (32 + kZOrdCellsDecl) * sizeof(float4) +
-                             (size_t)kZOrdStages * kZOrdTile * (kZOrdGS * sizeof(float2) + kZOrdAS * sizeof(uchar2));
+#ifndef WGS_ZORD_UNROLL
+#define WGS_ZORD_UNROLL 2
+#endif
+constexpr int kZOrdUnroll = WGS_ZORD_UNROLL;                             // additions per trip of a leader's loop
 constexpr int kZOrdCells = 66;                                           // classes with shared-memory cells: every depth up to 10
+constexpr size_t kZOrdSmem = (size_t)kZOrdWarps * (32 + kZOrdCells) * sizeof(float4) +
+                             (size_t)kZOrdStages * kZOrdTile * (kZOrdGS * sizeof(float2) + kZOrdAS * sizeof(uchar2));
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem);
@@ -203,15 +207,26 @@ __device__ __forceinline__ void ztally_ord_batch(float2 g, uchar2 a, bool valid,
     __syncwarp();                                            // the strip is complete
     // branch-free rounds (a divergent `if` per round cost a convergence barrier pair and doubled the instruction count):
     // a lane with nothing left re-reads its own strip entry and adds +0 to nothing
+    // kZOrdUnroll rounds per trip: the strip reads of a trip are issued together (their addresses come from `rem` alone),
+    // so one shared-memory latency covers the trip instead of one per addition (measured at 1M x 2,000, both launches of
+    // a z-score call: 30.7 ms with 1 round per trip, 28.6 with 2, 29.0 with 4, 29.5 with 8)
 #pragma unroll 1
-    for (int r = 0; r < maxn; ++r) {                         // warp-uniform trip count
-        const bool more = rem != 0u;
-        const float4 t = strip[more ? __ffs(rem) - 1 : lane];
-        const f32x2 n01 = fadd2(v01, pack2(t.x, t.y));
-        const float n2 = __fadd_rn(v2, t.z);
-        v01 = more ? n01 : v01;
-        v2 = more ? n2 : v2;
-        rem &= rem - 1u;                                     // 0 stays 0
+    for (int r = 0; r < maxn; r += kZOrdUnroll) {            // warp-uniform trip count
+        float4 t[kZOrdUnroll];
+        bool more[kZOrdUnroll];
+#pragma unroll
+        for (int u = 0; u < kZOrdUnroll; ++u) {
+            more[u] = rem != 0u;
+            t[u] = strip[more[u] ? __ffs(rem) - 1 : lane];
+            rem &= rem - 1u;                                 // 0 stays 0
+        }
+#pragma unroll
+        for (int u = 0; u < kZOrdUnroll; ++u) {
+            const f32x2 n01 = fadd2(v01, pack2(t[u].x, t[u].y));
+            const float n2 = __fadd_rn(v2, t[u].z);
+            v01 = more[u] ? n01 : v01;
+            v2 = more[u] ? n2 : v2;
+        }
     }
     if (leader) {
         const float2 v = unpack2(v01);
