@@ -2259,6 +2259,8 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);               // this warp is done with the slot
         if (t < 32) {                                           // warp 0 refills it once every warp has released it
+            // (refilling the PREVIOUS group's slot instead, so that warp 0 never waits here, measured 0.6 .. 1.3 % slower:
+            // one group less in flight costs more than the wait)
             const long nxt = tl + (long)nstages * gridDim.x;
             if (nxt < ntiles && dbg != 1) {
                 mbar_wait(&empty[slot], phase);
