@@ -29,7 +29,7 @@ def main():
         out["kernels"][fam] = {"kernel": r[hdr.index("Kernel Name")][:60], "sites": 200000, "individuals": 500, "populations": 10,
                                "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                                "ncu_time_s": val("gpu__time_duration.sum"), "source": os.path.basename(path)}
-    json.dump(out, open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "profiles", "ncu_traffic_%s.json" % tag.split("_")[0]), "w"), indent=1)
     print(json.dumps(out["kernels"], indent=1))
 
 
