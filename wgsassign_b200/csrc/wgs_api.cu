@@ -127,7 +127,7 @@ const char* const kOptionNames[] = {
     "em_step",            // 1: population EM with one iteration per launch
     "em_multi1",          // 1: shared-memory-tile multi-iteration population EM
     "em_no_lookahead",    // 1: read every stop decision before queueing the next iteration
-    "loo_v4", "loo_nofirst", "loo_fullfill", "loo_block", "loo_stages", "loo_passes", "loo_occ3", "loo_dbg", "prepack_v1",
+    "loo_v4", "loo_nofirst", "loo_fullfill", "loo_block", "loo_stages", "loo_passes", "loo_dbg", "prepack_v1",
     "loo_first_bpsm",     // blocks per SM of the first leave-one-out iteration (default 2)
     "loo_big_margin_pm",  // per mille of thread utilisation a 512-thread block must gain over two 256-thread ones to be chosen (default 0: chosen on a tie)
     "loo_by_pop",         // 1: leave-one-out EM population by population (one packed-row buffer at a time); -1: never
@@ -1234,12 +1234,12 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
     // whole multiples of 4 warps only: 7 warps per block leave one scheduler of the SM with less work
     // than the others (measured: 12 % slower than 8 warps, scripts/microbench/loo_quad_rate.cu)
     const int opt_bd = opt(ctx, "loo_block", 0);
-    for (int bd : {128, 256, 320, 384, 512}) {
-        if (opt_bd ? opt_bd != bd : bd == 320) continue;             // 320 (2 blocks of 10 warps at <= 102 registers): only on request
+    for (int bd = 128; bd <= 512; bd += 128) {
+        if (opt_bd && opt_bd != bd) continue;
         int rpp = bd / nq;
         if (rpp < 1) continue;
         double u = (double)(rpp * nq) / bd;
-        if (bd > 256 && best_u >= 0.88) break;                    // prefer the 3-blocks-per-SM variant unless it idles > 12 % of its threads
+        if (bd > 256 && best_u >= 0.88) break;                    // blocks above 256 threads (one per SM) only when the smaller ones idle > 12 % of their threads
         if (u > best_u + 1e-9) { best_u = u; best.block = bd; best.rows_per_pass = rpp; }
     }
     if (best.block == 0) return fail(ctx, "population of %d individuals exceeds the LOO-EM block limit (2048)", n);
@@ -1250,13 +1250,13 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
         const double u512 = (double)((512 / nq) * nq) / 512;
         if (u512 + 1e-9 >= best_u + opt(ctx, "loo_big_margin_pm", 0) * 1e-3) { best_u = u512; best.block = 512; best.rows_per_pass = 512 / nq; }
     }
-    best.big = best.block > 320;
+    best.big = best.block > 256;
     // per tile row - quad kernel: two packed buffers (odd 16-byte stride) + the raw TMA landing row;
     //              - packed kernel: double-buffered packed cells (odd 16-byte stride) + double-buffered raw row
     if (packed) {
         // ring of row groups: as many stages as fit in ~100 KB (two resident blocks per SM), at least 3
         const size_t group_bytes = (size_t)best.rows_per_pass * loo5_row_units(n) * 16;
-        const size_t ring_budget = (best.big ? 190 : opt(ctx, "loo_occ3") ? 68 : 100) * 1024;   // one / three / two resident blocks per SM
+        const size_t ring_budget = (best.big ? 190 : 100) * 1024;   // one / two resident blocks per SM
         int stages = (int)std::min<size_t>(kLoo5MaxStages, ring_budget / std::max<size_t>(group_bytes, 1));
         if (int o = opt(ctx, "loo_stages", 0)) stages = o;
         best.stages = std::max(3, std::min(stages, kLoo5MaxStages));
@@ -1281,8 +1281,6 @@ int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
     } while (0)
     if (packed) {
         if (best.big) LOO_PREP((loo_em_step5_kernel<512, 1>));
-        else if (best.block == 320) LOO_PREP((loo_em_step5_kernel<320, 2>));
-        else if (opt(ctx, "loo_occ3")) LOO_PREP((loo_em_step5_kernel<256, 3>));
         else LOO_PREP((loo_em_step5_kernel<256, 2>));
     }
     else        { if (best.big) LOO_PREP((loo_em_step4_kernel<512, 1>)); else LOO_PREP((loo_em_step4_kernel<256, 3>)); }
@@ -1433,14 +1431,8 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
             if (lc.big)
                 LAUNCH("loo_em", (loo_em_step5_kernel<512, 1>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
                        pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
-            else if (lc.block == 320)
-                LAUNCH("loo_em", (loo_em_step5_kernel<320, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
-                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
-            else if (!opt(ctx, "loo_occ3"))
-                LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
-                       pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
             else
-                LAUNCH("loo_em", (loo_em_step5_kernel<256, 3>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
+                LAUNCH("loo_em", (loo_em_step5_kernel<256, 2>), lc.grid, lc.block, lc.smem, ctx->stream, pk_of(k), ldg, M,
                        pd.col0, pd.n, lc.rows_per_pass, F, ldf, st.active.as<int>(), mask, st.partials.as<double>(), ntiles, lc.stages, loo_dbg, D2);
         } else {
             if (lc.big)

@@ -2066,10 +2066,9 @@ __device__ __forceinline__ float loo5_own(float g0, float g1, float g2, const Lo
     const float den = fmaf(g0, c.a, g1 + num);
     return num * fast_rcp(den);
 }
-template <int NP>
-__device__ __forceinline__ void loo5_quad(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3, f32x2 P4, const Loo5Coef (&c)[NP], f32x2 (&acc)[NP]) {
+__device__ __forceinline__ void loo5_quad(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3, f32x2 P4, const Loo5Coef (&c)[4], f32x2 (&acc)[4]) {
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
+    for (int k = 0; k < 4; ++k) {
         const f32x2 u = ffma2(P0, c[k].A, P1);
         const f32x2 v = ffma2(P4, c[k].B, P3);
         const f32x2 D = ffma2(v, c[k].B, ffma2(u, c[k].A, P2));
@@ -2088,11 +2087,10 @@ __device__ __forceinline__ void loo5_quad(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3
 // The first pair (low lanes) of a quad only, in scalar arithmetic: the same fused operations on half the lanes.
 // For a quad whose second pair is padding (n mod 4 = 1 or 2) this is half the FMA-pipe time and one reciprocal
 // instead of two per problem.
-template <int NP>
-__device__ __forceinline__ void loo5_pair_lo(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3, f32x2 P4, const Loo5Coef (&c)[NP], f32x2 (&acc)[NP]) {
+__device__ __forceinline__ void loo5_pair_lo(f32x2 P0, f32x2 P1, f32x2 P2, f32x2 P3, f32x2 P4, const Loo5Coef (&c)[4], f32x2 (&acc)[4]) {
     const float p0 = unpack2(P0).x, p1 = unpack2(P1).x, p2 = unpack2(P2).x, p3 = unpack2(P3).x, p4 = unpack2(P4).x;
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
+    for (int k = 0; k < 4; ++k) {
         const float a = c[k].a, b = c[k].b;
         const float ah = unpack2(c[k].AH).x, b43 = unpack2(c[k].B43).x, bh = unpack2(c[k].BH).x;
         const float u = fmaf(p0, a, p1);
@@ -2113,11 +2111,13 @@ __device__ __forceinline__ void loo5_pair_lo(f32x2 P0, f32x2 P1, f32x2 P2, f32x2
 // groups ahead of use.  (One copy per row from warp 0 made that warp 50 % slower than the others, and
 // every other warp then waited for it at "full": 23 % of all stall samples.)
 constexpr int kLoo5MaxStages = 6;
-// NP = problems evaluated per pass over a site row: 4 (one pass, 124 registers, 2 blocks of 256 per SM).  NP = 2 (two
-// passes over the same shared-memory row with half the coefficient registers: 80 registers, 3 blocks per SM) was tried
-// because the FMA pipe is only 57 % busy at 16 warps per SM (ncu r2): the kernel ran at HALF the speed, like every
-// other attempt to fit this loop into 80 registers - it is not instantiated.
-template <int MAXT, int MINB, int NP = 4>
+// Geometry: <512, 1> - one block of 16 warps per SM at 116 registers, ring of up to 190 KB - is the default; <256, 2>
+// (two blocks of 8 warps at 124 registers) runs 3..7 % slower and is kept for option loo_block.  Measured and dropped in
+// round 2, each on the same box as its control (0.554 ms per launch at 1M x 50 for <256, 2>): three blocks of 256 at 80
+// registers with a ring small enough for three 0.670 ms; two blocks of 320 at 96 registers 0.620 ms; two problems
+// per pass over the shared-memory row (half the coefficient registers) 1.1 ms.  The 97-instruction cell loop is the same
+// in all of them: registers for its eight independent chains matter more than resident warps.
+template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
                     int col0, int n, int rows_per_pass,
@@ -2208,48 +2208,40 @@ loo_em_step5_kernel(const ulonglong2* __restrict__ PK, int ldg, long M,
             const ulonglong2* row = pk0 + ((size_t)slot * TS + r) * ru;
             const int nfull = nq >> 1;                          // cells with both quads
             float fo[4], dq[4];
-#pragma unroll 1
-            for (int h0 = 0; h0 < 4; h0 += NP) {
-                Loo5Coef c[NP];
-                f32x2 acc[NP];
+            Loo5Coef c[4];
+            f32x2 acc[4];
 #pragma unroll
-                for (int k = 0; k < NP; ++k) { c[k] = loo5_coef(NP == 4 ? fin[k] : (h0 ? fin[2 + k] : fin[k])); acc[k] = 0ull; }
+            for (int k = 0; k < 4; ++k) { c[k] = loo5_coef(fin[k]); acc[k] = 0ull; }
 #pragma unroll 1
-                for (int cc = 0; cc < nfull; ++cc) {
-                    const ulonglong2 v0 = row[5 * cc], v1 = row[5 * cc + 1], v2 = row[5 * cc + 2], v3 = row[5 * cc + 3], v4 = row[5 * cc + 4];
-                    loo5_quad<NP>(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
-                    loo5_quad<NP>(v2.y, v3.x, v3.y, v4.x, v4.y, c, acc);
-                }
-                if (nq & 1) {
-                    const ulonglong2 v0 = row[5 * nfull], v1 = row[5 * nfull + 1], v2 = row[5 * nfull + 2];
-                    if (last_pair_only) loo5_pair_lo<NP>(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);   // the quad's second pair is padding
-                    else loo5_quad<NP>(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
-                }
-                // own terms: the four members of quad ti, from the raw pairs at the end of the row (loaded after the cell
-                // loop: eight fewer registers live across it)
-                const float4* rawrow = reinterpret_cast<const float4*>(row + 5 * nc);
-                const float4 ga = rawrow[2 * ti], gc = rawrow[2 * ti + 1];
-                const float og0[4] = {ga.x, ga.z, gc.x, gc.z}, og1[4] = {ga.y, ga.w, gc.y, gc.w};
+            for (int cc = 0; cc < nfull; ++cc) {
+                const ulonglong2 v0 = row[5 * cc], v1 = row[5 * cc + 1], v2 = row[5 * cc + 2], v3 = row[5 * cc + 3], v4 = row[5 * cc + 4];
+                loo5_quad(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
+                loo5_quad(v2.y, v3.x, v3.y, v4.x, v4.y, c, acc);
+            }
+            if (nq & 1) {
+                const ulonglong2 v0 = row[5 * nfull], v1 = row[5 * nfull + 1], v2 = row[5 * nfull + 2];
+                if (last_pair_only) loo5_pair_lo(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);   // the quad's second pair is padding
+                else loo5_quad(v0.x, v0.y, v1.x, v1.y, v2.x, c, acc);
+            }
+            // own terms: the four members of quad ti, from the raw pairs at the end of the row (loaded after the cell
+            // loop: eight fewer registers live across it)
+            const float4* rawrow = reinterpret_cast<const float4*>(row + 5 * nc);
+            const float4 ga = rawrow[2 * ti], gc = rawrow[2 * ti + 1];
+            const float og0[4] = {ga.x, ga.z, gc.x, gc.z}, og1[4] = {ga.y, ga.w, gc.y, gc.w};
 #pragma unroll
-                for (int k = 0; k < NP; ++k) {
-                    const int kk = NP == 4 ? k : (h0 ? 2 + k : k);          // member of the quad
-                    const float g0 = NP == 4 ? og0[k] : (h0 ? og0[2 + k] : og0[k]), g1 = NP == 4 ? og1[k] : (h0 ? og1[2 + k] : og1[k]);
-                    const float own = loo5_own(g0, g1, third_gl(g0, g1), c[k]);
-                    const float f_in = NP == 4 ? fin[k] : (h0 ? fin[2 + k] : fin[k]);
-                    const float2 a = unpack2(acc[k]);
-                    float fn = ((a.x + a.y) - own) * inv_div;
-                    if (fn < 1e-12f) fn = 1e-12f;               // comparisons are false for NaN: NaN survives
-                    if (fn > 0.99999994f) fn = 0.99999994f;
-                    float fo_k = f_in, dq_k = 0.f;              // frozen / masked problems keep their value
-                    if (okp & (1u << kk)) {                     // (v1 - v2) * (v1 - v2) as rmse1d forms it (emMAF_cy.pyx:31): no FMA
-                        const float d = __fsub_rn(fn, f_in);
-                        dq_k = __fmul_rn(d, d);
-                        fo_k = fn;
-                    }
-                    if (NP == 4) { fo[k] = fo_k; dq[k] = dq_k; ssq[k] = __fadd_rn(ssq[k], dq_k); }
-                    else if (h0 == 0) { fo[k] = fo_k; dq[k] = dq_k; ssq[k] = __fadd_rn(ssq[k], dq_k); }
-                    else { fo[2 + k] = fo_k; dq[2 + k] = dq_k; ssq[2 + k] = __fadd_rn(ssq[2 + k], dq_k); }
+            for (int k = 0; k < 4; ++k) {
+                const float own = loo5_own(og0[k], og1[k], third_gl(og0[k], og1[k]), c[k]);
+                const float2 a = unpack2(acc[k]);
+                float fn = ((a.x + a.y) - own) * inv_div;
+                if (fn < 1e-12f) fn = 1e-12f;                   // comparisons are false for NaN: NaN survives
+                if (fn > 0.99999994f) fn = 0.99999994f;
+                fo[k] = fin[k]; dq[k] = 0.f;                    // frozen / masked problems keep their value
+                if (okp & (1u << k)) {                          // (v1 - v2) * (v1 - v2) as rmse1d forms it (emMAF_cy.pyx:31): no FMA
+                    const float d = __fsub_rn(fn, fin[k]);
+                    dq[k] = __fmul_rn(d, d);
+                    fo[k] = fn;
                 }
+                ssq[k] = __fadd_rn(ssq[k], dq[k]);
             }
             *reinterpret_cast<float4*>(&F[(tl * TS + r) * (long)ldf + c0]) = make_float4(fo[0], fo[1], fo[2], fo[3]);
             // quad-major [ldg / 4][M][4]: one 16-byte store per thread, the sites of a quad contiguous (a purely problem-major
