@@ -1469,18 +1469,19 @@ int run_em_loo(wgs_ctx* ctx, int iter, double tole, float* F, int ldf, const uns
         if (tpr == 2) LOO_FIRST(2); else if (tpr == 4) LOO_FIRST(4); else if (tpr == 8) LOO_FIRST(8);
         else if (tpr == 16) LOO_FIRST(16); else LOO_FIRST(32);
 #undef LOO_FIRST
-        add_work(ctx, "loo_first", (double)M * pd.n * 8.0 + (double)M * pd.n * 4.0, (double)M * pd.n);
+        add_work(ctx, "loo_first", (double)M * pd.n * 8.0 + (double)M * pd.n * (D2 ? 8.0 : 4.0), (double)M * pd.n);
         return 0;
     };
     // algorithmic work of one iteration of population k, from the flags that were in force when it ran: the
-    // population's packed rows once + read/write of every active problem's f; n evaluations per active (site, problem)
+    // population's packed rows once + read/write of every active problem's f (+ its squared change, written for the
+    // exact stop rule); n evaluations per active (site, problem)
     auto account = [&](int k, int it) {
         if (it == 1 && use_first && first_tpr(k)) return;           // accounted as "loo_first" at launch
         PopDesc pd = ctx->pops[k];
         double act = 0;
         for (int j = 0; j < pd.n; ++j) act += st.h_active[pd.col0 + j] ? 1 : 0;
         if (act > 0)
-            add_work(ctx, "loo_em", (double)M * (cfgs[k].packed ? loo5_row_units(pd.n) * 16.0 : pd.n * 8.0) + (double)M * act * 8.0, (double)M * act * pd.n);
+            add_work(ctx, "loo_em", (double)M * (cfgs[k].packed ? loo5_row_units(pd.n) * 16.0 : pd.n * 8.0) + (double)M * act * (D2 ? 12.0 : 8.0), (double)M * act * pd.n);
     };
     auto pop_active = [&](int k) {
         bool any = false;
