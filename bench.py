@@ -410,6 +410,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     from wgsassign_b200 import _lib, dist, mixture
+    numa = dist.bind_near_gpu(local) if world > 1 else "numa: single process, not bound"   # before any pinned allocation
     if world > 1:
         import torch.distributed as td
         # keep rank 0's stdout to the one JSON line: NCCL prints its version banner to stdout at
@@ -741,7 +742,7 @@ def main():
             "l2": "inputs (%.1f GB GL per GPU) exceed the 126 MB L2, no flush needed" % (M_local * N_IND * 8 / 1e9),
             "timer": "host clock around blocking C-ABI calls, device-synchronised + barrier on both sides, max over ranks; "
                      "kernels timed with CUDA events on the library's stream",
-            "self_assignment_rate": assign_ok}
+            "self_assignment_rate": assign_ok, "host_binding_rank0": numa}
     if args.config == "cfg3":
         conf.update(em_iters_ref=[int(x) for x in res["its"]], em_iters_loo_minmax=[int(np.min(res["lits"])), int(np.max(res["lits"]))])
     if args.config == "cfg4":

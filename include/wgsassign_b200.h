@@ -48,6 +48,9 @@ typedef void (*wgs_allreduce_fn)(void *buf, int64_t n, int32_t dtype, void *user
 
 int32_t     wgs_abi_version(void);
 int32_t     wgs_device_count(void);
+/* PCI bus id of a device ("0000:1b:00.0", as sysfs names it): the host side uses it to allocate its pinned staging
+ * buffers on the NUMA node the GPU hangs off (dist.bind_near_gpu).  len >= 16. */
+int32_t     wgs_device_pci_bus_id(int32_t device, char *out, int32_t len);
 const char *wgs_last_error(const wgs_ctx *ctx); /* ctx may be NULL: last create() error */
 
 int32_t wgs_create(int32_t device, wgs_ctx **out);

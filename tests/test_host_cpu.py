@@ -300,3 +300,17 @@ def test_dist_plumbing_gloo_world2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_numa_binding_helper_is_failsafe(tmp_path, monkeypatch):
+    """dist.bind_near_gpu: parses sysfs cpulists, never raises, and leaves the affinity alone when there is no GPU."""
+    import os
+    from wgsassign_b200 import dist
+    assert dist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert dist._parse_cpulist("5") == {5}
+    before = os.sched_getaffinity(0)
+    msg = dist.bind_near_gpu(0, sysfs=str(tmp_path))            # no device (CPU box) or no such sysfs tree: a message, no change
+    assert msg.startswith("numa:")
+    assert os.sched_getaffinity(0) == before
+    monkeypatch.setenv("WGS_NO_NUMA_BIND", "1")
+    assert "off" in dist.bind_near_gpu(0)

@@ -96,6 +96,7 @@ class _Run:
             use_cuda = torch.cuda.is_available()
             if use_cuda:
                 torch.cuda.set_device(local)
+                self.dist.bind_near_gpu(local)               # pinned read buffers on the GPU's NUMA node
             if not td.is_initialized():
                 td.init_process_group("nccl" if use_cuda else "gloo")
             self.rank0 = td.get_rank() == 0

@@ -33,6 +33,7 @@ _vp, _i32, _i64, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.
 SYMBOLS = {
     "wgs_abi_version": (_i32, []),
     "wgs_device_count": (_i32, []),
+    "wgs_device_pci_bus_id": (_i32, [_i32, ctypes.c_char_p, _i32]),
     "wgs_last_error": (ctypes.c_char_p, [_vp]),
     "wgs_create": (_i32, [_i32, ctypes.POINTER(_vp)]),
     "wgs_destroy": (None, [_vp]),

@@ -1579,6 +1579,13 @@ int32_t wgs_device_count(void)
     return n;
 }
 
+int32_t wgs_device_pci_bus_id(int32_t device, char* out, int32_t len)
+{
+    if (!out || len < 16) return 1;
+    out[0] = 0;
+    return cudaDeviceGetPCIBusId(out, len, device) == cudaSuccess ? 0 : 1;
+}
+
 const char* wgs_last_error(const wgs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int32_t wgs_create(int32_t device, wgs_ctx** out)
