@@ -366,6 +366,18 @@ def ingest_probe(cfg, ctx_device):
                                "uncompressed_mb_per_s": st["uncompressed_bytes"] / 1e6 / wall, "matrix_gb_per_s": L.nbytes / 1e9 / wall,
                                "path": "readBeagle(on_block) + wgs_upload_gl_begin/rows/end: the upload of block b overlaps the parsing of block b+1"}
     session.reset()
+    # the same text as BGZF (what ANGSD writes): the members are inflated in parallel
+    pz = os.path.join(tmp, "x.bgzf.beagle.gz")
+    with open(pz, "wb") as fh:
+        member = synth.bgzf_compress(body)[:-28]                 # without the end-of-file member
+        fh.write(synth.bgzf_compress(header)[:-28])
+        for _ in range(reps):
+            fh.write(member)
+        fh.write(synth.bgzf_compress(b"")[-28:])
+    L, _, _ = reader.readBeagle(pz, threads)
+    out["beagle_bgzf"] = dict(reader.last_stats["beagle"], shape=[int(L.shape[0]), int(L.shape[1])])
+    del L
+    os.unlink(pz)
     AD = reader.readAD(pa, threads)
     out["allele_depths"] = dict(reader.last_stats["ad"], shape=[int(AD.shape[0]), int(AD.shape[1])], dtype=str(AD.dtype))
     for f in (pb, pa):

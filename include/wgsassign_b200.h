@@ -244,6 +244,9 @@ int64_t     wgs_beagle_stream_next(wgs_beagle_stream *s, float *out, int64_t max
 int64_t     wgs_beagle_stream_rows_seen(const wgs_beagle_stream *s);
 const char *wgs_beagle_stream_site(const wgs_beagle_stream *s, int64_t row);               /* rows seen so far */
 int64_t     wgs_beagle_stream_estimate_rows(const wgs_beagle_stream *s);                   /* total rows, from the bytes read so far */
+/* 1 when a Beagle / allele-depth stream reads a BGZF file (bgzip, what ANGSD writes: independent members of <= 64 KB
+ * of text, inflated by several threads at once), 0 for a plain gzip stream (one inflate thread). */
+int32_t     wgs_stream_is_bgzf(const void *stream);
 int32_t     wgs_beagle_stream_stats(const wgs_beagle_stream *s, double *inflate_s, double *parse_s,
                                     int64_t *compressed_bytes, int64_t *uncompressed_bytes);
 void        wgs_beagle_stream_close(wgs_beagle_stream *s);

@@ -314,3 +314,46 @@ def test_numa_binding_helper_is_failsafe(tmp_path, monkeypatch):
     assert os.sched_getaffinity(0) == before
     monkeypatch.setenv("WGS_NO_NUMA_BIND", "1")
     assert "off" in dist.bind_near_gpu(0)
+
+
+def test_bgzf_input_reads_like_plain_gzip(tmp_path):
+    """A BGZF Beagle / allele-depth file (members inflated in parallel) gives exactly what the same text gives as one
+    gzip stream: values, names, row ranges; a truncated or corrupted member is an error, not silent data."""
+    import gzip
+    from wgsassign_b200 import reader, synth
+    n, m = 7, 9000                                               # ~ 2 MB of text: dozens of 64 KB members, lines straddle them
+    rng = np.random.default_rng(5)
+    vals = np.round(rng.random((m, 3 * n)), 6)
+    header = "marker\tallele1\tallele2" + "".join("\tind%d\tind%d\tind%d" % (i, i, i) for i in range(n)) + "\n"
+    text = (header + "".join("chr1_%d\t0\t1\t%s\n" % (s, "\t".join("%.6f" % v for v in vals[s])) for s in range(m))).encode()
+    pg, pz = tmp_path / "a.beagle.gz", tmp_path / "a.bgzf.beagle.gz"
+    pg.write_bytes(gzip.compress(text, 1))
+    z = synth.bgzf_compress(text)
+    assert gzip.decompress(z) == text
+    pz.write_bytes(z)
+    A = reader.readBeagle(str(pg), 4)
+    assert reader.last_stats["beagle"]["bgzf"] is False
+    B = reader.readBeagle(str(pz), 4)
+    assert reader.last_stats["beagle"]["bgzf"] is True
+    assert np.array_equal(A[0], B[0]) and list(A[1]) == list(B[1]) and list(A[2]) == list(B[2])
+    assert A[0].shape == (m, 2 * n)
+    lo, hi = 1234, 7777
+    C = reader.readBeagle(str(pz), 3, rows=(lo, hi))
+    assert np.array_equal(C[0], A[0][lo:hi])
+    assert reader.count_rows(str(pz))[0] == m
+    # allele depths
+    ad = rng.integers(0, 40, size=(3000, 2 * n))
+    atext = "".join(" ".join(map(str, r)) + "\n" for r in ad).encode()
+    qa, qz = tmp_path / "ad.txt.gz", tmp_path / "ad.bgzf.txt.gz"
+    qa.write_bytes(gzip.compress(atext, 1))
+    qz.write_bytes(synth.bgzf_compress(atext))
+    assert np.array_equal(reader.readAD(str(qa), 4), reader.readAD(str(qz), 4))
+    # damage: flip a payload byte of a middle member / cut the file inside a member
+    bad = bytearray(z)
+    bad[len(bad) // 2] ^= 0x55
+    (tmp_path / "bad.beagle.gz").write_bytes(bytes(bad))
+    with pytest.raises(Exception):
+        reader.readBeagle(str(tmp_path / "bad.beagle.gz"), 4)
+    (tmp_path / "cut.beagle.gz").write_bytes(z[: len(z) // 2])
+    with pytest.raises(Exception):
+        reader.readBeagle(str(tmp_path / "cut.beagle.gz"), 4)

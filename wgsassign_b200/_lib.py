@@ -78,6 +78,7 @@ SYMBOLS = {
     "wgs_beagle_stream_rows_seen": (_i64, [_vp]),
     "wgs_beagle_stream_site": (ctypes.c_char_p, [_vp, _i64]),
     "wgs_beagle_stream_estimate_rows": (_i64, [_vp]),
+    "wgs_stream_is_bgzf": (_i32, [_vp]),
     "wgs_beagle_stream_stats": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "wgs_beagle_stream_close": (None, [_vp]),
     "wgs_ad_stream_open": (_i32, [ctypes.c_char_p, _i32, ctypes.POINTER(_vp)]),

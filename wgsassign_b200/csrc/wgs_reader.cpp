@@ -8,9 +8,10 @@
 // Output contract: float32 [M, 2N] whose values equal (float)atof(token) bit for bit, plus
 // the sample and site name lists.
 //
-// Pipeline (GzLines): inflate is inherently serial (one gzip stream) - a dedicated thread runs it
+// Pipeline (GzLines): inflating one gzip stream is inherently serial - a dedicated thread runs it
 // and hands decompressed blocks, cut at line boundaries, through a bounded queue, so inflating
-// block b+1.. overlaps the parsing of block b.  Parsing is not serial: a persistent pool of
+// block b+1.. overlaps the parsing of block b.  A BGZF file (bgzip; what ANGSD writes) is a chain of
+// independent members whose sizes stand in their headers: those are inflated by several threads at once.  Parsing is not serial: a persistent pool of
 // threads converts the lines of a block straight into the CALLER's row-major output (pinned
 // memory in the CLI - no intermediate copy), and rows outside the caller's keep range (another
 // rank's sites) are counted and named but never converted.  Plain "digits.digits" tokens (what
@@ -136,15 +137,45 @@ private:
 // ---- gzip text -> blocks of whole lines, inflated by a background thread ----
 struct Block { std::vector<char> data; size_t end = 0; };
 
+// BGZF (bgzip; what ANGSD itself writes): a gzip file made of independent members of at most 64 KB of text, each with
+// its compressed size in a "BC" extra subfield of the header and its text size in the trailer - the members of a batch
+// can be located without inflating anything and inflated in parallel straight into their places of one text buffer.
+// Returns the member's total size, 0 if [p, p + avail) does not hold the whole header yet, -1 if it is not BGZF.
+inline long bgzf_member_size(const unsigned char* p, size_t avail)
+{
+    if (avail < 12) return 0;
+    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return -1;
+    const size_t xlen = (size_t)p[10] | ((size_t)p[11] << 8);
+    if (avail < 12 + xlen) return 0;
+    for (size_t o = 12; o + 4 <= 12 + xlen;) {
+        const size_t slen = (size_t)p[o + 2] | ((size_t)p[o + 3] << 8);
+        if (p[o] == 'B' && p[o + 1] == 'C' && slen == 2 && o + 6 <= 12 + xlen)
+            return (long)((size_t)p[o + 4] | ((size_t)p[o + 5] << 8)) + 1;
+        o += 4 + slen;
+    }
+    return -1;
+}
+
 class GzLines {
 public:
-    bool open(const char* path, std::string* err) {
-        gz_ = gzopen(path, "rb");
-        if (!gz_) { *err = std::string("cannot open ") + path; return false; }
-        gzbuffer(gz_, 1 << 20);
+    // inflate_threads: workers of the BGZF path (a plain gzip stream is inflated by the one background thread)
+    bool open(const char* path, std::string* err, int inflate_threads = 1) {
         FILE* f = fopen(path, "rb");
-        if (f) { fseek(f, 0, SEEK_END); compressed_size_ = ftell(f); fclose(f); }
-        th_ = std::thread([this] { inflate_loop(); });
+        if (!f) { *err = std::string("cannot open ") + path; return false; }
+        unsigned char head[64];
+        const size_t got = fread(head, 1, sizeof head, f);
+        fseek(f, 0, SEEK_END); compressed_size_ = ftell(f);
+        if (bgzf_member_size(head, got) > 0) {
+            fseek(f, 0, SEEK_SET);
+            raw_ = f;
+            nth_ = std::max(1, std::min(inflate_threads, 32));
+        } else {
+            fclose(f);
+            gz_ = gzopen(path, "rb");
+            if (!gz_) { *err = std::string("cannot open ") + path; return false; }
+            gzbuffer(gz_, 1 << 20);
+        }
+        th_ = std::thread([this] { if (raw_) bgzf_loop(); else inflate_loop(); });
         return true;
     }
     ~GzLines() {
@@ -152,7 +183,9 @@ public:
         cv_space_.notify_all();
         if (th_.joinable()) th_.join();
         if (gz_) gzclose(gz_);
+        if (raw_) fclose(raw_);
     }
+    bool is_bgzf() const { return raw_ != nullptr; }
     // next block of whole lines; false at end of file or on error (failed())
     bool next(Block* out) {
         std::unique_lock<std::mutex> lk(m_);
@@ -170,6 +203,103 @@ public:
     long uncompressed_bytes() const { return uncompressed_.load(); }
     double inflate_seconds() const { return inflate_s_.load(); }
 private:
+    // cut a text block at its last line end (unless it is the file's last), keep the rest for the next one and queue it;
+    // false when the consumer went away
+    bool push_text(Block& b, std::string& carry, bool last) {
+        size_t end = b.data.size();
+        if (!last) {
+            while (end > 0 && b.data[end - 1] != '\n') --end;
+            if (end == 0) { carry.assign(b.data.begin(), b.data.end()); return true; }   // one line longer than the block
+        }
+        carry.assign(b.data.begin() + end, b.data.end());
+        b.end = end;
+        std::unique_lock<std::mutex> lk(m_);
+        cv_space_.wait(lk, [this] { return q_.size() < 3 || abort_; });
+        if (abort_) return false;
+        q_.push_back(std::move(b));
+        lk.unlock();
+        cv_data_.notify_one();
+        return true;
+    }
+    void fail_now() { std::lock_guard<std::mutex> lk(m_); failed_ = true; cv_data_.notify_all(); }
+
+    struct Member { size_t in_off; unsigned csize, isize; size_t out_off; };
+    // raw inflate of one member's deflate payload into dst; checks the text size and the CRC-32 of the trailer
+    static bool inflate_member(const unsigned char* p, unsigned csize, unsigned isize, char* dst) {
+        const size_t xlen = (size_t)p[10] | ((size_t)p[11] << 8), hdr = 12 + xlen;
+        if ((size_t)csize < hdr + 8) return false;
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) return false;
+        zs.next_in = const_cast<unsigned char*>(p + hdr);
+        zs.avail_in = (unsigned)(csize - hdr - 8);
+        zs.next_out = reinterpret_cast<unsigned char*>(dst);
+        zs.avail_out = isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        const bool ok = rc == Z_STREAM_END && zs.total_out == isize;
+        inflateEnd(&zs);
+        if (!ok) return false;
+        const unsigned char* t = p + csize - 8;
+        const unsigned long want = (unsigned long)t[0] | ((unsigned long)t[1] << 8) | ((unsigned long)t[2] << 16) | ((unsigned long)t[3] << 24);
+        return crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const unsigned char*>(dst), isize) == want;
+    }
+    void bgzf_loop() {
+        const size_t RAW = (size_t)8 << 20, TEXT = (size_t)32 << 20;
+        std::vector<unsigned char> raw(RAW + (1 << 17));
+        size_t have = 0, pos = 0;
+        long consumed = 0;
+        std::string carry;
+        bool file_done = false;
+        for (;;) {
+            if (pos > 0) { memmove(raw.data(), raw.data() + pos, have - pos); have -= pos; pos = 0; }
+            if (!file_done && have < RAW) {
+                const size_t got = fread(raw.data() + have, 1, RAW - have, raw_);
+                if (got == 0) file_done = true;
+                have += got;
+            }
+            std::vector<Member> mem;
+            size_t text = 0;
+            while (pos < have && text < TEXT) {
+                const long sz = bgzf_member_size(raw.data() + pos, have - pos);
+                if (sz < 0 || (sz == 0 && file_done)) { fail_now(); return; }      // not BGZF after all, or a truncated member
+                if (sz == 0 || pos + (size_t)sz > have) {
+                    if (file_done) { fail_now(); return; }
+                    break;                                                         // the rest of this member is still in the file
+                }
+                const unsigned char* t = raw.data() + pos + sz - 4;
+                const unsigned isize = (unsigned)t[0] | ((unsigned)t[1] << 8) | ((unsigned)t[2] << 16) | ((unsigned)t[3] << 24);
+                mem.push_back({pos, (unsigned)sz, isize, text});
+                pos += (size_t)sz;
+                text += isize;
+            }
+            const bool last = file_done && pos == have;
+            if (mem.empty() && !last) continue;                                    // (a member is at most 64 KB: the next read completes it)
+            Block b;
+            b.data.assign(carry.begin(), carry.end());
+            const size_t off = b.data.size();
+            b.data.resize(off + text);
+            const auto t0 = std::chrono::steady_clock::now();
+            std::atomic<size_t> nexti{0};
+            std::atomic<bool> bad{false};
+            auto work = [&] {
+                for (size_t i; (i = nexti.fetch_add(1)) < mem.size();)
+                    if (!inflate_member(raw.data() + mem[i].in_off, mem[i].csize, mem[i].isize, b.data.data() + off + mem[i].out_off)) bad = true;
+            };
+            std::vector<std::thread> ws;
+            for (int w = 1; w < nth_ && (size_t)w < mem.size(); ++w) ws.emplace_back(work);
+            work();
+            for (auto& w : ws) w.join();
+            inflate_s_.store(inflate_s_.load() + std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+            if (bad) { fail_now(); return; }
+            uncompressed_.fetch_add((long)text);
+            for (const Member& m : mem) consumed += m.csize;
+            compressed_pos_.store(consumed);
+            if (!push_text(b, carry, last)) return;
+            if (last) break;
+        }
+        { std::lock_guard<std::mutex> lk(m_); eof_ = true; }
+        cv_data_.notify_all();
+    }
     void inflate_loop() {
         const size_t CH = (size_t)32 << 20;
         std::string carry;
@@ -182,29 +312,19 @@ private:
             const auto t0 = std::chrono::steady_clock::now();
             const int got = gzread(gz_, b.data.data() + off, (unsigned)CH);
             inflate_s_.store(inflate_s_.load() + std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-            if (got < 0) { std::lock_guard<std::mutex> lk(m_); failed_ = true; cv_data_.notify_all(); return; }
+            if (got < 0) { fail_now(); return; }
             b.data.resize(off + (size_t)got);
             uncompressed_.fetch_add(got);
             compressed_pos_.store((long)gzoffset(gz_));
             eof = (size_t)got < CH;
-            size_t end = b.data.size();
-            if (!eof) {
-                while (end > 0 && b.data[end - 1] != '\n') --end;
-                if (end == 0) { carry.assign(b.data.begin(), b.data.end()); continue; }   // one line longer than the block
-            }
-            carry.assign(b.data.begin() + end, b.data.end());
-            b.end = end;
-            std::unique_lock<std::mutex> lk(m_);
-            cv_space_.wait(lk, [this] { return q_.size() < 3 || abort_; });
-            if (abort_) return;
-            q_.push_back(std::move(b));
-            lk.unlock();
-            cv_data_.notify_one();
+            if (!push_text(b, carry, eof)) return;
         }
         { std::lock_guard<std::mutex> lk(m_); eof_ = true; }
         cv_data_.notify_all();
     }
     gzFile gz_ = nullptr;
+    FILE* raw_ = nullptr;                                 // BGZF: the compressed file itself
+    int nth_ = 1;
     std::thread th_;
     std::mutex m_;
     std::condition_variable cv_data_, cv_space_;
@@ -340,8 +460,9 @@ Stream* open_stream(const char* path, int threads, bool is_ad)
 {
     Stream* S = new Stream();
     S->is_ad = is_ad;
-    if (!S->gz.open(path, &g_reader_error)) { delete S; return nullptr; }
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    // BGZF input: a quarter of the threads inflate (one core inflates ~4x the text it can parse)
+    if (!S->gz.open(path, &g_reader_error, std::max(2, threads / 4))) { delete S; return nullptr; }
     S->pool = new Pool(std::min(threads, 64));
     g_reader_error.clear();
     if (!ensure_lines(S) && !S->header_done) {
@@ -458,6 +579,9 @@ int64_t wgs_beagle_stream_estimate_rows(const wgs_beagle_stream* s)
     const double total_u = (double)ubytes * ((double)csize / (double)cpos);
     return (int64_t)(total_u / bpr) + 1;
 }
+// 1 when the stream is BGZF (members inflated in parallel), 0 for a plain gzip stream; either kind of stream handle
+int32_t wgs_stream_is_bgzf(const void* s) { return s && ((const Stream*)s)->gz.is_bgzf() ? 1 : 0; }
+
 int32_t wgs_beagle_stream_stats(const wgs_beagle_stream* s, double* inflate_s, double* parse_s, int64_t* compressed_bytes, int64_t* uncompressed_bytes)
 {
     const Stream* S = (const Stream*)s;

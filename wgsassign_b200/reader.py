@@ -30,7 +30,7 @@ def _stats(L, h, fn, wall, rows, kind):
     fn(h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(u))
     last_stats[kind] = dict(wall_s=wall, inflate_s=a.value, parse_s=b.value, compressed_bytes=c.value, uncompressed_bytes=u.value,
                             rows=rows, compressed_mb_per_s=c.value / 1e6 / max(wall, 1e-9),
-                            uncompressed_mb_per_s=u.value / 1e6 / max(wall, 1e-9))
+                            uncompressed_mb_per_s=u.value / 1e6 / max(wall, 1e-9), bgzf=bool(L.wgs_stream_is_bgzf(h)))
 
 
 def count_rows(beagle, threads=0):

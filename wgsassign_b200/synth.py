@@ -74,3 +74,18 @@ def write_beagle(path, L, sample_names, site_names):
             fh.write("%s\t0\t1\t" % site_names[r])
             fh.write("\t".join("%.6f" % v for v in cells))
             fh.write("\n")
+
+
+def bgzf_compress(data, level=1, block=65280):
+    """BGZF (bgzip) bytes of `data`: independent gzip members of <= 64 KB of text with their compressed size in a
+    "BC" extra subfield, then the end-of-file member - the container ANGSD writes its .beagle.gz in.  For the ingestion
+    probe of bench.py and the reader tests."""
+    import struct, zlib
+    out = bytearray()
+    for o in range(0, len(data), block):
+        chunk = data[o:o + block]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        payload = c.compress(chunk) + c.flush()
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(payload) + 8 - 1)
+        out += payload + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk))
+    return bytes(out) + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
