@@ -243,6 +243,8 @@ int32_t     wgs_beagle_stream_names(wgs_beagle_stream *s, int32_t keep);   /* 0:
 int64_t     wgs_beagle_stream_next(wgs_beagle_stream *s, float *out, int64_t max_rows);
 int64_t     wgs_beagle_stream_rows_seen(const wgs_beagle_stream *s);
 const char *wgs_beagle_stream_site(const wgs_beagle_stream *s, int64_t row);               /* rows seen so far */
+/* every site name seen so far, each followed by '\n', into out[0 .. cap); returns the bytes needed (out may be NULL) */
+int64_t     wgs_beagle_stream_sites_joined(const wgs_beagle_stream *s, char *out, int64_t cap);
 int64_t     wgs_beagle_stream_estimate_rows(const wgs_beagle_stream *s);                   /* total rows, from the bytes read so far */
 /* 1 when a Beagle / allele-depth stream reads a BGZF file (bgzip, what ANGSD writes: independent members of <= 64 KB
  * of text, inflated by several threads at once), 0 for a plain gzip stream (one inflate thread). */

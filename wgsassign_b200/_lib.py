@@ -77,6 +77,7 @@ SYMBOLS = {
     "wgs_beagle_stream_next": (_i64, [_vp, _vp, _i64]),
     "wgs_beagle_stream_rows_seen": (_i64, [_vp]),
     "wgs_beagle_stream_site": (ctypes.c_char_p, [_vp, _i64]),
+    "wgs_beagle_stream_sites_joined": (_i64, [_vp, _vp, _i64]),
     "wgs_beagle_stream_estimate_rows": (_i64, [_vp]),
     "wgs_stream_is_bgzf": (_i32, [_vp]),
     "wgs_beagle_stream_stats": (_i32, [_vp, _vp, _vp, _vp, _vp]),

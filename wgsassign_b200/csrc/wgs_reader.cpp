@@ -31,6 +31,7 @@
 #include <cstring>
 #include <deque>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -135,7 +136,22 @@ private:
 };
 
 // ---- gzip text -> blocks of whole lines, inflated by a background thread ----
-struct Block { std::vector<char> data; size_t end = 0; };
+// A text block: raw storage that is never value-initialised (zero-filling 32 MB per block cost as much as parsing it)
+// and that goes back to the producer for reuse when the consumer takes the next block (no fresh pages to fault in).
+struct Block {
+    std::unique_ptr<char[]> buf;
+    size_t cap = 0, size = 0, end = 0;
+    char* data() { return buf.get(); }
+    const char* data() const { return buf.get(); }
+    void reserve(size_t n) {                              // keeps the first `size` bytes
+        if (n <= cap) return;
+        std::unique_ptr<char[]> nb(new char[n]);
+        if (size) memcpy(nb.get(), buf.get(), size);
+        buf = std::move(nb);
+        cap = n;
+    }
+    void assign(const std::string& t) { size = 0; reserve(t.size()); if (!t.empty()) memcpy(buf.get(), t.data(), t.size()); size = t.size(); }
+};
 
 // BGZF (bgzip; what ANGSD itself writes): a gzip file made of independent members of at most 64 KB of text, each with
 // its compressed size in a "BC" extra subfield of the header and its text size in the trailer - the members of a batch
@@ -189,6 +205,7 @@ public:
     // next block of whole lines; false at end of file or on error (failed())
     bool next(Block* out) {
         std::unique_lock<std::mutex> lk(m_);
+        if (out->cap) { out->size = out->end = 0; spare_.push_back(std::move(*out)); *out = Block(); }   // the consumed block's storage
         cv_data_.wait(lk, [this] { return !q_.empty() || eof_ || failed_; });
         if (q_.empty()) return false;
         *out = std::move(q_.front());
@@ -206,12 +223,12 @@ private:
     // cut a text block at its last line end (unless it is the file's last), keep the rest for the next one and queue it;
     // false when the consumer went away
     bool push_text(Block& b, std::string& carry, bool last) {
-        size_t end = b.data.size();
+        size_t end = b.size;
         if (!last) {
-            while (end > 0 && b.data[end - 1] != '\n') --end;
-            if (end == 0) { carry.assign(b.data.begin(), b.data.end()); return true; }   // one line longer than the block
+            while (end > 0 && b.data()[end - 1] != '\n') --end;
+            if (end == 0) { carry.assign(b.data(), b.size); recycle(b); return true; }   // one line longer than the block
         }
-        carry.assign(b.data.begin() + end, b.data.end());
+        carry.assign(b.data() + end, b.size - end);
         b.end = end;
         std::unique_lock<std::mutex> lk(m_);
         cv_space_.wait(lk, [this] { return q_.size() < 3 || abort_; });
@@ -222,6 +239,14 @@ private:
         return true;
     }
     void fail_now() { std::lock_guard<std::mutex> lk(m_); failed_ = true; cv_data_.notify_all(); }
+    Block fresh() {
+        std::lock_guard<std::mutex> lk(m_);
+        if (spare_.empty()) return Block();
+        Block b = std::move(spare_.back());
+        spare_.pop_back();
+        return b;
+    }
+    void recycle(Block& b) { std::lock_guard<std::mutex> lk(m_); b.size = b.end = 0; spare_.push_back(std::move(b)); b = Block(); }
 
     struct Member { size_t in_off; unsigned csize, isize; size_t out_off; };
     // raw inflate of one member's deflate payload into dst; checks the text size and the CRC-32 of the trailer
@@ -274,16 +299,17 @@ private:
             }
             const bool last = file_done && pos == have;
             if (mem.empty() && !last) continue;                                    // (a member is at most 64 KB: the next read completes it)
-            Block b;
-            b.data.assign(carry.begin(), carry.end());
-            const size_t off = b.data.size();
-            b.data.resize(off + text);
+            Block b = fresh();
+            b.assign(carry);
+            const size_t off = b.size;
+            b.reserve(off + text);
+            b.size = off + text;
             const auto t0 = std::chrono::steady_clock::now();
             std::atomic<size_t> nexti{0};
             std::atomic<bool> bad{false};
             auto work = [&] {
                 for (size_t i; (i = nexti.fetch_add(1)) < mem.size();)
-                    if (!inflate_member(raw.data() + mem[i].in_off, mem[i].csize, mem[i].isize, b.data.data() + off + mem[i].out_off)) bad = true;
+                    if (!inflate_member(raw.data() + mem[i].in_off, mem[i].csize, mem[i].isize, b.data() + off + mem[i].out_off)) bad = true;
             };
             std::vector<std::thread> ws;
             for (int w = 1; w < nth_ && (size_t)w < mem.size(); ++w) ws.emplace_back(work);
@@ -305,15 +331,15 @@ private:
         std::string carry;
         bool eof = false;
         while (!eof) {
-            Block b;
-            b.data.assign(carry.begin(), carry.end());
-            const size_t off = b.data.size();
-            b.data.resize(off + CH);
+            Block b = fresh();
+            b.assign(carry);
+            const size_t off = b.size;
+            b.reserve(off + CH);
             const auto t0 = std::chrono::steady_clock::now();
-            const int got = gzread(gz_, b.data.data() + off, (unsigned)CH);
+            const int got = gzread(gz_, b.data() + off, (unsigned)CH);
             inflate_s_.store(inflate_s_.load() + std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
             if (got < 0) { fail_now(); return; }
-            b.data.resize(off + (size_t)got);
+            b.size = off + (size_t)got;
             uncompressed_.fetch_add(got);
             compressed_pos_.store((long)gzoffset(gz_));
             eof = (size_t)got < CH;
@@ -329,32 +355,52 @@ private:
     std::mutex m_;
     std::condition_variable cv_data_, cv_space_;
     std::deque<Block> q_;
+    std::vector<Block> spare_;                            // storage of consumed blocks, reused by the producer
     bool eof_ = false, failed_ = false, abort_ = false;
     long compressed_size_ = 0;
     std::atomic<long> compressed_pos_{0}, uncompressed_{0};
     std::atomic<double> inflate_s_{0.0};
 };
 
+// "D.DDDDDD" (what ANGSD's %f writes) at p, already known to be followed by a delimiter or the line end: the seven
+// digits as one integer, or -1 if the eight characters are anything else.  (double)v / 1e6 is the one correctly rounded
+// operation that parse_float performs for such a token, so the value is identical.
+inline long fixed6(const char* p)
+{
+    const unsigned d0 = (unsigned)(p[0] - '0'), d2 = (unsigned)(p[2] - '0'), d3 = (unsigned)(p[3] - '0'), d4 = (unsigned)(p[4] - '0'),
+                   d5 = (unsigned)(p[5] - '0'), d6 = (unsigned)(p[6] - '0'), d7 = (unsigned)(p[7] - '0');
+    if ((p[1] != '.') | (d0 > 9) | (d2 > 9) | (d3 > 9) | (d4 > 9) | (d5 > 9) | (d6 > 9) | (d7 > 9)) return -1;
+    return (long)(d0 * 1000000u + d2 * 100000u + d3 * 10000u + d4 * 1000u + d5 * 100u + d6 * 10u + d7);
+}
+
 // parse one Beagle data line [p, e) into out[0 .. 2n); returns false on a short line
 bool parse_line(const char* p, const char* e, int n_ind, float* out)
 {
-    auto next = [&](const char*& a, const char*& b) -> bool {
-        while (p < e && is_delim(*p)) ++p;
+    auto skip_delims = [&] { while (p < e && is_delim(*p)) ++p; };
+    auto skip_token = [&] { while (p < e && !is_delim(*p)) ++p; };
+    for (int k = 0; k < 3; ++k) {                         // site id (kept by the caller), allele1, allele2
+        skip_delims();
         if (p >= e) return false;
-        a = p;
-        while (p < e && !is_delim(*p)) ++p;
-        b = p;
-        return true;
-    };
-    const char *a, *b;
-    if (!next(a, b)) return false;                        // site id (kept by the caller)
-    if (!next(a, b) || !next(a, b)) return false;         // allele1, allele2
+        skip_token();
+    }
     for (int i = 0; i < n_ind; ++i) {
-        if (!next(a, b)) return false;
-        out[2 * i] = parse_float(a, b);
-        if (!next(a, b)) return false;
-        out[2 * i + 1] = parse_float(a, b);
-        if (!next(a, b)) return false;                    // third GL: dropped (reader_cy.pyx:62-63)
+#pragma GCC unroll 3
+        for (int g = 0; g < 3; ++g) {                     // the third GL is dropped (reader_cy.pyx:62-63)
+            if (p < e && is_delim(*p)) { ++p; if (p < e && is_delim(*p)) skip_delims(); }
+            if (p >= e) return false;
+            const long room = e - p;
+            if (room >= 8 && (room == 8 || is_delim(p[8]))) {     // an eight-character token: the fixed-point fast path
+                const long v = fixed6(p);
+                if (v >= 0) {
+                    if (g < 2) out[2 * i + g] = (float)((double)v / 1e6);
+                    p += 8;
+                    continue;
+                }
+            }
+            const char* a = p;
+            skip_token();
+            if (g < 2) out[2 * i + g] = parse_float(a, p);
+        }
     }
     return true;
 }
@@ -366,6 +412,14 @@ bool parse_ad_line(const char* p, const char* e, int ncol, T* out, bool* negativ
     for (int c = 0; c < ncol; ++c) {
         while (p < e && is_delim(*p)) ++p;
         if (p >= e) return false;
+        {   // one- and two-digit counts (nearly every token of a low-coverage file) without the general loop
+            const unsigned d0 = (unsigned)(p[0] - '0');
+            if (d0 <= 9) {
+                if (p + 1 == e || is_delim(p[1])) { out[c] = (T)d0; p += 1; continue; }
+                const unsigned d1 = (unsigned)(p[1] - '0');
+                if (d1 <= 9 && (p + 2 == e || is_delim(p[2]))) { out[c] = (T)(d0 * 10 + d1); p += 2; continue; }
+            }
+        }
         bool neg = false;
         if (*p == '-') { neg = true; ++p; } else if (*p == '+') ++p;
         long v = 0;
@@ -405,7 +459,7 @@ bool index_block(Stream* S)
 {
     S->lines.clear();
     S->line_pos = 0;
-    const char* p = S->cur.data.data();
+    const char* p = S->cur.data();
     const char* e = p + S->cur.end;
     if (!S->is_ad && !S->header_done) {
         const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
@@ -563,6 +617,18 @@ int64_t wgs_beagle_stream_next(wgs_beagle_stream* s, float* out, int64_t max_row
     return stream_next<float>(S, out, max_rows, 2 * n, [n](const char* p, const char* e, float* o) { return parse_line(p, e, n, o); });
 }
 int64_t wgs_beagle_stream_rows_seen(const wgs_beagle_stream* s) { return ((const Stream*)s)->rows_seen; }
+// all site names seen so far, each followed by '\n', into out[0 .. cap); returns the bytes needed (call with out = NULL
+// first).  One call instead of one per site: 20 M names through a per-name FFI call take longer than parsing them.
+int64_t wgs_beagle_stream_sites_joined(const wgs_beagle_stream* s, char* out, int64_t cap)
+{
+    const Stream* S = (const Stream*)s;
+    int64_t need = 0;
+    for (const std::string& t : S->sites) need += (int64_t)t.size() + 1;
+    if (!out || cap < need) return need;
+    char* w = out;
+    for (const std::string& t : S->sites) { memcpy(w, t.data(), t.size()); w += t.size(); *w++ = '\n'; }
+    return need;
+}
 const char* wgs_beagle_stream_site(const wgs_beagle_stream* s, int64_t row) { return ((const Stream*)s)->sites[(size_t)row].c_str(); }
 // estimate of the total number of data rows from what has been read so far (exact once the stream is exhausted):
 // compressed size x the compression ratio and bytes per row seen so far

@@ -33,6 +33,16 @@ def _stats(L, h, fn, wall, rows, kind):
                             uncompressed_mb_per_s=u.value / 1e6 / max(wall, 1e-9), bgzf=bool(L.wgs_stream_is_bgzf(h)))
 
 
+def _site_names(L, h):
+    """Names of all rows the stream has seen, through ONE call (a call per name costs more than parsing the row)."""
+    need = L.wgs_beagle_stream_sites_joined(h, None, 0)
+    if need <= 0:
+        return []
+    buf = ctypes.create_string_buffer(need)
+    L.wgs_beagle_stream_sites_joined(h, buf, need)
+    return buf.raw[:need - 1].decode().split("\n")
+
+
 def count_rows(beagle, threads=0):
     """(M, sample_names, site_names) without converting a single number (one inflate pass): what a site-sharded
     rank needs before it can tell which rows are its own."""
@@ -47,7 +57,7 @@ def count_rows(beagle, threads=0):
             raise IOError(L.wgs_beagle_last_error().decode())
         m = L.wgs_beagle_stream_rows_seen(h)
         samples = [L.wgs_beagle_stream_sample(h, i).decode() for i in range(n)]
-        sites = [L.wgs_beagle_stream_site(h, s).decode() for s in range(m)]
+        sites = _site_names(L, h)
     finally:
         L.wgs_beagle_stream_close(h)
     return m, samples, sites
@@ -95,7 +105,7 @@ def readBeagle(beagle, threads=0, rows=None, on_block=None):
             m += got
         total = L.wgs_beagle_stream_rows_seen(h)
         samples = [L.wgs_beagle_stream_sample(h, i).decode() for i in range(n)]
-        sites = [L.wgs_beagle_stream_site(h, s).decode() for s in range(total)]
+        sites = _site_names(L, h)
         _stats(L, h, L.wgs_beagle_stream_stats, time.perf_counter() - t0, total, "beagle")
     finally:
         L.wgs_beagle_stream_close(h)
