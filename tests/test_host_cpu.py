@@ -357,3 +357,35 @@ def test_bgzf_input_reads_like_plain_gzip(tmp_path):
     (tmp_path / "cut.beagle.gz").write_bytes(z[: len(z) // 2])
     with pytest.raises(Exception):
         reader.readBeagle(str(tmp_path / "cut.beagle.gz"), 4)
+
+
+def test_reader_tokens_equal_float_of_atof(tmp_path):
+    """Every token form around the fixed-point fast path converts to (float)atof(token): random D.DDDDDD values
+    (the path itself), eight-character tokens that are NOT of that form, and longer / shorter / signed / exponent forms."""
+    import gzip
+    from wgsassign_b200 import reader
+    rng = np.random.default_rng(11)
+    toks = ["%.6f" % v for v in rng.random(4000)] + ["%.6f" % v for v in (0.0, 1.0, 0.333333, 0.666667, 0.999999, 0.000001, 9.999999)]
+    toks += ["1.00e-05", "-0.12345", "12.34567", "+1.23456", "1234567.", ".1234567", "1e-00005", "0.12345e", "00000001", "0.5", "1", "0",
+             "0.1234567", "0.12345678901234567", "3.0e-1", "1E-3", "-0.000000", "0.0000001", "123456.5", "1.0000000"]
+    n = 3
+    per_row = 2 * n                                                  # tokens that are kept per row (the third of each triple is dropped)
+    while len(toks) % per_row:
+        toks.append("0.250000")
+    rows = []
+    for r in range(len(toks) // per_row):
+        t = toks[r * per_row:(r + 1) * per_row]
+        cells = []
+        for i in range(n):
+            cells += [t[2 * i], t[2 * i + 1], "0.111111"]
+        rows.append("s_%d\t0\t1\t%s\n" % (r, "\t".join(cells)))
+    header = "marker\tallele1\tallele2" + "".join("\ti%d\ti%d\ti%d" % (i, i, i) for i in range(n)) + "\n"
+    path = tmp_path / "tok.beagle.gz"
+    path.write_bytes(gzip.compress((header + "".join(rows)).encode(), 1))
+    L, _, _ = reader.readBeagle(str(path), 2)
+    import ctypes, ctypes.util
+    libc = ctypes.CDLL(ctypes.util.find_library("c"))
+    libc.atof.restype = ctypes.c_double
+    want = np.array([np.float32(libc.atof(t.encode())) for t in toks], np.float32).reshape(-1, per_row)
+    assert L.shape == want.shape
+    assert np.array_equal(L.view(np.uint32), want.view(np.uint32))
