@@ -1223,8 +1223,8 @@ struct LooLaunch { int block, rows_per_pass, passes, grid; bool big; size_t smem
 
 // Launch geometry of the leave-one-out EM step kernels (four problems per thread).  packed = the
 // pre-packed pair-polynomial kernel (loo_em_step5), else the in-kernel packing quad kernel (loo_em_step4).
-// The packed kernel runs 2 blocks of 256 threads per SM at 112 registers (no spills): 12 % faster than 3 blocks at
-// the 80 registers that fit then (spills around the loop); populations of > 1024 use one block of 512.
+// The packed kernel runs one block of 512 threads per SM (116 registers, no spills, ring of up to 190 KB) unless two
+// blocks of 256 idle fewer threads; populations of > 1024 individuals always take one block of 512.
 int loo_cfg(wgs_ctx* ctx, int n, bool packed, LooLaunch* out)
 {
     LooLaunch best{0, 0, 1, 0, false, 0, packed, 0, 3};

@@ -2112,7 +2112,7 @@ __device__ __forceinline__ void loo5_pair_lo(f32x2 P0, f32x2 P1, f32x2 P2, f32x2
 // every other warp then waited for it at "full": 23 % of all stall samples.)
 constexpr int kLoo5MaxStages = 6;
 // Geometry: <512, 1> - one block of 16 warps per SM at 116 registers, ring of up to 190 KB - is the default; <256, 2>
-// (two blocks of 8 warps at 124 registers) runs 3..7 % slower and is kept for option loo_block.  Measured and dropped in
+// (two blocks of 8 warps, the same 116 registers) runs 3..7 % slower and is kept for option loo_block.  Measured and dropped in
 // round 2, each on the same box as its control (0.554 ms per launch at 1M x 50 for <256, 2>): three blocks of 256 at 80
 // registers with a ring small enough for three 0.670 ms; two blocks of 320 at 96 registers 0.620 ms; two problems
 // per pass over the shared-memory row (half the coefficient registers) 1.1 ms.  The 97-instruction cell loop is the same
