@@ -248,6 +248,11 @@ int64_t     wgs_beagle_stream_sites_joined(const wgs_beagle_stream *s, char *out
 int64_t     wgs_beagle_stream_estimate_rows(const wgs_beagle_stream *s);                   /* total rows, from the bytes read so far */
 /* 1 when a Beagle / allele-depth stream reads a BGZF file (bgzip, what ANGSD writes: independent members of <= 64 KB
  * of text, inflated by several threads at once), 0 for a plain gzip stream (one inflate thread). */
+/* The part-th of `parts` equal byte ranges of a BGZF Beagle file: the rows that START inside it (every row of the file
+ * belongs to exactly one part; the parts in order are the file).  Processes reading different parts inflate disjoint
+ * shares of the file - what a site-sharded job wants instead of every rank inflating all of it.  Row numbers count from
+ * the part's first row; the sample names are those of the file's header.  An error for a plain gzip file. */
+int32_t     wgs_beagle_stream_open_part(const char *path, int32_t threads, int32_t part, int32_t parts, wgs_beagle_stream **out);
 int32_t     wgs_stream_is_bgzf(const void *stream);
 int32_t     wgs_beagle_stream_stats(const wgs_beagle_stream *s, double *inflate_s, double *parse_s,
                                     int64_t *compressed_bytes, int64_t *uncompressed_bytes);

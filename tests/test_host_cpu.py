@@ -207,7 +207,7 @@ def test_cli_surface():
               "get_reference_z_score": False, "ind_ad_file": None, "allele_count_threshold": None,
               "single_read_threshold": False, "ind_start": None, "ind_end": None, "pop_like": None, "pop_like_IDs": None,
               "get_em_mix": False, "get_mcmc_mix": False, "mixture_iter": 200}
-    extra = {"em_mix_logsumexp": False}          # additions of this implementation: optional, default = the reference's behaviour
+    extra = {"em_mix_logsumexp": False, "shard_by_bytes": False}          # additions of this implementation: optional, default = the reference's behaviour
     assert flags == {**expect, **extra}
     ref_cli = "/root/reference/WGSassign/WGSassign.py"
     if os.path.exists(ref_cli):
@@ -389,3 +389,136 @@ def test_reader_tokens_equal_float_of_atof(tmp_path):
     want = np.array([np.float32(libc.atof(t.encode())) for t in toks], np.float32).reshape(-1, per_row)
     assert L.shape == want.shape
     assert np.array_equal(L.view(np.uint32), want.view(np.uint32))
+
+
+GLOO_PARTS_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, %r)
+import torch.distributed as td
+from wgsassign_b200 import dist, reader
+td.init_process_group("gloo")
+r, w = td.get_rank(), td.get_world_size()
+path = %r
+L, samples, sites = reader.readBeagle(path, 2, part=(r, w))
+M, lo, ranges = dist.row_counts_to_ranges(L.shape[0])
+dist.enable(M, lo, ranges=ranges)
+assert ranges[r] == (lo, lo + L.shape[0]) and dist.rank_ranges() == ranges
+full = dist.gather_rows(L)                       # unequal row blocks, concatenated in rank order
+whole, wsamples, wsites = reader.readBeagle(path, 2)
+assert M == whole.shape[0] and np.array_equal(full, whole) and list(samples) == list(wsamples)
+assert list(sites) == list(wsites)[lo:lo + L.shape[0]]
+try:
+    dist.enable(M, lo + 1, ranges=ranges)
+    raise SystemExit("inconsistent ranges accepted")
+except ValueError:
+    pass
+td.destroy_process_group()
+print("ok", r, L.shape[0])
+"""
+
+
+def test_byte_range_parts_world3_gloo(tmp_path):
+    """Three processes read the three byte ranges of one BGZF file: their row counts give the shard geometry
+    (dist.row_counts_to_ranges / enable(ranges=...)), and the gathered rows are the whole file."""
+    from wgsassign_b200 import synth
+    n, m = 5, 4000
+    rng = np.random.default_rng(9)
+    vals = np.round(rng.random((m, 3 * n)), 6)
+    header = "marker\tallele1\tallele2" + "".join("\ti%d\ti%d\ti%d" % (i, i, i) for i in range(n)) + "\n"
+    text = (header + "".join("c_%d\t0\t1\t%s\n" % (s, "\t".join("%.6f" % v for v in vals[s])) for s in range(m))).encode()
+    path = tmp_path / "p.beagle.gz"
+    path.write_bytes(synth.bgzf_compress(text, block=20000))
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_PARTS_WORKER % (ROOT, str(path)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == 3
+
+
+def test_byte_range_parts_cover_the_file(tmp_path):
+    """reader.readBeagle(part=(p, P)): for every P the parts are disjoint, ordered and cover the file - rows longer than a
+    BGZF member, members far smaller than a row, more parts than members, a file without the end-of-file member."""
+    import gzip
+    from wgsassign_b200 import reader, synth
+    rng = np.random.default_rng(3)
+    for n, m, block, strip_eof in [(7, 3000, 65280, False), (3, 50, 65280, True), (2000, 12, 65280, False), (5, 1500, 777, True), (1, 5, 65280, False)]:
+        vals = np.round(rng.random((m, 3 * n)), 6)
+        header = "marker\tallele1\tallele2" + "".join("\ti%d\ti%d\ti%d" % (i, i, i) for i in range(n)) + "\n"
+        text = (header + "".join("c_%d\t0\t1\t%s\n" % (s, "\t".join("%.6f" % v for v in vals[s])) for s in range(m))).encode()
+        z = synth.bgzf_compress(text, block=block)
+        path = tmp_path / ("x_%d_%d.beagle.gz" % (n, block))
+        path.write_bytes(z[:-28] if strip_eof else z)
+        assert reader.is_bgzf(str(path))
+        A = reader.readBeagle(str(path), 3)
+        for P in (2, 3, 8, 64):
+            parts = [reader.readBeagle(str(path), 2, part=(q, P)) for q in range(P)]
+            assert np.array_equal(np.concatenate([x[0] for x in parts], axis=0), A[0]), (n, m, block, P)
+            assert sum([list(x[2]) for x in parts], []) == list(A[2])
+            assert all(list(x[1]) == list(A[1]) for x in parts)
+    plain = tmp_path / "g.beagle.gz"
+    plain.write_bytes(gzip.compress(b"marker\ta\tb\ti\ti\ti\nc\t0\t1\t0.1\t0.2\t0.7\n"))
+    assert not reader.is_bgzf(str(plain))
+    with pytest.raises(IOError):
+        reader.readBeagle(str(plain), 2, part=(0, 2))
+
+
+GLOO_CLI_PARTS_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, %r)
+import torch.distributed as td
+from wgsassign_b200 import WGSassign, dist, reader, session
+
+class FakeCtx:                                   # stands in for the device context: records what the host layer tells it
+    def set_shard(self, M_total, offset, fn): self.shard = (M_total, offset)
+    def set_rank(self, rank, world): self.rank = (rank, world)
+
+fake = FakeCtx()
+def stream_context(beagle, pop_of_ind=None, K=0, threads=0, rows=None, part=None):
+    assert rows is None and part == (td.get_rank(), td.get_world_size())
+    L, samples, sites = reader.readBeagle(beagle, threads, part=part)
+    return fake, L, samples, sites
+session.stream_context = stream_context
+
+path = %r
+args = WGSassign.parser.parse_args(["--beagle", path, "--shard_by_bytes", "--get_pop_like", "--threads", "2"])
+run = WGSassign._Run(args)                        # initialises torch.distributed (gloo: no CUDA here)
+run.parse_inputs()
+r, w = td.get_rank(), td.get_world_size()
+whole, _, wsites = reader.readBeagle(path, 2)
+lo, hi = run._ranges[r]
+assert run.M_total == whole.shape[0] and hi - lo == run.L.shape[0]
+assert np.array_equal(run.L, whole[lo:hi]) and list(run.site_names) == list(wsites)[lo:hi]
+assert fake.shard == (run.M_total, lo) and fake.rank == (r, w)
+assert run._range(run.M_total) == (lo, hi)
+X = np.arange(run.M_total * 2, dtype=np.float32).reshape(run.M_total, 2)      # a per-site input read whole (e.g. --pop_af_file)
+assert np.array_equal(run.shard(X), X[lo:hi])
+assert np.array_equal(run.full(run.shard(X)), X)
+td.destroy_process_group()
+print("ok", r, hi - lo)
+"""
+
+
+def test_cli_shard_by_bytes_host_logic_gloo(tmp_path):
+    """--shard_by_bytes under torchrun (gloo, two processes): parse_inputs reads each rank's byte range, derives the
+    shard geometry from the row counts, attaches the context with it, and shard() / full() follow the unequal ranges."""
+    from wgsassign_b200 import synth
+    n, m = 4, 3000
+    rng = np.random.default_rng(13)
+    vals = np.round(rng.random((m, 3 * n)), 6)
+    header = "marker\tallele1\tallele2" + "".join("\ti%d\ti%d\ti%d" % (i, i, i) for i in range(n)) + "\n"
+    text = (header + "".join("c_%d\t0\t1\t%s\n" % (s, "\t".join("%.6f" % v for v in vals[s])) for s in range(m))).encode()
+    path = tmp_path / "p.beagle.gz"
+    path.write_bytes(synth.bgzf_compress(text, block=30000))
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_CLI_PARTS_WORKER % (ROOT, str(path)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", CUDA_VISIBLE_DEVICES="")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29615", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == 2

@@ -55,6 +55,10 @@ def build_parser():
     p.add_argument("--em_mix_logsumexp", action="store_true",
                    help="(not in the reference) subtract each individual's largest log likelihood before exponentiating in --get_em_mix: "
                         "finite mixture proportions for genome-scale log likelihoods, identical results where the reference's are finite")
+    p.add_argument("--shard_by_bytes", action="store_true",
+                   help="(not in the reference; under torchrun only) when the Beagle file is BGZF (bgzip, as ANGSD writes it) every rank "
+                        "reads its own byte range of the file instead of inflating all of it: the ranks then hold unequal numbers of sites; "
+                        "results do not depend on how the sites are split")
     return p
 
 
@@ -108,6 +112,9 @@ class _Run:
     def _range(self, M):
         """This rank's contiguous site range of an M-site input (and the shard geometry for the library)."""
         import torch.distributed as td
+        if getattr(self, "_ranges", None) is not None:             # byte-range parts: the ranks' row ranges are what they read
+            assert M == self.M_total, "a per-site input has %d rows, the Beagle file %d" % (M, self.M_total)
+            return self._ranges[td.get_rank()]
         lo, hi = self.dist.shard_range(M, td.get_rank(), td.get_world_size())
         if self.M_total is None:
             self.M_total = M
@@ -153,14 +160,27 @@ class _Run:
             if a.loo_downsampled_beagle is None:
                 # streamed: a background thread inflates, a thread pool parses straight into pinned memory, every finished
                 # block is queued for upload while the next is parsed; a site-sharded rank converts only its own rows
-                rows = None
+                rows = part = None
                 if self._world() > 1:
-                    m_all, _, _ = reader.count_rows(a.beagle, a.threads)      # one inflate pass, nothing converted
-                    rows = self._range(m_all)
+                    import torch.distributed as td
+                    if a.shard_by_bytes and reader.is_bgzf(a.beagle):
+                        part = (td.get_rank(), td.get_world_size())          # every rank inflates only its share of the file
+                    else:
+                        if a.shard_by_bytes:
+                            self.say("--shard_by_bytes: not a BGZF file, every rank reads through the whole file.")
+                        m_all, _, _ = reader.count_rows(a.beagle, a.threads)      # one inflate pass, nothing converted
+                        rows = self._range(m_all)
                 pop_of, K = self._first_layout()
-                _, self.L, self.sample_names, self.site_names = session.stream_context(a.beagle, pop_of, K, a.threads, rows=rows)
+                ctx, self.L, self.sample_names, self.site_names = session.stream_context(a.beagle, pop_of, K, a.threads, rows=rows, part=part)
                 self._L_sharded = True
                 m, n = len(self.site_names), self.L.shape[1] // 2
+                if part is not None:
+                    # the ranks hold consecutive, unequal pieces: their row counts give the geometry (the site names of this
+                    # rank are its own rows only)
+                    self.M_total, lo, self._ranges = self.dist.row_counts_to_ranges(self.L.shape[0])
+                    self.dist.enable(self.M_total, lo, device=self._device, ranges=self._ranges)
+                    self.dist.attach(ctx)
+                    m = self.M_total
             else:
                 self.L, self.sample_names, self.site_names = reader.readBeagle(a.beagle, a.threads)
                 m, n = self.L.shape[0], self.L.shape[1] // 2

@@ -80,6 +80,7 @@ SYMBOLS = {
     "wgs_beagle_stream_sites_joined": (_i64, [_vp, _vp, _i64]),
     "wgs_beagle_stream_estimate_rows": (_i64, [_vp]),
     "wgs_stream_is_bgzf": (_i32, [_vp]),
+    "wgs_beagle_stream_open_part": (_i32, [ctypes.c_char_p, _i32, _i32, _i32, ctypes.POINTER(_vp)]),
     "wgs_beagle_stream_stats": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "wgs_beagle_stream_close": (None, [_vp]),
     "wgs_ad_stream_open": (_i32, [ctypes.c_char_p, _i32, ctypes.POINTER(_vp)]),

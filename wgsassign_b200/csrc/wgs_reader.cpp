@@ -174,17 +174,37 @@ inline long bgzf_member_size(const unsigned char* p, size_t avail)
 
 class GzLines {
 public:
-    // inflate_threads: workers of the BGZF path (a plain gzip stream is inflated by the one background thread)
-    bool open(const char* path, std::string* err, int inflate_threads = 1) {
+    // inflate_threads: workers of the BGZF path (a plain gzip stream is inflated by the one background thread).
+    // part / parts (BGZF only): this reader yields the LINES THAT START in the part-th of `parts` equal byte ranges of
+    // the compressed file - more exactly, with t0 / t1 the text positions where the members that start inside the range
+    // begin / end, the lines whose first character lies in (t0, t1] (part 0: [0, t1]).  Every line of the file belongs to
+    // exactly one part, the parts' lines concatenated in order are the file, and no part inflates more than its own
+    // members plus the end of its last line.
+    bool open(const char* path, std::string* err, int inflate_threads = 1, int part = 0, int parts = 1) {
         FILE* f = fopen(path, "rb");
         if (!f) { *err = std::string("cannot open ") + path; return false; }
         unsigned char head[64];
         const size_t got = fread(head, 1, sizeof head, f);
         fseek(f, 0, SEEK_END); compressed_size_ = ftell(f);
-        if (bgzf_member_size(head, got) > 0) {
-            fseek(f, 0, SEEK_SET);
+        const bool bgzf = bgzf_member_size(head, got) > 0;
+        if (parts > 1 && !bgzf) {
+            fclose(f);
+            *err = std::string("byte-range parts need a BGZF (bgzip) file: ") + path;
+            return false;
+        }
+        if (bgzf) {
             raw_ = f;
             nth_ = std::max(1, std::min(inflate_threads, 32));
+            part_ = part; parts_ = std::max(parts, 1);
+            if (parts_ > 1) {
+                const long size = compressed_size_;
+                const long lo = (long)((__int128)size * part / parts_);
+                hi_ = (long)((__int128)size * (part + 1) / parts_);
+                start_ = part == 0 ? 0 : find_member_start(f, lo, size);
+                if (start_ < 0 || start_ >= hi_) { start_ = hi_; }            // no member starts inside the range: no lines
+                compressed_size_ = hi_ - start_;
+            }
+            fseek(f, start_, SEEK_SET);
         } else {
             fclose(f);
             gz_ = gzopen(path, "rb");
@@ -253,6 +273,8 @@ private:
     static bool inflate_member(const unsigned char* p, unsigned csize, unsigned isize, char* dst) {
         const size_t xlen = (size_t)p[10] | ((size_t)p[11] << 8), hdr = 12 + xlen;
         if ((size_t)csize < hdr + 8) return false;
+        char nothing = 0;
+        if (!dst) dst = &nothing;                          // an empty member into an empty block: zlib refuses a null next_out
         z_stream zs;
         memset(&zs, 0, sizeof zs);
         if (inflateInit2(&zs, -15) != Z_OK) return false;
@@ -268,15 +290,72 @@ private:
         const unsigned long want = (unsigned long)t[0] | ((unsigned long)t[1] << 8) | ((unsigned long)t[2] << 16) | ((unsigned long)t[3] << 24);
         return crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const unsigned char*>(dst), isize) == want;
     }
+    // first member start at or after `from`: a header whose own size leads to another valid header (or to the end of the
+    // file), twice in a row - four magic bytes plus the BC subfield plus two chained sizes do not occur by accident
+    static long find_member_start(FILE* f, long from, long size) {
+        if (from >= size) return -1;
+        std::vector<unsigned char> w((size_t)std::min<long>(size - from, 320 * 1024));
+        fseek(f, from, SEEK_SET);
+        const size_t got = fread(w.data(), 1, w.size(), f);
+        for (size_t o = 0; o + 18 <= got && o <= 65536 + 18; ++o) {
+            if (w[o] != 0x1f || w[o + 1] != 0x8b || w[o + 2] != 8 || !(w[o + 3] & 4)) continue;
+            size_t q = o;
+            int chained = 0;
+            bool ok = true;
+            while (chained < 3) {
+                const long sz = bgzf_member_size(w.data() + q, got - q);
+                if (sz <= 0) { ok = (long)(from + q) == size && chained > 0; break; }   // clean end of file after >= 1 member
+                q += (size_t)sz;
+                ++chained;
+                if ((long)(from + q) == size) break;
+                if (q + 18 > got) break;                                          // window exhausted: accept what chained
+            }
+            if (ok && chained > 0) return from + (long)o;
+        }
+        return -1;
+    }
+    // text of the members from the current file position up to and including the first line end (or the end of file)
+    bool read_tail_line(std::string* out) {
+        std::vector<unsigned char> m(1 << 17);
+        std::vector<char> text(1 << 16);
+        for (;;) {
+            const size_t got = fread(m.data(), 1, 18, raw_);
+            if (got == 0) return true;                                            // end of file
+            if (got < 18) return false;
+            const size_t xlen = (size_t)m[10] | ((size_t)m[11] << 8);
+            if (12 + xlen > m.size()) return false;
+            if (12 + xlen > 18 && fread(m.data() + 18, 1, 12 + xlen - 18, raw_) != 12 + xlen - 18) return false;
+            const long sz = bgzf_member_size(m.data(), 12 + xlen);
+            if (sz <= 0 || (size_t)sz > m.size() || (size_t)sz < 12 + xlen + 8) return false;
+            const size_t had = std::max<size_t>(18, 12 + xlen);
+            if (fread(m.data() + had, 1, (size_t)sz - had, raw_) != (size_t)sz - had) return false;
+            const unsigned char* t = m.data() + sz - 4;
+            const unsigned isize = (unsigned)t[0] | ((unsigned)t[1] << 8) | ((unsigned)t[2] << 16) | ((unsigned)t[3] << 24);
+            if (isize > text.size()) text.resize(isize);
+            if (!inflate_member(m.data(), (unsigned)sz, isize, text.data())) return false;
+            const char* nl = (const char*)memchr(text.data(), '\n', isize);
+            out->append(text.data(), nl ? (size_t)(nl - text.data()) + 1 : isize);
+            if (nl) return true;
+        }
+    }
     void bgzf_loop() {
         const size_t RAW = (size_t)8 << 20, TEXT = (size_t)32 << 20;
         std::vector<unsigned char> raw(RAW + (1 << 17));
         size_t have = 0, pos = 0;
+        long raw0 = start_;                                         // file offset of raw[0]
         long consumed = 0;
         std::string carry;
         bool file_done = false;
+        const bool ranged = parts_ > 1;
+        bool skipping = ranged && part_ > 0;                        // a part other than the first drops its text through the first line end
+        bool own_done = false;                                      // the next member starts outside this part's byte range
+        if (ranged && start_ >= hi_) {                              // no member of its own: no lines
+            { std::lock_guard<std::mutex> lk(m_); eof_ = true; }
+            cv_data_.notify_all();
+            return;
+        }
         for (;;) {
-            if (pos > 0) { memmove(raw.data(), raw.data() + pos, have - pos); have -= pos; pos = 0; }
+            if (pos > 0) { memmove(raw.data(), raw.data() + pos, have - pos); have -= pos; raw0 += (long)pos; pos = 0; }
             if (!file_done && have < RAW) {
                 const size_t got = fread(raw.data() + have, 1, RAW - have, raw_);
                 if (got == 0) file_done = true;
@@ -285,6 +364,7 @@ private:
             std::vector<Member> mem;
             size_t text = 0;
             while (pos < have && text < TEXT) {
+                if (ranged && raw0 + (long)pos >= hi_) { own_done = true; break; }
                 const long sz = bgzf_member_size(raw.data() + pos, have - pos);
                 if (sz < 0 || (sz == 0 && file_done)) { fail_now(); return; }      // not BGZF after all, or a truncated member
                 if (sz == 0 || pos + (size_t)sz > have) {
@@ -297,7 +377,8 @@ private:
                 pos += (size_t)sz;
                 text += isize;
             }
-            const bool last = file_done && pos == have;
+            const bool at_eof = file_done && pos == have;
+            const bool last = at_eof || own_done;
             if (mem.empty() && !last) continue;                                    // (a member is at most 64 KB: the next read completes it)
             Block b = fresh();
             b.assign(carry);
@@ -320,6 +401,28 @@ private:
             uncompressed_.fetch_add((long)text);
             for (const Member& m : mem) consumed += m.csize;
             compressed_pos_.store(consumed);
+            if (skipping) {                                                        // (carry is empty while skipping)
+                const char* nl = (const char*)memchr(b.data(), '\n', b.size);
+                if (nl) {
+                    const size_t drop = (size_t)(nl - b.data()) + 1;
+                    memmove(b.data(), b.data() + drop, b.size - drop);
+                    b.size -= drop;
+                    skipping = false;
+                } else {
+                    b.size = 0;
+                }
+            }
+            if (last && own_done && !skipping) {
+                // the line in progress at the end of this part's text - or, if that text ends with a line end, the line
+                // that starts exactly there - is finished from the members of the next part
+                std::string tail;
+                fseek(raw_, raw0 + (long)pos, SEEK_SET);
+                if (!read_tail_line(&tail)) { fail_now(); return; }
+                b.reserve(b.size + tail.size());
+                memcpy(b.data() + b.size, tail.data(), tail.size());
+                b.size += tail.size();
+            }
+            if (last && skipping) b.size = 0;                                      // no line starts inside this part
             if (!push_text(b, carry, last)) return;
             if (last) break;
         }
@@ -351,6 +454,8 @@ private:
     gzFile gz_ = nullptr;
     FILE* raw_ = nullptr;                                 // BGZF: the compressed file itself
     int nth_ = 1;
+    int part_ = 0, parts_ = 1;                            // BGZF byte-range parts
+    long start_ = 0, hi_ = 0;                             // first own member / end of the byte range
     std::thread th_;
     std::mutex m_;
     std::condition_variable cv_data_, cv_space_;
@@ -510,18 +615,27 @@ bool ensure_lines(Stream* S)
     return true;
 }
 
-Stream* open_stream(const char* path, int threads, bool is_ad)
+Stream* open_stream(const char* path, int threads, bool is_ad, int part = 0, int parts = 1)
 {
     Stream* S = new Stream();
     S->is_ad = is_ad;
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (parts > 1 && part > 0 && !is_ad) {
+        // the header line belongs to part 0: read it from the start of the file (one member is inflated)
+        Stream* H = open_stream(path, 1, false);
+        if (!H) { delete S; return nullptr; }
+        S->samples = H->samples;
+        S->n_ind = H->n_ind;
+        S->header_done = true;
+        delete H;
+    }
     // BGZF input: three quarters of the threads inflate - with the fixed-point token path a core parses the text about
     // eight times faster than it inflates it (measured on the 16-core GPU host: 200 MB of Beagle text inflated in
     // 0.31 core-seconds x 4 threads, parsed in 0.01 s of wall time by 16)
-    if (!S->gz.open(path, &g_reader_error, std::max(2, threads * 3 / 4))) { delete S; return nullptr; }
+    if (!S->gz.open(path, &g_reader_error, std::max(2, threads * 3 / 4), part, parts)) { delete S; return nullptr; }
     S->pool = new Pool(std::min(threads, 64));
     g_reader_error.clear();
-    if (!ensure_lines(S) && !S->header_done) {
+    if (!ensure_lines(S) && (!S->header_done || !g_reader_error.empty())) {
         if (g_reader_error.empty()) g_reader_error = is_ad ? "empty allele-depth file" : "empty Beagle file";
         delete S;
         return nullptr;
@@ -598,6 +712,20 @@ int32_t wgs_beagle_stream_open(const char* path, int32_t threads, wgs_beagle_str
 {
     *out = nullptr;
     Stream* S = open_stream(path, threads, false);
+    if (!S) return 1;
+    S->ncol = 2 * S->n_ind;
+    *out = (wgs_beagle_stream*)S;
+    return 0;
+}
+// The part-th of `parts` byte ranges of a BGZF Beagle file (see GzLines::open): the rows that start inside it, in file
+// order; the parts of a file are disjoint, cover it and can be read by different processes at the same time, each
+// inflating only its own share.  Row numbers (wgs_beagle_stream_keep, rows_seen, site) count from the part's first row.
+// Fails for a plain gzip file (one deflate stream cannot be entered in the middle).
+int32_t wgs_beagle_stream_open_part(const char* path, int32_t threads, int32_t part, int32_t parts, wgs_beagle_stream** out)
+{
+    *out = nullptr;
+    if (parts < 1 || part < 0 || part >= parts) { g_reader_error = "part must lie in [0, parts)"; return 1; }
+    Stream* S = open_stream(path, threads, false, part, parts);
     if (!S) return 1;
     S->ncol = 2 * S->n_ind;
     *out = (wgs_beagle_stream*)S;

@@ -11,7 +11,7 @@ summed in rank order, so a result does not depend on reduction timing.
 """
 import numpy as np
 
-_cfg = {"enabled": False, "rank": 0, "world": 1, "M_total": None, "offset": 0, "device": None}
+_cfg = {"enabled": False, "rank": 0, "world": 1, "M_total": None, "offset": 0, "device": None, "ranges": None}
 
 
 def _parse_cpulist(text):
@@ -64,17 +64,49 @@ def shard_range(M, rank, world):
     return lo, hi
 
 
-def enable(M_total, offset, device=None):
-    """Declare that this process holds sites [offset, offset+M_local) of M_total."""
+def enable(M_total, offset, device=None, ranges=None):
+    """Declare that this process holds sites [offset, offset+M_local) of M_total.  ranges: the [lo, hi) of every rank
+    when they are not the equal split of shard_range (byte-range parts of a BGZF file hold unequal numbers of rows)."""
     import torch.distributed as td
     if not td.is_initialized():
         raise RuntimeError("torch.distributed is not initialised")
+    if ranges is not None:
+        ranges = [(int(a), int(b)) for a, b in ranges]
+        if len(ranges) != td.get_world_size() or ranges[0][0] != 0 or ranges[-1][1] != int(M_total) or \
+                any(ranges[i][1] != ranges[i + 1][0] for i in range(len(ranges) - 1)) or ranges[td.get_rank()][0] != int(offset):
+            raise ValueError("ranges must be contiguous, cover [0, M_total) and agree with offset")
     _cfg.update(enabled=True, rank=td.get_rank(), world=td.get_world_size(), M_total=int(M_total),
-                offset=int(offset), device=device)
+                offset=int(offset), device=device, ranges=ranges)
 
 
 def disable():
-    _cfg.update(enabled=False, rank=0, world=1, M_total=None, offset=0, device=None)
+    _cfg.update(enabled=False, rank=0, world=1, M_total=None, offset=0, device=None, ranges=None)
+
+
+def rank_ranges():
+    """[lo, hi) of every rank: the declared ranges, else the equal split."""
+    if _cfg["ranges"] is not None:
+        return list(_cfg["ranges"])
+    return [shard_range(_cfg["M_total"], r, _cfg["world"]) for r in range(_cfg["world"])]
+
+
+def row_counts_to_ranges(n_local):
+    """All-gather every rank's row count (ranks hold consecutive pieces of one file): -> (M_total, offset, ranges)."""
+    import torch
+    import torch.distributed as td
+    world, me = td.get_world_size(), td.get_rank()
+    t = torch.zeros(world, dtype=torch.int64)
+    t[me] = int(n_local)
+    dev = _cfg["device"]
+    if td.get_backend() == "nccl":
+        t = t.cuda() if dev is None else t.to(dev)
+    td.all_reduce(t)
+    counts = [int(x) for x in t.cpu().tolist()]
+    ranges, lo = [], 0
+    for c in counts:
+        ranges.append((lo, lo + c))
+        lo += c
+    return lo, ranges[me][0], ranges
 
 
 def enabled():
@@ -128,7 +160,7 @@ def gather_rows(arr):
     import torch
     import torch.distributed as td
     dev = _cfg["device"]
-    counts = [shard_range(_cfg["M_total"], r, _cfg["world"]) for r in range(_cfg["world"])]
+    counts = rank_ranges()
     out = []
     for r, (lo, hi) in enumerate(counts):
         shape = (hi - lo,) + tuple(arr.shape[1:])

@@ -63,16 +63,36 @@ def count_rows(beagle, threads=0):
     return m, samples, sites
 
 
-def readBeagle(beagle, threads=0, rows=None, on_block=None):
+def is_bgzf(path):
+    """True for a BGZF (bgzip) file - the container ANGSD writes: independent members that can be inflated in parallel
+    and entered in the middle (byte-range parts); False for a plain gzip stream or anything else."""
+    try:
+        with open(path, "rb") as fh:
+            h = fh.read(18)
+    except OSError:
+        return False
+    return len(h) >= 18 and h[:3] == b"\x1f\x8b\x08" and bool(h[3] & 4) and h[12:14] == b"BC"
+
+
+def readBeagle(beagle, threads=0, rows=None, on_block=None, part=None):
     """Returns ``(L float32 [M, 2N], sample_names list[str], site_names list[str])``.
 
     rows=(lo, hi): convert only that row range (L is then [hi-lo, 2N]; the names are still those of ALL sites).
     on_block(L, r0, r1): called after rows [r0, r1) of L have been written - the CLI queues their upload from it, so
-    the transfer of one block overlaps the parsing of the next."""
+    the transfer of one block overlaps the parsing of the next.
+    part=(p, P) (BGZF files only): read the p-th of P byte ranges of the file - the rows that start inside it; L and the
+    site names are then those rows only, and P processes reading the P parts inflate the file once between them
+    (with ``rows`` every process inflates all of it, twice: once to count).  The parts in order are the file."""
     L = _lib.lib()
     h = ctypes.c_void_p(0)
     t0 = time.perf_counter()
-    if L.wgs_beagle_stream_open(str(beagle).encode(), int(threads), ctypes.byref(h)) != 0:
+    if part is not None:
+        if rows is not None:
+            raise ValueError("rows and part are alternatives")
+        rc = L.wgs_beagle_stream_open_part(str(beagle).encode(), int(threads), int(part[0]), int(part[1]), ctypes.byref(h))
+    else:
+        rc = L.wgs_beagle_stream_open(str(beagle).encode(), int(threads), ctypes.byref(h))
+    if rc != 0:
         raise IOError(L.wgs_beagle_last_error().decode())
     try:
         n = L.wgs_beagle_stream_inds(h)

@@ -108,11 +108,14 @@ def context(L, pop_of_ind=None, K=0, async_upload=False):
     return ctx
 
 
-def stream_context(beagle, pop_of_ind=None, K=0, threads=0, rows=None):
+def stream_context(beagle, pop_of_ind=None, K=0, threads=0, rows=None, part=None):
     """Parse a Beagle file straight into a resident context: every finished row block is queued for upload while the
     next one is parsed (`readBeagle(on_block=...)` + `Context.upload_gl_begin/rows/end`).  Returns
     (ctx, L, sample_names, site_names); the context is registered for L, so the entry points that are later called
-    with this array find it resident.  pop_of_ind must already be known (the device layout is population-sorted)."""
+    with this array find it resident.  pop_of_ind must already be known (the device layout is population-sorted).
+    part=(p, P): this process reads the p-th byte range of a BGZF file (reader.readBeagle); the shard geometry is then
+    known only when every rank has counted its rows, so the CALLER declares it (dist.row_counts_to_ranges, dist.enable)
+    and attaches the context (dist.attach) afterwards."""
     from . import reader
     ctx = _state["ctx"]
     if ctx is None:
@@ -132,13 +135,14 @@ def stream_context(beagle, pop_of_ind=None, K=0, threads=0, rows=None):
                 if len(pop_of_ind) != n:
                     raise ValueError("Number of individuals in beagle and reference ID file do not match!")
                 ctx.set_pops(pop_of_ind, K)
-            dist.attach(ctx)
+            if part is None:
+                dist.attach(ctx)
             ctx.upload_gl_begin(arr.shape[0], n)
             state.update(begun=True, cap=arr.shape[0])
             if r0 > 0:
                 ctx.upload_gl_rows(arr, 0, r0)
         ctx.upload_gl_rows(arr, r0, r1)
-    L, samples, sites = reader.readBeagle(beagle, threads, rows=rows, on_block=on_block)
+    L, samples, sites = reader.readBeagle(beagle, threads, rows=rows, on_block=on_block, part=part)
     if state["begun"]:
         ctx.upload_gl_end(L.shape[0])
         ctx._pending_L = L
